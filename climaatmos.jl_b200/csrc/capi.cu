@@ -1,0 +1,656 @@
+// capi.cu — C-ABI of libb200dycore.so (declared in include/b200_dycore.h).
+// Context creation (geometry/topology ingestion), hook entry points and the native ARS343 stepper.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_dycore.h"
+#include "kernels_dss.cuh"
+#include "kernels_explicit.cuh"
+#include "kernels_implicit.cuh"
+
+using namespace b200;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- NCCL through dlopen (the torch-bundled libnccl.so.2 is already resident in the host process)
+typedef struct ncclComm* ncclComm_t;
+struct Id128 { char b[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, /* ncclUniqueId by value */ Id128, int) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail("dlopen(libnccl.so.2) failed: multi-GPU DSS halo needs NCCL");
+#define SYM(f, name)                                                   \
+  *(void**)(&g_nccl.f) = dlsym(g_nccl.lib, name);                      \
+  if (!g_nccl.f) return fail(std::string("dlsym failed: ") + name);
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+#define NK(x)                                                                                     \
+  do {                                                                                            \
+    int r_ = (x);                                                                                 \
+    if (r_ != 0) return fail(std::string(#x) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+  } while (0)
+
+struct b200_ctx {
+  b200_dims dims;
+  b200_params prm;
+  int ft = 4;
+  void* d_hgeo = nullptr;
+  void* d_vlev = nullptr;
+  int* d_off = nullptr;
+  int* d_mem = nullptr;
+  int nnodes = 0;
+  std::vector<int32_t> h_off, h_mem;
+  void* d_jac = nullptr;
+  // native stepper storage (allocated lazily)
+  void *Uc[2] = {nullptr, nullptr}, *Uf[2] = {nullptr, nullptr};
+  void *Tec[4] = {}, *Tef[4] = {}, *Tic[4] = {}, *Tif[4] = {};
+  void* H = nullptr;
+  void *Rc = nullptr, *Rf = nullptr, *dc = nullptr, *df = nullptr;
+  // halo
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  std::vector<int32_t> nbr, send_off, recv_off;
+  int* d_send_elems = nullptr;
+  int n_send = 0;
+  void *sendbuf = nullptr, *ghostbuf = nullptr;  // sized for the largest DSS call
+  size_t halo_cap = 0;
+  int64_t launches = 0;
+  size_t nc() const { return (size_t)dims.nh * 4 * 16 * dims.nv; }
+  size_t nf() const { return (size_t)dims.nh * 16 * (dims.nv + 1); }
+};
+
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b200_nccl_unique_id(void* out128) {
+  if (nccl_load()) return -1;
+  NK(g_nccl.GetUniqueId(out128));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// topology → CSR of unique perimeter nodes (must match climaatmos.jl_b200/grid.py:dss_node_csr)
+static void face_node(int f, int q, int& i, int& j) {
+  switch (f) {
+    case 0: i = q; j = 0; break;
+    case 1: i = 3; j = q; break;
+    case 2: i = 3 - q; j = 3; break;
+    default: i = 0; j = 3 - q; break;
+  }
+}
+static void vert_node(int v, int& i, int& j) {
+  static const int vi[4] = {0, 3, 3, 0}, vj[4] = {0, 0, 3, 3};
+  i = vi[v]; j = vj[v];
+}
+
+static void build_csr(const b200_topology* T, std::vector<int32_t>& off, std::vector<int32_t>& mem) {
+  off.clear(); mem.clear();
+  off.push_back(0);
+  for (int v = 0; v < T->n_verts; ++v) {
+    for (int q = T->local_vertex_offset[v]; q < T->local_vertex_offset[v + 1]; ++q) {
+      int e = T->local_vertices[2 * q], vert = T->local_vertices[2 * q + 1], i, j;
+      vert_node(vert, i, j);
+      mem.push_back(e * 16 + j * 4 + i);
+    }
+    off.push_back((int32_t)mem.size());
+  }
+  for (int f = 0; f < T->n_faces; ++f) {
+    const int32_t* F = T->interior_faces + 5 * f;
+    for (int q = 1; q < 3; ++q) {
+      int q2 = F[4] ? 3 - q : q, i, j;
+      face_node(F[1], q, i, j);
+      mem.push_back(F[0] * 16 + j * 4 + i);
+      face_node(F[3], q2, i, j);
+      mem.push_back(F[2] * 16 + j * 4 + i);
+      off.push_back((int32_t)mem.size());
+    }
+  }
+  if (T->elem_gid) {  // rank-count independent summation order: ascending global element id
+    for (size_t n = 0; n + 1 < off.size(); ++n)
+      std::stable_sort(mem.begin() + off[n], mem.begin() + off[n + 1],
+                       [&](int32_t a, int32_t b) { return T->elem_gid[a >> 4] < T->elem_gid[b >> 4]; });
+  }
+}
+
+extern "C" int b200_build_dss_csr(const b200_topology* T, int32_t* off_out, int32_t cap_nodes, int32_t* mem_out, int32_t cap_mem,
+                                  int32_t* nnodes, int32_t* nmem) {
+  std::vector<int32_t> off, mem;
+  build_csr(T, off, mem);
+  *nnodes = (int32_t)off.size() - 1; *nmem = (int32_t)mem.size();
+  if ((int32_t)off.size() > cap_nodes + 1 || (int32_t)mem.size() > cap_mem) return fail("b200_build_dss_csr: capacity too small");
+  memcpy(off_out, off.data(), off.size() * sizeof(int32_t));
+  memcpy(mem_out, mem.data(), mem.size() * sizeof(int32_t));
+  return 0;
+}
+
+extern "C" int b200_debug_dss_csr(b200_ctx* c, const int32_t** off, const int32_t** mem, int32_t* nnodes, int32_t* nmem) {
+  *off = c->h_off.data(); *mem = c->h_mem.data();
+  *nnodes = c->nnodes; *nmem = (int32_t)c->h_mem.size();
+  return 0;
+}
+
+template <class FT>
+static Par<FT> make_par(const b200_ctx* c) {
+  const b200_params& p = c->prm;
+  Par<FT> P;
+  P.R_d = (FT)p.R_d; P.cp_d = (FT)p.cp_d; P.cv_d = (FT)p.cv_d; P.T_0 = (FT)p.T_0; P.p0 = (FT)p.p_ref_theta;
+  P.kappa = (FT)(p.R_d / p.cp_d); P.Ts_ref = (FT)p.T_surf_ref; P.Tmin_ref = (FT)p.T_min_ref;
+  P.T_min_sgs = (FT)p.T_min_sgs; P.dt = (FT)p.dt;
+  P.nu4v = (FT)p.nu4_vorticity; P.nu4s = (FT)p.nu4_scalar; P.ddf = (FT)p.divergence_damping_factor;
+  P.nh = c->dims.nh; P.nv = c->dims.nv;
+  P.hyperdiff = p.hyperdiff; P.rayleigh = p.rayleigh_sponge; P.viscous = p.viscous_sponge; P.upwinding = p.energy_upwinding;
+  return P;
+}
+
+template <class FT>
+static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p) {
+  const int nht = c->dims.nh + c->dims.nh_ghost, nv = c->dims.nv, nf = nv + 1;
+  // ---- per-level constants
+  VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  const double R = G->radius;
+  auto sfun = [&](double z) { return c->dims.deep ? (R + z) / R : 1.0; };
+  auto zeta = [&](double z, double zd) { double s = sin(M_PI * ((z - zd) / (G->z_max - zd) / 2)); return s * s; };
+  for (int v = 0; v < nv; ++v) {
+    double s = sfun(G->z_c[v]);
+    V.sc2i[v] = (FT)(1.0 / (s * s));
+    V.dzc[v] = (FT)G->dz_c[v];
+    V.mc[v] = (FT)(s * s * G->dz_c[v]);
+    V.phic[v] = (FT)(p->grav * G->z_c[v]);
+    V.bruh[v] = (FT)(p->rayleigh_sponge && G->z_c[v] > p->zd_rayleigh ? p->alpha_rayleigh_uh * zeta(G->z_c[v], p->zd_rayleigh) : 0.0);
+    V.bvc[v] = (FT)(p->viscous_sponge && G->z_c[v] > p->zd_viscous ? p->kappa_2_sponge * zeta(G->z_c[v], p->zd_viscous) : 0.0);
+  }
+  for (int f = 0; f < nf; ++f) {
+    double s = sfun(G->z_f[f]);
+    V.sf2i[f] = (FT)(1.0 / (s * s));
+    V.sf[f] = (FT)s;
+    V.dzf[f] = (FT)G->dz_f[f];
+    V.g33f[f] = (FT)(1.0 / (G->dz_f[f] * G->dz_f[f]));
+    V.dphif[f] = (f > 0 && f < nv) ? (FT)((FT)(p->grav * G->z_c[f]) - (FT)(p->grav * G->z_c[f - 1])) : (FT)0;
+    V.brw[f] = (FT)(p->rayleigh_sponge && G->z_f[f] > p->zd_rayleigh ? p->alpha_rayleigh_w * zeta(G->z_f[f], p->zd_rayleigh) : 0.0);
+    V.bvf[f] = (FT)(p->viscous_sponge && G->z_f[f] > p->zd_viscous ? p->kappa_2_sponge * zeta(G->z_f[f], p->zd_viscous) : 0.0);
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 4; ++k) {
+      V.D[i * 4 + k] = (FT)G->gll_D[i * 4 + k];
+      V.Dw[i * 4 + k] = (FT)(-G->gll_D[k * 4 + i] * G->gll_w[k] / G->gll_w[i]);
+    }
+  CK(cudaMalloc(&c->d_vlev, sizeof(V)));
+  CK(cudaMemcpy(c->d_vlev, &V, sizeof(V), cudaMemcpyHostToDevice));
+  // ---- horizontal geometry
+  std::vector<double> WJ((size_t)nht * 16), tot((size_t)nht * 16);
+  for (int h = 0; h < nht; ++h)
+    for (int n = 0; n < 16; ++n) {
+      int i = n & 3, j = n >> 2;
+      WJ[h * 16 + n] = G->gll_w[i] * G->gll_w[j] * G->J2[h * 16 + n];
+      tot[h * 16 + n] = WJ[h * 16 + n];
+    }
+  for (int nd = 0; nd < c->nnodes; ++nd) {
+    double s = 0;
+    for (int q = c->h_off[nd]; q < c->h_off[nd + 1]; ++q) s += WJ[c->h_mem[q]];
+    for (int q = c->h_off[nd]; q < c->h_off[nd + 1]; ++q) tot[c->h_mem[q]] = s;
+  }
+  std::vector<FT> hg((size_t)nht * HG_N * 16);
+  for (int h = 0; h < nht; ++h)
+    for (int n = 0; n < 16; ++n) {
+      const double* A = G->dxdxi + ((size_t)h * 16 + n) * 4;  // A[a][b] = A[a*2+b]
+      double a00 = A[0], a01 = A[1], a10 = A[2], a11 = A[3];
+      double gc11 = a00 * a00 + a10 * a10, gc12 = a00 * a01 + a10 * a11, gc22 = a01 * a01 + a11 * a11;
+      double det = gc11 * gc22 - gc12 * gc12, dA = a00 * a11 - a01 * a10;
+      double lat = G->lat[h * 16 + n] * M_PI / 180.0;
+      double fv = 2 * p->Omega * cos(lat), fw = 2 * p->Omega * sin(lat);
+      double ai00 = a11 / dA, ai01 = -a01 / dA, ai10 = -a10 / dA, ai11 = a00 / dA;
+      FT* o = hg.data() + (size_t)h * HG_N * 16 + n;
+      o[HG_J2 * 16] = (FT)G->J2[h * 16 + n];
+      o[HG_RJ2 * 16] = (FT)(1.0 / G->J2[h * 16 + n]);
+      o[HG_GI11 * 16] = (FT)(gc22 / det); o[HG_GI12 * 16] = (FT)(-gc12 / det); o[HG_GI22 * 16] = (FT)(gc11 / det);
+      o[HG_GC11 * 16] = (FT)gc11; o[HG_GC12 * 16] = (FT)gc12; o[HG_GC22 * 16] = (FT)gc22;
+      o[HG_COR1 * 16] = (FT)(c->dims.deep ? ai01 * fv : 0.0);
+      o[HG_COR2 * 16] = (FT)(c->dims.deep ? ai11 * fv : 0.0);
+      o[HG_COR3 * 16] = (FT)fw;
+      o[HG_DSSW * 16] = (FT)(WJ[h * 16 + n] / tot[h * 16 + n]);
+      o[HG_A00 * 16] = (FT)a00; o[HG_A01 * 16] = (FT)a01; o[HG_A10 * 16] = (FT)a10; o[HG_A11 * 16] = (FT)a11;
+      o[HG_AI00 * 16] = (FT)ai00; o[HG_AI01 * 16] = (FT)ai01; o[HG_AI10 * 16] = (FT)ai10; o[HG_AI11 * 16] = (FT)ai11;
+    }
+  CK(cudaMalloc(&c->d_hgeo, hg.size() * sizeof(FT)));
+  CK(cudaMemcpy(c->d_hgeo, hg.data(), hg.size() * sizeof(FT), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// shared-memory footprints (bytes)
+template <class FT> static size_t smem_base() { return sizeof(VLev<FT>) + HG_ELEM * 16 * sizeof(FT); }
+template <class FT> static size_t smem_slabs(int n) { return smem_base<FT>() + (size_t)n * SLAB * sizeof(FT); }
+
+template <class FT>
+static int set_attrs() {
+  CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
+  CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
+  CK(cudaFuncSetAttribute(k_wfact<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
+  CK(cudaFuncSetAttribute(k_ldiv<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * SLAB * sizeof(FT))));
+  CK(cudaFuncSetAttribute(k_t_post_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
+  CK(cudaFuncSetAttribute(k_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(18)));
+  CK(cudaFuncSetAttribute(k_texp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(22)));
+  CK(cudaFuncSetAttribute(k_texp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
+  return 0;
+}
+
+extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geometry* G, const b200_topology* T,
+                           const b200_params* p, const void* nccl_id, int rank, int nranks) {
+  if (!out || !d || !G || !T || !p) return fail("b200_create: null argument");
+  if (d->nq != 4) return fail("b200_create: only Nq = 4 (nh_poly = 3) is supported");
+  if (d->nv + 1 > LV || d->nv < 2) return fail("b200_create: need 2 <= nv <= 63");
+  if (d->ft_bytes != 4 && d->ft_bytes != 8) return fail("b200_create: ft_bytes must be 4 or 8");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("b200_create: no CUDA device (this library has no CPU fallback)");
+  b200_ctx* c = new b200_ctx();
+  c->dims = *d; c->prm = *p; c->ft = d->ft_bytes; c->rank = rank; c->nranks = nranks;
+  build_csr(T, c->h_off, c->h_mem);
+  c->nnodes = (int)c->h_off.size() - 1;
+  // keep only nodes with at least one local member
+  {
+    std::vector<int32_t> off2{0}, mem2;
+    for (int n = 0; n < c->nnodes; ++n) {
+      bool local = false;
+      for (int q = c->h_off[n]; q < c->h_off[n + 1]; ++q) local |= (c->h_mem[q] >> 4) < d->nh;
+      if (!local) continue;
+      for (int q = c->h_off[n]; q < c->h_off[n + 1]; ++q) mem2.push_back(c->h_mem[q]);
+      off2.push_back((int32_t)mem2.size());
+    }
+    c->h_off.swap(off2); c->h_mem.swap(mem2);
+    c->nnodes = (int)c->h_off.size() - 1;
+  }
+  for (int n = 0; n < c->nnodes; ++n)
+    if (c->h_off[n + 1] - c->h_off[n] > 4) { delete c; return fail("b200_create: node shared by more than 4 elements"); }
+  CK(cudaMalloc(&c->d_off, c->h_off.size() * sizeof(int)));
+  CK(cudaMalloc(&c->d_mem, std::max<size_t>(1, c->h_mem.size()) * sizeof(int)));
+  CK(cudaMemcpy(c->d_off, c->h_off.data(), c->h_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_mem, c->h_mem.data(), c->h_mem.size() * sizeof(int), cudaMemcpyHostToDevice));
+  int r = (c->ft == 4) ? create_geo<float>(c, G, p) : create_geo<double>(c, G, p);
+  if (r) { delete c; return r; }
+  r = (c->ft == 4) ? set_attrs<float>() : set_attrs<double>();
+  if (r) { delete c; return r; }
+  // halo plan
+  if (nranks > 1 && T->n_neighbors > 0) {
+    if (!nccl_id) { delete c; return fail("b200_create: nccl_unique_id required for nranks > 1"); }
+    if (nccl_load()) { delete c; return -1; }
+    c->nbr.assign(T->neighbor_ranks, T->neighbor_ranks + T->n_neighbors);
+    c->send_off.assign(T->send_offset, T->send_offset + T->n_neighbors + 1);
+    c->recv_off.assign(T->recv_offset, T->recv_offset + T->n_neighbors + 1);
+    c->n_send = c->send_off.back();
+    CK(cudaMalloc(&c->d_send_elems, std::max(1, c->n_send) * sizeof(int)));
+    CK(cudaMemcpy(c->d_send_elems, T->send_elems, c->n_send * sizeof(int), cudaMemcpyHostToDevice));
+    Id128 id;
+    memcpy(&id, nccl_id, 128);
+    NK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" int b200_destroy(b200_ctx* c) {
+  if (!c) return 0;
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
+  for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
+  for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
+  fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  delete c;
+  return 0;
+}
+
+extern "C" int64_t b200_launch_count(b200_ctx* c) { return c ? c->launches : 0; }
+
+#define LAUNCH_CHECK(c)                                                               \
+  do {                                                                                \
+    (c)->launches++;                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                              \
+    if (e_ != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+static int impl_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs* o, cudaStream_t s) {
+  b200_cacheptrs z = {};
+  if (!o) o = &z;
+  k_cache_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(1), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                          (const FT*)Yc, (FT*)Yf, (FT*)o->u_c, (FT*)o->u3_f, (FT*)o->K_c,
+                                                          (FT*)o->T_c, (FT*)o->p_c, (FT*)o->h_tot_c);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs* o, void* stream) {
+  return c->ft == 4 ? impl_cache_imp<float>(c, Yc, Yf, o, (cudaStream_t)stream) : impl_cache_imp<double>(c, Yc, Yf, o, (cudaStream_t)stream);
+}
+
+template <class FT>
+static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
+  k_t_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                       (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
+  return c->ft == 4 ? impl_t_imp<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_imp<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
+}
+
+template <class FT>
+static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, cudaStream_t s) {
+  if (!c->d_jac) CK(cudaMalloc(&c->d_jac, (size_t)c->dims.nh * JC_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
+  k_wfact<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                       (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, double, void* stream) {
+  return c->ft == 4 ? impl_wfact<float>(c, Yc, Yf, dtg, (cudaStream_t)stream) : impl_wfact<double>(c, Yc, Yf, dtg, (cudaStream_t)stream);
+}
+
+template <class FT>
+static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, cudaStream_t s) {
+  if (!c->d_jac) return fail("b200_ldiv: b200_wfact has not been called");
+  k_ldiv<FT><<<c->dims.nh, NT, 8 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
+                                                         (FT*)dYc, (FT*)dYf);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, void* stream) {
+  return c->ft == 4 ? impl_ldiv<float>(c, dYc, dYf, Rc, Rf, (cudaStream_t)stream) : impl_ldiv<double>(c, dYc, dYf, Rc, Rf, (cudaStream_t)stream);
+}
+
+template <class FT>
+static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
+  k_t_post_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                            (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
+  return c->ft == 4 ? impl_t_post<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_post<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// DSS: local gather–scatter, with a whole-slab halo exchange for elements owned by other ranks.
+struct DssField { void* ptr; int nf; int is_face; int kind; };
+
+template <class FT>
+static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s) {
+  const int nv = c->dims.nv, nh = c->dims.nh;
+  DssArgs A;
+  A.n = 0;
+  // halo: exchange the raw slabs of the send elements; ghosts land in ghostbuf per field
+  size_t tot_slab = 0;
+  for (int k = 0; k < nfields; ++k) tot_slab += (size_t)F[k].nf * 16 * (nv + F[k].is_face);
+  const bool halo = c->comm != nullptr;
+  if (halo) {
+    size_t need_s = tot_slab * c->n_send * sizeof(FT), need_g = tot_slab * c->dims.nh_ghost * sizeof(FT);
+    if (need_s + need_g > c->halo_cap) {
+      if (c->sendbuf) cudaFree(c->sendbuf);
+      if (c->ghostbuf) cudaFree(c->ghostbuf);
+      CK(cudaMalloc(&c->sendbuf, std::max<size_t>(need_s, 16)));
+      CK(cudaMalloc(&c->ghostbuf, std::max<size_t>(need_g, 16)));
+      c->halo_cap = need_s + need_g;
+    }
+    size_t so = 0, go = 0;
+    for (int k = 0; k < nfields; ++k) {
+      int slab = F[k].nf * 16 * (nv + F[k].is_face);
+      if (c->n_send > 0) {
+        k_pack<FT><<<c->n_send, 256, 0, s>>>((const FT*)F[k].ptr, (FT*)c->sendbuf + so, c->d_send_elems, slab);
+        LAUNCH_CHECK(c);
+      }
+      so += (size_t)slab * c->n_send; go += (size_t)slab * c->dims.nh_ghost;
+    }
+    NK(g_nccl.GroupStart());
+    so = 0; go = 0;
+    const int dt_nccl = sizeof(FT) == 4 ? 7 /*ncclFloat32*/ : 8 /*ncclFloat64*/;
+    for (int k = 0; k < nfields; ++k) {
+      int slab = F[k].nf * 16 * (nv + F[k].is_face);
+      for (size_t q = 0; q < c->nbr.size(); ++q) {
+        int ns = c->send_off[q + 1] - c->send_off[q], nr = c->recv_off[q + 1] - c->recv_off[q];
+        if (ns > 0) NK(g_nccl.Send((FT*)c->sendbuf + so + (size_t)c->send_off[q] * slab, (size_t)ns * slab, dt_nccl, c->nbr[q], c->comm, s));
+        if (nr > 0) NK(g_nccl.Recv((FT*)c->ghostbuf + go + (size_t)c->recv_off[q] * slab, (size_t)nr * slab, dt_nccl, c->nbr[q], c->comm, s));
+      }
+      so += (size_t)slab * c->n_send; go += (size_t)slab * c->dims.nh_ghost;
+    }
+    NK(g_nccl.GroupEnd());
+  }
+  size_t go = 0;
+  for (int k = 0; k < nfields; ++k) {
+    const int nlev = nv + F[k].is_face;
+    const int estride = F[k].nf * 16 * nlev;
+    FT* base = (FT*)F[k].ptr;
+    FT* gbase = halo ? (FT*)c->ghostbuf + go : nullptr;
+    go += (size_t)estride * c->dims.nh_ghost;
+    int comp = 0;
+    auto add = [&](bool pair) -> int {
+      if (A.n >= DSS_MAX_ITEMS) return fail("b200_dss: too many components in one call (max 8 items)");
+      DssItem& I = A.it[A.n++];
+      I.p0 = base + (size_t)comp * 16 * nlev;
+      I.p1 = pair ? base + (size_t)(comp + 1) * 16 * nlev : nullptr;
+      I.g0 = gbase ? gbase + (size_t)comp * 16 * nlev : nullptr;
+      I.g1 = (gbase && pair) ? gbase + (size_t)(comp + 1) * 16 * nlev : nullptr;
+      I.nlev = nlev; I.estride = estride; I.gstride = estride;
+      comp += pair ? 2 : 1;
+      return 0;
+    };
+    if (F[k].kind == 2) { if (add(false)) return -1; if (add(true)) return -1; }
+    else if (F[k].kind == 1) { if (add(true)) return -1; }
+    while (comp < F[k].nf) if (add(false)) return -1;
+  }
+  dim3 blk(64, 4);
+  k_dss<FT><<<(c->nnodes + 3) / 4, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, const int32_t* is_face, const int32_t* kind,
+                        int32_t nfields, void* stream) {
+  if (nfields > 8) return fail("b200_dss: at most 8 fields per call");
+  DssField F[8];
+  for (int k = 0; k < nfields; ++k) F[k] = {fields[k], nf[k], is_face[k], kind[k]};
+  return c->ft == 4 ? impl_dss<float>(c, F, nfields, (cudaStream_t)stream) : impl_dss<double>(c, F, nfields, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* const* T, const double* coef, size_t N, cudaStream_t s) {
+  AxpyArgs<FT> A;
+  A.n = 0;
+  for (int k = 0; k < n; ++k) {
+    if (coef[k] == 0.0) continue;
+    if (A.n >= AXPY_MAX) return fail("b200_axpy_n: too many terms");
+    A.T[A.n] = T[k]; A.c[A.n] = (FT)coef[k]; A.n++;
+  }
+  bool al = (N % 4 == 0) && (((uintptr_t)out | (uintptr_t)base) % (4 * sizeof(FT)) == 0);
+  for (int k = 0; k < A.n; ++k) al = al && ((uintptr_t)A.T[k] % (4 * sizeof(FT)) == 0);
+  int blocks = 148 * 8;
+  if (al) k_axpy_n<FT, 4><<<blocks, 256, 0, s>>>(out, base, A, N / 4);
+  else k_axpy_n<FT, 1><<<blocks, 256, 0, s>>>(out, base, A, N);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+template <class FT>
+static int impl_axpy(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int n, const void* const* Tc,
+                     const void* const* Tf, const double* coef, cudaStream_t s) {
+  if (launch_axpy<FT>(c, (FT*)Uc, (const FT*)uc, n, (const FT* const*)Tc, coef, c->nc(), s)) return -1;
+  return launch_axpy<FT>(c, (FT*)Uf, (const FT*)uf, n, (const FT* const*)Tf, coef, c->nf(), s);
+}
+extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int32_t n, const void* const* Tc,
+                           const void* const* Tf, const double* coef, void* stream) {
+  return c->ft == 4 ? impl_axpy<float>(c, Uc, Uf, uc, uf, n, Tc, Tf, coef, (cudaStream_t)stream)
+                    : impl_axpy<double>(c, Uc, Uf, uc, uf, n, Tc, Tf, coef, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, cudaStream_t s) {
+  const bool hd = c->prm.hyperdiff != 0;
+  if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
+  if (Ylc) CK(cudaMemsetAsync(Ylc, 0, c->nc() * sizeof(FT), s));
+  if (Ylf) CK(cudaMemsetAsync(Ylf, 0, c->nf() * sizeof(FT), s));
+  k_texp_a<FT><<<c->dims.nh, NT, smem_slabs<FT>(22), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                        (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+  LAUNCH_CHECK(c);
+  if (hd) {
+    DssField F = {c->H, 4, 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d
+    if (impl_dss<FT>(c, &F, 1, s)) return -1;
+    k_texp_c<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                          (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+    LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, double,
+                              void* stream) {
+  return c->ft == 4 ? impl_t_exp<float>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream)
+                    : impl_t_exp<double>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ARS343 tableau (Ascher–Ruuth–Spiteri 1997 §2.7; ClimaTimeSteppers IMEXAlgorithm(ARS343))
+struct Tableau { double ae[4][4], ai[4][4], be[4], bi[4]; };
+static Tableau ars343() {
+  Tableau t;
+  memset(&t, 0, sizeof(t));
+  const double g = 0.4358665215084590, a42 = 0.5529291480359398, a43 = a42;
+  const double b1 = -3 * g * g / 2 + 4 * g - 0.25, b2 = 3 * g * g / 2 - 5 * g + 1.25;
+  const double a31 = (1 - 9 * g / 2 + 3 * g * g / 2) * a42 + (11.0 / 4 - 21 * g / 2 + 15 * g * g / 4) * a43 - 3.5 + 13 * g - 9 * g * g / 2;
+  const double a32 = (-1 + 9 * g / 2 - 3 * g * g / 2) * a42 + (-11.0 / 4 + 21 * g / 2 - 15 * g * g / 4) * a43 + 4 - 25 * g / 2 + 9 * g * g / 2;
+  t.ae[1][0] = g; t.ae[2][0] = a31; t.ae[2][1] = a32; t.ae[3][0] = 1 - a42 - a43; t.ae[3][1] = a42; t.ae[3][2] = a43;
+  t.ai[1][1] = g; t.ai[2][1] = (1 - g) / 2; t.ai[2][2] = g; t.ai[3][1] = b1; t.ai[3][2] = b2; t.ai[3][3] = g;
+  t.be[1] = b1; t.be[2] = b2; t.be[3] = g;
+  t.bi[1] = b1; t.bi[2] = b2; t.bi[3] = g;
+  return t;
+}
+
+template <class FT>
+static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT sc, size_t N, cudaStream_t s) {
+  bool al = (N % 4 == 0) && (((uintptr_t)out | (uintptr_t)a | (uintptr_t)b) % (4 * sizeof(FT)) == 0);
+  if (al) k_diff_scale<FT, 4><<<148 * 8, 256, 0, s>>>(out, a, b, sc, N / 4);
+  else k_diff_scale<FT, 1><<<148 * 8, 256, 0, s>>>(out, a, b, sc, N);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
+template <class FT>
+static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s) {
+  const size_t bc = c->nc() * sizeof(FT), bf = c->nf() * sizeof(FT);
+  if (!c->Uc[0]) {
+    for (int i = 0; i < 2; ++i) { CK(cudaMalloc(&c->Uc[i], bc)); CK(cudaMalloc(&c->Uf[i], bf)); }
+    for (int i = 0; i < 4; ++i) {
+      CK(cudaMalloc(&c->Tec[i], bc)); CK(cudaMalloc(&c->Tef[i], bf));
+      CK(cudaMalloc(&c->Tic[i], bc)); CK(cudaMalloc(&c->Tif[i], bf));
+    }
+    CK(cudaMalloc(&c->Rc, bc)); CK(cudaMalloc(&c->Rf, bf)); CK(cudaMalloc(&c->dc, bc)); CK(cudaMalloc(&c->df, bf));
+  }
+  const Tableau tb = ars343();
+  const double dt = c->prm.dt;
+  auto dss_state = [&](void* ac, void* af) -> int {
+    DssField F[2] = {{ac, 4, 0, 2}, {af, 1, 1, 0}};
+    return impl_dss<FT>(c, F, 2, s);
+  };
+  for (int i = 0; i < 4; ++i) {
+    void *Uc = Yc, *Uf = Yf;  // stage 1: U = u
+    if (i > 0) {
+      Uc = c->Uc[0]; Uf = c->Uf[0];
+      const void* Tc[8]; const void* Tf[8]; double cf[8]; int n = 0;
+      for (int j = 0; j < i; ++j) {
+        if (tb.ae[i][j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.ae[i][j]; }
+        if (tb.ai[i][j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.ai[i][j]; }
+      }
+      if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s)) return -1;
+      if (dss_state(Uc, Uf)) return -1;
+      const double dtg = dt * tb.ai[i][i];
+      void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
+      if (fused) {
+        CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
+        k_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(18), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                 (FT*)Nc, (FT*)Nf, (FT)dtg);
+        LAUNCH_CHECK(c);
+        // the boundary filter of cache_imp! must also be visible in temp (= U)
+        if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
+      } else {
+        if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
+        CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
+        if (impl_wfact<FT>(c, Nc, Nf, dtg, s)) return -1;
+        if (impl_t_imp<FT>(c, c->Rc, c->Rf, Nc, Nf, s)) return -1;
+        {  // R = temp + dtγ·T_imp(U) − U
+          const void* Tc[2] = {c->Rc, Nc}; const void* Tf[2] = {c->Rf, Nf}; double cf[2] = {dtg, -1.0};
+          if (impl_axpy<FT>(c, c->Rc, c->Rf, Uc, Uf, 2, Tc, Tf, cf, s)) return -1;
+        }
+        if (impl_ldiv<FT>(c, c->dc, c->df, c->Rc, c->Rf, s)) return -1;
+        {
+          const void* Tc[1] = {c->dc}; const void* Tf[1] = {c->df}; double cf[1] = {-1.0};
+          if (impl_axpy<FT>(c, Nc, Nf, Nc, Nf, 1, Tc, Tf, cf, s)) return -1;
+        }
+        if (impl_cache_imp<FT>(c, Nc, Nf, nullptr, s)) return -1;
+        if (c->prm.energy_upwinding != 0) {
+          if (impl_t_post<FT>(c, c->Rc, c->Rf, Nc, Nf, s)) return -1;
+          const void* Tc[1] = {c->Rc}; const void* Tf[1] = {c->Rf}; double cf[1] = {dtg};
+          if (impl_axpy<FT>(c, Nc, Nf, Nc, Nf, 1, Tc, Tf, cf, s)) return -1;
+        }
+      }
+      if (dss_state(Nc, Nf)) return -1;
+      if (!fused && impl_cache_imp<FT>(c, Nc, Nf, nullptr, s)) return -1;
+      // T_imp[i] = (U − temp)/dtγ
+      if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), s)) return -1;
+      if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), s)) return -1;
+      Uc = Nc; Uf = Nf;
+    } else {
+      if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
+    }
+    if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], nullptr, nullptr, Uc, Uf, s)) return -1;
+  }
+  {
+    const void* Tc[8]; const void* Tf[8]; double cf[8]; int n = 0;
+    for (int j = 0; j < 4; ++j) {
+      if (tb.be[j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.be[j]; }
+      if (tb.bi[j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.bi[j]; }
+    }
+    if (impl_axpy<FT>(c, Yc, Yf, Yc, Yf, n, Tc, Tf, cf, s)) return -1;
+  }
+  if (dss_state(Yc, Yf)) return -1;
+  return impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
+}
+extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
+  return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, (cudaStream_t)stream) : impl_step<double>(c, Yc, Yf, fused, (cudaStream_t)stream);
+}

@@ -1,0 +1,159 @@
+// common.cuh — shared device-side definitions for the B200 dycore kernels.
+//
+// Data layout (ClimaCore VIJFH, C order [h][f][j][i][v]): for a fixed element h and component f
+// the (j,i,v) slab is one contiguous block of 16*Nv (centres) or 16*(Nv+1) (faces) values with the
+// level index fastest.  Every element-kernel below assigns ONE ELEMENT PER CTA: consecutive lanes
+// own consecutive levels (fully coalesced global loads of the contiguous slab), the 16 GLL nodes
+// are spread over the warps, and all horizontal (4x4 derivative-matrix) and vertical (k±1)
+// neighbours are read from a shared-memory copy of the slab with node stride LVP = 65 words
+// (odd ⇒ conflict-free both for level-major and for column-sequential access).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int NQ = 4;
+constexpr int NN = 16;    // nodes per element
+constexpr int LV = 64;    // max faces per column (Nv + 1 <= 64)
+constexpr int LVP = 65;   // padded shared-memory node stride
+constexpr int NT = 256;   // threads per element CTA
+constexpr int NIT = (NN * LV) / NT;  // 4 point-iterations per thread
+constexpr int SLAB = NN * LVP;       // shared-memory words per field
+
+// horizontal geometry components, stored [h][HG_N][16]
+enum {
+  HG_J2 = 0, HG_RJ2, HG_GI11, HG_GI12, HG_GI22, HG_GC11, HG_GC12, HG_GC22,
+  HG_COR1, HG_COR2, HG_COR3, HG_DSSW, HG_A00, HG_A01, HG_A10, HG_A11,
+  HG_AI00, HG_AI01, HG_AI10, HG_AI11, HG_N
+};
+constexpr int HG_ELEM = 11;  // components the element kernels stage (J2..COR3)
+
+// per-level constants (host-precomputed in double, stored in FT)
+template <class FT>
+struct VLev {
+  FT sc2i[LV];   // 1 / s_c^2, s = (R+z)/R (deep) or 1
+  FT sf2i[LV];   // 1 / s_f^2
+  FT sf[LV];     // s_f
+  FT dzc[LV];    // vertical J at centres
+  FT dzf[LV];    // vertical J at faces
+  FT mc[LV];     // s_c^2 * dz_c   (J_c = J2 * mc)
+  FT g33f[LV];   // 1 / dz_f^2
+  FT phic[LV];   // grav * z_c
+  FT dphif[LV];  // ᶠgradᵥ(Φ): phic[f]-phic[f-1], 0 on boundary faces
+  FT brw[LV];    // β_rayleigh_u₃(z_f)
+  FT bruh[LV];   // β_rayleigh_uₕ(z_c)
+  FT bvc[LV];    // β_viscous(z_c)
+  FT bvf[LV];    // β_viscous(z_f)
+  FT D[16];      // strong derivative matrix  D[i*4+k]
+  FT Dw[16];     // weak derivative matrix   Dw[i*4+k] = -D[k][i] w_k / w_i
+};
+
+template <class FT>
+struct Par {
+  FT R_d, cp_d, cv_d, T_0, p0, kappa, Ts_ref, Tmin_ref, T_min_sgs, dt;
+  FT nu4v, nu4s, ddf;
+  int nh, nv;
+  int hyperdiff, rayleigh, viscous, upwinding;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class FT> __device__ __forceinline__ FT fmax_(FT a, FT b) { return a > b ? a : b; }
+template <class FT> __device__ __forceinline__ FT fmin_(FT a, FT b) { return a < b ? a : b; }
+__device__ __forceinline__ float  pow_(float a, float b)  { return powf(a, b); }
+__device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ float  log_(float a)  { return logf(a); }
+__device__ __forceinline__ double log_(double a) { return log(a); }
+__device__ __forceinline__ float  abs_(float a)  { return fabsf(a); }
+__device__ __forceinline__ double abs_(double a) { return fabs(a); }
+
+template <class FT> __device__ __forceinline__ FT pow7(FT x) {
+  FT x2 = x * x, x4 = x2 * x2;
+  return x4 * x2 * x;
+}
+
+// Dry thermodynamics + hydrostatic reference state at one point
+// (precomputed_quantities.jl:733-815 dry branch; refstate_thermodynamics.jl:22-168).
+template <class FT>
+struct Pt {
+  FT T, p, h, Pi, thp /*θ_v-θ_vr*/, thv, phir, sdr;
+};
+template <class FT>
+__device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K, FT Phi) {
+  Pt<FT> o;
+  FT etot = rhoe / rho;
+  FT eint = etot - K - Phi;
+  o.T = fmax_(P.T_min_sgs, P.T_0 + eint / P.cv_d);
+  o.h = etot + P.R_d * o.T;
+  o.p = rho * P.R_d * o.T;
+  o.Pi = pow_(o.p / P.p0, P.kappa);
+  FT Pi7 = pow7(o.Pi);
+  FT Tr = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * Pi7;
+  o.thv = o.T / o.Pi;
+  o.thp = o.thv - Tr / o.Pi;
+  o.phir = -P.cp_d * (P.Tmin_ref * log_(o.Pi) + (P.Ts_ref - P.Tmin_ref) / FT(7) * (Pi7 - FT(1)));
+  o.sdr = P.cp_d * (Tr - P.T_0) + o.phir;
+  return o;
+}
+
+// 4-point contractions along ξ1 (d1) and ξ2 (d2) of a shared slab a[n*LVP+v], n = j*4+i.
+template <class FT>
+__device__ __forceinline__ FT d1(const FT* __restrict__ M, const FT* a, int i, int j, int v) {
+  const FT* r = a + (j * 4) * LVP + v;
+  return M[i * 4 + 0] * r[0] + M[i * 4 + 1] * r[LVP] + M[i * 4 + 2] * r[2 * LVP] +
+         M[i * 4 + 3] * r[3 * LVP];
+}
+template <class FT>
+__device__ __forceinline__ FT d2(const FT* __restrict__ M, const FT* a, int i, int j, int v) {
+  const FT* r = a + i * LVP + v;
+  return M[j * 4 + 0] * r[0] + M[j * 4 + 1] * r[4 * LVP] + M[j * 4 + 2] * r[8 * LVP] +
+         M[j * 4 + 3] * r[12 * LVP];
+}
+// contractions of a product a*b (flux forms) without materialising it
+template <class FT>
+__device__ __forceinline__ FT d1p(const FT* __restrict__ M, const FT* a, const FT* b, int i, int j, int v) {
+  const int o = (j * 4) * LVP + v;
+  return M[i * 4 + 0] * (a[o] * b[o]) + M[i * 4 + 1] * (a[o + LVP] * b[o + LVP]) +
+         M[i * 4 + 2] * (a[o + 2 * LVP] * b[o + 2 * LVP]) + M[i * 4 + 3] * (a[o + 3 * LVP] * b[o + 3 * LVP]);
+}
+template <class FT>
+__device__ __forceinline__ FT d2p(const FT* __restrict__ M, const FT* a, const FT* b, int i, int j, int v) {
+  const int o = i * LVP + v;
+  return M[j * 4 + 0] * (a[o] * b[o]) + M[j * 4 + 1] * (a[o + 4 * LVP] * b[o + 4 * LVP]) +
+         M[j * 4 + 2] * (a[o + 8 * LVP] * b[o + 8 * LVP]) + M[j * 4 + 3] * (a[o + 12 * LVP] * b[o + 12 * LVP]);
+}
+template <class FT>
+__device__ __forceinline__ FT d1p3(const FT* __restrict__ M, const FT* a, const FT* b, const FT* c, int i, int j, int v) {
+  const int o = (j * 4) * LVP + v;
+  return M[i * 4 + 0] * (a[o] * b[o] * c[o]) + M[i * 4 + 1] * (a[o + LVP] * b[o + LVP] * c[o + LVP]) +
+         M[i * 4 + 2] * (a[o + 2 * LVP] * b[o + 2 * LVP] * c[o + 2 * LVP]) +
+         M[i * 4 + 3] * (a[o + 3 * LVP] * b[o + 3 * LVP] * c[o + 3 * LVP]);
+}
+template <class FT>
+__device__ __forceinline__ FT d2p3(const FT* __restrict__ M, const FT* a, const FT* b, const FT* c, int i, int j, int v) {
+  const int o = i * LVP + v;
+  return M[j * 4 + 0] * (a[o] * b[o] * c[o]) + M[j * 4 + 1] * (a[o + 4 * LVP] * b[o + 4 * LVP] * c[o + 4 * LVP]) +
+         M[j * 4 + 2] * (a[o + 8 * LVP] * b[o + 8 * LVP] * c[o + 8 * LVP]) +
+         M[j * 4 + 3] * (a[o + 12 * LVP] * b[o + 12 * LVP] * c[o + 12 * LVP]);
+}
+
+// Stage one component slab (nlev levels per node) from global into shared memory.
+template <class FT>
+__device__ __forceinline__ void load_slab(FT* s, const FT* __restrict__ g, int nlev) {
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v < nlev) s[n * LVP + v] = g[n * nlev + v];
+  }
+}
+template <class FT>
+__device__ __forceinline__ void load_hgeo(FT* s, const FT* __restrict__ hgeo, int h) {
+  for (int idx = threadIdx.x; idx < HG_ELEM * 16; idx += NT) s[idx] = hgeo[(size_t)h * HG_N * 16 + idx];
+}
+template <class FT>
+__device__ __forceinline__ void load_vlev(VLev<FT>* s, const VLev<FT>* __restrict__ g) {
+  const FT* gp = reinterpret_cast<const FT*>(g);
+  FT* sp = reinterpret_cast<FT*>(s);
+  for (int idx = threadIdx.x; idx < (int)(sizeof(VLev<FT>) / sizeof(FT)); idx += NT) sp[idx] = gp[idx];
+}
+
+}  // namespace b200

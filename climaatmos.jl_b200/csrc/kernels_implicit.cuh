@@ -1,0 +1,514 @@
+// kernels_implicit.cuh — vertically implicit part of the step, one element (16 columns) per CTA.
+//
+//   k_cache_imp   set_implicit_precomputed_quantities!  (src/cache/precomputed_quantities.jl:698-831)
+//   k_t_imp       implicit_tendency!                    (src/prognostic_equations/implicit/implicit_tendency.jl:36-98,185-298)
+//   k_wfact       update_jacobian! (advection blocks)   (.../implicit/manual_sparse_jacobian.jl:713-870)
+//   k_ldiv        invert_jacobian! (BlockArrowheadSolve → Schur onto u₃ → Thomas) (:504-585,1897)
+//   k_t_post_imp  correct_implicit_advection_tendency!  (implicit_tendency.jl:322-339)
+//   k_imp_stage   all of the above fused into one pass over the element (native stepper)
+//
+// The band-matrix blocks of the reference are never materialised as fields: k_wfact stores the
+// 15 per-level coefficients the solve needs (Schur tridiagonal + couplings); the fused kernel
+// keeps them in shared memory only.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// jacobian coefficient planes written by k_wfact, each [16][Nv+1] per element
+enum { JC_L = 0, JC_D, JC_U, JC_UR_LO, JC_UR_HI, JC_UE_LO, JC_UE_HI, JC_U1_LO, JC_U1_HI, JC_U2_LO,
+       JC_U2_HI, JC_RU_LO, JC_RU_HI, JC_EU_LO, JC_EU_HI, JC_N };
+
+template <class FT>
+__device__ __forceinline__ FT kinetic(const FT* hg, const VLev<FT>& V, FT u1, FT u2, FT u3lo, FT u3hi,
+                                      int n, int v) {
+  FT c1 = hg[HG_GI11 * 16 + n] * u1 + hg[HG_GI12 * 16 + n] * u2;
+  FT c2 = hg[HG_GI12 * 16 + n] * u1 + hg[HG_GI22 * 16 + n] * u2;
+  return FT(0.5) * ((u1 * c1 + u2 * c2) * V.sc2i[v] +
+                    FT(0.5) * (u3lo * (V.g33f[v] * u3lo) + u3hi * (V.g33f[v + 1] * u3hi)));
+}
+
+// shared-memory carve-up helper
+template <class FT>
+struct Smem {
+  FT* base;
+  __device__ Smem(void* p) : base(reinterpret_cast<FT*>(p)) {}
+  __device__ FT* take(int n) { FT* r = base; base += n; return r; }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+__global__ void __launch_bounds__(NT) k_cache_imp(Par<FT> P, const FT* __restrict__ hgeo,
+                                                  const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+                                                  FT* Yf, FT* uc, FT* u3f, FT* Kc, FT* Tc, FT* pc, FT* hc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  FT* s_u3 = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  load_vlev(&V, vlev);
+  load_hgeo(hg, hgeo, h);
+  FT* gYf = Yf + (size_t)h * 16 * nf;
+  load_slab(s_u3, gYf, nf);
+  __syncthreads();
+  // set_velocity_at_surface!/top! (:486-554): flat grid ⇒ ᶠuₕ³ = 0 ⇒ u₃ = -0/g³³ = 0 on both boundaries
+  if (threadIdx.x < 16) {
+    int n = threadIdx.x;
+    s_u3[n * LVP] = FT(0);
+    s_u3[n * LVP + nv] = FT(0);
+    gYf[n * nf] = FT(0);
+    gYf[n * nf + nv] = FT(0);
+  }
+  __syncthreads();
+  const FT* gYc = Yc + (size_t)h * 4 * 16 * nv;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v < nv) {
+      FT rho = gYc[(0 * 16 + n) * nv + v], u1 = gYc[(1 * 16 + n) * nv + v];
+      FT u2 = gYc[(2 * 16 + n) * nv + v], re = gYc[(3 * 16 + n) * nv + v];
+      FT lo = s_u3[n * LVP + v], hi = s_u3[n * LVP + v + 1];
+      FT K = kinetic(hg, V, u1, u2, lo, hi, n, v);
+      Pt<FT> t = thermo(P, rho, re, K, V.phic[v]);
+      size_t o = ((size_t)h * 16 + n) * nv + v;
+      if (Kc) Kc[o] = K;
+      if (Tc) Tc[o] = t.T;
+      if (pc) pc[o] = t.p;
+      if (hc) hc[o] = t.h;
+      if (uc) {
+        size_t o3 = ((size_t)h * 3 * 16 + n) * nv + v;
+        uc[o3] = u1;
+        uc[o3 + (size_t)16 * nv] = u2;
+        uc[o3 + (size_t)32 * nv] = FT(0.5) * (lo + hi);
+      }
+    }
+    if (v < nf && u3f) u3f[((size_t)h * 16 + n) * nf + v] = V.g33f[v] * s_u3[n * LVP + v];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared preparation: stage the state, compute per-centre thermodynamics into shared slabs.
+template <class FT>
+struct ImpSlabs {
+  FT *rho, *u1, *u2, *re, *u3;  // state
+  FT *K, *h, *Pi, *thv, *thp, *phr, *T;  // centre diagnostics
+};
+
+template <class FT>
+__device__ __forceinline__ void imp_carve(Smem<FT>& sm, ImpSlabs<FT>& S) {
+  S.rho = sm.take(SLAB); S.u1 = sm.take(SLAB); S.u2 = sm.take(SLAB); S.re = sm.take(SLAB); S.u3 = sm.take(SLAB);
+  S.K = sm.take(SLAB); S.h = sm.take(SLAB); S.Pi = sm.take(SLAB); S.thv = sm.take(SLAB); S.thp = sm.take(SLAB);
+  S.phr = sm.take(SLAB); S.T = sm.take(SLAB);
+}
+
+template <class FT>
+__device__ __forceinline__ void imp_load_state(ImpSlabs<FT>& S, const FT* __restrict__ Yc,
+                                               const FT* __restrict__ Yf, int h, int nv) {
+  const FT* gYc = Yc + (size_t)h * 4 * 16 * nv;
+  load_slab(S.rho, gYc, nv);
+  load_slab(S.u1, gYc + 16 * nv, nv);
+  load_slab(S.u2, gYc + 32 * nv, nv);
+  load_slab(S.re, gYc + 48 * nv, nv);
+  load_slab(S.u3, Yf + (size_t)h * 16 * (nv + 1), nv + 1);
+}
+
+template <class FT>
+__device__ __forceinline__ void imp_thermo(const Par<FT>& P, const FT* hg, const VLev<FT>& V, ImpSlabs<FT>& S) {
+  const int nv = P.nv;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v < nv) {
+      int o = n * LVP + v;
+      FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
+      Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
+      S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = t.phir; S.T[o] = t.T;
+    }
+  }
+}
+
+// mass flux through interior face f (zero on the boundary faces: ᶜadvdivᵥ SetValue(0)):
+// (ᶠinterp(ρJ)·u³)/J2 = ½(ρ[f-1] m_c[f-1] + ρ[f] m_c[f]) · g³³_f u₃[f]
+template <class FT>
+__device__ __forceinline__ FT rho_mface(const VLev<FT>& V, const FT* rho, int o, int f) {
+  return FT(0.5) * (rho[o - 1] * V.mc[f - 1] + rho[o] * V.mc[f]);
+}
+
+// T_imp at one centre / face given the prepared slabs
+template <class FT>
+__device__ __forceinline__ void timp_center(const VLev<FT>& V, const ImpSlabs<FT>& S, int n, int v, int nv,
+                                            FT& rt, FT& et) {
+  int o = n * LVP + v;
+  FT mlo = FT(0), mhi = FT(0), hlo = FT(0), hhi = FT(0);
+  if (v > 0) { mlo = rho_mface(V, S.rho, o, v) * (V.g33f[v] * S.u3[o]); hlo = FT(0.5) * (S.h[o - 1] + S.h[o]); }
+  if (v < nv - 1) { mhi = rho_mface(V, S.rho, o + 1, v + 1) * (V.g33f[v + 1] * S.u3[o + 1]); hhi = FT(0.5) * (S.h[o] + S.h[o + 1]); }
+  rt = -(mhi - mlo) / V.mc[v];
+  et = -(mhi * hhi - mlo * hlo) / V.mc[v];
+}
+template <class FT>
+__device__ __forceinline__ FT timp_face(const Par<FT>& P, const VLev<FT>& V, const ImpSlabs<FT>& S, int n, int f, int nv) {
+  int o = n * LVP + f;
+  FT r = FT(0);
+  if (f > 0 && f < nv) {
+    r = -(V.dphif[f] - (S.phr[o] - S.phr[o - 1]) +
+          P.cp_d * (FT(0.5) * (S.thp[o - 1] + S.thp[o])) * (S.Pi[o] - S.Pi[o - 1]));
+  }
+  if (P.rayleigh) r += -V.brw[f] * S.u3[o];
+  return r;
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_t_imp(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                              const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  ImpSlabs<FT> S; imp_carve(sm, S);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  __syncthreads();
+  imp_thermo(P, hg, V, S);
+  __syncthreads();
+  FT* gT = Ytc + (size_t)h * 4 * 16 * nv;
+  FT* gF = Ytf + (size_t)h * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v < nv) {
+      FT rt, et; timp_center(V, S, n, v, nv, rt, et);
+      gT[(0 * 16 + n) * nv + v] = rt; gT[(1 * 16 + n) * nv + v] = FT(0);
+      gT[(2 * 16 + n) * nv + v] = FT(0); gT[(3 * 16 + n) * nv + v] = et;
+    }
+    if (v < nf) gF[n * nf + v] = timp_face(P, V, S, n, v, nv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobian coefficients at face f / centre v (manual_sparse_jacobian.jl:746-868, dry flat grid).
+template <class FT>
+struct FaceCoef { FT l, d, u, ur_lo, ur_hi, ue_lo, ue_hi, u1_lo, u1_hi, u2_lo, u2_hi; };
+
+template <class FT>
+__device__ __forceinline__ void center_coef(const VLev<FT>& V, const ImpSlabs<FT>& S, FT dtg, int n, int v, int nv,
+                                            FT& ru_lo, FT& ru_hi, FT& eu_lo, FT& eu_hi) {
+  int o = n * LVP + v;
+  ru_lo = ru_hi = eu_lo = eu_hi = FT(0);
+  if (v > 0) {  // face v (lower)
+    FT a = dtg * (rho_mface(V, S.rho, o, v) / V.mc[v]) * V.g33f[v];
+    ru_lo = a; eu_lo = a * (FT(0.5) * (S.h[o - 1] + S.h[o]));
+  }
+  if (v < nv - 1) {  // face v+1 (upper)
+    FT a = -dtg * (rho_mface(V, S.rho, o + 1, v + 1) / V.mc[v]) * V.g33f[v + 1];
+    ru_hi = a; eu_hi = a * (FT(0.5) * (S.h[o] + S.h[o + 1]));
+  }
+}
+
+template <class FT>
+__device__ __forceinline__ FaceCoef<FT> face_coef(const Par<FT>& P, const FT* hg, const VLev<FT>& V,
+                                                  const ImpSlabs<FT>& S, FT dtg, int n, int f, int nv) {
+  FaceCoef<FT> c;
+  FT beta = P.rayleigh ? V.brw[f] : FT(0);
+  c.l = c.u = c.ur_lo = c.ur_hi = c.ue_lo = c.ue_hi = c.u1_lo = c.u1_hi = c.u2_lo = c.u2_hi = FT(0);
+  c.d = dtg * (-beta) - FT(1);
+  if (f == 0 || f == nv) return c;  // ᶠgradᵥ rows vanish on the boundary faces
+  int o = n * LVP + f;  // centre f ("hi"); centre f-1 is o-1 ("lo")
+  const FT kap = P.R_d / P.cv_d;
+  FT rlo = S.rho[o - 1], rhi = S.rho[o];
+  FT rf = FT(0.5) * (rlo + rhi);
+  FT pg_lo = FT(1) / rf, pg_hi = -FT(1) / rf;
+  FT dp_lo = kap * (P.T_0 * P.cp_d - S.K[o - 1] - V.phic[f - 1]) + (P.R_d - kap * P.cv_d) * S.T[o - 1];
+  FT dp_hi = kap * (P.T_0 * P.cp_d - S.K[o] - V.phic[f]) + (P.R_d - kap * P.cv_d) * S.T[o];
+  FT buoy = P.cp_d * (FT(0.5) * (S.thv[o - 1] + S.thv[o])) * (S.Pi[o] - S.Pi[o - 1]) / rf;
+  c.ur_lo = dtg * (pg_lo * dp_lo + buoy * FT(0.5));
+  c.ur_hi = dtg * (pg_hi * dp_hi + buoy * FT(0.5));
+  c.ue_lo = dtg * pg_lo * kap;
+  c.ue_hi = dtg * pg_hi * kap;
+  FT x_lo = pg_lo * (-kap * rlo), x_hi = pg_hi * (-kap * rhi);
+  {  // ∂K/∂uₕ = CT12(uₕ)
+    FT g11 = hg[HG_GI11 * 16 + n], g12 = hg[HG_GI12 * 16 + n], g22 = hg[HG_GI22 * 16 + n];
+    FT a1 = (g11 * S.u1[o - 1] + g12 * S.u2[o - 1]) * V.sc2i[f - 1];
+    FT a2 = (g12 * S.u1[o - 1] + g22 * S.u2[o - 1]) * V.sc2i[f - 1];
+    FT b1 = (g11 * S.u1[o] + g12 * S.u2[o]) * V.sc2i[f];
+    FT b2 = (g12 * S.u1[o] + g22 * S.u2[o]) * V.sc2i[f];
+    c.u1_lo = dtg * x_lo * a1; c.u1_hi = dtg * x_hi * b1;
+    c.u2_lo = dtg * x_lo * a2; c.u2_hi = dtg * x_hi * b2;
+  }
+  // ∂K/∂u₃ rows: centre k has ½g³³u₃ at faces k and k+1
+  FT km = FT(0.5) * V.g33f[f - 1] * S.u3[o - 1], k0 = FT(0.5) * V.g33f[f] * S.u3[o], kp = FT(0.5) * V.g33f[f + 1] * S.u3[o + 1];
+  FT l = dtg * (x_lo * km), d = dtg * ((x_lo * k0 + x_hi * k0) - beta) - FT(1), u = dtg * (x_hi * kp);
+  // Schur complement with the scalar blocks (A11 = -I): centres f-1 and f
+  FT ru_lo_a, ru_hi_a, eu_lo_a, eu_hi_a, ru_lo_b, ru_hi_b, eu_lo_b, eu_hi_b;
+  center_coef(V, S, dtg, n, f - 1, nv, ru_lo_a, ru_hi_a, eu_lo_a, eu_hi_a);
+  center_coef(V, S, dtg, n, f, nv, ru_lo_b, ru_hi_b, eu_lo_b, eu_hi_b);
+  l += c.ur_lo * ru_lo_a + c.ue_lo * eu_lo_a;
+  d += c.ur_lo * ru_hi_a + c.ur_hi * ru_lo_b + c.ue_lo * eu_hi_a + c.ue_hi * eu_lo_b;
+  u += c.ur_hi * ru_hi_b + c.ue_hi * eu_hi_b;
+  c.l = l; c.d = d; c.u = u;
+  return c;
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_wfact(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                              const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT dtg, FT* jac) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  ImpSlabs<FT> S; imp_carve(sm, S);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  __syncthreads();
+  imp_thermo(P, hg, V, S);
+  __syncthreads();
+  FT* gj = jac + (size_t)h * JC_N * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v >= nf) continue;
+    FaceCoef<FT> c = face_coef(P, hg, V, S, dtg, n, v, nv);
+    size_t o = (size_t)n * nf + v, pl = (size_t)16 * nf;
+    gj[JC_L * pl + o] = c.l; gj[JC_D * pl + o] = c.d; gj[JC_U * pl + o] = c.u;
+    gj[JC_UR_LO * pl + o] = c.ur_lo; gj[JC_UR_HI * pl + o] = c.ur_hi;
+    gj[JC_UE_LO * pl + o] = c.ue_lo; gj[JC_UE_HI * pl + o] = c.ue_hi;
+    gj[JC_U1_LO * pl + o] = c.u1_lo; gj[JC_U1_HI * pl + o] = c.u1_hi;
+    gj[JC_U2_LO * pl + o] = c.u2_lo; gj[JC_U2_HI * pl + o] = c.u2_hi;
+    FT a = FT(0), b = FT(0), cc = FT(0), dd = FT(0);
+    if (v < nv) center_coef(V, S, dtg, n, v, nv, a, b, cc, dd);
+    gj[JC_RU_LO * pl + o] = a; gj[JC_RU_HI * pl + o] = b; gj[JC_EU_LO * pl + o] = cc; gj[JC_EU_HI * pl + o] = dd;
+  }
+}
+
+// Thomas algorithm over one column held in shared memory (stride-1 in v, node stride LVP):
+// overwrites u with c', rhs with the solution.
+template <class FT>
+__device__ __forceinline__ void thomas_column(const FT* l, const FT* d, FT* u, FT* rhs, int nf) {
+  FT cp = u[0] / d[0];
+  FT dp = rhs[0] / d[0];
+  u[0] = cp; rhs[0] = dp;
+  for (int i = 1; i < nf; ++i) {
+    FT li = l[i];
+    FT den = d[i] - li * cp;
+    cp = u[i] / den;
+    dp = (rhs[i] - li * dp) / den;
+    u[i] = cp; rhs[i] = dp;
+  }
+  FT x = dp;
+  for (int i = nf - 2; i >= 0; --i) {
+    x = rhs[i] - u[i] * x;
+    rhs[i] = x;
+  }
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_ldiv(Par<FT> P, const FT* __restrict__ jac, const FT* __restrict__ Rc,
+                                             const FT* __restrict__ Rf, FT* dYc, FT* dYf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
+  FT* rr = sm.take(SLAB); FT* r1 = sm.take(SLAB); FT* r2 = sm.take(SLAB); FT* re = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
+  const size_t pl = (size_t)16 * nf;
+  const FT* gRc = Rc + (size_t)h * 4 * 16 * nv;
+  load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
+  load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
+  __syncthreads();
+  const FT* gRf = Rf + (size_t)h * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, f = idx & 63;
+    if (f >= nf) continue;
+    size_t o = (size_t)n * nf + f;
+    int s = n * LVP + f;
+    FT rhs = gRf[o];
+    if (f > 0 && f < nv) {
+      rhs += gj[JC_UR_LO * pl + o] * rr[s - 1] + gj[JC_UR_HI * pl + o] * rr[s];
+      rhs += gj[JC_UE_LO * pl + o] * re[s - 1] + gj[JC_UE_HI * pl + o] * re[s];
+      rhs += gj[JC_U1_LO * pl + o] * r1[s - 1] + gj[JC_U1_HI * pl + o] * r1[s];
+      rhs += gj[JC_U2_LO * pl + o] * r2[s - 1] + gj[JC_U2_HI * pl + o] * r2[s];
+    }
+    sr[s] = rhs;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    int n = threadIdx.x;
+    thomas_column(sl + n * LVP, sd + n * LVP, su + n * LVP, sr + n * LVP, nf);
+  }
+  __syncthreads();
+  FT* gdc = dYc + (size_t)h * 4 * 16 * nv;
+  FT* gdf = dYf + (size_t)h * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    int s = n * LVP + v;
+    size_t o = (size_t)n * nf + v;
+    if (v < nf) gdf[o] = sr[s];
+    if (v < nv) {
+      FT x0 = sr[s], x1 = sr[s + 1];
+      gdc[(0 * 16 + n) * nv + v] = gj[JC_RU_LO * pl + o] * x0 + gj[JC_RU_HI * pl + o] * x1 - rr[s];
+      gdc[(1 * 16 + n) * nv + v] = -r1[s];
+      gdc[(2 * 16 + n) * nv + v] = -r2[s];
+      gdc[(3 * 16 + n) * nv + v] = gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1 - re[s];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// van Leer (Lin 1994, MonotoneLocalExtrema) face value of χ upwinded with u³ (abbreviations.jl:250-256)
+template <class FT>
+__device__ __forceinline__ FT vl_slope(FT am, FT a0, FT ap) {
+  FT d = ((a0 - am) + (ap - a0)) / FT(2);
+  FT mn = fmin_(fmin_(am, a0), ap), mx = fmax_(fmax_(am, a0), ap);
+  FT lim = fmin_(abs_(d), fmin_(FT(2) * (a0 - mn), FT(2) * (mx - a0)));
+  return d > FT(0) ? lim : (d < FT(0) ? -lim : FT(0));
+}
+// returns (upwinded χ - centred χ) at interior face f for contravariant velocity w
+template <class FT>
+__device__ __forceinline__ FT upwind_minus_central(const Par<FT>& P, const FT* chi, int o, int f, int nv, FT w) {
+  FT am = chi[o - 1], ap = chi[o];
+  FT cen = FT(0.5) * (am + ap);
+  FT up;
+  if (P.upwinding == 3 && f >= 2 && f <= nv - 2) {
+    if (w >= FT(0)) up = am + vl_slope(chi[o - 2], am, ap) / FT(2) * (FT(1) - w * P.dt);
+    else up = ap - vl_slope(am, ap, chi[o + 1]) / FT(2) * (FT(1) + w * P.dt);
+  } else {
+    up = w >= FT(0) ? am : ap;  // first order (also the FirstOrderOneSided boundary closure)
+  }
+  return up - cen;
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_t_post_imp(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                                   const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  ImpSlabs<FT> S; imp_carve(sm, S);
+  FT* flx = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  __syncthreads();
+  imp_thermo(P, hg, V, S);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, f = idx & 63;
+    if (f >= nf) continue;
+    int o = n * LVP + f;
+    FT r = FT(0);
+    if (f > 0 && f < nv) {
+      FT w = V.g33f[f] * S.u3[o];
+      r = rho_mface(V, S.rho, o, f) * w * upwind_minus_central(P, S.h, o, f, nv, w);
+    }
+    flx[o] = r;
+  }
+  __syncthreads();
+  FT* gT = Ytc + (size_t)h * 4 * 16 * nv;
+  FT* gF = Ytf + (size_t)h * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    int o = n * LVP + v;
+    if (v < nv) {
+      gT[(0 * 16 + n) * nv + v] = FT(0); gT[(1 * 16 + n) * nv + v] = FT(0); gT[(2 * 16 + n) * nv + v] = FT(0);
+      gT[(3 * 16 + n) * nv + v] = -(flx[o + 1] - flx[o]) / V.mc[v];
+    }
+    if (v < nf) gF[n * nf + v] = FT(0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused implicit stage (native stepper): given the DSSed stage state U this performs, in one pass
+// over the element, cache_imp! (u₃ boundary filter) → Wfact → T_imp! residual → ldiv! → U -= ΔU →
+// cache_imp! → T_post_imp! (U += dtγ·correction).  Output: U (in place).  temp == U on entry, so
+// the Newton residual is R = dtγ·T_imp(U) (ClimaTimeSteppers, one Newton iteration).
+template <class FT>
+__global__ void __launch_bounds__(NT) k_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                                  FT* Yc, FT* Yf, FT dtg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  ImpSlabs<FT> S; imp_carve(sm, S);
+  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
+  FT* rr = sm.take(SLAB); FT* rre = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  __syncthreads();
+  if (threadIdx.x < 16) { S.u3[threadIdx.x * LVP] = FT(0); S.u3[threadIdx.x * LVP + nv] = FT(0); }
+  __syncthreads();
+  imp_thermo(P, hg, V, S);
+  __syncthreads();
+  // residual of the scalars at centres: R = dtγ·T_imp
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v < nv) {
+      FT rt, et; timp_center(V, S, n, v, nv, rt, et);
+      rr[n * LVP + v] = dtg * rt; rre[n * LVP + v] = dtg * et;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, f = idx & 63;
+    if (f >= nf) continue;
+    int s = n * LVP + f;
+    FaceCoef<FT> c = face_coef(P, hg, V, S, dtg, n, f, nv);
+    FT rhs = dtg * timp_face(P, V, S, n, f, nv);
+    if (f > 0 && f < nv) {
+      rhs += c.ur_lo * rr[s - 1] + c.ur_hi * rr[s] + c.ue_lo * rre[s - 1] + c.ue_hi * rre[s];
+      // R_uₕ = dtγ·0 = 0 ⇒ no (u₃,uₕ) contribution and Δuₕ = 0
+    }
+    sl[s] = c.l; sd[s] = c.d; su[s] = c.u; sr[s] = rhs;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    int n = threadIdx.x;
+    thomas_column(sl + n * LVP, sd + n * LVP, su + n * LVP, sr + n * LVP, nf);
+  }
+  __syncthreads();
+  // back-substitute and update U (sl/sd reused for new ρ, ρe)
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    int s = n * LVP + v;
+    if (v < nv) {
+      FT a, b, c, d; center_coef(V, S, dtg, n, v, nv, a, b, c, d);
+      FT x0 = sr[s], x1 = sr[s + 1];
+      sl[s] = S.rho[s] - (a * x0 + b * x1 - rr[s]);
+      sd[s] = S.re[s] - (c * x0 + d * x1 - rre[s]);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    int s = n * LVP + v;
+    if (v < nv) { S.rho[s] = sl[s]; S.re[s] = sd[s]; }
+    if (v < nf) S.u3[s] = (v == 0 || v == nv) ? FT(0) : S.u3[s] - sr[s];
+  }
+  __syncthreads();
+  FT* gYc = Yc + (size_t)h * 4 * 16 * nv;
+  FT* gYf = Yf + (size_t)h * 16 * nf;
+  if (P.upwinding != 0) {
+    imp_thermo(P, hg, V, S);  // cache_imp!(U) after the Newton update
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+      int n = idx >> 6, f = idx & 63;
+      if (f >= nf) continue;
+      int o = n * LVP + f;
+      FT r = FT(0);
+      if (f > 0 && f < nv) {
+        FT w = V.g33f[f] * S.u3[o];
+        r = rho_mface(V, S.rho, o, f) * w * upwind_minus_central(P, S.h, o, f, nv, w);
+      }
+      su[o] = r;
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    int s = n * LVP + v;
+    if (v < nv) {
+      gYc[(0 * 16 + n) * nv + v] = S.rho[s];
+      FT e = S.re[s];
+      if (P.upwinding != 0) e += dtg * (-(su[s + 1] - su[s]) / V.mc[v]);
+      gYc[(3 * 16 + n) * nv + v] = e;
+    }
+    if (v < nf) gYf[n * nf + v] = S.u3[s];
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,83 @@
+"""Parameter and numerics bundles consumed by the dycore (POD mirrors of the reference's types).
+
+``DycoreParams`` is the subset of ``ClimaAtmosParameters`` (src/parameters/Parameters.jl:541-568,
+src/parameters/create_parameters.jl:200-224) the dry/tracer dycore reads.  Default values are the
+ClimaParams 1.1.4 defaults [UPSTREAM-RECALL]; in a drop-in deployment they are read from the live
+``params`` object and passed across the C-ABI (include/b200_dycore.h: ``b200_params``).
+"""
+from __future__ import annotations
+
+import dataclasses
+
+
+@dataclasses.dataclass
+class DycoreParams:
+    R_d: float = 8.3144598 / 0.02897
+    kappa_d: float = 2.0 / 7.0
+    T_0: float = 273.16
+    grav: float = 9.81
+    Omega: float = 7.2921159e-5
+    planet_radius: float = 6.371e6
+    MSLP: float = 1.01325e5
+    p_ref_theta: float = 1.0e5
+    T_surf_ref: float = 290.0
+    T_min_ref: float = 220.0
+    T_min_sgs: float = 150.0  # model_getters.jl:224 fallback value
+    # sponges (types.jl:782-866)
+    zd_rayleigh: float = 15000.0
+    alpha_rayleigh_uh: float = 0.0
+    alpha_rayleigh_w: float = 1.0
+    zd_viscous: float = 15000.0
+    kappa_2_sponge: float = 1.0e6
+
+    @property
+    def cp_d(self):
+        return self.R_d / self.kappa_d
+
+    @property
+    def cv_d(self):
+        return self.cp_d - self.R_d
+
+
+@dataclasses.dataclass
+class DycoreNumerics:
+    """``AtmosNumerics`` + model switches relevant to the path (types.jl:1850, :499-503)."""
+
+    dt: float = 400.0
+    hyperdiff: bool = True
+    nu4_vorticity_coeff: float = 0.1857  # default_config.yml:30-32
+    prandtl_number: float = 0.2  # default_config.yml:33-35 (ν₄_scalar = ν₄_vorticity / Pr)
+    divergence_damping_factor: float = 5.0  # default_config.yml:218-220
+    rayleigh_sponge: bool = False
+    viscous_sponge: bool = False
+    energy_upwinding: str = "vanleer_limiter"  # default_config.yml:324-326
+    held_suarez: bool = False
+
+
+# ARS343 tableau (Ascher–Ruuth–Spiteri 1997 §2.7), as used by ClimaTimeSteppers' IMEXAlgorithm
+def ars343():
+    g = 0.4358665215084590
+    a42 = 0.5529291480359398
+    a43 = a42
+    b1 = -3 * g**2 / 2 + 4 * g - 1 / 4
+    b2 = 3 * g**2 / 2 - 5 * g + 5 / 4
+    a31 = (
+        (1 - 9 * g / 2 + 3 * g**2 / 2) * a42
+        + (11 / 4 - 21 * g / 2 + 15 * g**2 / 4) * a43
+        - 7 / 2
+        + 13 * g
+        - 9 * g**2 / 2
+    )
+    a32 = (
+        (-1 + 9 * g / 2 - 3 * g**2 / 2) * a42
+        + (-11 / 4 + 21 * g / 2 - 15 * g**2 / 4) * a43
+        + 4
+        - 25 * g / 2
+        + 9 * g**2 / 2
+    )
+    a41 = 1 - a42 - a43
+    a_exp = [[0, 0, 0, 0], [g, 0, 0, 0], [a31, a32, 0, 0], [a41, a42, a43, 0]]
+    a_imp = [[0, 0, 0, 0], [0, g, 0, 0], [0, (1 - g) / 2, g, 0], [0, b1, b2, g]]
+    b_exp = [0, b1, b2, g]
+    b_imp = [0, b1, b2, g]
+    return a_exp, a_imp, b_exp, b_imp, g

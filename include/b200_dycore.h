@@ -1,0 +1,144 @@
+/* b200_dycore.h — C-ABI of libb200dycore.so: the B200-native dry/tracer dynamical-core step.
+ *
+ * Drop-in boundary: these entry points are what a `ccall` glue module binds in place of the
+ * ClimaODEFunction hooks the reference wires at src/simulation/integrator.jl:215-225 (see
+ * INTEGRATION.md for the Julia stub).  Conventions:
+ *   - plain pointers and sizes only; every field pointer is a DEVICE pointer owned by the caller
+ *     (`pointer(parent(Fields.field_values(Y.c)))`), never retained beyond the call unless
+ *     registered at create time; `stream` is a cudaStream_t passed as void*;
+ *   - every call is asynchronous on `stream`; no hidden device synchronisation;
+ *   - return 0 on success, <0 on error (message via b200_last_error); nothing throws;
+ *   - FT is selected at create time (ft_bytes = 4 or 8); state pointers are FT*;
+ *   - field layout is ClimaCore VIJFH: parent array (Nv, Ni, Nj, Nf, Nh), first index fastest,
+ *     i.e. C order [h][f][j][i][v].  Y.c: Nf = 4 (ρ, uₕ₁, uₕ₂, ρe_tot), Nv levels;
+ *     Y.f: Nf = 1 (u₃), Nv+1 levels.  Nq = 4 only.
+ *   - there is NO CPU fallback: every compute entry point requires a CUDA device.
+ */
+#ifndef B200_DYCORE_H
+#define B200_DYCORE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+/* Sizes. Replaces what the glue reads from `axes(Y.c)` (ClimaCore Spaces). */
+typedef struct {
+  int32_t nh;        /* local elements (this rank) */
+  int32_t nh_ghost;  /* ghost elements appended after the local ones (0 for 1 GPU) */
+  int32_t nv;        /* centre levels (z_elem); faces = nv + 1; nv + 1 <= 64 */
+  int32_t nq;        /* GLL nodes per direction; must be 4 */
+  int32_t ft_bytes;  /* 4 = Float32, 8 = Float64 */
+  int32_t deep;      /* 1 = DeepSphericalGlobalGeometry, 0 = shallow (grids.jl:64-68) */
+} b200_dims;
+
+/* Geometry, copied from the live ClimaCore objects (HOST pointers, double precision; the
+ * library converts to FT).  Horizontal arrays are [nh + nh_ghost][4][4] in (j, i) order. */
+typedef struct {
+  const double* dxdxi;  /* [nh+g][j][i][2][2]: ∂x_a/∂ξ_b, local (east,north) basis, at radius */
+  const double* J2;     /* [nh+g][j][i] horizontal Jacobian at radius */
+  const double* lat;    /* [nh+g][j][i] degrees */
+  const double* gll_w;  /* [4] quadrature weights */
+  const double* gll_D;  /* [4][4] D[i][k] = l'_k(ξ_i) */
+  const double* z_c;    /* [nv]   */
+  const double* z_f;    /* [nv+1] */
+  const double* dz_c;   /* [nv]   vertical ∂z/∂ξ³ at centres */
+  const double* dz_f;   /* [nv+1] vertical ∂z/∂ξ³ at faces */
+  double radius;
+  double z_max;
+} b200_geometry;
+
+/* Connectivity in ClimaCore Topology2D form (HOST pointers, 0-based).  Element ids >= nh refer
+ * to ghost elements.  Replaces Topologies.Topology2D tables used by Spaces.weighted_dss!. */
+typedef struct {
+  const int32_t* interior_faces;      /* [n_faces][5]: e1, f1, e2, f2, reversed */
+  int32_t n_faces;
+  const int32_t* local_vertices;      /* [n_lv][2]: elem, vert */
+  const int32_t* local_vertex_offset; /* [n_verts + 1] */
+  int32_t n_verts;
+  /* multi-rank halo (all NULL/0 on one GPU) */
+  int32_t n_neighbors;
+  const int32_t* neighbor_ranks;   /* [n_neighbors] */
+  const int32_t* send_offset;      /* [n_neighbors + 1] into send_elems */
+  const int32_t* send_elems;       /* local element ids whose perimeter is sent */
+  const int32_t* recv_offset;      /* [n_neighbors + 1] into ghost slots (0-based ghost index) */
+  const int64_t* elem_gid;         /* [nh + nh_ghost] global element id (summation order) */
+} b200_topology;
+
+/* Parameters: subset of ClimaAtmosParameters + numerics read by the dycore
+ * (src/parameters/create_parameters.jl:200-224, src/types.jl:499-503,782-866). */
+typedef struct {
+  double R_d, cp_d, cv_d, T_0, grav, Omega, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs;
+  double dt;                        /* p.dt (van Leer Courant number) */
+  double nu4_vorticity, nu4_scalar; /* ν₄ (hyperdiffusion.jl:21-28); 0,0 disables hyperdiff */
+  double divergence_damping_factor;
+  int32_t hyperdiff;
+  int32_t rayleigh_sponge; double zd_rayleigh, alpha_rayleigh_uh, alpha_rayleigh_w;
+  int32_t viscous_sponge;  double zd_viscous, kappa_2_sponge;
+  int32_t energy_upwinding; /* 0 none, 1 first_order, 3 vanleer_limiter */
+} b200_params;
+
+/* Optional device pointers to p.precomputed fields written by b200_cache_imp (any may be NULL).
+ * (src/cache/precomputed_quantities.jl:53-61) */
+typedef struct {
+  void* u_c;    /* ᶜu   C123: [nh][3][16][nv]   */
+  void* u3_f;   /* ᶠu³  CT3:  [nh][1][16][nv+1] */
+  void* K_c;    /* ᶜK   */
+  void* T_c;    /* ᶜT   */
+  void* p_c;    /* ᶜp   */
+  void* h_tot_c;/* ᶜh_tot */
+} b200_cacheptrs;
+
+int b200_create(b200_ctx** out, const b200_dims*, const b200_geometry*, const b200_topology*,
+                const b200_params*, const void* nccl_unique_id /* NULL for 1 GPU */, int rank,
+                int nranks);
+int b200_destroy(b200_ctx*);
+const char* b200_last_error(void);
+/* 128-byte NCCL unique id for the DSS halo communicator (rank 0 calls, host broadcasts). */
+int b200_nccl_unique_id(void* out128);
+
+/* cache_imp! — set_implicit_precomputed_quantities! (precomputed_quantities.jl:698-831):
+ * applies the u₃ boundary filter to Yf IN PLACE and fills the optional precomputed fields. */
+int b200_cache_imp(b200_ctx*, void* Yc, void* Yf, const b200_cacheptrs* out, void* stream);
+/* T_exp_T_lim! — remaining_tendency! (remaining_tendency.jl:48-58). Ylc/Ylf may be NULL (dry). */
+int b200_t_exp_lim(b200_ctx*, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc,
+                   const void* Yf, double t, void* stream);
+/* T_imp! — implicit_tendency! (implicit/implicit_tendency.jl:36-98). */
+int b200_t_imp(b200_ctx*, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double t,
+               void* stream);
+/* Wfact — update_jacobian! (implicit/jacobian.jl:74-75 → manual_sparse_jacobian.jl:1850). */
+int b200_wfact(b200_ctx*, const void* Yc, const void* Yf, double dtgamma, double t, void* stream);
+/* ldiv! — invert_jacobian! (implicit/jacobian.jl:78-82 → manual_sparse_jacobian.jl:1897). */
+int b200_ldiv(b200_ctx*, void* dYc, void* dYf, const void* Rc, const void* Rf, void* stream);
+/* T_post_imp! — correct_implicit_advection_tendency! (implicit_tendency.jl:322-339). */
+int b200_t_post_imp(b200_ctx*, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double t,
+                    void* stream);
+/* dss! — Spaces.weighted_dss! (constrain_state.jl:59-64; remaining_tendency.jl:18-21).
+ * fields[k]: device pointer; nf[k]: components; is_face[k]: 0 centre / 1 face;
+ * kind[k]: 0 scalars, 1 = (c12 pair followed by nf-2 scalars), 2 = (ρ, c12 pair, scalars…). */
+int b200_dss(b200_ctx*, void* const* fields, const int32_t* nf, const int32_t* is_face,
+             const int32_t* kind, int32_t nfields, void* stream);
+/* Fused stage increment U = u + Σ_j c_j T_j over a state of (Yc, Yf) (ClimaTimeSteppers
+ * fused_increment!). */
+int b200_axpy_n(b200_ctx*, void* Uc, void* Uf, const void* uc, const void* uf, int32_t n,
+                const void* const* Tc, const void* const* Tf, const double* coef, void* stream);
+/* One full IMEX-ARK ARS343 step with one Newton iteration per implicit stage, using the hooks
+ * above in the order of DESIGN.md "Step trace" (role of CTS.step!, solve.jl:62,125).  The
+ * state (Yc, Yf) is advanced in place. `fused` selects the fused implicit-stage kernel. */
+int b200_step_ars343(b200_ctx*, void* Yc, void* Yf, double t, int32_t fused, void* stream);
+/* Host-only: build the unique-perimeter-node CSR from the Topology2D tables (no device needed).
+ * mem entries are elem*16 + j*4 + i.  Used by the bit-exact index-map tests; the same routine
+ * feeds b200_create.  Returns -1 if the output capacities are too small. */
+int b200_build_dss_csr(const b200_topology*, int32_t* off_out, int32_t cap_nodes, int32_t* mem_out,
+                       int32_t cap_mem, int32_t* nnodes, int32_t* nmem);
+/* Debug: the CSR actually held by a context (after dropping nodes without a local member). */
+int b200_debug_dss_csr(b200_ctx*, const int32_t** off, const int32_t** mem, int32_t* nnodes,
+                       int32_t* nmem);
+/* Number of kernels launched by this context since creation (bench evidence). */
+int64_t b200_launch_count(b200_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,621 @@
+"""CPU ORACLE — test infrastructure only (NOT part of the product path).
+
+NumPy restatement of the reference's dry dynamical-core time step.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this module; the product package never does.
+
+PARITY UNPINNED.  The arithmetic of this path lives in un-vendored Julia packages
+(ClimaCore 0.15.1, ClimaTimeSteppers 0.10.6, Thermodynamics 1.3.0 — pins from
+``.buildkite/Manifest-v1.11.toml``), none of which is under /root/reference, and Julia is not
+installed here, so the reference cannot be executed and the repo holds no golden vectors for this
+path (its hot-path unit tests are ``@test_skip`` placeholders).  What pins this
+oracle instead: the structural identities the reference *does* test (tests/test_oracle_*.py):
+χ≡1 consistency (test/prognostic_equations/tracer_mass_consistency_tests.jl:52-84),
+impenetrability (advection_tests.jl:46-58), corrected+central == upwind
+(correct_implicit_advection_tests.jl:40-67), sponge profiles
+(test/parameterized_tendencies/sponge.jl:44-80), operator identities
+(docs/src/discretization.md:76-94), a finite-difference check of the analytic Jacobian and
+conservation to round-off.
+
+Every function cites the reference file:line it restates.  Operators are applied *literally*, in
+the order the reference composes them and with full per-point metric arrays (no factorisation),
+so that the optimised CUDA kernels are checked against an independent formulation.
+
+Array conventions: centre fields ``[h, j, i, v]`` (v = 0..Nv-1), face fields ``[h, j, i, f]``
+(f = 0..Nv; face f is the lower face of centre f).  State ``Yc[h, 4, j, i, v]`` =
+(ρ, uₕ₁, uₕ₂, ρe_tot), ``Yf[h, 1, j, i, f]`` = u₃ (all covariant components).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class Geom:
+    """Per-point LocalGeometry pieces (ClimaCore ``Geometry.LocalGeometry`` [UPSTREAM-RECALL]):
+    J, WJ, gⁱʲ, gᵢⱼ at one staggering, built as the product of the horizontal 2-D geometry and
+    the vertical 1-D geometry with the deep-atmosphere scale factor ((R+z)/R)."""
+
+    def __init__(self, grid, z, dz, FT):
+        R = grid.radius
+        s = (R + z) / R if grid.deep else np.ones_like(z)
+        A = grid.dxdxi  # [h,j,i,a,b]
+        G = np.einsum("...ab,...ac->...bc", A, A)  # covariant 2-D metric
+        Ginv = np.linalg.inv(G)
+        s2 = (s * s)[None, None, None, :]
+        c = lambda a: np.ascontiguousarray(a, dtype=FT)
+        self.J = c(grid.J2[..., None] * s2 * dz[None, None, None, :])
+        self.WJ = c(grid.W[..., None] * grid.J2[..., None] * s2 * dz[None, None, None, :])
+        self.g11 = c(Ginv[..., 0, 0, None] / s2)
+        self.g12 = c(Ginv[..., 0, 1, None] / s2)
+        self.g22 = c(Ginv[..., 1, 1, None] / s2)
+        self.g33 = c(np.broadcast_to(1.0 / (dz * dz), self.J.shape))
+        self.c11 = c(G[..., 0, 0, None] * s2)
+        self.c12 = c(G[..., 0, 1, None] * s2)
+        self.c22 = c(G[..., 1, 1, None] * s2)
+        self.c33 = c(np.broadcast_to(dz * dz, self.J.shape))
+        self.z = c(np.broadcast_to(z, self.J.shape))
+        # local (east, north) physical components ↔ contravariant: u^a = (A_k⁻¹)·(u, v)
+        Ainv = np.linalg.inv(A)
+        self.Ainv = c(Ainv[..., None, :, :] / s[None, None, None, :, None, None])  # [h,j,i,v,a,b]
+
+
+class Oracle:
+    def __init__(self, grid, params, numerics, FT=np.float64):
+        self.grid, self.P, self.N, self.FT = grid, params, numerics, FT
+        g = grid
+        self.nv = g.nv
+        self.D = np.asarray(g.D, dtype=FT)
+        self.c = Geom(g, g.z_c, g.dz_c, FT)
+        self.f = Geom(g, g.z_f, g.dz_f, FT)
+        from climaatmos_jl_b200.grid import dss_node_csr  # index tables are data, not arithmetic
+
+        self.dss_offs, self.dss_mem = dss_node_csr(g.topology, g.nq)
+        # cache.jl:179-183: Φ = grav·z ; ᶠgradᵥ_ᶜΦ
+        self.Phi = np.asarray(params.grav * self.c.z, dtype=FT)
+        self.gradv_Phi = self.gradv_c2f(self.Phi)
+        # cache.jl:318-343 compute_coriolis (deep: 2Ω ẑ projected; shallow: 2Ω sin φ ŵ)
+        Om = params.Omega
+        lat = np.radians(g.lat)[..., None]
+        fu, fv, fw = 0.0 * lat, 2 * Om * np.cos(lat), 2 * Om * np.sin(lat)
+        self.f3_c = np.asarray(fw / g.dz_c[None, None, None, :], dtype=FT)  # CT3 = w / (∂z/∂ξ³)
+        if g.deep:
+            Ai = self.f.Ainv
+            self.f1_f = np.asarray(Ai[..., 0, 0] * fu + Ai[..., 0, 1] * fv, dtype=FT)
+            self.f2_f = np.asarray(Ai[..., 1, 0] * fu + Ai[..., 1, 1] * fv, dtype=FT)
+        else:
+            self.f1_f = self.f2_f = None
+        h = g.node_horizontal_length_scale()
+        # hyperdiffusion.jl:21-28
+        self.nu4_vort = FT(numerics.nu4_vorticity_coeff * h**3)
+        self.nu4_scalar = FT(self.nu4_vort / FT(numerics.prandtl_number))
+        # DSS weights: WJ / Σ_collocated WJ (horizontal; docs/src/discretization.md:139-154)
+        WJ2 = g.W * g.J2
+        tot = WJ2.copy()
+        for n in range(len(self.dss_offs) - 1):
+            m = self.dss_mem[self.dss_offs[n] : self.dss_offs[n + 1]]
+            ssum = sum(WJ2[e, j, i] for (e, i, j) in m)
+            for e, i, j in m:
+                tot[e, j, i] = ssum
+        self.dss_w = np.asarray(WJ2 / tot, dtype=FT)
+
+    # ------------------------------------------------------------------ horizontal SEM (A.1)
+    def dx(self, a):  # Σ_k D[i,k] a[h,j,k,v]
+        return np.einsum("ik,hjkv->hjiv", self.D, a)
+
+    def dy(self, a):
+        return np.einsum("jk,hkiv->hjiv", self.D, a)
+
+    def dxT(self, a):  # Σ_k D[k,i] a[h,j,k,v]
+        return np.einsum("ki,hjkv->hjiv", self.D, a)
+
+    def dyT(self, a):
+        return np.einsum("kj,hkiv->hjiv", self.D, a)
+
+    def grad(self, a):
+        return self.dx(a), self.dy(a)
+
+    def wgrad(self, a, G):
+        W = G.WJ / G.J
+        return -self.dxT(W * a) / W, -self.dyT(W * a) / W
+
+    def div(self, u1c, u2c, G):  # contravariant components in
+        return (self.dx(G.J * u1c) + self.dy(G.J * u2c)) / G.J
+
+    def wdiv(self, u1c, u2c, G):
+        return -(self.dxT(G.WJ * u1c) + self.dyT(G.WJ * u2c)) / G.WJ
+
+    def curl3(self, u1, u2, G):  # covariant (u1,u2) → contravariant 3
+        return (self.dx(u2) - self.dy(u1)) / G.J
+
+    def curl12(self, u3, G):  # covariant u3 → contravariant (1,2)
+        return self.dy(u3) / G.J, -self.dx(u3) / G.J
+
+    def wcurl3(self, u1, u2, G):
+        W = G.WJ / G.J
+        return (self.dyT(W * u1) - self.dxT(W * u2)) / G.WJ
+
+    def wcurl12(self, u3, G):
+        W = G.WJ / G.J
+        return -self.dyT(W * u3) / G.WJ, self.dxT(W * u3) / G.WJ
+
+    @staticmethod
+    def ct12(u1, u2, G):  # CT12(C12): u^a = g^{ab} u_b (flat: no vertical coupling)
+        return G.g11 * u1 + G.g12 * u2, G.g12 * u1 + G.g22 * u2
+
+    @staticmethod
+    def c12(v1, v2, G):
+        return G.c11 * v1 + G.c12 * v2, G.c12 * v1 + G.c22 * v2
+
+    def split_div(self, F1, F2, psi, G):
+        """docs/src/discretization.md:245-253: ½ wdiv(Fψ) + ½[ψ wdiv(F) + F·grad ψ]."""
+        gx, gy = self.grad(psi)
+        half = self.FT(0.5)
+        return half * self.wdiv(F1 * psi, F2 * psi, G) + half * (psi * self.wdiv(F1, F2, G) + F1 * gx + F2 * gy)
+
+    # ------------------------------------------------------------------ vertical FD (A.2)
+    def interp_f2c(self, a):
+        return self.FT(0.5) * (a[..., :-1] + a[..., 1:])
+
+    def interp_c2f(self, a):  # Extrapolate BCs (abbreviations.jl:173-176)
+        out = np.empty(a.shape[:-1] + (a.shape[-1] + 1,), dtype=a.dtype)
+        out[..., 1:-1] = self.FT(0.5) * (a[..., :-1] + a[..., 1:])
+        out[..., 0] = a[..., 0]
+        out[..., -1] = a[..., -1]
+        return out
+
+    def winterp_c2f(self, w, a):  # abbreviations.jl:184-187 ; discretization.md:171
+        return self.interp_c2f(w * a) / self.interp_c2f(w)
+
+    def gradv_c2f(self, a):  # SetGradient(0) BCs (abbreviations.jl:206-209)
+        out = np.zeros(a.shape[:-1] + (a.shape[-1] + 1,), dtype=a.dtype)
+        out[..., 1:-1] = a[..., 1:] - a[..., :-1]
+        return out
+
+    def advdiv_f2c(self, u3c):  # SetValue(0) BCs (abbreviations.jl:106-109); CT3 in
+        Ju = self.f.J * u3c
+        Ju = Ju.copy()
+        Ju[..., 0] = 0
+        Ju[..., -1] = 0
+        return (Ju[..., 1:] - Ju[..., :-1]) / self.c.J
+
+    def curlv_c2f(self, u1, u2):  # SetCurl(0) BCs (abbreviations.jl:216-219) → CT12
+        o1 = np.zeros(u1.shape[:-1] + (u1.shape[-1] + 1,), dtype=u1.dtype)
+        o2 = np.zeros_like(o1)
+        o1[..., 1:-1] = -(u2[..., 1:] - u2[..., :-1]) / self.f.J[..., 1:-1]
+        o2[..., 1:-1] = (u1[..., 1:] - u1[..., :-1]) / self.f.J[..., 1:-1]
+        return o1, o2
+
+    def upwind1(self, v, a):  # UpwindBiasedProductC2F; boundary faces one-sided (flux zeroed later)
+        lo = np.concatenate([a[..., :1], a], -1)
+        hi = np.concatenate([a, a[..., -1:]], -1)
+        return v * np.where(v >= 0, lo, hi)
+
+    def lin_vanleer(self, v, a, dt):
+        """LinVanLeerC2F, MonotoneLocalExtrema constraint, FirstOrderOneSided BCs
+        (abbreviations.jl:250-256; Lin 1994) [UPSTREAM-RECALL]: interior faces 2..Nv-2 use the
+        limited slope of the upwind cell with the Courant correction (1 ∓ v³dt); the two faces
+        next to each boundary fall back to first-order upwinding."""
+        FT = self.FT
+        out = self.upwind1(v, a)
+        nv = a.shape[-1]
+        if nv < 4:
+            return out
+
+        def slope(am, a0, ap):
+            d = ((a0 - am) + (ap - a0)) / FT(2)
+            mn = np.minimum(np.minimum(am, a0), ap)
+            mx = np.maximum(np.maximum(am, a0), ap)
+            lim = np.minimum(np.abs(d), np.minimum(FT(2) * (a0 - mn), FT(2) * (mx - a0)))
+            return np.sign(d) * lim
+
+        # face f (2..nv-2): a⁻⁻=a[f-2], a⁻=a[f-1], a⁺=a[f], a⁺⁺=a[f+1]
+        amm, am, ap, app = a[..., :-3], a[..., 1:-2], a[..., 2:-1], a[..., 3:]
+        vf = v[..., 2:-2]
+        pos = am + slope(amm, am, ap) / FT(2) * (FT(1) - vf * FT(dt))
+        neg = ap - slope(am, ap, app) / FT(2) * (FT(1) + vf * FT(dt))
+        out[..., 2:-2] = vf * np.where(vf >= 0, pos, neg)
+        return out
+
+    # ------------------------------------------------------------------ thermodynamics (A.4)
+    def exner(self, p):
+        return (p / self.FT(self.P.p_ref_theta)) ** self.FT(self.P.kappa_d)
+
+    def T_ref(self, p):  # refstate_thermodynamics.jl air_temperature_reference
+        P = self.P
+        return self.FT(P.T_min_ref) + self.FT(P.T_surf_ref - P.T_min_ref) * self.exner(p) ** 7
+
+    def theta_vr(self, p):
+        return self.T_ref(p) / self.exner(p)
+
+    def phi_r(self, p):
+        P, FT = self.P, self.FT
+        Pi = self.exner(p)
+        return -FT(P.cp_d) * (FT(P.T_min_ref) * np.log(Pi) + FT(P.T_surf_ref - P.T_min_ref) / FT(7) * (Pi**7 - FT(1)))
+
+    def sd_r(self, p):
+        P, FT = self.P, self.FT
+        return FT(P.cp_d) * (self.T_ref(p) - FT(P.T_0)) + self.phi_r(p)
+
+    # ------------------------------------------------------------------ sponges
+    def beta_rayleigh(self, z, alpha):  # rayleigh_sponge.jl:7-28
+        P = self.P
+        zeta = np.sin(np.pi * ((z - P.zd_rayleigh) / (self.grid.z_max - P.zd_rayleigh) / 2)) ** 2
+        return np.asarray(np.where(z > P.zd_rayleigh, alpha, 0.0) * zeta, dtype=self.FT)
+
+    def beta_viscous(self, z):  # viscous_sponge.jl:9-26
+        P = self.P
+        zeta = np.sin(np.pi * ((z - P.zd_viscous) / (self.grid.z_max - P.zd_viscous) / 2)) ** 2
+        return np.asarray(np.where(z > P.zd_viscous, P.kappa_2_sponge, 0.0) * zeta, dtype=self.FT)
+
+    # ------------------------------------------------------------------ cache_imp!
+    def set_implicit_precomputed_quantities(self, Yc, Yf):
+        """precomputed_quantities.jl:698-831 (dry branch). Mutates Yf at the boundary faces
+        (set_velocity_at_surface!/top!, :486-554) and returns the precomputed dict."""
+        FT, P, c, f = self.FT, self.P, self.c, self.f
+        rho, u1, u2, rhoe = Yc[:, 0], Yc[:, 1], Yc[:, 2], Yc[:, 3]
+        u3 = Yf[:, 0]
+        # :707 ᶠuₕ³ = ᶠwinterp(ρJ, CT3(uₕ)); flat grid: g³ʰ = 0 → CT3(uₕ) = 0
+        uh3 = self.winterp_c2f(rho * c.J, np.zeros_like(rho))
+        u3[..., 0] = -uh3[..., 0] / f.g33[..., 0]
+        u3[..., -1] = -uh3[..., -1] / f.g33[..., -1]
+        # :567-572 set_velocity_quantities!
+        u3c = self.interp_f2c(u3)  # covariant, interpolated component-wise
+        fu3 = uh3 + f.g33 * u3  # ᶠu³
+        # utilities.jl:194-209 compute_kinetic
+        c1, c2 = self.ct12(u1, u2, c)
+        K = FT(0.5) * ((u1 * c1 + u2 * c2) + self.interp_f2c(u3 * (f.g33 * u3)) + FT(2) * (FT(0) * u3c))
+        e_int = rhoe / rho - K - self.Phi
+        T = np.maximum(FT(P.T_min_sgs), FT(P.T_0) + e_int / FT(P.cv_d))
+        h_tot = rhoe / rho + FT(P.R_d) * T
+        p = rho * FT(P.R_d) * T
+        return dict(u1=u1, u2=u2, u3c=u3c, fu3=fu3, K=K, T=T, p=p, h_tot=h_tot)
+
+    # ------------------------------------------------------------------ T_imp!
+    def vertical_transport(self, rho, fu3, chi, dt, upwinding):
+        """implicit_tendency.jl:120-143."""
+        rJf = self.interp_c2f(rho * self.c.J) / self.f.J
+        if upwinding == "none":
+            return -self.advdiv_f2c(rJf * fu3 * self.interp_c2f(chi))
+        if upwinding == "first_order":
+            return -self.advdiv_f2c(rJf * self.upwind1(fu3, chi))
+        if upwinding == "vanleer_limiter":
+            return -self.advdiv_f2c(rJf * self.lin_vanleer(fu3, chi, dt))
+        raise ValueError(upwinding)
+
+    def theta_v(self, T, p):
+        return T / self.exner(p)
+
+    def implicit_tendency(self, Yc, Yf, pc):
+        """implicit_tendency.jl:36-98 → implicit_vertical_advection_tendency! :185-298 (dry)."""
+        FT, P = self.FT, self.P
+        Ytc, Ytf = np.zeros_like(Yc), np.zeros_like(Yf)
+        rho = Yc[:, 0]
+        Ytc[:, 0] -= self.advdiv_f2c(self.interp_c2f(rho * self.c.J) / self.f.J * pc["fu3"])
+        Ytc[:, 3] += self.vertical_transport(rho, pc["fu3"], pc["h_tot"], self.N.dt, "none")
+        p, T = pc["p"], pc["T"]
+        dth = self.theta_v(T, p) - self.theta_vr(p)
+        Ytf[:, 0] -= self.gradv_Phi - self.gradv_c2f(self.phi_r(p)) + FT(P.cp_d) * self.interp_c2f(dth) * self.gradv_c2f(self.exner(p))
+        if self.N.rayleigh_sponge:
+            Ytf[:, 0] += -self.beta_rayleigh(self.f.z, P.alpha_rayleigh_w) * Yf[:, 0]
+        return Ytc, Ytf
+
+    def correct_implicit_advection_tendency(self, Yc, Yf, pc):
+        """implicit_tendency.jl:322-339 (T_post_imp!)."""
+        Ytc, Ytf = np.zeros_like(Yc), np.zeros_like(Yf)
+        rho = Yc[:, 0]
+        up = self.vertical_transport(rho, pc["fu3"], pc["h_tot"], self.N.dt, self.N.energy_upwinding)
+        ce = self.vertical_transport(rho, pc["fu3"], pc["h_tot"], self.N.dt, "none")
+        Ytc[:, 3] = up - ce
+        return Ytc, Ytf
+
+    # ------------------------------------------------------------------ Wfact / ldiv!
+    def update_jacobian(self, Yc, Yf, pc, dtg):
+        """manual_sparse_jacobian.jl:713-870 (dry, flat): band blocks stored by diagonals.
+
+        Returned dict: bidiagonal centre-row blocks as (lo, hi) = entries at faces (k, k+1);
+        bidiagonal face-row blocks as (lo, hi) = entries at centres (f-1, f) (zero on boundary
+        rows); tridiagonal (u₃,u₃) as (l, d, u)."""
+        FT, P, c, f = self.FT, self.P, self.c, self.f
+        dtg = FT(dtg)
+        rho, u1, u2 = Yc[:, 0], Yc[:, 1], Yc[:, 2]
+        u3 = Yf[:, 0]
+        K, p, T, h_tot = pc["K"], pc["p"], pc["T"], pc["h_tot"]
+        kappa = FT(P.R_d) / FT(P.cv_d)  # ᶜkappa_m_field! :653-662 (dry)
+        z = lambda a: np.zeros_like(a)
+        # :746-754
+        dK_duh = self.ct12(u1, u2, c)  # Diag(CT12(uₕ)ᵀ)
+        g33u3 = f.g33 * u3
+        dK_du3 = (FT(0.5) * g33u3[..., :-1], FT(0.5) * g33u3[..., 1:])  # ᶜinterp_matrix⋅Diag(CT3(u₃))
+        # :756 ᶠp_grad_matrix = Diag(-1/ᶠinterp(ρ)) ⋅ ᶠgradᵥ_matrix  (boundary rows zero)
+        rf = self.interp_c2f(rho)
+        pg_lo, pg_hi = z(rf), z(rf)
+        pg_lo[..., 1:-1] = FT(1) / rf[..., 1:-1]
+        pg_hi[..., 1:-1] = -FT(1) / rf[..., 1:-1]
+        # :758-759 ᶜadvection_matrix = -(ᶜadvdivᵥ_matrix) ⋅ Diag(ᶠinterp(ρJ)/ᶠJ)
+        rJf = self.interp_c2f(rho * c.J) / f.J
+        Jf = f.J.copy()
+        Jf[..., 0] = 0
+        Jf[..., -1] = 0  # SetValue(0) rows/cols of the divergence matrix
+        adv_lo = Jf[..., :-1] / c.J * rJf[..., :-1]
+        adv_hi = -Jf[..., 1:] / c.J * rJf[..., 1:]
+        # :767-768, :783-785
+        hf = self.interp_c2f(h_tot)
+        A_rho_u3 = (dtg * adv_lo * f.g33[..., :-1], dtg * adv_hi * f.g33[..., 1:])
+        A_rhoe_u3 = (dtg * adv_lo * (hf * f.g33)[..., :-1], dtg * adv_hi * (hf * f.g33)[..., 1:])
+        # :816-825
+        thv = self.theta_v(T, p)
+        Pi = self.exner(p)
+        dp_drho = kappa * (FT(P.T_0) * FT(P.cp_d) - K - self.Phi) + (FT(P.R_d) - kappa * FT(P.cv_d)) * T
+        buoy = FT(P.cp_d) * self.interp_c2f(thv) * self.gradv_c2f(Pi) / rf  # diag on faces
+        im_lo, im_hi = z(rf), z(rf)  # ᶠinterp_matrix (Extrapolate rows)
+        im_lo[..., 1:-1] = FT(0.5)
+        im_hi[..., 1:-1] = FT(0.5)
+        im_hi[..., 0] = FT(1)
+        im_lo[..., -1] = FT(1)
+        cl = lambda a: np.concatenate([a[..., :1], a], -1)  # centre value at (f-1), padded
+        ch = lambda a: np.concatenate([a, a[..., -1:]], -1)  # centre value at f, padded
+        A_u3_rho = (
+            dtg * (pg_lo * cl(dp_drho) + buoy * im_lo),
+            dtg * (pg_hi * ch(dp_drho) + buoy * im_hi),
+        )
+        A_u3_rhoe = (dtg * pg_lo * kappa, dtg * pg_hi * kappa)
+        # :855-868
+        mk = lambda a: -kappa * a
+        A_u3_uh = tuple(
+            (dtg * pg_lo * cl(mk(rho) * dK_duh[a]), dtg * pg_hi * ch(mk(rho) * dK_duh[a])) for a in range(2)
+        )
+        X_lo, X_hi = pg_lo * cl(mk(rho)), pg_hi * ch(mk(rho))  # rows f, cols centres f-1, f
+        dKlo, dKhi = dK_du3  # rows k: faces k, k+1
+        l = X_lo * cl(dKlo)  # via centre f-1 → face f-1
+        d = X_lo * cl(dKhi) + X_hi * ch(dKlo)
+        u = X_hi * ch(dKhi)  # via centre f → face f+1
+        beta = self.beta_rayleigh(f.z, P.alpha_rayleigh_w) if self.N.rayleigh_sponge else z(rf)
+        A_u3_u3 = (dtg * l, dtg * (d - beta) - FT(1), dtg * u)
+        return dict(rho_u3=A_rho_u3, rhoe_u3=A_rhoe_u3, u3_rho=A_u3_rho, u3_rhoe=A_u3_rhoe, u3_uh=A_u3_uh, u3_u3=A_u3_u3)
+
+    def ldiv(self, Jm, Rc, Rf):
+        """jacobian.jl:78-82 → BlockArrowheadSolve(ρ, ρe_tot; alg₂ = BlockLowerTriangularSolve(uₕ))
+        (manual_sparse_jacobian.jl:579-584) [UPSTREAM-RECALL]: Schur complement onto u₃, Thomas
+        solve, back-substitution.  Scalar diagonal blocks are -I, (uₕ,uₕ) = -I (:476-481)."""
+        FT = self.FT
+        dYc, dYf = np.zeros_like(Rc), np.zeros_like(Rf)
+        Rrho, R1, R2, Rre = Rc[:, 0], Rc[:, 1], Rc[:, 2], Rc[:, 3]
+        R3 = Rf[:, 0]
+        cl = lambda a: np.concatenate([a[..., :1] * 0, a], -1)  # centre (f-1) value, 0 outside
+        ch = lambda a: np.concatenate([a, a[..., -1:] * 0], -1)
+        fl = lambda a: np.concatenate([a[..., :1] * 0, a[..., :-1]], -1)  # face f-1
+        fh = lambda a: np.concatenate([a[..., 1:], a[..., -1:] * 0], -1)  # face f+1
+        l, d, u = [a.copy() for a in Jm["u3_u3"]]
+        # Schur: A22 + A21·A12 (A11 = -I)
+        for a21, a12 in ((Jm["u3_rho"], Jm["rho_u3"]), (Jm["u3_rhoe"], Jm["rhoe_u3"])):
+            lo21, hi21 = a21  # row f: centres f-1, f
+            lo12, hi12 = a12  # row k: faces k, k+1
+            l += lo21 * cl(lo12)
+            d += lo21 * cl(hi12) + hi21 * ch(lo12)
+            u += hi21 * ch(hi12)
+        # velocities first: Δuₕ = -R_uₕ
+        dYc[:, 1], dYc[:, 2] = -R1, -R2
+        rhs = R3.copy()
+        for a21, r in ((Jm["u3_rho"], Rrho), (Jm["u3_rhoe"], Rre)):
+            rhs += a21[0] * cl(r) + a21[1] * ch(r)
+        for a in range(2):
+            r = (R1, R2)[a]
+            rhs += Jm["u3_uh"][a][0] * cl(r) + Jm["u3_uh"][a][1] * ch(r)
+        # Thomas algorithm
+        n = rhs.shape[-1]
+        cp = np.zeros_like(rhs)
+        dp = np.zeros_like(rhs)
+        cp[..., 0] = u[..., 0] / d[..., 0]
+        dp[..., 0] = rhs[..., 0] / d[..., 0]
+        for i in range(1, n):
+            den = d[..., i] - l[..., i] * cp[..., i - 1]
+            cp[..., i] = u[..., i] / den
+            dp[..., i] = (rhs[..., i] - l[..., i] * dp[..., i - 1]) / den
+        x = np.zeros_like(rhs)
+        x[..., -1] = dp[..., -1]
+        for i in range(n - 2, -1, -1):
+            x[..., i] = dp[..., i] - cp[..., i] * x[..., i + 1]
+        dYf[:, 0] = x
+        # back-substitute scalars: -Δρ + A12 Δu₃ = R  ⇒ Δρ = A12 Δu₃ - R
+        for idx, a12, r in ((0, Jm["rho_u3"], Rrho), (3, Jm["rhoe_u3"], Rre)):
+            dYc[:, idx] = a12[0] * x[..., :-1] + a12[1] * x[..., 1:] - r
+        return dYc, dYf
+
+    # ------------------------------------------------------------------ DSS
+    def weighted_dss(self, fields):
+        """Spaces.weighted_dss! (constrain_state.jl:59-64; discretization.md:139-154).
+        ``fields`` = list of (kind, arrays): kind 'scalar' → [a]; 'c12' → [u1, u2] summed in the
+        local (east, north) basis via ∂x/∂ξ [UPSTREAM-RECALL dss_transform]. In place."""
+        A = np.asarray(self.grid.dxdxi, dtype=self.FT)
+        Ainv = np.asarray(np.linalg.inv(self.grid.dxdxi), dtype=self.FT)
+        w = self.dss_w
+        offs, mem = self.dss_offs, self.dss_mem
+        E, I, Jn = mem[:, 0], mem[:, 1], mem[:, 2]
+        seg = np.repeat(np.arange(len(offs) - 1), np.diff(offs))
+        nn = len(offs) - 1
+        for kind, arrs in fields:
+            if kind == "scalar":
+                comps = [w[E, Jn, I, None] * arrs[0][E, Jn, I, :]]
+            else:
+                # covariant → physical: (u, v) = (A⁻¹)ᵀ (u1, u2)
+                a1, a2 = arrs[0][E, Jn, I, :], arrs[1][E, Jn, I, :]
+                Ai = Ainv[E, Jn, I]
+                uu = Ai[:, 0, 0, None] * a1 + Ai[:, 1, 0, None] * a2
+                vv = Ai[:, 0, 1, None] * a1 + Ai[:, 1, 1, None] * a2
+                comps = [w[E, Jn, I, None] * uu, w[E, Jn, I, None] * vv]
+            sums = []
+            for cmp in comps:
+                s = np.zeros((nn, cmp.shape[1]), dtype=self.FT)
+                # fixed summation order: members in table order
+                maxm = int(np.max(np.diff(offs)))
+                for q in range(maxm):
+                    sel = offs[:-1] + q
+                    ok = sel < offs[1:]
+                    s[ok] += cmp[sel[ok]]
+                sums.append(s[seg])
+            if kind == "scalar":
+                arrs[0][E, Jn, I, :] = sums[0]
+            else:
+                Am = A[E, Jn, I]
+                arrs[0][E, Jn, I, :] = Am[:, 0, 0, None] * sums[0] + Am[:, 1, 0, None] * sums[1]
+                arrs[1][E, Jn, I, :] = Am[:, 0, 1, None] * sums[0] + Am[:, 1, 1, None] * sums[1]
+
+    def dss_state(self, Yc, Yf):
+        self.weighted_dss(
+            [("scalar", [Yc[:, 0]]), ("c12", [Yc[:, 1], Yc[:, 2]]), ("scalar", [Yc[:, 3]]), ("scalar", [Yf[:, 0]])]
+        )
+
+    # ------------------------------------------------------------------ T_exp_T_lim!
+    def vector_laplacian(self, u1, u2, u3, G):
+        """hyperdiffusion.jl:141 / :273-277: C123(wgradₕ(divₕ(u))) - C123(wcurlₕ(C123(curlₕ(u))))
+        returning (graddiv_12, curlcurl_123) separately so callers can scale the grad-div part."""
+        c1, c2 = self.ct12(u1, u2, G)
+        gd1, gd2 = self.wgrad(self.div(c1, c2, G), G)
+        w3 = self.curl3(u1, u2, G)  # CT3
+        w1, w2 = self.curl12(u3, G)  # CT12
+        k1, k2 = self.c12(w1, w2, G)
+        k3 = G.c33 * w3
+        e3c = self.wcurl3(k1, k2, G)
+        e1c, e2c = self.wcurl12(k3, G)
+        e1, e2 = self.c12(e1c, e2c, G)
+        e3 = G.c33 * e3c
+        return (gd1, gd2), (e1, e2, e3)
+
+    def remaining_tendency(self, Yc, Yf, pc):
+        """remaining_tendency.jl:48-58 (dry): returns (Ytc, Ytf); Yₜ_lim ≡ 0 without tracers."""
+        FT, P, N, c, f = self.FT, self.P, self.N, self.c, self.f
+        Ytc, Ytf = np.zeros_like(Yc), np.zeros_like(Yf)
+        rho, u1, u2, rhoe = Yc[:, 0], Yc[:, 1], Yc[:, 2], Yc[:, 3]
+        u3 = Yf[:, 0]
+        K, T, p, h_tot, u3c, fu3 = pc["K"], pc["T"], pc["p"], pc["h_tot"], pc["u3c"], pc["fu3"]
+        cp_d = FT(P.cp_d)
+        # ---- horizontal_dynamics_tendency! advection.jl:36-91
+        c1, c2 = self.ct12(u1, u2, c)  # horizontal contravariant components of ᶜu
+        one = np.ones_like(rho)
+        Ytc[:, 0] -= self.split_div(rho * c1, rho * c2, one, c)
+        Ytc[:, 3] -= self.split_div(rho * c1, rho * c2, h_tot, c)
+        Pi = self.exner(p)
+        dth = self.theta_v(T, p) - self.theta_vr(p)
+        g1 = self.grad(K + self.Phi - self.phi_r(p))
+        gPi, gth, gthPi = self.grad(Pi), self.grad(dth), self.grad(dth * Pi)
+        for a in range(2):
+            Ytc[:, 1 + a] -= g1[a] + cp_d * (dth * gPi[a] + gthPi[a] - Pi * gth[a]) / FT(2)
+        # ---- hyperdiffusion_tendency! remaining_tendency.jl:15-24
+        if N.hyperdiff:
+            (gd, cc) = self.vector_laplacian(u1, u2, u3c, c)  # prep :141
+            L1, L2, L3 = gd[0] - cc[0], gd[1] - cc[1], -cc[2]
+            s_d = cp_d * (T - FT(P.T_0)) + self.Phi - self.sd_r(p)  # :142-147
+            gs = self.grad(s_d)
+            Ls = self.wdiv(*self.ct12(gs[0], gs[1], c), c)
+            self.weighted_dss([("c12", [L1, L2]), ("scalar", [L3]), ("scalar", [Ls])])  # :18-21
+            (gd, cc) = self.vector_laplacian(L1, L2, L3, c)  # apply :273-277
+            ddf = FT(N.divergence_damping_factor)
+            Q1, Q2, Q3 = ddf * gd[0] - cc[0], ddf * gd[1] - cc[1], -cc[2]
+            Ytc[:, 1] -= self.nu4_vort * Q1
+            Ytc[:, 2] -= self.nu4_vort * Q2
+            Ytf[:, 0] -= self.nu4_vort * self.winterp_c2f(c.J * rho, Q3)
+            gL = self.grad(Ls)
+            gL = self.ct12(gL[0], gL[1], c)
+            Ytc[:, 3] -= self.nu4_scalar * self.wdiv(rho * gL[0], rho * gL[1], c)  # :291,307
+        # ---- explicit_vertical_advection_tendency! advection.jl:205-290
+        w3 = self.wcurl3(u1, u2, c)  # ᶜω³ :228
+        o1, o2 = self.curlv_c2f(u1, u2)  # ᶠω¹² :233
+        a1, a2 = self.wcurl12(u3, f)  # :237
+        o1, o2 = o1 + a1, o2 + a2
+        if self.f1_f is not None:  # deep atmosphere :273-278
+            t1, t2 = self.f1_f + o1, self.f2_f + o2
+        else:
+            t1, t2 = o1, o2
+        V = self.interp_c2f(rho * c.J) * fu3  # CT3 component
+        # (CT12 × CT3) → C12: J (ω²V, -ω¹V)
+        x1, x2 = f.J * (t2 * V), -f.J * (t1 * V)
+        tot3 = self.f3_c + w3
+        Ytc[:, 1] -= self.interp_f2c(x1) / (rho * c.J) + (-c.J * tot3 * c2)  # CT3 × CT12 → C12
+        Ytc[:, 2] -= self.interp_f2c(x2) / (rho * c.J) + (c.J * tot3 * c1)
+        ub1, ub2 = self.interp_c2f(c1), self.interp_c2f(c2)
+        Ytf[:, 0] -= f.J * (t1 * ub2 - t2 * ub1) + self.gradv_c2f(K)  # CT12 × CT12 → C3
+        # ---- additional_tendency! remaining_tendency.jl:166-171
+        if N.rayleigh_sponge:
+            b = self.beta_rayleigh(c.z, P.alpha_rayleigh_uh)
+            Ytc[:, 1] += -b * u1
+            Ytc[:, 2] += -b * u2
+        if N.viscous_sponge:  # viscous_sponge.jl:138-175
+            bc, bf = self.beta_viscous(c.z), self.beta_viscous(f.z)
+            (gd, cc) = self.vector_laplacian(u1, u2, np.zeros_like(u1), c)
+            Ytc[:, 1] += bc * (gd[0] - cc[0])
+            Ytc[:, 2] += bc * (gd[1] - cc[1])
+            g3 = self.grad(u3)
+            Ytf[:, 0] += bf * self.wdiv(*self.ct12(g3[0], g3[1], f), f)
+            gs = self.grad(cp_d * (T - FT(P.T_0)) + self.Phi)
+            gs = self.ct12(gs[0], gs[1], c)
+            Ytc[:, 3] += bc * self.wdiv(rho * gs[0], rho * gs[1], c)
+        return Ytc, Ytf
+
+    # ------------------------------------------------------------------ ARS343 step
+    def step(self, Yc, Yf, trace=None):
+        """One IMEX-ARK (ARS343) step with one Newton iteration per implicit stage, hook order
+        reconstructed from ClimaTimeSteppers 0.10.6 [UPSTREAM-RECALL] (DESIGN.md
+        "Step trace").  Returns the new (Yc, Yf)."""
+        from climaatmos_jl_b200.params import ars343
+
+        FT = self.FT
+        a_exp, a_imp, b_exp, b_imp, gam = ars343()
+        dt = self.N.dt
+        uc, uf = Yc, Yf
+        Texp, Timp = [None] * 4, [None] * 4
+        log = (lambda s: trace.append(s)) if trace is not None else (lambda s: None)
+
+        def increment(i_coefs_exp, i_coefs_imp):
+            Uc, Uf = uc.copy(), uf.copy()
+            for j in range(4):
+                if i_coefs_exp[j] != 0 and Texp[j] is not None:
+                    Uc += FT(dt * i_coefs_exp[j]) * Texp[j][0]
+                    Uf += FT(dt * i_coefs_exp[j]) * Texp[j][1]
+                if i_coefs_imp[j] != 0 and Timp[j] is not None:
+                    Uc += FT(dt * i_coefs_imp[j]) * Timp[j][0]
+                    Uf += FT(dt * i_coefs_imp[j]) * Timp[j][1]
+            return Uc, Uf
+
+        for i in range(4):
+            Uc, Uf = increment(a_exp[i], a_imp[i])
+            if i != 0:
+                self.dss_state(Uc, Uf)
+                log("dss")
+            if a_imp[i][i] != 0:
+                dtg = dt * a_imp[i][i]
+                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
+                log("cache_imp")
+                tc, tf = Uc.copy(), Uf.copy()
+                Jm = self.update_jacobian(Uc, Uf, pc, dtg)
+                log("wfact")
+                Rc, Rf = self.implicit_tendency(Uc, Uf, pc)
+                log("t_imp")
+                Rc = tc + FT(dtg) * Rc - Uc
+                Rf = tf + FT(dtg) * Rf - Uf
+                dc, df = self.ldiv(Jm, Rc, Rf)
+                log("ldiv")
+                Uc -= dc
+                Uf -= df
+                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
+                log("cache_imp")
+                if self.N.energy_upwinding != "none":
+                    pc_, pf_ = self.correct_implicit_advection_tendency(Uc, Uf, pc)
+                    log("t_post_imp")
+                    Uc += FT(dtg) * pc_
+                    Uf += FT(dtg) * pf_
+                self.dss_state(Uc, Uf)
+                log("dss")
+                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
+                log("cache_imp")
+                Timp[i] = ((Uc - tc) / FT(dtg), (Uf - tf) / FT(dtg))
+            else:
+                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
+                log("cache_imp")
+            Texp[i] = self.remaining_tendency(Uc, Uf, pc)
+            log("t_exp")
+        uc, uf = increment(b_exp, b_imp)
+        self.dss_state(uc, uf)
+        log("dss")
+        self.set_implicit_precomputed_quantities(uc, uf)
+        log("cache")
+        return uc, uf
