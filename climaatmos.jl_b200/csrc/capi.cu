@@ -520,21 +520,34 @@ extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, cons
 
 // ---------------------------------------------------------------------------------------------
 template <class FT>
-static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, cudaStream_t s) {
+static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
   const bool hd = c->prm.hyperdiff != 0;
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
-  if (Ylc) CK(cudaMemsetAsync(Ylc, 0, c->nc() * sizeof(FT), s));
-  if (Ylf) CK(cudaMemsetAsync(Ylf, 0, c->nf() * sizeof(FT), s));
-  k_texp_a<FT><<<c->dims.nh, NT, smem_slabs<FT>(22), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                        (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
-  LAUNCH_CHECK(c);
-  if (hd) {
+  if (phase == 0) {
+    k_texp_a<FT><<<c->dims.nh, NT, smem_slabs<FT>(22), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                          (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+    LAUNCH_CHECK(c);
+  } else if (phase == 1 && hd) {
     DssField F = {c->H, 4, 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
+  } else if (phase == 2 && hd) {
     k_texp_c<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                           (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
   }
+  return 0;
+}
+extern "C" int b200_t_exp_phase(b200_ctx* c, int32_t phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, void* stream) {
+  return c->ft == 4 ? impl_t_exp_phase<float>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream)
+                    : impl_t_exp_phase<double>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
+}
+
+template <class FT>
+static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, cudaStream_t s) {
+  if (Ylc) CK(cudaMemsetAsync(Ylc, 0, c->nc() * sizeof(FT), s));
+  if (Ylf) CK(cudaMemsetAsync(Ylf, 0, c->nf() * sizeof(FT), s));
+  for (int ph = 0; ph < 3; ++ph)
+    if (impl_t_exp_phase<FT>(c, ph, Ytc, Ytf, Yc, Yf, s)) return -1;
   return 0;
 }
 extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, double,

@@ -83,7 +83,8 @@ __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K
   Pt<FT> o;
   FT etot = rhoe / rho;
   FT eint = etot - K - Phi;
-  o.T = fmax_(P.T_min_sgs, P.T_0 + eint / P.cv_d);
+  // e_int = cv_d (T − T_0) − R_d T_0  (docs/src/thermodynamics.md:103-111)
+  o.T = fmax_(P.T_min_sgs, P.T_0 + (eint + P.R_d * P.T_0) / P.cv_d);
   o.h = etot + P.R_d * o.T;
   o.p = rho * P.R_d * o.T;
   o.Pi = pow_(o.p / P.p0, P.kappa);

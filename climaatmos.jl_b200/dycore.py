@@ -134,6 +134,14 @@ class AtmosSimulation:
                    "b200_t_exp_lim")
         return Yt
 
+    def remaining_tendency_phase(self, phase, Yt, Y):
+        """Profiling aid: one phase of T_exp_T_lim! (0 pre-DSS kernel, 1 DSS of ∇² fields, 2 hyperdiffusion apply)."""
+        capi.check(self.lib.b200_t_exp_phase(self.ctx, int(phase), _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), self._stream()),
+                   "b200_t_exp_phase")
+
+    def remaining_tendency_phase_a(self, Yt, Y):
+        self.remaining_tendency_phase(0, Yt, Y)
+
     def implicit_tendency(self, Yt, Y, t=0.0):
         """T_imp! (implicit_tendency.jl:36-98)."""
         capi.check(self.lib.b200_t_imp(self.ctx, _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), float(t), self._stream()), "b200_t_imp")

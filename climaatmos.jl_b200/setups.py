@@ -60,7 +60,8 @@ def _barowave_values(z, lat, lon, params, perturb=True, deep=True):
 
 
 def _assemble(grid, params, T, p, u, v):
-    """prognostic_variables.jl:44-62: ρ = p/(R_d T); uₕ = C12(UV(u,v)); ρe_tot = ρ(cv_d(T-T_0)+K+Φ)."""
+    """prognostic_variables.jl:44-62: ρ = p/(R_d T); uₕ = C12(UV(u,v)); ρe_tot = ρ(e_int + K + Φ) with the
+    dry internal energy e_int = cv_d (T − T_0) − R_d T_0 (docs/src/thermodynamics.md:103-111)."""
     FT = grid.FT
     nel, nq, nv = grid.nelems, grid.nq, grid.nv
     rho = p / (params.R_d * T)
@@ -69,7 +70,7 @@ def _assemble(grid, params, T, p, u, v):
     u1 = A[..., 0, 0] * u + A[..., 1, 0] * v  # (∂x/∂ξ)ᵀ·(u, v)
     u2 = A[..., 0, 1] * u + A[..., 1, 1] * v
     z = grid.z_c[None, None, None, :]
-    e_tot = params.cv_d * (T - params.T_0) + 0.5 * (u * u + v * v) + params.grav * z
+    e_tot = params.cv_d * (T - params.T_0) - params.R_d * params.T_0 + 0.5 * (u * u + v * v) + params.grav * z
     Yc = np.zeros((nel, 4, nq, nq, nv), dtype=FT)
     Yc[:, 0] = rho
     Yc[:, 1] = u1

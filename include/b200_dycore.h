@@ -127,6 +127,10 @@ int b200_axpy_n(b200_ctx*, void* Uc, void* Uf, const void* uc, const void* uf, i
  * above in the order of DESIGN.md "Step trace" (role of CTS.step!, solve.jl:62,125).  The
  * state (Yc, Yf) is advanced in place. `fused` selects the fused implicit-stage kernel. */
 int b200_step_ars343(b200_ctx*, void* Yc, void* Yf, double t, int32_t fused, void* stream);
+/* Profiling aid: run ONE phase of b200_t_exp_lim — 0: pre-DSS kernel (Yₜ partial + ∇² fields),
+ * 1: DSS of the ∇² fields, 2: hyperdiffusion apply kernel. */
+int b200_t_exp_phase(b200_ctx*, int32_t phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf,
+                     void* stream);
 /* Host-only: build the unique-perimeter-node CSR from the Topology2D tables (no device needed).
  * mem entries are elem*16 + j*4 + i.  Used by the bit-exact index-map tests; the same routine
  * feeds b200_create.  Returns -1 if the output capacities are too small. */

@@ -265,7 +265,9 @@ class Oracle:
         c1, c2 = self.ct12(u1, u2, c)
         K = FT(0.5) * ((u1 * c1 + u2 * c2) + self.interp_f2c(u3 * (f.g33 * u3)) + FT(2) * (FT(0) * u3c))
         e_int = rhoe / rho - K - self.Phi
-        T = np.maximum(FT(P.T_min_sgs), FT(P.T_0) + e_int / FT(P.cv_d))
+        # Thermodynamics.jl air_temperature with the dry-air reference internal energy −R_d·T_0
+        # (docs/src/thermodynamics.md:103-111): e_int = cv_d (T − T_0) − R_d T_0
+        T = np.maximum(FT(P.T_min_sgs), FT(P.T_0) + (e_int + FT(P.R_d) * FT(P.T_0)) / FT(P.cv_d))
         h_tot = rhoe / rho + FT(P.R_d) * T
         p = rho * FT(P.R_d) * T
         return dict(u1=u1, u2=u2, u3c=u3c, fu3=fu3, K=K, T=T, p=p, h_tot=h_tot)

@@ -1,0 +1,147 @@
+"""CPU tests: grid construction, quadrature, topology, SFC, partition and stepper host logic."""
+import re
+import os
+import numpy as np
+import pytest
+
+from climaatmos_jl_b200 import grid as G
+from climaatmos_jl_b200 import partition, params, dycore
+
+
+def test_gll_quadrature_and_derivative_matrix():
+    x, w = G.gll_points_weights(4)
+    assert np.allclose(x, [-1, -1 / np.sqrt(5), 1 / np.sqrt(5), 1])
+    assert np.allclose(w, [1 / 6, 5 / 6, 5 / 6, 1 / 6])
+    D = G.differentiation_matrix(x)
+    # exact for polynomials up to degree 3; rows sum to zero
+    for p in range(4):
+        assert np.allclose(D @ x**p, p * x ** max(p - 1, 0) if p else 0 * x, atol=1e-13)
+    assert np.abs(D.sum(axis=1)).max() < 1e-14
+
+
+@pytest.mark.parametrize("ne", [2, 3, 6])
+def test_cubed_sphere_area_and_counts(ne):
+    g = G.make_sphere_grid(h_elem=ne, z_elem=4)
+    assert g.nelems == 6 * ne * ne
+    area = np.sum(g.J2 * g.W)
+    assert abs(area / (4 * np.pi * g.radius**2) - 1) < 5e-4 / ne**4 + 1e-6
+    t = g.topology
+    assert len(t.interior_faces) == 12 * ne * ne  # every element has 4 faces, each shared by 2
+    assert len(t.local_vertex_offset) - 1 == 6 * ne * ne + 2
+    counts = np.diff(t.local_vertex_offset)
+    assert sorted(np.unique(counts)) == [3, 4] and (counts == 3).sum() == 8  # cube corners
+    # all panels right-handed ⇒ shared faces are always traversed in opposite directions
+    assert np.all(t.interior_faces[:, 4] == 1)
+
+
+def test_collocated_nodes_coincide_in_space():
+    g = G.make_sphere_grid(h_elem=3, z_elem=4)
+    off, mem = G.dss_node_csr(g.topology, 4)
+    for n in range(len(off) - 1):
+        pts = np.array([g.xyz[e, j, i] for e, i, j in mem[off[n]:off[n + 1]]])
+        assert np.abs(pts - pts[0]).max() < 1e-12
+    # every perimeter node appears exactly once
+    keys = mem[:, 0] * 16 + mem[:, 2] * 4 + mem[:, 1]
+    assert len(np.unique(keys)) == len(keys) == g.nelems * 12
+
+
+def test_spacefillingcurve_selfconsistent():
+    """Mirror of the reference's SFC test (test/grids.jl:6-21)."""
+    order = G.spacefillingcurve(3)
+    index = {c: k for k, c in enumerate(order)}
+    for k, c in enumerate(order):
+        assert index[c] == k
+    linear = [(x, y, p) for p in range(6) for y in range(3) for x in range(3)]
+    assert sorted(order) == sorted(linear) and order != linear
+    # consecutive elements inside a panel are face neighbours (locality of the curve)
+    for a, b in zip(order[:8], order[1:9]):
+        assert abs(a[0] - b[0]) + abs(a[1] - b[1]) == 1
+
+
+def test_vertical_stretching():
+    zf = G.hyperbolic_tangent_stretching(60000.0, 63, 30.0)
+    assert zf[0] == 0 and zf[-1] == 60000.0 and abs((zf[1] - zf[0]) - 30.0) < 1e-6
+    assert np.all(np.diff(zf) > 0) and np.all(np.diff(np.diff(zf)) > -1e-9)
+    g = G.make_sphere_grid(h_elem=2, z_elem=10)
+    assert np.allclose(g.dz_f[1:-1], np.diff(g.z_c)) and np.isclose(g.dz_f[0], g.dz_c[0])
+
+
+def test_ars343_tableau():
+    a_exp, a_imp, b_exp, b_imp, gam = params.ars343()
+    c = [0, gam, (1 + gam) / 2, 1]
+    for i in range(4):
+        assert abs(sum(a_exp[i]) - c[i]) < 1e-14 and abs(sum(a_imp[i]) - c[i]) < 1e-14
+    assert abs(sum(b_exp) - 1) < 1e-14 and b_exp == b_imp
+    assert a_imp[3] == b_imp  # stiffly accurate
+
+
+def test_sypd_definition():
+    # solve.jl:40-45: 365-day years per wall-clock day
+    assert np.isclose(dycore.sypd(365 * 86400.0, 86400.0), 1.0)
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_partition_is_consistent(nranks):
+    g = G.make_sphere_grid(h_elem=4, z_elem=4)
+    parts = [partition.partition_grid(g, r, nranks) for r in range(nranks)]
+    assert sum(p.nh for p in parts) == g.nelems
+    assert max(p.nh for p in parts) - min(p.nh for p in parts) <= 1
+    owned = np.concatenate([p.elems_ext[: p.nh] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(g.nelems))
+    for p in parts:
+        for k, q in enumerate(p.neighbor_ranks):
+            s = p.elems_ext[p.send_elems[p.send_offset[k]:p.send_offset[k + 1]]]
+            pq = parts[q]
+            kk = list(pq.neighbor_ranks).index(p.rank)
+            r = pq.elems_ext[pq.nh + pq.recv_offset[kk]: pq.nh + pq.recv_offset[kk + 1]]
+            assert np.array_equal(s, r)
+        # every node with a local member keeps all of its members
+        off, mem = G.dss_node_csr(G.Topology2D(p.nh + p.nh_ghost, [], p.interior_faces, p.local_vertices, p.local_vertex_offset), 4)
+        goff, gmem = G.dss_node_csr(g.topology, 4)
+        glob = {}
+        for n in range(len(goff) - 1):
+            m = frozenset((int(e), int(i), int(j)) for e, i, j in gmem[goff[n]:goff[n + 1]])
+            for x in m:
+                glob[x] = m
+        for n in range(len(off) - 1):
+            m = frozenset((int(p.elems_ext[e]), int(i), int(j)) for e, i, j in mem[off[n]:off[n + 1]])
+            if any(e < p.nh for e, _, _ in mem[off[n]:off[n + 1]]):
+                assert m == glob[next(iter(m))]
+
+
+def test_header_symbols_exported(lib):
+    """The C-ABI library loads and exports every function include/b200_dycore.h declares."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "b200_dycore.h")).read()
+    names = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+@pytest.mark.parametrize("ne", [2, 5, 6])
+def test_dss_index_map_bit_exact(lib, ne):
+    """DSS element/node index maps built by the library from ClimaCore-shaped Topology2D tables are
+    bit-identical to the independent Python construction."""
+    from climaatmos_jl_b200 import capi
+
+    g = G.make_sphere_grid(h_elem=ne, z_elem=4)
+    off, mem = capi.build_dss_csr(g.topology)
+    o2, m2 = G.dss_node_csr(g.topology, 4)
+    assert np.array_equal(off, o2)
+    assert np.array_equal(mem, m2[:, 0] * 16 + m2[:, 2] * 4 + m2[:, 1])
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    """No CPU fallback: creating a context without a CUDA device is an error, not a silent path."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from climaatmos_jl_b200 import capi
+
+    g = G.make_sphere_grid(h_elem=2, z_elem=4)
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        capi.create_context(g, params.DycoreParams(), params.DycoreNumerics())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dycore.AtmosSimulation(h_elem=2, z_elem=4)
