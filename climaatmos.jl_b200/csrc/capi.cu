@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -14,6 +15,8 @@
 #include "kernels_dss.cuh"
 #include "kernels_explicit.cuh"
 #include "kernels_implicit.cuh"
+#include "kernels_reg.cuh"
+#include "kernels_row.cuh"
 
 using namespace b200;
 
@@ -93,6 +96,7 @@ struct b200_ctx {
   void *sendbuf = nullptr, *ghostbuf = nullptr;  // sized for the largest DSS call
   size_t halo_cap = 0;
   int64_t launches = 0;
+  int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   size_t nc() const { return (size_t)dims.nh * 4 * 16 * dims.nv; }
   size_t nf() const { return (size_t)dims.nh * 16 * (dims.nv + 1); }
 };
@@ -214,6 +218,12 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
     }
   CK(cudaMalloc(&c->d_vlev, sizeof(V)));
   CK(cudaMemcpy(c->d_vlev, &V, sizeof(V), cudaMemcpyHostToDevice));
+  {  // derivative matrices in the constant bank (register-resident kernels)
+    float mf[32]; double md[32];
+    for (int k = 0; k < 16; ++k) { md[k] = (double)V.D[k]; md[16 + k] = (double)V.Dw[k]; mf[k] = (float)V.D[k]; mf[16 + k] = (float)V.Dw[k]; }
+    if (sizeof(FT) == 4) CK(cudaMemcpyToSymbol(c_Df, mf, sizeof(mf)));
+    else CK(cudaMemcpyToSymbol(c_Dd, md, sizeof(md)));
+  }
   // ---- horizontal geometry
   std::vector<double> WJ((size_t)nht * 16), tot((size_t)nht * 16);
   for (int h = 0; h < nht; ++h)
@@ -258,8 +268,12 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
 template <class FT> static size_t smem_base() { return sizeof(VLev<FT>) + HG_ELEM * 16 * sizeof(FT); }
 template <class FT> static size_t smem_slabs(int n) { return smem_base<FT>() + (size_t)n * SLAB * sizeof(FT); }
 
+template <class FT> static size_t smem_row(int n) { return (HG_ELEM * 16 + (size_t)n * SLAB) * sizeof(FT); }
+
 template <class FT>
 static int set_attrs() {
+  CK(cudaFuncSetAttribute(k2_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
+  CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
   CK(cudaFuncSetAttribute(k_wfact<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
@@ -282,6 +296,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
     return fail("b200_create: no CUDA device (this library has no CPU fallback)");
   b200_ctx* c = new b200_ctx();
   c->dims = *d; c->prm = *p; c->ft = d->ft_bytes; c->rank = rank; c->nranks = nranks;
+  if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
   build_csr(T, c->h_off, c->h_mem);
   c->nnodes = (int)c->h_off.size() - 1;
   // keep only nodes with at least one local member
@@ -523,13 +538,32 @@ template <class FT>
 static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
   const bool hd = c->prm.hyperdiff != 0;
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
-  if (phase == 0) {
+  if (phase == 0 && c->legacy) {
     k_texp_a<FT><<<c->dims.nh, NT, smem_slabs<FT>(22), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                           (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+    LAUNCH_CHECK(c);
+  } else if (phase == 0 && c->legacy == 2) {
+    k_exp_s<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                        (const FT*)Yf, (FT*)Ytc, hd ? (FT*)c->H : nullptr);
+    LAUNCH_CHECK(c);
+    k_exp_m<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                        (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+    LAUNCH_CHECK(c);
+  } else if (phase == 0) {
+    k2_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                       (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
   } else if (phase == 1 && hd) {
     DssField F = {c->H, 4, 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
+  } else if (phase == 2 && hd && c->legacy == 2) {
+    k_exp_c<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                        (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+    LAUNCH_CHECK(c);
+  } else if (phase == 2 && hd && !c->legacy) {
+    k2_exp_c<FT><<<c->dims.nh, CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                       (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+    LAUNCH_CHECK(c);
   } else if (phase == 2 && hd) {
     k_texp_c<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                           (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);

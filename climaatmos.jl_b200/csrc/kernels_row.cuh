@@ -1,0 +1,383 @@
+// kernels_row.cuh — explicit-tendency kernels, "one GLL row per thread" layout (round-1, 2nd generation).
+//
+// One element per CTA of 256 threads.  Thread (v, j) owns the four nodes i = 0..3 of row j at level v in
+// registers; a warp holds 8 consecutive levels × 4 rows (lane = vl + 8·j).  On B200 this gives
+//   * ξ¹-derivatives: thread-local 4×4 contractions with D/Dw entries from the constant bank;
+//   * ξ²-derivatives: 4 warp shuffles (lanes vl, vl+8, vl+16, vl+24) per output with per-thread
+//     matrix rows D[j][·], Dw[j][·] — no shared-memory slabs, no block barriers for horizontal work;
+//   * vertical neighbours (k±1): a shared-memory column exchange, 3 block barriers per launch;
+//   * global accesses: 32-byte segments of 8 consecutive levels (full sector efficiency).
+// Why: ncu showed the first generation (whole slabs in shared memory, 500 LDS/point, 2 CTAs/SM) LSU- and
+// latency-bound and the one-thread-per-level variant (16 nodes/thread, 255 registers, ≈150 KB of
+// straight-line code) instruction-fetch-bound (profiles/r1_ncu_summary.md).  Per point this layout
+// needs ≈100 shuffles, ≈12 LDS and ≈80 registers per thread, with the 4-node body reused by all rows.
+//
+//   k2_exp_a  everything of remaining_tendency! before the DSS (see kernels_explicit.cuh for the list)
+//   k2_exp_c  apply_hyperdiffusion_tendency! after the DSS
+#pragma once
+#include "common.cuh"
+#include "kernels_reg.cuh"
+
+namespace b200 {
+
+constexpr int CT = 256;
+
+template <class FT, int W>
+__device__ __forceinline__ FT dxi4(const FT (&a)[4], int i) {
+  return cM<FT>(W + i * 4 + 0) * a[0] + cM<FT>(W + i * 4 + 1) * a[1] + cM<FT>(W + i * 4 + 2) * a[2] + cM<FT>(W + i * 4 + 3) * a[3];
+}
+// ξ²-derivative of the rows held by lanes vl + 8k with this thread's matrix row m[k] = M[j][k]
+template <class FT>
+__device__ __forceinline__ void deta4(const FT (&a)[4], const FT (&m)[4], int vl, FT (&o)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    FT s = m[0] * __shfl_sync(FULLM, a[i], vl);
+    s += m[1] * __shfl_sync(FULLM, a[i], vl + 8);
+    s += m[2] * __shfl_sync(FULLM, a[i], vl + 16);
+    s += m[3] * __shfl_sync(FULLM, a[i], vl + 24);
+    o[i] = s;
+  }
+}
+// o[i] = (∂₁ a1 + ∂₂ a2)[i]  (divergence-like) with matrix set W for ξ¹ and row m for ξ²
+template <class FT, int W>
+__device__ __forceinline__ void div4(const FT (&a1)[4], const FT (&a2)[4], const FT (&m)[4], int vl, FT (&o)[4]) {
+  deta4(a2, m, vl, o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] += dxi4<FT, W>(a1, i);
+}
+
+template <class FT>
+__device__ __forceinline__ void ld4(FT (&a)[4], const FT* __restrict__ g, int nlev, int j, int v, bool ok, FT dflt) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = ok ? g[(j * 4 + i) * nlev + v] : dflt;
+}
+template <class FT>
+__device__ __forceinline__ void sput(FT* s, const FT (&a)[4], int j, int v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[(j * 4 + i) * LVP + v] = a[i];
+}
+template <class FT>
+__device__ __forceinline__ void sget(const FT* s, FT (&a)[4], int j, int v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = s[(j * 4 + i) * LVP + v];
+}
+
+#define B200_ROW_PROLOGUE                                                                             \
+  const int e = blockIdx.x, lane = threadIdx.x & 31, vl = lane & 7, j = lane >> 3;                    \
+  const int v = (threadIdx.x >> 5) * 8 + vl, nv = P.nv, nf = nv + 1;                                  \
+  const bool cv = v < nv, fv = v < nf;                                                                \
+  for (int k = threadIdx.x; k < HG_ELEM * 16; k += CT) hg[k] = hgeo[(size_t)e * HG_N * 16 + k];       \
+  FT md[4], mw[4];                                                                                    \
+  _Pragma("unroll") for (int k = 0; k < 4; ++k) { md[k] = cM<FT>(j * 4 + k); mw[k] = cM<FT>(16 + j * 4 + k); } \
+  const Lev<FT> L = load_lev(vlev, v, nv);                                                            \
+  const int n0 = j * 4;
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
+k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+         const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  FT* sx = hg + HG_ELEM * 16;  // 9 exchange slabs
+  FT *s_u3 = sx, *s_r = sx + SLAB, *s_u1 = sx + 2 * SLAB, *s_u2 = sx + 3 * SLAB, *s_U1 = sx + 4 * SLAB, *s_U2 = sx + 5 * SLAB,
+     *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
+  B200_ROW_PROLOGUE
+  const bool interior = v > 0 && v < nv;
+  const FT* gY = Yc + (size_t)e * 64 * nv;
+  FT rho[4], u1[4], u2[4], re[4], u3[4], U1[4], U2[4];
+  ld4(rho, gY, nv, j, v, cv, FT(1)); ld4(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
+  ld4(re, gY + 48 * nv, nv, j, v, cv, FT(0)); ld4(u3, Yf + (size_t)e * 16 * nf, nf, j, v, fv, FT(0));
+  sput(s_u3, u3, j, v); sput(s_r, rho, j, v); sput(s_u1, u1, j, v); sput(s_u2, u2, j, v);
+  __syncthreads();  // hg + first exchange slabs
+  FT c1[4], c2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    c1[i] = hg[HG_GI11 * 16 + n0 + i] * u1[i] + hg[HG_GI12 * 16 + n0 + i] * u2[i];
+    c2[i] = hg[HG_GI12 * 16 + n0 + i] * u1[i] + hg[HG_GI22 * 16 + n0 + i] * u2[i];
+    U1[i] = hg[HG_J2 * 16 + n0 + i] * c1[i]; U2[i] = hg[HG_J2 * 16 + n0 + i] * c2[i];
+  }
+  sput(s_U1, U1, j, v); sput(s_U2, U2, j, v);
+  FT K[4], hh[4], ss[4], sd[4], Pi[4], th[4], sE[4], u3c[4];
+  {
+    FT u3h[4];
+    sget(s_u3, u3h, j, v < nv ? v + 1 : v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      K[i] = FT(0.5) * ((u1[i] * c1[i] + u2[i] * c2[i]) * L.sc + FT(0.5) * (u3[i] * (L.g33lo * u3[i]) + u3h[i] * (L.g33hi * u3h[i])));
+      Pt<FT> t = thermo(P, rho[i], re[i], K[i], L.phi);
+      hh[i] = t.h; Pi[i] = t.Pi; th[i] = t.thp; sE[i] = (K[i] + L.phi) - t.phir;
+      sd[i] = P.cp_d * (t.T - P.T_0) + L.phi; ss[i] = sd[i] - t.sdr;
+      u3c[i] = FT(0.5) * (u3[i] + u3h[i]);
+    }
+  }
+  sput(s_K, K, j, v);
+  FT* gT = Ytc + (size_t)e * 64 * nv;
+  FT* gH = H ? H + (size_t)e * 64 * nv : nullptr;
+  const bool any_visc = P.viscous && __any_sync(FULLM, L.bvc != FT(0));
+  // ---- scalars: split-form flux divergences (advection.jl:48,59), viscous sponge on ρe_tot, ∇²s_d
+  {
+    FT F1[4], F2[4], wd[4], t[4], g2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { F1[i] = rho[i] * U1[i]; F2[i] = rho[i] * U2[i]; }
+    div4<FT, 16>(F1, F2, mw, vl, wd);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wd[i] *= hg[HG_RJ2 * 16 + n0 + i] * L.sc;
+      if (cv) gT[(n0 + i) * nv + v] = -wd[i];
+    }
+    FT G1[4], G2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { G1[i] = F1[i] * hh[i]; G2[i] = F2[i] * hh[i]; }
+    div4<FT, 16>(G1, G2, mw, vl, t);
+    deta4(hh, md, vl, g2);
+    FT et[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT rjs = hg[HG_RJ2 * 16 + n0 + i] * L.sc;
+      FT g1 = dxi4<FT, 0>(hh, i);
+      et[i] = -(FT(0.5) * (t[i] * rjs) + FT(0.5) * (hh[i] * wd[i] + (F1[i] * g1 + F2[i] * g2[i]) * rjs));
+    }
+    if (any_visc) {  // β wdivₕ(ρ gradₕ s_d)  (viscous_sponge.jl:79)
+      FT S1[4], S2[4];
+      deta4(sd, md, vl, g2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        FT g1 = dxi4<FT, 0>(sd, i), rj = rho[i] * hg[HG_J2 * 16 + n0 + i];
+        S1[i] = rj * (hg[HG_GI11 * 16 + n0 + i] * g1 + hg[HG_GI12 * 16 + n0 + i] * g2[i]);
+        S2[i] = rj * (hg[HG_GI12 * 16 + n0 + i] * g1 + hg[HG_GI22 * 16 + n0 + i] * g2[i]);
+      }
+      div4<FT, 16>(S1, S2, mw, vl, t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) et[i] += L.bvc * (L.sc * t[i] * hg[HG_RJ2 * 16 + n0 + i]);
+    }
+    if (cv) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gT[(48 + n0 + i) * nv + v] = et[i];
+    }
+    if (gH) {  // ∇²(s_d − s_d,r)  (hyperdiffusion.jl:142-147)
+      FT Q1[4], Q2[4];
+      deta4(ss, md, vl, g2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        FT g1 = dxi4<FT, 0>(ss, i), J2 = hg[HG_J2 * 16 + n0 + i];
+        Q1[i] = J2 * (hg[HG_GI11 * 16 + n0 + i] * g1 + hg[HG_GI12 * 16 + n0 + i] * g2[i]);
+        Q2[i] = J2 * (hg[HG_GI12 * 16 + n0 + i] * g1 + hg[HG_GI22 * 16 + n0 + i] * g2[i]);
+      }
+      div4<FT, 16>(Q1, Q2, mw, vl, t);
+      if (cv) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gH[(48 + n0 + i) * nv + v] = L.sc * t[i] * hg[HG_RJ2 * 16 + n0 + i];
+      }
+    }
+  }
+  // ---- momentum: split-form PGF (advection.jl:82-88)
+  FT t1[4], t2[4];
+  {
+    FT tp[4], gE[4], gP[4], gT2[4], gTP[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tp[i] = th[i] * Pi[i];
+    deta4(sE, md, vl, gE); deta4(Pi, md, vl, gP); deta4(th, md, vl, gT2); deta4(tp, md, vl, gTP);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      t1[i] = -(dxi4<FT, 0>(sE, i) + P.cp_d * (th[i] * dxi4<FT, 0>(Pi, i) + dxi4<FT, 0>(tp, i) - Pi[i] * dxi4<FT, 0>(th, i)) / FT(2));
+      t2[i] = -(gE[i] + P.cp_d * (th[i] * gP[i] + gTP[i] - Pi[i] * gT2[i]) / FT(2));
+    }
+  }
+  // ---- ∇²u (hyperdiffusion.jl:141) and viscous sponge on uₕ
+  {
+    FT D2[4], ze[4], a[4], b[4];
+    div4<FT, 0>(U1, U2, md, vl, D2);
+    deta4(u1, md, vl, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      D2[i] *= hg[HG_RJ2 * 16 + n0 + i];
+      ze[i] = (dxi4<FT, 0>(u2, i) - a[i]) * hg[HG_RJ2 * 16 + n0 + i];
+    }
+    deta4(D2, mw, vl, a); deta4(ze, mw, vl, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT rJ2 = hg[HG_RJ2 * 16 + n0 + i];
+      FT dz1 = dxi4<FT, 16>(ze, i), dz2 = b[i];
+      FT L1 = L.sc * (dxi4<FT, 16>(D2, i) - (hg[HG_GC11 * 16 + n0 + i] * dz2 - hg[HG_GC12 * 16 + n0 + i] * dz1) * rJ2);
+      FT L2 = L.sc * (a[i] - (hg[HG_GC12 * 16 + n0 + i] * dz2 - hg[HG_GC22 * 16 + n0 + i] * dz1) * rJ2);
+      if (gH && cv) { gH[(n0 + i) * nv + v] = L1; gH[(16 + n0 + i) * nv + v] = L2; }
+      if (P.viscous) { t1[i] += L.bvc * L1; t2[i] += L.bvc * L2; }
+    }
+    if (gH) {  // ∇²u₃ = wdivₕ(gradₕ(ᶜinterp(u₃))) on the flat shell
+      FT P1[4], P2[4];
+      deta4(u3c, md, vl, a);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        FT g1 = dxi4<FT, 0>(u3c, i), J2 = hg[HG_J2 * 16 + n0 + i];
+        P1[i] = J2 * (hg[HG_GI11 * 16 + n0 + i] * g1 + hg[HG_GI12 * 16 + n0 + i] * a[i]);
+        P2[i] = J2 * (hg[HG_GI12 * 16 + n0 + i] * g1 + hg[HG_GI22 * 16 + n0 + i] * a[i]);
+      }
+      div4<FT, 16>(P1, P2, mw, vl, b);
+      if (cv) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gH[(32 + n0 + i) * nv + v] = L.sc * b[i] * hg[HG_RJ2 * 16 + n0 + i];
+      }
+    }
+    // (ᶜf³ + ᶜω³) × CT12(ᶜu), Rayleigh sponge (advection.jl:228,275-277; remaining_tendency.jl:166)
+    deta4(u1, mw, vl, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT wz = L.sc * (dxi4<FT, 16>(u2, i) - a[i]) * hg[HG_RJ2 * 16 + n0 + i];
+      FT tot = hg[HG_COR3 * 16 + n0 + i] + wz;
+      t1[i] += tot * U2[i]; t2[i] -= tot * U1[i];
+      if (P.rayleigh) { t1[i] -= L.bruh * u1[i]; t2[i] -= L.bruh * u2[i]; }
+    }
+  }
+  __syncthreads();  // s_U1, s_U2, s_K complete
+  // ---- face level v: ᶠω¹², mass flux, u₃ tendency (advection.jl:233-237,273-278)
+  FT X1[4], X2[4];
+  {
+    FT d3[4], rl[4], a1[4], a2[4], b1[4], b2[4], kl[4], lap[4];
+    deta4(u3, mw, vl, d3);
+    const int vm = v > 0 ? v - 1 : 0;
+    sget(s_r, rl, j, vm); sget(s_u1, a1, j, vm); sget(s_u2, a2, j, vm); sget(s_U1, b1, j, vm); sget(s_U2, b2, j, vm); sget(s_K, kl, j, vm);
+    const bool any_v3 = P.viscous && __any_sync(FULLM, L.bvf != FT(0));
+    if (any_v3) {  // β wdivₕ(gradₕ u₃) on faces (viscous_sponge.jl:64)
+      FT R1[4], R2[4], g2[4];
+      deta4(u3, md, vl, g2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        FT g1 = dxi4<FT, 0>(u3, i), J2 = hg[HG_J2 * 16 + n0 + i];
+        R1[i] = J2 * (hg[HG_GI11 * 16 + n0 + i] * g1 + hg[HG_GI12 * 16 + n0 + i] * g2[i]);
+        R2[i] = J2 * (hg[HG_GI12 * 16 + n0 + i] * g1 + hg[HG_GI22 * 16 + n0 + i] * g2[i]);
+      }
+      div4<FT, 16>(R1, R2, mw, vl, lap);
+    }
+    FT* gF = Ytf + (size_t)e * 16 * nf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const FT J2 = hg[HG_J2 * 16 + n0 + i], rJ2 = hg[HG_RJ2 * 16 + n0 + i];
+      FT jt1 = J2 * L.sf * L.dzf * hg[HG_COR1 * 16 + n0 + i] + d3[i];
+      FT jt2 = J2 * L.sf * L.dzf * hg[HG_COR2 * 16 + n0 + i] - dxi4<FT, 16>(u3, i);
+      FT Vn, ub1, ub2, dk = FT(0);
+      if (interior) {
+        jt1 -= (u2[i] - a2[i]); jt2 += (u1[i] - a1[i]);
+        Vn = FT(0.5) * (rl[i] * L.mclo + rho[i] * L.mc);
+        ub1 = FT(0.5) * (b1[i] * L.sclo + U1[i] * L.sc) * rJ2;
+        ub2 = FT(0.5) * (b2[i] * L.sclo + U2[i] * L.sc) * rJ2;
+        dk = K[i] - kl[i];
+      } else if (v == 0) {
+        Vn = rho[i] * L.mc; ub1 = U1[i] * L.sc * rJ2; ub2 = U2[i] * L.sc * rJ2;
+      } else {
+        Vn = rl[i] * L.mclo; ub1 = b1[i] * L.sclo * rJ2; ub2 = b2[i] * L.sclo * rJ2;
+      }
+      Vn *= L.g33lo * u3[i];
+      X1[i] = jt2 * Vn; X2[i] = -jt1 * Vn;
+      FT t3 = -(jt1 * ub2 - jt2 * ub1) - dk;
+      if (any_v3) t3 += L.bvf * (L.sf2i * lap[i] * rJ2);
+      if (fv) gF[(n0 + i) * nf + v] = t3;
+    }
+  }
+  sput(s_X1, X1, j, v); sput(s_X2, X2, j, v);
+  __syncthreads();
+  if (cv) {
+    FT h1[4], h2[4];
+    sget(s_X1, h1, j, v + 1); sget(s_X2, h2, j, v + 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT rm = rho[i] * L.mc;
+      gT[(16 + n0 + i) * nv + v] = t1[i] - FT(0.5) * (X1[i] + h1[i]) / rm;
+      gT[(32 + n0 + i) * nv + v] = t2[i] - FT(0.5) * (X2[i] + h2[i]) / rm;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 3 : 2))
+k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  FT* s_w = hg + HG_ELEM * 16;
+  FT* s_a = s_w + SLAB;
+  B200_ROW_PROLOGUE
+  const FT* gH = H + (size_t)e * 64 * nv;
+  FT* gT = Ytc + (size_t)e * 64 * nv;
+  FT* gF = Ytf + (size_t)e * 16 * nf;
+  FT rho[4], L1[4], L2[4], L3[4], Ls[4], old1[4], old2[4], old3[4], oldf[4];
+  ld4(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+  ld4(L1, gH, nv, j, v, cv, FT(0)); ld4(L2, gH + 16 * nv, nv, j, v, cv, FT(0));
+  ld4(L3, gH + 32 * nv, nv, j, v, cv, FT(0)); ld4(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
+  // issue the read-modify-write loads early so they overlap the arithmetic
+  ld4(old1, gT + 16 * nv, nv, j, v, cv, FT(0)); ld4(old2, gT + 32 * nv, nv, j, v, cv, FT(0));
+  ld4(old3, gT + 48 * nv, nv, j, v, cv, FT(0)); ld4(oldf, gF, nf, j, v, fv, FT(0));
+  __syncthreads();
+  FT a[4], b[4];
+  {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
+    FT U1[4], U2[4], D2[4], ze[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT J2 = hg[HG_J2 * 16 + n0 + i];
+      U1[i] = J2 * (hg[HG_GI11 * 16 + n0 + i] * L1[i] + hg[HG_GI12 * 16 + n0 + i] * L2[i]);
+      U2[i] = J2 * (hg[HG_GI12 * 16 + n0 + i] * L1[i] + hg[HG_GI22 * 16 + n0 + i] * L2[i]);
+    }
+    div4<FT, 0>(U1, U2, md, vl, D2);
+    deta4(L1, md, vl, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      D2[i] *= hg[HG_RJ2 * 16 + n0 + i];
+      ze[i] = (dxi4<FT, 0>(L2, i) - a[i]) * hg[HG_RJ2 * 16 + n0 + i];
+    }
+    deta4(D2, mw, vl, a); deta4(ze, mw, vl, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT rJ2 = hg[HG_RJ2 * 16 + n0 + i];
+      FT dz1 = dxi4<FT, 16>(ze, i), dz2 = b[i];
+      FT Qa = L.sc * (P.ddf * dxi4<FT, 16>(D2, i) - (hg[HG_GC11 * 16 + n0 + i] * dz2 - hg[HG_GC12 * 16 + n0 + i] * dz1) * rJ2);
+      FT Qb = L.sc * (P.ddf * a[i] - (hg[HG_GC12 * 16 + n0 + i] * dz2 - hg[HG_GC22 * 16 + n0 + i] * dz1) * rJ2);
+      if (cv) { gT[(16 + n0 + i) * nv + v] = old1[i] - P.nu4v * Qa; gT[(32 + n0 + i) * nv + v] = old2[i] - P.nu4v * Qb; }
+    }
+  }
+  {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
+    FT Q1[4], Q2[4];
+    deta4(Ls, md, vl, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT g1 = dxi4<FT, 0>(Ls, i), rj = rho[i] * hg[HG_J2 * 16 + n0 + i];
+      Q1[i] = rj * (hg[HG_GI11 * 16 + n0 + i] * g1 + hg[HG_GI12 * 16 + n0 + i] * a[i]);
+      Q2[i] = rj * (hg[HG_GI12 * 16 + n0 + i] * g1 + hg[HG_GI22 * 16 + n0 + i] * a[i]);
+    }
+    div4<FT, 16>(Q1, Q2, mw, vl, b);
+    if (cv) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gT[(48 + n0 + i) * nv + v] = old3[i] - P.nu4s * (L.sc * b[i] * hg[HG_RJ2 * 16 + n0 + i]);
+    }
+  }
+  {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
+    FT P1[4], P2[4], q[4], w[4];
+    deta4(L3, md, vl, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      FT g1 = dxi4<FT, 0>(L3, i), J2 = hg[HG_J2 * 16 + n0 + i];
+      P1[i] = J2 * (hg[HG_GI11 * 16 + n0 + i] * g1 + hg[HG_GI12 * 16 + n0 + i] * a[i]);
+      P2[i] = J2 * (hg[HG_GI12 * 16 + n0 + i] * g1 + hg[HG_GI22 * 16 + n0 + i] * a[i]);
+    }
+    div4<FT, 16>(P1, P2, mw, vl, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q[i] = L.sc * b[i] * hg[HG_RJ2 * 16 + n0 + i];
+      w[i] = L.mc * rho[i];
+    }
+    sput(s_w, w, j, v); sput(s_a, q, j, v);
+    __syncthreads();
+    if (fv) {
+      FT wl[4], ql[4];
+      const int vm = v > 0 ? v - 1 : 0;
+      sget(s_w, wl, j, vm); sget(s_a, ql, j, vm);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        FT val = (v == 0) ? q[i] : (v == nv ? ql[i] : (wl[i] * ql[i] + w[i] * q[i]) / (wl[i] + w[i]));
+        gF[(n0 + i) * nf + v] = oldf[i] - P.nu4v * val;
+      }
+    }
+  }
+}
+
+}  // namespace b200
