@@ -274,6 +274,7 @@ template <class FT>
 static int set_attrs() {
   CK(cudaFuncSetAttribute(k2_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
   CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
+  CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
   CK(cudaFuncSetAttribute(k_wfact<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
@@ -505,7 +506,8 @@ extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, con
 
 // ---------------------------------------------------------------------------------------------
 template <class FT>
-static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* const* T, const double* coef, size_t N, cudaStream_t s) {
+static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* const* T, const double* coef, size_t N, cudaStream_t s,
+                       int nlev = 0) {
   AxpyArgs<FT> A;
   A.n = 0;
   for (int k = 0; k < n; ++k) {
@@ -516,16 +518,16 @@ static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* co
   bool al = (N % 4 == 0) && (((uintptr_t)out | (uintptr_t)base) % (4 * sizeof(FT)) == 0);
   for (int k = 0; k < A.n; ++k) al = al && ((uintptr_t)A.T[k] % (4 * sizeof(FT)) == 0);
   int blocks = 148 * 8;
-  if (al) k_axpy_n<FT, 4><<<blocks, 256, 0, s>>>(out, base, A, N / 4);
-  else k_axpy_n<FT, 1><<<blocks, 256, 0, s>>>(out, base, A, N);
+  if (al) k_axpy_n<FT, 4><<<blocks, 256, 0, s>>>(out, base, A, N / 4, nlev);
+  else k_axpy_n<FT, 1><<<blocks, 256, 0, s>>>(out, base, A, N, nlev);
   LAUNCH_CHECK(c);
   return 0;
 }
 template <class FT>
 static int impl_axpy(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int n, const void* const* Tc,
-                     const void* const* Tf, const double* coef, cudaStream_t s) {
+                     const void* const* Tf, const double* coef, cudaStream_t s, bool filter_u3 = false) {
   if (launch_axpy<FT>(c, (FT*)Uc, (const FT*)uc, n, (const FT* const*)Tc, coef, c->nc(), s)) return -1;
-  return launch_axpy<FT>(c, (FT*)Uf, (const FT*)uf, n, (const FT* const*)Tf, coef, c->nf(), s);
+  return launch_axpy<FT>(c, (FT*)Uf, (const FT*)uf, n, (const FT* const*)Tf, coef, c->nf(), s, filter_u3 ? c->dims.nv + 1 : 0);
 }
 extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int32_t n, const void* const* Tc,
                            const void* const* Tf, const double* coef, void* stream) {
@@ -642,18 +644,21 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         if (tb.ae[i][j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.ae[i][j]; }
         if (tb.ai[i][j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.ai[i][j]; }
       }
-      if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s)) return -1;
+      // fused path: the u₃ boundary filter of cache_imp! is folded into the increment (the DSS keeps zeros)
+      if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
       if (dss_state(Uc, Uf)) return -1;
       const double dtg = dt * tb.ai[i][i];
       void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
-      if (fused) {
+      if (fused && c->legacy) {
         CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
         k_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(18), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                  (FT*)Nc, (FT*)Nf, (FT)dtg);
         LAUNCH_CHECK(c);
-        // the boundary filter of cache_imp! must also be visible in temp (= U)
-        if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
+      } else if (fused) {
+        k2_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(11), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                  (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+        LAUNCH_CHECK(c);
       } else {
         if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
         CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
@@ -682,8 +687,8 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), s)) return -1;
       if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), s)) return -1;
       Uc = Nc; Uf = Nf;
-    } else {
-      if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
+    } else if (!fused) {
+      if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;  // no-op on a filtered state; kept for the hook trace
     }
     if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], nullptr, nullptr, Uc, Uf, s)) return -1;
   }
@@ -693,10 +698,10 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       if (tb.be[j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.be[j]; }
       if (tb.bi[j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.bi[j]; }
     }
-    if (impl_axpy<FT>(c, Yc, Yf, Yc, Yf, n, Tc, Tf, cf, s)) return -1;
+    if (impl_axpy<FT>(c, Yc, Yf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
   }
   if (dss_state(Yc, Yf)) return -1;
-  return impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
+  return fused ? 0 : impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
 }
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
   return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, (cudaStream_t)stream) : impl_step<double>(c, Yc, Yf, fused, (cudaStream_t)stream);

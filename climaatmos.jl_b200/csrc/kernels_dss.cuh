@@ -114,8 +114,10 @@ struct AxpyArgs {
   int n;
 };
 
+// `nlev` > 0 marks a face field with nlev levels per column whose first and last level are forced to
+// zero (the u₃ impenetrability filter of cache_imp!, folded into the increment by the native stepper).
 template <class FT, int VEC>
-__global__ void __launch_bounds__(256) k_axpy_n(FT* out, const FT* base, AxpyArgs<FT> A, size_t nvec) {
+__global__ void __launch_bounds__(256) k_axpy_n(FT* out, const FT* base, AxpyArgs<FT> A, size_t nvec, int nlev) {
   struct alignas(sizeof(FT) * VEC) Vt { FT x[VEC]; };
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -124,6 +126,13 @@ __global__ void __launch_bounds__(256) k_axpy_n(FT* out, const FT* base, AxpyArg
       Vt t = reinterpret_cast<const Vt*>(A.T[k])[i];
 #pragma unroll
       for (int q = 0; q < VEC; ++q) r.x[q] += A.c[k] * t.x[q];
+    }
+    if (nlev > 0) {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        int lev = (int)((i * VEC + q) % (size_t)nlev);
+        if (lev == 0 || lev == nlev - 1) r.x[q] = FT(0);
+      }
     }
     reinterpret_cast<Vt*>(out)[i] = r;
   }

@@ -381,3 +381,215 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
 }
 
 }  // namespace b200
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// k2_imp_stage — fused implicit stage, second generation (out of place: U → N).
+//
+// Same arithmetic as k_imp_stage (cache_imp! → Wfact → T_imp! residual → ldiv! → U −= ΔU → cache_imp!
+// → T_post_imp!), restructured for the B200 after the first ncu profile (24 % warp occupancy, 213 M
+// instructions, 16 of 256 threads active in the Thomas sweep):
+//   * 11 shared slabs instead of 18 (coefficients live in registers of the (node, level) owner and the
+//     solver slabs alias the dead thermodynamic slabs) ⇒ 4 CTAs/SM so other CTAs cover the Thomas sweep;
+//   * thermodynamics evaluated once with transcendental functions (Π, Φ_r) and once without (only
+//     h_tot is needed after the Newton update);
+//   * the Schur tridiagonal is assembled from one per-face coefficient A = dtγ·ᶠinterp(ρJ)g³³/J2
+//     instead of calling the centre-row routine twice per face;
+//   * reciprocal-based Thomas sweep (one division per row).
+// The u₃ boundary filter of cache_imp! is applied on load, so the input may carry unfiltered boundary
+// values; uₕ is copied through (its Newton increment is identically zero because R_uₕ = dtγ·0).
+template <class FT>
+__global__ void __launch_bounds__(NT, (sizeof(FT) == 4 ? 4 : 2))
+k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+             const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  FT *s_rho = sm.take(SLAB), *s_u3 = sm.take(SLAB), *s_h = sm.take(SLAB), *s_Kh = sm.take(SLAB), *s_M = sm.take(SLAB),
+     *s_A = sm.take(SLAB);
+  FT *s_Pi = sm.take(SLAB), *s_thv = sm.take(SLAB), *s_thp = sm.take(SLAB), *s_phr = sm.take(SLAB), *s_dp = sm.take(SLAB);
+  FT *s_l = s_Pi, *s_d = s_thv, *s_u = s_thp, *s_r = s_phr;  // solver slabs alias dead thermodynamic slabs
+  const int e = blockIdx.x, nv = P.nv, nf = nv + 1;
+  const FT kap = P.R_d / P.cv_d;
+  load_vlev(&V, vlev);
+  load_hgeo(hg, hgeo, e);
+  const FT* gY = Yc + (size_t)e * 64 * nv;
+  const FT* gYf = Yf + (size_t)e * 16 * nf;
+  FT* gN = Nc + (size_t)e * 64 * nv;
+  FT* gNf = Nf + (size_t)e * 16 * nf;
+  FT r_re[NIT], r_u1[NIT], r_u2[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, v = idx & 63, o = n * LVP + v;
+    r_re[it] = r_u1[it] = r_u2[it] = FT(0);
+    if (v < nv) {
+      s_rho[o] = gY[n * nv + v];
+      r_u1[it] = gY[(16 + n) * nv + v]; r_u2[it] = gY[(32 + n) * nv + v]; r_re[it] = gY[(48 + n) * nv + v];
+      gN[(16 + n) * nv + v] = r_u1[it]; gN[(32 + n) * nv + v] = r_u2[it];
+    }
+    if (v < nf) s_u3[o] = (v == 0 || v == nv) ? FT(0) : gYf[n * nf + v];
+  }
+  __syncthreads();
+  // ---- phase 1: centre thermodynamics
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, v = idx & 63, o = n * LVP + v;
+    if (v < nv) {
+      FT a1 = r_u1[it], a2 = r_u2[it];
+      FT c1 = hg[HG_GI11 * 16 + n] * a1 + hg[HG_GI12 * 16 + n] * a2;
+      FT c2 = hg[HG_GI12 * 16 + n] * a1 + hg[HG_GI22 * 16 + n] * a2;
+      FT Kh = FT(0.5) * ((a1 * c1 + a2 * c2) * V.sc2i[v]);
+      FT lo = s_u3[o], hi = s_u3[o + 1];
+      FT K = Kh + FT(0.25) * (lo * (V.g33f[v] * lo) + hi * (V.g33f[v + 1] * hi));
+      Pt<FT> t = thermo(P, s_rho[o], r_re[it], K, V.phic[v]);
+      s_Kh[o] = Kh; s_h[o] = t.h; s_Pi[o] = t.Pi; s_thv[o] = t.thv; s_thp[o] = t.thp; s_phr[o] = t.phir;
+      s_dp[o] = kap * (P.T_0 * P.cp_d - K - V.phic[v]) + (P.R_d - kap * P.cv_d) * t.T;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: face mass-flux pieces  M = ᶠinterp(ρJ)u³/J2,  A = dtγ ᶠinterp(ρJ) g³³/J2 (zero on boundaries)
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, f = idx & 63, o = n * LVP + f;
+    if (f < nf) {
+      FT M = FT(0), A = FT(0);
+      if (f > 0 && f < nv) {
+        FT mr = rho_mface(V, s_rho, o, f);
+        A = dtg * mr * V.g33f[f];
+        M = mr * (V.g33f[f] * s_u3[o]);
+      }
+      s_M[o] = M; s_A[o] = A;
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: Schur tridiagonal and right-hand side of face row f (manual_sparse_jacobian.jl:746-868)
+  FT cl[NIT], cd[NIT], cu[NIT], cr[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, f = idx & 63, o = n * LVP + f;
+    cl[it] = cu[it] = cr[it] = FT(0); cd[it] = FT(-1);
+    if (f < nf) {
+      FT beta = P.rayleigh ? V.brw[f] : FT(0);
+      cd[it] = dtg * (-beta) - FT(1);
+      if (f > 0 && f < nv) {
+        FT rlo = s_rho[o - 1], rhi = s_rho[o];
+        FT irf = FT(1) / (FT(0.5) * (rlo + rhi));
+        FT dPi = s_Pi[o] - s_Pi[o - 1];
+        FT buoy = P.cp_d * (FT(0.5) * (s_thv[o - 1] + s_thv[o])) * dPi * irf;
+        FT ur_lo = dtg * (irf * s_dp[o - 1] + buoy * FT(0.5)), ur_hi = dtg * (-irf * s_dp[o] + buoy * FT(0.5));
+        FT ue_lo = dtg * irf * kap, ue_hi = -ue_lo;
+        FT x_lo = irf * (-kap * rlo), x_hi = -irf * (-kap * rhi);
+        FT k0 = FT(0.5) * V.g33f[f] * s_u3[o];
+        FT l = dtg * (x_lo * (FT(0.5) * V.g33f[f - 1] * s_u3[o - 1]));
+        FT d = dtg * ((x_lo * k0 + x_hi * k0) - beta) - FT(1);
+        FT u = dtg * (x_hi * (FT(0.5) * V.g33f[f + 1] * s_u3[o + 1]));
+        // centre rows f-1 ("a") and f ("b"): ru_lo = A[k]/m_c[k], ru_hi = −A[k+1]/m_c[k], eu = ru·ᶠinterp(h)
+        FT ima = FT(1) / V.mc[f - 1], imb = FT(1) / V.mc[f];
+        FT Am = s_A[o - 1], A0 = s_A[o], Ap = s_A[o + 1];
+        FT hm = (f > 1) ? FT(0.5) * (s_h[o - 2] + s_h[o - 1]) : FT(0);
+        FT h0 = FT(0.5) * (s_h[o - 1] + s_h[o]);
+        FT hp = (f < nv - 1) ? FT(0.5) * (s_h[o] + s_h[o + 1]) : FT(0);
+        FT ru_lo_a = Am * ima, ru_hi_a = -A0 * ima, ru_lo_b = A0 * imb, ru_hi_b = -Ap * imb;
+        l += ur_lo * ru_lo_a + ue_lo * (ru_lo_a * hm);
+        d += ur_lo * ru_hi_a + ur_hi * ru_lo_b + ue_lo * (ru_hi_a * h0) + ue_hi * (ru_lo_b * h0);
+        u += ur_hi * ru_hi_b + ue_hi * (ru_hi_b * hp);
+        // R = dtγ·T_imp(U): face part + couplings to the centre residuals of rows f-1 and f
+        FT Mm = s_M[o - 1], M0 = s_M[o], Mp = s_M[o + 1];
+        FT rr_a = -dtg * (M0 - Mm) * ima, rr_b = -dtg * (Mp - M0) * imb;
+        FT re_a = -dtg * (M0 * h0 - Mm * hm) * ima, re_b = -dtg * (Mp * hp - M0 * h0) * imb;
+        FT tf = -(V.dphif[f] - (s_phr[o] - s_phr[o - 1]) + P.cp_d * (FT(0.5) * (s_thp[o - 1] + s_thp[o])) * dPi) - beta * s_u3[o];
+        cl[it] = l; cd[it] = d; cu[it] = u;
+        cr[it] = dtg * tf + ur_lo * rr_a + ur_hi * rr_b + ue_lo * re_a + ue_hi * re_b;
+      }
+    }
+  }
+  __syncthreads();  // all reads of the thermodynamic slabs are done: reuse them for the solver
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, f = idx & 63, o = n * LVP + f;
+    if (f < nf) { s_l[o] = cl[it]; s_d[o] = cd[it]; s_u[o] = cu[it]; s_r[o] = cr[it]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {  // Thomas sweep, one column per thread (BlockArrowheadSolve → Thomas)
+    const FT *l = s_l + threadIdx.x * LVP, *d = s_d + threadIdx.x * LVP;
+    FT *u = s_u + threadIdx.x * LVP, *r = s_r + threadIdx.x * LVP;
+    FT rd = FT(1) / d[0];
+    FT cp = u[0] * rd, dp = r[0] * rd;
+    u[0] = cp; r[0] = dp;
+    for (int i = 1; i < nf; ++i) {
+      FT li = l[i];
+      rd = FT(1) / (d[i] - li * cp);
+      cp = u[i] * rd;
+      dp = (r[i] - li * dp) * rd;
+      u[i] = cp; r[i] = dp;
+    }
+    FT x = dp;
+    for (int i = nf - 2; i >= 0; --i) { x = r[i] - u[i] * x; r[i] = x; }
+  }
+  __syncthreads();
+  // ---- phase 5: U ← U − ΔU (back-substitution of the scalar rows)
+  FT n_re[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, v = idx & 63, o = n * LVP + v;
+    n_re[it] = FT(0);
+    FT nr = FT(0), nu = FT(0);
+    if (v < nv) {
+      FT im = FT(1) / V.mc[v];
+      FT A0 = s_A[o], Ap = s_A[o + 1], M0 = s_M[o], Mp = s_M[o + 1];
+      FT h0 = (v > 0) ? FT(0.5) * (s_h[o - 1] + s_h[o]) : FT(0);
+      FT hp = (v < nv - 1) ? FT(0.5) * (s_h[o] + s_h[o + 1]) : FT(0);
+      FT x0 = s_r[o], x1 = s_r[o + 1];
+      FT rr = -dtg * (Mp - M0) * im, rre = -dtg * (Mp * hp - M0 * h0) * im;
+      nr = s_rho[o] - ((A0 * im) * x0 + (-Ap * im) * x1 - rr);
+      n_re[it] = r_re[it] - ((A0 * im * h0) * x0 + (-Ap * im * hp) * x1 - rre);
+    }
+    if (v < nf) nu = (v == 0 || v == nv) ? FT(0) : s_u3[o] - s_r[o];
+    // (only own entries of s_rho/s_u3 are read in this phase, so they can be updated in place)
+    if (v < nv) { s_rho[o] = nr; gN[n * nv + v] = nr; }
+    if (v < nf) { s_u3[o] = nu; gNf[n * nf + v] = nu; }
+  }
+  __syncthreads();
+  if (P.upwinding != 0) {
+    // ---- phase 6: h_tot of the updated state (cache_imp! after the Newton update; no transcendentals needed)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = threadIdx.x + it * NT, n = idx >> 6, v = idx & 63, o = n * LVP + v;
+      if (v < nv) {
+        FT lo = s_u3[o], hi = s_u3[o + 1];
+        FT K = s_Kh[o] + FT(0.25) * (lo * (V.g33f[v] * lo) + hi * (V.g33f[v + 1] * hi));
+        FT etot = n_re[it] / s_rho[o];
+        FT T = fmax_(P.T_min_sgs, P.T_0 + ((etot - K - V.phic[v]) + P.R_d * P.T_0) / P.cv_d);
+        s_h[o] = etot + P.R_d * T;
+      }
+    }
+    __syncthreads();
+    // ---- phase 7: (upwinded − centred) enthalpy flux (implicit_tendency.jl:322-339)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = threadIdx.x + it * NT, n = idx >> 6, f = idx & 63, o = n * LVP + f;
+      if (f < nf) {
+        FT r = FT(0);
+        if (f > 0 && f < nv) {
+          FT w = V.g33f[f] * s_u3[o];
+          r = rho_mface(V, s_rho, o, f) * w * upwind_minus_central(P, s_h, o, f, nv, w);
+        }
+        s_M[o] = r;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int idx = threadIdx.x + it * NT, n = idx >> 6, v = idx & 63, o = n * LVP + v;
+    if (v < nv) {
+      FT e2 = n_re[it];
+      if (P.upwinding != 0) e2 += dtg * (-(s_M[o + 1] - s_M[o]) / V.mc[v]);
+      gN[(48 + n) * nv + v] = e2;
+    }
+  }
+}
+
+}  // namespace b200
