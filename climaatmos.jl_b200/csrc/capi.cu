@@ -81,6 +81,7 @@ struct b200_ctx {
   int* d_mem = nullptr;
   int nnodes = 0;
   std::vector<int32_t> h_off, h_mem;
+  void* d_dssrec = nullptr;
   void* d_jac = nullptr;
   // native stepper storage (allocated lazily)
   void *Uc[2] = {nullptr, nullptr}, *Uf[2] = {nullptr, nullptr};
@@ -261,6 +262,23 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
     }
   CK(cudaMalloc(&c->d_hgeo, hg.size() * sizeof(FT)));
   CK(cudaMemcpy(c->d_hgeo, hg.data(), hg.size() * sizeof(FT), cudaMemcpyHostToDevice));
+  // per-node DSS records (same arithmetic as k_dss: weight·(A⁻¹)ᵀ in, Aᵀ out, members in summation order)
+  std::vector<DssNode<FT>> rec((size_t)std::max(1, c->nnodes));
+  memset(rec.data(), 0, rec.size() * sizeof(DssNode<FT>));
+  for (int nd = 0; nd < c->nnodes; ++nd) {
+    DssNode<FT>& R = rec[nd];
+    R.cnt = c->h_off[nd + 1] - c->h_off[nd];
+    for (int q = 0; q < R.cnt; ++q) {
+      const int m = c->h_mem[c->h_off[nd] + q];
+      const FT* o = hg.data() + (size_t)(m >> 4) * HG_N * 16 + (m & 15);
+      R.mem[q] = m;
+      R.w[q] = o[HG_DSSW * 16];
+      R.ai[q][0] = o[HG_AI00 * 16]; R.ai[q][1] = o[HG_AI10 * 16]; R.ai[q][2] = o[HG_AI01 * 16]; R.ai[q][3] = o[HG_AI11 * 16];
+      R.a[q][0] = o[HG_A00 * 16]; R.a[q][1] = o[HG_A10 * 16]; R.a[q][2] = o[HG_A01 * 16]; R.a[q][3] = o[HG_A11 * 16];
+    }
+  }
+  CK(cudaMalloc(&c->d_dssrec, rec.size() * sizeof(DssNode<FT>)));
+  CK(cudaMemcpy(c->d_dssrec, rec.data(), rec.size() * sizeof(DssNode<FT>), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -344,7 +362,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
 extern "C" int b200_destroy(b200_ctx* c) {
   if (!c) return 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
+  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
   fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
@@ -491,8 +509,14 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
     else if (F[k].kind == 1) { if (add(true)) return -1; }
     while (comp < F[k].nf) if (add(false)) return -1;
   }
-  dim3 blk(64, 4);
-  k_dss<FT><<<(c->nnodes + 3) / 4, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh);
+  dim3 blk(64, 4), grd((c->nnodes + 3) / 4, 1);
+  const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
+  if (c->legacy) { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
+  else if (A.n == 1) k_dss2<FT, 1><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
+  else if (A.n == 2) k_dss2<FT, 2><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
+  else if (A.n == 3) k_dss2<FT, 3><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
+  else if (A.n == 4) k_dss2<FT, 4><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
+  else { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
   LAUNCH_CHECK(c);
   return 0;
 }

@@ -48,9 +48,13 @@ __global__ void __launch_bounds__(256) k_dss(DssArgs A, const int* __restrict__ 
       w[q] = hgeo[((size_t)el[q] * HG_N + HG_DSSW) * 16 + nd[q]];
     }
   }
-  for (int k = 0; k < A.n; ++k) {
+  // one item per blockIdx.y: every (node, level, item) is an independent thread, so the member loads of all
+  // items are in flight together (the first version looped over items per thread and was latency-bound at
+  // ≈1.7 TB/s, profiles/r1_ncu_summary.md)
+  {
+    const int k = blockIdx.y;
     const DssItem I = A.it[k];
-    if (v >= I.nlev) continue;
+    if (v >= I.nlev) return;
     FT* p0 = reinterpret_cast<FT*>(I.p0);
     FT* p1 = reinterpret_cast<FT*>(I.p1);
     const FT* g0 = reinterpret_cast<const FT*>(I.g0);
@@ -92,6 +96,87 @@ __global__ void __launch_bounds__(256) k_dss(DssArgs A, const int* __restrict__ 
           size_t o = (size_t)el[q] * I.estride + nd[q] * I.nlev + v;
           p0[o] = hg[HG_A00 * 16] * su + hg[HG_A10 * 16] * sv;
           p1[o] = hg[HG_A01 * 16] * su + hg[HG_A11 * 16] * sv;
+        }
+    }
+  }
+}
+
+// Second-generation DSS: one compact record per unique node (members, weights and the 2×2 basis-change
+// matrices of every member) so that a thread issues the record read and then ALL member loads of ALL items
+// back to back — two dependent memory latencies instead of four per item (off → mem → weight → data).
+template <class FT>
+struct DssNode {
+  int32_t cnt;
+  int32_t mem[4];       // elem*16 + node
+  FT w[4];              // DSS weight of the member
+  FT ai[4][4];          // w·(∂ξ/∂x)ᵀ rows: (ai00, ai10, ai01, ai11) of the member (covariant → weighted physical)
+  FT a[4][4];           // (a00, a10, a01, a11) of the member (physical → covariant)
+};
+
+template <class FT, int NI>
+__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int nnodes, int nh) {
+  __shared__ DssNode<FT> sr[4];
+  const int v = threadIdx.x;
+  const int node = blockIdx.x * 4 + threadIdx.y;
+  constexpr int RW = sizeof(DssNode<FT>) / 4;
+  if (node < nnodes && v < RW) reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v] = reinterpret_cast<const uint32_t*>(&rec[node])[v];
+  if (RW > 64 && node < nnodes && v + 64 < RW)
+    reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v + 64] = reinterpret_cast<const uint32_t*>(&rec[node])[v + 64];
+  __syncthreads();
+  if (node >= nnodes) return;
+  const DssNode<FT>& R = sr[threadIdx.y];
+  const int cnt = R.cnt;
+  FT x0[NI][4], x1[NI][4];
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const DssItem& I = A.it[k];
+    const bool pair = I.p1 != nullptr;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      x0[k][q] = FT(0); x1[k][q] = FT(0);
+      if (q < cnt && v < I.nlev) {
+        const int el = R.mem[q] >> 4, nd = R.mem[q] & 15;
+        if (el < nh) {
+          const size_t o = (size_t)el * I.estride + nd * I.nlev + v;
+          x0[k][q] = reinterpret_cast<const FT*>(I.p0)[o];
+          if (pair) x1[k][q] = reinterpret_cast<const FT*>(I.p1)[o];
+        } else {
+          const size_t o = (size_t)(el - nh) * I.gstride + nd * I.nlev + v;
+          x0[k][q] = reinterpret_cast<const FT*>(I.g0)[o];
+          if (pair) x1[k][q] = reinterpret_cast<const FT*>(I.g1)[o];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const DssItem& I = A.it[k];
+    if (v >= I.nlev) continue;
+    FT* p0 = reinterpret_cast<FT*>(I.p0);
+    FT* p1 = reinterpret_cast<FT*>(I.p1);
+    if (!p1) {
+      FT s = FT(0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < cnt) s += R.w[q] * x0[k][q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < cnt && (R.mem[q] >> 4) < nh) p0[(size_t)(R.mem[q] >> 4) * I.estride + (R.mem[q] & 15) * I.nlev + v] = s;
+    } else {
+      FT su = FT(0), sv = FT(0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < cnt) {
+          FT uu = R.ai[q][0] * x0[k][q] + R.ai[q][1] * x1[k][q];
+          FT vv = R.ai[q][2] * x0[k][q] + R.ai[q][3] * x1[k][q];
+          su += R.w[q] * uu; sv += R.w[q] * vv;
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < cnt && (R.mem[q] >> 4) < nh) {
+          const size_t o = (size_t)(R.mem[q] >> 4) * I.estride + (R.mem[q] & 15) * I.nlev + v;
+          p0[o] = R.a[q][0] * su + R.a[q][1] * sv;
+          p1[o] = R.a[q][2] * su + R.a[q][3] * sv;
         }
     }
   }
