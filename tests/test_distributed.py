@@ -1,0 +1,42 @@
+"""Multi-process tests: gloo world_size-2/3 on CPU for the halo protocol (host logic), NCCL on GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_halo_protocol(world):
+    import torch.multiprocessing as mp
+    from tests.dist_worker import gloo_halo
+
+    mp.spawn(gloo_halo, args=(world, _free_port()), nprocs=world, join=True)
+
+
+@pytest.mark.gpu
+def test_nccl_multi_gpu_step_is_rank_count_independent():
+    """With ≥ 2 GPUs: 3 ARS343 steps on 2 ranks (NCCL halo) equal the single-GPU run BITWISE on every
+    rank's owned elements (DSS sums in ascending global element order on every rank)."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_worker.py"), "nccl-step"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "bitwise_equal=True" in r.stdout
