@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <limits.h>
 
 #include <algorithm>
 #include <string>
@@ -178,6 +179,8 @@ static Par<FT> make_par(const b200_ctx* c) {
   P.R_d = (FT)p.R_d; P.cp_d = (FT)p.cp_d; P.cv_d = (FT)p.cv_d; P.T_0 = (FT)p.T_0; P.p0 = (FT)p.p_ref_theta;
   P.kappa = (FT)(p.R_d / p.cp_d); P.Ts_ref = (FT)p.T_surf_ref; P.Tmin_ref = (FT)p.T_min_ref;
   P.T_min_sgs = (FT)p.T_min_sgs; P.dt = (FT)p.dt;
+  P.icv = (FT)(1.0 / p.cv_d); P.ip0 = (FT)(1.0 / p.p_ref_theta); P.dTs7 = (FT)((p.T_surf_ref - p.T_min_ref) / 7.0);
+  P.RT0 = (FT)(p.R_d * p.T_0);
   P.nu4v = (FT)p.nu4_vorticity; P.nu4s = (FT)p.nu4_scalar; P.ddf = (FT)p.divergence_damping_factor;
   P.nh = c->dims.nh; P.nv = c->dims.nv;
   P.hyperdiff = p.hyperdiff; P.rayleigh = p.rayleigh_sponge; P.viscous = p.viscous_sponge; P.upwinding = p.energy_upwinding;
@@ -511,12 +514,20 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   }
   dim3 blk(64, 4), grd((c->nnodes + 3) / 4, 1);
   const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
-  if (c->legacy) { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
-  else if (A.n == 1) k_dss2<FT, 1><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
-  else if (A.n == 2) k_dss2<FT, 2><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
-  else if (A.n == 3) k_dss2<FT, 3><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
-  else if (A.n == 4) k_dss2<FT, 4><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh);
+  int pairs = 0;
+  for (int k = 0; k < A.n; ++k) pairs |= (A.it[k].p1 != nullptr) << k;
+  const bool small = (size_t)(nh + c->dims.nh_ghost) * 64 * (size_t)(nv + 1) < (size_t)INT32_MAX;  // 32-bit offsets
+#define DSS2(NI, PM)                                                                               \
+  (halo ? (void)(k_dss2<FT, NI, PM, true><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh))               \
+        : (void)(k_dss2<FT, NI, PM, false><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh)))
+  if (c->legacy || !small) { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
+  else if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);   // state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃
+  else if (A.n == 3 && pairs == 0x1) DSS2(3, 0x1);   // ∇² fields: (∇²u₁,∇²u₂), ∇²u₃, ∇²s_d
+  else if (A.n == 1 && pairs == 0x0) DSS2(1, 0x0);
+  else if (A.n == 1 && pairs == 0x1) DSS2(1, 0x1);
+  else if (A.n == 2 && pairs == 0x0) DSS2(2, 0x0);
   else { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
+#undef DSS2
   LAUNCH_CHECK(c);
   return 0;
 }

@@ -52,6 +52,7 @@ struct VLev {
 template <class FT>
 struct Par {
   FT R_d, cp_d, cv_d, T_0, p0, kappa, Ts_ref, Tmin_ref, T_min_sgs, dt;
+  FT icv, ip0, dTs7, RT0;  // 1/cv_d, 1/p0, (Ts_ref − Tmin_ref)/7, R_d·T_0
   FT nu4v, nu4s, ddf;
   int nh, nv;
   int hyperdiff, rayleigh, viscous, upwinding;
@@ -64,6 +65,8 @@ __device__ __forceinline__ float  pow_(float a, float b)  { return powf(a, b); }
 __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
 __device__ __forceinline__ float  log_(float a)  { return logf(a); }
 __device__ __forceinline__ double log_(double a) { return log(a); }
+__device__ __forceinline__ float  exp_(float a)  { return expf(a); }
+__device__ __forceinline__ double exp_(double a) { return exp(a); }
 __device__ __forceinline__ float  abs_(float a)  { return fabsf(a); }
 __device__ __forceinline__ double abs_(double a) { return fabs(a); }
 
@@ -81,18 +84,22 @@ struct Pt {
 template <class FT>
 __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K, FT Phi) {
   Pt<FT> o;
-  FT etot = rhoe / rho;
+  // one reciprocal for ρ and Π, one log shared by Π = exp(κ ln(p/p0)) and ln Π (the first version used
+  // powf + logf + 5 divisions per point; the XU pipe showed up at 12–16 % in ncu)
+  FT etot = rhoe * (FT(1) / rho);
   FT eint = etot - K - Phi;
   // e_int = cv_d (T − T_0) − R_d T_0  (docs/src/thermodynamics.md:103-111)
-  o.T = fmax_(P.T_min_sgs, P.T_0 + (eint + P.R_d * P.T_0) / P.cv_d);
+  o.T = fmax_(P.T_min_sgs, P.T_0 + (eint + P.RT0) * P.icv);
   o.h = etot + P.R_d * o.T;
   o.p = rho * P.R_d * o.T;
-  o.Pi = pow_(o.p / P.p0, P.kappa);
+  FT lnPi = P.kappa * log_(o.p * P.ip0);
+  o.Pi = exp_(lnPi);
+  FT rPi = FT(1) / o.Pi;
   FT Pi7 = pow7(o.Pi);
   FT Tr = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * Pi7;
-  o.thv = o.T / o.Pi;
-  o.thp = o.thv - Tr / o.Pi;
-  o.phir = -P.cp_d * (P.Tmin_ref * log_(o.Pi) + (P.Ts_ref - P.Tmin_ref) / FT(7) * (Pi7 - FT(1)));
+  o.thv = o.T * rPi;
+  o.thp = (o.T - Tr) * rPi;
+  o.phir = -P.cp_d * (P.Tmin_ref * lnPi + P.dTs7 * (Pi7 - FT(1)));
   o.sdr = P.cp_d * (Tr - P.T_0) + o.phir;
   return o;
 }

@@ -113,7 +113,68 @@ struct DssNode {
   FT a[4][4];           // (a00, a10, a01, a11) of the member (physical → covariant)
 };
 
-template <class FT, int NI>
+// Body for one (node, level) with a compile-time member bound CNT (2 for face-interior nodes — 80 % of the
+// nodes — 4 for vertices), compile-time item kinds (bit k of PAIRS ⇒ item k is a Covariant12 pair) and
+// compile-time halo flag: the generic fully predicated version issued ≈800 instructions per thread
+// (ncu: issue-active 77 %, i.e. instruction-bound, profiles/r1_ncu_summary.md).
+template <class FT, int NI, int PAIRS, int CNT, bool HALO>
+__device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R, int cnt, int v, int nh) {
+  FT x0[NI][CNT], x1[NI][CNT];
+  int off[NI][CNT];
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const DssItem& I = A.it[k];
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) {
+      x0[k][q] = FT(0); x1[k][q] = FT(0); off[k][q] = -1;
+      if ((CNT == 2 || q < cnt) && v < I.nlev) {
+        const int el = R.mem[q] >> 4, nd = R.mem[q] & 15;
+        if (!HALO || el < nh) {
+          const int o = el * I.estride + nd * I.nlev + v;
+          off[k][q] = o;
+          x0[k][q] = reinterpret_cast<const FT*>(I.p0)[o];
+          if (PAIRS & (1 << k)) x1[k][q] = reinterpret_cast<const FT*>(I.p1)[o];
+        } else {
+          const int o = (el - nh) * I.gstride + nd * I.nlev + v;
+          x0[k][q] = reinterpret_cast<const FT*>(I.g0)[o];
+          if (PAIRS & (1 << k)) x1[k][q] = reinterpret_cast<const FT*>(I.g1)[o];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const DssItem& I = A.it[k];
+    FT* p0 = reinterpret_cast<FT*>(I.p0);
+    FT* p1 = reinterpret_cast<FT*>(I.p1);
+    if (!(PAIRS & (1 << k))) {
+      FT s = FT(0);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (CNT == 2 || q < cnt) s += R.w[q] * x0[k][q];
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (off[k][q] >= 0) p0[off[k][q]] = s;
+    } else {
+      FT su = FT(0), sv = FT(0);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (CNT == 2 || q < cnt) {
+          FT uu = R.ai[q][0] * x0[k][q] + R.ai[q][1] * x1[k][q];
+          FT vv = R.ai[q][2] * x0[k][q] + R.ai[q][3] * x1[k][q];
+          su += R.w[q] * uu; sv += R.w[q] * vv;
+        }
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (off[k][q] >= 0) {
+          p0[off[k][q]] = R.a[q][0] * su + R.a[q][1] * sv;
+          p1[off[k][q]] = R.a[q][2] * su + R.a[q][3] * sv;
+        }
+    }
+  }
+}
+
+template <class FT, int NI, int PAIRS, bool HALO>
 __global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int nnodes, int nh) {
   __shared__ DssNode<FT> sr[4];
   const int v = threadIdx.x;
@@ -125,61 +186,9 @@ __global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __re
   __syncthreads();
   if (node >= nnodes) return;
   const DssNode<FT>& R = sr[threadIdx.y];
-  const int cnt = R.cnt;
-  FT x0[NI][4], x1[NI][4];
-#pragma unroll
-  for (int k = 0; k < NI; ++k) {
-    const DssItem& I = A.it[k];
-    const bool pair = I.p1 != nullptr;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      x0[k][q] = FT(0); x1[k][q] = FT(0);
-      if (q < cnt && v < I.nlev) {
-        const int el = R.mem[q] >> 4, nd = R.mem[q] & 15;
-        if (el < nh) {
-          const size_t o = (size_t)el * I.estride + nd * I.nlev + v;
-          x0[k][q] = reinterpret_cast<const FT*>(I.p0)[o];
-          if (pair) x1[k][q] = reinterpret_cast<const FT*>(I.p1)[o];
-        } else {
-          const size_t o = (size_t)(el - nh) * I.gstride + nd * I.nlev + v;
-          x0[k][q] = reinterpret_cast<const FT*>(I.g0)[o];
-          if (pair) x1[k][q] = reinterpret_cast<const FT*>(I.g1)[o];
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NI; ++k) {
-    const DssItem& I = A.it[k];
-    if (v >= I.nlev) continue;
-    FT* p0 = reinterpret_cast<FT*>(I.p0);
-    FT* p1 = reinterpret_cast<FT*>(I.p1);
-    if (!p1) {
-      FT s = FT(0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < cnt) s += R.w[q] * x0[k][q];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < cnt && (R.mem[q] >> 4) < nh) p0[(size_t)(R.mem[q] >> 4) * I.estride + (R.mem[q] & 15) * I.nlev + v] = s;
-    } else {
-      FT su = FT(0), sv = FT(0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < cnt) {
-          FT uu = R.ai[q][0] * x0[k][q] + R.ai[q][1] * x1[k][q];
-          FT vv = R.ai[q][2] * x0[k][q] + R.ai[q][3] * x1[k][q];
-          su += R.w[q] * uu; sv += R.w[q] * vv;
-        }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < cnt && (R.mem[q] >> 4) < nh) {
-          const size_t o = (size_t)(R.mem[q] >> 4) * I.estride + (R.mem[q] & 15) * I.nlev + v;
-          p0[o] = R.a[q][0] * su + R.a[q][1] * sv;
-          p1[o] = R.a[q][2] * su + R.a[q][3] * sv;
-        }
-    }
-  }
+  const int cnt = R.cnt;  // uniform over the two warps of a node
+  if (cnt == 2) dss_body<FT, NI, PAIRS, 2, HALO>(A, R, cnt, v, nh);
+  else dss_body<FT, NI, PAIRS, 4, HALO>(A, R, cnt, v, nh);
 }
 
 // copy element slabs (all components of one field) of the listed elements into a packed buffer

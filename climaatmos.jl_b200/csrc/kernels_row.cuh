@@ -560,8 +560,8 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       if (v < nv) {
         FT lo = s_u3[o], hi = s_u3[o + 1];
         FT K = s_Kh[o] + FT(0.25) * (lo * (V.g33f[v] * lo) + hi * (V.g33f[v + 1] * hi));
-        FT etot = n_re[it] / s_rho[o];
-        FT T = fmax_(P.T_min_sgs, P.T_0 + ((etot - K - V.phic[v]) + P.R_d * P.T_0) / P.cv_d);
+        FT etot = n_re[it] * (FT(1) / s_rho[o]);
+        FT T = fmax_(P.T_min_sgs, P.T_0 + ((etot - K - V.phic[v]) + P.RT0) * P.icv);
         s_h[o] = etot + P.R_d * T;
       }
     }
