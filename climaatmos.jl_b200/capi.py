@@ -46,7 +46,9 @@ class Params(C.Structure):
                                           "divergence_damping_factor")] + [
         ("hyperdiff", C.c_int32), ("rayleigh_sponge", C.c_int32), ("zd_rayleigh", C.c_double),
         ("alpha_rayleigh_uh", C.c_double), ("alpha_rayleigh_w", C.c_double), ("viscous_sponge", C.c_int32),
-        ("zd_viscous", C.c_double), ("kappa_2_sponge", C.c_double), ("energy_upwinding", C.c_int32)]
+        ("zd_viscous", C.c_double), ("kappa_2_sponge", C.c_double), ("energy_upwinding", C.c_int32),
+        ("held_suarez", C.c_int32)] + [(n, C.c_double) for n in ("hs_day", "hs_sigma_b", "hs_dT_y", "hs_T_equator",
+                                                               "hs_dtheta_z", "hs_T_min", "MSLP")]
 
 
 class CachePtrs(C.Structure):
@@ -129,7 +131,8 @@ def make_params(P, N, grid) -> Params:
         hyperdiff=int(N.hyperdiff), rayleigh_sponge=int(N.rayleigh_sponge), zd_rayleigh=P.zd_rayleigh,
         alpha_rayleigh_uh=P.alpha_rayleigh_uh, alpha_rayleigh_w=P.alpha_rayleigh_w,
         viscous_sponge=int(N.viscous_sponge), zd_viscous=P.zd_viscous, kappa_2_sponge=P.kappa_2_sponge,
-        energy_upwinding=up)
+        energy_upwinding=up, held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
+        hs_T_equator=P.T_equator_dry, hs_dtheta_z=P.dtheta_z, hs_T_min=P.T_min_hs, MSLP=P.MSLP)
 
 
 def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1):

@@ -181,6 +181,14 @@ static Par<FT> make_par(const b200_ctx* c) {
   P.T_min_sgs = (FT)p.T_min_sgs; P.dt = (FT)p.dt;
   P.icv = (FT)(1.0 / p.cv_d); P.ip0 = (FT)(1.0 / p.p_ref_theta); P.dTs7 = (FT)((p.T_surf_ref - p.T_min_ref) / 7.0);
   P.RT0 = (FT)(p.R_d * p.T_0);
+  P.hs = p.held_suarez;
+  if (p.held_suarez) {
+    P.hs_ka = (FT)(1.0 / (40 * p.hs_day)); P.hs_ks = (FT)(1.0 / (4 * p.hs_day)); P.hs_kf = (FT)(1.0 / p.hs_day);
+    P.hs_sigb = (FT)p.hs_sigma_b; P.hs_isig = (FT)(1.0 / (1.0 - p.hs_sigma_b)); P.hs_dTy = (FT)p.hs_dT_y; P.hs_Teq = (FT)p.hs_T_equator;
+    P.hs_dthz = (FT)p.hs_dtheta_z; P.hs_Tmin = (FT)p.hs_T_min; P.hs_iMSLP = (FT)(1.0 / p.MSLP); P.hs_ikap = (FT)(p.cp_d / p.R_d);
+  } else {
+    P.hs_ka = P.hs_ks = P.hs_kf = P.hs_sigb = P.hs_isig = P.hs_dTy = P.hs_Teq = P.hs_dthz = P.hs_Tmin = P.hs_iMSLP = P.hs_ikap = (FT)0;
+  }
   P.nu4v = (FT)p.nu4_vorticity; P.nu4s = (FT)p.nu4_scalar; P.ddf = (FT)p.divergence_damping_factor;
   P.nh = c->dims.nh; P.nv = c->dims.nv;
   P.hyperdiff = p.hyperdiff; P.rayleigh = p.rayleigh_sponge; P.viscous = p.viscous_sponge; P.upwinding = p.energy_upwinding;
@@ -259,6 +267,7 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
       o[HG_COR1 * 16] = (FT)(c->dims.deep ? ai01 * fv : 0.0);
       o[HG_COR2 * 16] = (FT)(c->dims.deep ? ai11 * fv : 0.0);
       o[HG_COR3 * 16] = (FT)fw;
+      o[HG_SIN2 * 16] = (FT)(sin(lat) * sin(lat)); o[HG_COS2 * 16] = (FT)(cos(lat) * cos(lat));
       o[HG_DSSW * 16] = (FT)(WJ[h * 16 + n] / tot[h * 16 + n]);
       o[HG_A00 * 16] = (FT)a00; o[HG_A01 * 16] = (FT)a01; o[HG_A10 * 16] = (FT)a10; o[HG_A11 * 16] = (FT)a11;
       o[HG_AI00 * 16] = (FT)ai00; o[HG_AI01 * 16] = (FT)ai01; o[HG_AI10 * 16] = (FT)ai10; o[HG_AI11 * 16] = (FT)ai11;
@@ -575,6 +584,7 @@ template <class FT>
 static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
   const bool hd = c->prm.hyperdiff != 0;
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
+  if (c->legacy && c->prm.held_suarez) return fail("Held-Suarez forcing is only implemented in the current (row-layout) kernels");
   if (phase == 0 && c->legacy) {
     k_texp_a<FT><<<c->dims.nh, NT, smem_slabs<FT>(22), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                           (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);

@@ -24,10 +24,10 @@ constexpr int SLAB = NN * LVP;       // shared-memory words per field
 // horizontal geometry components, stored [h][HG_N][16]
 enum {
   HG_J2 = 0, HG_RJ2, HG_GI11, HG_GI12, HG_GI22, HG_GC11, HG_GC12, HG_GC22,
-  HG_COR1, HG_COR2, HG_COR3, HG_DSSW, HG_A00, HG_A01, HG_A10, HG_A11,
+  HG_COR1, HG_COR2, HG_COR3, HG_SIN2, HG_COS2, HG_DSSW, HG_A00, HG_A01, HG_A10, HG_A11,
   HG_AI00, HG_AI01, HG_AI10, HG_AI11, HG_N
 };
-constexpr int HG_ELEM = 11;  // components the element kernels stage (J2..COR3)
+constexpr int HG_ELEM = 13;  // components the element kernels stage (J2..COS2)
 
 // per-level constants (host-precomputed in double, stored in FT)
 template <class FT>
@@ -56,6 +56,8 @@ struct Par {
   FT nu4v, nu4s, ddf;
   int nh, nv;
   int hyperdiff, rayleigh, viscous, upwinding;
+  int hs;  // Held–Suarez forcing
+  FT hs_ka, hs_ks, hs_kf, hs_sigb, hs_isig, hs_dTy, hs_Teq, hs_dthz, hs_Tmin, hs_iMSLP, hs_ikap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -79,7 +81,7 @@ template <class FT> __device__ __forceinline__ FT pow7(FT x) {
 // (precomputed_quantities.jl:733-815 dry branch; refstate_thermodynamics.jl:22-168).
 template <class FT>
 struct Pt {
-  FT T, p, h, Pi, thp /*θ_v-θ_vr*/, thv, phir, sdr;
+  FT T, p, h, Pi, thp /*θ_v-θ_vr*/, thv, phir, sdr, lnPi;
 };
 template <class FT>
 __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K, FT Phi) {
@@ -94,6 +96,7 @@ __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K
   o.p = rho * P.R_d * o.T;
   FT lnPi = P.kappa * log_(o.p * P.ip0);
   o.Pi = exp_(lnPi);
+  o.lnPi = lnPi;
   FT rPi = FT(1) / o.Pi;
   FT Pi7 = pow7(o.Pi);
   FT Tr = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * Pi7;

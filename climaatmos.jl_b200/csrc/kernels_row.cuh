@@ -99,6 +99,7 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   }
   sput(s_U1, U1, j, v); sput(s_U2, U2, j, v);
   FT K[4], hh[4], ss[4], sd[4], Pi[4], th[4], sE[4], u3c[4];
+  FT hs_e[4], hs_d[4];  // Held–Suarez: ρe_tot relaxation and uₕ drag coefficient (held_suarez.jl:111-296)
   {
     FT u3h[4];
     sget(s_u3, u3h, j, v < nv ? v + 1 : v);
@@ -109,6 +110,14 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       hh[i] = t.h; Pi[i] = t.Pi; th[i] = t.thp; sE[i] = (K[i] + L.phi) - t.phir;
       sd[i] = P.cp_d * (t.T - P.T_0) + L.phi; ss[i] = sd[i] - t.sdr;
       u3c[i] = FT(0.5) * (u3[i] + u3h[i]);
+      hs_e[i] = FT(0); hs_d[i] = FT(0);
+      if (P.hs) {
+        const FT s2 = hg[HG_SIN2 * 16 + n0 + i], c2 = hg[HG_COS2 * 16 + n0 + i];
+        FT hf = fmax_(FT(0), (t.p * P.hs_iMSLP - P.hs_sigb) * P.hs_isig);
+        FT Teq = fmax_(P.hs_Tmin, (P.hs_Teq - P.hs_dTy * s2 - P.hs_dthz * (t.lnPi * P.hs_ikap) * c2) * t.Pi);
+        FT dRT = (P.hs_ka + (P.hs_ks - P.hs_ka) * hf * c2 * c2) * rho[i] * (t.p / (rho[i] * P.R_d) - Teq);
+        hs_e[i] = -dRT * P.cv_d; hs_d[i] = P.hs_kf * hf;
+      }
     }
   }
   sput(s_K, K, j, v);
@@ -136,7 +145,7 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     for (int i = 0; i < 4; ++i) {
       FT rjs = hg[HG_RJ2 * 16 + n0 + i] * L.sc;
       FT g1 = dxi4<FT, 0>(hh, i);
-      et[i] = -(FT(0.5) * (t[i] * rjs) + FT(0.5) * (hh[i] * wd[i] + (F1[i] * g1 + F2[i] * g2[i]) * rjs));
+      et[i] = -(FT(0.5) * (t[i] * rjs) + FT(0.5) * (hh[i] * wd[i] + (F1[i] * g1 + F2[i] * g2[i]) * rjs)) + hs_e[i];
     }
     if (any_visc) {  // β wdivₕ(ρ gradₕ s_d)  (viscous_sponge.jl:79)
       FT S1[4], S2[4];
@@ -227,6 +236,7 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       FT tot = hg[HG_COR3 * 16 + n0 + i] + wz;
       t1[i] += tot * U2[i]; t2[i] -= tot * U1[i];
       if (P.rayleigh) { t1[i] -= L.bruh * u1[i]; t2[i] -= L.bruh * u2[i]; }
+      if (P.hs) { t1[i] -= hs_d[i] * u1[i]; t2[i] -= hs_d[i] * u2[i]; }
     }
   }
   __syncthreads();  // s_U1, s_U2, s_K complete

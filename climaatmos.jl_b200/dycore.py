@@ -62,14 +62,15 @@ class AtmosSimulation:
 
     def __init__(self, FT=np.float32, h_elem=6, z_elem=10, z_max=30000.0, dz_bottom=500.0, dt=400.0,
                  rayleigh_sponge=False, viscous_sponge=False, hyperdiff=True, deep_atmosphere=True,
-                 initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter",
+                 initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter", rad=None,
                  params: DycoreParams | None = None, device=None, comms=None, grid=None):
         torch = _torch()
         self.torch = torch
         self.FT = np.dtype(FT).type
         self.params = params or DycoreParams()
         self.numerics = DycoreNumerics(dt=float(dt), hyperdiff=hyperdiff, rayleigh_sponge=rayleigh_sponge,
-                                       viscous_sponge=viscous_sponge, energy_upwinding=energy_q_tot_upwinding)
+                                       viscous_sponge=viscous_sponge, energy_upwinding=energy_q_tot_upwinding,
+                                       held_suarez=(rad == "held_suarez"))
         self.grid = grid or make_sphere_grid(FT=self.FT, h_elem=h_elem, z_elem=z_elem, z_max=z_max, dz_bottom=dz_bottom,
                                              radius=self.params.planet_radius, deep_atmosphere=deep_atmosphere)
         self.comms = comms  # parallel.DistributedComms or None

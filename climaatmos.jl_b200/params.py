@@ -29,6 +29,13 @@ class DycoreParams:
     alpha_rayleigh_w: float = 1.0
     zd_viscous: float = 15000.0
     kappa_2_sponge: float = 1.0e6
+    # Held–Suarez forcing (held_suarez.jl:188-237; ClimaParams defaults [UPSTREAM-RECALL])
+    day: float = 86400.0
+    sigma_b: float = 0.7
+    dT_y_dry: float = 60.0
+    T_equator_dry: float = 315.0
+    dtheta_z: float = 10.0
+    T_min_hs: float = 200.0
 
     @property
     def cp_d(self):

@@ -77,6 +77,8 @@ typedef struct {
   int32_t rayleigh_sponge; double zd_rayleigh, alpha_rayleigh_uh, alpha_rayleigh_w;
   int32_t viscous_sponge;  double zd_viscous, kappa_2_sponge;
   int32_t energy_upwinding; /* 0 none, 1 first_order, 3 vanleer_limiter */
+  /* Held–Suarez forcing (src/parameterized_tendencies/radiation/held_suarez.jl:111-296); flat surface */
+  int32_t held_suarez; double hs_day, hs_sigma_b, hs_dT_y, hs_T_equator, hs_dtheta_z, hs_T_min, MSLP;
 } b200_params;
 
 /* Optional device pointers to p.precomputed fields written by b200_cache_imp (any may be NULL).

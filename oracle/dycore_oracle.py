@@ -541,6 +541,18 @@ class Oracle:
             b = self.beta_rayleigh(c.z, P.alpha_rayleigh_uh)
             Ytc[:, 1] += -b * u1
             Ytc[:, 2] += -b * u2
+        if N.held_suarez:  # held_suarez.jl:111-296 (flat surface: z_surface = 0 ⇒ p_surface = MSLP)
+            lat = np.radians(self.grid.lat)[..., None]
+            s2, c2 = np.asarray(np.sin(lat) ** 2, dtype=FT), np.asarray(np.cos(lat) ** 2, dtype=FT)
+            sigma = p / FT(P.MSLP)
+            hf = np.maximum(FT(0), (sigma - FT(P.sigma_b)) / FT(1 - P.sigma_b))
+            k_a, k_s, k_f = FT(1 / (40 * P.day)), FT(1 / (4 * P.day)), FT(1 / P.day)
+            ppr = p / FT(P.p_ref_theta)
+            Teq = np.maximum(FT(P.T_min_hs), (FT(P.T_equator_dry) - FT(P.dT_y_dry) * s2 - FT(P.dtheta_z) * np.log(ppr) * c2) * ppr ** FT(P.kappa_d))
+            dRT = (k_a + (k_s - k_a) * hf * c2 * c2) * rho * (p / (rho * FT(P.R_d)) - Teq)
+            Ytc[:, 1] += -(k_f * hf) * u1
+            Ytc[:, 2] += -(k_f * hf) * u2
+            Ytc[:, 3] += -dRT * FT(P.cv_d)
         if N.viscous_sponge:  # viscous_sponge.jl:138-175
             bc, bf = self.beta_viscous(c.z), self.beta_viscous(f.z)
             (gd, cc) = self.vector_laplacian(u1, u2, np.zeros_like(u1), c)

@@ -136,6 +136,52 @@ def test_one_step_matches_oracle(FT, name, fused):
     sim.close()
 
 
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_held_suarez_config_matches_oracle(FT):
+    """BASELINE.json configs[0]: dry Held–Suarez he6/ze10 (Appendix B1: z_max 55 km, dz_bottom 500 m, dt 400 s,
+    no sponges, DecayingProfile initial state, rad = held_suarez): T_exp hook and two full steps."""
+    P = prm.DycoreParams(zd_rayleigh=35000.0, zd_viscous=35000.0)  # toml/sphere_held_suarez.toml
+    sim = dycore.AtmosSimulation(FT=FT, h_elem=6, z_elem=10, z_max=55000.0, dz_bottom=500.0, dt=400.0, rad="held_suarez",
+                                 initial_condition="DecayingProfile", params=P)
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    assert sim.numerics.held_suarez
+    Yc0, Yf0 = sim.Y.cpu()
+    # hook level, on a perturbed state with wind so that the drag term is exercised
+    Yc, Yf, rng = perturbed_state(sim, FT)
+    Yc[:, 1:3] += (1e5 * rng.standard_normal(Yc[:, 1:3].shape)).astype(FT)
+    Y = sim.to_device(Yc, Yf)
+    oc, of = Yc.astype(np.float64), Yf.astype(np.float64)
+    pc = o.set_implicit_precomputed_quantities(oc, of)
+    sim.set_implicit_precomputed_quantities(Y)
+    Yt = Y.zeros_like()
+    sim.remaining_tendency(Yt, None, Y)
+    check(*Yt.cpu(), *o.remaining_tendency(oc, of, pc), tol(FT, "tend"), "t_exp (Held-Suarez)")
+    # the forcing is actually active: switching it off changes the energy tendency
+    o.N.held_suarez = False
+    e_off = o.remaining_tendency(oc, of, pc)[0][:, 3]
+    o.N.held_suarez = True
+    assert rel(Yt.c.cpu().numpy()[:, 3], e_off) > 1e-3
+    sim.Y = sim.to_device(Yc0, Yf0)
+    oc, of = Yc0.astype(np.float64), Yf0.astype(np.float64)
+    for _ in range(2):
+        sim.step(fused=True)
+        oc, of = o.step(oc, of)
+    gc, gf = sim.Y.cpu()
+    t = tol(FT, "state")
+    assert rel(gc[:, 0], oc[:, 0]) <= t["rho"] and rel(gc[:, 3], oc[:, 3]) <= t["rhoe"]
+    # The flow starts from rest (0.1 K perturbation): after two steps the winds are ~1e-6 m/s, i.e. pure
+    # cancellation noise in Float32, so relative norms are meaningless.  Hold the velocity ERROR against the
+    # covariant norm of a 1 m/s wind instead: RMS error < 2e-4 m/s (Float32) / 1e-12 m/s (Float64).
+    g = sim.grid
+    one_ms = np.linalg.norm(np.broadcast_to(g.dxdxi[..., 0, 0, None], gc[:, 1].shape))
+    one_ms_w = np.linalg.norm(np.broadcast_to(g.dz_f, gf[:, 0].shape))
+    bar = 2e-4 if FT == np.float32 else 1e-12
+    for k in (1, 2):
+        assert np.linalg.norm(gc[:, k].astype(np.float64) - oc[:, k]) / one_ms < bar
+    assert np.linalg.norm(gf[:, 0].astype(np.float64) - of[:, 0]) / one_ms_w < bar
+    sim.close()
+
+
 def test_fused_and_hook_paths_agree_bitwise_in_structure():
     sim, P = make(np.float64, "he3ze63")
     Y0 = sim.Y.clone()
