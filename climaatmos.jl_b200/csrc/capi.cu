@@ -209,6 +209,7 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
     V.sc2i[v] = (FT)(1.0 / (s * s));
     V.dzc[v] = (FT)G->dz_c[v];
     V.mc[v] = (FT)(s * s * G->dz_c[v]);
+    V.rmc[v] = (FT)(1.0 / (s * s * G->dz_c[v]));
     V.phic[v] = (FT)(p->grav * G->z_c[v]);
     V.bruh[v] = (FT)(p->rayleigh_sponge && G->z_c[v] > p->zd_rayleigh ? p->alpha_rayleigh_uh * zeta(G->z_c[v], p->zd_rayleigh) : 0.0);
     V.bvc[v] = (FT)(p->viscous_sponge && G->z_c[v] > p->zd_viscous ? p->kappa_2_sponge * zeta(G->z_c[v], p->zd_viscous) : 0.0);

@@ -38,6 +38,7 @@ struct VLev {
   FT dzc[LV];    // vertical J at centres
   FT dzf[LV];    // vertical J at faces
   FT mc[LV];     // s_c^2 * dz_c   (J_c = J2 * mc)
+  FT rmc[LV];    // 1 / mc
   FT g33f[LV];   // 1 / dz_f^2
   FT phic[LV];   // grav * z_c
   FT dphif[LV];  // ᶠgradᵥ(Φ): phic[f]-phic[f-1], 0 on boundary faces
@@ -69,6 +70,9 @@ __device__ __forceinline__ float  log_(float a)  { return logf(a); }
 __device__ __forceinline__ double log_(double a) { return log(a); }
 __device__ __forceinline__ float  exp_(float a)  { return expf(a); }
 __device__ __forceinline__ double exp_(double a) { return exp(a); }
+// reciprocal (IEEE division; a MUFU.RCP + Newton variant measured slower in k2_exp_a: 171 vs 163 µs)
+__device__ __forceinline__ float  rcp_(float x)  { return 1.0f / x; }
+__device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
 __device__ __forceinline__ float  abs_(float a)  { return fabsf(a); }
 __device__ __forceinline__ double abs_(double a) { return fabs(a); }
 
@@ -88,7 +92,7 @@ __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K
   Pt<FT> o;
   // one reciprocal for ρ and Π, one log shared by Π = exp(κ ln(p/p0)) and ln Π (the first version used
   // powf + logf + 5 divisions per point; the XU pipe showed up at 12–16 % in ncu)
-  FT etot = rhoe * (FT(1) / rho);
+  FT etot = rhoe * rcp_(rho);
   FT eint = etot - K - Phi;
   // e_int = cv_d (T − T_0) − R_d T_0  (docs/src/thermodynamics.md:103-111)
   o.T = fmax_(P.T_min_sgs, P.T_0 + (eint + P.RT0) * P.icv);
@@ -97,7 +101,7 @@ __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K
   FT lnPi = P.kappa * log_(o.p * P.ip0);
   o.Pi = exp_(lnPi);
   o.lnPi = lnPi;
-  FT rPi = FT(1) / o.Pi;
+  FT rPi = rcp_(o.Pi);
   FT Pi7 = pow7(o.Pi);
   FT Tr = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * Pi7;
   o.thv = o.T * rPi;

@@ -101,14 +101,14 @@ __device__ __forceinline__ void fix_dn(FT (&hi)[16], const FT* x) {
 
 template <class FT>
 struct Lev {  // per-thread level constants
-  FT sc, mc, phi, g33lo, g33hi, bruh, bvc;        // centre v
+  FT sc, mc, rmc, phi, g33lo, g33hi, bruh, bvc;   // centre v
   FT sf, sf2i, dzf, mclo, sclo, bvf;              // face v (mclo/sclo: centre v-1)
 };
 template <class FT>
 __device__ __forceinline__ Lev<FT> load_lev(const VLev<FT>* __restrict__ V, int v, int nv) {
   Lev<FT> L;
   const int vc = v < nv ? v : nv - 1, vm = v > 0 ? v - 1 : 0, vf = v <= nv ? v : nv, vf1 = v + 1 <= nv ? v + 1 : nv;
-  L.sc = V->sc2i[vc]; L.mc = V->mc[vc]; L.phi = V->phic[vc]; L.g33lo = V->g33f[vf]; L.g33hi = V->g33f[vf1];
+  L.sc = V->sc2i[vc]; L.mc = V->mc[vc]; L.rmc = V->rmc[vc]; L.phi = V->phic[vc]; L.g33lo = V->g33f[vf]; L.g33hi = V->g33f[vf1];
   L.bruh = V->bruh[vc]; L.bvc = V->bvc[vc];
   L.sf = V->sf[vf]; L.sf2i = V->sf2i[vf]; L.dzf = V->dzf[vf]; L.mclo = V->mc[vm < nv ? vm : nv - 1];
   L.sclo = V->sc2i[vm < nv ? vm : nv - 1]; L.bvf = V->bvf[vf];

@@ -291,9 +291,9 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     sget(s_X1, h1, j, v + 1); sget(s_X2, h2, j, v + 1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      FT rm = rho[i] * L.mc;
-      gT[(16 + n0 + i) * nv + v] = t1[i] - FT(0.5) * (X1[i] + h1[i]) / rm;
-      gT[(32 + n0 + i) * nv + v] = t2[i] - FT(0.5) * (X2[i] + h2[i]) / rm;
+      FT irm = FT(0.5) * L.rmc * rcp_(rho[i]);
+      gT[(16 + n0 + i) * nv + v] = t1[i] - (X1[i] + h1[i]) * irm;
+      gT[(32 + n0 + i) * nv + v] = t2[i] - (X2[i] + h2[i]) * irm;
     }
   }
 }
@@ -485,7 +485,7 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       cd[it] = dtg * (-beta) - FT(1);
       if (f > 0 && f < nv) {
         FT rlo = s_rho[o - 1], rhi = s_rho[o];
-        FT irf = FT(1) / (FT(0.5) * (rlo + rhi));
+        FT irf = rcp_(FT(0.5) * (rlo + rhi));
         FT dPi = s_Pi[o] - s_Pi[o - 1];
         FT buoy = P.cp_d * (FT(0.5) * (s_thv[o - 1] + s_thv[o])) * dPi * irf;
         FT ur_lo = dtg * (irf * s_dp[o - 1] + buoy * FT(0.5)), ur_hi = dtg * (-irf * s_dp[o] + buoy * FT(0.5));
@@ -496,7 +496,7 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
         FT d = dtg * ((x_lo * k0 + x_hi * k0) - beta) - FT(1);
         FT u = dtg * (x_hi * (FT(0.5) * V.g33f[f + 1] * s_u3[o + 1]));
         // centre rows f-1 ("a") and f ("b"): ru_lo = A[k]/m_c[k], ru_hi = −A[k+1]/m_c[k], eu = ru·ᶠinterp(h)
-        FT ima = FT(1) / V.mc[f - 1], imb = FT(1) / V.mc[f];
+        FT ima = V.rmc[f - 1], imb = V.rmc[f];
         FT Am = s_A[o - 1], A0 = s_A[o], Ap = s_A[o + 1];
         FT hm = (f > 1) ? FT(0.5) * (s_h[o - 2] + s_h[o - 1]) : FT(0);
         FT h0 = FT(0.5) * (s_h[o - 1] + s_h[o]);
@@ -525,12 +525,12 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   if (threadIdx.x < 16) {  // Thomas sweep, one column per thread (BlockArrowheadSolve → Thomas)
     const FT *l = s_l + threadIdx.x * LVP, *d = s_d + threadIdx.x * LVP;
     FT *u = s_u + threadIdx.x * LVP, *r = s_r + threadIdx.x * LVP;
-    FT rd = FT(1) / d[0];
+    FT rd = rcp_(d[0]);
     FT cp = u[0] * rd, dp = r[0] * rd;
     u[0] = cp; r[0] = dp;
     for (int i = 1; i < nf; ++i) {
       FT li = l[i];
-      rd = FT(1) / (d[i] - li * cp);
+      rd = rcp_(d[i] - li * cp);
       cp = u[i] * rd;
       dp = (r[i] - li * dp) * rd;
       u[i] = cp; r[i] = dp;
@@ -547,7 +547,7 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     n_re[it] = FT(0);
     FT nr = FT(0), nu = FT(0);
     if (v < nv) {
-      FT im = FT(1) / V.mc[v];
+      FT im = V.rmc[v];
       FT A0 = s_A[o], Ap = s_A[o + 1], M0 = s_M[o], Mp = s_M[o + 1];
       FT h0 = (v > 0) ? FT(0.5) * (s_h[o - 1] + s_h[o]) : FT(0);
       FT hp = (v < nv - 1) ? FT(0.5) * (s_h[o] + s_h[o + 1]) : FT(0);
@@ -570,7 +570,7 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       if (v < nv) {
         FT lo = s_u3[o], hi = s_u3[o + 1];
         FT K = s_Kh[o] + FT(0.25) * (lo * (V.g33f[v] * lo) + hi * (V.g33f[v + 1] * hi));
-        FT etot = n_re[it] * (FT(1) / s_rho[o]);
+        FT etot = n_re[it] * rcp_(s_rho[o]);
         FT T = fmax_(P.T_min_sgs, P.T_0 + ((etot - K - V.phic[v]) + P.RT0) * P.icv);
         s_h[o] = etot + P.R_d * T;
       }
@@ -596,7 +596,7 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     const int idx = threadIdx.x + it * NT, n = idx >> 6, v = idx & 63, o = n * LVP + v;
     if (v < nv) {
       FT e2 = n_re[it];
-      if (P.upwinding != 0) e2 += dtg * (-(s_M[o + 1] - s_M[o]) / V.mc[v]);
+      if (P.upwinding != 0) e2 += dtg * (-(s_M[o + 1] - s_M[o]) * V.rmc[v]);
       gN[(48 + n) * nv + v] = e2;
     }
   }
