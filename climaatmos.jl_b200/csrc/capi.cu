@@ -98,6 +98,7 @@ struct b200_ctx {
   void *sendbuf = nullptr, *ghostbuf = nullptr;  // sized for the largest DSS call
   size_t halo_cap = 0;
   int64_t launches = 0;
+  int imp_kernel = 2;  // B200_IMP_KERNEL=2|3|4: variant of the fused implicit-stage kernel (2 is fastest; 3, 4 kept as A/B evidence)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   size_t nc() const { return (size_t)dims.nh * 4 * 16 * dims.nv; }
   size_t nf() const { return (size_t)dims.nh * 16 * (dims.nv + 1); }
@@ -329,6 +330,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   b200_ctx* c = new b200_ctx();
   c->dims = *d; c->prm = *p; c->ft = d->ft_bytes; c->rank = rank; c->nranks = nranks;
   if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
+  if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
   build_csr(T, c->h_off, c->h_mem);
   c->nnodes = (int)c->h_off.size() - 1;
   // keep only nodes with at least one local member
@@ -609,7 +611,7 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
                                         (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
   } else if (phase == 2 && hd && !c->legacy) {
-    k2_exp_c<FT><<<c->dims.nh, CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+    k2_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                        (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
   } else if (phase == 2 && hd) {
@@ -695,11 +697,20 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       if (dss_state(Uc, Uf)) return -1;
       const double dtg = dt * tb.ai[i][i];
       void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
-      if (fused && c->legacy) {
+      if (fused && (c->legacy == 1 || c->legacy == 2)) {
         CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
         k_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(18), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                  (FT*)Nc, (FT*)Nf, (FT)dtg);
+        LAUNCH_CHECK(c);
+      } else if (fused && c->imp_kernel == 4) {
+        k4_imp_stage<FT><<<c->dims.nh * 4, QT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
+                                                     (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+        LAUNCH_CHECK(c);
+      } else if (fused && c->imp_kernel == 3) {
+        const int ncols = c->dims.nh * 16;
+        k3_imp_stage<FT><<<(ncols + 7) / 8, 256, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
+                                                       (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, ncols);
         LAUNCH_CHECK(c);
       } else if (fused) {
         k2_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(11), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,

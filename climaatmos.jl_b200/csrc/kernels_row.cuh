@@ -299,8 +299,11 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
 }
 
 // ---------------------------------------------------------------------------------------------
+// The three outputs (uₕ, ρe_tot, u₃) are independent given the DSSed ∇² fields: blockIdx.y selects one, which
+// triples the number of CTAs and cuts registers per thread (the single-kernel version was memory-latency
+// bound: long-scoreboard 5.0 stall cycles per issue at 24 warps/SM, profiles/r1_ncu_summary.md).
 template <class FT>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 3 : 2))
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
 k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
          const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -308,19 +311,16 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* s_w = hg + HG_ELEM * 16;
   FT* s_a = s_w + SLAB;
   B200_ROW_PROLOGUE
+  const int part = blockIdx.y;
   const FT* gH = H + (size_t)e * 64 * nv;
   FT* gT = Ytc + (size_t)e * 64 * nv;
   FT* gF = Ytf + (size_t)e * 16 * nf;
-  FT rho[4], L1[4], L2[4], L3[4], Ls[4], old1[4], old2[4], old3[4], oldf[4];
-  ld4(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
-  ld4(L1, gH, nv, j, v, cv, FT(0)); ld4(L2, gH + 16 * nv, nv, j, v, cv, FT(0));
-  ld4(L3, gH + 32 * nv, nv, j, v, cv, FT(0)); ld4(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
-  // issue the read-modify-write loads early so they overlap the arithmetic
-  ld4(old1, gT + 16 * nv, nv, j, v, cv, FT(0)); ld4(old2, gT + 32 * nv, nv, j, v, cv, FT(0));
-  ld4(old3, gT + 48 * nv, nv, j, v, cv, FT(0)); ld4(oldf, gF, nf, j, v, fv, FT(0));
-  __syncthreads();
   FT a[4], b[4];
-  {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
+  if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
+    FT L1[4], L2[4], old1[4], old2[4];
+    ld4(L1, gH, nv, j, v, cv, FT(0)); ld4(L2, gH + 16 * nv, nv, j, v, cv, FT(0));
+    ld4(old1, gT + 16 * nv, nv, j, v, cv, FT(0)); ld4(old2, gT + 32 * nv, nv, j, v, cv, FT(0));
+    __syncthreads();
     FT U1[4], U2[4], D2[4], ze[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -344,9 +344,12 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       FT Qb = L.sc * (P.ddf * a[i] - (hg[HG_GC12 * 16 + n0 + i] * dz2 - hg[HG_GC22 * 16 + n0 + i] * dz1) * rJ2);
       if (cv) { gT[(16 + n0 + i) * nv + v] = old1[i] - P.nu4v * Qa; gT[(32 + n0 + i) * nv + v] = old2[i] - P.nu4v * Qb; }
     }
-  }
-  {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
-    FT Q1[4], Q2[4];
+  } else if (part == 1) {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
+    FT rho[4], Ls[4], old3[4], Q1[4], Q2[4];
+    ld4(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
+    ld4(old3, gT + 48 * nv, nv, j, v, cv, FT(0));
+    __syncthreads();
     deta4(Ls, md, vl, a);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -359,9 +362,12 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
 #pragma unroll
       for (int i = 0; i < 4; ++i) gT[(48 + n0 + i) * nv + v] = old3[i] - P.nu4s * (L.sc * b[i] * hg[HG_RJ2 * 16 + n0 + i]);
     }
-  }
-  {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
-    FT P1[4], P2[4], q[4], w[4];
+  } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
+    FT rho[4], L3[4], oldf[4], P1[4], P2[4], q[4], w[4];
+    ld4(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4(L3, gH + 32 * nv, nv, j, v, cv, FT(0));
+    ld4(oldf, gF, nf, j, v, fv, FT(0));
+    __syncthreads();
     deta4(L3, md, vl, a);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -600,6 +606,410 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       gN[(48 + n) * nv + v] = e2;
     }
   }
+}
+
+// k4_imp_stage — the same kernel on a QUARTER element: CTA = 64 threads = 4 columns (one GLL row), so every
+// barrier only joins two warps and 16 CTAs are resident per SM; level constants and metric terms are read
+// straight from global/L1 instead of being staged per CTA.
+constexpr int QT = 64;
+constexpr int QSLAB = 4 * LVP;
+template <class FT>
+__global__ void __launch_bounds__(QT, (sizeof(FT) == 4 ? 16 : 8))
+k4_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+             const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg) {
+  __shared__ FT slab[11][QSLAB];
+  const VLev<FT>& V = *vlev;  // level constants straight from global/L1 (each thread owns one level)
+  FT *s_rho = slab[0], *s_u3 = slab[1], *s_h = slab[2], *s_Kh = slab[3], *s_M = slab[4], *s_A = slab[5];
+  FT *s_Pi = slab[6], *s_thv = slab[7], *s_thp = slab[8], *s_phr = slab[9], *s_dp = slab[10];
+  FT *s_l = s_Pi, *s_d = s_thv, *s_u = s_thp, *s_r = s_phr;  // solver slabs alias dead thermodynamic slabs
+  const int e = blockIdx.x >> 2, nq0 = (blockIdx.x & 3) * 4, nv = P.nv, nf = nv + 1;
+  const FT* hg = hgeo + (size_t)e * HG_N * 16;
+  const FT kap = P.R_d / P.cv_d;
+  const FT* gY = Yc + (size_t)e * 64 * nv;
+  const FT* gYf = Yf + (size_t)e * 16 * nf;
+  FT* gN = Nc + (size_t)e * 64 * nv;
+  FT* gNf = Nf + (size_t)e * 16 * nf;
+  FT r_re[NIT], r_u1[NIT], r_u2[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, v = threadIdx.x, o = it * LVP + v;
+    r_re[it] = r_u1[it] = r_u2[it] = FT(0);
+    if (v < nv) {
+      s_rho[o] = gY[n * nv + v];
+      r_u1[it] = gY[(16 + n) * nv + v]; r_u2[it] = gY[(32 + n) * nv + v]; r_re[it] = gY[(48 + n) * nv + v];
+      gN[(16 + n) * nv + v] = r_u1[it]; gN[(32 + n) * nv + v] = r_u2[it];
+    }
+    if (v < nf) s_u3[o] = (v == 0 || v == nv) ? FT(0) : gYf[n * nf + v];
+  }
+  __syncthreads();
+  // ---- phase 1: centre thermodynamics
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, v = threadIdx.x, o = it * LVP + v;
+    if (v < nv) {
+      FT a1 = r_u1[it], a2 = r_u2[it];
+      FT c1 = hg[HG_GI11 * 16 + n] * a1 + hg[HG_GI12 * 16 + n] * a2;
+      FT c2 = hg[HG_GI12 * 16 + n] * a1 + hg[HG_GI22 * 16 + n] * a2;
+      FT Kh = FT(0.5) * ((a1 * c1 + a2 * c2) * V.sc2i[v]);
+      FT lo = s_u3[o], hi = s_u3[o + 1];
+      FT K = Kh + FT(0.25) * (lo * (V.g33f[v] * lo) + hi * (V.g33f[v + 1] * hi));
+      Pt<FT> t = thermo(P, s_rho[o], r_re[it], K, V.phic[v]);
+      s_Kh[o] = Kh; s_h[o] = t.h; s_Pi[o] = t.Pi; s_thv[o] = t.thv; s_thp[o] = t.thp; s_phr[o] = t.phir;
+      s_dp[o] = kap * (P.T_0 * P.cp_d - K - V.phic[v]) + (P.R_d - kap * P.cv_d) * t.T;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: face mass-flux pieces  M = ᶠinterp(ρJ)u³/J2,  A = dtγ ᶠinterp(ρJ) g³³/J2 (zero on boundaries)
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, f = threadIdx.x, o = it * LVP + f; (void)n;
+    if (f < nf) {
+      FT M = FT(0), A = FT(0);
+      if (f > 0 && f < nv) {
+        FT mr = rho_mface(V, s_rho, o, f);
+        A = dtg * mr * V.g33f[f];
+        M = mr * (V.g33f[f] * s_u3[o]);
+      }
+      s_M[o] = M; s_A[o] = A;
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: Schur tridiagonal and right-hand side of face row f (manual_sparse_jacobian.jl:746-868)
+  FT cl[NIT], cd[NIT], cu[NIT], cr[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, f = threadIdx.x, o = it * LVP + f; (void)n;
+    cl[it] = cu[it] = cr[it] = FT(0); cd[it] = FT(-1);
+    if (f < nf) {
+      FT beta = P.rayleigh ? V.brw[f] : FT(0);
+      cd[it] = dtg * (-beta) - FT(1);
+      if (f > 0 && f < nv) {
+        FT rlo = s_rho[o - 1], rhi = s_rho[o];
+        FT irf = rcp_(FT(0.5) * (rlo + rhi));
+        FT dPi = s_Pi[o] - s_Pi[o - 1];
+        FT buoy = P.cp_d * (FT(0.5) * (s_thv[o - 1] + s_thv[o])) * dPi * irf;
+        FT ur_lo = dtg * (irf * s_dp[o - 1] + buoy * FT(0.5)), ur_hi = dtg * (-irf * s_dp[o] + buoy * FT(0.5));
+        FT ue_lo = dtg * irf * kap, ue_hi = -ue_lo;
+        FT x_lo = irf * (-kap * rlo), x_hi = -irf * (-kap * rhi);
+        FT k0 = FT(0.5) * V.g33f[f] * s_u3[o];
+        FT l = dtg * (x_lo * (FT(0.5) * V.g33f[f - 1] * s_u3[o - 1]));
+        FT d = dtg * ((x_lo * k0 + x_hi * k0) - beta) - FT(1);
+        FT u = dtg * (x_hi * (FT(0.5) * V.g33f[f + 1] * s_u3[o + 1]));
+        // centre rows f-1 ("a") and f ("b"): ru_lo = A[k]/m_c[k], ru_hi = −A[k+1]/m_c[k], eu = ru·ᶠinterp(h)
+        FT ima = V.rmc[f - 1], imb = V.rmc[f];
+        FT Am = s_A[o - 1], A0 = s_A[o], Ap = s_A[o + 1];
+        FT hm = (f > 1) ? FT(0.5) * (s_h[o - 2] + s_h[o - 1]) : FT(0);
+        FT h0 = FT(0.5) * (s_h[o - 1] + s_h[o]);
+        FT hp = (f < nv - 1) ? FT(0.5) * (s_h[o] + s_h[o + 1]) : FT(0);
+        FT ru_lo_a = Am * ima, ru_hi_a = -A0 * ima, ru_lo_b = A0 * imb, ru_hi_b = -Ap * imb;
+        l += ur_lo * ru_lo_a + ue_lo * (ru_lo_a * hm);
+        d += ur_lo * ru_hi_a + ur_hi * ru_lo_b + ue_lo * (ru_hi_a * h0) + ue_hi * (ru_lo_b * h0);
+        u += ur_hi * ru_hi_b + ue_hi * (ru_hi_b * hp);
+        // R = dtγ·T_imp(U): face part + couplings to the centre residuals of rows f-1 and f
+        FT Mm = s_M[o - 1], M0 = s_M[o], Mp = s_M[o + 1];
+        FT rr_a = -dtg * (M0 - Mm) * ima, rr_b = -dtg * (Mp - M0) * imb;
+        FT re_a = -dtg * (M0 * h0 - Mm * hm) * ima, re_b = -dtg * (Mp * hp - M0 * h0) * imb;
+        FT tf = -(V.dphif[f] - (s_phr[o] - s_phr[o - 1]) + P.cp_d * (FT(0.5) * (s_thp[o - 1] + s_thp[o])) * dPi) - beta * s_u3[o];
+        cl[it] = l; cd[it] = d; cu[it] = u;
+        cr[it] = dtg * tf + ur_lo * rr_a + ur_hi * rr_b + ue_lo * re_a + ue_hi * re_b;
+      }
+    }
+  }
+  __syncthreads();  // all reads of the thermodynamic slabs are done: reuse them for the solver
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, f = threadIdx.x, o = it * LVP + f; (void)n;
+    if (f < nf) { s_l[o] = cl[it]; s_d[o] = cd[it]; s_u[o] = cu[it]; s_r[o] = cr[it]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {  // Thomas sweep, one column per thread (BlockArrowheadSolve → Thomas)
+    const FT *l = s_l + threadIdx.x * LVP, *d = s_d + threadIdx.x * LVP;
+    FT *u = s_u + threadIdx.x * LVP, *r = s_r + threadIdx.x * LVP;
+    FT rd = rcp_(d[0]);
+    FT cp = u[0] * rd, dp = r[0] * rd;
+    u[0] = cp; r[0] = dp;
+    for (int i = 1; i < nf; ++i) {
+      FT li = l[i];
+      rd = rcp_(d[i] - li * cp);
+      cp = u[i] * rd;
+      dp = (r[i] - li * dp) * rd;
+      u[i] = cp; r[i] = dp;
+    }
+    FT x = dp;
+    for (int i = nf - 2; i >= 0; --i) { x = r[i] - u[i] * x; r[i] = x; }
+  }
+  __syncthreads();
+  // ---- phase 5: U ← U − ΔU (back-substitution of the scalar rows)
+  FT n_re[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, v = threadIdx.x, o = it * LVP + v;
+    n_re[it] = FT(0);
+    FT nr = FT(0), nu = FT(0);
+    if (v < nv) {
+      FT im = V.rmc[v];
+      FT A0 = s_A[o], Ap = s_A[o + 1], M0 = s_M[o], Mp = s_M[o + 1];
+      FT h0 = (v > 0) ? FT(0.5) * (s_h[o - 1] + s_h[o]) : FT(0);
+      FT hp = (v < nv - 1) ? FT(0.5) * (s_h[o] + s_h[o + 1]) : FT(0);
+      FT x0 = s_r[o], x1 = s_r[o + 1];
+      FT rr = -dtg * (Mp - M0) * im, rre = -dtg * (Mp * hp - M0 * h0) * im;
+      nr = s_rho[o] - ((A0 * im) * x0 + (-Ap * im) * x1 - rr);
+      n_re[it] = r_re[it] - ((A0 * im * h0) * x0 + (-Ap * im * hp) * x1 - rre);
+    }
+    if (v < nf) nu = (v == 0 || v == nv) ? FT(0) : s_u3[o] - s_r[o];
+    // (only own entries of s_rho/s_u3 are read in this phase, so they can be updated in place)
+    if (v < nv) { s_rho[o] = nr; gN[n * nv + v] = nr; }
+    if (v < nf) { s_u3[o] = nu; gNf[n * nf + v] = nu; }
+  }
+  __syncthreads();
+  if (P.upwinding != 0) {
+    // ---- phase 6: h_tot of the updated state (cache_imp! after the Newton update; no transcendentals needed)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int n = nq0 + it, v = threadIdx.x, o = it * LVP + v;
+      if (v < nv) {
+        FT lo = s_u3[o], hi = s_u3[o + 1];
+        FT K = s_Kh[o] + FT(0.25) * (lo * (V.g33f[v] * lo) + hi * (V.g33f[v + 1] * hi));
+        FT etot = n_re[it] * rcp_(s_rho[o]);
+        FT T = fmax_(P.T_min_sgs, P.T_0 + ((etot - K - V.phic[v]) + P.RT0) * P.icv);
+        s_h[o] = etot + P.R_d * T;
+      }
+    }
+    __syncthreads();
+    // ---- phase 7: (upwinded − centred) enthalpy flux (implicit_tendency.jl:322-339)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int n = nq0 + it, f = threadIdx.x, o = it * LVP + f; (void)n;
+      if (f < nf) {
+        FT r = FT(0);
+        if (f > 0 && f < nv) {
+          FT w = V.g33f[f] * s_u3[o];
+          r = rho_mface(V, s_rho, o, f) * w * upwind_minus_central(P, s_h, o, f, nv, w);
+        }
+        s_M[o] = r;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int n = nq0 + it, v = threadIdx.x, o = it * LVP + v;
+    if (v < nv) {
+      FT e2 = n_re[it];
+      if (P.upwinding != 0) e2 += dtg * (-(s_M[o + 1] - s_M[o]) * V.rmc[v]);
+      gN[(48 + n) * nv + v] = e2;
+    }
+  }
+}
+
+
+}  // namespace b200
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// k3_imp_stage — fused implicit stage, third generation: ONE WARP PER COLUMN.
+//
+// Lane l owns levels l and l+32 of its column in registers; every vertical neighbour is a warp shuffle, the
+// Thomas sweep runs on lane 0 over a 1 KB warp-private shared buffer between two __syncwarp()s, and there is
+// NO block-level barrier at all (the second generation spent 3.8 stall cycles per issue at its 8
+// __syncthreads, profiles/r1_ncu_summary.md).  CTA = 8 warps = 8 columns; grid = columns/8.  Same arithmetic
+// as k2_imp_stage.  Column c of element e, node n: centre data at ((e·4+f)·16+n)·Nv, faces at (e·16+n)·(Nv+1).
+template <class FT>
+struct Col2 { FT a[2]; };
+
+template <class FT>
+__device__ __forceinline__ void up2(const FT (&x)[2], FT (&hi)[2], int lane) {  // value at level v+1
+  hi[0] = __shfl_down_sync(FULLM, x[0], 1);
+  FT t = __shfl_sync(FULLM, x[1], 0);
+  if (lane == 31) hi[0] = t;
+  hi[1] = __shfl_down_sync(FULLM, x[1], 1);
+}
+template <class FT>
+__device__ __forceinline__ void dn2(const FT (&x)[2], FT (&lo)[2], int lane) {  // value at level v-1
+  lo[0] = __shfl_up_sync(FULLM, x[0], 1);
+  lo[1] = __shfl_up_sync(FULLM, x[1], 1);
+  FT t = __shfl_sync(FULLM, x[0], 31);
+  if (lane == 0) lo[1] = t;
+}
+
+template <class FT>
+__global__ void __launch_bounds__(256)
+k3_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+             const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg, int ncols) {
+  __shared__ FT sws[8][4][LV];  // per-warp Thomas workspace: l, d, u, r
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 8 + w;
+  if (col >= ncols) return;  // whole warp exits together
+  const int e = col >> 4, n = col & 15, nv = P.nv, nf = nv + 1;
+  const FT kap = P.R_d / P.cv_d;
+  const FT* gY = Yc + ((size_t)e * 64 + n) * nv;
+  const FT* gYf = Yf + ((size_t)e * 16 + n) * nf;
+  FT* gN = Nc + ((size_t)e * 64 + n) * nv;
+  FT* gNf = Nf + ((size_t)e * 16 + n) * nf;
+  const size_t cs = (size_t)16 * nv;  // component stride
+  const FT g11 = hgeo[((size_t)e * HG_N + HG_GI11) * 16 + n], g12 = hgeo[((size_t)e * HG_N + HG_GI12) * 16 + n],
+           g22 = hgeo[((size_t)e * HG_N + HG_GI22) * 16 + n];
+  FT rho[2], re[2], u3[2], Kh[2];
+  FT mc[2], rmc[2], g33[2], phic[2], sc[2];
+  bool cv[2], fv[2], fin[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int v = lane + 32 * q;
+    cv[q] = v < nv; fv[q] = v < nf; fin[q] = v > 0 && v < nv;
+    const int vc = cv[q] ? v : nv - 1, vf = fv[q] ? v : nv;
+    mc[q] = vlev->mc[vc]; rmc[q] = vlev->rmc[vc]; phic[q] = vlev->phic[vc]; sc[q] = vlev->sc2i[vc]; g33[q] = vlev->g33f[vf];
+    rho[q] = cv[q] ? gY[v] : FT(1);
+    FT a1 = cv[q] ? gY[cs + v] : FT(0), a2 = cv[q] ? gY[2 * cs + v] : FT(0);
+    re[q] = cv[q] ? gY[3 * cs + v] : FT(0);
+    if (cv[q]) { gN[cs + v] = a1; gN[2 * cs + v] = a2; }
+    u3[q] = fin[q] ? gYf[v] : FT(0);  // cache_imp! boundary filter applied on load
+    FT c1 = g11 * a1 + g12 * a2, c2 = g12 * a1 + g22 * a2;
+    Kh[q] = FT(0.5) * ((a1 * c1 + a2 * c2) * sc[q]);
+  }
+  // ---- centre thermodynamics
+  FT w3[2], w3h[2], g33h[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) w3[q] = g33[q] * u3[q] * u3[q];
+  up2(w3, w3h, lane);
+  FT hh[2], Pi[2], thv[2], thp[2], phr[2], dp[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    FT K = Kh[q] + FT(0.25) * (w3[q] + w3h[q]);
+    Pt<FT> t = thermo(P, rho[q], re[q], K, phic[q]);
+    hh[q] = t.h; Pi[q] = t.Pi; thv[q] = t.thv; thp[q] = t.thp; phr[q] = t.phir;
+    dp[q] = kap * (P.T_0 * P.cp_d - K - phic[q]) + (P.R_d - kap * P.cv_d) * t.T;
+  }
+  // ---- face quantities: M = ᶠinterp(ρJ)u³/J2,  A = dtγ ᶠinterp(ρJ) g³³/J2  (zero on the boundary faces)
+  FT rm[2], rml[2], hl[2], hl2[2], hu[2], M[2], A[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) rm[q] = rho[q] * mc[q];
+  dn2(rm, rml, lane); dn2(hh, hl, lane); dn2(hl, hl2, lane); up2(hh, hu, lane);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    FT mr = FT(0.5) * (rml[q] + rm[q]);
+    A[q] = fin[q] ? dtg * mr * g33[q] : FT(0);
+    M[q] = fin[q] ? mr * (g33[q] * u3[q]) : FT(0);
+  }
+  FT Am[2], Ap[2], Mm[2], Mp[2], rl[2], Pil[2], thvl[2], thpl[2], phrl[2], dpl[2], u3m[2], u3p[2], g33m[2], g33p[2], rmcl[2];
+  dn2(A, Am, lane); up2(A, Ap, lane); dn2(M, Mm, lane); up2(M, Mp, lane);
+  dn2(rho, rl, lane); dn2(Pi, Pil, lane); dn2(thv, thvl, lane); dn2(thp, thpl, lane); dn2(phr, phrl, lane); dn2(dp, dpl, lane);
+  {
+    FT gu[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) gu[q] = g33[q] * u3[q];
+    dn2(gu, u3m, lane); up2(gu, u3p, lane);  // g³³u₃ at faces f-1 and f+1
+  }
+  dn2(rmc, rmcl, lane);
+  FT* sl = sws[w][0]; FT* sd = sws[w][1]; FT* su = sws[w][2]; FT* sr = sws[w][3];
+  FT ru_lo[2], ru_hi[2], eu_lo[2], eu_hi[2], rr[2], rre[2];  // centre-row pieces reused in the back-substitution
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int f = lane + 32 * q;
+    FT beta = P.rayleigh ? vlev->brw[fv[q] ? f : nv] : FT(0);
+    FT l = FT(0), d = dtg * (-beta) - FT(1), u = FT(0), r = FT(0);
+    FT hm = FT(0.5) * (hl2[q] + hl[q]), h0 = FT(0.5) * (hl[q] + hh[q]), hp = FT(0.5) * (hh[q] + hu[q]);
+    if (f <= 1) hm = FT(0);
+    if (f >= nv - 1) hp = FT(0);
+    // centre row f ("b") pieces (also used after the solve): ru_lo = A[f]/m_c[f], ru_hi = −A[f+1]/m_c[f]
+    ru_lo[q] = A[q] * rmc[q]; ru_hi[q] = -Ap[q] * rmc[q];
+    FT h0c = (f > 0) ? h0 : FT(0);
+    eu_lo[q] = ru_lo[q] * h0c; eu_hi[q] = ru_hi[q] * hp;
+    rr[q] = -dtg * (Mp[q] - M[q]) * rmc[q];
+    rre[q] = -dtg * (Mp[q] * hp - M[q] * h0c) * rmc[q];
+    if (fin[q]) {
+      FT irf = rcp_(FT(0.5) * (rl[q] + rho[q]));
+      FT dPi = Pi[q] - Pil[q];
+      FT buoy = P.cp_d * (FT(0.5) * (thvl[q] + thv[q])) * dPi * irf;
+      FT ur_lo = dtg * (irf * dpl[q] + buoy * FT(0.5)), ur_hi = dtg * (-irf * dp[q] + buoy * FT(0.5));
+      FT ue_lo = dtg * irf * kap, ue_hi = -ue_lo;
+      FT x_lo = irf * (-kap * rl[q]), x_hi = -irf * (-kap * rho[q]);
+      FT k0 = FT(0.5) * (g33[q] * u3[q]);
+      l = dtg * (x_lo * (FT(0.5) * u3m[q]));
+      d = dtg * ((x_lo * k0 + x_hi * k0) - beta) - FT(1);
+      u = dtg * (x_hi * (FT(0.5) * u3p[q]));
+      FT ima = rmcl[q];
+      FT ru_lo_a = Am[q] * ima, ru_hi_a = -A[q] * ima;
+      l += ur_lo * ru_lo_a + ue_lo * (ru_lo_a * hm);
+      d += ur_lo * ru_hi_a + ur_hi * ru_lo[q] + ue_lo * (ru_hi_a * h0) + ue_hi * (ru_lo[q] * h0);
+      u += ur_hi * ru_hi[q] + ue_hi * (ru_hi[q] * hp);
+      FT rr_a = -dtg * (M[q] - Mm[q]) * ima, re_a = -dtg * (M[q] * h0 - Mm[q] * hm) * ima;
+      FT tf = -(vlev->dphif[f] - (phr[q] - phrl[q]) + P.cp_d * (FT(0.5) * (thpl[q] + thp[q])) * dPi) - beta * u3[q];
+      r = dtg * tf + ur_lo * rr_a + ur_hi * rr[q] + ue_lo * re_a + ue_hi * rre[q];
+    }
+    if (fv[q]) { sl[f] = l; sd[f] = d; su[f] = u; sr[f] = r; }
+  }
+  __syncwarp();
+  if (lane == 0) {  // Thomas sweep (BlockArrowheadSolve → tridiagonal solve of the Schur complement)
+    FT rd = rcp_(sd[0]);
+    FT cp = su[0] * rd, dq = sr[0] * rd;
+    su[0] = cp; sr[0] = dq;
+    for (int i = 1; i < nf; ++i) {
+      FT li = sl[i];
+      rd = rcp_(sd[i] - li * cp);
+      cp = su[i] * rd;
+      dq = (sr[i] - li * dq) * rd;
+      su[i] = cp; sr[i] = dq;
+    }
+    FT x = dq;
+    for (int i = nf - 2; i >= 0; --i) { x = sr[i] - su[i] * x; sr[i] = x; }
+  }
+  __syncwarp();
+  FT x[2], xp[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) x[q] = fv[q] ? sr[lane + 32 * q] : FT(0);
+  up2(x, xp, lane);
+  // ---- U ← U − ΔU
+  FT nre[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int v = lane + 32 * q;
+    FT nr = rho[q] - (ru_lo[q] * x[q] + ru_hi[q] * xp[q] - rr[q]);
+    nre[q] = re[q] - (eu_lo[q] * x[q] + eu_hi[q] * xp[q] - rre[q]);
+    rho[q] = cv[q] ? nr : FT(1);
+    u3[q] = fin[q] ? u3[q] - x[q] : FT(0);
+    if (cv[q]) gN[v] = rho[q];
+    if (fv[q]) gNf[v] = u3[q];
+  }
+  if (P.upwinding != 0) {
+    // ---- cache_imp! after the Newton update (only h_tot is needed) and T_post_imp!
+#pragma unroll
+    for (int q = 0; q < 2; ++q) w3[q] = g33[q] * u3[q] * u3[q];
+    up2(w3, w3h, lane);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      FT K = Kh[q] + FT(0.25) * (w3[q] + w3h[q]);
+      FT etot = nre[q] * rcp_(rho[q]);
+      FT T = fmax_(P.T_min_sgs, P.T_0 + ((etot - K - phic[q]) + P.RT0) * P.icv);
+      hh[q] = etot + P.R_d * T;
+      rm[q] = rho[q] * mc[q];
+    }
+    dn2(rm, rml, lane); dn2(hh, hl, lane); dn2(hl, hl2, lane); up2(hh, hu, lane);
+    FT F[2], Fp[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int f = lane + 32 * q;
+      F[q] = FT(0);
+      if (fin[q]) {
+        FT wv = g33[q] * u3[q];
+        FT am = hl[q], ap = hh[q];
+        FT cen = FT(0.5) * (am + ap), upw;
+        if (P.upwinding == 3 && f >= 2 && f <= nv - 2) {
+          if (wv >= FT(0)) upw = am + vl_slope(hl2[q], am, ap) / FT(2) * (FT(1) - wv * P.dt);
+          else upw = ap - vl_slope(am, ap, hu[q]) / FT(2) * (FT(1) + wv * P.dt);
+        } else {
+          upw = wv >= FT(0) ? am : ap;
+        }
+        F[q] = FT(0.5) * (rml[q] + rm[q]) * wv * (upw - cen);
+      }
+    }
+    up2(F, Fp, lane);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) nre[q] += dtg * (-(Fp[q] - F[q]) * rmc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    if (cv[q]) gN[3 * cs + lane + 32 * q] = nre[q];
 }
 
 }  // namespace b200
