@@ -19,7 +19,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 SYMBOLS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_nccl_unique_id", "b200_cache_imp",
     "b200_t_exp_lim", "b200_t_imp", "b200_wfact", "b200_ldiv", "b200_t_post_imp", "b200_dss",
-    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase",
+    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase",
 ]
 
 
@@ -95,6 +95,8 @@ def load():
     lib.b200_create.argtypes = [C.POINTER(vp), C.POINTER(Dims), C.POINTER(Geometry), C.POINTER(Topology), C.POINTER(Params), vp, C.c_int, C.c_int]
     lib.b200_destroy.argtypes = [vp]
     lib.b200_nccl_unique_id.argtypes = [vp]
+    lib.b200_halo_export.argtypes = [vp, vp]
+    lib.b200_halo_import.argtypes = [vp, vp, vp, vp]
     lib.b200_cache_imp.argtypes = [vp, vp, vp, C.POINTER(CachePtrs), vp]
     lib.b200_t_exp_lim.argtypes = [vp, vp, vp, vp, vp, vp, vp, dbl, vp]
     lib.b200_t_exp_phase.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -193,6 +195,28 @@ def build_dss_csr(topo, elem_gid=None):
     nn, nm = C.c_int32(), C.c_int32()
     check(lib.b200_build_dss_csr(C.byref(T), _ptr(off), cap_n, _ptr(mem), cap_m, C.byref(nn), C.byref(nm)), "b200_build_dss_csr")
     return off[: nn.value + 1].copy(), mem[: nm.value].copy()
+
+
+def setup_peer_halo(ctx, part, comms):
+    """NVLink peer-memory halo: exchange cudaIpc handles of the ghost buffers over torch.distributed and map
+    the neighbours' buffers (falls back to the NCCL send/recv halo if IPC mapping is not possible)."""
+    lib = load()
+    buf = C.create_string_buffer(64)
+    check(lib.b200_halo_export(ctx, C.cast(buf, C.c_void_p)), "b200_halo_export")
+    mine = dict(handle=buf.raw, nh_ghost=int(part.nh_ghost), nbrs=[int(x) for x in part.neighbor_ranks],
+                recv_offset=[int(x) for x in part.recv_offset])
+    allinfo = [None] * comms.nranks
+    comms.dist.all_gather_object(allinfo, mine)
+    nn = len(part.neighbor_ranks)
+    handles = b"".join(allinfo[int(q)]["handle"] for q in part.neighbor_ranks)
+    their_off = np.array([allinfo[int(q)]["recv_offset"][allinfo[int(q)]["nbrs"].index(comms.rank)] for q in part.neighbor_ranks], dtype=np.int32)
+    their_nhg = np.array([allinfo[int(q)]["nh_ghost"] for q in part.neighbor_ranks], dtype=np.int32)
+    hb = C.create_string_buffer(handles, 64 * nn)
+    rc = lib.b200_halo_import(ctx, C.cast(hb, C.c_void_p), _ptr(their_off), _ptr(their_nhg))
+    ok = comms.all_true(rc == 0)
+    if not ok and comms.rank == 0:
+        print("warning: peer-memory halo unavailable (" + lib.b200_last_error().decode() + "); using NCCL send/recv")
+    return ok
 
 
 def debug_dss_csr(ctx):

@@ -97,6 +97,15 @@ struct b200_ctx {
   int n_send = 0;
   void *sendbuf = nullptr, *ghostbuf = nullptr;  // sized for the largest DSS call
   size_t halo_cap = 0;
+  // peer-memory halo
+  void* p2p_buf = nullptr;      // [2 parities][p2p_cap bytes] ghost slabs written by the neighbours, then int flags[nranks]
+  size_t p2p_cap = 0;
+  bool p2p_ready = false;
+  int p2p_counter = 0;
+  std::vector<void*> p2p_peer;  // mapped neighbour buffers
+  void** d_p2p_dst = nullptr;   // device array [n_neighbors] of destination base pointers (rewritten per call)
+  int** d_p2p_flags = nullptr;  // device array [n_neighbors]: address of my flag in neighbour q
+  int *d_slot_nbr = nullptr, *d_slot_dst = nullptr, *d_nbr_nhg = nullptr, *d_nbr_rank = nullptr;
   int64_t launches = 0;
   int imp_kernel = 2;  // B200_IMP_KERNEL=2|3|4: variant of the fused implicit-stage kernel (2 is fastest; 3, 4 kept as A/B evidence)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
@@ -377,7 +386,9 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
 extern "C" int b200_destroy(b200_ctx* c) {
   if (!c) return 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
+  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec);
+  for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
+  fr(c->p2p_buf); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
   fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
@@ -457,6 +468,65 @@ extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-memory halo set-up
+static size_t p2p_state_slab(const b200_ctx* c) { return (size_t)(4 * 16 * c->dims.nv + 16 * (c->dims.nv + 1)); }
+extern "C" int b200_halo_export(b200_ctx* c, void* handle64_out) {
+  if (c->nbr.empty()) return fail("b200_halo_export: context has no neighbours");
+  if (!c->p2p_buf) {
+    c->p2p_cap = p2p_state_slab(c) * (size_t)std::max(1, (int)c->dims.nh_ghost) * c->ft;
+    c->p2p_cap = (c->p2p_cap + 255) / 256 * 256;
+    CK(cudaMalloc(&c->p2p_buf, 2 * c->p2p_cap + sizeof(int) * (size_t)c->nranks));
+    CK(cudaMemset(c->p2p_buf, 0, 2 * c->p2p_cap + sizeof(int) * (size_t)c->nranks));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->p2p_buf));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64_out, &h, 64);
+  return 0;
+}
+extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t* their_recv_offset, const int32_t* their_nh_ghost) {
+  if (!c->p2p_buf) return fail("b200_halo_import: call b200_halo_export first");
+  const int nn = (int)c->nbr.size();
+  std::vector<int*> flags(nn);
+  c->p2p_peer.resize(nn);
+  for (int q = 0; q < nn; ++q) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)q, 64);
+    CK(cudaIpcOpenMemHandle(&c->p2p_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  // per send slot: which neighbour and which ghost slot over there
+  std::vector<int> slot_nbr(c->n_send), slot_dst(c->n_send), nhg(nn), ranks(nn);
+  for (int q = 0; q < nn; ++q) {
+    nhg[q] = their_nh_ghost[q]; ranks[q] = c->nbr[q];
+    for (int k = c->send_off[q]; k < c->send_off[q + 1]; ++k) { slot_nbr[k] = q; slot_dst[k] = their_recv_offset[q] + (k - c->send_off[q]); }
+    // my flag lives at index `rank` of neighbour q's flag array, which sits after its two parity blocks
+    size_t their_cap = (p2p_state_slab(c) * (size_t)std::max(1, nhg[q]) * c->ft + 255) / 256 * 256;
+    flags[q] = reinterpret_cast<int*>((char*)c->p2p_peer[q] + 2 * their_cap) + c->rank;
+  }
+  CK(cudaMalloc(&c->d_slot_nbr, std::max(1, c->n_send) * sizeof(int)));
+  CK(cudaMalloc(&c->d_slot_dst, std::max(1, c->n_send) * sizeof(int)));
+  CK(cudaMalloc(&c->d_nbr_nhg, nn * sizeof(int)));
+  CK(cudaMalloc(&c->d_nbr_rank, nn * sizeof(int)));
+  CK(cudaMalloc(&c->d_p2p_dst, 2 * nn * sizeof(void*)));
+  CK(cudaMalloc(&c->d_p2p_flags, nn * sizeof(int*)));
+  CK(cudaMemcpy(c->d_slot_nbr, slot_nbr.data(), c->n_send * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_slot_dst, slot_dst.data(), c->n_send * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_nbr_nhg, nhg.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_nbr_rank, ranks.data(), nn * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_p2p_flags, flags.data(), nn * sizeof(int*), cudaMemcpyHostToDevice));
+  // destination base pointers for parity 0 and parity 1
+  std::vector<void*> dst(2 * nn);
+  for (int q = 0; q < nn; ++q) {
+    size_t their_cap = (p2p_state_slab(c) * (size_t)std::max(1, nhg[q]) * c->ft + 255) / 256 * 256;
+    dst[q] = c->p2p_peer[q];
+    dst[nn + q] = (char*)c->p2p_peer[q] + their_cap;
+  }
+  CK(cudaMemcpy(c->d_p2p_dst, dst.data(), 2 * nn * sizeof(void*), cudaMemcpyHostToDevice));
+  c->p2p_ready = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // DSS: local gather–scatter, with a whole-slab halo exchange for elements owned by other ranks.
 struct DssField { void* ptr; int nf; int is_face; int kind; };
 
@@ -469,7 +539,29 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   size_t tot_slab = 0;
   for (int k = 0; k < nfields; ++k) tot_slab += (size_t)F[k].nf * 16 * (nv + F[k].is_face);
   const bool halo = c->comm != nullptr;
-  if (halo) {
+  const bool p2p = halo && c->p2p_ready && nfields <= 4 && tot_slab <= p2p_state_slab(c) && !getenv("B200_HALO_NCCL");
+  void* ghost_base = nullptr;
+  if (p2p) {
+    // peer-memory halo: pack straight into the neighbours' ghost buffers, raise flags, wait for theirs
+    const int nn = (int)c->nbr.size(), k = ++c->p2p_counter, par = k & 1;
+    P2PArgs PA;
+    PA.nfields = nfields;
+    long long goff = 0;
+    for (int f = 0; f < nfields; ++f) {
+      int slab = F[f].nf * 16 * (nv + F[f].is_face);
+      PA.f[f] = {F[f].ptr, slab, goff};
+      goff += slab;
+    }
+    if (c->n_send > 0) {
+      k_pack_p2p<FT><<<c->n_send, 256, 0, s>>>(PA, c->d_send_elems, c->d_slot_nbr, c->d_slot_dst, (FT* const*)(c->d_p2p_dst + par * nn), c->d_nbr_nhg);
+      LAUNCH_CHECK(c);
+    }
+    k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, k);
+    LAUNCH_CHECK(c);
+    k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, nn, k);
+    LAUNCH_CHECK(c);
+    ghost_base = (char*)c->p2p_buf + par * c->p2p_cap;
+  } else if (halo) {
     size_t need_s = tot_slab * c->n_send * sizeof(FT), need_g = tot_slab * c->dims.nh_ghost * sizeof(FT);
     if (need_s + need_g > c->halo_cap) {
       if (c->sendbuf) cudaFree(c->sendbuf);
@@ -500,13 +592,14 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
       so += (size_t)slab * c->n_send; go += (size_t)slab * c->dims.nh_ghost;
     }
     NK(g_nccl.GroupEnd());
+    ghost_base = c->ghostbuf;
   }
   size_t go = 0;
   for (int k = 0; k < nfields; ++k) {
     const int nlev = nv + F[k].is_face;
     const int estride = F[k].nf * 16 * nlev;
     FT* base = (FT*)F[k].ptr;
-    FT* gbase = halo ? (FT*)c->ghostbuf + go : nullptr;
+    FT* gbase = halo ? (FT*)ghost_base + go : nullptr;
     go += (size_t)estride * c->dims.nh_ghost;
     int comp = 0;
     auto add = [&](bool pair) -> int {

@@ -200,6 +200,44 @@ __global__ void k_pack(const FT* __restrict__ src, FT* __restrict__ dst, const i
   for (int i = threadIdx.x; i < slab; i += blockDim.x) d[i] = s[i];
 }
 
+// ---- peer-memory halo (NVLink P2P): the sender writes its boundary-element slabs straight into the
+// neighbour's ghost buffer (cudaIpc-mapped pointer) and then raises a flag there; no NCCL call, no staging copy.
+struct P2PField { const void* src; int slab; long long goff; };  // goff: offset of this field's ghost block per unit nh_ghost
+struct P2PArgs {
+  P2PField f[4];
+  int nfields;
+};
+// one block per (send slot); dst[q] = base pointer (already offset to the right parity) of neighbour q's ghost buffer
+template <class FT>
+__global__ void k_pack_p2p(P2PArgs A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
+                           const int* __restrict__ slot_dst /* ghost slot in the neighbour */, FT* const* __restrict__ dst,
+                           const int* __restrict__ nbr_nh_ghost) {
+  const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
+  FT* base = dst[q];
+  for (int k = 0; k < A.nfields; ++k) {
+    const FT* s = reinterpret_cast<const FT*>(A.f[k].src) + (size_t)e * A.f[k].slab;
+    FT* d = base + (size_t)A.f[k].goff * nbr_nh_ghost[q] + (size_t)g * A.f[k].slab;
+    for (int i = threadIdx.x; i < A.f[k].slab; i += blockDim.x) d[i] = s[i];
+  }
+}
+// raise my flag in every neighbour's memory (after the pack kernel has completed)
+__global__ void k_p2p_signal(int* const* __restrict__ peer_flags, int my_slot_count, int value) {
+  const int q = threadIdx.x;
+  if (q < my_slot_count) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(peer_flags[q]) = value;
+  }
+}
+// wait until every neighbour has raised its flag to `value` in my memory
+__global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict__ nbr_rank, int n, int value) {
+  const int q = threadIdx.x;
+  if (q < n) {
+    const volatile int* f = flags + nbr_rank[q];
+    while (*f < value) { __nanosleep(50); }
+    __threadfence_system();
+  }
+}
+
 constexpr int AXPY_MAX = 8;
 template <class FT>
 struct AxpyArgs {

@@ -89,6 +89,11 @@ class AtmosSimulation:
             Yc, Yf = Yc[self.part.elems_ext[: self.part.nh]], Yf[self.part.elems_ext[: self.part.nh]]
             self.ctx = capi.create_context(self.grid, self.params, self.numerics, part=self.part,
                                            nccl_id=comms.nccl_unique_id(), rank=comms.rank, nranks=comms.nranks)
+            import os as _os
+
+            self.peer_halo = False
+            if not _os.environ.get("B200_HALO_NCCL"):
+                self.peer_halo = capi.setup_peer_halo(self.ctx, self.part, comms)
         else:
             self.ctx = capi.create_context(self.grid, self.params, self.numerics)
         self.lib = capi.load()

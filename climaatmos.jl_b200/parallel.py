@@ -53,6 +53,14 @@ class DistributedComms:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_true(self, flag: bool) -> bool:
+        if self.nranks == 1:
+            return bool(flag)
+        dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
+        t = self.torch.tensor([1 if flag else 0], dtype=self.torch.int32, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
     def finalize(self):
         if self.nranks > 1 and self.dist.is_initialized():
             self.dist.destroy_process_group()

@@ -100,6 +100,14 @@ const char* b200_last_error(void);
 /* 128-byte NCCL unique id for the DSS halo communicator (rank 0 calls, host broadcasts). */
 int b200_nccl_unique_id(void* out128);
 
+/* Peer-memory DSS halo over NVLink (optional; the NCCL send/recv path is used until it is set up).
+ * b200_halo_export writes this rank's 64-byte cudaIpcMemHandle; after the host has gathered them,
+ * b200_halo_import maps the neighbours' buffers: handles[q] / their_recv_offset[q] (first ghost slot my
+ * slabs occupy in neighbour q) / their_nh_ghost[q], q in the order of topology.neighbor_ranks. */
+int b200_halo_export(b200_ctx*, void* handle64_out);
+int b200_halo_import(b200_ctx*, const void* handles, const int32_t* their_recv_offset,
+                     const int32_t* their_nh_ghost);
+
 /* cache_imp! — set_implicit_precomputed_quantities! (precomputed_quantities.jl:698-831):
  * applies the u₃ boundary filter to Yf IN PLACE and fills the optional precomputed fields. */
 int b200_cache_imp(b200_ctx*, void* Yc, void* Yf, const b200_cacheptrs* out, void* stream);
