@@ -18,6 +18,7 @@
 #include "kernels_implicit.cuh"
 #include "kernels_reg.cuh"
 #include "kernels_row.cuh"
+#include "kernels_pair.cuh"
 
 using namespace b200;
 
@@ -107,6 +108,7 @@ struct b200_ctx {
   int** d_p2p_flags = nullptr;  // device array [n_neighbors]: address of my flag in neighbour q
   int *d_slot_nbr = nullptr, *d_slot_dst = nullptr, *d_nbr_nhg = nullptr, *d_nbr_rank = nullptr;
   int64_t launches = 0;
+  int exp_kernel = 5;  // B200_EXP_KERNEL=2|5: scalar row kernels (k2_*) or packed FFMA2 row kernels (k5_*)
   int imp_kernel = 2;  // B200_IMP_KERNEL=2|3|4: variant of the fused implicit-stage kernel (2 is fastest; 3, 4 kept as A/B evidence)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   size_t nc() const { return (size_t)dims.nh * 4 * 16 * dims.nv; }
@@ -246,6 +248,17 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
     for (int k = 0; k < 16; ++k) { md[k] = (double)V.D[k]; md[16 + k] = (double)V.Dw[k]; mf[k] = (float)V.D[k]; mf[16 + k] = (float)V.Dw[k]; }
     if (sizeof(FT) == 4) CK(cudaMemcpyToSymbol(c_Df, mf, sizeof(mf)));
     else CK(cudaMemcpyToSymbol(c_Dd, md, sizeof(md)));
+    // paired layout for the FFMA2 kernels: [(w*4 + k)*2 + p] = (M_w[2p][k], M_w[2p+1][k])
+    float2 pf[16]; double2 pd[16];
+    for (int w = 0; w < 2; ++w)
+      for (int k = 0; k < 4; ++k)
+        for (int pp = 0; pp < 2; ++pp) {
+          double lo = md[w * 16 + (2 * pp) * 4 + k], hi = md[w * 16 + (2 * pp + 1) * 4 + k];
+          pd[(w * 4 + k) * 2 + pp] = make_double2(lo, hi);
+          pf[(w * 4 + k) * 2 + pp] = make_float2((float)lo, (float)hi);
+        }
+    if (sizeof(FT) == 4) CK(cudaMemcpyToSymbol(c_Pf, pf, sizeof(pf)));
+    else CK(cudaMemcpyToSymbol(c_Pd, pd, sizeof(pd)));
   }
   // ---- horizontal geometry
   std::vector<double> WJ((size_t)nht * 16), tot((size_t)nht * 16);
@@ -315,6 +328,8 @@ template <class FT>
 static int set_attrs() {
   CK(cudaFuncSetAttribute(k2_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
   CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
   CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
@@ -340,6 +355,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   c->dims = *d; c->prm = *p; c->ft = d->ft_bytes; c->rank = rank; c->nranks = nranks;
   if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
   if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
+  if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
   build_csr(T, c->h_off, c->h_mem);
   c->nnodes = (int)c->h_off.size() - 1;
   // keep only nodes with at least one local member
@@ -692,6 +708,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     k_exp_m<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                         (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
+  } else if (phase == 0 && c->exp_kernel == 5) {
+    k5_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                       (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+    LAUNCH_CHECK(c);
   } else if (phase == 0) {
     k2_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                        (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
@@ -702,6 +722,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
   } else if (phase == 2 && hd && c->legacy == 2) {
     k_exp_c<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                         (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+    LAUNCH_CHECK(c);
+  } else if (phase == 2 && hd && !c->legacy && c->exp_kernel == 5) {
+    k5_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
   } else if (phase == 2 && hd && !c->legacy) {
     k2_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,

@@ -1,0 +1,397 @@
+// kernels_pair.cuh — explicit-tendency kernels in the row layout of kernels_row.cuh with PACKED two-lane
+// arithmetic (pair.cuh): the four GLL nodes of a thread's row are held as two pairs (nodes 0|1 and 2|3), so every
+// 4×4 contraction costs 8 FFMA2/FMUL2 instead of 16 FFMA/FMUL and the pointwise metric algebra is halved too.
+// Same arithmetic, operation order and memory traffic as k2_exp_a / k2_exp_c (which stay selectable with
+// B200_EXP_KERNEL=2 for A/B runs); Float64 instantiates the same code on a scalar two-member struct.
+#pragma once
+#include "common.cuh"
+#include "kernels_row.cuh"
+#include "pair.cuh"
+
+namespace b200 {
+
+__constant__ float2 c_Pf[16];   // [(w*4 + k)*2 + p] = (M_w[2p][k], M_w[2p+1][k]),  w = 0: D, 1: Dw
+__constant__ double2 c_Pd[16];
+template <class FT> __device__ __forceinline__ P2<FT> cP(int idx);
+template <> __device__ __forceinline__ P2<float> cP<float>(int idx) {
+  P2<float> r;
+  r.v = *reinterpret_cast<const unsigned long long*>(&c_Pf[idx]);
+  return r;
+}
+template <> __device__ __forceinline__ P2<double> cP<double>(int idx) { return P2<double>(c_Pd[idx].x, c_Pd[idx].y); }
+
+template <class FT, int W>
+__device__ __forceinline__ void dxi4p(const P2<FT> (&a)[2], P2<FT> (&o)[2]) {
+  const FT a0 = a[0].lo(), a1 = a[0].hi(), a2 = a[1].lo(), a3 = a[1].hi();
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+    o[p] = fma2(cP<FT>((W * 4 + 3) * 2 + p), a3, fma2(cP<FT>((W * 4 + 2) * 2 + p), a2, fma2(cP<FT>((W * 4 + 1) * 2 + p), a1, cP<FT>((W * 4 + 0) * 2 + p) * a0)));
+}
+template <class FT>
+__device__ __forceinline__ P2<FT> shflp(const P2<FT>& a, int src) {
+  return P2<FT>(__shfl_sync(FULLM, a.lo(), src), __shfl_sync(FULLM, a.hi(), src));
+}
+template <class FT>
+__device__ __forceinline__ void deta4p(const P2<FT> (&a)[2], const FT (&m)[4], int vl, P2<FT> (&o)[2]) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    P2<FT> s = shflp(a[p], vl) * m[0];
+    s = fma2(shflp(a[p], vl + 8), m[1], s);
+    s = fma2(shflp(a[p], vl + 16), m[2], s);
+    s = fma2(shflp(a[p], vl + 24), m[3], s);
+    o[p] = s;
+  }
+}
+template <class FT, int W>
+__device__ __forceinline__ void div4p(const P2<FT> (&a1)[2], const P2<FT> (&a2)[2], const FT (&m)[4], int vl, P2<FT> (&o)[2]) {
+  P2<FT> t[2];
+  deta4p(a2, m, vl, o);
+  dxi4p<FT, W>(a1, t);
+  o[0] = o[0] + t[0]; o[1] = o[1] + t[1];
+}
+template <class FT>
+__device__ __forceinline__ void ld4p(P2<FT> (&a)[2], const FT* __restrict__ g, int nlev, int j, int v, bool ok, FT dflt) {
+  FT t[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = ok ? g[(j * 4 + i) * nlev + v] : dflt;
+  a[0] = P2<FT>(t[0], t[1]); a[1] = P2<FT>(t[2], t[3]);
+}
+template <class FT>
+__device__ __forceinline__ void st4p(const P2<FT> (&a)[2], FT* __restrict__ g, int nlev, int j, int v) {
+  g[(j * 4 + 0) * nlev + v] = a[0].lo(); g[(j * 4 + 1) * nlev + v] = a[0].hi();
+  g[(j * 4 + 2) * nlev + v] = a[1].lo(); g[(j * 4 + 3) * nlev + v] = a[1].hi();
+}
+template <class FT>
+__device__ __forceinline__ void sputp(FT* s, const P2<FT> (&a)[2], int j, int v) {
+  s[(j * 4 + 0) * LVP + v] = a[0].lo(); s[(j * 4 + 1) * LVP + v] = a[0].hi();
+  s[(j * 4 + 2) * LVP + v] = a[1].lo(); s[(j * 4 + 3) * LVP + v] = a[1].hi();
+}
+template <class FT>
+__device__ __forceinline__ void sgetp(const FT* s, P2<FT> (&a)[2], int j, int v) {
+  a[0] = P2<FT>(s[(j * 4 + 0) * LVP + v], s[(j * 4 + 1) * LVP + v]);
+  a[1] = P2<FT>(s[(j * 4 + 2) * LVP + v], s[(j * 4 + 3) * LVP + v]);
+}
+// metric pair of component c for nodes (2p, 2p+1) of this thread's row
+#define HGP(c, p) ldpair(&hg[(c) * 16 + n0 + 2 * (p)])
+// J2·G^{ab}·(g1, g2): contravariant flux components scaled by J2 (a pointwise 2×2 metric product)
+#define METRIC_FLUX(o1, o2, g1, g2, pre)                                                        \
+  _Pragma("unroll") for (int p = 0; p < 2; ++p) {                                               \
+    P2<FT> w_ = pre;                                                                            \
+    o1[p] = w_ * fma2(HGP(HG_GI12, p), g2[p], HGP(HG_GI11, p) * g1[p]);                         \
+    o2[p] = w_ * fma2(HGP(HG_GI22, p), g2[p], HGP(HG_GI12, p) * g1[p]);                         \
+  }
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
+k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+         const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H) {
+  using V = P2<FT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  FT* sx = hg + HG_ELEM * 16;
+  FT *s_u3 = sx, *s_r = sx + SLAB, *s_u1 = sx + 2 * SLAB, *s_u2 = sx + 3 * SLAB, *s_U1 = sx + 4 * SLAB, *s_U2 = sx + 5 * SLAB,
+     *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
+  B200_ROW_PROLOGUE
+  const bool interior = v > 0 && v < nv;
+  const FT* gY = Yc + (size_t)e * 64 * nv;
+  V rho[2], u1[2], u2[2], re[2], u3[2], U1[2], U2[2];
+  ld4p(rho, gY, nv, j, v, cv, FT(1)); ld4p(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4p(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
+  ld4p(re, gY + 48 * nv, nv, j, v, cv, FT(0)); ld4p(u3, Yf + (size_t)e * 16 * nf, nf, j, v, fv, FT(0));
+  sputp(s_u3, u3, j, v); sputp(s_r, rho, j, v); sputp(s_u1, u1, j, v); sputp(s_u2, u2, j, v);
+  __syncthreads();  // hg + first exchange slabs
+  V c1[2], c2[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    c1[p] = fma2(HGP(HG_GI12, p), u2[p], HGP(HG_GI11, p) * u1[p]);
+    c2[p] = fma2(HGP(HG_GI22, p), u2[p], HGP(HG_GI12, p) * u1[p]);
+    U1[p] = HGP(HG_J2, p) * c1[p]; U2[p] = HGP(HG_J2, p) * c2[p];
+  }
+  sputp(s_U1, U1, j, v); sputp(s_U2, U2, j, v);
+  V K[2], hh[2], ss[2], sd[2], Pi[2], th[2], sE[2], u3c[2], hs_e[2], hs_d[2];
+  {
+    V u3h[2];
+    sgetp(s_u3, u3h, j, v < nv ? v + 1 : v);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      V kh = fma2(u2[p], c2[p], u1[p] * c1[p]) * L.sc;
+      V kv = fma2(u3h[p], u3h[p] * L.g33hi, u3[p] * (u3[p] * L.g33lo)) * FT(0.5);
+      K[p] = (kh + kv) * FT(0.5);
+      u3c[p] = (u3[p] + u3h[p]) * FT(0.5);
+      Pt<FT> ta = thermo(P, rho[p].lo(), re[p].lo(), K[p].lo(), L.phi);
+      Pt<FT> tb = thermo(P, rho[p].hi(), re[p].hi(), K[p].hi(), L.phi);
+      hh[p] = V(ta.h, tb.h); Pi[p] = V(ta.Pi, tb.Pi); th[p] = V(ta.thp, tb.thp);
+      sE[p] = (K[p] + L.phi) - V(ta.phir, tb.phir);
+      sd[p] = fma2(V(ta.T, tb.T) - P.T_0, P.cp_d, V(L.phi));
+      ss[p] = sd[p] - V(ta.sdr, tb.sdr);
+      hs_e[p] = V(FT(0)); hs_d[p] = V(FT(0));
+      if (P.hs) {  // Held–Suarez forcing (held_suarez.jl:111-296), scalar per node
+        FT he[2], hd[2];
+        const Pt<FT>* tt[2] = {&ta, &tb};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const FT s2 = hg[HG_SIN2 * 16 + n0 + 2 * p + q], cc2 = hg[HG_COS2 * 16 + n0 + 2 * p + q];
+          const FT r = q ? rho[p].hi() : rho[p].lo();
+          FT hf = fmax_(FT(0), (tt[q]->p * P.hs_iMSLP - P.hs_sigb) * P.hs_isig);
+          FT Teq = fmax_(P.hs_Tmin, (P.hs_Teq - P.hs_dTy * s2 - P.hs_dthz * (tt[q]->lnPi * P.hs_ikap) * cc2) * tt[q]->Pi);
+          FT dRT = (P.hs_ka + (P.hs_ks - P.hs_ka) * hf * cc2 * cc2) * r * (tt[q]->p / (r * P.R_d) - Teq);
+          he[q] = -dRT * P.cv_d; hd[q] = P.hs_kf * hf;
+        }
+        hs_e[p] = V(he[0], he[1]); hs_d[p] = V(hd[0], hd[1]);
+      }
+    }
+  }
+  sputp(s_K, K, j, v);
+  FT* gT = Ytc + (size_t)e * 64 * nv;
+  FT* gH = H ? H + (size_t)e * 64 * nv : nullptr;
+  const bool any_visc = P.viscous && __any_sync(FULLM, L.bvc != FT(0));
+  V rjs[2];  // sc / J2
+#pragma unroll
+  for (int p = 0; p < 2; ++p) rjs[p] = HGP(HG_RJ2, p) * L.sc;
+  // ---- scalars: split-form flux divergences (advection.jl:48,59), viscous sponge on ρe_tot, ∇²s_d
+  {
+    V F1[2], F2[2], wd[2], t[2], g1[2], g2[2], G1[2], G2[2], et[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { F1[p] = rho[p] * U1[p]; F2[p] = rho[p] * U2[p]; }
+    div4p<FT, 1>(F1, F2, mw, vl, wd);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { wd[p] = wd[p] * rjs[p]; G1[p] = F1[p] * hh[p]; G2[p] = F2[p] * hh[p]; }
+    if (cv) { V nwd[2] = {-wd[0], -wd[1]}; st4p(nwd, gT, nv, j, v); }
+    div4p<FT, 1>(G1, G2, mw, vl, t);
+    deta4p(hh, md, vl, g2);
+    dxi4p<FT, 0>(hh, g1);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      V adv = fma2(F2[p], g2[p], F1[p] * g1[p]) * rjs[p];
+      et[p] = hs_e[p] - ((t[p] * rjs[p]) * FT(0.5) + fma2(hh[p], wd[p], adv) * FT(0.5));
+    }
+    if (any_visc) {  // β wdivₕ(ρ gradₕ s_d)  (viscous_sponge.jl:79)
+      V S1[2], S2[2];
+      deta4p(sd, md, vl, g2);
+      dxi4p<FT, 0>(sd, g1);
+      METRIC_FLUX(S1, S2, g1, g2, rho[p] * HGP(HG_J2, p))
+      div4p<FT, 1>(S1, S2, mw, vl, t);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) et[p] = fma2(t[p] * rjs[p], L.bvc, et[p]);
+    }
+    if (cv) st4p(et, gT + 48 * nv, nv, j, v);
+    if (gH) {  // ∇²(s_d − s_d,r)  (hyperdiffusion.jl:142-147)
+      V Q1[2], Q2[2];
+      deta4p(ss, md, vl, g2);
+      dxi4p<FT, 0>(ss, g1);
+      METRIC_FLUX(Q1, Q2, g1, g2, HGP(HG_J2, p))
+      div4p<FT, 1>(Q1, Q2, mw, vl, t);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) t[p] = t[p] * rjs[p];
+      if (cv) st4p(t, gH + 48 * nv, nv, j, v);
+    }
+  }
+  // ---- momentum: split-form PGF (advection.jl:82-88)
+  V t1[2], t2[2];
+  {
+    V tp[2], a[2], b[2], c[2], d[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) tp[p] = th[p] * Pi[p];
+    const FT hcp = P.cp_d * FT(0.5);
+    dxi4p<FT, 0>(sE, a); dxi4p<FT, 0>(Pi, b); dxi4p<FT, 0>(tp, c); dxi4p<FT, 0>(th, d);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) t1[p] = -(fma2((fma2(th[p], b[p], c[p]) - Pi[p] * d[p]), hcp, a[p]));
+    deta4p(sE, md, vl, a); deta4p(Pi, md, vl, b); deta4p(tp, md, vl, c); deta4p(th, md, vl, d);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) t2[p] = -(fma2((fma2(th[p], b[p], c[p]) - Pi[p] * d[p]), hcp, a[p]));
+  }
+  // ---- ∇²u (hyperdiffusion.jl:141) and viscous sponge on uₕ
+  {
+    V D2[2], ze[2], a[2], b[2], g1[2];
+    div4p<FT, 0>(U1, U2, md, vl, D2);
+    deta4p(u1, md, vl, a);
+    dxi4p<FT, 0>(u2, g1);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      D2[p] = D2[p] * HGP(HG_RJ2, p);
+      ze[p] = (g1[p] - a[p]) * HGP(HG_RJ2, p);
+    }
+    V dD1[2], dz1[2];
+    deta4p(D2, mw, vl, a); deta4p(ze, mw, vl, b);  // a = ∂̃₂D2, b = ∂̃₂ζ
+    dxi4p<FT, 1>(D2, dD1); dxi4p<FT, 1>(ze, dz1);
+    V L1[2], L2[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      V rJ2 = HGP(HG_RJ2, p);
+      L1[p] = (dD1[p] - (HGP(HG_GC11, p) * b[p] - HGP(HG_GC12, p) * dz1[p]) * rJ2) * L.sc;
+      L2[p] = (a[p] - (HGP(HG_GC12, p) * b[p] - HGP(HG_GC22, p) * dz1[p]) * rJ2) * L.sc;
+      if (P.viscous) { t1[p] = fma2(L1[p], L.bvc, t1[p]); t2[p] = fma2(L2[p], L.bvc, t2[p]); }
+    }
+    if (gH && cv) { st4p(L1, gH, nv, j, v); st4p(L2, gH + 16 * nv, nv, j, v); }
+    if (gH) {  // ∇²u₃ = wdivₕ(gradₕ(ᶜinterp(u₃))) on the flat shell
+      V P1[2], P2_[2];
+      deta4p(u3c, md, vl, a);
+      dxi4p<FT, 0>(u3c, g1);
+      METRIC_FLUX(P1, P2_, g1, a, HGP(HG_J2, p))
+      div4p<FT, 1>(P1, P2_, mw, vl, b);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) b[p] = b[p] * rjs[p];
+      if (cv) st4p(b, gH + 32 * nv, nv, j, v);
+    }
+    // (ᶜf³ + ᶜω³) × CT12(ᶜu), Rayleigh sponge, Held–Suarez drag
+    deta4p(u1, mw, vl, a);
+    dxi4p<FT, 1>(u2, g1);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      V tot = fma2(g1[p] - a[p], rjs[p], HGP(HG_COR3, p));
+      t1[p] = fma2(tot, U2[p], t1[p]); t2[p] = t2[p] - tot * U1[p];
+      if (P.rayleigh) { t1[p] = t1[p] - u1[p] * L.bruh; t2[p] = t2[p] - u2[p] * L.bruh; }
+      if (P.hs) { t1[p] = t1[p] - hs_d[p] * u1[p]; t2[p] = t2[p] - hs_d[p] * u2[p]; }
+    }
+  }
+  __syncthreads();  // s_U1, s_U2, s_K complete
+  // ---- face level v: ᶠω¹², mass flux, u₃ tendency (advection.jl:233-237,273-278)
+  V X1[2], X2[2];
+  {
+    V d3[2], d3x[2], rl[2], a1[2], a2[2], b1[2], b2[2], kl[2], lap[2];
+    deta4p(u3, mw, vl, d3);
+    dxi4p<FT, 1>(u3, d3x);
+    const int vm = v > 0 ? v - 1 : 0;
+    sgetp(s_r, rl, j, vm); sgetp(s_u1, a1, j, vm); sgetp(s_u2, a2, j, vm); sgetp(s_U1, b1, j, vm); sgetp(s_U2, b2, j, vm); sgetp(s_K, kl, j, vm);
+    const bool any_v3 = P.viscous && __any_sync(FULLM, L.bvf != FT(0));
+    if (any_v3) {  // β wdivₕ(gradₕ u₃) on faces (viscous_sponge.jl:64)
+      V R1[2], R2[2], g1[2], g2[2];
+      deta4p(u3, md, vl, g2);
+      dxi4p<FT, 0>(u3, g1);
+      METRIC_FLUX(R1, R2, g1, g2, HGP(HG_J2, p))
+      div4p<FT, 1>(R1, R2, mw, vl, lap);
+    }
+    V t3[2];
+    const FT cf = L.sf * L.dzf;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const V J2 = HGP(HG_J2, p), rJ2 = HGP(HG_RJ2, p);
+      V jt1 = fma2(J2 * cf, HGP(HG_COR1, p), d3[p]);
+      V jt2 = fma2(J2 * cf, HGP(HG_COR2, p), -d3x[p]);
+      V Vn, ub1, ub2, dk = V(FT(0));
+      if (interior) {
+        jt1 = jt1 - (u2[p] - a2[p]); jt2 = jt2 + (u1[p] - a1[p]);
+        Vn = fma2(rho[p], L.mc, rl[p] * L.mclo) * FT(0.5);
+        ub1 = (fma2(U1[p], L.sc, b1[p] * L.sclo) * FT(0.5)) * rJ2;
+        ub2 = (fma2(U2[p], L.sc, b2[p] * L.sclo) * FT(0.5)) * rJ2;
+        dk = K[p] - kl[p];
+      } else if (v == 0) {
+        Vn = rho[p] * L.mc; ub1 = (U1[p] * L.sc) * rJ2; ub2 = (U2[p] * L.sc) * rJ2;
+      } else {
+        Vn = rl[p] * L.mclo; ub1 = (b1[p] * L.sclo) * rJ2; ub2 = (b2[p] * L.sclo) * rJ2;
+      }
+      Vn = Vn * (u3[p] * L.g33lo);
+      X1[p] = jt2 * Vn; X2[p] = -(jt1 * Vn);
+      t3[p] = -(jt1 * ub2 - jt2 * ub1) - dk;
+      if (any_v3) t3[p] = fma2((lap[p] * L.sf2i) * rJ2, L.bvf, t3[p]);
+    }
+    if (fv) st4p(t3, Ytf + (size_t)e * 16 * nf, nf, j, v);
+  }
+  sputp(s_X1, X1, j, v); sputp(s_X2, X2, j, v);
+  __syncthreads();
+  if (cv) {
+    V h1[2], h2[2];
+    sgetp(s_X1, h1, j, v + 1); sgetp(s_X2, h2, j, v + 1);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      V irm = V(FT(0.5) * L.rmc * rcp_(rho[p].lo()), FT(0.5) * L.rmc * rcp_(rho[p].hi()));
+      t1[p] = t1[p] - (X1[p] + h1[p]) * irm;
+      t2[p] = t2[p] - (X2[p] + h2[p]) * irm;
+    }
+    st4p(t1, gT + 16 * nv, nv, j, v);
+    st4p(t2, gT + 32 * nv, nv, j, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
+k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
+  using V = P2<FT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  FT* s_w = hg + HG_ELEM * 16;
+  FT* s_a = s_w + SLAB;
+  B200_ROW_PROLOGUE
+  const int part = blockIdx.y;
+  const FT* gH = H + (size_t)e * 64 * nv;
+  FT* gT = Ytc + (size_t)e * 64 * nv;
+  FT* gF = Ytf + (size_t)e * 16 * nf;
+  V a[2], b[2], g1[2];
+  if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
+    V L1[2], L2[2], old1[2], old2[2];
+    ld4p(L1, gH, nv, j, v, cv, FT(0)); ld4p(L2, gH + 16 * nv, nv, j, v, cv, FT(0));
+    ld4p(old1, gT + 16 * nv, nv, j, v, cv, FT(0)); ld4p(old2, gT + 32 * nv, nv, j, v, cv, FT(0));
+    __syncthreads();
+    V U1[2], U2[2], D2[2], ze[2], dD1[2], dz1[2];
+    METRIC_FLUX(U1, U2, L1, L2, HGP(HG_J2, p))
+    div4p<FT, 0>(U1, U2, md, vl, D2);
+    deta4p(L1, md, vl, a);
+    dxi4p<FT, 0>(L2, g1);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      D2[p] = D2[p] * HGP(HG_RJ2, p);
+      ze[p] = (g1[p] - a[p]) * HGP(HG_RJ2, p);
+    }
+    deta4p(D2, mw, vl, a); deta4p(ze, mw, vl, b);
+    dxi4p<FT, 1>(D2, dD1); dxi4p<FT, 1>(ze, dz1);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      V rJ2 = HGP(HG_RJ2, p);
+      V Qa = (dD1[p] * P.ddf - (HGP(HG_GC11, p) * b[p] - HGP(HG_GC12, p) * dz1[p]) * rJ2) * L.sc;
+      V Qb = (a[p] * P.ddf - (HGP(HG_GC12, p) * b[p] - HGP(HG_GC22, p) * dz1[p]) * rJ2) * L.sc;
+      old1[p] = old1[p] - Qa * P.nu4v; old2[p] = old2[p] - Qb * P.nu4v;
+    }
+    if (cv) { st4p(old1, gT + 16 * nv, nv, j, v); st4p(old2, gT + 32 * nv, nv, j, v); }
+  } else if (part == 1) {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
+    V rho[2], Ls[2], old3[2], Q1[2], Q2[2];
+    ld4p(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4p(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
+    ld4p(old3, gT + 48 * nv, nv, j, v, cv, FT(0));
+    __syncthreads();
+    deta4p(Ls, md, vl, a);
+    dxi4p<FT, 0>(Ls, g1);
+    METRIC_FLUX(Q1, Q2, g1, a, rho[p] * HGP(HG_J2, p))
+    div4p<FT, 1>(Q1, Q2, mw, vl, b);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) old3[p] = old3[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
+    if (cv) st4p(old3, gT + 48 * nv, nv, j, v);
+  } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
+    V rho[2], L3[2], oldf[2], P1[2], P2_[2], q[2], w[2];
+    ld4p(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4p(L3, gH + 32 * nv, nv, j, v, cv, FT(0));
+    ld4p(oldf, gF, nf, j, v, fv, FT(0));
+    __syncthreads();
+    deta4p(L3, md, vl, a);
+    dxi4p<FT, 0>(L3, g1);
+    METRIC_FLUX(P1, P2_, g1, a, HGP(HG_J2, p))
+    div4p<FT, 1>(P1, P2_, mw, vl, b);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      q[p] = (b[p] * L.sc) * HGP(HG_RJ2, p);
+      w[p] = rho[p] * L.mc;
+    }
+    sputp(s_w, w, j, v); sputp(s_a, q, j, v);
+    __syncthreads();
+    if (fv) {
+      V wl[2], ql[2];
+      const int vm = v > 0 ? v - 1 : 0;
+      sgetp(s_w, wl, j, vm); sgetp(s_a, ql, j, vm);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        V val;
+        if (v == 0) val = q[p];
+        else if (v == nv) val = ql[p];
+        else {
+          V num = fma2(w[p], q[p], wl[p] * ql[p]), den = wl[p] + w[p];
+          val = V(num.lo() / den.lo(), num.hi() / den.hi());
+        }
+        oldf[p] = oldf[p] - val * P.nu4v;
+      }
+      st4p(oldf, gF, nf, j, v);
+    }
+  }
+}
+
+}  // namespace b200
