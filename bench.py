@@ -279,8 +279,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": sy(ms_e2e), "unit": "SYPD", "ms_per_step": ms_e2e, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "pipeline": "3 streams (copy-in / step / copy-out), double-buffered", "finite": e2e_ok},
-            "roofline": {"bound": "hbm", "kernel": "k_texp_a<float>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes,
+            "roofline": {"bound": "hbm", "kernel": "k5_exp_a<float> (T_exp_T_lim! pre-DSS kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at he30/ze63 (114.1 + 146.3 MB), from the
+                         # ncu --set full capture summarised in profiles/r1_ncu_full_packed_kernels.txt; scaled by elements
+                         "traffic": 260.4e6 * nh_local / 5400.0, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s"},
             "roofline_step": {"model_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms * 1e-3) / 1e9 / nranks,
                               "frac": step_bytes / (ms * 1e-3) / 1e9 / nranks / peak, "model": "54.5 S + 14 H (SURVEY.md §8d)"},
