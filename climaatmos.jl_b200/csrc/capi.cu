@@ -108,6 +108,8 @@ struct b200_ctx {
   int** d_p2p_flags = nullptr;  // device array [n_neighbors]: address of my flag in neighbour q
   int *d_slot_nbr = nullptr, *d_slot_dst = nullptr, *d_nbr_nhg = nullptr, *d_nbr_rank = nullptr;
   int64_t launches = 0;
+  cudaStream_t side = nullptr;           // side stream: T_imp = (U − temp)/dtγ runs concurrently with the T_exp kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int exp_kernel = 5;  // B200_EXP_KERNEL=2|5: scalar row kernels (k2_*) or packed FFMA2 row kernels (k5_*)
   int imp_kernel = 2;  // B200_IMP_KERNEL=2|3|4: variant of the fused implicit-stage kernel (2 is fastest; 3, 4 kept as A/B evidence)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
@@ -408,6 +410,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
   fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
+  if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
   return 0;
@@ -857,14 +860,28 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       }
       if (dss_state(Nc, Nf)) return -1;
       if (!fused && impl_cache_imp<FT>(c, Nc, Nf, nullptr, s)) return -1;
-      // T_imp[i] = (U − temp)/dtγ
-      if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), s)) return -1;
-      if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), s)) return -1;
+      // T_imp[i] = (U − temp)/dtγ.  It only feeds later increments, so the fused path runs this HBM-bound pass on
+      // a side stream, concurrently with the latency-bound T_exp kernels of the same stage.
+      cudaStream_t sd = s;
+      if (fused && !c->legacy) {
+        if (!c->side) {
+          CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+          CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(c->ev_fork, s));
+        CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        sd = c->side;
+      }
+      if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), sd)) return -1;
+      if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), sd)) return -1;
+      if (sd != s) { CK(cudaEventRecord(c->ev_join, sd)); }
       Uc = Nc; Uf = Nf;
     } else if (!fused) {
       if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;  // no-op on a filtered state; kept for the hook trace
     }
     if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], nullptr, nullptr, Uc, Uf, s)) return -1;
+    if (i > 0 && fused && !c->legacy) CK(cudaStreamWaitEvent(s, c->ev_join, 0));  // join the side stream
   }
   {
     const void* Tc[8]; const void* Tf[8]; double cf[8]; int n = 0;
