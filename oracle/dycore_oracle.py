@@ -58,6 +58,16 @@ class Geom:
         Ainv = np.linalg.inv(A)
         self.Ainv = c(Ainv[..., None, :, :] / s[None, None, None, :, None, None])  # [h,j,i,v,a,b]
 
+    def slice(self, sl):
+        """View of the geometry restricted to the element range ``sl`` (for the multi-threaded CPU arm)."""
+        import copy
+
+        g = copy.copy(self)
+        for k, v in self.__dict__.items():
+            if isinstance(v, np.ndarray):
+                setattr(g, k, v[sl])
+        return g
+
 
 class Oracle:
     def __init__(self, grid, params, numerics, FT=np.float64):
@@ -97,6 +107,20 @@ class Oracle:
             for e, i, j in m:
                 tot[e, j, i] = ssum
         self.dss_w = np.asarray(WJ2 / tot, dtype=FT)
+        self.lat_rad = np.radians(g.lat)[..., None]
+
+    def slice(self, sl):
+        """Shallow copy whose element-local arrays are views of the element range ``sl``; every tendency /
+        Jacobian / solve routine is element-local, so running them on slices gives bitwise the same numbers.
+        Used by ``step(..., pool=...)`` to run the CPU baseline on all host cores."""
+        import copy
+
+        o = copy.copy(self)
+        o.c, o.f = self.c.slice(sl), self.f.slice(sl)
+        for k in ("Phi", "gradv_Phi", "f3_c", "f1_f", "f2_f", "lat_rad"):
+            v = getattr(self, k)
+            setattr(o, k, None if v is None else v[sl])
+        return o
 
     # ------------------------------------------------------------------ horizontal SEM (A.1)
     def dx(self, a):  # Σ_k D[i,k] a[h,j,k,v]
@@ -485,7 +509,32 @@ class Oracle:
 
     def remaining_tendency(self, Yc, Yf, pc):
         """remaining_tendency.jl:48-58 (dry): returns (Ytc, Ytf); Yₜ_lim ≡ 0 without tracers."""
+        Ytc, Ytf, L = self._rt_pre(Yc, Yf, pc)
+        if L is not None:
+            self.weighted_dss([("c12", [L[0], L[1]]), ("scalar", [L[2]]), ("scalar", [L[3]])])  # :18-21
+            self._rt_post(Ytc, Ytf, Yc, L)
+        return Ytc, Ytf
+
+    def _rt_post(self, Ytc, Ytf, Yc, L):
+        """apply_hyperdiffusion_tendency! (hyperdiffusion.jl:247-307) on the DSSed ∇² fields (element-local)."""
+        FT, N, c = self.FT, self.N, self.c
+        rho = Yc[:, 0]
+        L1, L2, L3, Ls = L
+        (gd, cc) = self.vector_laplacian(L1, L2, L3, c)  # apply :273-277
+        ddf = FT(N.divergence_damping_factor)
+        Q1, Q2, Q3 = ddf * gd[0] - cc[0], ddf * gd[1] - cc[1], -cc[2]
+        Ytc[:, 1] -= self.nu4_vort * Q1
+        Ytc[:, 2] -= self.nu4_vort * Q2
+        Ytf[:, 0] -= self.nu4_vort * self.winterp_c2f(c.J * rho, Q3)
+        gL = self.grad(Ls)
+        gL = self.ct12(gL[0], gL[1], c)
+        Ytc[:, 3] -= self.nu4_scalar * self.wdiv(rho * gL[0], rho * gL[1], c)  # :291,307
+
+    def _rt_pre(self, Yc, Yf, pc):
+        """Everything of remaining_tendency! that is element-local before the DSS of the ∇² fields.
+        Returns (Ytc, Ytf, (∇²u₁, ∇²u₂, ∇²u₃, ∇²s_d) or None)."""
         FT, P, N, c, f = self.FT, self.P, self.N, self.c, self.f
+        L = None
         Ytc, Ytf = np.zeros_like(Yc), np.zeros_like(Yf)
         rho, u1, u2, rhoe = Yc[:, 0], Yc[:, 1], Yc[:, 2], Yc[:, 3]
         u3 = Yf[:, 0]
@@ -509,16 +558,7 @@ class Oracle:
             s_d = cp_d * (T - FT(P.T_0)) + self.Phi - self.sd_r(p)  # :142-147
             gs = self.grad(s_d)
             Ls = self.wdiv(*self.ct12(gs[0], gs[1], c), c)
-            self.weighted_dss([("c12", [L1, L2]), ("scalar", [L3]), ("scalar", [Ls])])  # :18-21
-            (gd, cc) = self.vector_laplacian(L1, L2, L3, c)  # apply :273-277
-            ddf = FT(N.divergence_damping_factor)
-            Q1, Q2, Q3 = ddf * gd[0] - cc[0], ddf * gd[1] - cc[1], -cc[2]
-            Ytc[:, 1] -= self.nu4_vort * Q1
-            Ytc[:, 2] -= self.nu4_vort * Q2
-            Ytf[:, 0] -= self.nu4_vort * self.winterp_c2f(c.J * rho, Q3)
-            gL = self.grad(Ls)
-            gL = self.ct12(gL[0], gL[1], c)
-            Ytc[:, 3] -= self.nu4_scalar * self.wdiv(rho * gL[0], rho * gL[1], c)  # :291,307
+            L = (L1, L2, L3, Ls)
         # ---- explicit_vertical_advection_tendency! advection.jl:205-290
         w3 = self.wcurl3(u1, u2, c)  # ᶜω³ :228
         o1, o2 = self.curlv_c2f(u1, u2)  # ᶠω¹² :233
@@ -542,7 +582,7 @@ class Oracle:
             Ytc[:, 1] += -b * u1
             Ytc[:, 2] += -b * u2
         if N.held_suarez:  # held_suarez.jl:111-296 (flat surface: z_surface = 0 ⇒ p_surface = MSLP)
-            lat = np.radians(self.grid.lat)[..., None]
+            lat = self.lat_rad
             s2, c2 = np.asarray(np.sin(lat) ** 2, dtype=FT), np.asarray(np.cos(lat) ** 2, dtype=FT)
             sigma = p / FT(P.MSLP)
             hf = np.maximum(FT(0), (sigma - FT(P.sigma_b)) / FT(1 - P.sigma_b))
@@ -563,32 +603,98 @@ class Oracle:
             gs = self.grad(cp_d * (T - FT(P.T_0)) + self.Phi)
             gs = self.ct12(gs[0], gs[1], c)
             Ytc[:, 3] += bc * self.wdiv(rho * gs[0], rho * gs[1], c)
-        return Ytc, Ytf
+        return Ytc, Ytf, L
 
     # ------------------------------------------------------------------ ARS343 step
-    def step(self, Yc, Yf, trace=None):
+    def _implicit_stage_local(self, Uc, Uf, dtg, log):
+        """cache_imp! → Wfact → T_imp! → ldiv! → U −= ΔU → cache_imp! → T_post_imp!, in place (element-local)."""
+        FT = self.FT
+        pc = self.set_implicit_precomputed_quantities(Uc, Uf)
+        log("cache_imp")
+        tc, tf = Uc.copy(), Uf.copy()
+        Jm = self.update_jacobian(Uc, Uf, pc, dtg)
+        log("wfact")
+        Rc, Rf = self.implicit_tendency(Uc, Uf, pc)
+        log("t_imp")
+        Rc = tc + FT(dtg) * Rc - Uc
+        Rf = tf + FT(dtg) * Rf - Uf
+        dc, df = self.ldiv(Jm, Rc, Rf)
+        log("ldiv")
+        Uc -= dc
+        Uf -= df
+        pc = self.set_implicit_precomputed_quantities(Uc, Uf)
+        log("cache_imp")
+        if self.N.energy_upwinding != "none":
+            pc_, pf_ = self.correct_implicit_advection_tendency(Uc, Uf, pc)
+            log("t_post_imp")
+            Uc += FT(dtg) * pc_
+            Uf += FT(dtg) * pf_
+        return tc, tf
+
+    def step(self, Yc, Yf, trace=None, pool=None, nchunks=1):
         """One IMEX-ARK (ARS343) step with one Newton iteration per implicit stage, hook order
         reconstructed from ClimaTimeSteppers 0.10.6 [UPSTREAM-RECALL] (DESIGN.md
-        "Step trace").  Returns the new (Yc, Yf)."""
+        "Step trace").  Returns the new (Yc, Yf).
+
+        ``pool`` (a ``concurrent.futures.ThreadPoolExecutor``) with ``nchunks`` > 1 runs every element-local
+        phase on element chunks in parallel (NumPy releases the GIL); the DSS stays global.  The result is
+        bitwise identical to the serial path (checked in tests/test_oracle_identities.py)."""
         from climaatmos_jl_b200.params import ars343
 
         FT = self.FT
         a_exp, a_imp, b_exp, b_imp, gam = ars343()
         dt = self.N.dt
         uc, uf = Yc, Yf
+        nel = Yc.shape[0]
         Texp, Timp = [None] * 4, [None] * 4
         log = (lambda s: trace.append(s)) if trace is not None else (lambda s: None)
+        nolog = lambda s: None
+        if pool is not None and nchunks > 1:
+            bounds = np.linspace(0, nel, nchunks + 1).astype(int)
+            chunks = [(slice(int(a), int(b)), self.slice(slice(int(a), int(b)))) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+
+            def pmap(fn):
+                return list(pool.map(lambda cs: fn(cs[1], cs[0]), chunks))
+        else:
+            chunks = [(slice(0, nel), self)]
+
+            def pmap(fn):
+                return [fn(self, slice(0, nel))]
 
         def increment(i_coefs_exp, i_coefs_imp):
-            Uc, Uf = uc.copy(), uf.copy()
-            for j in range(4):
-                if i_coefs_exp[j] != 0 and Texp[j] is not None:
-                    Uc += FT(dt * i_coefs_exp[j]) * Texp[j][0]
-                    Uf += FT(dt * i_coefs_exp[j]) * Texp[j][1]
-                if i_coefs_imp[j] != 0 and Timp[j] is not None:
-                    Uc += FT(dt * i_coefs_imp[j]) * Timp[j][0]
-                    Uf += FT(dt * i_coefs_imp[j]) * Timp[j][1]
+            Uc, Uf = np.empty_like(uc), np.empty_like(uf)
+
+            def work(sub, sl):
+                Uc[sl] = uc[sl]
+                Uf[sl] = uf[sl]
+                for j in range(4):
+                    if i_coefs_exp[j] != 0 and Texp[j] is not None:
+                        Uc[sl] += FT(dt * i_coefs_exp[j]) * Texp[j][0][sl]
+                        Uf[sl] += FT(dt * i_coefs_exp[j]) * Texp[j][1][sl]
+                    if i_coefs_imp[j] != 0 and Timp[j] is not None:
+                        Uc[sl] += FT(dt * i_coefs_imp[j]) * Timp[j][0][sl]
+                        Uf[sl] += FT(dt * i_coefs_imp[j]) * Timp[j][1][sl]
+
+            pmap(work)
             return Uc, Uf
+
+        def t_exp(Uc, Uf):
+            Ytc, Ytf = np.empty_like(Uc), np.empty_like(Uf)
+            Ls = [np.empty_like(Uc[:, 0]) for _ in range(4)] if self.N.hyperdiff else None
+
+            def pre(sub, sl):
+                pc = sub.set_implicit_precomputed_quantities(Uc[sl], Uf[sl])
+                a, b, L = sub._rt_pre(Uc[sl], Uf[sl], pc)
+                Ytc[sl], Ytf[sl] = a, b
+                if L is not None:
+                    for k in range(4):
+                        Ls[k][sl] = L[k]
+
+            pmap(pre)
+            if Ls is not None:
+                self.weighted_dss([("c12", [Ls[0], Ls[1]]), ("scalar", [Ls[2]]), ("scalar", [Ls[3]])])
+                pmap(lambda sub, sl: sub._rt_post(Ytc[sl], Ytf[sl], Uc[sl], tuple(a[sl] for a in Ls)))
+            return Ytc, Ytf
 
         for i in range(4):
             Uc, Uf = increment(a_exp[i], a_imp[i])
@@ -597,35 +703,27 @@ class Oracle:
                 log("dss")
             if a_imp[i][i] != 0:
                 dtg = dt * a_imp[i][i]
-                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
-                log("cache_imp")
-                tc, tf = Uc.copy(), Uf.copy()
-                Jm = self.update_jacobian(Uc, Uf, pc, dtg)
-                log("wfact")
-                Rc, Rf = self.implicit_tendency(Uc, Uf, pc)
-                log("t_imp")
-                Rc = tc + FT(dtg) * Rc - Uc
-                Rf = tf + FT(dtg) * Rf - Uf
-                dc, df = self.ldiv(Jm, Rc, Rf)
-                log("ldiv")
-                Uc -= dc
-                Uf -= df
-                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
-                log("cache_imp")
-                if self.N.energy_upwinding != "none":
-                    pc_, pf_ = self.correct_implicit_advection_tendency(Uc, Uf, pc)
-                    log("t_post_imp")
-                    Uc += FT(dtg) * pc_
-                    Uf += FT(dtg) * pf_
+                tc, tf = np.empty_like(Uc), np.empty_like(Uf)
+
+                def imp(sub, sl, first=[True]):
+                    lg = log if sl.start == 0 else nolog
+                    a, b = sub._implicit_stage_local(Uc[sl], Uf[sl], dtg, lg)
+                    tc[sl], tf[sl] = a, b
+
+                pmap(imp)
                 self.dss_state(Uc, Uf)
                 log("dss")
-                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
                 log("cache_imp")
-                Timp[i] = ((Uc - tc) / FT(dtg), (Uf - tf) / FT(dtg))
+                Timp[i] = (np.empty_like(Uc), np.empty_like(Uf))
+
+                def diff(sub, sl):
+                    Timp[i][0][sl] = (Uc[sl] - tc[sl]) / FT(dtg)
+                    Timp[i][1][sl] = (Uf[sl] - tf[sl]) / FT(dtg)
+
+                pmap(diff)
             else:
-                pc = self.set_implicit_precomputed_quantities(Uc, Uf)
                 log("cache_imp")
-            Texp[i] = self.remaining_tendency(Uc, Uf, pc)
+            Texp[i] = t_exp(Uc, Uf)
             log("t_exp")
         uc, uf = increment(b_exp, b_imp)
         self.dss_state(uc, uf)
