@@ -25,7 +25,7 @@ SYMBOLS = [
 
 class Dims(C.Structure):
     _fields_ = [("nh", C.c_int32), ("nh_ghost", C.c_int32), ("nv", C.c_int32), ("nq", C.c_int32),
-                ("ft_bytes", C.c_int32), ("deep", C.c_int32)]
+                ("ft_bytes", C.c_int32), ("deep", C.c_int32), ("n_tracers", C.c_int32)]
 
 
 class Geometry(C.Structure):
@@ -47,7 +47,7 @@ class Params(C.Structure):
         ("hyperdiff", C.c_int32), ("rayleigh_sponge", C.c_int32), ("zd_rayleigh", C.c_double),
         ("alpha_rayleigh_uh", C.c_double), ("alpha_rayleigh_w", C.c_double), ("viscous_sponge", C.c_int32),
         ("zd_viscous", C.c_double), ("kappa_2_sponge", C.c_double), ("energy_upwinding", C.c_int32),
-        ("held_suarez", C.c_int32)] + [(n, C.c_double) for n in ("hs_day", "hs_sigma_b", "hs_dT_y", "hs_T_equator",
+        ("tracer_upwinding", C.c_int32), ("held_suarez", C.c_int32)] + [(n, C.c_double) for n in ("hs_day", "hs_sigma_b", "hs_dT_y", "hs_T_equator",
                                                                "hs_dtheta_z", "hs_T_min", "MSLP")]
 
 
@@ -133,11 +133,11 @@ def make_params(P, N, grid) -> Params:
         hyperdiff=int(N.hyperdiff), rayleigh_sponge=int(N.rayleigh_sponge), zd_rayleigh=P.zd_rayleigh,
         alpha_rayleigh_uh=P.alpha_rayleigh_uh, alpha_rayleigh_w=P.alpha_rayleigh_w,
         viscous_sponge=int(N.viscous_sponge), zd_viscous=P.zd_viscous, kappa_2_sponge=P.kappa_2_sponge,
-        energy_upwinding=up, held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
+        energy_upwinding=up, tracer_upwinding={"none": 0, "first_order": 1, "vanleer_limiter": 3}[N.tracer_upwinding], held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
         hs_T_equator=P.T_equator_dry, hs_dtheta_z=P.dtheta_z, hs_T_min=P.T_min_hs, MSLP=P.MSLP)
 
 
-def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1):
+def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1, n_tracers: int = 0):
     """b200_create from a ``SphereGrid`` (or one rank's partition of it, see partition.py)."""
     lib = load()
     ft = 4 if np.dtype(grid.FT) == np.float32 else 8
@@ -164,7 +164,7 @@ def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: in
                      n_neighbors=len(part.neighbor_ranks), neighbor_ranks=arr(part.neighbor_ranks, np.int32),
                      send_offset=arr(part.send_offset, np.int32), send_elems=arr(part.send_elems, np.int32),
                      recv_offset=arr(part.recv_offset, np.int32), elem_gid=arr(part.elems_ext, np.int64))
-    dims = Dims(nh=nh, nh_ghost=ng, nv=grid.nv, nq=grid.nq, ft_bytes=ft, deep=int(grid.deep))
+    dims = Dims(nh=nh, nh_ghost=ng, nv=grid.nv, nq=grid.nq, ft_bytes=ft, deep=int(grid.deep), n_tracers=int(n_tracers))
     G = Geometry(dxdxi=arr(grid.dxdxi[elems], np.float64), J2=arr(grid.J2[elems], np.float64),
                  lat=arr(grid.lat[elems], np.float64), gll_w=arr(grid.wq, np.float64), gll_D=arr(grid.D, np.float64),
                  z_c=arr(grid.z_c, np.float64), z_f=arr(grid.z_f, np.float64), dz_c=arr(grid.dz_c, np.float64),

@@ -113,7 +113,8 @@ struct b200_ctx {
   int exp_kernel = 5;  // B200_EXP_KERNEL=2|5: scalar row kernels (k2_*) or packed FFMA2 row kernels (k5_*)
   int imp_kernel = 2;  // B200_IMP_KERNEL=2|3|4: variant of the fused implicit-stage kernel (2 is fastest; 3, 4 kept as A/B evidence)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
-  size_t nc() const { return (size_t)dims.nh * 4 * 16 * dims.nv; }
+  int ncf() const { return 4 + dims.n_tracers; }
+  size_t nc() const { return (size_t)dims.nh * ncf() * 16 * dims.nv; }
   size_t nf() const { return (size_t)dims.nh * 16 * (dims.nv + 1); }
 };
 
@@ -204,7 +205,7 @@ static Par<FT> make_par(const b200_ctx* c) {
     P.hs_ka = P.hs_ks = P.hs_kf = P.hs_sigb = P.hs_isig = P.hs_dTy = P.hs_Teq = P.hs_dthz = P.hs_Tmin = P.hs_iMSLP = P.hs_ikap = (FT)0;
   }
   P.nu4v = (FT)p.nu4_vorticity; P.nu4s = (FT)p.nu4_scalar; P.ddf = (FT)p.divergence_damping_factor;
-  P.nh = c->dims.nh; P.nv = c->dims.nv;
+  P.nh = c->dims.nh; P.nv = c->dims.nv; P.ncf = c->ncf(); P.tupw = p.tracer_upwinding;
   P.hyperdiff = p.hyperdiff; P.rayleigh = p.rayleigh_sponge; P.viscous = p.viscous_sponge; P.upwinding = p.energy_upwinding;
   return P;
 }
@@ -332,6 +333,7 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
   CK(cudaFuncSetAttribute(k5_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
   CK(cudaFuncSetAttribute(k5_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
+  CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
@@ -350,6 +352,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (d->nq != 4) return fail("b200_create: only Nq = 4 (nh_poly = 3) is supported");
   if (d->nv + 1 > LV || d->nv < 2) return fail("b200_create: need 2 <= nv <= 63");
   if (d->ft_bytes != 4 && d->ft_bytes != 8) return fail("b200_create: ft_bytes must be 4 or 8");
+  if (d->n_tracers < 0 || d->n_tracers > 4) return fail("b200_create: 0 <= n_tracers <= 4");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("b200_create: no CUDA device (this library has no CPU fallback)");
@@ -358,6 +361,10 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
   if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
+  if (d->n_tracers > 0 && (c->legacy || c->imp_kernel != 2)) {
+    delete c;
+    return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
+  }
   build_csr(T, c->h_off, c->h_mem);
   c->nnodes = (int)c->h_off.size() - 1;
   // keep only nodes with at least one local member
@@ -488,7 +495,7 @@ extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc
 
 // ---------------------------------------------------------------------------------------------
 // Peer-memory halo set-up
-static size_t p2p_state_slab(const b200_ctx* c) { return (size_t)(4 * 16 * c->dims.nv + 16 * (c->dims.nv + 1)); }
+static size_t p2p_state_slab(const b200_ctx* c) { return (size_t)(c->ncf() * 16 * c->dims.nv + 16 * (c->dims.nv + 1)); }
 extern "C" int b200_halo_export(b200_ctx* c, void* handle64_out) {
   if (c->nbr.empty()) return fail("b200_halo_export: context has no neighbours");
   if (!c->p2p_buf) {
@@ -647,6 +654,10 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   if (c->legacy || !small) { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
   else if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);   // state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃
   else if (A.n == 3 && pairs == 0x1) DSS2(3, 0x1);   // ∇² fields: (∇²u₁,∇²u₂), ∇²u₃, ∇²s_d
+  else if (A.n == 5 && pairs == 0x2) DSS2(5, 0x2);   // state with one passive tracer
+  else if (A.n == 4 && pairs == 0x1) DSS2(4, 0x1);   // ∇² fields with one passive tracer
+  else if (A.n == 6 && pairs == 0x2) DSS2(6, 0x2);   // two tracers
+  else if (A.n == 5 && pairs == 0x1) DSS2(5, 0x1);
   else if (A.n == 1 && pairs == 0x0) DSS2(1, 0x0);
   else if (A.n == 1 && pairs == 0x1) DSS2(1, 0x1);
   else if (A.n == 2 && pairs == 0x0) DSS2(2, 0x0);
@@ -696,7 +707,8 @@ extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, cons
 
 // ---------------------------------------------------------------------------------------------
 template <class FT>
-static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
+static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s,
+                            void* Ylc = nullptr) {
   const bool hd = c->prm.hyperdiff != 0;
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
   if (c->legacy && c->prm.held_suarez) return fail("Held-Suarez forcing is only implemented in the current (row-layout) kernels");
@@ -715,12 +727,18 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     k5_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                        (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
+    if (c->dims.n_tracers > 0) {
+      k5_tracer_a<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(3), s>>>(
+          make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ylc,
+          hd ? (FT*)c->H : nullptr);
+      LAUNCH_CHECK(c);
+    }
   } else if (phase == 0) {
     k2_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                        (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
   } else if (phase == 1 && hd) {
-    DssField F = {c->H, 4, 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d
+    DssField F = {c->H, c->ncf(), 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d, ∇²χ…
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
   } else if (phase == 2 && hd && c->legacy == 2) {
     k_exp_c<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
@@ -730,6 +748,11 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     k5_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                 (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
+    if (c->dims.n_tracers > 0) {
+      k5_tracer_c<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(0), s>>>(
+          make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)c->H, (FT*)(Ylc ? Ylc : Ytc));
+      LAUNCH_CHECK(c);
+    }
   } else if (phase == 2 && hd && !c->legacy) {
     k2_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                        (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
@@ -750,8 +773,9 @@ template <class FT>
 static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, cudaStream_t s) {
   if (Ylc) CK(cudaMemsetAsync(Ylc, 0, c->nc() * sizeof(FT), s));
   if (Ylf) CK(cudaMemsetAsync(Ylf, 0, c->nf() * sizeof(FT), s));
+  if (c->dims.n_tracers > 0 && c->exp_kernel != 5) return fail("passive tracers need B200_EXP_KERNEL=5 (default)");
   for (int ph = 0; ph < 3; ++ph)
-    if (impl_t_exp_phase<FT>(c, ph, Ytc, Ytf, Yc, Yf, s)) return -1;
+    if (impl_t_exp_phase<FT>(c, ph, Ytc, Ytf, Yc, Yf, s, Ylc)) return -1;
   return 0;
 }
 extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, double,
@@ -800,7 +824,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   const Tableau tb = ars343();
   const double dt = c->prm.dt;
   auto dss_state = [&](void* ac, void* af) -> int {
-    DssField F[2] = {{ac, 4, 0, 2}, {af, 1, 1, 0}};
+    DssField F[2] = {{ac, c->ncf(), 0, 2}, {af, 1, 1, 0}};
     return impl_dss<FT>(c, F, 2, s);
   };
   for (int i = 0; i < 4; ++i) {

@@ -56,6 +56,8 @@ struct Par {
   FT icv, ip0, dTs7, RT0;  // 1/cv_d, 1/p0, (Ts_ref − Tmin_ref)/7, R_d·T_0
   FT nu4v, nu4s, ddf;
   int nh, nv;
+  int ncf;   // components of Y.c: 4 + number of passive tracers (ρ, uₕ₁, uₕ₂, ρe_tot, ρχ…)
+  int tupw;  // tracer_upwinding: 0 none, 1 first_order, 3 vanleer_limiter
   int hyperdiff, rayleigh, viscous, upwinding;
   int hs;  // Held–Suarez forcing
   FT hs_ka, hs_ks, hs_kf, hs_sigb, hs_isig, hs_dTy, hs_Teq, hs_dthz, hs_Tmin, hs_iMSLP, hs_ikap;

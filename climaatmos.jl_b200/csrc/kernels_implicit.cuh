@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(NT) k_cache_imp(Par<FT> P, const FT* __restric
     gYf[n * nf + nv] = FT(0);
   }
   __syncthreads();
-  const FT* gYc = Yc + (size_t)h * 4 * 16 * nv;
+  const FT* gYc = Yc + (size_t)h * P.ncf * 16 * nv;
   for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
     int n = idx >> 6, v = idx & 63;
     if (v < nv) {
@@ -103,8 +103,8 @@ __device__ __forceinline__ void imp_carve(Smem<FT>& sm, ImpSlabs<FT>& S) {
 
 template <class FT>
 __device__ __forceinline__ void imp_load_state(ImpSlabs<FT>& S, const FT* __restrict__ Yc,
-                                               const FT* __restrict__ Yf, int h, int nv) {
-  const FT* gYc = Yc + (size_t)h * 4 * 16 * nv;
+                                               const FT* __restrict__ Yf, int h, int nv, int ncf) {
+  const FT* gYc = Yc + (size_t)h * ncf * 16 * nv;
   load_slab(S.rho, gYc, nv);
   load_slab(S.u1, gYc + 16 * nv, nv);
   load_slab(S.u2, gYc + 32 * nv, nv);
@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(NT) k_t_imp(Par<FT> P, const FT* __restrict__ 
   FT* hg = sm.take(HG_ELEM * 16);
   ImpSlabs<FT> S; imp_carve(sm, S);
   const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
   __syncthreads();
   imp_thermo(P, hg, V, S);
   __syncthreads();
-  FT* gT = Ytc + (size_t)h * 4 * 16 * nv;
+  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
   FT* gF = Ytf + (size_t)h * 16 * nf;
   for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
     int n = idx >> 6, v = idx & 63;
@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(NT) k_t_imp(Par<FT> P, const FT* __restrict__ 
       FT rt, et; timp_center(V, S, n, v, nv, rt, et);
       gT[(0 * 16 + n) * nv + v] = rt; gT[(1 * 16 + n) * nv + v] = FT(0);
       gT[(2 * 16 + n) * nv + v] = FT(0); gT[(3 * 16 + n) * nv + v] = et;
+      for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);  // passive tracers are advected explicitly
     }
     if (v < nf) gF[n * nf + v] = timp_face(P, V, S, n, v, nv);
   }
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(NT) k_wfact(Par<FT> P, const FT* __restrict__ 
   FT* hg = sm.take(HG_ELEM * 16);
   ImpSlabs<FT> S; imp_carve(sm, S);
   const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
   __syncthreads();
   imp_thermo(P, hg, V, S);
   __syncthreads();
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(NT) k_ldiv(Par<FT> P, const FT* __restrict__ j
   const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
   const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
   const size_t pl = (size_t)16 * nf;
-  const FT* gRc = Rc + (size_t)h * 4 * 16 * nv;
+  const FT* gRc = Rc + (size_t)h * P.ncf * 16 * nv;
   load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
   load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
   __syncthreads();
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(NT) k_ldiv(Par<FT> P, const FT* __restrict__ j
     thomas_column(sl + n * LVP, sd + n * LVP, su + n * LVP, sr + n * LVP, nf);
   }
   __syncthreads();
-  FT* gdc = dYc + (size_t)h * 4 * 16 * nv;
+  FT* gdc = dYc + (size_t)h * P.ncf * 16 * nv;
   FT* gdf = dYf + (size_t)h * 16 * nf;
   for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
     int n = idx >> 6, v = idx & 63;
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(NT) k_ldiv(Par<FT> P, const FT* __restrict__ j
       gdc[(1 * 16 + n) * nv + v] = -r1[s];
       gdc[(2 * 16 + n) * nv + v] = -r2[s];
       gdc[(3 * 16 + n) * nv + v] = gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1 - re[s];
+      for (int q = 4; q < P.ncf; ++q) gdc[(q * 16 + n) * nv + v] = -gRc[(q * 16 + n) * nv + v];  // fallback −I block
     }
   }
 }
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(NT) k_t_post_imp(Par<FT> P, const FT* __restri
   ImpSlabs<FT> S; imp_carve(sm, S);
   FT* flx = sm.take(SLAB);
   const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
   __syncthreads();
   imp_thermo(P, hg, V, S);
   __syncthreads();
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(NT) k_t_post_imp(Par<FT> P, const FT* __restri
     flx[o] = r;
   }
   __syncthreads();
-  FT* gT = Ytc + (size_t)h * 4 * 16 * nv;
+  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
   FT* gF = Ytf + (size_t)h * 16 * nf;
   for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
     int n = idx >> 6, v = idx & 63;
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(NT) k_t_post_imp(Par<FT> P, const FT* __restri
     if (v < nv) {
       gT[(0 * 16 + n) * nv + v] = FT(0); gT[(1 * 16 + n) * nv + v] = FT(0); gT[(2 * 16 + n) * nv + v] = FT(0);
       gT[(3 * 16 + n) * nv + v] = -(flx[o + 1] - flx[o]) / V.mc[v];
+      for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
     }
     if (v < nf) gF[n * nf + v] = FT(0);
   }
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(NT) k_imp_stage(Par<FT> P, const FT* __restric
   FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
   FT* rr = sm.take(SLAB); FT* rre = sm.take(SLAB);
   const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv);
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
   __syncthreads();
   if (threadIdx.x < 16) { S.u3[threadIdx.x * LVP] = FT(0); S.u3[threadIdx.x * LVP + nv] = FT(0); }
   __syncthreads();
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(NT) k_imp_stage(Par<FT> P, const FT* __restric
     if (v < nf) S.u3[s] = (v == 0 || v == nv) ? FT(0) : S.u3[s] - sr[s];
   }
   __syncthreads();
-  FT* gYc = Yc + (size_t)h * 4 * 16 * nv;
+  FT* gYc = Yc + (size_t)h * P.ncf * 16 * nv;
   FT* gYf = Yf + (size_t)h * 16 * nf;
   if (P.upwinding != 0) {
     imp_thermo(P, hg, V, S);  // cache_imp!(U) after the Newton update

@@ -94,7 +94,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
      *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
   B200_ROW_PROLOGUE
   const bool interior = v > 0 && v < nv;
-  const FT* gY = Yc + (size_t)e * 64 * nv;
+  const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   V rho[2], u1[2], u2[2], re[2], u3[2], U1[2], U2[2];
   ld4p(rho, gY, nv, j, v, cv, FT(1)); ld4p(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4p(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
   ld4p(re, gY + 48 * nv, nv, j, v, cv, FT(0)); ld4p(u3, Yf + (size_t)e * 16 * nf, nf, j, v, fv, FT(0));
@@ -142,8 +142,8 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
   }
   sputp(s_K, K, j, v);
-  FT* gT = Ytc + (size_t)e * 64 * nv;
-  FT* gH = H ? H + (size_t)e * 64 * nv : nullptr;
+  FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv;
+  FT* gH = H ? H + (size_t)e * P.ncf * 16 * nv : nullptr;
   const bool any_visc = P.viscous && __any_sync(FULLM, L.bvc != FT(0));
   V rjs[2];  // sc / J2
 #pragma unroll
@@ -315,8 +315,8 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* s_a = s_w + SLAB;
   B200_ROW_PROLOGUE
   const int part = blockIdx.y;
-  const FT* gH = H + (size_t)e * 64 * nv;
-  FT* gT = Ytc + (size_t)e * 64 * nv;
+  const FT* gH = H + (size_t)e * P.ncf * 16 * nv;
+  FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv;
   FT* gF = Ytf + (size_t)e * 16 * nf;
   V a[2], b[2], g1[2];
   if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
@@ -346,7 +346,7 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     if (cv) { st4p(old1, gT + 16 * nv, nv, j, v); st4p(old2, gT + 32 * nv, nv, j, v); }
   } else if (part == 1) {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
     V rho[2], Ls[2], old3[2], Q1[2], Q2[2];
-    ld4p(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
     ld4p(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
     ld4p(old3, gT + 48 * nv, nv, j, v, cv, FT(0));
     __syncthreads();
@@ -359,7 +359,7 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     if (cv) st4p(old3, gT + 48 * nv, nv, j, v);
   } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
     V rho[2], L3[2], oldf[2], P1[2], P2_[2], q[2], w[2];
-    ld4p(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
     ld4p(L3, gH + 32 * nv, nv, j, v, cv, FT(0));
     ld4p(oldf, gF, nf, j, v, fv, FT(0));
     __syncthreads();
@@ -392,6 +392,149 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       st4p(oldf, gF, nf, j, v);
     }
   }
+}
+
+}  // namespace b200
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Passive grid-scale tracers ρχ (components 4.. of Y.c, e.g. the chemistry tracer ρq_gas_A), one (element, tracer)
+// per CTA in the same row layout:
+//   k5_tracer_a  horizontal_tracer_advection_tendency!  ρχₜ_lim −= split_divₕ(ρu, χ)          (advection.jl:113-143)
+//                prep_tracer_hyperdiffusion_tendency!   ∇²χ = wdivₕ(gradₕ χ) → H[4+q]          (hyperdiffusion.jl:420-432)
+//                explicit vertical transport            ρχₜ += −ᶜadvdivᵥ(ᶠinterp(ρJ)/ᶠJ · U(ᶠu³, χ)) with tracer_upwinding
+//                                                       (advection.jl:249-255; implicit_tendency.jl:120-143)
+//                viscous sponge                          ρχₜ += β wdivₕ(ρ gradₕ χ)              (viscous_sponge.jl:226-231)
+//   k5_tracer_c  apply_tracer_hyperdiffusion_tendency!  ρχₜ_lim −= ν₄ₛ wdivₕ(ρ gradₕ ∇²χ)       (hyperdiffusion.jl:524-532)
+// With Ylc == nullptr (native stepper: lim! is a no-op) the limited part is accumulated into Yₜ as well.
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 3 : 1))
+k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+            const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ylc, FT* __restrict__ H) {
+  using V = P2<FT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  FT* sx = hg + HG_ELEM * 16;
+  FT *s_chi = sx, *s_r = sx + SLAB, *s_fx = sx + 2 * SLAB;
+  B200_ROW_PROLOGUE
+  const int q = 4 + blockIdx.y;
+  const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
+  V rho[2], u1[2], u2[2], rq[2], u3[2], chi[2];
+  ld4p(rho, gY, nv, j, v, cv, FT(1)); ld4p(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4p(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
+  ld4p(rq, gY + (size_t)q * 16 * nv, nv, j, v, cv, FT(0)); ld4p(u3, Yf + (size_t)e * 16 * nf, nf, j, v, fv, FT(0));
+#pragma unroll
+  for (int p = 0; p < 2; ++p) chi[p] = V(rq[p].lo() / rho[p].lo(), rq[p].hi() / rho[p].hi());
+  sputp(s_chi, chi, j, v); sputp(s_r, rho, j, v);
+  __syncthreads();
+  V U1[2], U2[2], F1[2], F2[2], rjs[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    V c1 = fma2(HGP(HG_GI12, p), u2[p], HGP(HG_GI11, p) * u1[p]);
+    V c2 = fma2(HGP(HG_GI22, p), u2[p], HGP(HG_GI12, p) * u1[p]);
+    U1[p] = HGP(HG_J2, p) * c1; U2[p] = HGP(HG_J2, p) * c2;
+    F1[p] = rho[p] * U1[p]; F2[p] = rho[p] * U2[p];
+    rjs[p] = HGP(HG_RJ2, p) * L.sc;
+  }
+  V wd[2], t[2], g1[2], g2[2], G1[2], G2[2], lim[2], out[2];
+  div4p<FT, 1>(F1, F2, mw, vl, wd);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) { wd[p] = wd[p] * rjs[p]; G1[p] = F1[p] * chi[p]; G2[p] = F2[p] * chi[p]; }
+  div4p<FT, 1>(G1, G2, mw, vl, t);
+  deta4p(chi, md, vl, g2);
+  dxi4p<FT, 0>(chi, g1);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    V adv = fma2(F2[p], g2[p], F1[p] * g1[p]) * rjs[p];
+    lim[p] = -((t[p] * rjs[p]) * FT(0.5) + fma2(chi[p], wd[p], adv) * FT(0.5));
+    out[p] = V(FT(0));
+  }
+  if (H) {  // ∇²χ
+    V Q1[2], Q2[2];
+    METRIC_FLUX(Q1, Q2, g1, g2, HGP(HG_J2, p))
+    div4p<FT, 1>(Q1, Q2, mw, vl, t);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) t[p] = t[p] * rjs[p];
+    if (cv) st4p(t, H + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv, nv, j, v);
+  }
+  if (P.viscous && __any_sync(FULLM, L.bvc != FT(0))) {
+    V S1[2], S2[2];
+    METRIC_FLUX(S1, S2, g1, g2, rho[p] * HGP(HG_J2, p))
+    div4p<FT, 1>(S1, S2, mw, vl, t);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) out[p] = (t[p] * rjs[p]) * L.bvc;
+  }
+  // vertical transport: flux through face v of (ᶠinterp(ρJ)/J2)·u³·χ_face, zero on the boundary faces
+  {
+    const bool interior = v > 0 && v < nv;
+    FT fx[4];
+    const int vm = v > 0 ? v - 1 : 0, vm2 = v > 1 ? v - 2 : 0, vp = v < nv - 1 ? v + 1 : v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = (n0 + i) * LVP;
+      FT r = FT(0);
+      if (interior) {
+        const FT u3i = (i < 2) ? (i == 0 ? u3[0].lo() : u3[0].hi()) : (i == 2 ? u3[1].lo() : u3[1].hi());
+        const FT w = L.g33lo * u3i;
+        const FT am = s_chi[o + vm], ap = s_chi[o + v];
+        FT face;
+        if (P.tupw == 3 && v >= 2 && v <= nv - 2) {
+          if (w >= FT(0)) face = am + vl_slope(s_chi[o + vm2], am, ap) / FT(2) * (FT(1) - w * P.dt);
+          else face = ap - vl_slope(am, ap, s_chi[o + vp]) / FT(2) * (FT(1) + w * P.dt);
+        } else if (P.tupw == 0) {
+          face = FT(0.5) * (am + ap);
+        } else {
+          face = w >= FT(0) ? am : ap;
+        }
+        r = (FT(0.5) * (s_r[o + vm] * L.mclo + s_r[o + v] * L.mc)) * (w * face);
+      }
+      fx[i] = r;
+      if (fv) s_fx[o + v] = r;
+    }
+    __syncthreads();
+    if (cv) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int o0 = (n0 + 2 * p) * LVP + v + 1, o1 = (n0 + 2 * p + 1) * LVP + v + 1;
+        V up(s_fx[o0], s_fx[o1]), dn(fx[2 * p], fx[2 * p + 1]);
+        out[p] = out[p] - (up - dn) * L.rmc;
+      }
+    }
+  }
+  if (cv) {
+    FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv;
+    if (Ylc) {
+      st4p(out, gT, nv, j, v);
+      st4p(lim, Ylc + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv, nv, j, v);
+    } else {
+      out[0] = out[0] + lim[0]; out[1] = out[1] + lim[1];
+      st4p(out, gT, nv, j, v);
+    }
+  }
+}
+
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
+k5_tracer_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+            const FT* __restrict__ H, FT* __restrict__ Tgt) {
+  using V = P2<FT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  B200_ROW_PROLOGUE
+  const int q = 4 + blockIdx.y;
+  V rho[2], Lq[2], old[2], a[2], g1[2], Q1[2], Q2[2], b[2];
+  FT* gT = Tgt + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv;
+  ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
+  ld4p(Lq, H + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv, nv, j, v, cv, FT(0));
+  ld4p(old, gT, nv, j, v, cv, FT(0));
+  __syncthreads();
+  deta4p(Lq, md, vl, a);
+  dxi4p<FT, 0>(Lq, g1);
+  METRIC_FLUX(Q1, Q2, g1, a, rho[p] * HGP(HG_J2, p))
+  div4p<FT, 1>(Q1, Q2, mw, vl, b);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) old[p] = old[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
+  if (cv) st4p(old, gT, nv, j, v);
 }
 
 }  // namespace b200

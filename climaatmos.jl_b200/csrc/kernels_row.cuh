@@ -84,7 +84,7 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
      *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
   B200_ROW_PROLOGUE
   const bool interior = v > 0 && v < nv;
-  const FT* gY = Yc + (size_t)e * 64 * nv;
+  const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   FT rho[4], u1[4], u2[4], re[4], u3[4], U1[4], U2[4];
   ld4(rho, gY, nv, j, v, cv, FT(1)); ld4(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
   ld4(re, gY + 48 * nv, nv, j, v, cv, FT(0)); ld4(u3, Yf + (size_t)e * 16 * nf, nf, j, v, fv, FT(0));
@@ -121,8 +121,8 @@ k2_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
   }
   sput(s_K, K, j, v);
-  FT* gT = Ytc + (size_t)e * 64 * nv;
-  FT* gH = H ? H + (size_t)e * 64 * nv : nullptr;
+  FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv;
+  FT* gH = H ? H + (size_t)e * P.ncf * 16 * nv : nullptr;
   const bool any_visc = P.viscous && __any_sync(FULLM, L.bvc != FT(0));
   // ---- scalars: split-form flux divergences (advection.jl:48,59), viscous sponge on ρe_tot, ∇²s_d
   {
@@ -312,8 +312,8 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* s_a = s_w + SLAB;
   B200_ROW_PROLOGUE
   const int part = blockIdx.y;
-  const FT* gH = H + (size_t)e * 64 * nv;
-  FT* gT = Ytc + (size_t)e * 64 * nv;
+  const FT* gH = H + (size_t)e * P.ncf * 16 * nv;
+  FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv;
   FT* gF = Ytf + (size_t)e * 16 * nf;
   FT a[4], b[4];
   if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
@@ -346,7 +346,7 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
   } else if (part == 1) {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
     FT rho[4], Ls[4], old3[4], Q1[4], Q2[4];
-    ld4(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
     ld4(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
     ld4(old3, gT + 48 * nv, nv, j, v, cv, FT(0));
     __syncthreads();
@@ -364,7 +364,7 @@ k2_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
   } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
     FT rho[4], L3[4], oldf[4], P1[4], P2[4], q[4], w[4];
-    ld4(rho, Yc + (size_t)e * 64 * nv, nv, j, v, cv, FT(1));
+    ld4(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
     ld4(L3, gH + 32 * nv, nv, j, v, cv, FT(0));
     ld4(oldf, gF, nf, j, v, fv, FT(0));
     __syncthreads();
@@ -431,9 +431,9 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   const FT kap = P.R_d / P.cv_d;
   load_vlev(&V, vlev);
   load_hgeo(hg, hgeo, e);
-  const FT* gY = Yc + (size_t)e * 64 * nv;
+  const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   const FT* gYf = Yf + (size_t)e * 16 * nf;
-  FT* gN = Nc + (size_t)e * 64 * nv;
+  FT* gN = Nc + (size_t)e * P.ncf * 16 * nv;
   FT* gNf = Nf + (size_t)e * 16 * nf;
   FT r_re[NIT], r_u1[NIT], r_u2[NIT];
 #pragma unroll
@@ -444,6 +444,7 @@ k2_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       s_rho[o] = gY[n * nv + v];
       r_u1[it] = gY[(16 + n) * nv + v]; r_u2[it] = gY[(32 + n) * nv + v]; r_re[it] = gY[(48 + n) * nv + v];
       gN[(16 + n) * nv + v] = r_u1[it]; gN[(32 + n) * nv + v] = r_u2[it];
+      for (int q = 4; q < P.ncf; ++q) gN[(q * 16 + n) * nv + v] = gY[(q * 16 + n) * nv + v];  // passive tracers: ΔU = 0
     }
     if (v < nf) s_u3[o] = (v == 0 || v == nv) ? FT(0) : gYf[n * nf + v];
   }
@@ -625,9 +626,9 @@ k4_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   const int e = blockIdx.x >> 2, nq0 = (blockIdx.x & 3) * 4, nv = P.nv, nf = nv + 1;
   const FT* hg = hgeo + (size_t)e * HG_N * 16;
   const FT kap = P.R_d / P.cv_d;
-  const FT* gY = Yc + (size_t)e * 64 * nv;
+  const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   const FT* gYf = Yf + (size_t)e * 16 * nf;
-  FT* gN = Nc + (size_t)e * 64 * nv;
+  FT* gN = Nc + (size_t)e * P.ncf * 16 * nv;
   FT* gNf = Nf + (size_t)e * 16 * nf;
   FT r_re[NIT], r_u1[NIT], r_u2[NIT];
 #pragma unroll
@@ -843,9 +844,9 @@ k3_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   if (col >= ncols) return;  // whole warp exits together
   const int e = col >> 4, n = col & 15, nv = P.nv, nf = nv + 1;
   const FT kap = P.R_d / P.cv_d;
-  const FT* gY = Yc + ((size_t)e * 64 + n) * nv;
+  const FT* gY = Yc + ((size_t)e * P.ncf * 16 + n) * nv;
   const FT* gYf = Yf + ((size_t)e * 16 + n) * nf;
-  FT* gN = Nc + ((size_t)e * 64 + n) * nv;
+  FT* gN = Nc + ((size_t)e * P.ncf * 16 + n) * nv;
   FT* gNf = Nf + ((size_t)e * 16 + n) * nf;
   const size_t cs = (size_t)16 * nv;  // component stride
   const FT g11 = hgeo[((size_t)e * HG_N + HG_GI11) * 16 + n], g12 = hgeo[((size_t)e * HG_N + HG_GI12) * 16 + n],

@@ -63,6 +63,7 @@ class AtmosSimulation:
     def __init__(self, FT=np.float32, h_elem=6, z_elem=10, z_max=30000.0, dz_bottom=500.0, dt=400.0,
                  rayleigh_sponge=False, viscous_sponge=False, hyperdiff=True, deep_atmosphere=True,
                  initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter", rad=None,
+                 tracers=None, tracer_upwinding="vanleer_limiter",
                  params: DycoreParams | None = None, device=None, comms=None, grid=None):
         torch = _torch()
         self.torch = torch
@@ -70,7 +71,7 @@ class AtmosSimulation:
         self.params = params or DycoreParams()
         self.numerics = DycoreNumerics(dt=float(dt), hyperdiff=hyperdiff, rayleigh_sponge=rayleigh_sponge,
                                        viscous_sponge=viscous_sponge, energy_upwinding=energy_q_tot_upwinding,
-                                       held_suarez=(rad == "held_suarez"))
+                                       held_suarez=(rad == "held_suarez"), tracer_upwinding=tracer_upwinding)
         self.grid = grid or make_sphere_grid(FT=self.FT, h_elem=h_elem, z_elem=z_elem, z_max=z_max, dz_bottom=dz_bottom,
                                              radius=self.params.planet_radius, deep_atmosphere=deep_atmosphere)
         self.comms = comms  # parallel.DistributedComms or None
@@ -81,6 +82,16 @@ class AtmosSimulation:
             Yc, Yf = setups.decaying_profile(self.grid, self.params)
         else:
             raise ValueError(f"unknown initial_condition {initial_condition}")
+        # passive grid-scale tracers ρχ appended after ρe_tot (e.g. the chemistry tracer ρq_gas_A,
+        # setups/common/prognostic_variables.jl:138-145): ``tracers`` = list of χ(lat°, lon°, z) callables or arrays
+        self.n_tracers = len(tracers) if tracers else 0
+        if self.n_tracers:
+            zz = np.broadcast_to(self.grid.z_c, Yc[:, 0].shape)
+            extra = []
+            for tr in tracers:
+                chi = tr(self.grid.lat[..., None], self.grid.lon[..., None], zz) if callable(tr) else np.asarray(tr)
+                extra.append((Yc[:, 0].astype(np.float64) * chi).astype(self.FT)[:, None])
+            Yc = np.concatenate([Yc] + extra, axis=1)
         self.part = None
         if comms is not None and comms.nranks > 1:
             from .partition import partition_grid
@@ -88,14 +99,15 @@ class AtmosSimulation:
             self.part = partition_grid(self.grid, comms.rank, comms.nranks)
             Yc, Yf = Yc[self.part.elems_ext[: self.part.nh]], Yf[self.part.elems_ext[: self.part.nh]]
             self.ctx = capi.create_context(self.grid, self.params, self.numerics, part=self.part,
-                                           nccl_id=comms.nccl_unique_id(), rank=comms.rank, nranks=comms.nranks)
+                                           nccl_id=comms.nccl_unique_id(), rank=comms.rank, nranks=comms.nranks,
+                                           n_tracers=self.n_tracers)
             import os as _os
 
             self.peer_halo = False
             if not _os.environ.get("B200_HALO_NCCL"):
                 self.peer_halo = capi.setup_peer_halo(self.ctx, self.part, comms)
         else:
-            self.ctx = capi.create_context(self.grid, self.params, self.numerics)
+            self.ctx = capi.create_context(self.grid, self.params, self.numerics, n_tracers=self.n_tracers)
         self.lib = capi.load()
         self.Y = FieldVector(torch.from_numpy(np.ascontiguousarray(Yc)).to(self.device),
                              torch.from_numpy(np.ascontiguousarray(Yf)).to(self.device))
@@ -167,7 +179,7 @@ class AtmosSimulation:
 
     def dss(self, Y, t=0.0):
         """dss! (constrain_state.jl:59-64): weighted DSS of Y.c (uₕ as a Covariant12 vector) and Y.f."""
-        self.weighted_dss([(Y.c, 4, 0, 2), (Y.f, 1, 1, 0)])
+        self.weighted_dss([(Y.c, int(Y.c.shape[1]), 0, 2), (Y.f, 1, 1, 0)])
 
     def weighted_dss(self, fields):
         """Spaces.weighted_dss!(pairs...): ``fields`` = [(tensor, ncomp, is_face, kind)]."""

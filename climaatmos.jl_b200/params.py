@@ -58,6 +58,7 @@ class DycoreNumerics:
     rayleigh_sponge: bool = False
     viscous_sponge: bool = False
     energy_upwinding: str = "vanleer_limiter"  # default_config.yml:324-326
+    tracer_upwinding: str = "vanleer_limiter"  # default_config.yml:321-323
     held_suarez: bool = False
 
 

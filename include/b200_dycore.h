@@ -31,6 +31,7 @@ typedef struct {
   int32_t nq;        /* GLL nodes per direction; must be 4 */
   int32_t ft_bytes;  /* 4 = Float32, 8 = Float64 */
   int32_t deep;      /* 1 = DeepSphericalGlobalGeometry, 0 = shallow (grids.jl:64-68) */
+  int32_t n_tracers; /* passive grid-scale tracers ρχ appended to Y.c after ρe_tot (0..4): Y.c has Nf = 4 + n_tracers */
 } b200_dims;
 
 /* Geometry, copied from the live ClimaCore objects (HOST pointers, double precision; the
@@ -77,6 +78,7 @@ typedef struct {
   int32_t rayleigh_sponge; double zd_rayleigh, alpha_rayleigh_uh, alpha_rayleigh_w;
   int32_t viscous_sponge;  double zd_viscous, kappa_2_sponge;
   int32_t energy_upwinding; /* 0 none, 1 first_order, 3 vanleer_limiter */
+  int32_t tracer_upwinding; /* same encoding (default_config.yml:321-323) */
   /* Held–Suarez forcing (src/parameterized_tendencies/radiation/held_suarez.jl:111-296); flat surface */
   int32_t held_suarez; double hs_day, hs_sigma_b, hs_dT_y, hs_T_equator, hs_dtheta_z, hs_T_min, MSLP;
 } b200_params;

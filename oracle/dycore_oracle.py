@@ -419,8 +419,9 @@ class Oracle:
             l += lo21 * cl(lo12)
             d += lo21 * cl(hi12) + hi21 * ch(lo12)
             u += hi21 * ch(hi12)
-        # velocities first: Δuₕ = -R_uₕ
+        # velocities first: Δuₕ = -R_uₕ ; passive tracers only have the fallback -I block (:476-481)
         dYc[:, 1], dYc[:, 2] = -R1, -R2
+        dYc[:, 4:] = -Rc[:, 4:]
         rhs = R3.copy()
         for a21, r in ((Jm["u3_rho"], Rrho), (Jm["u3_rhoe"], Rre)):
             rhs += a21[0] * cl(r) + a21[1] * ch(r)
@@ -488,7 +489,9 @@ class Oracle:
 
     def dss_state(self, Yc, Yf):
         self.weighted_dss(
-            [("scalar", [Yc[:, 0]]), ("c12", [Yc[:, 1], Yc[:, 2]]), ("scalar", [Yc[:, 3]]), ("scalar", [Yf[:, 0]])]
+            [("scalar", [Yc[:, 0]]), ("c12", [Yc[:, 1], Yc[:, 2]]), ("scalar", [Yc[:, 3]])]
+            + [("scalar", [Yc[:, q]]) for q in range(4, Yc.shape[1])]
+            + [("scalar", [Yf[:, 0]])]
         )
 
     # ------------------------------------------------------------------ T_exp_T_lim!
@@ -507,13 +510,51 @@ class Oracle:
         e3 = G.c33 * e3c
         return (gd1, gd2), (e1, e2, e3)
 
-    def remaining_tendency(self, Yc, Yf, pc):
-        """remaining_tendency.jl:48-58 (dry): returns (Ytc, Ytf); Yₜ_lim ≡ 0 without tracers."""
+    def remaining_tendency(self, Yc, Yf, pc, with_lim=False):
+        """remaining_tendency.jl:48-58: returns (Ytc, Ytf) and, with ``with_lim``, also Yₜ_lim.c — the limited
+        tracer tendencies (horizontal advection + tracer hyperdiffusion; zero for the non-tracer components)."""
         Ytc, Ytf, L = self._rt_pre(Yc, Yf, pc)
+        Ylc = np.zeros_like(Yc)
+        self._tracer_pre(Ytc, Ylc, Yc, Yf, pc)
         if L is not None:
-            self.weighted_dss([("c12", [L[0], L[1]]), ("scalar", [L[2]]), ("scalar", [L[3]])])  # :18-21
+            Lq = self._tracer_laplacians(Yc)
+            self.weighted_dss([("c12", [L[0], L[1]]), ("scalar", [L[2]]), ("scalar", [L[3]])] + [("scalar", [a]) for a in Lq])  # :18-21
             self._rt_post(Ytc, Ytf, Yc, L)
-        return Ytc, Ytf
+            self._tracer_post(Ylc, Yc, Lq)
+        return (Ytc, Ytf, Ylc) if with_lim else (Ytc + Ylc, Ytf)
+
+    # ---- passive grid-scale tracers ρχ (components 4.. of Y.c), e.g. the chemistry tracer ρq_gas_A
+    def _tracer_pre(self, Ytc, Ylc, Yc, Yf, pc):
+        """horizontal_tracer_advection_tendency! (advection.jl:113-143, into Yₜ_lim), explicit vertical transport
+        with ``tracer_upwinding`` (advection.jl:249-255, into Yₜ) and the viscous-sponge tracer term
+        (viscous_sponge.jl:226-231, into Yₜ).  Element-local."""
+        FT, N, c = self.FT, self.N, self.c
+        rho, u1, u2 = Yc[:, 0], Yc[:, 1], Yc[:, 2]
+        c1, c2 = self.ct12(u1, u2, c)
+        for q in range(4, Yc.shape[1]):
+            chi = Yc[:, q] / rho
+            Ylc[:, q] -= self.split_div(rho * c1, rho * c2, chi, c)
+            Ytc[:, q] += self.vertical_transport(rho, pc["fu3"], chi, N.dt, N.tracer_upwinding)
+            if N.viscous_sponge:
+                g = self.grad(chi)
+                g = self.ct12(g[0], g[1], c)
+                Ytc[:, q] += self.beta_viscous(c.z) * self.wdiv(rho * g[0], rho * g[1], c)
+
+    def _tracer_laplacians(self, Yc):
+        """prep_tracer_hyperdiffusion_tendency! (hyperdiffusion.jl:420-432): ∇²χ = wdivₕ(gradₕ(ρχ/ρ))."""
+        out = []
+        for q in range(4, Yc.shape[1]):
+            g = self.grad(Yc[:, q] / Yc[:, 0])
+            out.append(self.wdiv(*self.ct12(g[0], g[1], self.c), self.c))
+        return out
+
+    def _tracer_post(self, Ylc, Yc, Lq):
+        """apply_tracer_hyperdiffusion_tendency! (hyperdiffusion.jl:524-532): ρχₜ −= ν₄ₛ wdivₕ(ρ gradₕ(∇²χ))."""
+        rho = Yc[:, 0]
+        for k, q in enumerate(range(4, Yc.shape[1])):
+            g = self.grad(Lq[k])
+            g = self.ct12(g[0], g[1], self.c)
+            Ylc[:, q] -= self.nu4_scalar * self.wdiv(rho * g[0], rho * g[1], self.c)
 
     def _rt_post(self, Ytc, Ytf, Yc, L):
         """apply_hyperdiffusion_tendency! (hyperdiffusion.jl:247-307) on the DSSed ∇² fields (element-local)."""
@@ -680,20 +721,30 @@ class Oracle:
 
         def t_exp(Uc, Uf):
             Ytc, Ytf = np.empty_like(Uc), np.empty_like(Uf)
-            Ls = [np.empty_like(Uc[:, 0]) for _ in range(4)] if self.N.hyperdiff else None
+            nq = Uc.shape[1] - 4
+            Ls = [np.empty_like(Uc[:, 0]) for _ in range(4 + nq)] if self.N.hyperdiff else None
 
             def pre(sub, sl):
                 pc = sub.set_implicit_precomputed_quantities(Uc[sl], Uf[sl])
                 a, b, L = sub._rt_pre(Uc[sl], Uf[sl], pc)
-                Ytc[sl], Ytf[sl] = a, b
+                lim = np.zeros_like(a)
+                sub._tracer_pre(a, lim, Uc[sl], Uf[sl], pc)
+                Ytc[sl], Ytf[sl] = a + lim, b  # lim! is a no-op (no limiter configured): T_lim joins T_exp
                 if L is not None:
                     for k in range(4):
                         Ls[k][sl] = L[k]
+                    for k, lq in enumerate(sub._tracer_laplacians(Uc[sl])):
+                        Ls[4 + k][sl] = lq
 
             pmap(pre)
             if Ls is not None:
-                self.weighted_dss([("c12", [Ls[0], Ls[1]]), ("scalar", [Ls[2]]), ("scalar", [Ls[3]])])
-                pmap(lambda sub, sl: sub._rt_post(Ytc[sl], Ytf[sl], Uc[sl], tuple(a[sl] for a in Ls)))
+                self.weighted_dss([("c12", [Ls[0], Ls[1]]), ("scalar", [Ls[2]]), ("scalar", [Ls[3]])] + [("scalar", [a]) for a in Ls[4:]])
+
+                def post(sub, sl):
+                    sub._rt_post(Ytc[sl], Ytf[sl], Uc[sl], tuple(a[sl] for a in Ls[:4]))
+                    sub._tracer_post(Ytc[sl], Uc[sl], [a[sl] for a in Ls[4:]])
+
+                pmap(post)
             return Ytc, Ytf
 
         for i in range(4):

@@ -183,6 +183,80 @@ def test_held_suarez_config_matches_oracle(FT):
     sim.close()
 
 
+def _tracer_fns():
+    chi1 = lambda lat, lon, z: np.ones_like(z) + 0 * lat
+    chi2 = lambda lat, lon, z: 0.5 * (1 + np.sin(np.radians(lat)) * np.cos(np.radians(lon))) * np.exp(-z / 8000.0)
+    return [chi1, chi2]
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_passive_tracers_match_oracle(FT):
+    """Tracer-carrying configuration (two passive grid-scale tracers ρχ, cf. ρq_gas_A): hooks and two full steps
+    against the oracle, plus the reference's χ ≡ 1 consistency check
+    (test/prognostic_equations/tracer_mass_consistency_tests.jl:52-84) evaluated on the CUDA tendencies."""
+    he, ze, zmax, dzb, dt, sp = CASES["he3ze63"]
+    P = prm.DycoreParams(zd_rayleigh=0.66 * zmax, zd_viscous=0.66 * zmax)
+    sim = dycore.AtmosSimulation(FT=FT, h_elem=he, z_elem=ze, z_max=zmax, dz_bottom=dzb, dt=dt, rayleigh_sponge=sp, viscous_sponge=sp,
+                                 params=P, tracers=_tracer_fns())
+    assert sim.Y.c.shape[1] == 6
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    Yc0, Yf0 = sim.Y.cpu()
+    Yc, Yf, rng = perturbed_state(sim, FT)
+    Yc[:, 4] = Yc[:, 0]  # keep χ₁ ≡ 1 exactly on the perturbed state
+    Y = sim.to_device(Yc, Yf)
+    oc, of = Yc.astype(np.float64), Yf.astype(np.float64)
+    sim.dss(Y)
+    o.dss_state(oc, of)
+    gc, gf = Y.cpu()
+    lim = 1e-11 if FT == np.float64 else 1e-5
+    for q in range(6):
+        assert rel(gc[:, q], oc[:, q]) < lim, f"dss comp {q}"
+    sim.set_implicit_precomputed_quantities(Y)
+    pc = o.set_implicit_precomputed_quantities(oc, of)
+    Yt, Yl = Y.zeros_like(), Y.zeros_like()
+    sim.remaining_tendency(Yt, Yl, Y)
+    tc, tf, lc = o.remaining_tendency(oc, of, pc, with_lim=True)
+    gt, gtf = Yt.cpu()
+    gl, _ = Yl.cpu()
+    tl = 1e-10 if FT == np.float64 else 5e-4
+    for q in (4, 5):
+        assert rel(gt[:, q], tc[:, q]) < tl, f"Yt tracer {q}: {rel(gt[:, q], tc[:, q])}"
+        assert rel(gl[:, q], lc[:, q]) < tl, f"Yt_lim tracer {q}: {rel(gl[:, q], lc[:, q])}"
+    assert np.all(gl[:, :4] == 0)
+    check(gt[:, :4], gtf, tc[:, :4], tf, tol(FT, "tend"), "t_exp (dry components with tracers present)")
+    # χ ≡ 1: limited (horizontal) tracer tendency == horizontal mass tendency; explicit vertical == implicit mass tendency
+    Ti = Y.zeros_like()
+    sim.implicit_tendency(Ti, Y)
+    gi, _ = Ti.cpu()
+    eps = np.finfo(FT).eps
+    assert np.abs(gl[:, 4] - gt[:, 0]).max() <= 100 * eps * np.abs(gt[:, 0]).max()
+    assert np.abs(gt[:, 4] - gi[:, 0]).max() <= 100 * eps * np.abs(gi[:, 0]).max()
+    assert np.all(gi[:, 4:] == 0)
+    # ldiv: passive tracers only have the −I block
+    sim.update_jacobian(Y, 0.43 * dt)
+    R = sim.to_device(rng.standard_normal(Yc.shape).astype(FT), rng.standard_normal(Yf.shape).astype(FT))
+    dY = R.zeros_like()
+    sim.ldiv(dY, R)
+    assert np.array_equal(dY.c.cpu().numpy()[:, 4:], -R.c.cpu().numpy()[:, 4:])
+    # two full steps
+    sim.Y = sim.to_device(Yc0, Yf0)
+    oc, of = Yc0.astype(np.float64), Yf0.astype(np.float64)
+    for _ in range(2):
+        sim.step(fused=True)
+        oc, of = o.step(oc, of)
+    gc, gf = sim.Y.cpu()
+    check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state"), "2 steps with tracers")
+    for q in (4, 5):
+        assert rel(gc[:, q], oc[:, q]) < (1e-11 if FT == np.float64 else 1e-5), f"tracer {q} after 2 steps"
+    # hook-by-hook stepping gives the same state
+    sim.Y = sim.to_device(Yc0, Yf0)
+    for _ in range(2):
+        sim.step(fused=False)
+    hc, hf = sim.Y.cpu()
+    assert rel(hc, gc) < (1e-12 if FT == np.float64 else 1e-5)
+    sim.close()
+
+
 def test_fused_and_hook_paths_agree_bitwise_in_structure():
     sim, P = make(np.float64, "he3ze63")
     Y0 = sim.Y.clone()
