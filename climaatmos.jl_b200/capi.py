@@ -19,7 +19,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 SYMBOLS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_nccl_unique_id", "b200_cache_imp",
     "b200_t_exp_lim", "b200_t_imp", "b200_wfact", "b200_ldiv", "b200_t_post_imp", "b200_dss",
-    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase",
+    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase", "b200_implicit_stage",
 ]
 
 
@@ -101,6 +101,7 @@ def load():
     lib.b200_t_exp_lim.argtypes = [vp, vp, vp, vp, vp, vp, vp, dbl, vp]
     lib.b200_t_exp_phase.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b200_t_imp.argtypes = [vp, vp, vp, vp, vp, dbl, vp]
+    lib.b200_implicit_stage.argtypes = [vp, vp, vp, vp, vp, dbl, vp]
     lib.b200_wfact.argtypes = [vp, vp, vp, dbl, dbl, vp]
     lib.b200_ldiv.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.b200_t_post_imp.argtypes = [vp, vp, vp, vp, vp, dbl, vp]

@@ -19,6 +19,7 @@
 #include "kernels_reg.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_imp5.cuh"
 
 using namespace b200;
 
@@ -111,7 +112,10 @@ struct b200_ctx {
   cudaStream_t side = nullptr;           // side stream: T_imp = (U − temp)/dtγ runs concurrently with the T_exp kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int exp_kernel = 5;  // B200_EXP_KERNEL=2|5: scalar row kernels (k2_*) or packed FFMA2 row kernels (k5_*)
-  int imp_kernel = 2;  // B200_IMP_KERNEL=2|3|4: variant of the fused implicit-stage kernel (2 is fastest; 3, 4 kept as A/B evidence)
+  int imp_kernel = 5;  // B200_IMP_KERNEL=5|2|3|4: fused implicit-stage kernel (5: packed row layout; 2, 3, 4 kept as A/B evidence)
+  int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
+  int imp_minb = 3;    // B200_IMP_MINB=3|4|2: CTAs/SM the nv=63 k5_imp_stage is compiled for (80, 64 or 128 registers; measured 149/181 µs)
+  int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   int ncf() const { return 4 + dims.n_tracers; }
   size_t nc() const { return (size_t)dims.nh * ncf() * 16 * dims.nv; }
@@ -335,6 +339,13 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k5_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 1, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 1, 63, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
   CK(cudaFuncSetAttribute(k_wfact<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
@@ -360,8 +371,11 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   c->dims = *d; c->prm = *p; c->ft = d->ft_bytes; c->rank = rank; c->nranks = nranks;
   if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
   if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
+  if (const char* e = getenv("B200_IMP_SOLVER")) c->imp_solver = atoi(e);
+  if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
+  if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
-  if (d->n_tracers > 0 && (c->legacy || c->imp_kernel != 2)) {
+  if (d->n_tracers > 0 && (c->legacy || (c->imp_kernel != 2 && c->imp_kernel != 5))) {
     delete c;
     return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
   }
@@ -810,6 +824,53 @@ static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One fused implicit stage (one Newton iteration of the CTS implicit solve, integrator.jl:63-120): N = U − J⁻¹·R(U) with
+// cache_imp!, Wfact, T_imp!, ldiv! and T_post_imp! in ONE kernel; U may carry unfiltered u₃ boundary values.
+template <class FT>
+static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtg, cudaStream_t s) {
+  const size_t bc = c->nc() * sizeof(FT), bf = c->nf() * sizeof(FT);
+  if (c->legacy == 1 || c->legacy == 2) {
+    CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
+    k_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(18), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                             (FT*)Nc, (FT*)Nf, (FT)dtg);
+    LAUNCH_CHECK(c);
+  } else if (c->imp_kernel == 4) {
+    k4_imp_stage<FT><<<c->dims.nh * 4, QT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
+                                                 (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+    LAUNCH_CHECK(c);
+  } else if (c->imp_kernel == 3) {
+    const int ncols = c->dims.nh * 16;
+    k3_imp_stage<FT><<<(ncols + 7) / 8, 256, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
+                                                   (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, ncols);
+    LAUNCH_CHECK(c);
+  } else if (c->imp_kernel == 5) {
+#define IMP5_LAUNCH(TS, NVC_, MB)                                                                                          \
+  k5_imp_stage<FT, TS, NVC_, MB><<<c->dims.nh, 256, smem_imp5<FT>(), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, \
+                                                                      (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg)
+    const bool nv63 = c->dims.nv == 63 && !c->generic_nv;
+    if (c->imp_solver == 0) IMP5_LAUNCH(0, 0, 4);
+    else if (c->imp_solver == 1 && nv63) IMP5_LAUNCH(1, 63, 3);
+    else if (c->imp_solver == 1) IMP5_LAUNCH(1, 0, 4);
+    else if (nv63 && c->imp_minb == 4) IMP5_LAUNCH(2, 63, 4);
+    else if (nv63 && c->imp_minb == 2) IMP5_LAUNCH(2, 63, 2);
+    else if (nv63) IMP5_LAUNCH(2, 63, 3);
+    else IMP5_LAUNCH(2, 0, 3);
+#undef IMP5_LAUNCH
+    LAUNCH_CHECK(c);
+  } else {
+    k2_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(11), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                              (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+    LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+extern "C" int b200_implicit_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtgamma, void* stream) {
+  return c->ft == 4 ? impl_imp_stage<float>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream)
+                    : impl_imp_stage<double>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream);
+}
+
 template <class FT>
 static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s) {
   const size_t bc = c->nc() * sizeof(FT), bf = c->nf() * sizeof(FT);
@@ -841,25 +902,8 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       if (dss_state(Uc, Uf)) return -1;
       const double dtg = dt * tb.ai[i][i];
       void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
-      if (fused && (c->legacy == 1 || c->legacy == 2)) {
-        CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
-        k_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(18), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                 (FT*)Nc, (FT*)Nf, (FT)dtg);
-        LAUNCH_CHECK(c);
-      } else if (fused && c->imp_kernel == 4) {
-        k4_imp_stage<FT><<<c->dims.nh * 4, QT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
-                                                     (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
-        LAUNCH_CHECK(c);
-      } else if (fused && c->imp_kernel == 3) {
-        const int ncols = c->dims.nh * 16;
-        k3_imp_stage<FT><<<(ncols + 7) / 8, 256, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
-                                                       (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, ncols);
-        LAUNCH_CHECK(c);
-      } else if (fused) {
-        k2_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(11), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                  (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
-        LAUNCH_CHECK(c);
+      if (fused) {
+        if (impl_imp_stage<FT>(c, Nc, Nf, Uc, Uf, dtg, s)) return -1;
       } else {
         if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
         CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));

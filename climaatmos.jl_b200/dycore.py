@@ -160,6 +160,12 @@ class AtmosSimulation:
     def remaining_tendency_phase_a(self, Yt, Y):
         self.remaining_tendency_phase(0, Yt, Y)
 
+    def implicit_stage(self, N, U, dtgamma):
+        """Fused implicit stage (one Newton iteration of the CTS stage solve, integrator.jl:63-120): N ← U − J⁻¹R(U)
+        plus the T_post_imp! correction, out of place."""
+        capi.check(self.lib.b200_implicit_stage(self.ctx, _p(N.c), _p(N.f), _p(U.c), _p(U.f), float(dtgamma), self._stream()),
+                   "b200_implicit_stage")
+
     def implicit_tendency(self, Yt, Y, t=0.0):
         """T_imp! (implicit_tendency.jl:36-98)."""
         capi.check(self.lib.b200_t_imp(self.ctx, _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), float(t), self._stream()), "b200_t_imp")

@@ -139,6 +139,12 @@ int b200_axpy_n(b200_ctx*, void* Uc, void* Uf, const void* uc, const void* uf, i
  * above in the order of DESIGN.md "Step trace" (role of CTS.step!, solve.jl:62,125).  The
  * state (Yc, Yf) is advanced in place. `fused` selects the fused implicit-stage kernel. */
 int b200_step_ars343(b200_ctx*, void* Yc, void* Yf, double t, int32_t fused, void* stream);
+/* One fused implicit stage = one Newton iteration of ClimaTimeSteppers' implicit solve on the stage problem
+ * (integrator.jl:63-120: initialize_imp!/cache_imp!, Wfact, T_imp!, ldiv!, U −= ΔU, cache_imp!, T_post_imp!):
+ *   N = U − J(U)⁻¹ (dtγ·T_imp(U))  [+ dtγ·(vtt_upwind − vtt_central)(N) when energy upwinding is on]
+ * in ONE kernel, out of place (U is read-only; its u₃ boundary faces are treated as zero). */
+int b200_implicit_stage(b200_ctx*, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtgamma,
+                        void* stream);
 /* Profiling aid: run ONE phase of b200_t_exp_lim — 0: pre-DSS kernel (Yₜ partial + ∇² fields),
  * 1: DSS of the ∇² fields, 2: hyperdiffusion apply kernel. */
 int b200_t_exp_phase(b200_ctx*, int32_t phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf,

@@ -30,7 +30,14 @@ timeit("t_exp phase0 (pre-DSS)", lambda: sim.remaining_tendency_phase(0, Yt, Y))
 timeit("t_exp phase1 (DSS H)", lambda: sim.remaining_tendency_phase(1, Yt, Y))
 timeit("t_exp phase2 (hyper apply)", lambda: sim.remaining_tendency_phase(2, Yt, Y))
 timeit("t_exp total", lambda: sim.remaining_tendency(Yt, None, Y))
+N = Y.zeros_like()
+timeit("implicit stage (fused)", lambda: sim.implicit_stage(N, Y, 39.0))
 timeit("dss state", lambda: sim.dss(Y))
+QUICK = bool(os.environ.get("QUICK"))
+if QUICK:
+    timeit("step fused", lambda: sim.step(True), reps=10)
+    print("finite:", bool(torch.isfinite(sim.Y.c).all()))
+    sys.exit(0)
 timeit("cache_imp", lambda: sim.set_implicit_precomputed_quantities(Y))
 timeit("t_imp", lambda: sim.implicit_tendency(Yt, Y))
 timeit("wfact", lambda: sim.update_jacobian(Y, 39.0))
