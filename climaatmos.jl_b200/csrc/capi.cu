@@ -109,12 +109,19 @@ struct b200_ctx {
   int** d_p2p_flags = nullptr;  // device array [n_neighbors]: address of my flag in neighbour q
   int *d_slot_nbr = nullptr, *d_slot_dst = nullptr, *d_nbr_nhg = nullptr, *d_nbr_rank = nullptr;
   int64_t launches = 0;
+  // CUDA graph of one fused step (single-rank contexts): captured on the second call with the same (Yc, Yf, stream)
+  int use_graph = 1;  // B200_GRAPH=0 disables
+  struct StepGraph { cudaGraphExec_t exec; void *Yc, *Yf; int64_t launches; };
+  std::vector<StepGraph> graphs;       // small cache (double-buffered callers alternate between two states)
+  cudaStream_t gstream = nullptr;      // capture/replay stream used when the caller passes the legacy default stream
+  cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
+  int eager_steps = 0;
   cudaStream_t side = nullptr;           // side stream: T_imp = (U − temp)/dtγ runs concurrently with the T_exp kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int exp_kernel = 5;  // B200_EXP_KERNEL=2|5: scalar row kernels (k2_*) or packed FFMA2 row kernels (k5_*)
   int imp_kernel = 5;  // B200_IMP_KERNEL=5|2|3|4: fused implicit-stage kernel (5: packed row layout; 2, 3, 4 kept as A/B evidence)
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
-  int imp_minb = 3;    // B200_IMP_MINB=3|4|2: CTAs/SM the nv=63 k5_imp_stage is compiled for (80, 64 or 128 registers; measured 149/181 µs)
+  int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
   int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   int ncf() const { return 4 + dims.n_tracers; }
@@ -335,14 +342,16 @@ template <class FT>
 static int set_attrs() {
   CK(cudaFuncSetAttribute(k2_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
   CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
-  CK(cudaFuncSetAttribute(k5_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
-  CK(cudaFuncSetAttribute(k5_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 1, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 1, 63, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
@@ -372,6 +381,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
   if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
   if (const char* e = getenv("B200_IMP_SOLVER")) c->imp_solver = atoi(e);
+  if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
   if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
@@ -431,6 +441,8 @@ extern "C" int b200_destroy(b200_ctx* c) {
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
   fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+  if (c->gstream) { cudaStreamDestroy(c->gstream); cudaEventDestroy(c->ev_gin); cudaEventDestroy(c->ev_gout); }
   if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
@@ -738,8 +750,12 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
                                         (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
   } else if (phase == 0 && c->exp_kernel == 5) {
-    k5_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                       (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+    if (c->dims.nv == 63 && !c->generic_nv)
+      k5_exp_a<FT, 63><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+    else
+      k5_exp_a<FT, 0><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                            (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
       k5_tracer_a<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(3), s>>>(
@@ -759,8 +775,12 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
                                         (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
   } else if (phase == 2 && hd && !c->legacy && c->exp_kernel == 5) {
-    k5_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+    if (c->dims.nv == 63 && !c->generic_nv)
+      k5_exp_c<FT, 63><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                      (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+    else
+      k5_exp_c<FT, 0><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                     (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
       k5_tracer_c<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(0), s>>>(
@@ -854,9 +874,9 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
     else if (c->imp_solver == 1 && nv63) IMP5_LAUNCH(1, 63, 3);
     else if (c->imp_solver == 1) IMP5_LAUNCH(1, 0, 4);
     else if (nv63 && c->imp_minb == 4) IMP5_LAUNCH(2, 63, 4);
-    else if (nv63 && c->imp_minb == 2) IMP5_LAUNCH(2, 63, 2);
-    else if (nv63) IMP5_LAUNCH(2, 63, 3);
-    else IMP5_LAUNCH(2, 0, 3);
+    else if (nv63 && c->imp_minb == 3) IMP5_LAUNCH(2, 63, 3);
+    else if (nv63) IMP5_LAUNCH(2, 63, 2);
+    else IMP5_LAUNCH(2, 0, 2);
 #undef IMP5_LAUNCH
     LAUNCH_CHECK(c);
   } else {
@@ -963,5 +983,54 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   return fused ? 0 : impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
 }
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
-  return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, (cudaStream_t)stream) : impl_step<double>(c, Yc, Yf, fused, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto run = [&](cudaStream_t q) { return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, q) : impl_step<double>(c, Yc, Yf, fused, q); };
+  // One CUDA graph per state buffer: ≈35 kernel launches, the side-stream fork/join and the memsets replay as one launch.
+  // Multi-rank contexts stay eager (the peer-memory halo passes a fresh flag value to every DSS call).
+  const bool graphable = c->use_graph && fused && c->nbr.empty() && !c->legacy;
+  if (!graphable) return run(s);
+  if (c->eager_steps < 1) { c->eager_steps++; return run(s); }  // first step eager: performs the lazy allocations
+  // the legacy default stream cannot be captured: order an internal stream after/before it with events instead
+  cudaStream_t q = s;
+  const bool legacy_stream = (s == nullptr || s == cudaStreamLegacy);
+  if (legacy_stream) {
+    if (!c->gstream) {
+      CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->ev_gin, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->ev_gout, cudaEventDisableTiming));
+    }
+    q = c->gstream;
+    CK(cudaEventRecord(c->ev_gin, s));
+    CK(cudaStreamWaitEvent(q, c->ev_gin, 0));
+  }
+  b200_ctx::StepGraph* G = nullptr;
+  for (auto& g : c->graphs) if (g.Yc == Yc && g.Yf == Yf) G = &g;
+  if (!G) {
+    if (c->graphs.size() >= 4) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+    const int64_t before = c->launches;
+    CK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal));
+    const int rc = run(q);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(q, &g);
+    if (rc != 0 || e != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      (void)cudaGetLastError();
+      c->use_graph = 0;  // fall back to eager launches for this context
+      c->launches = before;
+      return rc != 0 ? rc : run(s);
+    }
+    cudaGraphExec_t ex = nullptr;
+    CK(cudaGraphInstantiate(&ex, g, 0));
+    cudaGraphDestroy(g);
+    c->graphs.push_back({ex, Yc, Yf, c->launches - before});
+    c->launches = before;
+    G = &c->graphs.back();
+  }
+  CK(cudaGraphLaunch(G->exec, q));
+  c->launches += G->launches;
+  if (legacy_stream) {
+    CK(cudaEventRecord(c->ev_gout, q));
+    CK(cudaStreamWaitEvent(s, c->ev_gout, 0));
+  }
+  return 0;
 }

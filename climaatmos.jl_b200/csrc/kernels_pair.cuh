@@ -61,6 +61,19 @@ __device__ __forceinline__ void st4p(const P2<FT> (&a)[2], FT* __restrict__ g, i
   g[(j * 4 + 0) * nlev + v] = a[0].lo(); g[(j * 4 + 1) * nlev + v] = a[0].hi();
   g[(j * 4 + 2) * nlev + v] = a[1].lo(); g[(j * 4 + 3) * nlev + v] = a[1].hi();
 }
+// thread-pointer forms: g already points at (row j, level v); the four nodes of the row are nlev apart.  With a
+// compile-time nlev every offset is an immediate of the load/store (no per-access address arithmetic).
+template <class FT>
+__device__ __forceinline__ void ld4q(P2<FT> (&a)[2], const FT* __restrict__ g, int nlev, bool ok, FT dflt) {
+  FT t[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = ok ? g[i * nlev] : dflt;
+  a[0] = P2<FT>(t[0], t[1]); a[1] = P2<FT>(t[2], t[3]);
+}
+template <class FT>
+__device__ __forceinline__ void st4q(const P2<FT> (&a)[2], FT* __restrict__ g, int nlev) {
+  g[0] = a[0].lo(); g[nlev] = a[0].hi(); g[2 * nlev] = a[1].lo(); g[3 * nlev] = a[1].hi();
+}
 template <class FT>
 __device__ __forceinline__ void sputp(FT* s, const P2<FT> (&a)[2], int j, int v) {
   s[(j * 4 + 0) * LVP + v] = a[0].lo(); s[(j * 4 + 1) * LVP + v] = a[0].hi();
@@ -82,7 +95,8 @@ __device__ __forceinline__ void sgetp(const FT* s, P2<FT> (&a)[2], int j, int v)
   }
 
 // ---------------------------------------------------------------------------------------------
-template <class FT>
+// NVC: compile-time number of levels (63 in every production configuration), 0 = run-time P.nv
+template <class FT, int NVC>
 __global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
 k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
          const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H) {
@@ -92,12 +106,13 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* sx = hg + HG_ELEM * 16;
   FT *s_u3 = sx, *s_r = sx + SLAB, *s_u1 = sx + 2 * SLAB, *s_u2 = sx + 3 * SLAB, *s_U1 = sx + 4 * SLAB, *s_U2 = sx + 5 * SLAB,
      *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
-  B200_ROW_PROLOGUE
+  B200_ROW_PROLOGUE_NV(NVC)
   const bool interior = v > 0 && v < nv;
-  const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
+  const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v), offf = (size_t)e * 16 * nf + (n0 * nf + v);  // (row j, level v)
+  const FT* gY = Yc + offc;
   V rho[2], u1[2], u2[2], re[2], u3[2], U1[2], U2[2];
-  ld4p(rho, gY, nv, j, v, cv, FT(1)); ld4p(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4p(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
-  ld4p(re, gY + 48 * nv, nv, j, v, cv, FT(0)); ld4p(u3, Yf + (size_t)e * 16 * nf, nf, j, v, fv, FT(0));
+  ld4q(rho, gY, nv, cv, FT(1)); ld4q(u1, gY + 16 * nv, nv, cv, FT(0)); ld4q(u2, gY + 32 * nv, nv, cv, FT(0));
+  ld4q(re, gY + 48 * nv, nv, cv, FT(0)); ld4q(u3, Yf + offf, nf, fv, FT(0));
   sputp(s_u3, u3, j, v); sputp(s_r, rho, j, v); sputp(s_u1, u1, j, v); sputp(s_u2, u2, j, v);
   __syncthreads();  // hg + first exchange slabs
   V c1[2], c2[2];
@@ -142,8 +157,8 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
   }
   sputp(s_K, K, j, v);
-  FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv;
-  FT* gH = H ? H + (size_t)e * P.ncf * 16 * nv : nullptr;
+  FT* gT = Ytc + offc;
+  FT* gH = H ? H + offc : nullptr;
   const bool any_visc = P.viscous && __any_sync(FULLM, L.bvc != FT(0));
   V rjs[2];  // sc / J2
 #pragma unroll
@@ -156,7 +171,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     div4p<FT, 1>(F1, F2, mw, vl, wd);
 #pragma unroll
     for (int p = 0; p < 2; ++p) { wd[p] = wd[p] * rjs[p]; G1[p] = F1[p] * hh[p]; G2[p] = F2[p] * hh[p]; }
-    if (cv) { V nwd[2] = {-wd[0], -wd[1]}; st4p(nwd, gT, nv, j, v); }
+    if (cv) { V nwd[2] = {-wd[0], -wd[1]}; st4q(nwd, gT, nv); }
     div4p<FT, 1>(G1, G2, mw, vl, t);
     deta4p(hh, md, vl, g2);
     dxi4p<FT, 0>(hh, g1);
@@ -174,7 +189,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
 #pragma unroll
       for (int p = 0; p < 2; ++p) et[p] = fma2(t[p] * rjs[p], L.bvc, et[p]);
     }
-    if (cv) st4p(et, gT + 48 * nv, nv, j, v);
+    if (cv) st4q(et, gT + 48 * nv, nv);
     if (gH) {  // ∇²(s_d − s_d,r)  (hyperdiffusion.jl:142-147)
       V Q1[2], Q2[2];
       deta4p(ss, md, vl, g2);
@@ -183,7 +198,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       div4p<FT, 1>(Q1, Q2, mw, vl, t);
 #pragma unroll
       for (int p = 0; p < 2; ++p) t[p] = t[p] * rjs[p];
-      if (cv) st4p(t, gH + 48 * nv, nv, j, v);
+      if (cv) st4q(t, gH + 48 * nv, nv);
     }
   }
   // ---- momentum: split-form PGF (advection.jl:82-88)
@@ -222,7 +237,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       L2[p] = (a[p] - (HGP(HG_GC12, p) * b[p] - HGP(HG_GC22, p) * dz1[p]) * rJ2) * L.sc;
       if (P.viscous) { t1[p] = fma2(L1[p], L.bvc, t1[p]); t2[p] = fma2(L2[p], L.bvc, t2[p]); }
     }
-    if (gH && cv) { st4p(L1, gH, nv, j, v); st4p(L2, gH + 16 * nv, nv, j, v); }
+    if (gH && cv) { st4q(L1, gH, nv); st4q(L2, gH + 16 * nv, nv); }
     if (gH) {  // ∇²u₃ = wdivₕ(gradₕ(ᶜinterp(u₃))) on the flat shell
       V P1[2], P2_[2];
       deta4p(u3c, md, vl, a);
@@ -231,7 +246,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       div4p<FT, 1>(P1, P2_, mw, vl, b);
 #pragma unroll
       for (int p = 0; p < 2; ++p) b[p] = b[p] * rjs[p];
-      if (cv) st4p(b, gH + 32 * nv, nv, j, v);
+      if (cv) st4q(b, gH + 32 * nv, nv);
     }
     // (ᶜf³ + ᶜω³) × CT12(ᶜu), Rayleigh sponge, Held–Suarez drag
     deta4p(u1, mw, vl, a);
@@ -285,7 +300,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       t3[p] = -(jt1 * ub2 - jt2 * ub1) - dk;
       if (any_v3) t3[p] = fma2((lap[p] * L.sf2i) * rJ2, L.bvf, t3[p]);
     }
-    if (fv) st4p(t3, Ytf + (size_t)e * 16 * nf, nf, j, v);
+    if (fv) st4q(t3, Ytf + offf, nf);
   }
   sputp(s_X1, X1, j, v); sputp(s_X2, X2, j, v);
   __syncthreads();
@@ -298,13 +313,13 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       t1[p] = t1[p] - (X1[p] + h1[p]) * irm;
       t2[p] = t2[p] - (X2[p] + h2[p]) * irm;
     }
-    st4p(t1, gT + 16 * nv, nv, j, v);
-    st4p(t2, gT + 32 * nv, nv, j, v);
+    st4q(t1, gT + 16 * nv, nv);
+    st4q(t2, gT + 32 * nv, nv);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class FT>
+template <class FT, int NVC>
 __global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
 k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
          const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
@@ -313,16 +328,17 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* hg = reinterpret_cast<FT*>(smem_raw);
   FT* s_w = hg + HG_ELEM * 16;
   FT* s_a = s_w + SLAB;
-  B200_ROW_PROLOGUE
+  B200_ROW_PROLOGUE_NV(NVC)
   const int part = blockIdx.y;
-  const FT* gH = H + (size_t)e * P.ncf * 16 * nv;
-  FT* gT = Ytc + (size_t)e * P.ncf * 16 * nv;
-  FT* gF = Ytf + (size_t)e * 16 * nf;
+  const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v);
+  const FT* gH = H + offc;
+  FT* gT = Ytc + offc;
+  FT* gF = Ytf + ((size_t)e * 16 * nf + (n0 * nf + v));
   V a[2], b[2], g1[2];
   if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
     V L1[2], L2[2], old1[2], old2[2];
-    ld4p(L1, gH, nv, j, v, cv, FT(0)); ld4p(L2, gH + 16 * nv, nv, j, v, cv, FT(0));
-    ld4p(old1, gT + 16 * nv, nv, j, v, cv, FT(0)); ld4p(old2, gT + 32 * nv, nv, j, v, cv, FT(0));
+    ld4q(L1, gH, nv, cv, FT(0)); ld4q(L2, gH + 16 * nv, nv, cv, FT(0));
+    ld4q(old1, gT + 16 * nv, nv, cv, FT(0)); ld4q(old2, gT + 32 * nv, nv, cv, FT(0));
     __syncthreads();
     V U1[2], U2[2], D2[2], ze[2], dD1[2], dz1[2];
     METRIC_FLUX(U1, U2, L1, L2, HGP(HG_J2, p))
@@ -343,12 +359,12 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       V Qb = (a[p] * P.ddf - (HGP(HG_GC12, p) * b[p] - HGP(HG_GC22, p) * dz1[p]) * rJ2) * L.sc;
       old1[p] = old1[p] - Qa * P.nu4v; old2[p] = old2[p] - Qb * P.nu4v;
     }
-    if (cv) { st4p(old1, gT + 16 * nv, nv, j, v); st4p(old2, gT + 32 * nv, nv, j, v); }
+    if (cv) { st4q(old1, gT + 16 * nv, nv); st4q(old2, gT + 32 * nv, nv); }
   } else if (part == 1) {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
     V rho[2], Ls[2], old3[2], Q1[2], Q2[2];
-    ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
-    ld4p(Ls, gH + 48 * nv, nv, j, v, cv, FT(0));
-    ld4p(old3, gT + 48 * nv, nv, j, v, cv, FT(0));
+    ld4q(rho, Yc + offc, nv, cv, FT(1));
+    ld4q(Ls, gH + 48 * nv, nv, cv, FT(0));
+    ld4q(old3, gT + 48 * nv, nv, cv, FT(0));
     __syncthreads();
     deta4p(Ls, md, vl, a);
     dxi4p<FT, 0>(Ls, g1);
@@ -356,12 +372,12 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     div4p<FT, 1>(Q1, Q2, mw, vl, b);
 #pragma unroll
     for (int p = 0; p < 2; ++p) old3[p] = old3[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
-    if (cv) st4p(old3, gT + 48 * nv, nv, j, v);
+    if (cv) st4q(old3, gT + 48 * nv, nv);
   } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
     V rho[2], L3[2], oldf[2], P1[2], P2_[2], q[2], w[2];
-    ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
-    ld4p(L3, gH + 32 * nv, nv, j, v, cv, FT(0));
-    ld4p(oldf, gF, nf, j, v, fv, FT(0));
+    ld4q(rho, Yc + offc, nv, cv, FT(1));
+    ld4q(L3, gH + 32 * nv, nv, cv, FT(0));
+    ld4q(oldf, gF, nf, fv, FT(0));
     __syncthreads();
     deta4p(L3, md, vl, a);
     dxi4p<FT, 0>(L3, g1);
@@ -389,7 +405,7 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
         }
         oldf[p] = oldf[p] - val * P.nu4v;
       }
-      st4p(oldf, gF, nf, j, v);
+      st4q(oldf, gF, nf);
     }
   }
 }

@@ -72,6 +72,16 @@ __device__ __forceinline__ void sget(const FT* s, FT (&a)[4], int j, int v) {
   const Lev<FT> L = load_lev(vlev, v, nv);                                                            \
   const int n0 = j * 4;
 
+#define B200_ROW_PROLOGUE_NV(NVC_)                                                                            \
+  const int e = blockIdx.x, lane = threadIdx.x & 31, vl = lane & 7, j = lane >> 3;                    \
+  const int v = (threadIdx.x >> 5) * 8 + vl, nv = (NVC_) ? (NVC_) : P.nv, nf = nv + 1;                                  \
+  const bool cv = v < nv, fv = v < nf;                                                                \
+  for (int k = threadIdx.x; k < HG_ELEM * 16; k += CT) hg[k] = hgeo[(size_t)e * HG_N * 16 + k];       \
+  FT md[4], mw[4];                                                                                    \
+  _Pragma("unroll") for (int k = 0; k < 4; ++k) { md[k] = cM<FT>(j * 4 + k); mw[k] = cM<FT>(16 + j * 4 + k); } \
+  const Lev<FT> L = load_lev(vlev, v, nv);                                                            \
+  const int n0 = j * 4;
+
 // ---------------------------------------------------------------------------------------------
 template <class FT>
 __global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
