@@ -111,6 +111,7 @@ struct b200_ctx {
   int64_t launches = 0;
   // CUDA graph of one fused step (single-rank contexts): captured on the second call with the same (Yc, Yf, stream)
   int use_graph = 1;  // B200_GRAPH=0 disables
+  int fuse_axdss = 1; // B200_FUSE_AXDSS=0: stage increment and state DSS as two passes (k_axpy_n, k_dss2) instead of k_axpy_dss
   struct StepGraph { cudaGraphExec_t exec; void *Yc, *Yf; int64_t launches; };
   std::vector<StepGraph> graphs;       // small cache (double-buffered callers alternate between two states)
   cudaStream_t gstream = nullptr;      // capture/replay stream used when the caller passes the legacy default stream
@@ -382,6 +383,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
   if (const char* e = getenv("B200_IMP_SOLVER")) c->imp_solver = atoi(e);
   if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
+  if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
   if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
@@ -844,6 +846,35 @@ static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT 
   return 0;
 }
 
+// U = dss!(u + Σ c_j T_j) in one kernel (k_axpy_dss); returns 1 when this context/call cannot use it (caller falls back)
+template <class FT>
+static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int n, const void* const* Tc,
+                         const void* const* Tf, const double* coef, cudaStream_t s) {
+  const int nh = c->dims.nh, nv = c->dims.nv;
+  const bool small = (size_t)nh * c->ncf() * 16 * (size_t)(nv + 1) < (size_t)INT32_MAX;
+  if (!c->fuse_axdss || c->legacy || !c->nbr.empty() || c->dims.nh_ghost > 0 || !small) return 1;
+  AxDssArgs<FT> A;
+  int m = 0;
+  for (int k = 0; k < n; ++k) {
+    if (coef[k] == 0.0) continue;
+    if (m >= AXPY_MAX) return 1;
+    A.Tc[m] = (const FT*)Tc[k]; A.Tf[m] = (const FT*)Tf[k]; A.c[m] = (FT)coef[k]; ++m;
+  }
+  if (m < 1) return 1;
+  A.out_c = (FT*)Uc; A.out_f = (FT*)Uf; A.base_c = (const FT*)uc; A.base_f = (const FT*)uf; A.ncf = c->ncf(); A.nv = nv;
+  const int nbn = (c->nnodes + 3) / 4;
+  dim3 blk(64, 4), grd(nbn + nh);
+  const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
+  switch (m) {
+#define AXD(N_) case N_: k_axpy_dss<FT, N_><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nbn); break;
+    AXD(1) AXD(2) AXD(3) AXD(4) AXD(5) AXD(6) AXD(7) AXD(8)
+#undef AXD
+    default: return 1;
+  }
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One fused implicit stage (one Newton iteration of the CTS implicit solve, integrator.jl:63-120): N = U − J⁻¹·R(U) with
 // cache_imp!, Wfact, T_imp!, ldiv! and T_post_imp! in ONE kernel; U may carry unfiltered u₃ boundary values.
@@ -918,8 +949,13 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         if (tb.ai[i][j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.ai[i][j]; }
       }
       // fused path: the u₃ boundary filter of cache_imp! is folded into the increment (the DSS keeps zeros)
-      if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
-      if (dss_state(Uc, Uf)) return -1;
+      // fused path: increment and DSS in one kernel where possible (single rank), else two passes
+      int rc = fused ? impl_axpy_dss<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s) : 1;
+      if (rc < 0) return -1;
+      if (rc == 1) {
+        if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
+        if (dss_state(Uc, Uf)) return -1;
+      }
       const double dtg = dt * tb.ai[i][i];
       void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
       if (fused) {
@@ -977,9 +1013,13 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       if (tb.be[j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.be[j]; }
       if (tb.bi[j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.bi[j]; }
     }
-    if (impl_axpy<FT>(c, Yc, Yf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
+    int rc = fused ? impl_axpy_dss<FT>(c, Yc, Yf, Yc, Yf, n, Tc, Tf, cf, s) : 1;
+    if (rc < 0) return -1;
+    if (rc == 1) {
+      if (impl_axpy<FT>(c, Yc, Yf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
+      if (dss_state(Yc, Yf)) return -1;
+    }
   }
-  if (dss_state(Yc, Yf)) return -1;
   return fused ? 0 : impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
 }
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {

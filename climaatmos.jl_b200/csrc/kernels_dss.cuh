@@ -270,6 +270,129 @@ __global__ void __launch_bounds__(256) k_axpy_n(FT* out, const FT* base, AxpyArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_axpy_dss — stage increment FUSED with the state DSS (single-rank contexts):
+//     U = dss!(u + Σ_j c_j T_j)          (CTS fused_increment! followed by dss!, constrain_state.jl:59-64)
+// The separate passes move (2 + n)·S for the increment and then 2·(12/16)·S for the DSS; here every unique
+// perimeter node assembles the increment of each of its members on the fly (same FMA order as k_axpy_n, so the
+// result is bitwise the one of k_axpy_n → k_dss2), sums, and writes the members once; the four interior nodes of
+// an element are a plain increment.  The u₃ boundary filter of cache_imp! is folded in (face levels 0 and nv are
+// written as zero).  N = number of tendency terms (compile time: all member loads are issued back to back).
+template <class FT>
+struct AxDssArgs {
+  FT* out_c; FT* out_f;
+  const FT* base_c; const FT* base_f;
+  const FT* Tc[AXPY_MAX]; const FT* Tf[AXPY_MAX];
+  FT c[AXPY_MAX];
+  int ncf, nv;
+};
+template <class FT, int N>
+__device__ __forceinline__ FT axv(const FT* __restrict__ b, const FT* const* T, const FT* c, int o) {
+  FT t[N];
+  FT r = b[o];
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = T[k][o];
+#pragma unroll
+  for (int k = 0; k < N; ++k) r += c[k] * t[k];
+  return r;
+}
+template <class FT, int N, int CNT>
+__device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode<FT>& R, int cnt, int v) {
+  const int nv = A.nv, nf = nv + 1, ec = A.ncf * 16 * nv, ef = 16 * nf;
+  int oc[CNT], of[CNT];
+#pragma unroll
+  for (int q = 0; q < CNT; ++q) {
+    const int el = R.mem[q] >> 4, nd = R.mem[q] & 15;
+    oc[q] = el * ec + nd * nv + v; of[q] = el * ef + nd * nf + v;
+  }
+  if (v < nv) {
+    // ρ, then the Covariant12 pair (uₕ₁, uₕ₂) in the local physical basis, then ρe_tot and the tracers
+    FT x[CNT], y[CNT];
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q]) : FT(0);
+    {
+      FT s = FT(0);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) A.out_c[oc[q]] = s;
+    }
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) {
+      x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + 16 * nv) : FT(0);
+      y[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + 32 * nv) : FT(0);
+    }
+    {
+      FT su = FT(0), sv = FT(0);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (CNT == 2 || q < cnt) {
+          FT uu = R.ai[q][0] * x[q] + R.ai[q][1] * y[q];
+          FT vv = R.ai[q][2] * x[q] + R.ai[q][3] * y[q];
+          su += R.w[q] * uu; sv += R.w[q] * vv;
+        }
+#pragma unroll
+      for (int q = 0; q < CNT; ++q)
+        if (CNT == 2 || q < cnt) {
+          A.out_c[oc[q] + 16 * nv] = R.a[q][0] * su + R.a[q][1] * sv;
+          A.out_c[oc[q] + 32 * nv] = R.a[q][2] * su + R.a[q][3] * sv;
+        }
+    }
+    for (int k = 3; k < A.ncf; ++k) {
+      const int ko = k * 16 * nv;
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + ko) : FT(0);
+      FT s = FT(0);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) A.out_c[oc[q] + ko] = s;
+    }
+  }
+  if (v < nf) {
+    FT s = FT(0);
+    if (v > 0 && v < nv) {
+      FT x[CNT];
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_f, A.Tf, A.c, of[q]) : FT(0);
+#pragma unroll
+      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
+    }
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) A.out_f[of[q]] = s;
+  }
+}
+// blocks [0, nbn): four unique perimeter nodes × 64 levels;  blocks [nbn, nbn + nh): the 4 interior nodes of one element
+template <class FT, int N>
+__global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int nnodes, int nbn) {
+  __shared__ DssNode<FT> sr[4];
+  const int v = threadIdx.x;
+  if ((int)blockIdx.x >= nbn) {
+    const int e = blockIdx.x - nbn, nv = A.nv, nf = nv + 1;
+    const int nd = 5 + (threadIdx.y & 1) + 4 * (threadIdx.y >> 1);  // nodes (j, i) ∈ {1,2}²
+    if (v < nv) {
+      const int o = e * A.ncf * 16 * nv + nd * nv + v;
+      for (int k = 0; k < A.ncf; ++k) A.out_c[o + k * 16 * nv] = axv<FT, N>(A.base_c, A.Tc, A.c, o + k * 16 * nv);
+    }
+    if (v < nf) {
+      const int o = e * 16 * nf + nd * nf + v;
+      A.out_f[o] = (v > 0 && v < nv) ? axv<FT, N>(A.base_f, A.Tf, A.c, o) : FT(0);
+    }
+    return;
+  }
+  const int node = blockIdx.x * 4 + threadIdx.y;
+  constexpr int RW = sizeof(DssNode<FT>) / 4;
+  if (node < nnodes && v < RW) reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v] = reinterpret_cast<const uint32_t*>(&rec[node])[v];
+  if (RW > 64 && node < nnodes && v + 64 < RW)
+    reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v + 64] = reinterpret_cast<const uint32_t*>(&rec[node])[v + 64];
+  __syncthreads();
+  if (node >= nnodes) return;
+  const DssNode<FT>& R = sr[threadIdx.y];
+  const int cnt = R.cnt;
+  if (cnt == 2) axdss_body<FT, N, 2>(A, R, cnt, v);
+  else axdss_body<FT, N, 4>(A, R, cnt, v);
+}
+
 // out = (a - b) * s   (T_imp[i] = (U - temp)/dtγ)
 template <class FT, int VEC>
 __global__ void __launch_bounds__(256) k_diff_scale(FT* out, const FT* a, const FT* b, FT s, size_t nvec) {

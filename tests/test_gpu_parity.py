@@ -364,3 +364,51 @@ def test_full_size_properties_he30_ze63_f32():
     scale = (vol * np.abs(rt)).sum(axis=(1, 2))
     assert np.abs(per_elem / scale).max() < 5e-5
     sim.close()
+
+
+def _steps_with_env(env, FT, name, nsteps=3, **kw):
+    import os
+
+    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_IMP_KERNEL", "B200_IMP_SOLVER", "B200_GENERIC_NV")
+    old = {k: os.environ.pop(k, None) for k in keys}
+    os.environ.update(env)
+    try:
+        sim, _ = make(FT, name, **kw)
+        for _ in range(nsteps):
+            sim.step(fused=True)
+        out = sim.Y.cpu()
+        n = sim.launch_count()
+        sim.close()
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+            if old[k] is not None:
+                os.environ[k] = old[k]
+    return out, n
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["he4ze10", "he3ze63"])
+def test_fused_increment_dss_and_graph_are_bitwise_neutral(FT, name):
+    """k_axpy_dss (stage increment fused with the state DSS) and the CUDA-graph replay of the step must give bitwise the state of
+    the separate k_axpy_n → k_dss2 passes launched eagerly: they only remove memory passes and launches."""
+    (rc, rf), n_ref = _steps_with_env({"B200_FUSE_AXDSS": "0", "B200_GRAPH": "0"}, FT, name)
+    (gc, gf), n_fused = _steps_with_env({}, FT, name)
+    assert np.array_equal(rc, gc) and np.array_equal(rf, gf)
+    assert n_fused < n_ref  # 8 launches fewer per step
+    (tc, tf), _ = _steps_with_env({"B200_FUSE_AXDSS": "0", "B200_GRAPH": "0"}, FT, name, tracers=_tracer_fns())
+    (hc, hf), _ = _steps_with_env({}, FT, name, tracers=_tracer_fns())
+    assert np.array_equal(tc, hc) and np.array_equal(tf, hf)
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_implicit_stage_variants_agree(FT):
+    """The fused implicit-stage kernels (k5_imp_stage with parallel cyclic reduction, two-sided Thomas, one-sided Thomas; the
+    nv = 63 specialisation and the generic build; the previous-generation k2_imp_stage) agree to round-off."""
+    ref = _steps_with_env({"B200_IMP_KERNEL": "2"}, FT, "he3ze63", nsteps=2)[0]
+    lim = 1e-12 if FT == np.float64 else 2e-6
+    for env in ({}, {"B200_IMP_SOLVER": "1"}, {"B200_IMP_SOLVER": "0"}, {"B200_GENERIC_NV": "1"}):
+        got = _steps_with_env(env, FT, "he3ze63", nsteps=2)[0]
+        for k in range(4):
+            assert rel(got[0][:, k], ref[0][:, k]) < lim, (env, k)
+        assert rel(got[1], ref[1]) < (1e-10 if FT == np.float64 else 2e-4), env

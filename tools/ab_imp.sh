@@ -2,9 +2,8 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
-echo "== parity default"; python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "== parity GENERIC_NV"; B200_GENERIC_NV=1 python -m pytest tests -m gpu -x -q -k "step or fused or tracer or smoke or tend or hook" 2>&1 | tail -3
-for cfg in "" "B200_GENERIC_NV=1"; do
+echo "== parity default"; python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for cfg in "" "B200_FUSE_AXDSS=0"; do
   echo "== timing [$cfg]"; env $cfg QUICK=1 python tools/gpu_time_kernels.py 2>&1 | grep -E "implicit stage|step fused|finite|phase|dss"
 done
 } > gpurun_out/ab_imp.log 2>&1
