@@ -111,6 +111,7 @@ struct b200_ctx {
   int64_t launches = 0;
   // CUDA graph of one fused step (single-rank contexts): captured on the second call with the same (Yc, Yf, stream)
   int use_graph = 1;  // B200_GRAPH=0 disables
+  int pdl = 63;       // B200_PDL=<bit mask>: programmatic dependent launch per kernel group (1 exp_a, 2 exp_c, 4 dss2, 8 axpy, 16 imp, 32 diff); 0 = off
   int fuse_axdss = 1; // B200_FUSE_AXDSS=0: stage increment and state DSS as two passes (k_axpy_n, k_dss2) instead of k_axpy_dss
   struct StepGraph { cudaGraphExec_t exec; void *Yc, *Yf; int64_t launches; };
   std::vector<StepGraph> graphs;       // small cache (double-buffered callers alternate between two states)
@@ -383,6 +384,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
   if (const char* e = getenv("B200_IMP_SOLVER")) c->imp_solver = atoi(e);
   if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
+  if (const char* e = getenv("B200_PDL")) c->pdl = atoi(e);
   if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
   if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
@@ -452,6 +454,21 @@ extern "C" int b200_destroy(b200_ctx* c) {
 }
 
 extern "C" int64_t b200_launch_count(b200_ctx* c) { return c ? c->launches : 0; }
+
+// Kernel launch through cudaLaunchKernelEx, optionally as a programmatic dependent launch (PDL): the grid may start while the tail
+// of the previous kernel of the stream is still running; every kernel launched this way executes griddepcontrol.wait before it touches
+// global data (common.cuh: pdl_wait), so the stream order of memory effects is unchanged.
+template <typename... P, typename... A>
+static cudaError_t launchx(int pdl, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
 
 #define LAUNCH_CHECK(c)                                                               \
   do {                                                                                \
@@ -677,8 +694,8 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   for (int k = 0; k < A.n; ++k) pairs |= (A.it[k].p1 != nullptr) << k;
   const bool small = (size_t)(nh + c->dims.nh_ghost) * 64 * (size_t)(nv + 1) < (size_t)INT32_MAX;  // 32-bit offsets
 #define DSS2(NI, PM)                                                                               \
-  (halo ? (void)(k_dss2<FT, NI, PM, true><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh))               \
-        : (void)(k_dss2<FT, NI, PM, false><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nh)))
+  (halo ? (void)(launchx(c->pdl & 4, k_dss2<FT, NI, PM, true>, grd, blk, 0, s, A, rec, c->nnodes, nh))               \
+        : (void)(launchx(c->pdl & 4, k_dss2<FT, NI, PM, false>, grd, blk, 0, s, A, rec, c->nnodes, nh)))
   if (c->legacy || !small) { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
   else if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);   // state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃
   else if (A.n == 3 && pairs == 0x1) DSS2(3, 0x1);   // ∇² fields: (∇²u₁,∇²u₂), ∇²u₃, ∇²s_d
@@ -716,8 +733,8 @@ static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* co
   bool al = (N % 4 == 0) && (((uintptr_t)out | (uintptr_t)base) % (4 * sizeof(FT)) == 0);
   for (int k = 0; k < A.n; ++k) al = al && ((uintptr_t)A.T[k] % (4 * sizeof(FT)) == 0);
   int blocks = 148 * 8;
-  if (al) k_axpy_n<FT, 4><<<blocks, 256, 0, s>>>(out, base, A, N / 4, nlev);
-  else k_axpy_n<FT, 1><<<blocks, 256, 0, s>>>(out, base, A, N, nlev);
+  if (al) launchx(c->pdl & 8, k_axpy_n<FT, 4>, blocks, 256, 0, s, out, base, A, N / 4, nlev);
+  else launchx(c->pdl & 8, k_axpy_n<FT, 1>, blocks, 256, 0, s, out, base, A, N, nlev);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -753,10 +770,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     LAUNCH_CHECK(c);
   } else if (phase == 0 && c->exp_kernel == 5) {
     if (c->dims.nv == 63 && !c->generic_nv)
-      k5_exp_a<FT, 63><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+      launchx(c->pdl & 1, k5_exp_a<FT, 63>, c->dims.nh, CT, smem_row<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                              (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     else
-      k5_exp_a<FT, 0><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+      launchx(c->pdl & 1, k5_exp_a<FT, 0>, c->dims.nh, CT, smem_row<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
@@ -778,10 +795,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     LAUNCH_CHECK(c);
   } else if (phase == 2 && hd && !c->legacy && c->exp_kernel == 5) {
     if (c->dims.nv == 63 && !c->generic_nv)
-      k5_exp_c<FT, 63><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+      launchx(c->pdl & 2, k5_exp_c<FT, 63>, dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                       (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     else
-      k5_exp_c<FT, 0><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+      launchx(c->pdl & 2, k5_exp_c<FT, 0>, dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                      (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
@@ -840,8 +857,8 @@ static Tableau ars343() {
 template <class FT>
 static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT sc, size_t N, cudaStream_t s) {
   bool al = (N % 4 == 0) && (((uintptr_t)out | (uintptr_t)a | (uintptr_t)b) % (4 * sizeof(FT)) == 0);
-  if (al) k_diff_scale<FT, 4><<<148 * 8, 256, 0, s>>>(out, a, b, sc, N / 4);
-  else k_diff_scale<FT, 1><<<148 * 8, 256, 0, s>>>(out, a, b, sc, N);
+  if (al) launchx(c->pdl & 32, k_diff_scale<FT, 4>, 148 * 8, 256, 0, s, out, a, b, sc, N / 4);
+  else launchx(c->pdl & 32, k_diff_scale<FT, 1>, 148 * 8, 256, 0, s, out, a, b, sc, N);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -866,7 +883,7 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
   dim3 blk(64, 4), grd(nbn + nh);
   const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
   switch (m) {
-#define AXD(N_) case N_: k_axpy_dss<FT, N_><<<grd, blk, 0, s>>>(A, rec, c->nnodes, nbn); break;
+#define AXD(N_) case N_: launchx(c->pdl & 8, k_axpy_dss<FT, N_>, grd, blk, 0, s, A, rec, c->nnodes, nbn); break;
     AXD(1) AXD(2) AXD(3) AXD(4) AXD(5) AXD(6) AXD(7) AXD(8)
 #undef AXD
     default: return 1;
@@ -898,7 +915,7 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
     LAUNCH_CHECK(c);
   } else if (c->imp_kernel == 5) {
 #define IMP5_LAUNCH(TS, NVC_, MB)                                                                                          \
-  k5_imp_stage<FT, TS, NVC_, MB><<<c->dims.nh, 256, smem_imp5<FT>(), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, \
+  launchx(c->pdl & 16, k5_imp_stage<FT, TS, NVC_, MB>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, \
                                                                       (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg)
     const bool nv63 = c->dims.nv == 63 && !c->generic_nv;
     if (c->imp_solver == 0) IMP5_LAUNCH(0, 0, 4);

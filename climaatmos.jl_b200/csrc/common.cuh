@@ -63,6 +63,24 @@ struct Par {
   FT hs_ka, hs_ks, hs_kf, hs_sigb, hs_isig, hs_dTy, hs_Teq, hs_dthz, hs_Tmin, hs_iMSLP, hs_ikap;
 };
 
+// Programmatic dependent launch (capi.cu: launchx).  pdl_launch lets the next kernel of the stream start its CTAs as soon as every
+// CTA of this grid has been scheduled; pdl_wait blocks until all earlier grids have completed and their writes are visible.  A kernel
+// only reads context constants (geometry, level tables, DSS records) before pdl_wait.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// pdl_wait + pointer laundering.  Loads through `const T* __restrict__` kernel parameters are "invariant" for the compiler and may be
+// hoisted above any barrier, including griddepcontrol.wait (observed: k5_exp_a read the state before the previous kernel had written
+// it).  Passing the pointers that earlier kernels write through an opaque asm AFTER the wait makes every later load depend on it.
+template <class P> __device__ __forceinline__ void pdl_launder(P& p) {
+  unsigned long long u = reinterpret_cast<unsigned long long>(p);
+  asm volatile("" : "+l"(u) : : "memory");
+  p = reinterpret_cast<P>(u);
+}
+template <class... P> __device__ __forceinline__ void pdl_wait(P&... p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  (pdl_launder(p), ...);
+}
+
 // ---------------------------------------------------------------------------------------------
 template <class FT> __device__ __forceinline__ FT fmax_(FT a, FT b) { return a > b ? a : b; }
 template <class FT> __device__ __forceinline__ FT fmin_(FT a, FT b) { return a < b ? a : b; }

@@ -177,6 +177,7 @@ __device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R,
 template <class FT, int NI, int PAIRS, bool HALO>
 __global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int nnodes, int nh) {
   __shared__ DssNode<FT> sr[4];
+  pdl_launch();
   const int v = threadIdx.x;
   const int node = blockIdx.x * 4 + threadIdx.y;
   constexpr int RW = sizeof(DssNode<FT>) / 4;
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __re
     reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v + 64] = reinterpret_cast<const uint32_t*>(&rec[node])[v + 64];
   __syncthreads();
   if (node >= nnodes) return;
+  pdl_wait();
   const DssNode<FT>& R = sr[threadIdx.y];
   const int cnt = R.cnt;  // uniform over the two warps of a node
   if (cnt == 2) dss_body<FT, NI, PAIRS, 2, HALO>(A, R, cnt, v, nh);
@@ -251,6 +253,10 @@ struct AxpyArgs {
 template <class FT, int VEC>
 __global__ void __launch_bounds__(256) k_axpy_n(FT* out, const FT* base, AxpyArgs<FT> A, size_t nvec, int nlev) {
   struct alignas(sizeof(FT) * VEC) Vt { FT x[VEC]; };
+  pdl_launch();
+  pdl_wait(out, base);
+#pragma unroll
+  for (int k = 0; k < AXPY_MAX; ++k) pdl_launder(A.T[k]);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     Vt r = reinterpret_cast<const Vt*>(base)[i];
@@ -366,8 +372,10 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
 template <class FT, int N>
 __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int nnodes, int nbn) {
   __shared__ DssNode<FT> sr[4];
+  pdl_launch();
   const int v = threadIdx.x;
   if ((int)blockIdx.x >= nbn) {
+    pdl_wait();
     const int e = blockIdx.x - nbn, nv = A.nv, nf = nv + 1;
     const int nd = 5 + (threadIdx.y & 1) + 4 * (threadIdx.y >> 1);  // nodes (j, i) ∈ {1,2}²
     if (v < nv) {
@@ -387,6 +395,7 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
     reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v + 64] = reinterpret_cast<const uint32_t*>(&rec[node])[v + 64];
   __syncthreads();
   if (node >= nnodes) return;
+  pdl_wait();
   const DssNode<FT>& R = sr[threadIdx.y];
   const int cnt = R.cnt;
   if (cnt == 2) axdss_body<FT, N, 2>(A, R, cnt, v);
@@ -397,6 +406,8 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
 template <class FT, int VEC>
 __global__ void __launch_bounds__(256) k_diff_scale(FT* out, const FT* a, const FT* b, FT s, size_t nvec) {
   struct alignas(sizeof(FT) * VEC) Vt { FT x[VEC]; };
+  pdl_launch();
+  pdl_wait(out, a, b);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     Vt x = reinterpret_cast<const Vt*>(a)[i], y = reinterpret_cast<const Vt*>(b)[i], r;

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256, (sizeof(FT) == 4 ? MINB : 2))
 k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
              const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg) {
   using V2 = P2<FT>;
+  pdl_launch();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V2* sb = reinterpret_cast<V2*>(smem_raw);
   V2 *s_rho = sb, *s_u3 = sb + PSLAB, *s_h = sb + 2 * PSLAB, *s_A = sb + 3 * PSLAB, *s_M = sb + 4 * PSLAB,
@@ -140,6 +141,7 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   const FT sc2i = vlev->sc2i[vc], phi = vlev->phic[vc], mc = vlev->mc[vc], mclo = vlev->mc[vmc], rmc = vlev->rmc[vc],
            rmclo = vlev->rmc[vmc], g33lo = vlev->g33f[vf], g33hi = vlev->g33f[vf1], g33m = vlev->g33f[vm],
            dphif = vlev->dphif[vf], beta = P.rayleigh ? vlev->brw[vf] : FT(0);
+  pdl_wait(Yc, Yf, Nc, Nf);
   const int cs = 16 * nv;  // component stride of Y.c
   const FT* gY = Yc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + v);   // (ρ, node n0, level v) of this thread
   const FT* gYf = Yf + ((size_t)e * 16 * nf + n0 * nf + v);

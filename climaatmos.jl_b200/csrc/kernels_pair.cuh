@@ -106,7 +106,9 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* sx = hg + HG_ELEM * 16;
   FT *s_u3 = sx, *s_r = sx + SLAB, *s_u1 = sx + 2 * SLAB, *s_u2 = sx + 3 * SLAB, *s_U1 = sx + 4 * SLAB, *s_U2 = sx + 5 * SLAB,
      *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
+  pdl_launch();
   B200_ROW_PROLOGUE_NV(NVC)
+  pdl_wait(Yc, Yf, Ytc, Ytf, H);
   const bool interior = v > 0 && v < nv;
   const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v), offf = (size_t)e * 16 * nf + (n0 * nf + v);  // (row j, level v)
   const FT* gY = Yc + offc;
@@ -328,7 +330,9 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* hg = reinterpret_cast<FT*>(smem_raw);
   FT* s_w = hg + HG_ELEM * 16;
   FT* s_a = s_w + SLAB;
+  pdl_launch();
   B200_ROW_PROLOGUE_NV(NVC)
+  pdl_wait(Yc, H, Ytc, Ytf);
   const int part = blockIdx.y;
   const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v);
   const FT* gH = H + offc;
