@@ -96,6 +96,15 @@ __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
 __device__ __forceinline__ float  abs_(float a)  { return fabsf(a); }
 __device__ __forceinline__ double abs_(double a) { return fabs(a); }
 
+// reciprocal of a NORMAL number: MUFU.RCP + one Newton step (≤ 1 ulp) for Float32 — the IEEE division expands to ≈12
+// instructions with a slow-path branch — plain division for Float64.  Used by the packed (k5_*) kernels.
+__device__ __forceinline__ float rcpn_(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+__device__ __forceinline__ double rcpn_(double x) { return 1.0 / x; }
+
 template <class FT> __device__ __forceinline__ FT pow7(FT x) {
   FT x2 = x * x, x4 = x2 * x2;
   return x4 * x2 * x;
@@ -107,12 +116,12 @@ template <class FT>
 struct Pt {
   FT T, p, h, Pi, thp /*θ_v-θ_vr*/, thv, phir, sdr, lnPi;
 };
-template <class FT>
+template <class FT, bool FASTRCP = false>
 __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K, FT Phi) {
   Pt<FT> o;
   // one reciprocal for ρ and Π, one log shared by Π = exp(κ ln(p/p0)) and ln Π (the first version used
   // powf + logf + 5 divisions per point; the XU pipe showed up at 12–16 % in ncu)
-  FT etot = rhoe * rcp_(rho);
+  FT etot = rhoe * (FASTRCP ? rcpn_(rho) : rcp_(rho));
   FT eint = etot - K - Phi;
   // e_int = cv_d (T − T_0) − R_d T_0  (docs/src/thermodynamics.md:103-111)
   o.T = fmax_(P.T_min_sgs, P.T_0 + (eint + P.RT0) * P.icv);
@@ -121,7 +130,7 @@ __device__ __forceinline__ Pt<FT> thermo(const Par<FT>& P, FT rho, FT rhoe, FT K
   FT lnPi = P.kappa * log_(o.p * P.ip0);
   o.Pi = exp_(lnPi);
   o.lnPi = lnPi;
-  FT rPi = rcp_(o.Pi);
+  FT rPi = FASTRCP ? rcpn_(o.Pi) : rcp_(o.Pi);
   FT Pi7 = pow7(o.Pi);
   FT Tr = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * Pi7;
   o.thv = o.T * rPi;

@@ -33,14 +33,6 @@ __device__ __forceinline__ double mn_(double a, double b) { return fmin(a, b); }
 __device__ __forceinline__ float mx_(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double mx_(double a, double b) { return fmax(a, b); }
 template <class FT> __device__ __forceinline__ P2<FT> max2(FT s, P2<FT> a) { return P2<FT>(mx_(s, a.lo()), mx_(s, a.hi())); }
-// reciprocal of a NORMAL number inside the parallel cyclic reduction: MUFU.RCP + one Newton step (≤ 1 ulp) for
-// Float32 (the IEEE division expands to ≈12 instructions with a slow-path branch), plain division for Float64
-__device__ __forceinline__ float rcpn_(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return fmaf(fmaf(-x, r, 1.0f), r, r);
-}
-__device__ __forceinline__ double rcpn_(double x) { return 1.0 / x; }
 template <class FT> __device__ __forceinline__ P2<FT> rcpn2(P2<FT> a) { return P2<FT>(rcpn_(a.lo()), rcpn_(a.hi())); }
 // van Leer limited slope (same value as vl_slope in kernels_implicit.cuh, written with min/max instructions)
 template <class FT>
@@ -179,7 +171,7 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     h[p] = V2(FT(0));
     if (cv) {
       const V2 K = Kh[p] + (u3[p] * (u3[p] * g33lo) + u3h[p] * (u3h[p] * g33hi)) * FT(0.25);
-      const Pt<FT> a = thermo(P, rho[p].lo(), re[p].lo(), K.lo(), phi), b = thermo(P, rho[p].hi(), re[p].hi(), K.hi(), phi);
+      const Pt<FT> a = thermo<FT, true>(P, rho[p].lo(), re[p].lo(), K.lo(), phi), b = thermo<FT, true>(P, rho[p].hi(), re[p].hi(), K.hi(), phi);
       h[p] = V2(a.h, b.h); Pi = V2(a.Pi, b.Pi); thv = V2(a.thv, b.thv); thp = V2(a.thp, b.thp); phr = V2(a.phir, b.phir);
       // ∂p/∂ρ at fixed ρe_tot (manual_sparse_jacobian.jl:816-818)
       dp = fma2(V2(a.T, b.T), V2(P.R_d - kap * P.cv_d), ((V2(P.T_0 * P.cp_d) - K) - phi) * kap);
@@ -217,7 +209,7 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       const V2 Am = s_A[om], Mm = s_M[om], u3m = s_u3[om];
       const V2 Pil = s_Pi[om], thvl = s_thv[om], thpl = s_thp[om], phrl = s_phr[om], dpl = s_dp[om];
       const V2 Pi = s_Pi[o], thv = s_thv[o], thp = s_thp[o], phr = s_phr[o], dp = s_dp[o];
-      const V2 irf = rcp2((rlo[p] + rho[p]) * FT(0.5));
+      const V2 irf = rcpn2((rlo[p] + rho[p]) * FT(0.5));
       const V2 dPi = Pi - Pil;
       const V2 buoy = ((((thvl + thv) * FT(0.5)) * P.cp_d) * dPi) * irf;
       const V2 hb = buoy * FT(0.5);
@@ -308,7 +300,7 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       hn[p] = V2(FT(0));
       if (cv) {
         const V2 K = Kh[p] + (nu[p] * (nu[p] * g33lo) + nu1[p] * (nu1[p] * g33hi)) * FT(0.25);
-        const V2 etot = nre[p] * rcp2(nr[p]);
+        const V2 etot = nre[p] * rcpn2(nr[p]);
         const V2 T = max2(P.T_min_sgs, fma2(((etot - K) - phi) + P.RT0, V2(P.icv), V2(P.T_0)));
         hn[p] = fma2(T, V2(P.R_d), etot);
       }

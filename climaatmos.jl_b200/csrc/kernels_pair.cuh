@@ -135,8 +135,8 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       V kv = fma2(u3h[p], u3h[p] * L.g33hi, u3[p] * (u3[p] * L.g33lo)) * FT(0.5);
       K[p] = (kh + kv) * FT(0.5);
       u3c[p] = (u3[p] + u3h[p]) * FT(0.5);
-      Pt<FT> ta = thermo(P, rho[p].lo(), re[p].lo(), K[p].lo(), L.phi);
-      Pt<FT> tb = thermo(P, rho[p].hi(), re[p].hi(), K[p].hi(), L.phi);
+      Pt<FT> ta = thermo<FT, true>(P, rho[p].lo(), re[p].lo(), K[p].lo(), L.phi);
+      Pt<FT> tb = thermo<FT, true>(P, rho[p].hi(), re[p].hi(), K[p].hi(), L.phi);
       hh[p] = V(ta.h, tb.h); Pi[p] = V(ta.Pi, tb.Pi); th[p] = V(ta.thp, tb.thp);
       sE[p] = (K[p] + L.phi) - V(ta.phir, tb.phir);
       sd[p] = fma2(V(ta.T, tb.T) - P.T_0, P.cp_d, V(L.phi));
@@ -311,7 +311,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     sgetp(s_X1, h1, j, v + 1); sgetp(s_X2, h2, j, v + 1);
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-      V irm = V(FT(0.5) * L.rmc * rcp_(rho[p].lo()), FT(0.5) * L.rmc * rcp_(rho[p].hi()));
+      V irm = V(FT(0.5) * L.rmc * rcpn_(rho[p].lo()), FT(0.5) * L.rmc * rcpn_(rho[p].hi()));
       t1[p] = t1[p] - (X1[p] + h1[p]) * irm;
       t2[p] = t2[p] - (X2[p] + h2[p]) * irm;
     }
