@@ -19,6 +19,7 @@
 #include "kernels_implicit.cuh"
 #include "kernels_reg.cuh"
 #include "pair.cuh"
+#include "thermo2.cuh"
 
 namespace b200 {
 
@@ -28,12 +29,6 @@ constexpr int IMP5_SLABS = 13;
 template <class FT> constexpr size_t smem_imp5() { return (size_t)IMP5_SLABS * PSLAB * sizeof(P2<FT>); }
 
 template <class FT> __device__ __forceinline__ P2<FT> rcp2(P2<FT> a) { return P2<FT>(rcp_(a.lo()), rcp_(a.hi())); }
-__device__ __forceinline__ float mn_(float a, float b) { return fminf(a, b); }
-__device__ __forceinline__ double mn_(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ float mx_(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double mx_(double a, double b) { return fmax(a, b); }
-template <class FT> __device__ __forceinline__ P2<FT> max2(FT s, P2<FT> a) { return P2<FT>(mx_(s, a.lo()), mx_(s, a.hi())); }
-template <class FT> __device__ __forceinline__ P2<FT> rcpn2(P2<FT> a) { return P2<FT>(rcpn_(a.lo()), rcpn_(a.hi())); }
 // van Leer limited slope (same value as vl_slope in kernels_implicit.cuh, written with min/max instructions)
 template <class FT>
 __device__ __forceinline__ FT vl_slope5(FT am, FT a0, FT ap) {
@@ -171,10 +166,10 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     h[p] = V2(FT(0));
     if (cv) {
       const V2 K = Kh[p] + (u3[p] * (u3[p] * g33lo) + u3h[p] * (u3h[p] * g33hi)) * FT(0.25);
-      const Pt<FT> a = thermo<FT, true>(P, rho[p].lo(), re[p].lo(), K.lo(), phi), b = thermo<FT, true>(P, rho[p].hi(), re[p].hi(), K.hi(), phi);
-      h[p] = V2(a.h, b.h); Pi = V2(a.Pi, b.Pi); thv = V2(a.thv, b.thv); thp = V2(a.thp, b.thp); phr = V2(a.phir, b.phir);
+      const Pt2<FT> t = thermo2(P, rho[p], re[p], K, phi);
+      h[p] = t.h; Pi = t.Pi; thv = t.thv; thp = t.thp; phr = t.phir;
       // ∂p/∂ρ at fixed ρe_tot (manual_sparse_jacobian.jl:816-818)
-      dp = fma2(V2(a.T, b.T), V2(P.R_d - kap * P.cv_d), ((V2(P.T_0 * P.cp_d) - K) - phi) * kap);
+      dp = fma2(t.T, V2(P.R_d - kap * P.cv_d), ((V2(P.T_0 * P.cp_d) - K) - phi) * kap);
     }
     A[p] = M[p] = V2(FT(0));
     if (interior) {  // M = ᶠinterp(ρJ)u³/J2,  A = dtγ ᶠinterp(ρJ) g³³/J2

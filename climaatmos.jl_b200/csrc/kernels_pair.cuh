@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "kernels_row.cuh"
 #include "pair.cuh"
+#include "thermo2.cuh"
 
 namespace b200 {
 
@@ -135,23 +136,22 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       V kv = fma2(u3h[p], u3h[p] * L.g33hi, u3[p] * (u3[p] * L.g33lo)) * FT(0.5);
       K[p] = (kh + kv) * FT(0.5);
       u3c[p] = (u3[p] + u3h[p]) * FT(0.5);
-      Pt<FT> ta = thermo<FT, true>(P, rho[p].lo(), re[p].lo(), K[p].lo(), L.phi);
-      Pt<FT> tb = thermo<FT, true>(P, rho[p].hi(), re[p].hi(), K[p].hi(), L.phi);
-      hh[p] = V(ta.h, tb.h); Pi[p] = V(ta.Pi, tb.Pi); th[p] = V(ta.thp, tb.thp);
-      sE[p] = (K[p] + L.phi) - V(ta.phir, tb.phir);
-      sd[p] = fma2(V(ta.T, tb.T) - P.T_0, P.cp_d, V(L.phi));
-      ss[p] = sd[p] - V(ta.sdr, tb.sdr);
+      const Pt2<FT> t = thermo2(P, rho[p], re[p], K[p], L.phi);
+      hh[p] = t.h; Pi[p] = t.Pi; th[p] = t.thp;
+      sE[p] = (K[p] + L.phi) - t.phir;
+      sd[p] = fma2(t.T - P.T_0, P.cp_d, V(L.phi));
+      ss[p] = sd[p] - t.sdr;
       hs_e[p] = V(FT(0)); hs_d[p] = V(FT(0));
       if (P.hs) {  // Held–Suarez forcing (held_suarez.jl:111-296), scalar per node
         FT he[2], hd[2];
-        const Pt<FT>* tt[2] = {&ta, &tb};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const FT s2 = hg[HG_SIN2 * 16 + n0 + 2 * p + q], cc2 = hg[HG_COS2 * 16 + n0 + 2 * p + q];
-          const FT r = q ? rho[p].hi() : rho[p].lo();
-          FT hf = fmax_(FT(0), (tt[q]->p * P.hs_iMSLP - P.hs_sigb) * P.hs_isig);
-          FT Teq = fmax_(P.hs_Tmin, (P.hs_Teq - P.hs_dTy * s2 - P.hs_dthz * (tt[q]->lnPi * P.hs_ikap) * cc2) * tt[q]->Pi);
-          FT dRT = (P.hs_ka + (P.hs_ks - P.hs_ka) * hf * cc2 * cc2) * r * (tt[q]->p / (r * P.R_d) - Teq);
+          const FT r = q ? rho[p].hi() : rho[p].lo(), tp = q ? t.p.hi() : t.p.lo(), tl = q ? t.lnPi.hi() : t.lnPi.lo(),
+                   tP = q ? t.Pi.hi() : t.Pi.lo();
+          FT hf = fmax_(FT(0), (tp * P.hs_iMSLP - P.hs_sigb) * P.hs_isig);
+          FT Teq = fmax_(P.hs_Tmin, (P.hs_Teq - P.hs_dTy * s2 - P.hs_dthz * (tl * P.hs_ikap) * cc2) * tP);
+          FT dRT = (P.hs_ka + (P.hs_ks - P.hs_ka) * hf * cc2 * cc2) * r * (tp / (r * P.R_d) - Teq);
           he[q] = -dRT * P.cv_d; hd[q] = P.hs_kf * hf;
         }
         hs_e[p] = V(he[0], he[1]); hs_d[p] = V(hd[0], hd[1]);

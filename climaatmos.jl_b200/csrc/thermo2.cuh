@@ -1,0 +1,45 @@
+// thermo2.cuh — packed (two-lane) dry thermodynamics + hydrostatic reference state for the k5_* kernels.
+// Same formulas and operation order as `thermo` in common.cuh (precomputed_quantities.jl:733-815 dry branch;
+// refstate_thermodynamics.jl:22-168), evaluated on f32x2 pairs: FFMA2/FMUL2 algebra, packed log/exp (pair.cuh), MUFU-based
+// reciprocals.  Float64 instantiates the same code on the two-member struct with log/exp/division from libm.
+#pragma once
+#include "common.cuh"
+#include "pair.cuh"
+
+namespace b200 {
+
+template <class FT> __device__ __forceinline__ P2<FT> rcpn2(P2<FT> a) { return P2<FT>(rcpn_(a.lo()), rcpn_(a.hi())); }
+__device__ __forceinline__ float mx_(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double mx_(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float mn_(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double mn_(double a, double b) { return fmin(a, b); }
+template <class FT> __device__ __forceinline__ P2<FT> max2(FT s, P2<FT> a) { return P2<FT>(mx_(s, a.lo()), mx_(s, a.hi())); }
+
+template <class FT>
+struct Pt2 {
+  P2<FT> T, p, h, Pi, thp /*θ_v-θ_vr*/, thv, phir, sdr, lnPi;
+};
+template <class FT>
+__device__ __forceinline__ Pt2<FT> thermo2(const Par<FT>& P, P2<FT> rho, P2<FT> rhoe, P2<FT> K, FT Phi) {
+  using V = P2<FT>;
+  Pt2<FT> o;
+  const V etot = rhoe * rcpn2(rho);
+  const V eint = (etot - K) - Phi;
+  // e_int = cv_d (T − T_0) − R_d T_0  (docs/src/thermodynamics.md:103-111)
+  o.T = max2(P.T_min_sgs, fma2(eint + P.RT0, V(P.icv), V(P.T_0)));
+  o.h = fma2(o.T, V(P.R_d), etot);
+  o.p = (rho * P.R_d) * o.T;
+  o.lnPi = logp(o.p * P.ip0) * P.kappa;
+  o.Pi = expp(o.lnPi);
+  const V rPi = rcpn2(o.Pi);
+  const V x2 = o.Pi * o.Pi, x4 = x2 * x2;
+  const V Pi7 = (x4 * x2) * o.Pi;
+  const V Tr = fma2(Pi7, V(P.Ts_ref - P.Tmin_ref), V(P.Tmin_ref));
+  o.thv = o.T * rPi;
+  o.thp = (o.T - Tr) * rPi;
+  o.phir = fma2(o.lnPi, V(P.Tmin_ref), (Pi7 - FT(1)) * P.dTs7) * (-P.cp_d);
+  o.sdr = fma2(Tr - P.T_0, V(P.cp_d), o.phir);
+  return o;
+}
+
+}  // namespace b200
