@@ -85,6 +85,7 @@ struct b200_ctx {
   int nnodes = 0;
   std::vector<int32_t> h_off, h_mem;
   void* d_dssrec = nullptr;
+  int32_t* d_node_off = nullptr;  // records [d_node_off[e], d_node_off[e+1]) are owned by local element e
   void* d_jac = nullptr;
   // native stepper storage (allocated lazily)
   void *Uc[2] = {nullptr, nullptr}, *Uf[2] = {nullptr, nullptr};
@@ -329,6 +330,31 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
       R.a[q][0] = o[HG_A00 * 16]; R.a[q][1] = o[HG_A10 * 16]; R.a[q][2] = o[HG_A01 * 16]; R.a[q][3] = o[HG_A11 * 16];
     }
   }
+  // Device order of the records: by owner element (the lowest local member), then by node address, so that the unique nodes of one
+  // element are processed together (k_axpy_dss runs one CTA per owner element; k_dss2 gets the same L2 locality).  The host CSR
+  // (h_off/h_mem, the bit-exact index-map contract) keeps ClimaCore's vertex-then-face enumeration.
+  {
+    const int nh = c->dims.nh;
+    std::vector<int> key(c->nnodes), perm(c->nnodes);
+    for (int nd = 0; nd < c->nnodes; ++nd) {
+      int k = INT_MAX;
+      for (int q = 0; q < rec[nd].cnt; ++q)
+        if ((rec[nd].mem[q] >> 4) < nh) k = std::min(k, rec[nd].mem[q]);
+      key[nd] = k; perm[nd] = nd;
+    }
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<DssNode<FT>> sorted(rec.size());
+    std::vector<int32_t> noff((size_t)nh + 1, 0);
+    for (int k = 0; k < c->nnodes; ++k) {
+      sorted[k] = rec[perm[k]];
+      const int owner = key[perm[k]] == INT_MAX ? nh - 1 : (key[perm[k]] >> 4);
+      noff[owner + 1]++;
+    }
+    for (int e = 0; e < nh; ++e) noff[e + 1] += noff[e];
+    if (c->nnodes > 0) rec.swap(sorted);
+    CK(cudaMalloc(&c->d_node_off, noff.size() * sizeof(int32_t)));
+    CK(cudaMemcpy(c->d_node_off, noff.data(), noff.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc(&c->d_dssrec, rec.size() * sizeof(DssNode<FT>)));
   CK(cudaMemcpy(c->d_dssrec, rec.data(), rec.size() * sizeof(DssNode<FT>), cudaMemcpyHostToDevice));
   return 0;
@@ -439,7 +465,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
 extern "C" int b200_destroy(b200_ctx* c) {
   if (!c) return 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec);
+  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
   fr(c->p2p_buf); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
@@ -883,7 +909,7 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
   dim3 blk(64, 4), grd(nbn + nh);
   const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
   switch (m) {
-#define AXD(N_) case N_: launchx(c->pdl & 8, k_axpy_dss<FT, N_>, grd, blk, 0, s, A, rec, c->nnodes, nbn); break;
+#define AXD(N_) case N_: launchx(c->pdl & 8, k_axpy_dss<FT, N_>, grd, blk, 0, s, A, rec, c->nnodes, nbn, nh); break;
     AXD(1) AXD(2) AXD(3) AXD(4) AXD(5) AXD(6) AXD(7) AXD(8)
 #undef AXD
     default: return 1;
