@@ -104,7 +104,8 @@ struct b200_ctx {
   void* p2p_buf = nullptr;      // [2 parities][p2p_cap bytes] ghost slabs written by the neighbours, then int flags[nranks]
   size_t p2p_cap = 0;
   bool p2p_ready = false;
-  int p2p_counter = 0;
+  int* d_p2p_seq = nullptr;     // device-side exchange number (kernels_dss.cuh: k_p2p_signal)
+  int n_int_nodes = 0;          // records [0, n_int_nodes) have no ghost member (sorted first)
   std::vector<void*> p2p_peer;  // mapped neighbour buffers
   void** d_p2p_dst = nullptr;   // device array [n_neighbors] of destination base pointers (rewritten per call)
   int** d_p2p_flags = nullptr;  // device array [n_neighbors]: address of my flag in neighbour q
@@ -336,13 +337,19 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
   {
     const int nh = c->dims.nh;
     std::vector<int> key(c->nnodes), perm(c->nnodes);
+    std::vector<char> ghosty(c->nnodes, 0);
+    c->n_int_nodes = 0;
     for (int nd = 0; nd < c->nnodes; ++nd) {
       int k = INT_MAX;
-      for (int q = 0; q < rec[nd].cnt; ++q)
+      for (int q = 0; q < rec[nd].cnt; ++q) {
         if ((rec[nd].mem[q] >> 4) < nh) k = std::min(k, rec[nd].mem[q]);
+        else ghosty[nd] = 1;
+      }
       key[nd] = k; perm[nd] = nd;
+      c->n_int_nodes += !ghosty[nd];
     }
-    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+    // nodes without a ghost member first (they can be summed while the halo is in flight), each group by owner element
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return ghosty[a] != ghosty[b] ? ghosty[a] < ghosty[b] : key[a] < key[b]; });
     std::vector<DssNode<FT>> sorted(rec.size());
     std::vector<int32_t> noff((size_t)nh + 1, 0);
     for (int k = 0; k < c->nnodes; ++k) {
@@ -467,7 +474,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
-  fr(c->p2p_buf); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
+  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
   fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
@@ -619,6 +626,8 @@ extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t*
     dst[nn + q] = (char*)c->p2p_peer[q] + their_cap;
   }
   CK(cudaMemcpy(c->d_p2p_dst, dst.data(), 2 * nn * sizeof(void*), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_p2p_seq, sizeof(int)));
+  CK(cudaMemset(c->d_p2p_seq, 0, sizeof(int)));
   c->p2p_ready = true;
   return 0;
 }
@@ -640,7 +649,7 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   void* ghost_base = nullptr;
   if (p2p) {
     // peer-memory halo: pack straight into the neighbours' ghost buffers, raise flags, wait for theirs
-    const int nn = (int)c->nbr.size(), k = ++c->p2p_counter, par = k & 1;
+    const int nn = (int)c->nbr.size();
     P2PArgs PA;
     PA.nfields = nfields;
     long long goff = 0;
@@ -650,14 +659,13 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
       goff += slab;
     }
     if (c->n_send > 0) {
-      k_pack_p2p<FT><<<c->n_send, 256, 0, s>>>(PA, c->d_send_elems, c->d_slot_nbr, c->d_slot_dst, (FT* const*)(c->d_p2p_dst + par * nn), c->d_nbr_nhg);
+      k_pack_p2p<FT><<<c->n_send, 256, 0, s>>>(PA, c->d_send_elems, c->d_slot_nbr, c->d_slot_dst, (FT* const*)c->d_p2p_dst, c->d_nbr_nhg,
+                                              c->d_p2p_seq, nn);
       LAUNCH_CHECK(c);
     }
-    k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, k);
+    k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
     LAUNCH_CHECK(c);
-    k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, nn, k);
-    LAUNCH_CHECK(c);
-    ghost_base = (char*)c->p2p_buf + par * c->p2p_cap;
+    ghost_base = c->p2p_buf;  // parity block 0; the kernels add (*seq & 1)·p2p_cap
   } else if (halo) {
     size_t need_s = tot_slab * c->n_send * sizeof(FT), need_g = tot_slab * c->dims.nh_ghost * sizeof(FT);
     if (need_s + need_g > c->halo_cap) {
@@ -718,23 +726,52 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
   int pairs = 0;
   for (int k = 0; k < A.n; ++k) pairs |= (A.it[k].p1 != nullptr) << k;
+  A.seq = p2p ? c->d_p2p_seq : nullptr; A.gpar = (long long)c->p2p_cap;
   const bool small = (size_t)(nh + c->dims.nh_ghost) * 64 * (size_t)(nv + 1) < (size_t)INT32_MAX;  // 32-bit offsets
-#define DSS2(NI, PM)                                                                               \
-  (halo ? (void)(launchx(c->pdl & 4, k_dss2<FT, NI, PM, true>, grd, blk, 0, s, A, rec, c->nnodes, nh))               \
-        : (void)(launchx(c->pdl & 4, k_dss2<FT, NI, PM, false>, grd, blk, 0, s, A, rec, c->nnodes, nh)))
-  if (c->legacy || !small) { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
-  else if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);   // state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃
-  else if (A.n == 3 && pairs == 0x1) DSS2(3, 0x1);   // ∇² fields: (∇²u₁,∇²u₂), ∇²u₃, ∇²s_d
-  else if (A.n == 5 && pairs == 0x2) DSS2(5, 0x2);   // state with one passive tracer
-  else if (A.n == 4 && pairs == 0x1) DSS2(4, 0x1);   // ∇² fields with one passive tracer
-  else if (A.n == 6 && pairs == 0x2) DSS2(6, 0x2);   // two tracers
-  else if (A.n == 5 && pairs == 0x1) DSS2(5, 0x1);
-  else if (A.n == 1 && pairs == 0x0) DSS2(1, 0x0);
-  else if (A.n == 1 && pairs == 0x1) DSS2(1, 0x1);
-  else if (A.n == 2 && pairs == 0x0) DSS2(2, 0x0);
-  else { grd.y = A.n; k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh); }
+  // With the peer-memory halo the nodes without ghost members are summed while the neighbours' slabs are still in flight; the
+  // flag wait and the (few) ghost-touching nodes follow.  k_dss2<…, HALO> takes the record range [node0, node1).
+  int node0 = 0, node1 = c->nnodes;
+  bool with_halo = halo;
+  auto wait_p2p = [&]() -> int {
+    k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, (int)c->nbr.size(), c->d_p2p_seq);
+    LAUNCH_CHECK(c);
+    return 0;
+  };
+#define DSS2(NI, PM)                                                                                                       \
+  (with_halo ? (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, true>, grd, blk, 0, s, A, rec, node0, node1, nh)             \
+             : (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, false>, grd, blk, 0, s, A, rec, node0, node1, nh))
+#define DSS2_ANY()                                                                                                         \
+  do {                                                                                                                     \
+    if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);        /* state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃ */                                 \
+    else if (A.n == 3 && pairs == 0x1) DSS2(3, 0x1);   /* ∇² fields: (∇²u₁,∇²u₂), ∇²u₃, ∇²s_d */                             \
+    else if (A.n == 5 && pairs == 0x2) DSS2(5, 0x2);   /* state with one passive tracer */                                 \
+    else if (A.n == 4 && pairs == 0x1) DSS2(4, 0x1);   /* ∇² fields with one passive tracer */                             \
+    else if (A.n == 6 && pairs == 0x2) DSS2(6, 0x2);   /* two tracers */                                                   \
+    else if (A.n == 5 && pairs == 0x1) DSS2(5, 0x1);                                                                       \
+    else if (A.n == 1 && pairs == 0x0) DSS2(1, 0x0);                                                                       \
+    else if (A.n == 1 && pairs == 0x1) DSS2(1, 0x1);                                                                       \
+    else DSS2(2, 0x0);                                                                                                     \
+    LAUNCH_CHECK(c);                                                                                                       \
+  } while (0)
+  const bool special = (A.n == 4 && pairs == 0x2) || (A.n == 3 && pairs == 0x1) || (A.n == 5 && pairs == 0x2) || (A.n == 4 && pairs == 0x1) ||
+                       (A.n == 6 && pairs == 0x2) || (A.n == 5 && pairs == 0x1) || (A.n == 1 && pairs == 0x0) || (A.n == 1 && pairs == 0x1) ||
+                       (A.n == 2 && pairs == 0x0);
+  if (c->legacy || !small || !special) {
+    if (p2p && wait_p2p()) return -1;
+    grd.y = A.n;
+    k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh);
+    LAUNCH_CHECK(c);
+  } else if (p2p) {
+    node0 = 0; node1 = c->n_int_nodes; with_halo = false;
+    if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
+    if (wait_p2p()) return -1;
+    node0 = c->n_int_nodes; node1 = c->nnodes; with_halo = true;
+    if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
+  } else {
+    DSS2_ANY();
+  }
+#undef DSS2_ANY
 #undef DSS2
-  LAUNCH_CHECK(c);
   return 0;
 }
 extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, const int32_t* is_face, const int32_t* kind,
@@ -889,13 +926,18 @@ static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT 
   return 0;
 }
 
-// U = dss!(u + Σ c_j T_j) in one kernel (k_axpy_dss); returns 1 when this context/call cannot use it (caller falls back)
+// U = dss!(u + Σ c_j T_j) in one pass (k_axpy_dss); returns 1 when this context/call cannot use it (caller falls back).
+// Multi-rank contexts with the peer-memory halo: the send elements are assembled straight into the neighbours' ghost blocks
+// (k_pack_axpy_p2p), the nodes without ghost members and the interior nodes are processed while those slabs are in flight, then the
+// flag wait and the ghost-touching nodes.
 template <class FT>
 static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int n, const void* const* Tc,
                          const void* const* Tf, const double* coef, cudaStream_t s) {
   const int nh = c->dims.nh, nv = c->dims.nv;
-  const bool small = (size_t)nh * c->ncf() * 16 * (size_t)(nv + 1) < (size_t)INT32_MAX;
-  if (!c->fuse_axdss || c->legacy || !c->nbr.empty() || c->dims.nh_ghost > 0 || !small) return 1;
+  const bool small = (size_t)(nh + c->dims.nh_ghost) * c->ncf() * 16 * (size_t)(nv + 1) < (size_t)INT32_MAX;
+  const bool multi = c->comm != nullptr || !c->nbr.empty() || c->dims.nh_ghost > 0;
+  const bool p2p = multi && c->p2p_ready && !getenv("B200_HALO_NCCL");
+  if (!c->fuse_axdss || c->legacy || (multi && !p2p) || !small) return 1;
   AxDssArgs<FT> A;
   int m = 0;
   for (int k = 0; k < n; ++k) {
@@ -905,16 +947,37 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
   }
   if (m < 1) return 1;
   A.out_c = (FT*)Uc; A.out_f = (FT*)Uf; A.base_c = (const FT*)uc; A.base_f = (const FT*)uf; A.ncf = c->ncf(); A.nv = nv;
-  const int nbn = (c->nnodes + 3) / 4;
-  dim3 blk(64, 4), grd(nbn + nh);
+  A.ghost = (const FT*)c->p2p_buf; A.gpar = (long long)c->p2p_cap; A.seq = c->d_p2p_seq; A.nh = nh; A.nh_ghost = c->dims.nh_ghost;
   const DssNode<FT>* rec = (const DssNode<FT>*)c->d_dssrec;
-  switch (m) {
-#define AXD(N_) case N_: launchx(c->pdl & 8, k_axpy_dss<FT, N_>, grd, blk, 0, s, A, rec, c->nnodes, nbn, nh); break;
-    AXD(1) AXD(2) AXD(3) AXD(4) AXD(5) AXD(6) AXD(7) AXD(8)
-#undef AXD
-    default: return 1;
+  dim3 blk(64, 4);
+  const int nn = (int)c->nbr.size();
+  const int n_first = p2p ? c->n_int_nodes : c->nnodes;  // records of the first launch
+  const int nbn1 = (n_first + 3) / 4, nbn2 = (c->nnodes - n_first + 3) / 4;
+#define AXD_CASES(STMT) \
+  switch (m) { case 1: { constexpr int N_ = 1; STMT; } break; case 2: { constexpr int N_ = 2; STMT; } break; \
+               case 3: { constexpr int N_ = 3; STMT; } break; case 4: { constexpr int N_ = 4; STMT; } break; \
+               case 5: { constexpr int N_ = 5; STMT; } break; case 6: { constexpr int N_ = 6; STMT; } break; \
+               case 7: { constexpr int N_ = 7; STMT; } break; case 8: { constexpr int N_ = 8; STMT; } break; default: return 1; }
+  if (p2p) {
+    if (c->n_send > 0) {
+      AXD_CASES((launchx(c->pdl & 8, k_pack_axpy_p2p<FT, N_>, dim3(c->n_send), dim3(256), 0, s, A, (const int*)c->d_send_elems, (const int*)c->d_slot_nbr,
+                         (const int*)c->d_slot_dst, (FT* const*)c->d_p2p_dst, (const int*)c->d_nbr_nhg, nn)));
+      LAUNCH_CHECK(c);
+    }
+    k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
+    LAUNCH_CHECK(c);
   }
+  AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, false>, dim3(nbn1 + nh), blk, 0, s, A, rec, 0, n_first, nbn1, nh)));
   LAUNCH_CHECK(c);
+  if (p2p) {
+    k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, nn, c->d_p2p_seq);
+    LAUNCH_CHECK(c);
+    if (nbn2 > 0) {
+      AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, true>, dim3(nbn2), blk, 0, s, A, rec, n_first, c->nnodes, nbn2, 0)));
+      LAUNCH_CHECK(c);
+    }
+  }
+#undef AXD_CASES
   return 0;
 }
 
@@ -1069,8 +1132,9 @@ extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t
   cudaStream_t s = (cudaStream_t)stream;
   auto run = [&](cudaStream_t q) { return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, q) : impl_step<double>(c, Yc, Yf, fused, q); };
   // One CUDA graph per state buffer: ≈35 kernel launches, the side-stream fork/join and the memsets replay as one launch.
-  // Multi-rank contexts stay eager (the peer-memory halo passes a fresh flag value to every DSS call).
-  const bool graphable = c->use_graph && fused && c->nbr.empty() && !c->legacy;
+  // Multi-rank contexts replay too when the halo runs over peer memory (its exchange number lives in device memory); the NCCL
+  // halo stays eager.
+  const bool graphable = c->use_graph && fused && !c->legacy && (c->nbr.empty() || (c->p2p_ready && !getenv("B200_HALO_NCCL")));
   if (!graphable) return run(s);
   if (c->eager_steps < 1) { c->eager_steps++; return run(s); }  // first step eager: performs the lazy allocations
   // the legacy default stream cannot be captured: order an internal stream after/before it with events instead

@@ -28,6 +28,9 @@ struct DssItem {
 struct DssArgs {
   DssItem it[DSS_MAX_ITEMS];
   int n;
+  // peer-memory halo: the ghost planes g0/g1 point into parity block 0; the block in use is (*seq & 1), gpar bytes further on
+  const int* seq;
+  long long gpar;
 };
 
 template <class FT>
@@ -57,8 +60,9 @@ __global__ void __launch_bounds__(256) k_dss(DssArgs A, const int* __restrict__ 
     if (v >= I.nlev) return;
     FT* p0 = reinterpret_cast<FT*>(I.p0);
     FT* p1 = reinterpret_cast<FT*>(I.p1);
-    const FT* g0 = reinterpret_cast<const FT*>(I.g0);
-    const FT* g1 = reinterpret_cast<const FT*>(I.g1);
+    const size_t gp = A.seq ? (size_t)(*A.seq & 1) * (size_t)A.gpar : 0;  // parity block of the peer-memory halo
+    const FT* g0 = reinterpret_cast<const FT*>(reinterpret_cast<const char*>(I.g0) + gp);
+    const FT* g1 = reinterpret_cast<const FT*>(reinterpret_cast<const char*>(I.g1) + gp);
     if (!p1) {
       FT s = FT(0);
 #pragma unroll
@@ -121,6 +125,7 @@ template <class FT, int NI, int PAIRS, int CNT, bool HALO>
 __device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R, int cnt, int v, int nh) {
   FT x0[NI][CNT], x1[NI][CNT];
   int off[NI][CNT];
+  const size_t gp = (HALO && A.seq) ? (size_t)(*A.seq & 1) * (size_t)A.gpar : 0;
 #pragma unroll
   for (int k = 0; k < NI; ++k) {
     const DssItem& I = A.it[k];
@@ -136,8 +141,8 @@ __device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R,
           if (PAIRS & (1 << k)) x1[k][q] = reinterpret_cast<const FT*>(I.p1)[o];
         } else {
           const int o = (el - nh) * I.gstride + nd * I.nlev + v;
-          x0[k][q] = reinterpret_cast<const FT*>(I.g0)[o];
-          if (PAIRS & (1 << k)) x1[k][q] = reinterpret_cast<const FT*>(I.g1)[o];
+          x0[k][q] = reinterpret_cast<const FT*>(reinterpret_cast<const char*>(I.g0) + gp)[o];
+          if (PAIRS & (1 << k)) x1[k][q] = reinterpret_cast<const FT*>(reinterpret_cast<const char*>(I.g1) + gp)[o];
         }
       }
     }
@@ -175,11 +180,11 @@ __device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R,
 }
 
 template <class FT, int NI, int PAIRS, bool HALO>
-__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int nnodes, int nh) {
+__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nh) {
   __shared__ DssNode<FT> sr[4];
   pdl_launch();
   const int v = threadIdx.x;
-  const int node = blockIdx.x * 4 + threadIdx.y;
+  const int node = node0 + blockIdx.x * 4 + threadIdx.y;  // records [node0, nnodes)
   constexpr int RW = sizeof(DssNode<FT>) / 4;
   if (node < nnodes && v < RW) reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v] = reinterpret_cast<const uint32_t*>(&rec[node])[v];
   if (RW > 64 && node < nnodes && v + 64 < RW)
@@ -209,30 +214,37 @@ struct P2PArgs {
   P2PField f[4];
   int nfields;
 };
-// one block per (send slot); dst[q] = base pointer (already offset to the right parity) of neighbour q's ghost buffer
+// The exchange number lives in DEVICE memory (*seq, incremented by k_p2p_signal), so none of these kernels takes a per-call value:
+// a captured CUDA graph of the step replays correctly.  Ghost blocks are double-buffered by the parity of the exchange number
+// (a block is rewritten two exchanges later, after the neighbour's next flag has proved it finished reading).
+// one block per (send slot); dst[par*nn + q] = neighbour q's ghost buffer of parity par
 template <class FT>
 __global__ void k_pack_p2p(P2PArgs A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
                            const int* __restrict__ slot_dst /* ghost slot in the neighbour */, FT* const* __restrict__ dst,
-                           const int* __restrict__ nbr_nh_ghost) {
+                           const int* __restrict__ nbr_nh_ghost, const int* seq, int nn) {
   const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
-  FT* base = dst[q];
+  FT* base = dst[((*seq + 1) & 1) * nn + q];
   for (int k = 0; k < A.nfields; ++k) {
     const FT* s = reinterpret_cast<const FT*>(A.f[k].src) + (size_t)e * A.f[k].slab;
     FT* d = base + (size_t)A.f[k].goff * nbr_nh_ghost[q] + (size_t)g * A.f[k].slab;
     for (int i = threadIdx.x; i < A.f[k].slab; i += blockDim.x) d[i] = s[i];
   }
 }
-// raise my flag in every neighbour's memory (after the pack kernel has completed)
-__global__ void k_p2p_signal(int* const* __restrict__ peer_flags, int my_slot_count, int value) {
+// raise my flag in every neighbour's memory (after the pack kernel has completed) and advance the exchange number
+__global__ void k_p2p_signal(int* const* __restrict__ peer_flags, int n, int* seq) {
   const int q = threadIdx.x;
-  if (q < my_slot_count) {
+  const int value = *seq + 1;
+  if (q < n) {
     __threadfence_system();
     *reinterpret_cast<volatile int*>(peer_flags[q]) = value;
   }
+  __syncwarp();
+  if (q == 0) *seq = value;
 }
-// wait until every neighbour has raised its flag to `value` in my memory
-__global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict__ nbr_rank, int n, int value) {
+// wait until every neighbour has raised its flag to the current exchange number in my memory
+__global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict__ nbr_rank, int n, const int* seq) {
   const int q = threadIdx.x;
+  const int value = *seq;
   if (q < n) {
     const volatile int* f = flags + nbr_rank[q];
     while (*f < value) { __nanosleep(50); }
@@ -291,6 +303,9 @@ struct AxDssArgs {
   const FT* Tc[AXPY_MAX]; const FT* Tf[AXPY_MAX];
   FT c[AXPY_MAX];
   int ncf, nv;
+  // multi-rank: members with element index >= nh are ghosts whose ASSEMBLED slabs the owner has written into the peer-memory
+  // ghost block (k_pack_axpy_p2p): [nh_ghost][ncf·16·nv] centre slabs, then [nh_ghost][16·(nv+1)] face slabs
+  const FT* ghost; long long gpar; const int* seq; int nh, nh_ghost;
 };
 template <class FT, int N>
 __device__ __forceinline__ FT axv(const FT* __restrict__ b, const FT* const* T, const FT* c, int o) {
@@ -302,32 +317,43 @@ __device__ __forceinline__ FT axv(const FT* __restrict__ b, const FT* const* T, 
   for (int k = 0; k < N; ++k) r += c[k] * t[k];
   return r;
 }
-template <class FT, int N, int CNT>
+template <class FT, int N, int CNT, bool HALO>
 __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode<FT>& R, int cnt, int v) {
   const int nv = A.nv, nf = nv + 1, ec = A.ncf * 16 * nv, ef = 16 * nf;
   int oc[CNT], of[CNT];
+  bool gh[CNT];
+  const FT *gc = nullptr, *gf = nullptr;
+  if (HALO) {
+    gc = reinterpret_cast<const FT*>(reinterpret_cast<const char*>(A.ghost) + (size_t)(*A.seq & 1) * (size_t)A.gpar);
+    gf = gc + (size_t)ec * A.nh_ghost;
+  }
 #pragma unroll
   for (int q = 0; q < CNT; ++q) {
     const int el = R.mem[q] >> 4, nd = R.mem[q] & 15;
-    oc[q] = el * ec + nd * nv + v; of[q] = el * ef + nd * nf + v;
+    gh[q] = HALO && el >= A.nh && (CNT == 2 || q < cnt);
+    const int le = gh[q] ? el - A.nh : el;
+    oc[q] = le * ec + nd * nv + v; of[q] = le * ef + nd * nf + v;
   }
+  // value of member q at centre-plane offset ko: assembled on the fly (local) or read from the ghost block (already assembled)
+  auto cval = [&](int q, int ko) -> FT {
+    if (!(CNT == 2 || q < cnt)) return FT(0);
+    if (gh[q]) return gc[oc[q] + ko];
+    return axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + ko);
+  };
   if (v < nv) {
     // ρ, then the Covariant12 pair (uₕ₁, uₕ₂) in the local physical basis, then ρe_tot and the tracers
     FT x[CNT], y[CNT];
 #pragma unroll
-    for (int q = 0; q < CNT; ++q) x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q]) : FT(0);
+    for (int q = 0; q < CNT; ++q) x[q] = cval(q, 0);
     {
       FT s = FT(0);
 #pragma unroll
       for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
 #pragma unroll
-      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) A.out_c[oc[q]] = s;
+      for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_c[oc[q]] = s;
     }
 #pragma unroll
-    for (int q = 0; q < CNT; ++q) {
-      x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + 16 * nv) : FT(0);
-      y[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + 32 * nv) : FT(0);
-    }
+    for (int q = 0; q < CNT; ++q) { x[q] = cval(q, 16 * nv); y[q] = cval(q, 32 * nv); }
     {
       FT su = FT(0), sv = FT(0);
 #pragma unroll
@@ -339,7 +365,7 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
         }
 #pragma unroll
       for (int q = 0; q < CNT; ++q)
-        if (CNT == 2 || q < cnt) {
+        if ((CNT == 2 || q < cnt) && !gh[q]) {
           A.out_c[oc[q] + 16 * nv] = R.a[q][0] * su + R.a[q][1] * sv;
           A.out_c[oc[q] + 32 * nv] = R.a[q][2] * su + R.a[q][3] * sv;
         }
@@ -347,12 +373,12 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
     for (int k = 3; k < A.ncf; ++k) {
       const int ko = k * 16 * nv;
 #pragma unroll
-      for (int q = 0; q < CNT; ++q) x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + ko) : FT(0);
+      for (int q = 0; q < CNT; ++q) x[q] = cval(q, ko);
       FT s = FT(0);
 #pragma unroll
       for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
 #pragma unroll
-      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) A.out_c[oc[q] + ko] = s;
+      for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_c[oc[q] + ko] = s;
     }
   }
   if (v < nf) {
@@ -360,12 +386,31 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
     if (v > 0 && v < nv) {
       FT x[CNT];
 #pragma unroll
-      for (int q = 0; q < CNT; ++q) x[q] = (CNT == 2 || q < cnt) ? axv<FT, N>(A.base_f, A.Tf, A.c, of[q]) : FT(0);
+      for (int q = 0; q < CNT; ++q)
+        x[q] = !(CNT == 2 || q < cnt) ? FT(0) : (gh[q] ? gf[of[q]] : axv<FT, N>(A.base_f, A.Tf, A.c, of[q]));
 #pragma unroll
       for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
     }
 #pragma unroll
-    for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) A.out_f[of[q]] = s;
+    for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_f[of[q]] = s;
+  }
+}
+// Multi-rank: assemble the state of the SEND elements and write it straight into the neighbours' ghost blocks (peer memory),
+// same arithmetic as k_axpy_n including the u₃ boundary filter — the receiving k_axpy_dss reads assembled values.
+template <class FT, int N>
+__global__ void k_pack_axpy_p2p(AxDssArgs<FT> A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
+                                const int* __restrict__ slot_dst, FT* const* __restrict__ dst, const int* __restrict__ nbr_nh_ghost, int nn) {
+  pdl_launch();
+  const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
+  pdl_wait();
+  const int nv = A.nv, nf = nv + 1, ec = A.ncf * 16 * nv, ef = 16 * nf;
+  FT* base = dst[((*A.seq + 1) & 1) * nn + q];
+  FT* dc = base + (size_t)g * ec;
+  FT* df = base + (size_t)ec * nbr_nh_ghost[q] + (size_t)g * ef;
+  for (int i = threadIdx.x; i < ec; i += blockDim.x) dc[i] = axv<FT, N>(A.base_c, A.Tc, A.c, e * ec + i);
+  for (int i = threadIdx.x; i < ef; i += blockDim.x) {
+    const int lev = i % nf;
+    df[i] = (lev == 0 || lev == nv) ? FT(0) : axv<FT, N>(A.base_f, A.Tf, A.c, e * ef + i);
   }
 }
 // nbn node blocks (four unique perimeter nodes × 64 levels; records sorted by owner element, capi.cu) and nh interior blocks (the
@@ -373,14 +418,15 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
 // as its perimeter columns and the partially used 32-byte sectors between adjacent node columns are still in L2 (the first version
 // ran all interior blocks after all node blocks: 26 % more DRAM reads than algorithmic).  A CTA per element that loops over its
 // owned nodes was slower (dependent record → member latencies in series: +130 µs per step).
-template <class FT, int N>
-__global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int nnodes, int nbn, int nh) {
+// Records [node0, nnodes) in nbn node blocks; nint interior blocks (0 = none) interleaved with them.
+template <class FT, int N, bool HALO>
+__global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nbn, int nint) {
   __shared__ DssNode<FT> sr[4];
   pdl_launch();
   const int v = threadIdx.x;
-  const long long tot = (long long)nbn + nh, b = blockIdx.x;
-  const int ib = (int)(b * nh / tot);                 // interior blocks before this one
-  if ((int)((b + 1) * nh / tot) != ib) {              // this block is interior block ib
+  const long long tot = (long long)nbn + nint, b = blockIdx.x;
+  const int ib = (int)(b * nint / tot);               // interior blocks before this one
+  if ((int)((b + 1) * nint / tot) != ib) {            // this block is interior block ib
     pdl_wait();
     const int e = ib, nv = A.nv, nf = nv + 1;
     const int nd = 5 + (threadIdx.y & 1) + 4 * (threadIdx.y >> 1);  // nodes (j, i) ∈ {1,2}²
@@ -394,7 +440,7 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
     }
     return;
   }
-  const int node = ((int)b - ib) * 4 + threadIdx.y;
+  const int node = node0 + ((int)b - ib) * 4 + threadIdx.y;
   constexpr int RW = sizeof(DssNode<FT>) / 4;
   if (node < nnodes && v < RW) reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v] = reinterpret_cast<const uint32_t*>(&rec[node])[v];
   if (RW > 64 && node < nnodes && v + 64 < RW)
@@ -404,8 +450,8 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
   pdl_wait();
   const DssNode<FT>& R = sr[threadIdx.y];
   const int cnt = R.cnt;
-  if (cnt == 2) axdss_body<FT, N, 2>(A, R, cnt, v);
-  else axdss_body<FT, N, 4>(A, R, cnt, v);
+  if (cnt == 2) axdss_body<FT, N, 2, HALO>(A, R, cnt, v);
+  else axdss_body<FT, N, 4, HALO>(A, R, cnt, v);
 }
 
 // out = (a - b) * s   (T_imp[i] = (U - temp)/dtγ)
