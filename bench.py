@@ -283,6 +283,7 @@ def main():
                 "h_elem": w["h_elem"], "z_elem": nv, "dt_s": w["dt"], "elements_total": sim.grid.nelems, "elements_per_gpu": nh_local,
                 "columns_total": ncols_total, "parallelism": f"sfc-domain-decomposition x{nranks}",
                 "halo": ("nvlink-peer-memory" if getattr(sim, "peer_halo", False) else "nccl-send-recv") if nranks > 1 else "none", "implicit_stage": "fused" if fused else "hooks",
+                "launch": "CUDA graph replay of the step + programmatic dependent launch" if fused else "eager hook-by-hook",
                 "l2_policy": "working set (≈1.2 GB of stage vectors per step) larger than the 126 MB L2; no explicit flush",
                 "weak_scaling_note": "dt ∝ 1/h_elem; efficiency = (ms_1/ms_N)·(elements_N/(N·elements_1))",
             },
@@ -291,11 +292,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": sy(ms_e2e), "unit": "SYPD", "ms_per_step": ms_e2e, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "pipeline": "3 streams (copy-in / step / copy-out), double-buffered", "finite": e2e_ok},
-            "roofline": {"bound": "hbm", "kernel": "k5_exp_a<float> (T_exp_T_lim! pre-DSS kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at he30/ze63 (114.1 + 146.3 MB), from the
-                         # ncu --set full capture summarised in profiles/r1_ncu_full_packed_kernels.txt; scaled by elements
-                         "traffic": 260.4e6 * nh_local / 5400.0, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes,
+            "roofline": {"bound": "hbm", "kernel": "k5_exp_a<float, 63> (T_exp_T_lim! pre-DSS kernel, the largest share of the step)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at he30/ze63 (114.1 + 141.1 MB), from the
+                         # ncu --set full capture summarised in profiles/r1_ncu_full_session2_kernels.txt; scaled by elements
+                         "traffic": 255.3e6 * nh_local / 5400.0, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s"},
             "roofline_step": {"model_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms * 1e-3) / 1e9 / nranks,
                               "frac": step_bytes / (ms * 1e-3) / 1e9 / nranks / peak, "model": "54.5 S + 14 H (SURVEY.md §8d)"},
