@@ -29,10 +29,22 @@ WEAK_H = {1: 30, 2: 42, 4: 60, 8: 85}
 ZD = 40000.0  # zd_rayleigh = zd_viscous as in toml/longrun_held_suarez.toml
 
 
-def workload(n_gpus):
+def workload(n_gpus, config="weak"):
+    """BASELINE.json configs.  "weak" (default) is the north-star series; the others are extra measurements (--config):
+    "strong": dry BW he60/ze63 on every N (configs[4]); "he16": dry BW he16/ze63 (configs[1]); "tracer": he30/ze63 with one passive
+    tracer (configs[2], dycore + tracer advection only); "hs": Held–Suarez he6/ze10 (configs[0])."""
+    if config == "strong":
+        return dict(h_elem=60, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=45.0, scaling="strong", name="dry_baroclinic_wave")
+    if config == "he16":
+        return dict(h_elem=16, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=120.0, scaling="weak", name="dry_baroclinic_wave")
+    if config == "hs":
+        return dict(h_elem=6, z_elem=10, z_max=55000.0, dz_bottom=500.0, dt=400.0, scaling="weak", name="held_suarez", sponge=False, rad="held_suarez")
     h = WEAK_H.get(n_gpus, int(round(30 * np.sqrt(n_gpus))))
     dt = float(round(90.0 * 30 / h))
-    return dict(h_elem=h, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=dt)
+    w = dict(h_elem=h, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=dt, scaling="weak", name="dry_baroclinic_wave")
+    if config == "tracer":
+        w.update(tracers=1, name="dry_baroclinic_wave + 1 passive tracer")
+    return w
 
 
 def model_bytes_per_step(ncols, nv, s=4, k=0):
@@ -144,6 +156,7 @@ def main():
     ap.add_argument("--ref-h-elem", type=int, default=16, help="horizontal resolution of the bounded CPU sample")
     ap.add_argument("--cpu-threads", type=int, default=16, help="upper bound on host threads used by the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="weak", choices=["weak", "strong", "he16", "tracer", "hs"], help="BASELINE.json config (default: the north-star weak series)")
     ap.add_argument("--unfused", action="store_true", help="hook-by-hook implicit stage instead of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -159,10 +172,14 @@ def main():
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={nranks}; using WORLD_SIZE", file=sys.stderr)
     W = max(args.warmup, 3)
     K = args.steps
-    w = workload(nranks)
+    w = workload(nranks, args.config)
     P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD)
+    sponge = w.get("sponge", True)
+    ntr = w.get("tracers", 0)
+    tracers = [lambda lat, lon, z: 0.5 * (1 + np.sin(np.radians(lat)) * np.cos(np.radians(lon))) * np.exp(-z / 8000.0)] * ntr or None
     sim = dycore.AtmosSimulation(FT=np.float32, h_elem=w["h_elem"], z_elem=w["z_elem"], z_max=w["z_max"], dz_bottom=w["dz_bottom"],
-                                 dt=w["dt"], rayleigh_sponge=True, viscous_sponge=True, params=P, comms=comms if nranks > 1 else None)
+                                 dt=w["dt"], rayleigh_sponge=sponge, viscous_sponge=sponge, params=P, rad=w.get("rad"), tracers=tracers,
+                                 comms=comms if nranks > 1 else None)
     fused = not args.unfused
     nh_local = sim.Y.c.shape[0]
     ncols_total = sim.grid.ncols
@@ -263,7 +280,7 @@ def main():
     nv = w["z_elem"]
     c_b = nh_local * 16 * nv * 4
     f_b = nh_local * 16 * (nv + 1) * 4
-    k_bytes = (4 * c_b + f_b) * 2 + 4 * c_b  # read Y, write Yₜ, write H = (∇²u, ∇²s_d)   
+    k_bytes = (4 * c_b + f_b) * 2 + 4 * c_b  # read Y (dry components), write Yₜ, write H = (∇²u, ∇²s_d)   
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -274,12 +291,12 @@ def main():
 
     if rank == 0:
         sy = lambda m: (w["dt"] / (365 * 86400.0)) / (m * 1e-3 / 86400.0)
-        step_bytes = model_bytes_per_step(ncols_total, nv)
+        step_bytes = model_bytes_per_step(ncols_total, nv, k=ntr)
         line = {
             "metric": "sypd", "value": sy(ms), "unit": "SYPD", "n_gpus": nranks, "steps": K, "warmup": W, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"dry_baroclinic_wave he{w['h_elem']} ze63 Float32 dt={w['dt']:.0f}s (ARS343, hyperdiffusion, Rayleigh+viscous sponge)",
+                "workload": f"{w['name']} he{w['h_elem']} ze{w['z_elem']} Float32 dt={w['dt']:.0f}s (ARS343, hyperdiffusion" + (", Rayleigh+viscous sponge)" if sponge else ")"),
                 "h_elem": w["h_elem"], "z_elem": nv, "dt_s": w["dt"], "elements_total": sim.grid.nelems, "elements_per_gpu": nh_local,
                 "columns_total": ncols_total, "parallelism": f"sfc-domain-decomposition x{nranks}",
                 "halo": ("nvlink-peer-memory" if getattr(sim, "peer_halo", False) else "nccl-send-recv") if nranks > 1 else "none", "implicit_stage": "fused" if fused else "hooks",
