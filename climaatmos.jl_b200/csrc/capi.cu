@@ -97,6 +97,7 @@ struct b200_ctx {
   ncclComm_t comm = nullptr;
   std::vector<int32_t> nbr, send_off, recv_off;
   int* d_send_elems = nullptr;
+  int* d_slot_mask = nullptr;   // per send slot: bit n set ⇔ node n of the element is shared with the receiving rank
   int n_send = 0;
   void *sendbuf = nullptr, *ghostbuf = nullptr;  // sized for the largest DSS call
   size_t halo_cap = 0;
@@ -104,7 +105,7 @@ struct b200_ctx {
   void* p2p_buf = nullptr;      // [2 parities][p2p_cap bytes] ghost slabs written by the neighbours, then int flags[nranks]
   size_t p2p_cap = 0;
   bool p2p_ready = false;
-  int* d_p2p_seq = nullptr;     // device-side exchange number (kernels_dss.cuh: k_p2p_signal)
+  int* d_p2p_seq = nullptr;     // device-side exchange number, followed by the pack-kernel completion counter (kernels_dss.cuh: P2PSig)
   int n_int_nodes = 0;          // records [0, n_int_nodes) have no ghost member (sorted first)
   std::vector<void*> p2p_peer;  // mapped neighbour buffers
   void** d_p2p_dst = nullptr;   // device array [n_neighbors] of destination base pointers (rewritten per call)
@@ -463,6 +464,31 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
     c->n_send = c->send_off.back();
     CK(cudaMalloc(&c->d_send_elems, std::max(1, c->n_send) * sizeof(int)));
     CK(cudaMemcpy(c->d_send_elems, T->send_elems, c->n_send * sizeof(int), cudaMemcpyHostToDevice));
+    {  // node masks of the send slots, from the DSS CSR: a local member is sent to rank q iff its node has a ghost member owned by q
+      const int nn = T->n_neighbors, nh = c->dims.nh;
+      std::vector<int> mask(std::max(1, c->n_send), 0);
+      std::vector<std::vector<int>> slot_of(nn, std::vector<int>(nh, -1));
+      for (int q = 0; q < nn; ++q)
+        for (int k = c->send_off[q]; k < c->send_off[q + 1]; ++k) slot_of[q][T->send_elems[k]] = k;
+      for (size_t nd = 0; nd + 1 < c->h_off.size(); ++nd) {
+        unsigned qs = 0;  // neighbours owning a ghost member of this node
+        for (int m = c->h_off[nd]; m < c->h_off[nd + 1]; ++m) {
+          const int el = c->h_mem[m] >> 4;
+          if (el >= nh)
+            for (int q = 0; q < nn; ++q)
+              if (el - nh >= c->recv_off[q] && el - nh < c->recv_off[q + 1]) qs |= 1u << q;
+        }
+        if (!qs) continue;
+        for (int m = c->h_off[nd]; m < c->h_off[nd + 1]; ++m) {
+          const int el = c->h_mem[m] >> 4, n = c->h_mem[m] & 15;
+          if (el >= nh) continue;
+          for (int q = 0; q < nn; ++q)
+            if ((qs >> q & 1) && slot_of[q][el] >= 0) mask[slot_of[q][el]] |= 1 << n;
+        }
+      }
+      CK(cudaMalloc(&c->d_slot_mask, mask.size() * sizeof(int)));
+      CK(cudaMemcpy(c->d_slot_mask, mask.data(), mask.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     Id128 id;
     memcpy(&id, nccl_id, 128);
     NK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
@@ -479,7 +505,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
-  fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->sendbuf); fr(c->ghostbuf);
+  fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->d_slot_mask); fr(c->sendbuf); fr(c->ghostbuf);
   for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->gstream) { cudaStreamDestroy(c->gstream); cudaEventDestroy(c->ev_gin); cudaEventDestroy(c->ev_gout); }
   if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
@@ -628,12 +654,17 @@ extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t*
     dst[nn + q] = (char*)c->p2p_peer[q] + their_cap;
   }
   CK(cudaMemcpy(c->d_p2p_dst, dst.data(), 2 * nn * sizeof(void*), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&c->d_p2p_seq, sizeof(int)));
-  CK(cudaMemset(c->d_p2p_seq, 0, sizeof(int)));
+  CK(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(int)));
+  CK(cudaMemset(c->d_p2p_seq, 0, 2 * sizeof(int)));
   c->p2p_ready = true;
   return 0;
 }
 
+static P2PSig p2p_sig(const b200_ctx* c) { return P2PSig{c->d_p2p_flags, c->d_p2p_seq, c->d_p2p_seq + 1, (int)c->nbr.size()}; }
+static P2PWait p2p_wait_args(const b200_ctx* c, bool on) {
+  if (!on) return P2PWait{nullptr, nullptr, nullptr, 0};
+  return P2PWait{reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, c->d_p2p_seq, (int)c->nbr.size()};
+}
 // ---------------------------------------------------------------------------------------------
 // DSS: local gather–scatter, with a whole-slab halo exchange for elements owned by other ranks.
 struct DssField { void* ptr; int nf; int is_face; int kind; };
@@ -657,16 +688,17 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
     long long goff = 0;
     for (int f = 0; f < nfields; ++f) {
       int slab = F[f].nf * 16 * (nv + F[f].is_face);
-      PA.f[f] = {F[f].ptr, slab, goff};
+      PA.f[f] = {F[f].ptr, slab, goff, F[f].nf, nv + F[f].is_face};
       goff += slab;
     }
-    if (c->n_send > 0) {
-      k_pack_p2p<FT><<<c->n_send, 256, 0, s>>>(PA, c->d_send_elems, c->d_slot_nbr, c->d_slot_dst, (FT* const*)c->d_p2p_dst, c->d_nbr_nhg,
-                                              c->d_p2p_seq, nn);
-      LAUNCH_CHECK(c);
+    if (c->n_send > 0) {  // the last pack block to finish raises the flags
+      launchx(c->pdl & 4, k_pack_p2p<FT>, dim3(c->n_send), dim3(256), 0, s, PA, (const int*)c->d_send_elems, (const int*)c->d_slot_nbr,
+              (const int*)c->d_slot_dst, (const int*)c->d_slot_mask, (FT* const*)c->d_p2p_dst, (const int*)c->d_nbr_nhg, p2p_sig(c));
+    } else {
+      k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
     }
-    k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
     LAUNCH_CHECK(c);
+    (void)nn;
     ghost_base = c->p2p_buf;  // parity block 0; the kernels add (*seq & 1)·p2p_cap
   } else if (halo) {
     size_t need_s = tot_slab * c->n_send * sizeof(FT), need_g = tot_slab * c->dims.nh_ghost * sizeof(FT);
@@ -740,8 +772,8 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
     return 0;
   };
 #define DSS2(NI, PM)                                                                                                       \
-  (with_halo ? (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, true>, grd, blk, 0, s, A, rec, node0, node1, nh)             \
-             : (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, false>, grd, blk, 0, s, A, rec, node0, node1, nh))
+  (with_halo ? (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, true>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, p2p)) \
+             : (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, false>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, false)))
 #define DSS2_ANY()                                                                                                         \
   do {                                                                                                                     \
     if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);        /* state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃ */                                 \
@@ -766,9 +798,9 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   } else if (p2p) {
     node0 = 0; node1 = c->n_int_nodes; with_halo = false;
     if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
-    if (wait_p2p()) return -1;
-    node0 = c->n_int_nodes; node1 = c->nnodes; with_halo = true;
+    node0 = c->n_int_nodes; node1 = c->nnodes; with_halo = true;  // these blocks poll the neighbours' flags themselves
     if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
+    else if (wait_p2p()) return -1;  // keep the exchange protocol in step even without ghost-touching nodes
   } else {
     DSS2_ANY();
   }
@@ -963,21 +995,21 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
   if (p2p) {
     if (c->n_send > 0) {
       AXD_CASES((launchx(c->pdl & 8, k_pack_axpy_p2p<FT, N_>, dim3(c->n_send), dim3(256), 0, s, A, (const int*)c->d_send_elems, (const int*)c->d_slot_nbr,
-                         (const int*)c->d_slot_dst, (FT* const*)c->d_p2p_dst, (const int*)c->d_nbr_nhg, nn)));
-      LAUNCH_CHECK(c);
+                         (const int*)c->d_slot_dst, (const int*)c->d_slot_mask, (FT* const*)c->d_p2p_dst, (const int*)c->d_nbr_nhg, p2p_sig(c))));
+    } else {
+      k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
     }
-    k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
     LAUNCH_CHECK(c);
   }
-  AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, false>, dim3(nbn1 + nh), blk, 0, s, A, rec, 0, n_first, nbn1, nh)));
+  AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, false>, dim3(nbn1 + nh), blk, 0, s, A, rec, 0, n_first, nbn1, nh, p2p_wait_args(c, false))));
   LAUNCH_CHECK(c);
   if (p2p) {
-    k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, nn, c->d_p2p_seq);
-    LAUNCH_CHECK(c);
-    if (nbn2 > 0) {
-      AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, true>, dim3(nbn2), blk, 0, s, A, rec, n_first, c->nnodes, nbn2, 0)));
-      LAUNCH_CHECK(c);
+    if (nbn2 > 0) {  // these blocks poll the neighbours' flags themselves
+      AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, true>, dim3(nbn2), blk, 0, s, A, rec, n_first, c->nnodes, nbn2, 0, p2p_wait_args(c, true))));
+    } else {
+      k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, nn, c->d_p2p_seq);
     }
+    LAUNCH_CHECK(c);
   }
 #undef AXD_CASES
   return 0;

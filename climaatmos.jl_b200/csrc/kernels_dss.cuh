@@ -33,6 +33,21 @@ struct DssArgs {
   long long gpar;
 };
 
+// wait (inside a consumer kernel) until every neighbour has raised its flag to the current exchange number: thread 0 of the
+// block polls the flags in my own memory, the block then proceeds
+struct P2PWait { const int* flags; const int* nbr_rank; const int* seq; int nn; };
+__device__ __forceinline__ void p2p_block_wait(const P2PWait& W) {
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int value = *reinterpret_cast<const volatile int*>(W.seq);
+    for (int q = 0; q < W.nn; ++q) {
+      const volatile int* f = W.flags + W.nbr_rank[q];
+      while (*f < value) { __nanosleep(40); }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
 template <class FT>
 __global__ void __launch_bounds__(256) k_dss(DssArgs A, const int* __restrict__ off, const int* __restrict__ mem,
                                             const FT* __restrict__ hgeo, int nnodes, int nh) {
@@ -180,7 +195,7 @@ __device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R,
 }
 
 template <class FT, int NI, int PAIRS, bool HALO>
-__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nh) {
+__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nh, P2PWait W) {
   __shared__ DssNode<FT> sr[4];
   pdl_launch();
   const int v = threadIdx.x;
@@ -190,8 +205,9 @@ __global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __re
   if (RW > 64 && node < nnodes && v + 64 < RW)
     reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v + 64] = reinterpret_cast<const uint32_t*>(&rec[node])[v + 64];
   __syncthreads();
+  pdl_wait();                             // earlier kernels of this stream (incl. the pack kernel that advanced *seq) are complete
+  if (HALO && W.seq) p2p_block_wait(W);   // … and now the neighbours' slabs of this exchange have landed
   if (node >= nnodes) return;
-  pdl_wait();
   const DssNode<FT>& R = sr[threadIdx.y];
   const int cnt = R.cnt;  // uniform over the two warps of a node
   if (cnt == 2) dss_body<FT, NI, PAIRS, 2, HALO>(A, R, cnt, v, nh);
@@ -209,7 +225,7 @@ __global__ void k_pack(const FT* __restrict__ src, FT* __restrict__ dst, const i
 
 // ---- peer-memory halo (NVLink P2P): the sender writes its boundary-element slabs straight into the
 // neighbour's ghost buffer (cudaIpc-mapped pointer) and then raises a flag there; no NCCL call, no staging copy.
-struct P2PField { const void* src; int slab; long long goff; };  // goff: offset of this field's ghost block per unit nh_ghost
+struct P2PField { const void* src; int slab; long long goff; int ncomp, nlev; };  // goff: offset of this field's ghost block per unit nh_ghost; slab = ncomp·16·nlev
 struct P2PArgs {
   P2PField f[4];
   int nfields;
@@ -217,18 +233,61 @@ struct P2PArgs {
 // The exchange number lives in DEVICE memory (*seq, incremented by k_p2p_signal), so none of these kernels takes a per-call value:
 // a captured CUDA graph of the step replays correctly.  Ghost blocks are double-buffered by the parity of the exchange number
 // (a block is rewritten two exchanges later, after the neighbour's next flag has proved it finished reading).
+// Signalling is part of the pack kernels: every block bumps a device counter when its slab is written; the last one to finish
+// raises my flag in every neighbour's memory and advances the exchange number (P2PSig).  k_p2p_signal remains for ranks with
+// nothing to send.
+struct P2PSig {
+  int* const* peer_flags;  // [nn] address of my flag in neighbour q
+  int* seq;                // exchange number (device memory)
+  int* done;               // blocks finished in the current pack launch
+  int nn;
+};
+__device__ __forceinline__ void p2p_block_done(const P2PSig& S, int nblocks, int value) {
+  __shared__ int s_last;
+  __threadfence_system();  // this thread's peer writes are visible system-wide before the block reports
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(S.done, 1) == nblocks - 1);
+  __syncthreads();
+  if (s_last) {
+    if ((int)threadIdx.x < S.nn) {
+      __threadfence_system();
+      *reinterpret_cast<volatile int*>(S.peer_flags[threadIdx.x]) = value;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *S.done = 0; *S.seq = value; }
+  }
+}
+// Only the node columns the neighbour actually sums are sent: slot_mask[slot] has bit n set when node n of the send element is
+// collocated with a node of an element owned by that neighbour (4 of 16 columns across an edge, 1 across a vertex).
+__device__ __forceinline__ int p2p_nodes(unsigned mask, int* nodes /* shared, 16 */) {
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int n = 0; n < 16; ++n) if (mask >> n & 1) nodes[c++] = n;
+  }
+  __syncthreads();
+  return __popc(mask);
+}
 // one block per (send slot); dst[par*nn + q] = neighbour q's ghost buffer of parity par
 template <class FT>
 __global__ void k_pack_p2p(P2PArgs A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
-                           const int* __restrict__ slot_dst /* ghost slot in the neighbour */, FT* const* __restrict__ dst,
-                           const int* __restrict__ nbr_nh_ghost, const int* seq, int nn) {
+                           const int* __restrict__ slot_dst /* ghost slot in the neighbour */, const int* __restrict__ slot_mask,
+                           FT* const* __restrict__ dst, const int* __restrict__ nbr_nh_ghost, P2PSig S) {
+  __shared__ int nodes[16];
   const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
-  FT* base = dst[((*seq + 1) & 1) * nn + q];
+  const int cnt = p2p_nodes((unsigned)slot_mask[slot], nodes);
+  pdl_wait();
+  const int value = *S.seq + 1;
+  FT* base = dst[(value & 1) * S.nn + q];
   for (int k = 0; k < A.nfields; ++k) {
     const FT* s = reinterpret_cast<const FT*>(A.f[k].src) + (size_t)e * A.f[k].slab;
     FT* d = base + (size_t)A.f[k].goff * nbr_nh_ghost[q] + (size_t)g * A.f[k].slab;
-    for (int i = threadIdx.x; i < A.f[k].slab; i += blockDim.x) d[i] = s[i];
+    const int nlev = A.f[k].nlev, tot = A.f[k].ncomp * cnt * nlev;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+      const int lev = i % nlev, t = i / nlev, o = ((t / cnt) * 16 + nodes[t % cnt]) * nlev + lev;
+      d[o] = s[o];
+    }
   }
+  p2p_block_done(S, gridDim.x, value);
 }
 // raise my flag in every neighbour's memory (after the pack kernel has completed) and advance the exchange number
 __global__ void k_p2p_signal(int* const* __restrict__ peer_flags, int n, int* seq) {
@@ -399,28 +458,32 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
 // same arithmetic as k_axpy_n including the u₃ boundary filter — the receiving k_axpy_dss reads assembled values.
 template <class FT, int N>
 __global__ void k_pack_axpy_p2p(AxDssArgs<FT> A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
-                                const int* __restrict__ slot_dst, FT* const* __restrict__ dst, const int* __restrict__ nbr_nh_ghost, int nn) {
+                                const int* __restrict__ slot_dst, const int* __restrict__ slot_mask, FT* const* __restrict__ dst,
+                                const int* __restrict__ nbr_nh_ghost, P2PSig S) {
+  __shared__ int nodes[16];
   pdl_launch();
   const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
+  const int cnt = p2p_nodes((unsigned)slot_mask[slot], nodes);
   pdl_wait();
   const int nv = A.nv, nf = nv + 1, ec = A.ncf * 16 * nv, ef = 16 * nf;
-  FT* base = dst[((*A.seq + 1) & 1) * nn + q];
+  const int value = *S.seq + 1;
+  FT* base = dst[(value & 1) * S.nn + q];
   FT* dc = base + (size_t)g * ec;
   FT* df = base + (size_t)ec * nbr_nh_ghost[q] + (size_t)g * ef;
-  for (int i = threadIdx.x; i < ec; i += blockDim.x) dc[i] = axv<FT, N>(A.base_c, A.Tc, A.c, e * ec + i);
-  for (int i = threadIdx.x; i < ef; i += blockDim.x) {
-    const int lev = i % nf;
-    df[i] = (lev == 0 || lev == nv) ? FT(0) : axv<FT, N>(A.base_f, A.Tf, A.c, e * ef + i);
+  for (int i = threadIdx.x; i < A.ncf * cnt * nv; i += blockDim.x) {
+    const int lev = i % nv, t = i / nv, o = ((t / cnt) * 16 + nodes[t % cnt]) * nv + lev;
+    dc[o] = axv<FT, N>(A.base_c, A.Tc, A.c, e * ec + o);
   }
+  for (int i = threadIdx.x; i < cnt * nf; i += blockDim.x) {
+    const int lev = i % nf, o = nodes[i / nf] * nf + lev;
+    df[o] = (lev == 0 || lev == nv) ? FT(0) : axv<FT, N>(A.base_f, A.Tf, A.c, e * ef + o);
+  }
+  p2p_block_done(S, gridDim.x, value);
 }
-// nbn node blocks (four unique perimeter nodes × 64 levels; records sorted by owner element, capi.cu) and nh interior blocks (the
-// 4 interior nodes of one element) are INTERLEAVED in proportion, so an element's interior columns are read at about the same time
-// as its perimeter columns and the partially used 32-byte sectors between adjacent node columns are still in L2 (the first version
-// ran all interior blocks after all node blocks: 26 % more DRAM reads than algorithmic).  A CTA per element that loops over its
-// owned nodes was slower (dependent record → member latencies in series: +130 µs per step).
 // Records [node0, nnodes) in nbn node blocks; nint interior blocks (0 = none) interleaved with them.
 template <class FT, int N, bool HALO>
-__global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nbn, int nint) {
+__global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nbn, int nint,
+                                                   P2PWait W) {
   __shared__ DssNode<FT> sr[4];
   pdl_launch();
   const int v = threadIdx.x;
@@ -446,8 +509,9 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
   if (RW > 64 && node < nnodes && v + 64 < RW)
     reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v + 64] = reinterpret_cast<const uint32_t*>(&rec[node])[v + 64];
   __syncthreads();
-  if (node >= nnodes) return;
   pdl_wait();
+  if (HALO && W.seq) p2p_block_wait(W);
+  if (node >= nnodes) return;
   const DssNode<FT>& R = sr[threadIdx.y];
   const int cnt = R.cnt;
   if (cnt == 2) axdss_body<FT, N, 2, HALO>(A, R, cnt, v);
