@@ -660,6 +660,13 @@ extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t*
   return 0;
 }
 
+static P2PSig p2p_sig(const b200_ctx* c);
+static P2PPlan p2p_plan(const b200_ctx* c) {
+  P2PPlan Q;
+  Q.send_elems = c->d_send_elems; Q.slot_nbr = c->d_slot_nbr; Q.slot_dst = c->d_slot_dst; Q.slot_mask = c->d_slot_mask;
+  Q.dst = c->d_p2p_dst; Q.nbr_nh_ghost = c->d_nbr_nhg; Q.S = p2p_sig(c); Q.nblocks = c->n_send;
+  return Q;
+}
 static P2PSig p2p_sig(const b200_ctx* c) { return P2PSig{c->d_p2p_flags, c->d_p2p_seq, c->d_p2p_seq + 1, (int)c->nbr.size()}; }
 static P2PWait p2p_wait_args(const b200_ctx* c, bool on) {
   if (!on) return P2PWait{nullptr, nullptr, nullptr, 0};
@@ -680,6 +687,8 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   const bool halo = c->comm != nullptr;
   const bool p2p = halo && c->p2p_ready && nfields <= 4 && tot_slab <= p2p_state_slab(c) && !getenv("B200_HALO_NCCL");
   void* ghost_base = nullptr;
+  P2PArgs PAp; PAp.nfields = 0;
+  bool have_pack = false;  // this exchange has slabs to send (packed inside the ghost-free DSS launch, or by k_pack_p2p)
   if (p2p) {
     // peer-memory halo: pack straight into the neighbours' ghost buffers, raise flags, wait for theirs
     const int nn = (int)c->nbr.size();
@@ -691,13 +700,7 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
       PA.f[f] = {F[f].ptr, slab, goff, F[f].nf, nv + F[f].is_face};
       goff += slab;
     }
-    if (c->n_send > 0) {  // the last pack block to finish raises the flags
-      launchx(c->pdl & 4, k_pack_p2p<FT>, dim3(c->n_send), dim3(256), 0, s, PA, (const int*)c->d_send_elems, (const int*)c->d_slot_nbr,
-              (const int*)c->d_slot_dst, (const int*)c->d_slot_mask, (FT* const*)c->d_p2p_dst, (const int*)c->d_nbr_nhg, p2p_sig(c));
-    } else {
-      k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
-    }
-    LAUNCH_CHECK(c);
+    PAp = PA; have_pack = c->n_send > 0;
     (void)nn;
     ghost_base = c->p2p_buf;  // parity block 0; the kernels add (*seq & 1)·p2p_cap
   } else if (halo) {
@@ -765,15 +768,22 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   // With the peer-memory halo the nodes without ghost members are summed while the neighbours' slabs are still in flight; the
   // flag wait and the (few) ghost-touching nodes follow.  k_dss2<…, HALO> takes the record range [node0, node1).
   int node0 = 0, node1 = c->nnodes;
-  bool with_halo = halo;
+  bool with_halo = halo, with_pack = false;
+  auto pack_alone = [&]() -> int {  // pack + signal as their own launch (generic paths)
+    if (have_pack) launchx(c->pdl & 4, k_pack_p2p<FT>, dim3(c->n_send), dim3(256), 0, s, PAp, p2p_plan(c));
+    else k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, (int)c->nbr.size(), c->d_p2p_seq);
+    LAUNCH_CHECK(c);
+    return 0;
+  };
   auto wait_p2p = [&]() -> int {
     k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, (int)c->nbr.size(), c->d_p2p_seq);
     LAUNCH_CHECK(c);
     return 0;
   };
 #define DSS2(NI, PM)                                                                                                       \
-  (with_halo ? (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, true>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, p2p)) \
-             : (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, false>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, false)))
+  (with_halo ? (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, true, false>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, p2p), P2PArgs(), P2PPlan()) \
+   : with_pack ? (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, false, true>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, false), PAp, p2p_plan(c)) \
+               : (void)launchx(c->pdl & 4, k_dss2<FT, NI, PM, false, false>, grd, blk, 0, s, A, rec, node0, node1, nh, p2p_wait_args(c, false), P2PArgs(), P2PPlan()))
 #define DSS2_ANY()                                                                                                         \
   do {                                                                                                                     \
     if (A.n == 4 && pairs == 0x2) DSS2(4, 0x2);        /* state: ρ, (uₕ₁,uₕ₂), ρe_tot, u₃ */                                 \
@@ -791,13 +801,20 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
                        (A.n == 6 && pairs == 0x2) || (A.n == 5 && pairs == 0x1) || (A.n == 1 && pairs == 0x0) || (A.n == 1 && pairs == 0x1) ||
                        (A.n == 2 && pairs == 0x0);
   if (c->legacy || !small || !special) {
-    if (p2p && wait_p2p()) return -1;
+    if (p2p && (pack_alone() || wait_p2p())) return -1;
     grd.y = A.n;
     k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh);
     LAUNCH_CHECK(c);
   } else if (p2p) {
     node0 = 0; node1 = c->n_int_nodes; with_halo = false;
-    if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
+    if (have_pack) {  // the first n_send blocks of this launch pack and signal, the others sum the ghost-free nodes
+      with_pack = true;
+      grd.x = c->n_send + (node1 - node0 + 3) / 4; DSS2_ANY();
+      with_pack = false;
+    } else {
+      if (pack_alone()) return -1;
+      if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
+    }
     node0 = c->n_int_nodes; node1 = c->nnodes; with_halo = true;  // these blocks poll the neighbours' flags themselves
     if (node1 > node0) { grd.x = (node1 - node0 + 3) / 4; DSS2_ANY(); }
     else if (wait_p2p()) return -1;  // keep the exchange protocol in step even without ghost-touching nodes
@@ -992,20 +1009,18 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
                case 3: { constexpr int N_ = 3; STMT; } break; case 4: { constexpr int N_ = 4; STMT; } break; \
                case 5: { constexpr int N_ = 5; STMT; } break; case 6: { constexpr int N_ = 6; STMT; } break; \
                case 7: { constexpr int N_ = 7; STMT; } break; case 8: { constexpr int N_ = 8; STMT; } break; default: return 1; }
-  if (p2p) {
-    if (c->n_send > 0) {
-      AXD_CASES((launchx(c->pdl & 8, k_pack_axpy_p2p<FT, N_>, dim3(c->n_send), dim3(256), 0, s, A, (const int*)c->d_send_elems, (const int*)c->d_slot_nbr,
-                         (const int*)c->d_slot_dst, (const int*)c->d_slot_mask, (FT* const*)c->d_p2p_dst, (const int*)c->d_nbr_nhg, p2p_sig(c))));
-    } else {
-      k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq);
-    }
-    LAUNCH_CHECK(c);
+  if (p2p && c->n_send > 0) {  // the first n_send blocks assemble + send the boundary columns and signal
+    AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, false, true>, dim3(c->n_send + nbn1 + nh), blk, 0, s, A, rec, 0, n_first, nbn1, nh,
+                       p2p_wait_args(c, false), p2p_plan(c))));
+  } else {
+    if (p2p) { k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, nn, c->d_p2p_seq); LAUNCH_CHECK(c); }
+    AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, false, false>, dim3(nbn1 + nh), blk, 0, s, A, rec, 0, n_first, nbn1, nh,
+                       p2p_wait_args(c, false), P2PPlan())));
   }
-  AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, false>, dim3(nbn1 + nh), blk, 0, s, A, rec, 0, n_first, nbn1, nh, p2p_wait_args(c, false))));
   LAUNCH_CHECK(c);
   if (p2p) {
     if (nbn2 > 0) {  // these blocks poll the neighbours' flags themselves
-      AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, true>, dim3(nbn2), blk, 0, s, A, rec, n_first, c->nnodes, nbn2, 0, p2p_wait_args(c, true))));
+      AXD_CASES((launchx(c->pdl & 8, k_axpy_dss<FT, N_, true, false>, dim3(nbn2), blk, 0, s, A, rec, n_first, c->nnodes, nbn2, 0, p2p_wait_args(c, true), P2PPlan())));
     } else {
       k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, nn, c->d_p2p_seq);
     }

@@ -120,6 +120,108 @@ __global__ void __launch_bounds__(256) k_dss(DssArgs A, const int* __restrict__ 
   }
 }
 
+// ---- peer-memory halo (NVLink P2P): the sender writes its boundary-element slabs straight into the
+// neighbour's ghost buffer (cudaIpc-mapped pointer) and then raises a flag there; no NCCL call, no staging copy.
+struct P2PField { const void* src; int slab; long long goff; int ncomp, nlev; };  // goff: offset of this field's ghost block per unit nh_ghost; slab = ncomp·16·nlev
+struct P2PArgs {
+  P2PField f[4];
+  int nfields;
+};
+// The exchange number lives in DEVICE memory (*seq, incremented by k_p2p_signal), so none of these kernels takes a per-call value:
+// a captured CUDA graph of the step replays correctly.  Ghost blocks are double-buffered by the parity of the exchange number
+// (a block is rewritten two exchanges later, after the neighbour's next flag has proved it finished reading).
+// Signalling is part of the pack kernels: every block bumps a device counter when its slab is written; the last one to finish
+// raises my flag in every neighbour's memory and advances the exchange number (P2PSig).  k_p2p_signal remains for ranks with
+// nothing to send.
+struct P2PSig {
+  int* const* peer_flags;  // [nn] address of my flag in neighbour q
+  int* seq;                // exchange number (device memory)
+  int* done;               // blocks finished in the current pack launch
+  int nn;
+};
+__device__ __forceinline__ void p2p_block_done(const P2PSig& S, int nblocks, int value) {
+  __shared__ int s_last;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  __threadfence_system();  // this thread's peer writes are visible system-wide before the block reports
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(S.done, 1) == nblocks - 1);
+  __syncthreads();
+  if (s_last) {
+    if (tid < S.nn) {
+      __threadfence_system();
+      *reinterpret_cast<volatile int*>(S.peer_flags[tid]) = value;
+    }
+    __syncthreads();
+    if (tid == 0) { *S.done = 0; *S.seq = value; }
+  }
+}
+// Only the node columns the neighbour actually sums are sent: slot_mask[slot] has bit n set when node n of the send element is
+// collocated with a node of an element owned by that neighbour (4 of 16 columns across an edge, 1 across a vertex).
+__device__ __forceinline__ int p2p_nodes(unsigned mask, int* nodes /* shared, 16 */) {
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int c = 0;
+    for (int n = 0; n < 16; ++n) if (mask >> n & 1) nodes[c++] = n;
+  }
+  __syncthreads();
+  return __popc(mask);
+}
+// The send plan of a rank.  The pack work rides in the FIRST nblocks blocks of the kernel that sums the ghost-free nodes (k_dss2 /
+// k_axpy_dss with PACK): the slabs fly while the rest of that grid works, and the packed (ghost-touching) node columns are
+// disjoint from the columns the ghost-free nodes update in place.
+struct P2PPlan {
+  const int* send_elems; const int* slot_nbr; const int* slot_dst; const int* slot_mask;
+  void* const* dst;          // [2][nn] neighbour ghost blocks per parity
+  const int* nbr_nh_ghost;
+  P2PSig S;
+  int nblocks;               // send slots
+};
+// one block per (send slot): copy the shared node columns of the element into the neighbour's ghost block, then report
+template <class FT>
+__device__ __forceinline__ void p2p_pack_body(const P2PArgs& A, const P2PPlan& Q, int slot, int* nodes) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  const int e = Q.send_elems[slot], q = Q.slot_nbr[slot], g = Q.slot_dst[slot];
+  const int cnt = p2p_nodes((unsigned)Q.slot_mask[slot], nodes);
+  const int value = *Q.S.seq + 1;
+  FT* base = reinterpret_cast<FT*>(Q.dst[(value & 1) * Q.S.nn + q]);
+  for (int k = 0; k < A.nfields; ++k) {
+    const FT* s = reinterpret_cast<const FT*>(A.f[k].src) + (size_t)e * A.f[k].slab;
+    FT* d = base + (size_t)A.f[k].goff * Q.nbr_nh_ghost[q] + (size_t)g * A.f[k].slab;
+    const int nlev = A.f[k].nlev, tot = A.f[k].ncomp * cnt * nlev;
+    for (int i = tid; i < tot; i += nt) {
+      const int lev = i % nlev, t = i / nlev, o = ((t / cnt) * 16 + nodes[t % cnt]) * nlev + lev;
+      d[o] = s[o];
+    }
+  }
+  p2p_block_done(Q.S, Q.nblocks, value);
+}
+template <class FT>
+__global__ void k_pack_p2p(P2PArgs A, P2PPlan Q) {
+  __shared__ int nodes[16];
+  pdl_wait();
+  p2p_pack_body<FT>(A, Q, blockIdx.x, nodes);
+}
+// raise my flag in every neighbour's memory (after the pack kernel has completed) and advance the exchange number
+__global__ void k_p2p_signal(int* const* __restrict__ peer_flags, int n, int* seq) {
+  const int q = threadIdx.x;
+  const int value = *seq + 1;
+  if (q < n) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(peer_flags[q]) = value;
+  }
+  __syncwarp();
+  if (q == 0) *seq = value;
+}
+// wait until every neighbour has raised its flag to the current exchange number in my memory
+__global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict__ nbr_rank, int n, const int* seq) {
+  const int q = threadIdx.x;
+  const int value = *seq;
+  if (q < n) {
+    const volatile int* f = flags + nbr_rank[q];
+    while (*f < value) { __nanosleep(50); }
+    __threadfence_system();
+  }
+}
+
 // Second-generation DSS: one compact record per unique node (members, weights and the 2×2 basis-change
 // matrices of every member) so that a thread issues the record read and then ALL member loads of ALL items
 // back to back — two dependent memory latencies instead of four per item (off → mem → weight → data).
@@ -194,12 +296,20 @@ __device__ __forceinline__ void dss_body(const DssArgs& A, const DssNode<FT>& R,
   }
 }
 
-template <class FT, int NI, int PAIRS, bool HALO>
-__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nh, P2PWait W) {
+template <class FT, int NI, int PAIRS, bool HALO, bool PACK = false>
+__global__ void __launch_bounds__(256) k_dss2(DssArgs A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nh, P2PWait W,
+                                              P2PArgs PA = P2PArgs(), P2PPlan Q = P2PPlan()) {
   __shared__ DssNode<FT> sr[4];
+  __shared__ int pk_nodes[16];
   pdl_launch();
   const int v = threadIdx.x;
-  const int node = node0 + blockIdx.x * 4 + threadIdx.y;  // records [node0, nnodes)
+  const int npack = PACK ? Q.nblocks : 0;
+  if (PACK && (int)blockIdx.x < npack) {  // the first blocks send this rank's boundary columns
+    pdl_wait();
+    p2p_pack_body<FT>(PA, Q, blockIdx.x, pk_nodes);
+    return;
+  }
+  const int node = node0 + ((int)blockIdx.x - npack) * 4 + threadIdx.y;  // records [node0, nnodes)
   constexpr int RW = sizeof(DssNode<FT>) / 4;
   if (node < nnodes && v < RW) reinterpret_cast<uint32_t*>(&sr[threadIdx.y])[v] = reinterpret_cast<const uint32_t*>(&rec[node])[v];
   if (RW > 64 && node < nnodes && v + 64 < RW)
@@ -221,94 +331,6 @@ __global__ void k_pack(const FT* __restrict__ src, FT* __restrict__ dst, const i
   const FT* s = src + (size_t)e * slab;
   FT* d = dst + (size_t)blockIdx.x * slab;
   for (int i = threadIdx.x; i < slab; i += blockDim.x) d[i] = s[i];
-}
-
-// ---- peer-memory halo (NVLink P2P): the sender writes its boundary-element slabs straight into the
-// neighbour's ghost buffer (cudaIpc-mapped pointer) and then raises a flag there; no NCCL call, no staging copy.
-struct P2PField { const void* src; int slab; long long goff; int ncomp, nlev; };  // goff: offset of this field's ghost block per unit nh_ghost; slab = ncomp·16·nlev
-struct P2PArgs {
-  P2PField f[4];
-  int nfields;
-};
-// The exchange number lives in DEVICE memory (*seq, incremented by k_p2p_signal), so none of these kernels takes a per-call value:
-// a captured CUDA graph of the step replays correctly.  Ghost blocks are double-buffered by the parity of the exchange number
-// (a block is rewritten two exchanges later, after the neighbour's next flag has proved it finished reading).
-// Signalling is part of the pack kernels: every block bumps a device counter when its slab is written; the last one to finish
-// raises my flag in every neighbour's memory and advances the exchange number (P2PSig).  k_p2p_signal remains for ranks with
-// nothing to send.
-struct P2PSig {
-  int* const* peer_flags;  // [nn] address of my flag in neighbour q
-  int* seq;                // exchange number (device memory)
-  int* done;               // blocks finished in the current pack launch
-  int nn;
-};
-__device__ __forceinline__ void p2p_block_done(const P2PSig& S, int nblocks, int value) {
-  __shared__ int s_last;
-  __threadfence_system();  // this thread's peer writes are visible system-wide before the block reports
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(S.done, 1) == nblocks - 1);
-  __syncthreads();
-  if (s_last) {
-    if ((int)threadIdx.x < S.nn) {
-      __threadfence_system();
-      *reinterpret_cast<volatile int*>(S.peer_flags[threadIdx.x]) = value;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { *S.done = 0; *S.seq = value; }
-  }
-}
-// Only the node columns the neighbour actually sums are sent: slot_mask[slot] has bit n set when node n of the send element is
-// collocated with a node of an element owned by that neighbour (4 of 16 columns across an edge, 1 across a vertex).
-__device__ __forceinline__ int p2p_nodes(unsigned mask, int* nodes /* shared, 16 */) {
-  if (threadIdx.x == 0) {
-    int c = 0;
-    for (int n = 0; n < 16; ++n) if (mask >> n & 1) nodes[c++] = n;
-  }
-  __syncthreads();
-  return __popc(mask);
-}
-// one block per (send slot); dst[par*nn + q] = neighbour q's ghost buffer of parity par
-template <class FT>
-__global__ void k_pack_p2p(P2PArgs A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
-                           const int* __restrict__ slot_dst /* ghost slot in the neighbour */, const int* __restrict__ slot_mask,
-                           FT* const* __restrict__ dst, const int* __restrict__ nbr_nh_ghost, P2PSig S) {
-  __shared__ int nodes[16];
-  const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
-  const int cnt = p2p_nodes((unsigned)slot_mask[slot], nodes);
-  pdl_wait();
-  const int value = *S.seq + 1;
-  FT* base = dst[(value & 1) * S.nn + q];
-  for (int k = 0; k < A.nfields; ++k) {
-    const FT* s = reinterpret_cast<const FT*>(A.f[k].src) + (size_t)e * A.f[k].slab;
-    FT* d = base + (size_t)A.f[k].goff * nbr_nh_ghost[q] + (size_t)g * A.f[k].slab;
-    const int nlev = A.f[k].nlev, tot = A.f[k].ncomp * cnt * nlev;
-    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-      const int lev = i % nlev, t = i / nlev, o = ((t / cnt) * 16 + nodes[t % cnt]) * nlev + lev;
-      d[o] = s[o];
-    }
-  }
-  p2p_block_done(S, gridDim.x, value);
-}
-// raise my flag in every neighbour's memory (after the pack kernel has completed) and advance the exchange number
-__global__ void k_p2p_signal(int* const* __restrict__ peer_flags, int n, int* seq) {
-  const int q = threadIdx.x;
-  const int value = *seq + 1;
-  if (q < n) {
-    __threadfence_system();
-    *reinterpret_cast<volatile int*>(peer_flags[q]) = value;
-  }
-  __syncwarp();
-  if (q == 0) *seq = value;
-}
-// wait until every neighbour has raised its flag to the current exchange number in my memory
-__global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict__ nbr_rank, int n, const int* seq) {
-  const int q = threadIdx.x;
-  const int value = *seq;
-  if (q < n) {
-    const volatile int* f = flags + nbr_rank[q];
-    while (*f < value) { __nanosleep(50); }
-    __threadfence_system();
-  }
 }
 
 constexpr int AXPY_MAX = 8;
@@ -457,37 +479,40 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
 // Multi-rank: assemble the state of the SEND elements and write it straight into the neighbours' ghost blocks (peer memory),
 // same arithmetic as k_axpy_n including the u₃ boundary filter — the receiving k_axpy_dss reads assembled values.
 template <class FT, int N>
-__global__ void k_pack_axpy_p2p(AxDssArgs<FT> A, const int* __restrict__ send_elems, const int* __restrict__ slot_nbr,
-                                const int* __restrict__ slot_dst, const int* __restrict__ slot_mask, FT* const* __restrict__ dst,
-                                const int* __restrict__ nbr_nh_ghost, P2PSig S) {
-  __shared__ int nodes[16];
-  pdl_launch();
-  const int slot = blockIdx.x, e = send_elems[slot], q = slot_nbr[slot], g = slot_dst[slot];
-  const int cnt = p2p_nodes((unsigned)slot_mask[slot], nodes);
-  pdl_wait();
+__device__ __forceinline__ void p2p_pack_axpy_body(const AxDssArgs<FT>& A, const P2PPlan& Q, int slot, int* nodes) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  const int e = Q.send_elems[slot], q = Q.slot_nbr[slot], g = Q.slot_dst[slot];
+  const int cnt = p2p_nodes((unsigned)Q.slot_mask[slot], nodes);
   const int nv = A.nv, nf = nv + 1, ec = A.ncf * 16 * nv, ef = 16 * nf;
-  const int value = *S.seq + 1;
-  FT* base = dst[(value & 1) * S.nn + q];
+  const int value = *Q.S.seq + 1;
+  FT* base = reinterpret_cast<FT*>(Q.dst[(value & 1) * Q.S.nn + q]);
   FT* dc = base + (size_t)g * ec;
-  FT* df = base + (size_t)ec * nbr_nh_ghost[q] + (size_t)g * ef;
-  for (int i = threadIdx.x; i < A.ncf * cnt * nv; i += blockDim.x) {
+  FT* df = base + (size_t)ec * Q.nbr_nh_ghost[q] + (size_t)g * ef;
+  for (int i = tid; i < A.ncf * cnt * nv; i += nt) {
     const int lev = i % nv, t = i / nv, o = ((t / cnt) * 16 + nodes[t % cnt]) * nv + lev;
     dc[o] = axv<FT, N>(A.base_c, A.Tc, A.c, e * ec + o);
   }
-  for (int i = threadIdx.x; i < cnt * nf; i += blockDim.x) {
+  for (int i = tid; i < cnt * nf; i += nt) {
     const int lev = i % nf, o = nodes[i / nf] * nf + lev;
     df[o] = (lev == 0 || lev == nv) ? FT(0) : axv<FT, N>(A.base_f, A.Tf, A.c, e * ef + o);
   }
-  p2p_block_done(S, gridDim.x, value);
+  p2p_block_done(Q.S, Q.nblocks, value);
 }
 // Records [node0, nnodes) in nbn node blocks; nint interior blocks (0 = none) interleaved with them.
-template <class FT, int N, bool HALO>
+template <class FT, int N, bool HALO, bool PACK = false>
 __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode<FT>* __restrict__ rec, int node0, int nnodes, int nbn, int nint,
-                                                   P2PWait W) {
+                                                   P2PWait W, P2PPlan Q = P2PPlan()) {
   __shared__ DssNode<FT> sr[4];
+  __shared__ int pk_nodes[16];
   pdl_launch();
   const int v = threadIdx.x;
-  const long long tot = (long long)nbn + nint, b = blockIdx.x;
+  const int npack = PACK ? Q.nblocks : 0;
+  if (PACK && (int)blockIdx.x < npack) {  // the first blocks assemble and send this rank's boundary columns
+    pdl_wait();
+    p2p_pack_axpy_body<FT, N>(A, Q, blockIdx.x, pk_nodes);
+    return;
+  }
+  const long long tot = (long long)nbn + nint, b = (long long)blockIdx.x - npack;
   const int ib = (int)(b * nint / tot);               // interior blocks before this one
   if ((int)((b + 1) * nint / tot) != ib) {            // this block is interior block ib
     pdl_wait();
