@@ -19,7 +19,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 SYMBOLS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_nccl_unique_id", "b200_cache_imp",
     "b200_t_exp_lim", "b200_t_imp", "b200_wfact", "b200_ldiv", "b200_t_post_imp", "b200_dss",
-    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase", "b200_implicit_stage",
+    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase", "b200_implicit_stage", "b200_lim",
 ]
 
 
@@ -48,7 +48,7 @@ class Params(C.Structure):
         ("alpha_rayleigh_uh", C.c_double), ("alpha_rayleigh_w", C.c_double), ("viscous_sponge", C.c_int32),
         ("zd_viscous", C.c_double), ("kappa_2_sponge", C.c_double), ("energy_upwinding", C.c_int32),
         ("tracer_upwinding", C.c_int32), ("held_suarez", C.c_int32)] + [(n, C.c_double) for n in ("hs_day", "hs_sigma_b", "hs_dT_y", "hs_T_equator",
-                                                               "hs_dtheta_z", "hs_T_min", "MSLP")]
+                                                               "hs_dtheta_z", "hs_T_min", "MSLP")] + [("sem_quasimonotone_limiter", C.c_int32)]
 
 
 class CachePtrs(C.Structure):
@@ -102,6 +102,7 @@ def load():
     lib.b200_t_exp_phase.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b200_t_imp.argtypes = [vp, vp, vp, vp, vp, dbl, vp]
     lib.b200_implicit_stage.argtypes = [vp, vp, vp, vp, vp, dbl, vp]
+    lib.b200_lim.argtypes = [vp, vp, vp, vp, vp, dbl, vp]
     lib.b200_wfact.argtypes = [vp, vp, vp, dbl, dbl, vp]
     lib.b200_ldiv.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.b200_t_post_imp.argtypes = [vp, vp, vp, vp, vp, dbl, vp]
@@ -135,7 +136,8 @@ def make_params(P, N, grid) -> Params:
         alpha_rayleigh_uh=P.alpha_rayleigh_uh, alpha_rayleigh_w=P.alpha_rayleigh_w,
         viscous_sponge=int(N.viscous_sponge), zd_viscous=P.zd_viscous, kappa_2_sponge=P.kappa_2_sponge,
         energy_upwinding=up, tracer_upwinding={"none": 0, "first_order": 1, "vanleer_limiter": 3}[N.tracer_upwinding], held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
-        hs_T_equator=P.T_equator_dry, hs_dtheta_z=P.dtheta_z, hs_T_min=P.T_min_hs, MSLP=P.MSLP)
+        hs_T_equator=P.T_equator_dry, hs_dtheta_z=P.dtheta_z, hs_T_min=P.T_min_hs, MSLP=P.MSLP,
+        sem_quasimonotone_limiter=int(getattr(N, "apply_sem_quasimonotone_limiter", False)))
 
 
 def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1, n_tracers: int = 0):

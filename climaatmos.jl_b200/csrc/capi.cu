@@ -20,6 +20,7 @@
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_imp5.cuh"
+#include "kernels_limiter.cuh"
 
 using namespace b200;
 
@@ -85,7 +86,10 @@ struct b200_ctx {
   int nnodes = 0;
   std::vector<int32_t> h_off, h_mem;
   void* d_dssrec = nullptr;
-  int32_t* d_node_off = nullptr;  // records [d_node_off[e], d_node_off[e+1]) are owned by local element e
+  int32_t* d_node_off = nullptr;
+  int32_t *d_lim_nbr_off = nullptr, *d_lim_nbr = nullptr;  // vertex neighbours of every local element (limiter bounds)
+  void* d_lim_bnd = nullptr;    // [n_tracers][nh][2][64] element bounds of q
+  void* Tlc[4] = {nullptr, nullptr, nullptr, nullptr};  // T_lim of the four stages (stepper, limiter on)  // records [d_node_off[e], d_node_off[e+1]) are owned by local element e
   void* d_jac = nullptr;
   // native stepper storage (allocated lazily)
   void *Uc[2] = {nullptr, nullptr}, *Uf[2] = {nullptr, nullptr};
@@ -313,6 +317,7 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
       o[HG_COR3 * 16] = (FT)fw;
       o[HG_SIN2 * 16] = (FT)(sin(lat) * sin(lat)); o[HG_COS2 * 16] = (FT)(cos(lat) * cos(lat));
       o[HG_DSSW * 16] = (FT)(WJ[h * 16 + n] / tot[h * 16 + n]);
+      o[HG_WJ * 16] = (FT)WJ[h * 16 + n];
       o[HG_A00 * 16] = (FT)a00; o[HG_A01 * 16] = (FT)a01; o[HG_A10 * 16] = (FT)a10; o[HG_A11 * 16] = (FT)a11;
       o[HG_AI00 * 16] = (FT)ai00; o[HG_AI01 * 16] = (FT)ai01; o[HG_AI10 * 16] = (FT)ai10; o[HG_AI11 * 16] = (FT)ai11;
     }
@@ -430,6 +435,27 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
     return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
   }
   build_csr(T, c->h_off, c->h_mem);
+  {  // Topologies.local_neighboring_elements: elements sharing a vertex, from the vertex tables (limiter bounds)
+    const int nh = d->nh;
+    std::vector<std::vector<int32_t>> nb(nh);
+    for (int v = 0; v < T->n_verts; ++v)
+      for (int a = T->local_vertex_offset[v]; a < T->local_vertex_offset[v + 1]; ++a)
+        for (int b = T->local_vertex_offset[v]; b < T->local_vertex_offset[v + 1]; ++b) {
+          const int ea = T->local_vertices[2 * a], eb = T->local_vertices[2 * b];
+          if (ea != eb && ea < nh && eb < nh) nb[ea].push_back(eb);
+        }
+    std::vector<int32_t> off(nh + 1, 0), lst;
+    for (int e = 0; e < nh; ++e) {
+      std::sort(nb[e].begin(), nb[e].end());
+      nb[e].erase(std::unique(nb[e].begin(), nb[e].end()), nb[e].end());
+      lst.insert(lst.end(), nb[e].begin(), nb[e].end());
+      off[e + 1] = (int32_t)lst.size();
+    }
+    if (cudaMalloc(&c->d_lim_nbr_off, off.size() * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&c->d_lim_nbr, std::max<size_t>(1, lst.size()) * sizeof(int32_t)) != cudaSuccess) { delete c; return fail("b200_create: cudaMalloc (limiter tables)"); }
+    cudaMemcpy(c->d_lim_nbr_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_lim_nbr, lst.data(), lst.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  }
   c->nnodes = (int)c->h_off.size() - 1;
   // keep only nodes with at least one local member
   {
@@ -500,7 +526,8 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
 extern "C" int b200_destroy(b200_ctx* c) {
   if (!c) return 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off);
+  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off); fr(c->d_lim_nbr_off); fr(c->d_lim_nbr); fr(c->d_lim_bnd);
+  for (int i = 0; i < 4; ++i) fr(c->Tlc[i]);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
   fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
@@ -977,6 +1004,26 @@ static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// lim!(Y, p, t, ref_Y) (limited_tendencies.jl:64-122): SEM quasi-monotone limiter on every tracer of Y.c, bounds from ref_Y.
+// The reference's no-op when no limiter is configured.
+template <class FT>
+static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
+  const int ntr = c->dims.n_tracers, nh = c->dims.nh, nv = c->dims.nv;
+  if (!c->prm.sem_quasimonotone_limiter || ntr == 0) return 0;
+  if (c->nranks > 1) return fail("b200_lim: the quasi-monotone limiter is single-rank in this round (neighbour bounds are not exchanged)");
+  if (!c->d_lim_bnd) CK(cudaMalloc(&c->d_lim_bnd, (size_t)ntr * nh * 2 * LV * sizeof(FT)));
+  k_lim_bounds<FT><<<dim3(nh, ntr), 64, 0, s>>>((const FT*)refc, c->ncf(), nv, nh, (FT*)c->d_lim_bnd);
+  LAUNCH_CHECK(c);
+  k_lim_apply<FT><<<dim3(nh, ntr), 64, 0, s>>>((FT*)Yc, c->ncf(), nv, nh, (const FT*)c->d_lim_bnd, c->d_lim_nbr_off, c->d_lim_nbr, (const FT*)c->d_hgeo);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+extern "C" int b200_lim(b200_ctx* c, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double, void* stream) {
+  (void)Yf; (void)ref_Yf;
+  return c->ft == 4 ? impl_lim<float>(c, Yc, ref_Yc, (cudaStream_t)stream) : impl_lim<double>(c, Yc, ref_Yc, (cudaStream_t)stream);
+}
+
 // U = dss!(u + Σ c_j T_j) in one pass (k_axpy_dss); returns 1 when this context/call cannot use it (caller falls back).
 // Multi-rank contexts with the peer-memory halo: the send elements are assembled straight into the neighbours' ghost blocks
 // (k_pack_axpy_p2p), the nodes without ghost members and the interior nodes are processed while those slabs are in flight, then the
@@ -1090,7 +1137,21 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   }
   const Tableau tb = ars343();
   const double dt = c->prm.dt;
-  bool stiff = fused && !c->legacy && c->stiff_final;
+  // lim! between the limited and the unlimited increments (CTS update_stage!): only when a limiter is configured AND tracers exist
+  const bool limiter = c->prm.sem_quasimonotone_limiter && c->dims.n_tracers > 0;
+  if (limiter)
+    for (int i = 0; i < 4; ++i)
+      if (!c->Tlc[i]) CK(cudaMalloc(&c->Tlc[i], bc));
+  // U = u + dt Σ coef_j T_lim[j] (centres; faces are copied), then lim!(U, ref = u)
+  auto limited_increment = [&](void* Uc_, void* Uf_, const double* coef, int nst) -> int {
+    const void* Tl[4]; double cl[4]; int nl = 0;
+    for (int j = 0; j < nst; ++j)
+      if (coef[j] != 0) { Tl[nl] = c->Tlc[j]; cl[nl++] = dt * coef[j]; }
+    if (launch_axpy<FT>(c, (FT*)Uc_, (const FT*)Yc, nl, (const FT* const*)Tl, cl, c->nc(), s)) return -1;
+    if (launch_axpy<FT>(c, (FT*)Uf_, (const FT*)Yf, 0, (const FT* const*)Tl, cl, c->nf(), s)) return -1;
+    return nl > 0 ? impl_lim<FT>(c, Uc_, Yc, s) : 0;
+  };
+  bool stiff = fused && !c->legacy && c->stiff_final && !limiter;
   for (int j = 0; j < 4; ++j) stiff = stiff && tb.bi[j] == tb.ai[3][j];
   auto dss_state = [&](void* ac, void* af) -> int {
     DssField F[2] = {{ac, c->ncf(), 0, 2}, {af, 1, 1, 0}};
@@ -1107,11 +1168,17 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       }
       // fused path: the u₃ boundary filter of cache_imp! is folded into the increment (the DSS keeps zeros)
       // fused path: increment and DSS in one kernel where possible (single rank), else two passes
-      int rc = fused ? impl_axpy_dss<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s) : 1;
-      if (rc < 0) return -1;
-      if (rc == 1) {
-        if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
+      if (limiter) {
+        if (limited_increment(Uc, Uf, tb.ae[i], i)) return -1;
+        if (impl_axpy<FT>(c, Uc, Uf, Uc, Uf, n, Tc, Tf, cf, s, fused != 0)) return -1;
         if (dss_state(Uc, Uf)) return -1;
+      } else {
+        int rc = fused ? impl_axpy_dss<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s) : 1;
+        if (rc < 0) return -1;
+        if (rc == 1) {
+          if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
+          if (dss_state(Uc, Uf)) return -1;
+        }
       }
       const double dtg = dt * tb.ai[i][i];
       void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
@@ -1166,7 +1233,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;  // no-op on a filtered state; kept for the hook trace
     }
   t_exp_of_stage:
-    if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], nullptr, nullptr, Uc, Uf, s)) return -1;
+    if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], limiter ? c->Tlc[i] : nullptr, nullptr, Uc, Uf, s)) return -1;
     if (i > 0 && fused && !c->legacy && !(stiff && i == 3)) CK(cudaStreamWaitEvent(s, c->ev_join, 0));  // join the side stream
   }
   {
@@ -1182,11 +1249,17 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         if (tb.bi[j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.bi[j]; }
       }
     }
-    int rc = fused ? impl_axpy_dss<FT>(c, Yc, Yf, bc_, bf_, n, Tc, Tf, cf, s) : 1;
-    if (rc < 0) return -1;
-    if (rc == 1) {
-      if (impl_axpy<FT>(c, Yc, Yf, bc_, bf_, n, Tc, Tf, cf, s, fused != 0)) return -1;
+    if (limiter) {
+      if (limited_increment(c->Uc[0], c->Uf[0], tb.be, 4)) return -1;
+      if (impl_axpy<FT>(c, Yc, Yf, c->Uc[0], c->Uf[0], n, Tc, Tf, cf, s, fused != 0)) return -1;
       if (dss_state(Yc, Yf)) return -1;
+    } else {
+      int rc = fused ? impl_axpy_dss<FT>(c, Yc, Yf, bc_, bf_, n, Tc, Tf, cf, s) : 1;
+      if (rc < 0) return -1;
+      if (rc == 1) {
+        if (impl_axpy<FT>(c, Yc, Yf, bc_, bf_, n, Tc, Tf, cf, s, fused != 0)) return -1;
+        if (dss_state(Yc, Yf)) return -1;
+      }
     }
   }
   return fused ? 0 : impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);

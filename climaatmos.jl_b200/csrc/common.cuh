@@ -25,7 +25,7 @@ constexpr int SLAB = NN * LVP;       // shared-memory words per field
 enum {
   HG_J2 = 0, HG_RJ2, HG_GI11, HG_GI12, HG_GI22, HG_GC11, HG_GC12, HG_GC22,
   HG_COR1, HG_COR2, HG_COR3, HG_SIN2, HG_COS2, HG_DSSW, HG_A00, HG_A01, HG_A10, HG_A11,
-  HG_AI00, HG_AI01, HG_AI10, HG_AI11, HG_N
+  HG_AI00, HG_AI01, HG_AI10, HG_AI11, HG_WJ /* quadrature weight × J2 (limiter) */, HG_N
 };
 constexpr int HG_ELEM = 13;  // components the element kernels stage (J2..COS2)
 

@@ -63,7 +63,7 @@ class AtmosSimulation:
     def __init__(self, FT=np.float32, h_elem=6, z_elem=10, z_max=30000.0, dz_bottom=500.0, dt=400.0,
                  rayleigh_sponge=False, viscous_sponge=False, hyperdiff=True, deep_atmosphere=True,
                  initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter", rad=None,
-                 tracers=None, tracer_upwinding="vanleer_limiter",
+                 tracers=None, tracer_upwinding="vanleer_limiter", apply_sem_quasimonotone_limiter=False,
                  params: DycoreParams | None = None, device=None, comms=None, grid=None):
         torch = _torch()
         self.torch = torch
@@ -71,7 +71,8 @@ class AtmosSimulation:
         self.params = params or DycoreParams()
         self.numerics = DycoreNumerics(dt=float(dt), hyperdiff=hyperdiff, rayleigh_sponge=rayleigh_sponge,
                                        viscous_sponge=viscous_sponge, energy_upwinding=energy_q_tot_upwinding,
-                                       held_suarez=(rad == "held_suarez"), tracer_upwinding=tracer_upwinding)
+                                       held_suarez=(rad == "held_suarez"), tracer_upwinding=tracer_upwinding,
+                                       apply_sem_quasimonotone_limiter=bool(apply_sem_quasimonotone_limiter))
         self.grid = grid or make_sphere_grid(FT=self.FT, h_elem=h_elem, z_elem=z_elem, z_max=z_max, dz_bottom=dz_bottom,
                                              radius=self.params.planet_radius, deep_atmosphere=deep_atmosphere)
         self.comms = comms  # parallel.DistributedComms or None
@@ -200,7 +201,9 @@ class AtmosSimulation:
         """constrain_state! (constrain_state.jl:34-39): no-op for dry / non-EDMF configurations."""
 
     def limiters_func(self, Y, t, ref_Y):
-        """lim! (limited_tendencies.jl:64-122): no-op when no limiter is configured (defaults)."""
+        """lim!(Y, p, t, ref_Y) (limited_tendencies.jl:64-122): SEM quasi-monotone limiter of the tracers of Y with bounds from
+        ref_Y; the reference's no-op when no limiter is configured (defaults)."""
+        capi.check(self.lib.b200_lim(self.ctx, _p(Y.c), _p(Y.f), _p(ref_Y.c), _p(ref_Y.f), float(t), self._stream()), "b200_lim")
 
     def initialize_implicit_stage_problem(self, Y, dtgamma):
         """initialize_imp! (initialize_implicit_problem.jl:33-57): no-op unless PrognosticEDMFX."""

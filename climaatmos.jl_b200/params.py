@@ -59,6 +59,7 @@ class DycoreNumerics:
     viscous_sponge: bool = False
     energy_upwinding: str = "vanleer_limiter"  # default_config.yml:324-326
     tracer_upwinding: str = "vanleer_limiter"  # default_config.yml:321-323
+    apply_sem_quasimonotone_limiter: bool = False  # default_config.yml (Limiters.QuasiMonotoneLimiter in lim!, type_getters.jl:129)
     held_suarez: bool = False
 
 

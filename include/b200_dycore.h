@@ -81,6 +81,9 @@ typedef struct {
   int32_t tracer_upwinding; /* same encoding (default_config.yml:321-323) */
   /* Held–Suarez forcing (src/parameterized_tendencies/radiation/held_suarez.jl:111-296); flat surface */
   int32_t held_suarez; double hs_day, hs_sigma_b, hs_dT_y, hs_T_equator, hs_dtheta_z, hs_T_min, MSLP;
+  /* apply_sem_quasimonotone_limiter (config/default_configs/default_config.yml; type_getters.jl:129): lim! applies ClimaCore's
+   * Limiters.QuasiMonotoneLimiter to every tracer; 0 = lim! is the reference's no-op */
+  int32_t sem_quasimonotone_limiter;
 } b200_params;
 
 /* Optional device pointers to p.precomputed fields written by b200_cache_imp (any may be NULL).
@@ -139,6 +142,10 @@ int b200_axpy_n(b200_ctx*, void* Uc, void* Uf, const void* uc, const void* uf, i
  * above in the order of DESIGN.md "Step trace" (role of CTS.step!, solve.jl:62,125).  The
  * state (Yc, Yf) is advanced in place. `fused` selects the fused implicit-stage kernel. */
 int b200_step_ars343(b200_ctx*, void* Yc, void* Yf, double t, int32_t fused, void* stream);
+/* lim!(Y, p, t, ref_Y) (src/prognostic_equations/limited_tendencies.jl:64-122): SEM quasi-monotone limiter of every tracer ρχ of
+ * Y.c (in place) with bounds from ref_Y (element min/max of χ widened over the vertex neighbours).  No-op unless
+ * params.sem_quasimonotone_limiter and n_tracers > 0.  Single-rank contexts only in this round. */
+int b200_lim(b200_ctx*, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double t, void* stream);
 /* One fused implicit stage = one Newton iteration of ClimaTimeSteppers' implicit solve on the stage problem
  * (integrator.jl:63-120: initialize_imp!/cache_imp!, Wfact, T_imp!, ldiv!, U −= ΔU, cache_imp!, T_post_imp!):
  *   N = U − J(U)⁻¹ (dtγ·T_imp(U))  [+ dtγ·(vtt_upwind − vtt_central)(N) when energy upwinding is on]

@@ -494,6 +494,86 @@ class Oracle:
             + [("scalar", [Yf[:, 0]])]
         )
 
+    # ------------------------------------------------------------------ lim!  (limited_tendencies.jl:64-122)
+    def neighboring_elements(self):
+        """``Topologies.local_neighboring_elements``: elements sharing a vertex (hence also a face) with each element
+        [UPSTREAM-RECALL ClimaCore 0.15.1 src/Topologies/topology2d.jl], from the vertex tables."""
+        if getattr(self, "_nbrs", None) is None:
+            topo = self.grid.topology
+            lv, lo = np.asarray(topo.local_vertices), np.asarray(topo.local_vertex_offset)
+            nb = [set() for _ in range(self.grid.nelems)]
+            for v in range(len(lo) - 1):
+                es = [int(e) for e in lv[lo[v]:lo[v + 1], 0]]
+                for e in es:
+                    nb[e].update(es)
+            self._nbrs = [sorted(s - {e}) for e, s in enumerate(nb)]
+        return self._nbrs
+
+    def limiter_bounds(self, ref_rhoq, ref_rho):
+        """``Limiters.compute_bounds!`` [UPSTREAM-RECALL ClimaCore src/Limiters/quasimonotone.jl]: per element and level the
+        min / max of q = ρq/ρ over the Nq² nodes (compute_element_bounds!), then min / max over the element and its
+        vertex-neighbours (compute_neighbor_bounds_local!).  Returns (q_min, q_max), each [h, v]."""
+        q = ref_rhoq / ref_rho
+        lo, hi = q.min(axis=(1, 2)), q.max(axis=(1, 2))
+        qmin, qmax = lo.copy(), hi.copy()
+        for e, ns in enumerate(self.neighboring_elements()):
+            for n in ns:
+                qmin[e] = np.minimum(qmin[e], lo[n])
+                qmax[e] = np.maximum(qmax[e], hi[n])
+        return qmin, qmax
+
+    def apply_limiter(self, rhoq, rho, qmin, qmax):
+        """``Limiters.apply_limiter!`` → ``apply_limit_slab!`` [UPSTREAM-RECALL]: per (element, level) slab clip ρq to
+        [ρ q_min, ρ q_max] (bounds relaxed to contain the slab mean) and redistribute the clipped tracer mass over the nodes that
+        still have room, in proportion to ρ·WJ; at most Nq² iterations, stop when |Δmass| ≤ rtol·|mass| with rtol = eps(FT).
+        All slabs are iterated together; sums run over the nodes in the order n = 4j + i.  ``rhoq`` is modified in place."""
+        FT = self.FT
+        nh, nq, _, nv = rhoq.shape
+        r = rho.reshape(nh, nq * nq, nv)
+        x = rhoq.reshape(nh, nq * nq, nv).copy()
+        w = np.asarray(self.c.WJ, dtype=FT).reshape(nh, nq * nq, nv)
+        nn = nq * nq
+        rtol = np.finfo(FT).eps
+
+        def ssum(a):  # sequential sum over the nodes (the kernel's order)
+            t = np.zeros(a.shape[:1] + a.shape[2:], dtype=FT)
+            for n in range(nn):
+                t = t + a[:, n]
+            return t
+
+        total_mass = ssum(r * w)
+        tracer_mass = ssum(x * w)
+        q_avg = tracer_mass / total_mass
+        lo, hi = np.minimum(qmin, q_avg)[:, None, :], np.maximum(qmax, q_avg)[:, None, :]
+        active = np.ones(total_mass.shape, dtype=bool)
+        for _ in range(nn):
+            xmax, xmin = r * hi, r * lo
+            over, under = x > xmax, (x < xmin) & ~(x > xmax)
+            d = np.where(over, (x - xmax) * w, np.where(under, (x - xmin) * w, FT(0)))
+            dm = ssum(d)
+            a3 = active[:, None, :]
+            x = np.where(a3 & over, xmax, np.where(a3 & under, xmin, x))
+            active = active & ~(np.abs(dm) <= rtol * np.abs(tracer_mass))
+            if not active.any():
+                break
+            add = dm > 0
+            room = np.where(add[:, None, :], x < xmax, x > xmin)
+            mass_at = ssum(np.where(room, r * w, FT(0)))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dq = dm / mass_at
+            upd = active[:, None, :] & room
+            x = np.where(upd, x + r * dq[:, None, :], x)
+        rhoq[...] = x.reshape(rhoq.shape)
+
+    def limiters_func(self, Yc, ref_Yc):
+        """lim!(Y, p, t, ref_Y) (limited_tendencies.jl:64-122) for the SEM quasi-monotone limiter: bounds from ref_Y, applied to
+        every tracer of Y.c in place.  No-op unless ``apply_sem_quasimonotone_limiter``."""
+        if not getattr(self.N, "apply_sem_quasimonotone_limiter", False):
+            return
+        for q in range(4, Yc.shape[1]):
+            qmin, qmax = self.limiter_bounds(ref_Yc[:, q], ref_Yc[:, 0])
+            self.apply_limiter(Yc[:, q], Yc[:, 0], qmin, qmax)
+
     # ------------------------------------------------------------------ T_exp_T_lim!
     def vector_laplacian(self, u1, u2, u3, G):
         """hyperdiffusion.jl:141 / :273-277: C123(wgradₕ(divₕ(u))) - C123(wcurlₕ(C123(curlₕ(u))))
@@ -687,7 +767,8 @@ class Oracle:
         dt = self.N.dt
         uc, uf = Yc, Yf
         nel = Yc.shape[0]
-        Texp, Timp = [None] * 4, [None] * 4
+        Texp, Timp, Tlim = [None] * 4, [None] * 4, [None] * 4
+        limiter = bool(getattr(self.N, "apply_sem_quasimonotone_limiter", False)) and Yc.shape[1] > 4
         log = (lambda s: trace.append(s)) if trace is not None else (lambda s: None)
         nolog = lambda s: None
         if pool is not None and nchunks > 1:
@@ -704,10 +785,20 @@ class Oracle:
 
         def increment(i_coefs_exp, i_coefs_imp):
             Uc, Uf = np.empty_like(uc), np.empty_like(uf)
+            if limiter:  # CTS update_stage!: U = u + dt Σ a_exp T_lim ; lim!(U, p, t, u) ; then the unlimited increments
+                Uc[...] = uc
+                Uf[...] = uf
+                for j in range(4):
+                    if i_coefs_exp[j] != 0 and Tlim[j] is not None:
+                        Uc += FT(dt * i_coefs_exp[j]) * Tlim[j]
+                if any(i_coefs_exp[j] != 0 and Tlim[j] is not None for j in range(4)):
+                    self.limiters_func(Uc, uc)
+                    log("lim")
 
             def work(sub, sl):
-                Uc[sl] = uc[sl]
-                Uf[sl] = uf[sl]
+                if not limiter:
+                    Uc[sl] = uc[sl]
+                    Uf[sl] = uf[sl]
                 for j in range(4):
                     if i_coefs_exp[j] != 0 and Texp[j] is not None:
                         Uc[sl] += FT(dt * i_coefs_exp[j]) * Texp[j][0][sl]
@@ -721,6 +812,7 @@ class Oracle:
 
         def t_exp(Uc, Uf):
             Ytc, Ytf = np.empty_like(Uc), np.empty_like(Uf)
+            Ylc = np.zeros_like(Uc) if limiter else None
             nq = Uc.shape[1] - 4
             Ls = [np.empty_like(Uc[:, 0]) for _ in range(4 + nq)] if self.N.hyperdiff else None
 
@@ -729,7 +821,10 @@ class Oracle:
                 a, b, L = sub._rt_pre(Uc[sl], Uf[sl], pc)
                 lim = np.zeros_like(a)
                 sub._tracer_pre(a, lim, Uc[sl], Uf[sl], pc)
-                Ytc[sl], Ytf[sl] = a + lim, b  # lim! is a no-op (no limiter configured): T_lim joins T_exp
+                if limiter:
+                    Ytc[sl], Ytf[sl], Ylc[sl] = a, b, lim
+                else:
+                    Ytc[sl], Ytf[sl] = a + lim, b  # lim! is a no-op (no limiter configured): T_lim joins T_exp
                 if L is not None:
                     for k in range(4):
                         Ls[k][sl] = L[k]
@@ -742,10 +837,10 @@ class Oracle:
 
                 def post(sub, sl):
                     sub._rt_post(Ytc[sl], Ytf[sl], Uc[sl], tuple(a[sl] for a in Ls[:4]))
-                    sub._tracer_post(Ytc[sl], Uc[sl], [a[sl] for a in Ls[4:]])
+                    sub._tracer_post(Ylc[sl] if limiter else Ytc[sl], Uc[sl], [a[sl] for a in Ls[4:]])
 
                 pmap(post)
-            return Ytc, Ytf
+            return (Ytc, Ytf, Ylc) if limiter else (Ytc, Ytf)
 
         for i in range(4):
             Uc, Uf = increment(a_exp[i], a_imp[i])
@@ -774,7 +869,10 @@ class Oracle:
                 pmap(diff)
             else:
                 log("cache_imp")
-            Texp[i] = t_exp(Uc, Uf)
+            te = t_exp(Uc, Uf)
+            Texp[i] = te[:2]
+            if limiter:
+                Tlim[i] = te[2]
             log("t_exp")
         uc, uf = increment(b_exp, b_imp)
         self.dss_state(uc, uf)

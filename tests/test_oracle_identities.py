@@ -327,3 +327,58 @@ def test_step_with_tracers_leaves_dry_components_alone(case):
     b, bf = o.step(Yq[:, :4].copy(), Yf.copy())
     assert np.abs(a[:, :4] - b).max() <= 1e-12 * np.abs(b).max() and np.abs(af - bf).max() <= 1e-10 * max(np.abs(bf).max(), 1e-30)
     assert np.isfinite(a).all() and (a[:, 4] > 0).all()
+
+
+def test_quasimonotone_limiter_properties(case):
+    """lim! with the SEM quasi-monotone limiter (limited_tendencies.jl:64-122; ClimaCore Limiters.QuasiMonotoneLimiter): per
+    (element, level) slab the tracer mass Σ WJ ρχ is conserved to round-off, χ ends inside the neighbour bounds (relaxed to the slab
+    mean), a state inside its own bounds is untouched, and the limiter is idempotent."""
+    g, P, N, o, Yc, Yf, rng = case
+    N2 = prm.DycoreNumerics(dt=N.dt, apply_sem_quasimonotone_limiter=True)
+    ol = Oracle(g, P, N2, np.float64)
+    zz = np.broadcast_to(g.z_c, Yc[:, 0].shape)
+    chi = (np.abs(g.lat[..., None]) < 30.0) * (zz < 12000.0) * 1.0
+    ref = np.concatenate([Yc, (Yc[:, 0] * chi)[:, None]], axis=1)
+    Y = ref.copy()
+    Y[:, 4] += 0.3 * ref[:, 0] * rng.standard_normal(chi.shape)
+    m0 = (ol.c.WJ * Y[:, 4]).sum(axis=(1, 2))
+    rho_m = (ol.c.WJ * Y[:, 0]).sum(axis=(1, 2))
+    qmin, qmax = ol.limiter_bounds(ref[:, 4], ref[:, 0])
+    assert (qmin <= (ref[:, 4] / ref[:, 0]).min(axis=(1, 2))).all()  # neighbour bounds contain the element's own
+    ol.limiters_func(Y, ref)
+    m1 = (ol.c.WJ * Y[:, 4]).sum(axis=(1, 2))
+    assert np.abs(m1 - m0).max() <= 1e-13 * np.abs(m0).max()
+    q = Y[:, 4] / Y[:, 0]
+    lo, hi = np.minimum(qmin, m0 / rho_m), np.maximum(qmax, m0 / rho_m)
+    assert (q >= lo[:, None, None, :] - 1e-14).all() and (q <= hi[:, None, None, :] + 1e-14).all()
+    Y2 = Y.copy()
+    ol.limiters_func(Y2, ref)
+    assert np.abs(Y2 - Y).max() <= 1e-15 * np.abs(Y).max()
+    Y3 = ref.copy()
+    ol.limiters_func(Y3, ref)
+    assert np.array_equal(Y3, ref)
+    # disabled limiter: the reference's no-op
+    Y4 = Y.copy()
+    o.limiters_func(Y4, ref)
+    assert np.array_equal(Y4, Y)
+
+
+def test_step_with_limiter_reduces_overshoots(case):
+    """ARS343 step with T_lim kept apart and lim! between the limited and the unlimited increments (CTS update_stage!): the
+    overshoot of a step-function tracer is smaller than without the limiter and the global tracer mass is unchanged."""
+    g, P, N, o, Yc, Yf, rng = case
+    zz = np.broadcast_to(g.z_c, Yc[:, 0].shape)
+    chi = (np.abs(g.lat[..., None]) < 30.0) * (zz < 12000.0) * 1.0
+    Yq = np.concatenate([Yc, (Yc[:, 0] * chi)[:, None]], axis=1)
+    o.dss_state(Yq, Yf)
+    N2 = prm.DycoreNumerics(dt=N.dt, rayleigh_sponge=True, viscous_sponge=True, apply_sem_quasimonotone_limiter=True)
+    ol = Oracle(g, P, N2, np.float64)
+    tr = []
+    a, af = ol.step(Yq.copy(), Yf.copy(), trace=tr)
+    b, bf = o.step(Yq.copy(), Yf.copy())
+    assert tr.count("lim") == 4  # stages 2-4 and the final update
+    assert np.abs(a[:, :4] - b[:, :4]).max() <= 1e-12 * np.abs(b[:, :4]).max()  # the dry components do not see the limiter
+    over = lambda y: max((y[:, 4] / y[:, 0]).max() - 1.0, -(y[:, 4] / y[:, 0]).min())
+    assert over(a) < 0.5 * over(b)
+    ma, mb = (ol.c.WJ * a[:, 4]).sum(), (o.c.WJ * b[:, 4]).sum()
+    assert abs(ma - mb) <= 1e-9 * abs(mb)
