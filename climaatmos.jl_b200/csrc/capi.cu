@@ -89,6 +89,8 @@ struct b200_ctx {
   int32_t* d_node_off = nullptr;
   int32_t *d_lim_nbr_off = nullptr, *d_lim_nbr = nullptr;  // vertex neighbours of every local element (limiter bounds)
   void* d_lim_bnd = nullptr;    // [n_tracers][nh][2][64] element bounds of q
+  void* d_lim_E = nullptr;      // multi-rank: the bounds as a centre-shaped field [nh][2·n_tracers][16][nv] for the halo
+  int32_t* d_lim_ghost_node = nullptr;  // per ghost element: a node whose column this rank receives
   void* Tlc[4] = {nullptr, nullptr, nullptr, nullptr};  // T_lim of the four stages (stepper, limiter on)  // records [d_node_off[e], d_node_off[e+1]) are owned by local element e
   void* d_jac = nullptr;
   // native stepper storage (allocated lazily)
@@ -442,7 +444,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
       for (int a = T->local_vertex_offset[v]; a < T->local_vertex_offset[v + 1]; ++a)
         for (int b = T->local_vertex_offset[v]; b < T->local_vertex_offset[v + 1]; ++b) {
           const int ea = T->local_vertices[2 * a], eb = T->local_vertices[2 * b];
-          if (ea != eb && ea < nh && eb < nh) nb[ea].push_back(eb);
+          if (ea != eb && ea < nh) nb[ea].push_back(eb);  // eb >= nh: ghost neighbour (bounds arrive through the halo)
         }
     std::vector<int32_t> off(nh + 1, 0), lst;
     for (int e = 0; e < nh; ++e) {
@@ -526,7 +528,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
 extern "C" int b200_destroy(b200_ctx* c) {
   if (!c) return 0;
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off); fr(c->d_lim_nbr_off); fr(c->d_lim_nbr); fr(c->d_lim_bnd);
+  fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off); fr(c->d_lim_nbr_off); fr(c->d_lim_nbr); fr(c->d_lim_bnd); fr(c->d_lim_E); fr(c->d_lim_ghost_node);
   for (int i = 0; i < 4; ++i) fr(c->Tlc[i]);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
   fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
@@ -1009,13 +1011,35 @@ static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT 
 // The reference's no-op when no limiter is configured.
 template <class FT>
 static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
-  const int ntr = c->dims.n_tracers, nh = c->dims.nh, nv = c->dims.nv;
+  const int ntr = c->dims.n_tracers, nh = c->dims.nh, nv = c->dims.nv, ng = c->dims.nh_ghost;
   if (!c->prm.sem_quasimonotone_limiter || ntr == 0) return 0;
-  if (c->nranks > 1) return fail("b200_lim: the quasi-monotone limiter is single-rank in this round (neighbour bounds are not exchanged)");
+  const bool multi = c->nranks > 1 && !c->nbr.empty();
+  if (multi && (!c->p2p_ready || getenv("B200_HALO_NCCL")))
+    return fail("b200_lim: on multi-rank contexts the limiter needs the peer-memory halo (neighbour bounds travel through it)");
   if (!c->d_lim_bnd) CK(cudaMalloc(&c->d_lim_bnd, (size_t)ntr * nh * 2 * LV * sizeof(FT)));
-  k_lim_bounds<FT><<<dim3(nh, ntr), 64, 0, s>>>((const FT*)refc, c->ncf(), nv, nh, (FT*)c->d_lim_bnd);
+  if (multi && !c->d_lim_E) {
+    CK(cudaMalloc(&c->d_lim_E, (size_t)nh * 2 * ntr * 16 * nv * sizeof(FT)));
+    // a received node column of every ghost element: any ghost member of a DSS record
+    std::vector<int32_t> gn(std::max(1, ng), 0);
+    for (int32_t m : c->h_mem)
+      if ((m >> 4) >= nh) gn[(m >> 4) - nh] = m & 15;
+    CK(cudaMalloc(&c->d_lim_ghost_node, gn.size() * sizeof(int32_t)));
+    CK(cudaMemcpy(c->d_lim_ghost_node, gn.data(), gn.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  k_lim_bounds<FT><<<dim3(nh, ntr), 64, 0, s>>>((const FT*)refc, c->ncf(), nv, nh, (FT*)c->d_lim_bnd, multi ? (FT*)c->d_lim_E : nullptr, ntr);
   LAUNCH_CHECK(c);
-  k_lim_apply<FT><<<dim3(nh, ntr), 64, 0, s>>>((FT*)Yc, c->ncf(), nv, nh, (const FT*)c->d_lim_bnd, c->d_lim_nbr_off, c->d_lim_nbr, (const FT*)c->d_hgeo);
+  if (multi) {  // one more exchange of the peer-memory halo: the bounds field of the send elements
+    P2PArgs PA;
+    PA.nfields = 1;
+    PA.f[0] = {c->d_lim_E, 2 * ntr * 16 * nv, 0, 2 * ntr, nv};
+    if (c->n_send > 0) launchx(0, k_pack_p2p<FT>, dim3(c->n_send), dim3(256), 0, s, PA, p2p_plan(c));
+    else k_p2p_signal<<<1, 32, 0, s>>>(c->d_p2p_flags, (int)c->nbr.size(), c->d_p2p_seq);
+    LAUNCH_CHECK(c);
+    k_p2p_wait<<<1, 32, 0, s>>>(reinterpret_cast<const int*>((char*)c->p2p_buf + 2 * c->p2p_cap), c->d_nbr_rank, (int)c->nbr.size(), c->d_p2p_seq);
+    LAUNCH_CHECK(c);
+  }
+  k_lim_apply<FT><<<dim3(nh, ntr), 64, 0, s>>>((FT*)Yc, c->ncf(), nv, nh, (const FT*)c->d_lim_bnd, c->d_lim_nbr_off, c->d_lim_nbr, (const FT*)c->d_hgeo,
+                                            multi ? (const FT*)c->p2p_buf : nullptr, (long long)c->p2p_cap, c->d_p2p_seq, c->d_lim_ghost_node, ntr);
   LAUNCH_CHECK(c);
   return 0;
 }

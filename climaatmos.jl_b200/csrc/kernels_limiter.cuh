@@ -18,8 +18,11 @@ template <class FT> __device__ __forceinline__ FT eps_();
 template <> __device__ __forceinline__ float eps_<float>() { return 1.1920929e-07f; }
 template <> __device__ __forceinline__ double eps_<double>() { return 2.220446049250313e-16; }
 
+// E (multi-rank only): the bounds again, in the shape of a centre field [h][2·ntr][16][nv] (every node column of the element holds
+// the element's bound), so the ordinary peer-memory halo (k_pack_p2p: the node columns shared with each neighbour) carries them.
 template <class FT>
-__global__ void __launch_bounds__(64) k_lim_bounds(const FT* __restrict__ ref_c, int ncf, int nv, int nh, FT* __restrict__ bnd) {
+__global__ void __launch_bounds__(64) k_lim_bounds(const FT* __restrict__ ref_c, int ncf, int nv, int nh, FT* __restrict__ bnd,
+                                                   FT* __restrict__ E, int ntr) {
   const int e = blockIdx.x, t = blockIdx.y, v = threadIdx.x;
   if (v >= nv) return;
   const FT* r = ref_c + (size_t)e * ncf * 16 * nv + v;
@@ -32,20 +35,34 @@ __global__ void __launch_bounds__(64) k_lim_bounds(const FT* __restrict__ ref_c,
   }
   FT* b = bnd + ((size_t)(t * nh + e) * 2) * LV;
   b[v] = lo; b[LV + v] = hi;
+  if (E) {
+    FT* d = E + ((size_t)e * 2 * ntr + 2 * t) * 16 * nv + v;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) { d[n * nv] = lo; d[(16 + n) * nv] = hi; }
+  }
 }
 
 template <class FT>
 __global__ void __launch_bounds__(64) k_lim_apply(FT* __restrict__ Yc, int ncf, int nv, int nh, const FT* __restrict__ bnd,
                                                   const int* __restrict__ nbr_off, const int* __restrict__ nbr_list,
-                                                  const FT* __restrict__ hgeo) {
+                                                  const FT* __restrict__ hgeo, const FT* __restrict__ ghostE, long long gpar,
+                                                  const int* __restrict__ seq, const int* __restrict__ ghost_node, int ntr) {
   const int e = blockIdx.x, t = blockIdx.y, v = threadIdx.x;
   if (v >= nv) return;
   const FT* bt = bnd + (size_t)t * nh * 2 * LV;
   FT qmin = bt[(size_t)e * 2 * LV + v], qmax = bt[(size_t)e * 2 * LV + LV + v];
+  const FT* gE = ghostE ? reinterpret_cast<const FT*>(reinterpret_cast<const char*>(ghostE) + (size_t)(*seq & 1) * (size_t)gpar) : nullptr;
   for (int k = nbr_off[e]; k < nbr_off[e + 1]; ++k) {
     const int nb = nbr_list[k];
-    qmin = fmin_(qmin, bt[(size_t)nb * 2 * LV + v]);
-    qmax = fmax_(qmax, bt[(size_t)nb * 2 * LV + LV + v]);
+    if (nb < nh) {
+      qmin = fmin_(qmin, bt[(size_t)nb * 2 * LV + v]);
+      qmax = fmax_(qmax, bt[(size_t)nb * 2 * LV + LV + v]);
+    } else {  // ghost neighbour: its bounds arrived in the node column the owner shares with this rank
+      const int g = nb - nh;
+      const FT* p = gE + ((size_t)g * 2 * ntr + 2 * t) * 16 * nv + ghost_node[g] * nv + v;
+      qmin = fmin_(qmin, p[0]);
+      qmax = fmax_(qmax, p[(size_t)16 * nv]);
+    }
   }
   const FT* r = Yc + (size_t)e * ncf * 16 * nv + v;
   FT* xg = Yc + (size_t)e * ncf * 16 * nv + (size_t)(4 + t) * 16 * nv + v;

@@ -144,7 +144,8 @@ int b200_axpy_n(b200_ctx*, void* Uc, void* Uf, const void* uc, const void* uf, i
 int b200_step_ars343(b200_ctx*, void* Yc, void* Yf, double t, int32_t fused, void* stream);
 /* lim!(Y, p, t, ref_Y) (src/prognostic_equations/limited_tendencies.jl:64-122): SEM quasi-monotone limiter of every tracer ρχ of
  * Y.c (in place) with bounds from ref_Y (element min/max of χ widened over the vertex neighbours).  No-op unless
- * params.sem_quasimonotone_limiter and n_tracers > 0.  Single-rank contexts only in this round. */
+ * params.sem_quasimonotone_limiter and n_tracers > 0.  Multi-rank contexts: needs the peer-memory halo (b200_halo_import), which
+ * carries the bounds of the ghost elements. */
 int b200_lim(b200_ctx*, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double t, void* stream);
 /* One fused implicit stage = one Newton iteration of ClimaTimeSteppers' implicit solve on the stage problem
  * (integrator.jl:63-120: initialize_imp!/cache_imp!, Wfact, T_imp!, ldiv!, U −= ΔU, cache_imp!, T_post_imp!):

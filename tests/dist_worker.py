@@ -81,7 +81,7 @@ def gloo_halo(rank, world, port):
     assert float(t.max()) < 1e-12, f"halo DSS mismatch {t}"
 
 
-def nccl_step():
+def nccl_step(tracers=False):
     import torch
     from climaatmos_jl_b200 import dycore, params as prm
     from climaatmos_jl_b200.parallel import DistributedComms
@@ -89,6 +89,8 @@ def nccl_step():
     comms = DistributedComms()
     P = prm.DycoreParams(zd_rayleigh=20000.0, zd_viscous=20000.0)
     kw = dict(FT=np.float32, h_elem=4, z_elem=15, z_max=30000.0, dz_bottom=300.0, dt=300.0, rayleigh_sponge=True, viscous_sponge=True, params=P)
+    if tracers:  # a step-function tracer with the SEM quasi-monotone limiter: neighbour bounds travel through the peer-memory halo
+        kw.update(tracers=[lambda lat, lon, z: (np.abs(lat) < 30.0) * (z < 12000.0) * 1.0 + 0 * lon], apply_sem_quasimonotone_limiter=True)
     sim = dycore.AtmosSimulation(comms=comms, **kw)
     for _ in range(3):
         sim.step(True)
@@ -113,3 +115,5 @@ def nccl_step():
 if __name__ == "__main__":
     if sys.argv[1] == "nccl-step":
         nccl_step()
+    elif sys.argv[1] == "nccl-step-tracer-limiter":
+        nccl_step(tracers=True)

@@ -40,3 +40,21 @@ def test_nccl_multi_gpu_step_is_rank_count_independent():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bitwise_equal=True" in r.stdout
+
+
+@pytest.mark.gpu
+def test_multi_gpu_tracer_step_with_limiter_is_rank_count_independent():
+    """With >= 2 GPUs: 3 ARS343 steps of a tracer-carrying configuration with the quasi-monotone limiter (lim! between the limited
+    and unlimited increments; the neighbour bounds of ghost elements arrive through the peer-memory halo) equal the single-GPU run
+    BITWISE on every rank's owned elements."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_worker.py"), "nccl-step-tracer-limiter"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "bitwise_equal=True" in r.stdout
