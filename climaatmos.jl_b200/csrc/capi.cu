@@ -121,6 +121,9 @@ struct b200_ctx {
   // CUDA graph of one fused step (single-rank contexts): captured on the second call with the same (Yc, Yf, stream)
   int use_graph = 1;  // B200_GRAPH=0 disables
   int pdl = 63;       // B200_PDL=<bit mask>: programmatic dependent launch per kernel group (1 exp_a, 2 exp_c, 4 dss2, 8 axpy, 16 imp, 32 diff); 0 = off
+  int zform = 1;       // B200_ZFORM=0: the fused stepper forms T_imp[j] = (N_j − U_j)/dtγ (side stream) instead of using the stage solutions
+  void *Nsc[4] = {nullptr, nullptr, nullptr, nullptr}, *Nsf[4] = {nullptr, nullptr, nullptr, nullptr};  // stage solutions N_j (zform)
+  int dbg_skip_diff = 0;  // B200_DEBUG_SKIP_TIMP=1 (timing experiments only, WRONG results): do not form T_imp
   int stiff_final = 1; // B200_STIFF_FINAL=0: literal final increment u + dt Σ b_j (T_exp[j] + T_imp[j]) in the fused path too
   int fuse_axdss = 1; // B200_FUSE_AXDSS=0: stage increment and state DSS as two passes (k_axpy_n, k_dss2) instead of k_axpy_dss
   struct StepGraph { cudaGraphExec_t exec; void *Yc, *Yf; int64_t launches; };
@@ -428,6 +431,8 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
   if (const char* e = getenv("B200_PDL")) c->pdl = atoi(e);
   if (const char* e = getenv("B200_STIFF_FINAL")) c->stiff_final = atoi(e);
+  if (const char* e = getenv("B200_DEBUG_SKIP_TIMP")) c->dbg_skip_diff = atoi(e);
+  if (const char* e = getenv("B200_ZFORM")) c->zform = atoi(e);
   if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
   if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
@@ -533,6 +538,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
   fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
+  for (int i = 0; i < 4; ++i) { fr(c->Nsc[i]); fr(c->Nsf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
   fr(c->Rc); fr(c->Rf); fr(c->dc); fr(c->df); fr(c->d_send_elems); fr(c->d_slot_mask); fr(c->sendbuf); fr(c->ghostbuf);
   for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
@@ -865,12 +871,13 @@ extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, con
 // ---------------------------------------------------------------------------------------------
 template <class FT>
 static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* const* T, const double* coef, size_t N, cudaStream_t s,
-                       int nlev = 0) {
+                       int nlev = 0, unsigned dmask = 0) {
   AxpyArgs<FT> A;
-  A.n = 0;
+  A.n = 0; A.dmask = 0;
   for (int k = 0; k < n; ++k) {
     if (coef[k] == 0.0) continue;
     if (A.n >= AXPY_MAX) return fail("b200_axpy_n: too many terms");
+    if (dmask >> k & 1) A.dmask |= 1u << A.n;
     A.T[A.n] = T[k]; A.c[A.n] = (FT)coef[k]; A.n++;
   }
   bool al = (N % 4 == 0) && (((uintptr_t)out | (uintptr_t)base) % (4 * sizeof(FT)) == 0);
@@ -883,9 +890,9 @@ static int launch_axpy(b200_ctx* c, FT* out, const FT* base, int n, const FT* co
 }
 template <class FT>
 static int impl_axpy(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int n, const void* const* Tc,
-                     const void* const* Tf, const double* coef, cudaStream_t s, bool filter_u3 = false) {
-  if (launch_axpy<FT>(c, (FT*)Uc, (const FT*)uc, n, (const FT* const*)Tc, coef, c->nc(), s)) return -1;
-  return launch_axpy<FT>(c, (FT*)Uf, (const FT*)uf, n, (const FT* const*)Tf, coef, c->nf(), s, filter_u3 ? c->dims.nv + 1 : 0);
+                     const void* const* Tf, const double* coef, cudaStream_t s, bool filter_u3 = false, unsigned dmask = 0) {
+  if (launch_axpy<FT>(c, (FT*)Uc, (const FT*)uc, n, (const FT* const*)Tc, coef, c->nc(), s, 0, dmask)) return -1;
+  return launch_axpy<FT>(c, (FT*)Uf, (const FT*)uf, n, (const FT* const*)Tf, coef, c->nf(), s, filter_u3 ? c->dims.nv + 1 : 0, dmask);
 }
 extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int32_t n, const void* const* Tc,
                            const void* const* Tf, const double* coef, void* stream) {
@@ -1054,7 +1061,7 @@ extern "C" int b200_lim(b200_ctx* c, void* Yc, void* Yf, const void* ref_Yc, con
 // flag wait and the ghost-touching nodes.
 template <class FT>
 static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int n, const void* const* Tc,
-                         const void* const* Tf, const double* coef, cudaStream_t s) {
+                         const void* const* Tf, const double* coef, cudaStream_t s, unsigned dmask = 0) {
   const int nh = c->dims.nh, nv = c->dims.nv;
   const bool small = (size_t)(nh + c->dims.nh_ghost) * c->ncf() * 16 * (size_t)(nv + 1) < (size_t)INT32_MAX;
   const bool multi = c->comm != nullptr || !c->nbr.empty() || c->dims.nh_ghost > 0;
@@ -1062,9 +1069,11 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
   if (!c->fuse_axdss || c->legacy || (multi && !p2p) || !small) return 1;
   AxDssArgs<FT> A;
   int m = 0;
+  A.dmask = 0;
   for (int k = 0; k < n; ++k) {
     if (coef[k] == 0.0) continue;
     if (m >= AXPY_MAX) return 1;
+    if (dmask >> k & 1) A.dmask |= 1u << m;
     A.Tc[m] = (const FT*)Tc[k]; A.Tf[m] = (const FT*)Tf[k]; A.c[m] = (FT)coef[k]; ++m;
   }
   if (m < 1) return 1;
@@ -1177,6 +1186,27 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   };
   bool stiff = fused && !c->legacy && c->stiff_final && !limiter;
   for (int j = 0; j < 4; ++j) stiff = stiff && tb.bi[j] == tb.ai[3][j];
+  // Stage-solution form of the increments (fused path, stiffly accurate tableau).  T_imp[j] ≡ (N_j − U_j)/(dt·a_imp[j][j]) only
+  // ever enters later increments, and U_j is itself an increment, so by recursion every stage state is
+  //     U_i = u + Σ_j α_ij (N_j − u) + dt Σ_j β_ij T_exp[j]
+  // with host-computed α, β: the increment kernels read the stage solutions N_j directly (term c·(N_j − u), the difference of two
+  // close numbers is exact) and T_imp is never formed.  The two 3·S passes that formed it could not overlap anything (every kernel
+  // of the step fills the register file) and cost 86 µs per step.  Same reads per increment as before (N_j replaces T_imp[j]).
+  const bool zform = stiff && c->zform;
+  double al[4][4] = {{0}}, bt[4][4] = {{0}};
+  if (zform) {
+    for (int i = 1; i < 4; ++i) {
+      for (int j = 0; j < i; ++j) bt[i][j] = tb.ae[i][j];
+      for (int j = 1; j < i; ++j) {
+        if (tb.ai[i][j] == 0) continue;
+        const double w = tb.ai[i][j] / tb.ai[j][j];
+        al[i][j] += w;
+        for (int k = 0; k < j; ++k) { al[i][k] -= w * al[j][k]; bt[i][k] -= w * bt[j][k]; }
+      }
+    }
+    for (int i = 1; i < 4; ++i)
+      if (!c->Nsc[i]) { CK(cudaMalloc(&c->Nsc[i], bc)); CK(cudaMalloc(&c->Nsf[i], bf)); }
+  }
   auto dss_state = [&](void* ac, void* af) -> int {
     DssField F[2] = {{ac, c->ncf(), 0, 2}, {af, 1, 1, 0}};
     return impl_dss<FT>(c, F, 2, s);
@@ -1186,9 +1216,17 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
     if (i > 0) {
       Uc = c->Uc[0]; Uf = c->Uf[0];
       const void* Tc[8]; const void* Tf[8]; double cf[8]; int n = 0;
-      for (int j = 0; j < i; ++j) {
-        if (tb.ae[i][j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.ae[i][j]; }
-        if (tb.ai[i][j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.ai[i][j]; }
+      unsigned dmask = 0;
+      if (zform) {
+        for (int j = 1; j < i; ++j)
+          if (al[i][j] != 0) { dmask |= 1u << n; Tc[n] = c->Nsc[j]; Tf[n] = c->Nsf[j]; cf[n++] = al[i][j]; }
+        for (int j = 0; j < i; ++j)
+          if (bt[i][j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * bt[i][j]; }
+      } else {
+        for (int j = 0; j < i; ++j) {
+          if (tb.ae[i][j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * tb.ae[i][j]; }
+          if (tb.ai[i][j] != 0) { Tc[n] = c->Tic[j]; Tf[n] = c->Tif[j]; cf[n++] = dt * tb.ai[i][j]; }
+        }
       }
       // fused path: the u₃ boundary filter of cache_imp! is folded into the increment (the DSS keeps zeros)
       // fused path: increment and DSS in one kernel where possible (single rank), else two passes
@@ -1197,15 +1235,15 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         if (impl_axpy<FT>(c, Uc, Uf, Uc, Uf, n, Tc, Tf, cf, s, fused != 0)) return -1;
         if (dss_state(Uc, Uf)) return -1;
       } else {
-        int rc = fused ? impl_axpy_dss<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s) : 1;
+        int rc = fused ? impl_axpy_dss<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, dmask) : 1;
         if (rc < 0) return -1;
         if (rc == 1) {
-          if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0)) return -1;
+          if (impl_axpy<FT>(c, Uc, Uf, Yc, Yf, n, Tc, Tf, cf, s, fused != 0, dmask)) return -1;
           if (dss_state(Uc, Uf)) return -1;
         }
       }
       const double dtg = dt * tb.ai[i][i];
-      void *Nc = c->Uc[1], *Nf = c->Uf[1];  // Newton-updated state
+      void *Nc = zform ? c->Nsc[i] : c->Uc[1], *Nf = zform ? c->Nsf[i] : c->Uf[1];  // Newton-updated state
       if (fused) {
         if (impl_imp_stage<FT>(c, Nc, Nf, Uc, Uf, dtg, s)) return -1;
       } else {
@@ -1237,7 +1275,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       // Stiffly accurate tableau (the last row of A_imp equals b, ARS343): the stage-4 solution already contains every implicit
       // term of the step, u_new = N₄ + dt Σ_j (b_j − a_exp[4][j]) T_exp[j]  (T_imp[4] ≡ (N₄ − U₄)/dtγ by definition), so the fused
       // path neither forms T_imp[4] nor reads u and the three T_imp vectors in the final increment (5 vectors instead of 7).
-      if (stiff && i == 3) { Uc = Nc; Uf = Nf; goto t_exp_of_stage; }
+      if (zform || (stiff && i == 3)) { Uc = Nc; Uf = Nf; goto t_exp_of_stage; }
       cudaStream_t sd = s;
       if (fused && !c->legacy) {
         if (!c->side) {
@@ -1249,8 +1287,10 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
         sd = c->side;
       }
-      if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), sd)) return -1;
-      if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), sd)) return -1;
+      if (!c->dbg_skip_diff) {
+        if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), sd)) return -1;
+        if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), sd)) return -1;
+      }
       if (sd != s) { CK(cudaEventRecord(c->ev_join, sd)); }
       Uc = Nc; Uf = Nf;
     } else if (!fused) {
@@ -1258,13 +1298,13 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
     }
   t_exp_of_stage:
     if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], limiter ? c->Tlc[i] : nullptr, nullptr, Uc, Uf, s)) return -1;
-    if (i > 0 && fused && !c->legacy && !(stiff && i == 3)) CK(cudaStreamWaitEvent(s, c->ev_join, 0));  // join the side stream
+    if (i > 0 && fused && !c->legacy && !zform && !(stiff && i == 3)) CK(cudaStreamWaitEvent(s, c->ev_join, 0));  // join the side stream
   }
   {
     const void* Tc[8]; const void* Tf[8]; double cf[8]; int n = 0;
     const void *bc_ = Yc, *bf_ = Yf;
     if (stiff) {
-      bc_ = c->Uc[1]; bf_ = c->Uf[1];  // N₄
+      bc_ = zform ? c->Nsc[3] : c->Uc[1]; bf_ = zform ? c->Nsf[3] : c->Uf[1];  // N₄
       for (int j = 0; j < 4; ++j)
         if (tb.be[j] - tb.ae[3][j] != 0) { Tc[n] = c->Tec[j]; Tf[n] = c->Tef[j]; cf[n++] = dt * (tb.be[j] - tb.ae[3][j]); }
     } else {

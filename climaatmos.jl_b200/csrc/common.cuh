@@ -93,6 +93,8 @@ __device__ __forceinline__ double exp_(double a) { return exp(a); }
 // reciprocal (IEEE division; a MUFU.RCP + Newton variant measured slower in k2_exp_a: 171 vs 163 µs)
 __device__ __forceinline__ float  rcp_(float x)  { return 1.0f / x; }
 __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+__device__ __forceinline__ float  fma_(float a, float b, float c)  { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float  abs_(float a)  { return fabsf(a); }
 __device__ __forceinline__ double abs_(double a) { return fabs(a); }
 

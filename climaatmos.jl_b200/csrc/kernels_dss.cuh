@@ -339,6 +339,7 @@ struct AxpyArgs {
   const FT* T[AXPY_MAX];
   FT c[AXPY_MAX];
   int n;
+  unsigned dmask;  // bit k set: term k enters as c_k·(T_k − base) (a stage solution N_j measured from u, see impl_step)
 };
 
 // `nlev` > 0 marks a face field with nlev levels per column whose first and last level are forced to
@@ -355,8 +356,15 @@ __global__ void __launch_bounds__(256) k_axpy_n(FT* out, const FT* base, AxpyArg
     Vt r = reinterpret_cast<const Vt*>(base)[i];
     for (int k = 0; k < A.n; ++k) {
       Vt t = reinterpret_cast<const Vt*>(A.T[k])[i];
+      // explicit fma: the increment kernels (k_axpy_n, axv in k_axpy_dss / k_pack_axpy_p2p) must round identically
+      if (A.dmask >> k & 1) {
+        const Vt b0 = reinterpret_cast<const Vt*>(base)[i];
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) r.x[q] += A.c[k] * t.x[q];
+        for (int q = 0; q < VEC; ++q) r.x[q] = fma_(A.c[k], t.x[q] - b0.x[q], r.x[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) r.x[q] = fma_(A.c[k], t.x[q], r.x[q]);
+      }
     }
     if (nlev > 0) {
 #pragma unroll
@@ -383,19 +391,21 @@ struct AxDssArgs {
   const FT* base_c; const FT* base_f;
   const FT* Tc[AXPY_MAX]; const FT* Tf[AXPY_MAX];
   FT c[AXPY_MAX];
+  unsigned dmask;  // bit k set: term k enters as c_k·(T_k − base)
   int ncf, nv;
   // multi-rank: members with element index >= nh are ghosts whose ASSEMBLED slabs the owner has written into the peer-memory
   // ghost block (k_pack_axpy_p2p): [nh_ghost][ncf·16·nv] centre slabs, then [nh_ghost][16·(nv+1)] face slabs
   const FT* ghost; long long gpar; const int* seq; int nh, nh_ghost;
 };
 template <class FT, int N>
-__device__ __forceinline__ FT axv(const FT* __restrict__ b, const FT* const* T, const FT* c, int o) {
+__device__ __forceinline__ FT axv(const FT* __restrict__ b, const FT* const* T, const FT* c, int o, unsigned dmask = 0) {
   FT t[N];
-  FT r = b[o];
+  const FT b0 = b[o];
+  FT r = b0;
 #pragma unroll
   for (int k = 0; k < N; ++k) t[k] = T[k][o];
 #pragma unroll
-  for (int k = 0; k < N; ++k) r += c[k] * t[k];
+  for (int k = 0; k < N; ++k) r = fma_(c[k], (dmask >> k & 1) ? t[k] - b0 : t[k], r);
   return r;
 }
 template <class FT, int N, int CNT, bool HALO>
@@ -419,7 +429,7 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
   auto cval = [&](int q, int ko) -> FT {
     if (!(CNT == 2 || q < cnt)) return FT(0);
     if (gh[q]) return gc[oc[q] + ko];
-    return axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + ko);
+    return axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + ko, A.dmask);
   };
   if (v < nv) {
     // ρ, then the Covariant12 pair (uₕ₁, uₕ₂) in the local physical basis, then ρe_tot and the tracers
@@ -468,7 +478,7 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
       FT x[CNT];
 #pragma unroll
       for (int q = 0; q < CNT; ++q)
-        x[q] = !(CNT == 2 || q < cnt) ? FT(0) : (gh[q] ? gf[of[q]] : axv<FT, N>(A.base_f, A.Tf, A.c, of[q]));
+        x[q] = !(CNT == 2 || q < cnt) ? FT(0) : (gh[q] ? gf[of[q]] : axv<FT, N>(A.base_f, A.Tf, A.c, of[q], A.dmask));
 #pragma unroll
       for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
     }
@@ -490,11 +500,11 @@ __device__ __forceinline__ void p2p_pack_axpy_body(const AxDssArgs<FT>& A, const
   FT* df = base + (size_t)ec * Q.nbr_nh_ghost[q] + (size_t)g * ef;
   for (int i = tid; i < A.ncf * cnt * nv; i += nt) {
     const int lev = i % nv, t = i / nv, o = ((t / cnt) * 16 + nodes[t % cnt]) * nv + lev;
-    dc[o] = axv<FT, N>(A.base_c, A.Tc, A.c, e * ec + o);
+    dc[o] = axv<FT, N>(A.base_c, A.Tc, A.c, e * ec + o, A.dmask);
   }
   for (int i = tid; i < cnt * nf; i += nt) {
     const int lev = i % nf, o = nodes[i / nf] * nf + lev;
-    df[o] = (lev == 0 || lev == nv) ? FT(0) : axv<FT, N>(A.base_f, A.Tf, A.c, e * ef + o);
+    df[o] = (lev == 0 || lev == nv) ? FT(0) : axv<FT, N>(A.base_f, A.Tf, A.c, e * ef + o, A.dmask);
   }
   p2p_block_done(Q.S, Q.nblocks, value);
 }
@@ -520,11 +530,11 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
     const int nd = 5 + (threadIdx.y & 1) + 4 * (threadIdx.y >> 1);  // nodes (j, i) ∈ {1,2}²
     if (v < nv) {
       const int o = e * A.ncf * 16 * nv + nd * nv + v;
-      for (int k = 0; k < A.ncf; ++k) A.out_c[o + k * 16 * nv] = axv<FT, N>(A.base_c, A.Tc, A.c, o + k * 16 * nv);
+      for (int k = 0; k < A.ncf; ++k) A.out_c[o + k * 16 * nv] = axv<FT, N>(A.base_c, A.Tc, A.c, o + k * 16 * nv, A.dmask);
     }
     if (v < nf) {
       const int o = e * 16 * nf + nd * nf + v;
-      A.out_f[o] = (v > 0 && v < nv) ? axv<FT, N>(A.base_f, A.Tf, A.c, o) : FT(0);
+      A.out_f[o] = (v > 0 && v < nv) ? axv<FT, N>(A.base_f, A.Tf, A.c, o, A.dmask) : FT(0);
     }
     return;
   }

@@ -369,7 +369,7 @@ def test_full_size_properties_he30_ze63_f32():
 def _steps_with_env(env, FT, name, nsteps=3, **kw):
     import os
 
-    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_IMP_KERNEL", "B200_IMP_SOLVER", "B200_GENERIC_NV")
+    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_IMP_KERNEL", "B200_IMP_SOLVER", "B200_GENERIC_NV", "B200_ZFORM", "B200_STIFF_FINAL")
     old = {k: os.environ.pop(k, None) for k in keys}
     os.environ.update(env)
     try:
@@ -407,7 +407,9 @@ def test_implicit_stage_variants_agree(FT):
     nv = 63 specialisation and the generic build; the previous-generation k2_imp_stage) agree to round-off."""
     ref = _steps_with_env({"B200_IMP_KERNEL": "2"}, FT, "he3ze63", nsteps=2)[0]
     lim = 1e-12 if FT == np.float64 else 2e-6
-    for env in ({}, {"B200_IMP_SOLVER": "1"}, {"B200_IMP_SOLVER": "0"}, {"B200_GENERIC_NV": "1"}):
+    # … and so do the algebraic forms of the increments: stage-solution form (default), T_imp formed explicitly, literal final
+    for env in ({}, {"B200_IMP_SOLVER": "1"}, {"B200_IMP_SOLVER": "0"}, {"B200_GENERIC_NV": "1"}, {"B200_ZFORM": "0"},
+                {"B200_ZFORM": "0", "B200_STIFF_FINAL": "0"}):
         got = _steps_with_env(env, FT, "he3ze63", nsteps=2)[0]
         for k in range(4):
             assert rel(got[0][:, k], ref[0][:, k]) < lim, (env, k)
