@@ -35,13 +35,20 @@ struct DssArgs {
 
 // wait (inside a consumer kernel) until every neighbour has raised its flag to the current exchange number: thread 0 of the
 // block polls the flags in my own memory, the block then proceeds
+// a rank that waits longer than this many SM clocks (≈ 30 s) for a neighbour traps instead of hanging the GPU: the error then
+// surfaces on the host at the next CUDA call
+constexpr long long P2P_SPIN_LIMIT = 60000000000ll;
 struct P2PWait { const int* flags; const int* nbr_rank; const int* seq; int nn; };
 __device__ __forceinline__ void p2p_block_wait(const P2PWait& W) {
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     const int value = *reinterpret_cast<const volatile int*>(W.seq);
+    const long long t0 = clock64();
     for (int q = 0; q < W.nn; ++q) {
       const volatile int* f = W.flags + W.nbr_rank[q];
-      while (*f < value) { __nanosleep(40); }
+      while (*f < value) {
+        __nanosleep(40);
+        if (clock64() - t0 > P2P_SPIN_LIMIT) { printf("b200 halo: neighbour %d never signalled exchange %d\n", W.nbr_rank[q], value); __trap(); }
+      }
     }
     __threadfence_system();
   }
@@ -217,7 +224,11 @@ __global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict_
   const int value = *seq;
   if (q < n) {
     const volatile int* f = flags + nbr_rank[q];
-    while (*f < value) { __nanosleep(50); }
+    const long long t0 = clock64();
+    while (*f < value) {
+      __nanosleep(50);
+      if (clock64() - t0 > P2P_SPIN_LIMIT) { printf("b200 halo: neighbour %d never signalled exchange %d\n", nbr_rank[q], value); __trap(); }
+    }
     __threadfence_system();
   }
 }
