@@ -442,38 +442,53 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
     if (gh[q]) return gc[oc[q] + ko];
     return axv<FT, N>(A.base_c, A.Tc, A.c, oc[q] + ko, A.dmask);
   };
-  if (v < nv) {
-    // ρ, then the Covariant12 pair (uₕ₁, uₕ₂) in the local physical basis, then ρe_tot and the tracers
-    FT x[CNT], y[CNT];
+  // All loads and sums first, all stores last: out/base/T may alias as far as the compiler knows, so a store between two items
+  // would pin the loads of the later item behind it (four dependent DRAM round trips per thread instead of one).
+  // ρ, the Covariant12 pair (uₕ₁, uₕ₂) in the local physical basis, ρe_tot, u₃; further tracers are handled one by one below.
+  const bool cvl = v < nv, fvl = v < nf;
+  FT s_rho = FT(0), su = FT(0), sv = FT(0), s_re = FT(0), s_u3 = FT(0);
+  if (cvl) {
+    FT x[CNT], y[CNT], z[CNT], e[CNT];
 #pragma unroll
-    for (int q = 0; q < CNT; ++q) x[q] = cval(q, 0);
-    {
-      FT s = FT(0);
+    for (int q = 0; q < CNT; ++q) { x[q] = cval(q, 0); y[q] = cval(q, 16 * nv); z[q] = cval(q, 32 * nv); e[q] = cval(q, 48 * nv); }
 #pragma unroll
-      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
+    for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s_rho += R.w[q] * x[q];
 #pragma unroll
-      for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_c[oc[q]] = s;
-    }
+    for (int q = 0; q < CNT; ++q)
+      if (CNT == 2 || q < cnt) {
+        FT uu = R.ai[q][0] * y[q] + R.ai[q][1] * z[q];
+        FT vv = R.ai[q][2] * y[q] + R.ai[q][3] * z[q];
+        su += R.w[q] * uu; sv += R.w[q] * vv;
+      }
 #pragma unroll
-    for (int q = 0; q < CNT; ++q) { x[q] = cval(q, 16 * nv); y[q] = cval(q, 32 * nv); }
-    {
-      FT su = FT(0), sv = FT(0);
+    for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s_re += R.w[q] * e[q];
+  }
+  if (fvl && v > 0 && v < nv) {
+    FT x[CNT];
 #pragma unroll
-      for (int q = 0; q < CNT; ++q)
-        if (CNT == 2 || q < cnt) {
-          FT uu = R.ai[q][0] * x[q] + R.ai[q][1] * y[q];
-          FT vv = R.ai[q][2] * x[q] + R.ai[q][3] * y[q];
-          su += R.w[q] * uu; sv += R.w[q] * vv;
-        }
+    for (int q = 0; q < CNT; ++q)
+      x[q] = !(CNT == 2 || q < cnt) ? FT(0) : (gh[q] ? gf[of[q]] : axv<FT, N>(A.base_f, A.Tf, A.c, of[q], A.dmask));
 #pragma unroll
-      for (int q = 0; q < CNT; ++q)
-        if ((CNT == 2 || q < cnt) && !gh[q]) {
-          A.out_c[oc[q] + 16 * nv] = R.a[q][0] * su + R.a[q][1] * sv;
-          A.out_c[oc[q] + 32 * nv] = R.a[q][2] * su + R.a[q][3] * sv;
-        }
-    }
-    for (int k = 3; k < A.ncf; ++k) {
+    for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s_u3 += R.w[q] * x[q];
+  }
+  if (cvl) {
+#pragma unroll
+    for (int q = 0; q < CNT; ++q)
+      if ((CNT == 2 || q < cnt) && !gh[q]) {
+        A.out_c[oc[q]] = s_rho;
+        A.out_c[oc[q] + 16 * nv] = R.a[q][0] * su + R.a[q][1] * sv;
+        A.out_c[oc[q] + 32 * nv] = R.a[q][2] * su + R.a[q][3] * sv;
+        A.out_c[oc[q] + 48 * nv] = s_re;
+      }
+  }
+  if (fvl) {
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_f[of[q]] = s_u3;
+  }
+  if (cvl) {
+    for (int k = 4; k < A.ncf; ++k) {  // passive tracers
       const int ko = k * 16 * nv;
+      FT x[CNT];
 #pragma unroll
       for (int q = 0; q < CNT; ++q) x[q] = cval(q, ko);
       FT s = FT(0);
@@ -482,19 +497,6 @@ __device__ __forceinline__ void axdss_body(const AxDssArgs<FT>& A, const DssNode
 #pragma unroll
       for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_c[oc[q] + ko] = s;
     }
-  }
-  if (v < nf) {
-    FT s = FT(0);
-    if (v > 0 && v < nv) {
-      FT x[CNT];
-#pragma unroll
-      for (int q = 0; q < CNT; ++q)
-        x[q] = !(CNT == 2 || q < cnt) ? FT(0) : (gh[q] ? gf[of[q]] : axv<FT, N>(A.base_f, A.Tf, A.c, of[q], A.dmask));
-#pragma unroll
-      for (int q = 0; q < CNT; ++q) if (CNT == 2 || q < cnt) s += R.w[q] * x[q];
-    }
-#pragma unroll
-    for (int q = 0; q < CNT; ++q) if ((CNT == 2 || q < cnt) && !gh[q]) A.out_f[of[q]] = s;
   }
 }
 // Multi-rank: assemble the state of the SEND elements and write it straight into the neighbours' ghost blocks (peer memory),
@@ -539,14 +541,20 @@ __global__ void __launch_bounds__(256) k_axpy_dss(AxDssArgs<FT> A, const DssNode
     pdl_wait();
     const int e = ib, nv = A.nv, nf = nv + 1;
     const int nd = 5 + (threadIdx.y & 1) + 4 * (threadIdx.y >> 1);  // nodes (j, i) ∈ {1,2}²
+    const int o = e * A.ncf * 16 * nv + nd * nv + v, of_ = e * 16 * nf + nd * nf + v;
+    FT r[4], rf = FT(0);
     if (v < nv) {
-      const int o = e * A.ncf * 16 * nv + nd * nv + v;
-      for (int k = 0; k < A.ncf; ++k) A.out_c[o + k * 16 * nv] = axv<FT, N>(A.base_c, A.Tc, A.c, o + k * 16 * nv, A.dmask);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = axv<FT, N>(A.base_c, A.Tc, A.c, o + k * 16 * nv, A.dmask);
     }
-    if (v < nf) {
-      const int o = e * 16 * nf + nd * nf + v;
-      A.out_f[o] = (v > 0 && v < nv) ? axv<FT, N>(A.base_f, A.Tf, A.c, o, A.dmask) : FT(0);
+    if (v > 0 && v < nv) rf = axv<FT, N>(A.base_f, A.Tf, A.c, of_, A.dmask);
+    if (v < nv) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) A.out_c[o + k * 16 * nv] = r[k];
     }
+    if (v < nf) A.out_f[of_] = rf;
+    if (v < nv)
+      for (int k = 4; k < A.ncf; ++k) A.out_c[o + k * 16 * nv] = axv<FT, N>(A.base_c, A.Tc, A.c, o + k * 16 * nv, A.dmask);
     return;
   }
   const int node = node0 + ((int)b - ib) * 4 + threadIdx.y;

@@ -369,7 +369,7 @@ def test_full_size_properties_he30_ze63_f32():
 def _steps_with_env(env, FT, name, nsteps=3, **kw):
     import os
 
-    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_IMP_KERNEL", "B200_IMP_SOLVER", "B200_GENERIC_NV", "B200_ZFORM", "B200_STIFF_FINAL")
+    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_IMP_KERNEL", "B200_IMP_SOLVER", "B200_GENERIC_NV", "B200_ZFORM", "B200_STIFF_FINAL", "B200_PDL")
     old = {k: os.environ.pop(k, None) for k in keys}
     os.environ.update(env)
     try:
@@ -396,6 +396,8 @@ def test_fused_increment_dss_and_graph_are_bitwise_neutral(FT, name):
     (gc, gf), n_fused = _steps_with_env({}, FT, name)
     assert np.array_equal(rc, gc) and np.array_equal(rf, gf)
     assert n_fused < n_ref  # 8 launches fewer per step
+    (pc, pf), _ = _steps_with_env({"B200_PDL": "0"}, FT, name)  # programmatic dependent launch only changes when grids start
+    assert np.array_equal(pc, gc) and np.array_equal(pf, gf)
     (tc, tf), _ = _steps_with_env({"B200_FUSE_AXDSS": "0", "B200_GRAPH": "0"}, FT, name, tracers=_tracer_fns())
     (hc, hf), _ = _steps_with_env({}, FT, name, tracers=_tracer_fns())
     assert np.array_equal(tc, hc) and np.array_equal(tf, hf)
