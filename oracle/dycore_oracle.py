@@ -14,8 +14,9 @@ oracle instead: the structural identities the reference *does* test (tests/test_
 impenetrability (advection_tests.jl:46-58), corrected+central == upwind
 (correct_implicit_advection_tests.jl:40-67), sponge profiles
 (test/parameterized_tendencies/sponge.jl:44-80), operator identities
-(docs/src/discretization.md:76-94), a finite-difference check of the analytic Jacobian and
-conservation to round-off.
+(docs/src/discretization.md:76-94), a finite-difference check of the analytic Jacobian,
+conservation to round-off, and convergence of the total tendency to zero at the design orders on the
+analytic steady state of src/setups/DryBaroclinicWave.jl (the PDE itself as the judge).
 
 Every function cites the reference file:line it restates.  Operators are applied *literally*, in
 the order the reference composes them and with full per-point metric arrays (no factorisation),
