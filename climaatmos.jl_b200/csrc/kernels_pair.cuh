@@ -32,17 +32,26 @@ template <class FT>
 __device__ __forceinline__ P2<FT> shflp(const P2<FT>& a, int src) {
   return P2<FT>(__shfl_sync(FULLM, a.lo(), src), __shfl_sync(FULLM, a.hi(), src));
 }
+// ξ²-contraction o_j = Σ_k M[j][k]·a_k over the four lanes j = lane>>3 of a level, as a REDUCE-SCATTER: every lane multiplies its
+// own row by the matrix COLUMN it owns and the partial sums travel in two butterfly steps (lanes ^16, then ^8) — 3 shuffles per
+// value instead of the 4 of a gather (ncu: the LSU pipe, i.e. the shuffles, is the busiest pipe of k5_exp_a / k5_exp_c).
+// `m` is the column in butterfly order (ROW_COLUMNS below): m[k] = M[j ^ k][j].
 template <class FT>
-__device__ __forceinline__ void deta4p(const P2<FT> (&a)[2], const FT (&m)[4], int vl, P2<FT> (&o)[2]) {
+__device__ __forceinline__ P2<FT> shflxp(const P2<FT>& a, int mask) {
+  return P2<FT>(__shfl_xor_sync(FULLM, a.lo(), mask), __shfl_xor_sync(FULLM, a.hi(), mask));
+}
+template <class FT>
+__device__ __forceinline__ void deta4p(const P2<FT> (&a)[2], const FT (&m)[4], int /*vl*/, P2<FT> (&o)[2]) {
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
-    P2<FT> s = shflp(a[p], vl) * m[0];
-    s = fma2(shflp(a[p], vl + 8), m[1], s);
-    s = fma2(shflp(a[p], vl + 16), m[2], s);
-    s = fma2(shflp(a[p], vl + 24), m[3], s);
-    o[p] = s;
+    const P2<FT> rC = shflxp(a[p] * m[2], 16), rD = shflxp(a[p] * m[3], 16);  // partner j^2 collects rows j^2 and j^3
+    const P2<FT> qa = fma2(a[p], m[0], rC), qb = fma2(a[p], m[1], rD);          // rows j and j^1 over lanes {j, j^2}
+    o[p] = qa + shflxp(qb, 8);                                                  // partner j^1 collects row j^1
   }
 }
+// after B200_ROW_PROLOGUE*: replace the matrix rows by the columns in butterfly order
+#define ROW_COLUMNS                                                                               \
+  _Pragma("unroll") for (int k = 0; k < 4; ++k) { md[k] = cM<FT>((j ^ k) * 4 + j); mw[k] = cM<FT>(16 + (j ^ k) * 4 + j); }
 template <class FT, int W>
 __device__ __forceinline__ void div4p(const P2<FT> (&a1)[2], const P2<FT> (&a2)[2], const FT (&m)[4], int vl, P2<FT> (&o)[2]) {
   P2<FT> t[2];
@@ -109,6 +118,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
      *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
   pdl_launch();
   B200_ROW_PROLOGUE_NV(NVC)
+  ROW_COLUMNS
   pdl_wait(Yc, Yf, Ytc, Ytf, H);
   const bool interior = v > 0 && v < nv;
   const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v), offf = (size_t)e * 16 * nf + (n0 * nf + v);  // (row j, level v)
@@ -332,6 +342,7 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   FT* s_a = s_w + SLAB;
   pdl_launch();
   B200_ROW_PROLOGUE_NV(NVC)
+  ROW_COLUMNS
   pdl_wait(Yc, H, Ytc, Ytf);
   const int part = blockIdx.y;
   const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v);
@@ -438,6 +449,7 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   FT* sx = hg + HG_ELEM * 16;
   FT *s_chi = sx, *s_r = sx + SLAB, *s_fx = sx + 2 * SLAB;
   B200_ROW_PROLOGUE
+  ROW_COLUMNS
   const int q = 4 + blockIdx.y;
   const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   V rho[2], u1[2], u2[2], rq[2], u3[2], chi[2];
@@ -541,6 +553,7 @@ k5_tracer_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
   B200_ROW_PROLOGUE
+  ROW_COLUMNS
   const int q = 4 + blockIdx.y;
   V rho[2], Lq[2], old[2], a[2], g1[2], Q1[2], Q2[2], b[2];
   FT* gT = Tgt + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv;
