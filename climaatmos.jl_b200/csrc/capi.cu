@@ -384,15 +384,16 @@ template <class FT> static size_t smem_base() { return sizeof(VLev<FT>) + HG_ELE
 template <class FT> static size_t smem_slabs(int n) { return smem_base<FT>() + (size_t)n * SLAB * sizeof(FT); }
 
 template <class FT> static size_t smem_row(int n) { return (HG_ELEM * 16 + (size_t)n * SLAB) * sizeof(FT); }
+template <class FT> static size_t smem_rowq(int n) { return (HG_ELEM * 16 + (size_t)n * XSLAB) * sizeof(FT); }  // pair-layout slabs (k5_exp_a/c)
 
 template <class FT>
 static int set_attrs() {
   CK(cudaFuncSetAttribute(k2_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
   CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
-  CK(cudaFuncSetAttribute(k5_exp_a<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
-  CK(cudaFuncSetAttribute(k5_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
-  CK(cudaFuncSetAttribute(k5_exp_a<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
-  CK(cudaFuncSetAttribute(k5_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
@@ -920,10 +921,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     LAUNCH_CHECK(c);
   } else if (phase == 0 && c->exp_kernel == 5) {
     if (c->dims.nv == 63 && !c->generic_nv)
-      launchx(c->pdl & 1, k5_exp_a<FT, 63>, c->dims.nh, CT, smem_row<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+      launchx(c->pdl & 1, k5_exp_a<FT, 63>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                              (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     else
-      launchx(c->pdl & 1, k5_exp_a<FT, 0>, c->dims.nh, CT, smem_row<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+      launchx(c->pdl & 1, k5_exp_a<FT, 0>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
@@ -945,10 +946,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     LAUNCH_CHECK(c);
   } else if (phase == 2 && hd && !c->legacy && c->exp_kernel == 5) {
     if (c->dims.nv == 63 && !c->generic_nv)
-      launchx(c->pdl & 2, k5_exp_c<FT, 63>, dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+      launchx(c->pdl & 2, k5_exp_c<FT, 63>, dim3(c->dims.nh, 3), CT, smem_rowq<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                       (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     else
-      launchx(c->pdl & 2, k5_exp_c<FT, 0>, dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+      launchx(c->pdl & 2, k5_exp_c<FT, 0>, dim3(c->dims.nh, 3), CT, smem_rowq<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                      (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {

@@ -94,6 +94,21 @@ __device__ __forceinline__ void sgetp(const FT* s, P2<FT> (&a)[2], int j, int v)
   a[0] = P2<FT>(s[(j * 4 + 0) * LVP + v], s[(j * 4 + 1) * LVP + v]);
   a[1] = P2<FT>(s[(j * 4 + 2) * LVP + v], s[(j * 4 + 3) * LVP + v]);
 }
+// Pair-layout exchange slabs for k5_exp_a / k5_exp_c: s[(2j + p)·XLV + v] holds the pair p of row j at level v as ONE 64-bit word
+// (STS.64 / LDS.64: half the LSU instructions of the scalar slabs).  XLV = 68: the row stride 2·XLV pairs = 272 words ≡ 16 (mod 32)
+// puts the two rows of a half-warp on disjoint banks (the scalar slabs with stride 65 were 2-way conflicted).
+constexpr int XLV = 68;
+constexpr int XSLAB = 8 * XLV * 2;  // FT words per pair slab
+template <class FT>
+__device__ __forceinline__ void sputq(FT* s, const P2<FT> (&a)[2], int j, int v) {
+  P2<FT>* q = reinterpret_cast<P2<FT>*>(s);
+  q[(2 * j) * XLV + v] = a[0]; q[(2 * j + 1) * XLV + v] = a[1];
+}
+template <class FT>
+__device__ __forceinline__ void sgetq(const FT* s, P2<FT> (&a)[2], int j, int v) {
+  const P2<FT>* q = reinterpret_cast<const P2<FT>*>(s);
+  a[0] = q[(2 * j) * XLV + v]; a[1] = q[(2 * j + 1) * XLV + v];
+}
 // metric pair of component c for nodes (2p, 2p+1) of this thread's row
 #define HGP(c, p) ldpair(&hg[(c) * 16 + n0 + 2 * (p)])
 // J2·G^{ab}·(g1, g2): contravariant flux components scaled by J2 (a pointwise 2×2 metric product)
@@ -114,8 +129,8 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
   FT* sx = hg + HG_ELEM * 16;
-  FT *s_u3 = sx, *s_r = sx + SLAB, *s_u1 = sx + 2 * SLAB, *s_u2 = sx + 3 * SLAB, *s_U1 = sx + 4 * SLAB, *s_U2 = sx + 5 * SLAB,
-     *s_K = sx + 6 * SLAB, *s_X1 = sx + 7 * SLAB, *s_X2 = sx + 8 * SLAB;
+  FT *s_u3 = sx, *s_r = sx + XSLAB, *s_u1 = sx + 2 * XSLAB, *s_u2 = sx + 3 * XSLAB, *s_U1 = sx + 4 * XSLAB, *s_U2 = sx + 5 * XSLAB,
+     *s_K = sx + 6 * XSLAB, *s_X1 = sx + 7 * XSLAB, *s_X2 = sx + 8 * XSLAB;
   pdl_launch();
   B200_ROW_PROLOGUE_NV(NVC)
   ROW_COLUMNS
@@ -126,7 +141,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   V rho[2], u1[2], u2[2], re[2], u3[2], U1[2], U2[2];
   ld4q(rho, gY, nv, cv, FT(1)); ld4q(u1, gY + 16 * nv, nv, cv, FT(0)); ld4q(u2, gY + 32 * nv, nv, cv, FT(0));
   ld4q(re, gY + 48 * nv, nv, cv, FT(0)); ld4q(u3, Yf + offf, nf, fv, FT(0));
-  sputp(s_u3, u3, j, v); sputp(s_r, rho, j, v); sputp(s_u1, u1, j, v); sputp(s_u2, u2, j, v);
+  sputq(s_u3, u3, j, v); sputq(s_r, rho, j, v); sputq(s_u1, u1, j, v); sputq(s_u2, u2, j, v);
   __syncthreads();  // hg + first exchange slabs
   V c1[2], c2[2];
 #pragma unroll
@@ -135,11 +150,11 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     c2[p] = fma2(HGP(HG_GI22, p), u2[p], HGP(HG_GI12, p) * u1[p]);
     U1[p] = HGP(HG_J2, p) * c1[p]; U2[p] = HGP(HG_J2, p) * c2[p];
   }
-  sputp(s_U1, U1, j, v); sputp(s_U2, U2, j, v);
+  sputq(s_U1, U1, j, v); sputq(s_U2, U2, j, v);
   V K[2], hh[2], ss[2], sd[2], Pi[2], th[2], sE[2], u3c[2], hs_e[2], hs_d[2];
   {
     V u3h[2];
-    sgetp(s_u3, u3h, j, v < nv ? v + 1 : v);
+    sgetq(s_u3, u3h, j, v < nv ? v + 1 : v);
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       V kh = fma2(u2[p], c2[p], u1[p] * c1[p]) * L.sc;
@@ -168,7 +183,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       }
     }
   }
-  sputp(s_K, K, j, v);
+  sputq(s_K, K, j, v);
   FT* gT = Ytc + offc;
   FT* gH = H ? H + offc : nullptr;
   const bool any_visc = P.viscous && __any_sync(FULLM, L.bvc != FT(0));
@@ -279,7 +294,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     deta4p(u3, mw, vl, d3);
     dxi4p<FT, 1>(u3, d3x);
     const int vm = v > 0 ? v - 1 : 0;
-    sgetp(s_r, rl, j, vm); sgetp(s_u1, a1, j, vm); sgetp(s_u2, a2, j, vm); sgetp(s_U1, b1, j, vm); sgetp(s_U2, b2, j, vm); sgetp(s_K, kl, j, vm);
+    sgetq(s_r, rl, j, vm); sgetq(s_u1, a1, j, vm); sgetq(s_u2, a2, j, vm); sgetq(s_U1, b1, j, vm); sgetq(s_U2, b2, j, vm); sgetq(s_K, kl, j, vm);
     const bool any_v3 = P.viscous && __any_sync(FULLM, L.bvf != FT(0));
     if (any_v3) {  // β wdivₕ(gradₕ u₃) on faces (viscous_sponge.jl:64)
       V R1[2], R2[2], g1[2], g2[2];
@@ -314,11 +329,11 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
     if (fv) st4q(t3, Ytf + offf, nf);
   }
-  sputp(s_X1, X1, j, v); sputp(s_X2, X2, j, v);
+  sputq(s_X1, X1, j, v); sputq(s_X2, X2, j, v);
   __syncthreads();
   if (cv) {
     V h1[2], h2[2];
-    sgetp(s_X1, h1, j, v + 1); sgetp(s_X2, h2, j, v + 1);
+    sgetq(s_X1, h1, j, v + 1); sgetq(s_X2, h2, j, v + 1);
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       V irm = V(FT(0.5) * L.rmc * rcpn_(rho[p].lo()), FT(0.5) * L.rmc * rcpn_(rho[p].hi()));
@@ -339,7 +354,7 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
   FT* s_w = hg + HG_ELEM * 16;
-  FT* s_a = s_w + SLAB;
+  FT* s_a = s_w + XSLAB;
   pdl_launch();
   B200_ROW_PROLOGUE_NV(NVC)
   ROW_COLUMNS
@@ -403,12 +418,12 @@ k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       q[p] = (b[p] * L.sc) * HGP(HG_RJ2, p);
       w[p] = rho[p] * L.mc;
     }
-    sputp(s_w, w, j, v); sputp(s_a, q, j, v);
+    sputq(s_w, w, j, v); sputq(s_a, q, j, v);
     __syncthreads();
     if (fv) {
       V wl[2], ql[2];
       const int vm = v > 0 ? v - 1 : 0;
-      sgetp(s_w, wl, j, vm); sgetp(s_a, ql, j, vm);
+      sgetq(s_w, wl, j, vm); sgetq(s_a, ql, j, vm);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         V val;
