@@ -311,9 +311,9 @@ def main():
                     "pipeline": "3 streams (copy-in / step / copy-out), double-buffered", "finite": e2e_ok},
             "roofline": {"bound": "hbm", "kernel": "k5_exp_a<float, 63> (T_exp_T_lim! pre-DSS kernel, the largest share of the step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at he30/ze63 (114.1 + 141.1 MB), from the
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at he30/ze63 (114.1 + 141.9 MB), from the
                          # ncu --set full capture summarised in profiles/r1_ncu_full_session2_kernels.txt; scaled by elements
-                         "traffic": 255.3e6 * nh_local / 5400.0, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes,
+                         "traffic": 256.0e6 * nh_local / 5400.0, "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s"},
             "roofline_step": {"model_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms * 1e-3) / 1e9 / nranks,
                               "frac": step_bytes / (ms * 1e-3) / 1e9 / nranks / peak, "model": "54.5 S + 14 H (SURVEY.md §8d)"},
