@@ -123,7 +123,6 @@ struct b200_ctx {
   int pdl = 63;       // B200_PDL=<bit mask>: programmatic dependent launch per kernel group (1 exp_a, 2 exp_c, 4 dss2, 8 axpy, 16 imp, 32 diff); 0 = off
   int zform = 1;       // B200_ZFORM=0: the fused stepper forms T_imp[j] = (N_j − U_j)/dtγ (side stream) instead of using the stage solutions
   void *Nsc[4] = {nullptr, nullptr, nullptr, nullptr}, *Nsf[4] = {nullptr, nullptr, nullptr, nullptr};  // stage solutions N_j (zform)
-  int dbg_skip_diff = 0;  // B200_DEBUG_SKIP_TIMP=1 (timing experiments only, WRONG results): do not form T_imp
   int stiff_final = 1; // B200_STIFF_FINAL=0: literal final increment u + dt Σ b_j (T_exp[j] + T_imp[j]) in the fused path too
   int fuse_axdss = 1; // B200_FUSE_AXDSS=0: stage increment and state DSS as two passes (k_axpy_n, k_dss2) instead of k_axpy_dss
   struct StepGraph { cudaGraphExec_t exec; void *Yc, *Yf; int64_t launches; };
@@ -432,7 +431,6 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
   if (const char* e = getenv("B200_PDL")) c->pdl = atoi(e);
   if (const char* e = getenv("B200_STIFF_FINAL")) c->stiff_final = atoi(e);
-  if (const char* e = getenv("B200_DEBUG_SKIP_TIMP")) c->dbg_skip_diff = atoi(e);
   if (const char* e = getenv("B200_ZFORM")) c->zform = atoi(e);
   if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
@@ -1288,10 +1286,8 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
         sd = c->side;
       }
-      if (!c->dbg_skip_diff) {
-        if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), sd)) return -1;
-        if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), sd)) return -1;
-      }
+      if (launch_diff_scale<FT>(c, (FT*)c->Tic[i], (const FT*)Nc, (const FT*)Uc, (FT)dtg, c->nc(), sd)) return -1;
+      if (launch_diff_scale<FT>(c, (FT*)c->Tif[i], (const FT*)Nf, (const FT*)Uf, (FT)dtg, c->nf(), sd)) return -1;
       if (sd != s) { CK(cudaEventRecord(c->ev_join, sd)); }
       Uc = Nc; Uf = Nf;
     } else if (!fused) {
