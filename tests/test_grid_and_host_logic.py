@@ -145,3 +145,34 @@ def test_create_without_gpu_fails_loudly(lib):
         capi.create_context(g, params.DycoreParams(), params.DycoreNumerics())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dycore.AtmosSimulation(h_elem=2, z_elem=4)
+
+
+def test_ctypes_mirrors_match_the_c_structs(tmp_path):
+    """The drop-in boundary is plain C structs: the ctypes mirrors in capi.py (what the tests and bench.py bind through, and the
+    template for the Julia `struct` mirrors of INTEGRATION.md) must have exactly the size and field offsets gcc gives the structs of
+    include/b200_dycore.h."""
+    import ctypes as C
+    import re
+    import subprocess
+
+    from climaatmos_jl_b200 import capi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"b200_dims": capi.Dims, "b200_geometry": capi.Geometry, "b200_topology": capi.Topology, "b200_params": capi.Params,
+             "b200_cacheptrs": capi.CachePtrs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200_dycore.h"', "int main(void) {"]
+    for cname, T in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in T._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(re.findall(r"(\S+) (\d+)", out))
+    for cname, T in pairs.items():
+        assert int(got[cname]) == C.sizeof(T), cname
+        for fname, _ in T._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(T, fname).offset, f"{cname}.{fname}"
