@@ -137,6 +137,40 @@ def test_one_step_matches_oracle(FT, name, fused):
 
 
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_shallow_atmosphere_matches_oracle(FT):
+    """`deep_atmosphere: false` (SphericalGlobalGeometry, grids.jl:64-68: no (R+z)/R metric scaling, no horizontal Coriolis
+    components): explicit and implicit tendencies on a perturbed state and two steps (fused and hook-by-hook) against the oracle."""
+    sim, P = make(FT, "he3ze63", deep_atmosphere=False)
+    assert not sim.grid.deep
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    Yc0, Yf0 = sim.Y.cpu()
+    Yc, Yf, rng = perturbed_state(sim, FT)
+    Y = sim.to_device(Yc, Yf)
+    oc, of = Yc.astype(np.float64), Yf.astype(np.float64)
+    sim.dss(Y)
+    o.dss_state(oc, of)
+    sim.set_implicit_precomputed_quantities(Y)
+    pc = o.set_implicit_precomputed_quantities(oc, of)
+    Yt = Y.zeros_like()
+    sim.remaining_tendency(Yt, None, Y)
+    tc, tf = o.remaining_tendency(oc, of, pc)
+    check(*Yt.cpu(), tc, tf, tol(FT, "tend"), "shallow t_exp")
+    sim.implicit_tendency(Yt, Y)
+    ic, if_ = o.implicit_tendency(oc, of, pc)
+    gi, gif = Yt.cpu()
+    assert rel(gi[:, 0], ic[:, 0]) < tol(FT, "tend")["rho"] and rel(gi[:, 3], ic[:, 3]) < tol(FT, "tend")["rhoe"]
+    assert rel(gif, if_) < tol(FT, "tend")["u3"]
+    for fused in (True, False):
+        sim.Y = sim.to_device(Yc0, Yf0)
+        oc, of = Yc0.astype(np.float64), Yf0.astype(np.float64)
+        for _ in range(2):
+            sim.step(fused=fused)
+            oc, of = o.step(oc, of)
+        check(*sim.Y.cpu(), oc, of, tol(FT, "state"), f"shallow 2 steps fused={fused}")
+    sim.close()
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_held_suarez_config_matches_oracle(FT):
     """BASELINE.json configs[0]: dry Held–Suarez he6/ze10 (Appendix B1: z_max 55 km, dz_bottom 500 m, dt 400 s,
     no sponges, DecayingProfile initial state, rad = held_suarez): T_exp hook and two full steps."""
