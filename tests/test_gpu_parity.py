@@ -170,6 +170,36 @@ def test_shallow_atmosphere_matches_oracle(FT):
     sim.close()
 
 
+@pytest.mark.parametrize("opts", [
+    dict(energy_q_tot_upwinding="none"),            # T_post_imp! = nothing (integrator.jl:212-214)
+    dict(energy_q_tot_upwinding="first_order"),
+    dict(hyperdiff=False),                           # no ∇⁴, no DSS inside T_exp (remaining_tendency.jl:15-24)
+    dict(tracer_upwinding="none", tracers=True),
+    dict(tracer_upwinding="first_order", tracers=True),
+])
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_numerics_options_match_oracle(FT, opts):
+    """The upwinding / hyperdiffusion switches of config/default_configs/default_config.yml (energy_q_tot_upwinding,
+    tracer_upwinding ∈ none | first_order | vanleer_limiter; hyperdiff): two ARS343 steps, fused and hook-by-hook, against the oracle."""
+    kw = dict(opts)
+    if kw.pop("tracers", False):
+        kw["tracers"] = _tracer_fns()
+    sim, P = make(FT, "he3ze63", **kw)
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    Yc0, Yf0 = sim.Y.cpu()
+    for fused in (True, False):
+        sim.Y = sim.to_device(Yc0, Yf0)
+        oc, of = Yc0.astype(np.float64), Yf0.astype(np.float64)
+        for _ in range(2):
+            sim.step(fused=fused)
+            oc, of = o.step(oc, of)
+        gc, gf = sim.Y.cpu()
+        check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state"), f"{opts} fused={fused}")
+        for q in range(4, gc.shape[1]):
+            assert rel(gc[:, q], oc[:, q]) < (1e-11 if FT == np.float64 else 1e-5), f"{opts} tracer {q}"
+    sim.close()
+
+
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_held_suarez_config_matches_oracle(FT):
     """BASELINE.json configs[0]: dry Held–Suarez he6/ze10 (Appendix B1: z_max 55 km, dz_bottom 500 m, dt 400 s,
