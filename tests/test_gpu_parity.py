@@ -200,6 +200,28 @@ def test_numerics_options_match_oracle(FT, opts):
     sim.close()
 
 
+@pytest.mark.parametrize("ntr", [3, 4])
+def test_three_and_four_tracers_match_oracle(ntr):
+    """n_tracers up to the documented maximum of 4 (the DSS falls back from the specialised k_dss2 instantiations to the generic
+    k_dss beyond two tracers; the increment and tracer kernels take any count): one step, fused and hook-by-hook, Float64."""
+    fns = _tracer_fns()
+    more = [lambda lat, lon, z: 0.3 + 0.2 * np.cos(np.radians(lat)) ** 2 + 0 * lon + 0 * z,
+            lambda lat, lon, z: np.exp(-((z - 9000.0) / 4000.0) ** 2) * (1 + 0.5 * np.sin(np.radians(lon))) + 0 * lat]
+    sim, P = make(np.float64, "he4ze10", tracers=(fns + more)[:ntr], apply_sem_quasimonotone_limiter=(ntr == 4))
+    assert sim.Y.c.shape[1] == 4 + ntr
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    Yc0, Yf0 = sim.Y.cpu()
+    for fused in (True, False):
+        sim.Y = sim.to_device(Yc0, Yf0)
+        sim.step(fused=fused)
+        oc, of = o.step(Yc0.copy(), Yf0.copy())
+        gc, gf = sim.Y.cpu()
+        check(gc[:, :4], gf, oc[:, :4], of, tol(np.float64, "state"), f"{ntr} tracers fused={fused}")
+        for q in range(4, 4 + ntr):
+            assert rel(gc[:, q], oc[:, q]) < 1e-10, f"tracer {q} of {ntr}: {rel(gc[:, q], oc[:, q])}"
+    sim.close()
+
+
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_held_suarez_config_matches_oracle(FT):
     """BASELINE.json configs[0]: dry Held–Suarez he6/ze10 (Appendix B1: z_max 55 km, dz_bottom 500 m, dt 400 s,
