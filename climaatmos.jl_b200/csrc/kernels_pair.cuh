@@ -97,6 +97,9 @@ __device__ __forceinline__ void sgetp(const FT* s, P2<FT> (&a)[2], int j, int v)
 // Pair-layout exchange slabs for k5_exp_a / k5_exp_c: s[(2j + p)·XLV + v] holds the pair p of row j at level v as ONE 64-bit word
 // (STS.64 / LDS.64: half the LSU instructions of the scalar slabs).  XLV = 68: the row stride 2·XLV pairs = 272 words ≡ 16 (mod 32)
 // puts the two rows of a half-warp on disjoint banks (the scalar slabs with stride 65 were 2-way conflicted).
+#ifndef EXPC_MINB
+#define EXPC_MINB 5  // 47 registers, no spills: 5 CTAs/SM (73.2 → 70.6 µs; 6 CTAs/SM spills: 74.7 µs)
+#endif
 constexpr int XLV = 68;
 constexpr int XSLAB = 8 * XLV * 2;  // FT words per pair slab
 template <class FT>
@@ -347,7 +350,7 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
 
 // ---------------------------------------------------------------------------------------------
 template <class FT, int NVC>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? EXPC_MINB : 2))
 k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
          const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
   using V = P2<FT>;
