@@ -2,7 +2,7 @@
 the dry baroclinic wave he30/ze63 (the oracle, element-chunked over the host threads, needs a few seconds per step) — and a
 300-step soak of the fused, graph-replayed stepper (finite state, mass drift).  Writes gpurun_out/fullsize_parity.json."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import numpy as np, torch
 from concurrent.futures import ThreadPoolExecutor
 from climaatmos_jl_b200 import dycore, params as prm
