@@ -36,6 +36,11 @@ class DycoreParams:
     T_equator_dry: float = 315.0
     dtheta_z: float = 10.0
     T_min_hs: float = 200.0
+    # vertical diffusion (create_parameters.jl:327-331 vert_diff_params: C_E, H_diffusion → H, D_0_diffusion → D₀;
+    # values [UPSTREAM-RECALL], cf. toml/rcemipii_box.toml:61-65, toml/bomex_box_rhoe.toml:1-2)
+    C_E: float = 0.0044
+    H_diffusion: float = 7000.0
+    D_0_diffusion: float = 1.0
 
     @property
     def cp_d(self):
@@ -61,6 +66,14 @@ class DycoreNumerics:
     tracer_upwinding: str = "vanleer_limiter"  # default_config.yml:321-323
     apply_sem_quasimonotone_limiter: bool = False  # default_config.yml (Limiters.QuasiMonotoneLimiter in lim!, type_getters.jl:129)
     held_suarez: bool = False
+    # vertical diffusion: vert_diff ∈ {None, "VerticalDiffusion", "DecayWithHeightDiffusion"}
+    # (default_config.yml:166-168, model_getters.jl:332-358); implicit_diffusion → diff_mode (type_getters.jl:131);
+    # approximate_linear_solve_iters (default_config.yml:397-402); momentum diffusion is disabled for Held–Suarez runs
+    # (type_getters.jl:46)
+    vert_diff: str | None = None
+    implicit_diffusion: bool = False
+    approximate_linear_solve_iters: int = 1
+    disable_momentum_vertical_diffusion: bool = False
 
 
 # ARS343 tableau (Ascher–Ruuth–Spiteri 1997 §2.7), as used by ClimaTimeSteppers' IMEXAlgorithm

@@ -58,6 +58,8 @@ class Geom:
         # local (east, north) physical components ↔ contravariant: u^a = (A_k⁻¹)·(u, v)
         Ainv = np.linalg.inv(A)
         self.Ainv = c(Ainv[..., None, :, :] / s[None, None, None, :, None, None])  # [h,j,i,v,a,b]
+        # covariant ← physical: u_b = Σ_a (u, v)_a ∂x_a/∂ξ_b, with ∂x/∂ξ scaled by (R+z)/R in the deep shell
+        self.A = c(A[..., None, :, :] * s[None, None, None, :, None, None])
 
     def slice(self, sl):
         """View of the geometry restricted to the element range ``sl`` (for the multi-threaded CPU arm)."""
@@ -324,7 +326,224 @@ class Oracle:
         Ytf[:, 0] -= self.gradv_Phi - self.gradv_c2f(self.phi_r(p)) + FT(P.cp_d) * self.interp_c2f(dth) * self.gradv_c2f(self.exner(p))
         if self.N.rayleigh_sponge:
             Ytf[:, 0] += -self.beta_rayleigh(self.f.z, P.alpha_rayleigh_w) * Yf[:, 0]
+        if self.vert_diff and self.implicit_diffusion:  # implicit_tendency.jl:69-78 (diff_mode == Implicit())
+            self.vertical_diffusion_boundary_layer_tendency(Ytc, Yc, pc)
         return Ytc, Ytf
+
+    # ------------------------------------------------------------------ vertical diffusion
+    @property
+    def vert_diff(self):
+        return getattr(self.N, "vert_diff", None)
+
+    @property
+    def implicit_diffusion(self):
+        return bool(getattr(self.N, "implicit_diffusion", False))
+
+    def eddy_diffusivity(self, Yc, pc):
+        """ᶜcompute_eddy_diffusivity_coefficient (src/cache/eddy_diffusivity_coefficient.jl:16-42) with
+        eddy_diffusivity_coefficient_H / eddy_diffusivity_coefficient (src/cache/precomputed_quantities.jl:652-676).
+        K_u = K_h (vertical_diffusion_boundary_layer.jl:18, manual_sparse_jacobian.jl:984-992)."""
+        FT, P, c = self.FT, self.P, self.c
+        if self.vert_diff == "DecayWithHeightDiffusion":
+            z_sfc = self.f.z[..., :1]
+            return np.asarray(FT(P.D_0_diffusion) * np.exp(-(c.z - z_sfc) / FT(P.H_diffusion)), dtype=FT)
+        if self.vert_diff == "VerticalDiffusion":
+            u1, u2 = Yc[:, 1, ..., :1], Yc[:, 2, ..., :1]  # Fields.level(ᶜuₕ, 1)
+            g11, g12, g22 = c.g11[..., :1], c.g12[..., :1], c.g22[..., :1]
+            norm = np.sqrt(u1 * (g11 * u1 + g12 * u2) + u2 * (g12 * u1 + g22 * u2))  # LinearAlgebra.norm of a Covariant12Vector
+            z_a = FT(self.grid.dz_c[0]) / FT(2)  # Fields.Δz_field(level 1) / 2
+            K_E = FT(P.C_E) * norm * z_a
+            p = pc["p"]
+            p_pbl, p_strato = FT(85000), FT(10000)
+            return np.asarray(np.where(p > p_pbl, K_E, K_E * np.exp(-(((p_pbl - p) / p_strato) ** 2))), dtype=FT)
+        raise ValueError(f"vert_diff = {self.vert_diff!r}")
+
+    def _rhoK_face(self, Yc, pc):
+        """ᶠρK = ᶠinterp(ρ) / ᶠinterp(1 / max(K_h, ε)) — harmonic-mean face diffusivity
+        (vertical_diffusion_boundary_layer.jl:86-90; manual_sparse_jacobian.jl:1078-1082)."""
+        eps = np.finfo(self.FT).eps
+        K = self.eddy_diffusivity(Yc, pc)
+        return self.interp_c2f(Yc[:, 0]) / self.interp_c2f(self.FT(1) / np.maximum(K, eps))
+
+    def diffdiv_f2c(self, F3):
+        """ᶜdiffdivᵥ (abbreviations.jl:124-135) of a covariant-3 face flux: SetValue(C3(0)) at both boundaries;
+        the divergence acts on the contravariant component g³³ F₃."""
+        return self.advdiv_f2c(self.f.g33 * F3)
+
+    def vertical_diffusion_boundary_layer_tendency(self, Ytc, Yc, pc):
+        """vertical_diffusion_boundary_layer_tendency! (src/prognostic_equations/vertical_diffusion_boundary_layer.jl:64-154),
+        dry branch + passive tracers; ADDS into Ytc.  Called from additional_tendency! (remaining_tendency.jl:185-195) when
+        diffusion is explicit, from implicit_tendency! otherwise."""
+        FT, P, c, f = self.FT, self.P, self.c, self.f
+        rho = Yc[:, 0]
+        rhoK = self._rhoK_face(Yc, pc)
+        if not getattr(self.N, "disable_momentum_vertical_diffusion", False):
+            # :91-96  uₕₜ −= C12(ᶜdivᵥ(−2 ᶠρK ᶠstrain_rate) / ρ), strain rate of UVW(ᶜu) (utilities.jl:251-262):
+            # ε = (G + Gᵀ)/2 with G[w, b] = ∂(u, v, w)_b/∂z on interior faces, zero on the boundary faces (SetGradient(0)).
+            # The vertical divergence contracts the w index: (divᵥ τ)_b = (1/J) δ(J τ_wb / (∂z/∂ξ³)), and ε_wb = ½ ∂(u,v)_b/∂z for
+            # the two horizontal components, which are all C12 keeps on a flat grid.
+            A = c.A
+            Ai = c.Ainv
+            up = [Ai[..., 0, a] * Yc[:, 1] + Ai[..., 1, a] * Yc[:, 2] for a in range(2)]  # physical (u, v) = A⁻ᵀ uₕ
+            dzf = np.asarray(np.broadcast_to(self.grid.dz_f, f.J.shape), dtype=FT)
+            dv = []
+            for a in range(2):
+                strain = FT(0.5) * self.gradv_c2f(up[a]) / dzf  # ε_wa on faces (W component: covariant / (∂z/∂ξ³))
+                tau = -FT(2) * rhoK * strain
+                Jt = f.J * (tau / dzf)  # contravariant-3 part of the w index
+                dv.append((Jt[..., 1:] - Jt[..., :-1]) / c.J / rho)  # ᶜdivᵥ has no BCs; the boundary strain is already 0
+            for b in range(2):
+                Ytc[:, 1 + b] -= A[..., 0, b] * dv[0] + A[..., 1, b] * dv[1]
+        # :101-102  ρe_totₜ −= ᶜdiffdivᵥ(−(ᶠρK ᶠgradᵥ(dry_static_energy(T, Φ))))
+        s_d = FT(P.cp_d) * (pc["T"] - FT(P.T_0)) + self.Phi
+        Ytc[:, 3] -= self.diffdiv_f2c(-(rhoK * self.gradv_c2f(s_d)))
+        # :150-153 passive grid-scale tracers
+        for q in range(4, Yc.shape[1]):
+            Ytc[:, q] -= self.diffdiv_f2c(-(rhoK * self.gradv_c2f(Yc[:, q] / rho)))
+
+    def update_diffusion_jacobian(self, Jm, Yc, pc, dtg):
+        """update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261), dry non-EDMF branch.  Tridiagonal centre→centre
+        blocks stored as (lo, d, hi) with lo[..., 0] = hi[..., -1] = 0.  ᶜdiffusion_h_matrix = ᶜadvdivᵥ_matrix ⋅ Diag(ᶠρK) ⋅
+        ᶠgradᵥ_matrix (:1078-1084); K_u = K_h so ᶜdiffusion_u_matrix is the same matrix (:1096-1100)."""
+        FT, P, c, f = self.FT, self.P, self.c, self.f
+        dtg = FT(dtg)
+        rho = Yc[:, 0]
+        w = f.J * f.g33 * self._rhoK_face(Yc, pc)
+        w[..., 0] = 0
+        w[..., -1] = 0
+        lo, hi = w[..., :-1] / c.J, w[..., 1:] / c.J  # columns k-1 and k+1 of row k
+        d = -(lo + hi)
+        z = np.zeros_like(rho[..., :1])
+        left = lambda a: np.concatenate([z, a[..., :-1]], -1)  # value at k-1
+        right = lambda a: np.concatenate([a[..., 1:], z], -1)  # value at k+1
+
+        def scaled_cols(sc):  # dtγ · D · Diag(sc) − I
+            return (dtg * lo * left(sc), dtg * d * sc - FT(1), dtg * hi * right(sc))
+
+        out = dict(rhoe_rhoe=scaled_cols(FT(P.cp_d) / (FT(P.cv_d) * rho)))  # :1129-1131 (cv_m = cv_d when dry)
+        out["tracer"] = scaled_cols(FT(1) / rho) if Yc.shape[1] > 4 else None  # :1190-1195
+        if not getattr(self.N, "disable_momentum_vertical_diffusion", False):  # :1252-1258  dtγ Diag(1/ρ) ⋅ D_u − I
+            out["uh_uh"] = (dtg * lo / rho, dtg * d / rho - FT(1), dtg * hi / rho)
+        else:
+            out["uh_uh"] = None
+        Jm["diff"] = out
+        return Jm
+
+    @staticmethod
+    def _tri_solve(tri, rhs):
+        """Thomas algorithm along the last axis (ClimaCore single_field_solver.jl tridiagonal case [UPSTREAM-RECALL])."""
+        l, d, u = tri
+        n = rhs.shape[-1]
+        cp, dp = np.zeros_like(rhs), np.zeros_like(rhs)
+        cp[..., 0] = u[..., 0] / d[..., 0]
+        dp[..., 0] = rhs[..., 0] / d[..., 0]
+        for i in range(1, n):
+            den = d[..., i] - l[..., i] * cp[..., i - 1]
+            cp[..., i] = u[..., i] / den
+            dp[..., i] = (rhs[..., i] - l[..., i] * dp[..., i - 1]) / den
+        x = np.zeros_like(rhs)
+        x[..., -1] = dp[..., -1]
+        for i in range(n - 2, -1, -1):
+            x[..., i] = dp[..., i] - cp[..., i] * x[..., i + 1]
+        return x
+
+    @staticmethod
+    def _tri_mul(tri, x):
+        l, d, u = tri
+        y = d * x
+        y[..., 1:] += l[..., 1:] * x[..., :-1]
+        y[..., :-1] += u[..., :-1] * x[..., 1:]
+        return y
+
+    def ldiv_iterative(self, Jm, Rc, Rf):
+        """ldiv! with implicit diffusion: ApproximateBlockArrowheadIterativeSolve(ρ, ρe_tot; alg₁ = BlockLowerTriangularSolve(ρ),
+        alg₂ = BlockLowerTriangularSolve(uₕ), P_alg₁ = MainDiagonalPreconditioner(), n_iters)
+        (manual_sparse_jacobian.jl:538-578) [UPSTREAM-RECALL ClimaCore 0.15.1 MatrixFields/field_matrix_solver.jl]:
+        a SchurComplementReductionSolve — x₂ solves (A₂₂ − A₂₁A₁₁⁻¹A₁₂) x₂ = b₂ − A₂₁A₁₁⁻¹b₁ by a StationaryIterativeSolve
+        x ← x + P⁻¹(b − S x) started from x = P⁻¹ b, with P = A₂₂ − A₂₁ diag(A₁₁)⁻¹ A₁₂ solved block-lower-triangularly
+        (uₕ first); then x₁ = A₁₁⁻¹(b₁ − A₁₂x₂).  names₁ = (ρ, ρe_tot): A_ρρ = −I, A_ρe,ρ = 0, A_ρe,ρe tridiagonal;
+        names₂ = (passive tracers, uₕ, u₃): passive tracers and uₕ do not couple to names₁ on a flat grid, so their
+        tridiagonal solves are exact at x[0]."""
+        FT = self.FT
+        D = Jm["diff"]
+        n_iters = int(getattr(self.N, "approximate_linear_solve_iters", 1))
+        dYc, dYf = np.zeros_like(Rc), np.zeros_like(Rf)
+        Rrho, R1, R2, Rre, R3 = Rc[:, 0], Rc[:, 1], Rc[:, 2], Rc[:, 3], Rf[:, 0]
+        cl = lambda a: np.concatenate([a[..., :1] * 0, a], -1)
+        ch = lambda a: np.concatenate([a, a[..., -1:] * 0], -1)
+        f2 = lambda a21, r: a21[0] * cl(r) + a21[1] * ch(r)  # face-row bidiagonal block · centre vector
+        c2 = lambda a12, x: a12[0] * x[..., :-1] + a12[1] * x[..., 1:]  # centre-row bidiagonal block · face vector
+        Aee = D["rhoe_rhoe"]
+        # uₕ and passive tracers: (uₕ,uₕ) / (ρχ,ρχ) tridiagonal or the −I fallback
+        if D["uh_uh"] is not None:
+            x1, x2 = self._tri_solve(D["uh_uh"], R1), self._tri_solve(D["uh_uh"], R2)
+        else:
+            x1, x2 = -R1, -R2
+        dYc[:, 1], dYc[:, 2] = x1, x2
+        for q in range(4, Rc.shape[1]):
+            dYc[:, q] = self._tri_solve(D["tracer"], Rc[:, q])
+        # Schur right-hand side for u₃ and the lower-triangular coupling to uₕ
+        b3 = R3 - f2(Jm["u3_rho"], -Rrho) - f2(Jm["u3_rhoe"], self._tri_solve(Aee, Rre))
+        b3 = b3 - f2(Jm["u3_uh"][0], x1) - f2(Jm["u3_uh"][1], x2)
+        A33 = Jm["u3_u3"]
+
+        def schur_mul(x):  # (A₃₃ − A₃ρ A_ρρ⁻¹ A_ρ3 − A₃e A_ee⁻¹ A_e3) x
+            return self._tri_mul(A33, x) - f2(Jm["u3_rho"], -c2(Jm["rho_u3"], x)) - f2(Jm["u3_rhoe"], self._tri_solve(Aee, c2(Jm["rhoe_u3"], x)))
+
+        # preconditioner: A₁₁ replaced by its main diagonal (−1 for ρ, d_ee for ρe_tot) → tridiagonal
+        l, d, u = [a.copy() for a in A33]
+        for a21, a12, dinv in ((Jm["u3_rho"], Jm["rho_u3"], -np.ones_like(Rrho)), (Jm["u3_rhoe"], Jm["rhoe_u3"], FT(1) / Aee[1])):
+            lo21, hi21 = a21
+            lo12, hi12 = a12[0] * dinv, a12[1] * dinv
+            l -= lo21 * cl(lo12)
+            d -= lo21 * cl(hi12) + hi21 * ch(lo12)
+            u -= hi21 * ch(hi12)
+        P33 = (l, d, u)
+        x3 = self._tri_solve(P33, b3)
+        for _ in range(n_iters):
+            x3 = x3 + self._tri_solve(P33, b3 - schur_mul(x3))
+        dYf[:, 0] = x3
+        dYc[:, 0] = -(Rrho - c2(Jm["rho_u3"], x3))
+        dYc[:, 3] = self._tri_solve(Aee, Rre - c2(Jm["rhoe_u3"], x3))
+        return dYc, dYf
+
+    def jacobian_dense_column(self, Jm, h, j, i, ntr=0):
+        """Test helper: the full Jacobian of one column as a dense matrix over (ρ, uₕ₁, uₕ₂, ρe_tot, tracers…, u₃)."""
+        nv = self.nv
+        nc = 4 + ntr
+        N = nc * nv + nv + 1
+        M = np.zeros((N, N))
+        o = lambda q: q * nv
+        o3 = nc * nv
+        sel = lambda a: np.asarray(a[h, j, i], dtype=np.float64)
+        D = Jm.get("diff")
+        for q in range(nc):
+            M[o(q) : o(q) + nv, o(q) : o(q) + nv] = -np.eye(nv)
+        if D is not None:
+            def put_tri(q, tri):
+                l, d, u = [sel(a) for a in tri]
+                B = np.diag(d) + np.diag(l[1:], -1) + np.diag(u[:-1], 1)
+                M[o(q) : o(q) + nv, o(q) : o(q) + nv] = B
+            put_tri(3, D["rhoe_rhoe"])
+            if D["uh_uh"] is not None:
+                put_tri(1, D["uh_uh"]); put_tri(2, D["uh_uh"])
+            for q in range(4, nc):
+                put_tri(q, D["tracer"])
+        for q, key in ((0, "rho_u3"), (3, "rhoe_u3")):
+            lo, hi = [sel(a) for a in Jm[key]]
+            for k in range(nv):
+                M[o(q) + k, o3 + k] += lo[k]
+                M[o(q) + k, o3 + k + 1] += hi[k]
+        for q, blk in ((0, Jm["u3_rho"]), (3, Jm["u3_rhoe"]), (1, Jm["u3_uh"][0]), (2, Jm["u3_uh"][1])):
+            lo, hi = [sel(a) for a in blk]
+            for fidx in range(nv + 1):
+                if fidx > 0:
+                    M[o3 + fidx, o(q) + fidx - 1] += lo[fidx]
+                if fidx < nv:
+                    M[o3 + fidx, o(q) + fidx] += hi[fidx]
+        l, d, u = [sel(a) for a in Jm["u3_u3"]]
+        M[o3:, o3:] = np.diag(d) + np.diag(l[1:], -1) + np.diag(u[:-1], 1)
+        return M
 
     def correct_implicit_advection_tendency(self, Yc, Yf, pc):
         """implicit_tendency.jl:322-339 (T_post_imp!)."""
@@ -398,13 +617,18 @@ class Oracle:
         u = X_hi * ch(dKhi)  # via centre f → face f+1
         beta = self.beta_rayleigh(f.z, P.alpha_rayleigh_w) if self.N.rayleigh_sponge else z(rf)
         A_u3_u3 = (dtg * l, dtg * (d - beta) - FT(1), dtg * u)
-        return dict(rho_u3=A_rho_u3, rhoe_u3=A_rhoe_u3, u3_rho=A_u3_rho, u3_rhoe=A_u3_rhoe, u3_uh=A_u3_uh, u3_u3=A_u3_u3)
+        Jm = dict(rho_u3=A_rho_u3, rhoe_u3=A_rhoe_u3, u3_rho=A_u3_rho, u3_rhoe=A_u3_rhoe, u3_uh=A_u3_uh, u3_u3=A_u3_u3)
+        if self.vert_diff and self.implicit_diffusion:  # diffusion_flag = DerivativeFlag(atmos.diff_mode) (:88)
+            self.update_diffusion_jacobian(Jm, Yc, pc, dtg)
+        return Jm
 
     def ldiv(self, Jm, Rc, Rf):
         """jacobian.jl:78-82 → BlockArrowheadSolve(ρ, ρe_tot; alg₂ = BlockLowerTriangularSolve(uₕ))
         (manual_sparse_jacobian.jl:579-584) [UPSTREAM-RECALL]: Schur complement onto u₃, Thomas
         solve, back-substitution.  Scalar diagonal blocks are -I, (uₕ,uₕ) = -I (:476-481)."""
         FT = self.FT
+        if "diff" in Jm:  # use_derivative(diffusion_flag) → ApproximateBlockArrowheadIterativeSolve (:538-578)
+            return self.ldiv_iterative(Jm, Rc, Rf)
         dYc, dYf = np.zeros_like(Rc), np.zeros_like(Rf)
         Rrho, R1, R2, Rre = Rc[:, 0], Rc[:, 1], Rc[:, 2], Rc[:, 3]
         R3 = Rf[:, 0]
@@ -725,6 +949,8 @@ class Oracle:
             gs = self.grad(cp_d * (T - FT(P.T_0)) + self.Phi)
             gs = self.ct12(gs[0], gs[1], c)
             Ytc[:, 3] += bc * self.wdiv(rho * gs[0], rho * gs[1], c)
+        if self.vert_diff and not self.implicit_diffusion:  # remaining_tendency.jl:185-195 (diff_mode == Explicit())
+            self.vertical_diffusion_boundary_layer_tendency(Ytc, Yc, pc)
         return Ytc, Ytf, L
 
     # ------------------------------------------------------------------ ARS343 step
