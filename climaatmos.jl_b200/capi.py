@@ -48,7 +48,9 @@ class Params(C.Structure):
         ("alpha_rayleigh_uh", C.c_double), ("alpha_rayleigh_w", C.c_double), ("viscous_sponge", C.c_int32),
         ("zd_viscous", C.c_double), ("kappa_2_sponge", C.c_double), ("energy_upwinding", C.c_int32),
         ("tracer_upwinding", C.c_int32), ("held_suarez", C.c_int32)] + [(n, C.c_double) for n in ("hs_day", "hs_sigma_b", "hs_dT_y", "hs_T_equator",
-                                                               "hs_dtheta_z", "hs_T_min", "MSLP")] + [("sem_quasimonotone_limiter", C.c_int32)]
+                                                               "hs_dtheta_z", "hs_T_min", "MSLP")] + [("sem_quasimonotone_limiter", C.c_int32)] + [
+        (n, C.c_int32) for n in ("vert_diff", "implicit_diffusion", "approximate_linear_solve_iters",
+                                 "disable_momentum_vertical_diffusion")] + [(n, C.c_double) for n in ("C_E", "H_diffusion", "D_0_diffusion")]
 
 
 class CachePtrs(C.Structure):
@@ -137,7 +139,12 @@ def make_params(P, N, grid) -> Params:
         viscous_sponge=int(N.viscous_sponge), zd_viscous=P.zd_viscous, kappa_2_sponge=P.kappa_2_sponge,
         energy_upwinding=up, tracer_upwinding={"none": 0, "first_order": 1, "vanleer_limiter": 3}[N.tracer_upwinding], held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
         hs_T_equator=P.T_equator_dry, hs_dtheta_z=P.dtheta_z, hs_T_min=P.T_min_hs, MSLP=P.MSLP,
-        sem_quasimonotone_limiter=int(getattr(N, "apply_sem_quasimonotone_limiter", False)))
+        sem_quasimonotone_limiter=int(getattr(N, "apply_sem_quasimonotone_limiter", False)),
+        vert_diff={None: 0, "VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[getattr(N, "vert_diff", None)],
+        implicit_diffusion=int(getattr(N, "implicit_diffusion", False)),
+        approximate_linear_solve_iters=int(getattr(N, "approximate_linear_solve_iters", 1)),
+        disable_momentum_vertical_diffusion=int(getattr(N, "disable_momentum_vertical_diffusion", False)),
+        C_E=getattr(P, "C_E", 0.0), H_diffusion=getattr(P, "H_diffusion", 1.0), D_0_diffusion=getattr(P, "D_0_diffusion", 0.0))
 
 
 def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1, n_tracers: int = 0):

@@ -21,6 +21,7 @@
 #include "kernels_pair.cuh"
 #include "kernels_imp5.cuh"
 #include "kernels_limiter.cuh"
+#include "kernels_vdiff.cuh"
 
 using namespace b200;
 
@@ -93,6 +94,8 @@ struct b200_ctx {
   int32_t* d_lim_ghost_node = nullptr;  // per ghost element: a node whose column this rank receives
   void* Tlc[4] = {nullptr, nullptr, nullptr, nullptr};  // T_lim of the four stages (stepper, limiter on)  // records [d_node_off[e], d_node_off[e+1]) are owned by local element e
   void* d_jac = nullptr;
+  void* d_jacd = nullptr;  // vertical-diffusion Jacobian planes (k_vdiff_jac)
+  void* d_kdec = nullptr;  // [LV] DecayWithHeightDiffusion K(z_c)
   // native stepper storage (allocated lazily)
   void *Uc[2] = {nullptr, nullptr}, *Uf[2] = {nullptr, nullptr};
   void *Tec[4] = {}, *Tef[4] = {}, *Tic[4] = {}, *Tif[4] = {};
@@ -118,6 +121,7 @@ struct b200_ctx {
   int** d_p2p_flags = nullptr;  // device array [n_neighbors]: address of my flag in neighbour q
   int *d_slot_nbr = nullptr, *d_slot_dst = nullptr, *d_nbr_nhg = nullptr, *d_nbr_rank = nullptr;
   int64_t launches = 0;
+  double dz_sfc = 0;  // Δz of the lowest cell (VerticalDiffusion: z_a = Δz/2)
   // CUDA graph of one fused step (single-rank contexts): captured on the second call with the same (Yc, Yf, stream)
   int use_graph = 1;  // B200_GRAPH=0 disables
   int pdl = 63;       // B200_PDL=<bit mask>: programmatic dependent launch per kernel group (1 exp_a, 2 exp_c, 4 dss2, 8 axpy, 16 imp, 32 diff); 0 = off
@@ -271,6 +275,13 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
     }
   CK(cudaMalloc(&c->d_vlev, sizeof(V)));
   CK(cudaMemcpy(c->d_vlev, &V, sizeof(V), cudaMemcpyHostToDevice));
+  if (p->vert_diff) {  // eddy_diffusivity_coefficient_H (precomputed_quantities.jl:652-654): D₀ exp(−(z − z_sfc)/H)
+    FT kd[LV];
+    for (int v = 0; v < LV; ++v) kd[v] = v < nv ? (FT)(p->D_0_diffusion * exp(-(G->z_c[v] - G->z_f[0]) / p->H_diffusion)) : (FT)0;
+    CK(cudaMalloc(&c->d_kdec, sizeof(kd)));
+    CK(cudaMemcpy(c->d_kdec, kd, sizeof(kd), cudaMemcpyHostToDevice));
+    c->dz_sfc = G->dz_c[0];
+  }
   {  // derivative matrices in the constant bank (register-resident kernels)
     float mf[32]; double md[32];
     for (int k = 0; k < 16; ++k) { md[k] = (double)V.D[k]; md[16 + k] = (double)V.Dw[k]; mf[k] = (float)V.D[k]; mf[16 + k] = (float)V.Dw[k]; }
@@ -379,6 +390,18 @@ static int create_geo(b200_ctx* c, const b200_geometry* G, const b200_params* p)
 }
 
 // shared-memory footprints (bytes)
+template <class FT>
+static VDiff<FT> make_vdiff(const b200_ctx* c) {
+  const b200_params& p = c->prm;
+  VDiff<FT> D;
+  D.mode = p.vert_diff; D.momentum = !p.disable_momentum_vertical_diffusion; D.n_iters = p.approximate_linear_solve_iters;
+  D.ce_za = (FT)(p.C_E * c->dz_sfc / 2); D.eps = sizeof(FT) == 4 ? (FT)1.1920928955078125e-7 : (FT)2.220446049250313e-16;
+  D.cpcv = (FT)(p.cp_d / p.cv_d); D.kdec = (const FT*)c->d_kdec;
+  return D;
+}
+static bool vdiff_implicit(const b200_ctx* c) { return c->prm.vert_diff != 0 && c->prm.implicit_diffusion != 0; }
+static bool vdiff_explicit(const b200_ctx* c) { return c->prm.vert_diff != 0 && c->prm.implicit_diffusion == 0; }
+
 template <class FT> static size_t smem_base() { return sizeof(VLev<FT>) + HG_ELEM * 16 * sizeof(FT); }
 template <class FT> static size_t smem_slabs(int n) { return smem_base<FT>() + (size_t)n * SLAB * sizeof(FT); }
 
@@ -408,6 +431,9 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k_ldiv<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_t_post_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
   CK(cudaFuncSetAttribute(k_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(18)));
+  CK(cudaFuncSetAttribute(k_vdiff_tend<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
+  CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
+  CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_texp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(22)));
   CK(cudaFuncSetAttribute(k_texp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
   return 0;
@@ -420,6 +446,10 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (d->nv + 1 > LV || d->nv < 2) return fail("b200_create: need 2 <= nv <= 63");
   if (d->ft_bytes != 4 && d->ft_bytes != 8) return fail("b200_create: ft_bytes must be 4 or 8");
   if (d->n_tracers < 0 || d->n_tracers > 4) return fail("b200_create: 0 <= n_tracers <= 4");
+  if (p->vert_diff < 0 || p->vert_diff > 2) return fail("b200_create: vert_diff must be 0 (none), 1 (VerticalDiffusion) or 2 (DecayWithHeightDiffusion)");
+  if (p->implicit_diffusion && !p->vert_diff)
+    return fail("b200_create: implicit_diffusion needs a vert_diff model (the reference's update_diffusion_jacobian! has no diffusivity otherwise)");
+  if (p->vert_diff && p->approximate_linear_solve_iters < 0) return fail("b200_create: approximate_linear_solve_iters < 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("b200_create: no CUDA device (this library has no CPU fallback)");
@@ -535,7 +565,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off); fr(c->d_lim_nbr_off); fr(c->d_lim_nbr); fr(c->d_lim_bnd); fr(c->d_lim_E); fr(c->d_lim_ghost_node);
   for (int i = 0; i < 4; ++i) fr(c->Tlc[i]);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
-  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->H);
+  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->d_jacd); fr(c->d_kdec); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Nsc[i]); fr(c->Nsf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
@@ -587,11 +617,21 @@ extern "C" int b200_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cachep
   return c->ft == 4 ? impl_cache_imp<float>(c, Yc, Yf, o, (cudaStream_t)stream) : impl_cache_imp<double>(c, Yc, Yf, o, (cudaStream_t)stream);
 }
 
+// Yₜ.c += vertical_diffusion_boundary_layer_tendency!(Y)  (kernels_vdiff.cuh)
+template <class FT>
+static int launch_vdiff_tend(b200_ctx* c, void* Ytc, const void* Yc, const void* Yf, cudaStream_t s) {
+  k_vdiff_tend<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                            (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT*)Ytc);
+  LAUNCH_CHECK(c);
+  return 0;
+}
+
 template <class FT>
 static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
   k_t_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                        (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
+  if (vdiff_implicit(c)) return launch_vdiff_tend<FT>(c, Ytc, Yc, Yf, s);  // implicit_tendency.jl:69-78
   return 0;
 }
 extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
@@ -604,6 +644,13 @@ static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, c
   k_wfact<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                        (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
   LAUNCH_CHECK(c);
+  if (vdiff_implicit(c)) {  // update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261)
+    if (!c->d_jacd) CK(cudaMalloc(&c->d_jacd, (size_t)c->dims.nh * JD_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
+    k_vdiff_jac<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                             (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT)dtg,
+                                                             (FT*)c->d_jacd);
+    LAUNCH_CHECK(c);
+  }
   return 0;
 }
 extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, double, void* stream) {
@@ -613,6 +660,14 @@ extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dt
 template <class FT>
 static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, cudaStream_t s) {
   if (!c->d_jac) return fail("b200_ldiv: b200_wfact has not been called");
+  if (vdiff_implicit(c)) {  // ApproximateBlockArrowheadIterativeSolve (manual_sparse_jacobian.jl:538-578)
+    if (!c->d_jacd) return fail("b200_ldiv: b200_wfact has not been called");
+    k_ldiv_diff<FT><<<c->dims.nh, NT, (22 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
+                                                                 (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
+                                                                 (const FT*)Rf, (FT*)dYc, (FT*)dYf);
+    LAUNCH_CHECK(c);
+    return 0;
+  }
   k_ldiv<FT><<<c->dims.nh, NT, 8 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
                                                          (FT*)dYc, (FT*)dYf);
   LAUNCH_CHECK(c);
@@ -978,6 +1033,7 @@ static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, c
   if (c->dims.n_tracers > 0 && c->exp_kernel != 5) return fail("passive tracers need B200_EXP_KERNEL=5 (default)");
   for (int ph = 0; ph < 3; ++ph)
     if (impl_t_exp_phase<FT>(c, ph, Ytc, Ytf, Yc, Yf, s, Ylc)) return -1;
+  if (vdiff_explicit(c)) return launch_vdiff_tend<FT>(c, Ytc, Yc, Yf, s);  // additional_tendency! (remaining_tendency.jl:185-195)
   return 0;
 }
 extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, double,
@@ -1152,6 +1208,7 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
   return 0;
 }
 extern "C" int b200_implicit_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtgamma, void* stream) {
+  if (c && vdiff_implicit(c)) return fail("b200_implicit_stage: implicit vertical diffusion is served by the hook entry points (b200_wfact, b200_t_imp, b200_ldiv)");
   return c->ft == 4 ? impl_imp_stage<float>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream)
                     : impl_imp_stage<double>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream);
 }
@@ -1327,6 +1384,9 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
 }
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  // implicit vertical diffusion: the fused implicit-stage kernel does not carry the diffusion blocks yet — the stage runs through
+  // the hook sequence (cache_imp!, Wfact, T_imp!, ldiv!, T_post_imp!) of the literal path
+  if (vdiff_implicit(c)) fused = 0;
   auto run = [&](cudaStream_t q) { return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, q) : impl_step<double>(c, Yc, Yf, fused, q); };
   // One CUDA graph per state buffer: ≈35 kernel launches, the side-stream fork/join and the memsets replay as one launch.
   // Multi-rank contexts replay too when the halo runs over peer memory (its exchange number lives in device memory); the NCCL

@@ -1,0 +1,342 @@
+// kernels_vdiff.cuh — vertical (K-theory) diffusion and the approximate arrowhead solve that implicit diffusion switches on
+// (SURVEY.md §8f n2), hook level, one element (16 columns) per CTA in the slab layout of kernels_implicit.cuh.
+//
+//   k_vdiff_tend   vertical_diffusion_boundary_layer_tendency!  (src/prognostic_equations/vertical_diffusion_boundary_layer.jl:64-154,
+//                  dry branch + passive tracers) — ADDS to Yₜ.c; appended to T_exp (diff_mode Explicit, remaining_tendency.jl:185-195)
+//                  or to T_imp (diff_mode Implicit, implicit/implicit_tendency.jl:69-78)
+//   k_vdiff_jac    update_diffusion_jacobian!  (implicit/manual_sparse_jacobian.jl:1031-1261, dry non-EDMF branch): two planes per
+//                  element, dtγ·(J g³³ ᶠρK)/J2 on faces and 1/ρ at centres — every tridiagonal block of the reference is a row or
+//                  column scaling of ᶜadvdivᵥ_matrix ⋅ Diag(ᶠρK) ⋅ ᶠgradᵥ_matrix, so the blocks themselves are never stored
+//   k_ldiv_diff    ldiv! with ApproximateBlockArrowheadIterativeSolve(ρ, ρe_tot; alg₁ = BlockLowerTriangularSolve(ρ),
+//                  alg₂ = BlockLowerTriangularSolve(uₕ), P_alg₁ = MainDiagonalPreconditioner(), n_iters)
+//                  (manual_sparse_jacobian.jl:538-578; ClimaCore MatrixFields field_matrix_solver.jl [UPSTREAM-RECALL])
+//
+// Eddy diffusivity (src/cache/eddy_diffusivity_coefficient.jl:16-42, src/cache/precomputed_quantities.jl:652-676): K_u = K_h;
+// DecayWithHeightDiffusion K = D₀ exp(−(z − z_sfc)/H) (host table per level), VerticalDiffusion K = C_E |uₕ(level 1)| Δz₁/2 below
+// 850 hPa, Gaussian taper in pressure above.  Face value: harmonic mean ᶠinterp(ρ)/ᶠinterp(1/max(K, ε)).
+//
+// Metric factors: J_f g³³_f / J2 = s_f²/Δz_f and J_c/J2 = s_c² Δz_c (VLev::mc), the horizontal Jacobian cancels; the physical
+// wind is A⁻ᵀuₕ with A = s_c·A₂D, so on the flat deep shell the momentum diffusion acts on uₕ/s_c and A₂D cancels as well.
+#pragma once
+#include "kernels_implicit.cuh"
+
+namespace b200 {
+
+enum { JD_PW = 0, JD_IRHO, JD_N };  // planes written by k_vdiff_jac, each [16][Nv+1] per element
+
+template <class FT>
+struct VDiff {
+  int mode;      // 1 VerticalDiffusion, 2 DecayWithHeightDiffusion
+  int momentum;  // !disable_momentum_vertical_diffusion
+  int n_iters;   // approximate_linear_solve_iters
+  FT ce_za;      // C_E · Δz(level 1)/2
+  FT eps;        // eps(FT)
+  FT cpcv;       // cp_d / cv_d  (∂s_d/∂e_tot, manual_sparse_jacobian.jl:1129-1131 with cv_m = cv_d)
+  const FT* kdec;  // [LV] D₀ exp(−(z_c − z_sfc)/H)
+};
+
+// K_h at the centres of the element → kh; needs S.rho, S.u1, S.u2, S.T.
+template <class FT>
+__device__ __forceinline__ void vdiff_kh(const Par<FT>& P, const VDiff<FT>& D, const FT* hg, const VLev<FT>& V,
+                                         const ImpSlabs<FT>& S, FT* kh) {
+  const int nv = P.nv;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v >= nv) continue;
+    int o = n * LVP + v;
+    FT K;
+    if (D.mode == 2) {
+      K = D.kdec[v];
+    } else {
+      FT a = S.u1[n * LVP], b = S.u2[n * LVP];  // Fields.level(ᶜuₕ, 1)
+      FT g11 = hg[HG_GI11 * 16 + n], g12 = hg[HG_GI12 * 16 + n], g22 = hg[HG_GI22 * 16 + n];
+      FT nrm = sqrt((a * (g11 * a + g12 * b) + b * (g12 * a + g22 * b)) * V.sc2i[0]);
+      FT KE = D.ce_za * nrm;
+      FT p = S.rho[o] * P.R_d * S.T[o];
+      FT x = (FT(85000) - p) / FT(10000);
+      K = p > FT(85000) ? KE : KE * exp_(-(x * x));
+    }
+    kh[o] = K;
+  }
+}
+
+// scale · (J g³³ ᶠρK)/J2 on the faces of the element → pw (zero on the boundary faces: ᶜdiffdivᵥ / ᶠgradᵥ boundary conditions)
+template <class FT>
+__device__ __forceinline__ void vdiff_pw(const Par<FT>& P, const VDiff<FT>& D, const VLev<FT>& V, const ImpSlabs<FT>& S,
+                                         const FT* kh, FT* pw, FT scale) {
+  const int nv = P.nv, nf = nv + 1;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, f = idx & 63;
+    if (f >= nf) continue;
+    int o = n * LVP + f;
+    FT w = FT(0);
+    if (f > 0 && f < nv) {
+      FT rf = FT(0.5) * (S.rho[o - 1] + S.rho[o]);
+      FT ik = FT(0.5) * (FT(1) / fmax_(kh[o - 1], D.eps) + FT(1) / fmax_(kh[o], D.eps));
+      w = scale * (V.dzf[f] * V.g33f[f] / V.sf2i[f]) * (rf / ik);
+    }
+    pw[o] = w;
+  }
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_vdiff_tend(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
+                                                   const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+                                                   const FT* __restrict__ Yf, FT* Ytc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  ImpSlabs<FT> S; imp_carve(sm, S);
+  FT* kh = sm.take(SLAB); FT* pw = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv;
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
+  __syncthreads();
+  imp_thermo(P, hg, V, S);
+  __syncthreads();
+  vdiff_kh(P, D, hg, V, S, kh);
+  __syncthreads();
+  vdiff_pw(P, D, V, S, kh, pw, FT(1));
+  __syncthreads();
+  const FT* gY = Yc + (size_t)h * P.ncf * 16 * nv;
+  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v >= nv) continue;
+    const int o = n * LVP + v;
+    const bool lo = v > 0, hi = v < nv - 1;
+    const FT wl = lo ? pw[o] : FT(0), wh = hi ? pw[o + 1] : FT(0);
+    const FT rm = V.rmc[v];
+    // ρe_tot: dry static energy s_d = cp_d (T − T_0) + Φ  (:101-102)
+    {
+      FT s0 = P.cp_d * (S.T[o] - P.T_0) + V.phic[v];
+      FT fl = lo ? wl * (s0 - (P.cp_d * (S.T[o - 1] - P.T_0) + V.phic[v - 1])) : FT(0);
+      FT fh = hi ? wh * ((P.cp_d * (S.T[o + 1] - P.T_0) + V.phic[v + 1]) - s0) : FT(0);
+      gT[(3 * 16 + n) * nv + v] += (fh - fl) * rm;
+    }
+    // uₕ: −C12(ᶜdivᵥ(−2 ᶠρK ε)/ρ) (:91-96) = s_c/(ρ J_c) δ(J g³³ ᶠρK δ(uₕ/s_c)) per covariant component
+    if (D.momentum) {
+      FT is0 = sqrt(V.sc2i[v]);  // 1/s_c
+      FT isl = lo ? sqrt(V.sc2i[v - 1]) : FT(0), ish = hi ? sqrt(V.sc2i[v + 1]) : FT(0);
+      FT sir = rm / (is0 * S.rho[o]);
+      {
+        FT c0 = S.u1[o] * is0;
+        FT fl = lo ? wl * (c0 - S.u1[o - 1] * isl) : FT(0), fh = hi ? wh * (S.u1[o + 1] * ish - c0) : FT(0);
+        gT[(1 * 16 + n) * nv + v] += (fh - fl) * sir;
+      }
+      {
+        FT c0 = S.u2[o] * is0;
+        FT fl = lo ? wl * (c0 - S.u2[o - 1] * isl) : FT(0), fh = hi ? wh * (S.u2[o + 1] * ish - c0) : FT(0);
+        gT[(2 * 16 + n) * nv + v] += (fh - fl) * sir;
+      }
+    }
+    // passive grid-scale tracers χ = ρχ/ρ (:150-153)
+    for (int q = 4; q < P.ncf; ++q) {
+      const FT* gq = gY + (size_t)(q * 16 + n) * nv;
+      FT c0 = gq[v] / S.rho[o];
+      FT fl = lo ? wl * (c0 - gq[v - 1] / S.rho[o - 1]) : FT(0), fh = hi ? wh * (gq[v + 1] / S.rho[o + 1] - c0) : FT(0);
+      gT[(q * 16 + n) * nv + v] += (fh - fl) * rm;
+    }
+  }
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_vdiff_jac(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
+                                                  const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+                                                  const FT* __restrict__ Yf, FT dtg, FT* jacd) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
+  FT* hg = sm.take(HG_ELEM * 16);
+  ImpSlabs<FT> S; imp_carve(sm, S);
+  FT* kh = sm.take(SLAB); FT* pw = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
+  __syncthreads();
+  imp_thermo(P, hg, V, S);
+  __syncthreads();
+  vdiff_kh(P, D, hg, V, S, kh);
+  __syncthreads();
+  vdiff_pw(P, D, V, S, kh, pw, dtg);
+  __syncthreads();
+  FT* gj = jacd + (size_t)h * JD_N * 16 * nf;
+  const size_t pl = (size_t)16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v >= nf) continue;
+    size_t o = (size_t)n * nf + v;
+    gj[JD_PW * pl + o] = pw[n * LVP + v];
+    gj[JD_IRHO * pl + o] = v < nv ? FT(1) / S.rho[n * LVP + v] : FT(0);
+  }
+}
+
+// Thomas algorithm that leaves the matrix untouched: c' goes to cpw, the solution overwrites x (same operation order as the
+// oracle's _tri_solve).
+template <class FT>
+__device__ __forceinline__ void thomas_nd(const FT* l, const FT* d, const FT* u, FT* cpw, FT* x, int n) {
+  FT cp = u[0] / d[0], dp = x[0] / d[0];
+  cpw[0] = cp; x[0] = dp;
+  for (int i = 1; i < n; ++i) {
+    FT li = l[i];
+    FT den = d[i] - li * cp;
+    cp = u[i] / den;
+    dp = (x[i] - li * dp) / den;
+    cpw[i] = cp; x[i] = dp;
+  }
+  FT xx = dp;
+  for (int i = n - 2; i >= 0; --i) {
+    xx = x[i] - cpw[i] * xx;
+    x[i] = xx;
+  }
+}
+
+#define VD_FOR_POINTS(n, v) \
+  for (int idx_ = threadIdx.x, n = idx_ >> 6, v = idx_ & 63; idx_ < NN * LV; idx_ += NT, n = idx_ >> 6, v = idx_ & 63)
+
+// The Schur complement stored by k_wfact (JC_L/D/U) is T = A₃₃ + A₃ρA_ρ3 + A₃eA_e3, i.e. the exact one for A_ρρ = A_ee = −I.
+// With implicit diffusion A_ee is tridiagonal (dtγ·D·Diag(cp_d/(cv_d ρ)) − I), so
+//     S x = T x − A₃e (A_ee⁻¹ + I) A_e3 x           (the u₃ Schur complement of the full Jacobian)
+//     P   = T − A₃e Diag(1 + 1/d_ee) A_e3           (A_ee replaced by its main diagonal: tridiagonal preconditioner)
+// and 1 + 1/d_ee = m/(m − 1) with m = dtγ·D_kk·cp_d/(cv_d ρ_k) ≤ 0 evaluated without cancellation.
+template <class FT>
+__global__ void __launch_bounds__(NT) k_ldiv_diff(Par<FT> P, VDiff<FT> D, const VLev<FT>* __restrict__ vlev,
+                                                  const FT* __restrict__ jac, const FT* __restrict__ jacd,
+                                                  const FT* __restrict__ Rc, const FT* __restrict__ Rf, FT* dYc, FT* dYf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB);   // T (faces)
+  FT* pl_ = sm.take(SLAB); FT* pd = sm.take(SLAB); FT* pu = sm.take(SLAB);  // (uₕ,uₕ) / tracer blocks, then P (faces)
+  FT* el = sm.take(SLAB); FT* ed = sm.take(SLAB); FT* eu = sm.take(SLAB);   // A_ee (centres)
+  FT* fac = sm.take(SLAB);                                                  // m/(m − 1) (centres)
+  FT* scp = sm.take(SLAB); FT* zz = sm.take(SLAB);                          // Thomas scratch / centre scratch
+  FT* rr = sm.take(SLAB); FT* r1 = sm.take(SLAB); FT* r2 = sm.take(SLAB); FT* re = sm.take(SLAB);
+  FT* ye = sm.take(SLAB); FT* b3 = sm.take(SLAB); FT* x3 = sm.take(SLAB); FT* r3 = sm.take(SLAB);
+  FT* pw = sm.take(SLAB); FT* ir = sm.take(SLAB);
+  FT* s_rmc = sm.take(LV);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
+  const FT* gd = jacd + (size_t)h * JD_N * 16 * nf;
+  const size_t pl = (size_t)16 * nf;
+  const FT* gRc = Rc + (size_t)h * P.ncf * 16 * nv;
+  const FT* gRf = Rf + (size_t)h * 16 * nf;
+  FT* gdc = dYc + (size_t)h * P.ncf * 16 * nv;
+  FT* gdf = dYf + (size_t)h * 16 * nf;
+  if (threadIdx.x < LV) s_rmc[threadIdx.x] = vlev->rmc[threadIdx.x];
+  load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
+  load_slab(pw, gd + JD_PW * pl, nf); load_slab(ir, gd + JD_IRHO * pl, nf);
+  load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
+  __syncthreads();
+  // ---- A_ee, the factor 1 + 1/d_ee, and the (uₕ,uₕ) block dtγ Diag(1/ρ)⋅D − I (:1252-1258)
+  VD_FOR_POINTS(n, v) {
+    if (v >= nv) continue;
+    const int o = n * LVP + v;
+    const FT lo = v > 0 ? pw[o] * s_rmc[v] : FT(0), hi = v < nv - 1 ? pw[o + 1] * s_rmc[v] : FT(0);
+    const FT dg = -(lo + hi);
+    const FT m = dg * (D.cpcv * ir[o]);
+    el[o] = v > 0 ? lo * (D.cpcv * ir[o - 1]) : FT(0);
+    ed[o] = m - FT(1);
+    eu[o] = v < nv - 1 ? hi * (D.cpcv * ir[o + 1]) : FT(0);
+    fac[o] = m / (m - FT(1));
+    pl_[o] = lo * ir[o]; pd[o] = dg * ir[o] - FT(1); pu[o] = hi * ir[o];
+    ye[o] = re[o];
+  }
+  __syncthreads();
+  // ---- uₕ (exact tridiagonal solves or the −I fallback) and y_e = A_ee⁻¹ R_ρe
+  if (D.momentum) {
+    if (threadIdx.x < 16) thomas_nd(pl_ + threadIdx.x * LVP, pd + threadIdx.x * LVP, pu + threadIdx.x * LVP, scp + threadIdx.x * LVP, r1 + threadIdx.x * LVP, nv);
+    else if (threadIdx.x >= 32 && threadIdx.x < 48) { int n = threadIdx.x - 32; thomas_nd(pl_ + n * LVP, pd + n * LVP, pu + n * LVP, zz + n * LVP, r2 + n * LVP, nv); }
+    else if (threadIdx.x >= 64 && threadIdx.x < 80) { int n = threadIdx.x - 64; thomas_nd(el + n * LVP, ed + n * LVP, eu + n * LVP, b3 + n * LVP, ye + n * LVP, nv); }
+  } else {
+    VD_FOR_POINTS(n, v) { if (v < nv) { int o = n * LVP + v; r1[o] = -r1[o]; r2[o] = -r2[o]; } }
+    if (threadIdx.x >= 64 && threadIdx.x < 80) { int n = threadIdx.x - 64; thomas_nd(el + n * LVP, ed + n * LVP, eu + n * LVP, b3 + n * LVP, ye + n * LVP, nv); }
+  }
+  __syncthreads();
+  VD_FOR_POINTS(n, v) {
+    if (v < nv) { gdc[(1 * 16 + n) * nv + v] = r1[n * LVP + v]; gdc[(2 * 16 + n) * nv + v] = r2[n * LVP + v]; }
+  }
+  // ---- passive tracers: (ρχ,ρχ) = dtγ D⋅Diag(1/ρ) − I (:1190-1195), exact tridiagonal solve
+  for (int q = 4; q < P.ncf; ++q) {
+    __syncthreads();
+    VD_FOR_POINTS(n, v) {
+      if (v >= nv) continue;
+      const int o = n * LVP + v;
+      const FT lo = v > 0 ? pw[o] * s_rmc[v] : FT(0), hi = v < nv - 1 ? pw[o + 1] * s_rmc[v] : FT(0);
+      pl_[o] = v > 0 ? lo * ir[o - 1] : FT(0); pd[o] = -(lo + hi) * ir[o] - FT(1); pu[o] = v < nv - 1 ? hi * ir[o + 1] : FT(0);
+      zz[o] = gRc[(size_t)(q * 16 + n) * nv + v];
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) thomas_nd(pl_ + threadIdx.x * LVP, pd + threadIdx.x * LVP, pu + threadIdx.x * LVP, scp + threadIdx.x * LVP, zz + threadIdx.x * LVP, nv);
+    __syncthreads();
+    VD_FOR_POINTS(n, v) { if (v < nv) gdc[(size_t)(q * 16 + n) * nv + v] = zz[n * LVP + v]; }
+  }
+  __syncthreads();
+  // ---- Schur right-hand side b₃ = R₃ + A₃ρR_ρ − A₃e y_e − A₃ₕ xₕ  and the preconditioner P
+  VD_FOR_POINTS(n, f) {
+    if (f >= nf) continue;
+    const size_t o = (size_t)n * nf + f;
+    const int s = n * LVP + f;
+    FT rhs = gRf[o];
+    FT l = sl[s], d = sd[s], u = su[s];
+    if (f > 0 && f < nv) {
+      const FT ue_lo = gj[JC_UE_LO * pl + o], ue_hi = gj[JC_UE_HI * pl + o];
+      rhs += gj[JC_UR_LO * pl + o] * rr[s - 1] + gj[JC_UR_HI * pl + o] * rr[s];
+      rhs -= ue_lo * ye[s - 1] + ue_hi * ye[s];
+      rhs -= gj[JC_U1_LO * pl + o] * r1[s - 1] + gj[JC_U1_HI * pl + o] * r1[s];
+      rhs -= gj[JC_U2_LO * pl + o] * r2[s - 1] + gj[JC_U2_HI * pl + o] * r2[s];
+      const FT a = ue_lo * fac[s - 1], b = ue_hi * fac[s];
+      l -= a * gj[JC_EU_LO * pl + o - 1];
+      d -= a * gj[JC_EU_HI * pl + o - 1] + b * gj[JC_EU_LO * pl + o];
+      u -= b * gj[JC_EU_HI * pl + o];
+    }
+    b3[s] = rhs; x3[s] = rhs;
+    pl_[s] = l; pd[s] = d; pu[s] = u;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) thomas_nd(pl_ + threadIdx.x * LVP, pd + threadIdx.x * LVP, pu + threadIdx.x * LVP, scp + threadIdx.x * LVP, x3 + threadIdx.x * LVP, nf);  // x[0] = P⁻¹ b
+  __syncthreads();
+  for (int it = 0; it < D.n_iters; ++it) {
+    VD_FOR_POINTS(n, v) {  // y = A_e3 x
+      if (v >= nv) continue;
+      const size_t o = (size_t)n * nf + v;
+      const int s = n * LVP + v;
+      FT y = gj[JC_EU_LO * pl + o] * x3[s] + gj[JC_EU_HI * pl + o] * x3[s + 1];
+      ye[s] = y; zz[s] = y;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) thomas_nd(el + threadIdx.x * LVP, ed + threadIdx.x * LVP, eu + threadIdx.x * LVP, scp + threadIdx.x * LVP, zz + threadIdx.x * LVP, nv);
+    __syncthreads();
+    VD_FOR_POINTS(n, f) {  // r = b − S x
+      if (f >= nf) continue;
+      const size_t o = (size_t)n * nf + f;
+      const int s = n * LVP + f;
+      FT tx = sd[s] * x3[s];
+      if (f > 0) tx += sl[s] * x3[s - 1];
+      if (f < nv) tx += su[s] * x3[s + 1];
+      FT r = b3[s] - tx;
+      if (f > 0 && f < nv) r += gj[JC_UE_LO * pl + o] * (zz[s - 1] + ye[s - 1]) + gj[JC_UE_HI * pl + o] * (zz[s] + ye[s]);
+      r3[s] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) thomas_nd(pl_ + threadIdx.x * LVP, pd + threadIdx.x * LVP, pu + threadIdx.x * LVP, scp + threadIdx.x * LVP, r3 + threadIdx.x * LVP, nf);
+    __syncthreads();
+    VD_FOR_POINTS(n, f) { if (f < nf) x3[n * LVP + f] += r3[n * LVP + f]; }
+    __syncthreads();
+  }
+  // ---- x₁ = A₁₁⁻¹(b₁ − A₁₂x₂)
+  VD_FOR_POINTS(n, v) {
+    const int s = n * LVP + v;
+    const size_t o = (size_t)n * nf + v;
+    if (v < nf) gdf[o] = x3[s];
+    if (v < nv) {
+      const FT x0 = x3[s], x1 = x3[s + 1];
+      gdc[(0 * 16 + n) * nv + v] = gj[JC_RU_LO * pl + o] * x0 + gj[JC_RU_HI * pl + o] * x1 - rr[s];
+      ye[s] = re[s] - (gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) thomas_nd(el + threadIdx.x * LVP, ed + threadIdx.x * LVP, eu + threadIdx.x * LVP, scp + threadIdx.x * LVP, ye + threadIdx.x * LVP, nv);
+  __syncthreads();
+  VD_FOR_POINTS(n, v) { if (v < nv) gdc[(3 * 16 + n) * nv + v] = ye[n * LVP + v]; }
+}
+
+}  // namespace b200

@@ -57,13 +57,15 @@ class AtmosSimulation:
 
     Keyword surface follows ``AtmosSimulation{FT}(; …)`` / the YAML keys of
     config/default_configs/default_config.yml: ``h_elem, z_elem, z_max, dz_bottom, dt,
-    rayleigh_sponge, viscous_sponge, hyperdiff, initial_condition, deep_atmosphere``.
+    rayleigh_sponge, viscous_sponge, hyperdiff, initial_condition, deep_atmosphere, vert_diff, implicit_diffusion,
+    approximate_linear_solve_iters``.
     """
 
     def __init__(self, FT=np.float32, h_elem=6, z_elem=10, z_max=30000.0, dz_bottom=500.0, dt=400.0,
                  rayleigh_sponge=False, viscous_sponge=False, hyperdiff=True, deep_atmosphere=True,
                  initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter", rad=None,
                  tracers=None, tracer_upwinding="vanleer_limiter", apply_sem_quasimonotone_limiter=False,
+                 vert_diff=None, implicit_diffusion=False, approximate_linear_solve_iters=1,
                  params: DycoreParams | None = None, device=None, comms=None, grid=None):
         torch = _torch()
         self.torch = torch
@@ -72,7 +74,12 @@ class AtmosSimulation:
         self.numerics = DycoreNumerics(dt=float(dt), hyperdiff=hyperdiff, rayleigh_sponge=rayleigh_sponge,
                                        viscous_sponge=viscous_sponge, energy_upwinding=energy_q_tot_upwinding,
                                        held_suarez=(rad == "held_suarez"), tracer_upwinding=tracer_upwinding,
-                                       apply_sem_quasimonotone_limiter=bool(apply_sem_quasimonotone_limiter))
+                                       apply_sem_quasimonotone_limiter=bool(apply_sem_quasimonotone_limiter),
+                                       # vert_diff / implicit_diffusion / approximate_linear_solve_iters: default_config.yml:166-168,
+                                       # 397-402; momentum diffusion is off for Held–Suarez runs (type_getters.jl:46)
+                                       vert_diff=vert_diff, implicit_diffusion=bool(implicit_diffusion),
+                                       approximate_linear_solve_iters=int(approximate_linear_solve_iters),
+                                       disable_momentum_vertical_diffusion=(rad == "held_suarez"))
         self.grid = grid or make_sphere_grid(FT=self.FT, h_elem=h_elem, z_elem=z_elem, z_max=z_max, dz_bottom=dz_bottom,
                                              radius=self.params.planet_radius, deep_atmosphere=deep_atmosphere)
         self.comms = comms  # parallel.DistributedComms or None

@@ -84,6 +84,14 @@ typedef struct {
   /* apply_sem_quasimonotone_limiter (config/default_configs/default_config.yml; type_getters.jl:129): lim! applies ClimaCore's
    * Limiters.QuasiMonotoneLimiter to every tracer; 0 = lim! is the reference's no-op */
   int32_t sem_quasimonotone_limiter;
+  /* Vertical diffusion (src/prognostic_equations/vertical_diffusion_boundary_layer.jl:64-154; model_getters.jl:332-358):
+   * vert_diff 0 = none (`~`), 1 = VerticalDiffusion (C_E), 2 = DecayWithHeightDiffusion (H_diffusion, D_0_diffusion);
+   * implicit_diffusion → diff_mode (type_getters.jl:131): 0 the tendency joins T_exp (remaining_tendency.jl:185-195), 1 it joins
+   * T_imp!, Wfact adds the diffusion blocks (manual_sparse_jacobian.jl:1031-1261) and ldiv! becomes the
+   * ApproximateBlockArrowheadIterativeSolve with approximate_linear_solve_iters iterations (:538-578);
+   * disable_momentum_vertical_diffusion: scalars only (Held–Suarez runs, type_getters.jl:46). */
+  int32_t vert_diff, implicit_diffusion, approximate_linear_solve_iters, disable_momentum_vertical_diffusion;
+  double C_E, H_diffusion, D_0_diffusion;
 } b200_params;
 
 /* Optional device pointers to p.precomputed fields written by b200_cache_imp (any may be NULL).

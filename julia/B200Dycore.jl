@@ -48,6 +48,11 @@ struct ParamsC
     hs_day::Float64; hs_sigma_b::Float64; hs_dT_y::Float64; hs_T_equator::Float64; hs_dtheta_z::Float64; hs_T_min::Float64
     MSLP::Float64
     sem_quasimonotone_limiter::Int32
+    vert_diff::Int32             # 0 none, 1 VerticalDiffusion, 2 DecayWithHeightDiffusion
+    implicit_diffusion::Int32
+    approximate_linear_solve_iters::Int32
+    disable_momentum_vertical_diffusion::Int32
+    C_E::Float64; H_diffusion::Float64; D_0_diffusion::Float64
 end
 struct CachePtrs
     u_c::Ptr{Cvoid}; u3_f::Ptr{Cvoid}; K_c::Ptr{Cvoid}; T_c::Ptr{Cvoid}; p_c::Ptr{Cvoid}; h_tot_c::Ptr{Cvoid}
@@ -65,12 +70,12 @@ stream() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
 upw(x) = x == Val(:none) ? Int32(0) : x == Val(:first_order) ? Int32(1) : Int32(3)
 
 """
-    create(Y, p) -> Ctx
+    create(Y, p; approximate_solve_iters = 1) -> Ctx
 
 Called once at the end of `build_cache` (src/cache/cache.jl:165-305): copies geometry, connectivity and parameters
 from the live ClimaCore objects into the library.  [UPSTREAM-RECALL] for the ClimaCore accessors.
 """
-function create(Y, p)
+function create(Y, p; approximate_solve_iters = 1)   # = B200Jacobian(...).approximate_solve_iters (YAML approximate_linear_solve_iters)
     FT = eltype(Y)
     space = axes(Y.c)
     hspace = Spaces.horizontal_space(space)
@@ -106,6 +111,7 @@ function create(Y, p)
     topo_c = TopologyC(pointer(faces), length(faces) ÷ 5, pointer(lv), pointer(lvo), length(lvo) - 1, length(nbr),
                        pointer(nbr), pointer(soff), pointer(selems), pointer(roff), pointer(gid))
     rs, vs = p.atmos.rayleigh_sponge, p.atmos.viscous_sponge
+    vd = p.atmos.vertical_diffusion
     prm = ParamsC(CAP.R_d(params), CAP.cp_d(params), CAP.cv_d(params), CAP.T_0(params), CAP.grav(params), CAP.Omega(params),
                   CAP.p_ref_theta(params), CAP.T_surf_ref(params), CAP.T_min_ref(params), CAP.T_min_sgs(params),
                   Float64(p.dt), ν₄ᵥ, ν₄ₛ, p.atmos.hyperdiff === nothing ? 1.0 : Float64(p.atmos.hyperdiff.divergence_damping_factor),
@@ -116,7 +122,13 @@ function create(Y, p)
                   p.atmos.radiation_mode isa CA.RRTMGPI.HeldSuarezForcing ? 1 : 0,    # held_suarez.jl
                   CAP.day(params), CAP.σ_b(params), CAP.ΔT_y_dry(params), CAP.T_equator_dry(params), CAP.Δθ_z(params),
                   CAP.T_min_hs(params), CAP.MSLP(params),
-                  p.numerics.sem_quasimonotone_limiter === nothing ? 0 : 1)
+                  p.numerics.sem_quasimonotone_limiter === nothing ? 0 : 1,
+                  vd === nothing ? 0 : (vd isa CA.VerticalDiffusion ? 1 : 2),                 # types.jl:564-597
+                  p.atmos.diff_mode == CA.Implicit() ? 1 : 0,                                # type_getters.jl:131
+                  Int32(approximate_solve_iters), CA.disable_momentum_vertical_diffusion(vd) ? 1 : 0,
+                  vd isa CA.VerticalDiffusion ? Float64(vd.C_E) : 0.0,
+                  vd isa CA.DecayWithHeightDiffusion ? Float64(vd.H) : 1.0,
+                  vd isa CA.DecayWithHeightDiffusion ? Float64(vd.D₀) : 0.0)
     comms = ClimaComms.context(Y.c)
     rank, nranks = ClimaComms.mypid(comms) - 1, ClimaComms.nprocs(comms)
     id = zeros(UInt8, 128)
@@ -168,7 +180,10 @@ limiters_func!(Y, p, t, ref_Y) =                              # prognostic_equat
                 p.b200.ptr, dptr(Y.c), dptr(Y.f), dptr(ref_Y.c), dptr(ref_Y.f), Float64(t), stream()), "b200_lim")
 
 # ---- Jacobian: the three-method JacobianAlgorithm contract of implicit/jacobian.jl:16-26 ---------------------------
-struct B200Jacobian <: CA.JacobianAlgorithm end
+struct B200Jacobian <: CA.JacobianAlgorithm
+    approximate_solve_iters::Int     # as ManualSparseJacobian.approximate_solve_iters (manual_sparse_jacobian.jl:45-60); used when diff_mode is Implicit
+end
+B200Jacobian() = B200Jacobian(1)
 CA.jacobian_cache(::B200Jacobian, Y, atmos) = (; ctx = Ref{Ctx}())    # ctx[] = p.b200, set right after build_cache
 CA.update_jacobian!(::B200Jacobian, cache, Y, p, dtγ, t) =           # Wfact, implicit/jacobian.jl:74
     check(ccall((:b200_wfact, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cvoid}),

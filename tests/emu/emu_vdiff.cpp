@@ -1,0 +1,58 @@
+// CPU emulation of single CTAs running the vertical-diffusion kernels of climaatmos.jl_b200/csrc/kernels_vdiff.cuh (and k_wfact, whose
+// planes k_ldiv_diff consumes) — the kernel source is compiled unchanged by g++ against the stub cuda_runtime.h in this directory;
+// 256 host threads play the threads of a block.  Test infrastructure only (tests/test_vdiff_kernels_cpu_emulation.py): it checks
+// indexing, barriers-as-phases and arithmetic of the kernels against the oracle when no GPU is at hand.  It is NOT a product path.
+#include <thread>
+#include <vector>
+
+#include "cuda_runtime.h"
+thread_local uint3_emu threadIdx, blockIdx;
+std::barrier<>* g_cta_barrier = nullptr;
+namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
+
+#include "kernels_vdiff.cuh"
+
+using namespace b200;
+typedef double FT;
+
+template <class F>
+static void run_grid(int nblocks, F&& body) {
+  std::barrier<> bar(NT);
+  g_cta_barrier = &bar;
+  std::vector<std::thread> th;
+  for (int t = 0; t < NT; ++t)
+    th.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; ++b) {
+        threadIdx = {(unsigned)t, 0, 0};
+        blockIdx = {(unsigned)b, 0, 0};
+        body();
+        bar.arrive_and_wait();  // next block reuses the shared memory
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+// sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ
+// vl: [11][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw ; hgeo: [nh][HG_N][16] ; kdec [64]
+extern "C" int emu_vdiff(int nh, int nv, int ncf, const double* sc, const double* vl, const double* hgeo, const double* kdec,
+                         const double* Yc, const double* Yf, const double* Rc, const double* Rf, double* Ytc, double* jac,
+                         double* jacd, double* dYc, double* dYf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = ncf; P.rayleigh = (int)sc[9];
+  VDiff<FT> D;
+  D.mode = (int)sc[10]; D.momentum = (int)sc[11]; D.n_iters = (int)sc[12]; D.ce_za = sc[13]; D.eps = 2.220446049250313e-16;
+  D.cpcv = sc[1] / sc[2]; D.kdec = kdec;
+  const FT dtg = sc[14];
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  run_grid(nh, [&] { k_vdiff_tend<FT>(P, D, hgeo, &V, Yc, Yf, Ytc); });
+  run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+  run_grid(nh, [&] { k_vdiff_jac<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
+  run_grid(nh, [&] { k_ldiv_diff<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
+  return 0;
+}

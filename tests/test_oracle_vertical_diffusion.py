@@ -196,3 +196,68 @@ def test_step_with_vertical_diffusion_smooths_a_tracer_and_conserves(implicit):
     c0, f0 = o2.step(Yc.copy(), Yf.copy())
     var = lambda c: np.var((c[:, 4] / c[:, 0])[..., :3], axis=-1).mean()  # lowest levels, where K Δt/Δz² ≈ 0.15
     assert var(c1) < 0.9 * var(c0)
+
+
+def test_kernel_formulation_of_the_iterative_solve():
+    """k_ldiv_diff (csrc/kernels_vdiff.cuh) never sees A₃₃: it starts from the Schur tridiagonal T = A₃₃ + A₃ρA_ρ3 + A₃eA_e3 that
+    k_wfact stores for the dry solve and uses  S x = T x − A₃e (A_ee⁻¹ + I) A_e3 x,  P = T − A₃e Diag(m/(m − 1)) A_e3  with
+    m = d_ee + 1, and builds A_ee / (uₕ,uₕ) / tracer blocks from two planes (dtγ·J g³³ ᶠρK / J2 on faces, 1/ρ at centres).  This
+    restates that algebra in NumPy from the same planes and checks it against the oracle's literal block formulation."""
+    g, P, N, o, Yc, Yf, rng = make("VerticalDiffusion", D0=200.0)
+    dtg = 87.0
+    pc = o.set_implicit_precomputed_quantities(Yc[:, :4], Yf)
+    Jm = o.update_jacobian(Yc, Yf, pc, dtg)
+    Rc, Rf = rng.standard_normal(Yc.shape), rng.standard_normal(Yf.shape)
+    nv = g.nv
+    cl = lambda a: np.concatenate([a[..., :1] * 0, a], -1)
+    ch = lambda a: np.concatenate([a, a[..., -1:] * 0], -1)
+    f2 = lambda a21, r: a21[0] * cl(r) + a21[1] * ch(r)
+    c2 = lambda a12, x: a12[0] * x[..., :-1] + a12[1] * x[..., 1:]
+    # --- the two planes of k_vdiff_jac and the per-level 1/(s_c² Δz_c)
+    s_c = (g.radius + g.z_c) / g.radius
+    s_f = (g.radius + g.z_f) / g.radius
+    rmc = 1.0 / (s_c**2 * g.dz_c)
+    pw = dtg * (s_f**2 / g.dz_f) * o._rhoK_face(Yc, pc)
+    pw[..., 0] = 0
+    pw[..., -1] = 0
+    ir = 1.0 / Yc[:, 0]
+    lo, hi = pw[..., :-1] * rmc, pw[..., 1:] * rmc
+    dg = -(lo + hi)
+    z = np.zeros_like(ir[..., :1])
+    left = lambda a: np.concatenate([z, a[..., :-1]], -1)
+    right = lambda a: np.concatenate([a[..., 1:], z], -1)
+    cpcv = P.cp_d / P.cv_d
+    m = dg * cpcv * ir
+    Aee = (lo * cpcv * left(ir), m - 1.0, hi * cpcv * right(ir))
+    fac = m / (m - 1.0)
+    Ahh = (lo * ir, dg * ir - 1.0, hi * ir)
+    Att = (lo * left(ir), dg * ir - 1.0, hi * right(ir))
+    for a, b in zip(Aee, Jm["diff"]["rhoe_rhoe"]):
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+    for a, b in zip(Ahh, Jm["diff"]["uh_uh"]):
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+    for a, b in zip(Att, Jm["diff"]["tracer"]):
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+    # --- T as k_wfact stores it (dry Schur complement)
+    T = [a.copy() for a in Jm["u3_u3"]]
+    for a21, a12 in ((Jm["u3_rho"], Jm["rho_u3"]), (Jm["u3_rhoe"], Jm["rhoe_u3"])):
+        T[0] += a21[0] * cl(a12[0])
+        T[1] += a21[0] * cl(a12[1]) + a21[1] * ch(a12[0])
+        T[2] += a21[1] * ch(a12[1])
+    ue, eu = Jm["u3_rhoe"], Jm["rhoe_u3"]
+    Pm = [T[0] - ue[0] * cl(fac * eu[0]), T[1] - ue[0] * cl(fac * eu[1]) - ue[1] * ch(fac * eu[0]), T[2] - ue[1] * ch(fac * eu[1])]
+    x1, x2 = o._tri_solve(Ahh, Rc[:, 1]), o._tri_solve(Ahh, Rc[:, 2])
+    ye = o._tri_solve(Aee, Rc[:, 3])
+    b3 = Rf[:, 0] + f2(Jm["u3_rho"], Rc[:, 0]) - f2(ue, ye) - f2(Jm["u3_uh"][0], x1) - f2(Jm["u3_uh"][1], x2)
+    x3 = o._tri_solve(Pm, b3.copy())
+    for _ in range(N.approximate_linear_solve_iters):
+        y = c2(eu, x3)
+        zz = o._tri_solve(Aee, y)
+        r = b3 - o._tri_mul(T, x3) + f2(ue, zz + y)
+        x3 = x3 + o._tri_solve(Pm, r)
+    xr = c2(Jm["rho_u3"], x3) - Rc[:, 0]
+    xe = o._tri_solve(Aee, Rc[:, 3] - c2(eu, x3))
+    xt = o._tri_solve(Att, Rc[:, 4])
+    dc, df = o.ldiv(Jm, Rc, Rf)
+    for got, ref in ((xr, dc[:, 0]), (x1, dc[:, 1]), (x2, dc[:, 2]), (xe, dc[:, 3]), (xt, dc[:, 4]), (x3, df[:, 0])):
+        assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()

@@ -1,0 +1,112 @@
+"""The vertical-diffusion CUDA kernels (csrc/kernels_vdiff.cuh), executed on the CPU: tests/emu/ compiles the kernel SOURCE
+unchanged with g++ against a stub cuda_runtime.h and runs each CTA with 256 host threads and a std::barrier for
+__syncthreads().  k_vdiff_tend, k_wfact → k_vdiff_jac → k_ldiv_diff are then compared with the oracle (Float64).
+
+This is a stand-in for the GPU parity run of these kernels (tests/test_gpu_vertical_diffusion.py), written when the round's GPU
+budget was spent: it exercises the indexing, phase structure and arithmetic of the very same code, not warp-level behaviour."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from climaatmos_jl_b200 import grid as G, params as prm, setups
+from oracle.dycore_oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HG_N, HG_GI11, HG_GI12, HG_GI22 = 23, 2, 3, 4
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(HERE, "emu", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_vdiff.so")
+    src = os.path.join(HERE, "emu", "emu_vdiff.cpp")
+    csrc = os.path.join(os.path.dirname(HERE), "climaatmos.jl_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-I", os.path.join(HERE, "emu"), "-I", csrc, src, "-o", so],
+                   check=True)
+    return C.CDLL(so)
+
+
+def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False):
+    P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
+    N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=iters,
+                           disable_momentum_vertical_diffusion=dm, rayleigh_sponge=rayleigh)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(1234)
+    Yc = Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    Yf[..., 0] = 0
+    Yf[..., -1] = 0
+    Yc = np.concatenate([Yc] + [Yc[:, :1] * 1e-2 * (1 + 0.5 * rng.random(Yc[:, :1].shape)) for _ in range(ntr)], axis=1)
+    Yc, Yf = np.ascontiguousarray(Yc), np.ascontiguousarray(Yf)
+    nh, ncf, nv = Yc.shape[0], Yc.shape[1], g.nv
+    dtg = 0.4358665215084590 * N.dt
+    # context constants as capi.cu:create_geo builds them
+    s_c = (g.radius + g.z_c) / g.radius if deep else np.ones(nv)
+    s_f = (g.radius + g.z_f) / g.radius if deep else np.ones(nv + 1)
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    brw = o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if rayleigh else np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif), pad(brw)])
+    A = g.dxdxi
+    Ginv = np.linalg.inv(np.einsum("...ab,...ac->...bc", A, A))
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_GI11] = Ginv[..., 0, 0].reshape(nh, 16)
+    hgeo[:, HG_GI12] = Ginv[..., 0, 1].reshape(nh, 16)
+    hgeo[:, HG_GI22] = Ginv[..., 1, 1].reshape(nh, 16)
+    kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
+    mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), mode,
+                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg])
+    Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
+    Rf = rng.standard_normal(Yf.shape)
+    Ytc = np.zeros_like(Yc)
+    jac = np.zeros((nh, 15, 16, nv + 1))
+    jacd = np.zeros((nh, 2, 16, nv + 1))
+    dYc, dYf = np.zeros_like(Yc), np.zeros_like(Yf)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu.emu_vdiff(nh, nv, ncf, p(sc), p(vl), p(hgeo), p(kdec), p(Yc), p(Yf), p(Rc), p(Rf), p(Ytc), p(jac), p(jacd), p(dYc), p(dYf))
+    assert rc == 0
+    # oracle
+    pc = o.set_implicit_precomputed_quantities(Yc[:, :4].copy(), Yf.copy())
+    ot = np.zeros_like(Yc)
+    o.vertical_diffusion_boundary_layer_tendency(ot, Yc, pc)
+    Jm = o.update_jacobian(Yc, Yf, pc, dtg)
+    oc, of = o.ldiv(Jm, Rc, Rf)
+    return (Ytc, dYc, dYf), (ot, oc, of)
+
+
+def rel(a, b):
+    n = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / n if n > 0 else np.linalg.norm(a.ravel())
+
+
+@pytest.mark.parametrize("vd,deep,dm,iters,ntr,rayleigh", [
+    ("DecayWithHeightDiffusion", True, False, 2, 1, False),
+    ("VerticalDiffusion", True, False, 2, 1, True),
+    ("DecayWithHeightDiffusion", False, False, 1, 2, False),
+    ("DecayWithHeightDiffusion", True, True, 0, 0, False),
+    ("VerticalDiffusion", False, True, 3, 1, False),
+])
+def test_emulated_vdiff_kernels_match_oracle(emu, vd, deep, dm, iters, ntr, rayleigh):
+    (gt, gc, gf), (ot, oc, of) = run_case(emu, vd, deep, dm, iters, ntr, rayleigh)
+    ncf = gt.shape[1]
+    for k in range(ncf):
+        if k == 0 or (dm and k in (1, 2)):
+            assert np.all(gt[:, k] == 0) and np.all(ot[:, k] == 0)
+        else:
+            assert rel(gt[:, k], ot[:, k]) < 1e-11, ("tend", k, rel(gt[:, k], ot[:, k]))
+    for k in range(ncf):
+        assert rel(gc[:, k], oc[:, k]) < 1e-10, ("ldiv", k, rel(gc[:, k], oc[:, k]))
+    assert rel(gf, of) < 1e-10, ("ldiv u3", rel(gf, of))
