@@ -5,6 +5,9 @@
 #include <thread>
 #include <vector>
 
+// The product library exports host stubs with the kernels' mangled names; when both are loaded in one process the dynamic linker
+// would bind the emulator's calls to those stubs.  A private namespace keeps the two apart.
+#define b200 b200_emu
 #include "cuda_runtime.h"
 thread_local uint3_emu threadIdx, blockIdx;
 std::barrier<>* g_cta_barrier = nullptr;
@@ -34,7 +37,7 @@ static void run_grid(int nblocks, F&& body) {
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ
 // vl: [11][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw ; hgeo: [nh][HG_N][16] ; kdec [64]
-extern "C" int emu_vdiff(int nh, int nv, int ncf, const double* sc, const double* vl, const double* hgeo, const double* kdec,
+extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, int ncf, const double* sc, const double* vl, const double* hgeo, const double* kdec,
                          const double* Yc, const double* Yf, const double* Rc, const double* Rf, double* Ytc, double* jac,
                          double* jacd, double* dYc, double* dYf) {
   Par<FT> P;

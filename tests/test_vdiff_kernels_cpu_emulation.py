@@ -28,7 +28,7 @@ def emu():
     so = os.path.join(out, "libemu_vdiff.so")
     src = os.path.join(HERE, "emu", "emu_vdiff.cpp")
     csrc = os.path.join(os.path.dirname(HERE), "climaatmos.jl_b200", "csrc")
-    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-I", os.path.join(HERE, "emu"), "-I", csrc, src, "-o", so],
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden", "-I", os.path.join(HERE, "emu"), "-I", csrc, src, "-o", so],
                    check=True)
     return C.CDLL(so)
 
