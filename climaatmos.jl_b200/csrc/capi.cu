@@ -141,6 +141,7 @@ struct b200_ctx {
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
   int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
   int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
+  int vdiff_kernel = 1;  // B200_VDIFF_KERNEL=1|2: k_vdiff_tend (element slabs) or k_vdiff_tend2 (quarter element, no slabs)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   int ncf() const { return 4 + dims.n_tracers; }
   size_t nc() const { return (size_t)dims.nh * ncf() * 16 * dims.nv; }
@@ -466,6 +467,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
   if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
+  if (const char* e = getenv("B200_VDIFF_KERNEL")) c->vdiff_kernel = atoi(e);
   if (d->n_tracers > 0 && (c->legacy || (c->imp_kernel != 2 && c->imp_kernel != 5))) {
     delete c;
     return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
@@ -620,8 +622,13 @@ extern "C" int b200_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cachep
 // Yₜ.c += vertical_diffusion_boundary_layer_tendency!(Y)  (kernels_vdiff.cuh)
 template <class FT>
 static int launch_vdiff_tend(b200_ctx* c, void* Ytc, const void* Yc, const void* Yf, cudaStream_t s) {
-  k_vdiff_tend<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-                                                            (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT*)Ytc);
+  if (c->vdiff_kernel == 2)  // quarter element per CTA, HBM-bound (bitwise identical to k_vdiff_tend)
+    k_vdiff_tend2<FT><<<c->dims.nh * 4, NT, VD2_ARR * 4 * VD2_ST * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                                                 (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                                                 (const FT*)Yf, (FT*)Ytc);
+  else
+    k_vdiff_tend<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                              (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT*)Ytc);
   LAUNCH_CHECK(c);
   return 0;
 }

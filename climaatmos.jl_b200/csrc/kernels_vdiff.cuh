@@ -140,6 +140,96 @@ __global__ void __launch_bounds__(NT) k_vdiff_tend(Par<FT> P, VDiff<FT> D, const
   }
 }
 
+// Second generation of k_vdiff_tend: a quarter element (4 columns × 64 levels) per CTA, no state slabs — each thread loads its own
+// point, computes T (and K_h) once, and only the six per-column profiles the vertical differences need (ρ, K_h, s_d, uₕ/s_c, χ) and the
+// face weights go through 7.4 KB of shared memory, so the kernel is HBM-bound (read Y, read-modify-write Yₜ) instead of latency-bound.
+// Same operations in the same order as k_vdiff_tend: bitwise identical results (tests/test_vdiff_kernels_cpu_emulation.py).
+constexpr int VD2_ST = 66;  // column stride
+constexpr int VD2_ARR = 7;
+template <class FT>
+__global__ void __launch_bounds__(NT) k_vdiff_tend2(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
+                                                    const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+                                                    const FT* __restrict__ Yf, FT* Ytc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  FT* s_rho = sm.take(4 * VD2_ST); FT* s_kh = sm.take(4 * VD2_ST); FT* s_pw = sm.take(4 * VD2_ST); FT* s_sd = sm.take(4 * VD2_ST);
+  FT* s_a = sm.take(4 * VD2_ST); FT* s_b = sm.take(4 * VD2_ST); FT* s_c = sm.take(4 * VD2_ST);
+  const int h = blockIdx.x >> 2, nl = threadIdx.x >> 6, n = (blockIdx.x & 3) * 4 + nl, v = threadIdx.x & 63, nv = P.nv;
+  const VLev<FT>& V = *vlev;
+  const FT* hg = hgeo + (size_t)h * HG_N * 16;
+  const FT* gY = Yc + (size_t)h * P.ncf * 16 * nv;
+  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
+  const bool act = v < nv;
+  const int o = nl * VD2_ST + v;
+  FT rho = FT(1), is0 = FT(0);
+  if (act) {
+    rho = gY[(0 * 16 + n) * nv + v];
+    const FT u1 = gY[(1 * 16 + n) * nv + v], u2 = gY[(2 * 16 + n) * nv + v], re = gY[(3 * 16 + n) * nv + v];
+    const FT* gf = Yf + (size_t)h * 16 * (nv + 1) + (size_t)n * (nv + 1);
+    const FT K = kinetic(hg, V, u1, u2, gf[v], gf[v + 1], n, v);
+    const Pt<FT> t = thermo(P, rho, re, K, V.phic[v]);
+    FT kh;
+    if (D.mode == 2) {
+      kh = D.kdec[v];
+    } else {
+      const FT a = gY[(1 * 16 + n) * nv], b = gY[(2 * 16 + n) * nv];  // Fields.level(ᶜuₕ, 1)
+      const FT g11 = hg[HG_GI11 * 16 + n], g12 = hg[HG_GI12 * 16 + n], g22 = hg[HG_GI22 * 16 + n];
+      const FT nrm = sqrt((a * (g11 * a + g12 * b) + b * (g12 * a + g22 * b)) * V.sc2i[0]);
+      const FT KE = D.ce_za * nrm;
+      const FT p = rho * P.R_d * t.T;
+      const FT x = (FT(85000) - p) / FT(10000);
+      kh = p > FT(85000) ? KE : KE * exp_(-(x * x));
+    }
+    is0 = sqrt(V.sc2i[v]);
+    s_rho[o] = rho; s_kh[o] = kh; s_sd[o] = P.cp_d * (t.T - P.T_0) + V.phic[v];
+    s_a[o] = u1 * is0; s_b[o] = u2 * is0;
+  }
+  __syncthreads();
+  {  // weight of the lower face of level v; faces 0 and nv carry no flux
+    FT w = FT(0);
+    if (act && v > 0) {
+      const FT rf = FT(0.5) * (s_rho[o - 1] + s_rho[o]);
+      const FT ik = FT(0.5) * (FT(1) / fmax_(s_kh[o - 1], D.eps) + FT(1) / fmax_(s_kh[o], D.eps));
+      w = FT(1) * (V.dzf[v] * V.g33f[v] / V.sf2i[v]) * (rf / ik);
+    }
+    if (v <= nv) s_pw[o] = w;
+  }
+  __syncthreads();
+  const bool lo = v > 0, hi = v < nv - 1;
+  const FT wl = (act && lo) ? s_pw[o] : FT(0), wh = (act && hi) ? s_pw[o + 1] : FT(0);
+  const FT rm = act ? V.rmc[v] : FT(0);
+  if (act) {
+    {
+      const FT s0 = s_sd[o];
+      const FT fl = lo ? wl * (s0 - s_sd[o - 1]) : FT(0), fh = hi ? wh * (s_sd[o + 1] - s0) : FT(0);
+      gT[(3 * 16 + n) * nv + v] += (fh - fl) * rm;
+    }
+    if (D.momentum) {
+      const FT sir = rm / (is0 * rho);
+      {
+        const FT c0 = s_a[o];
+        const FT fl = lo ? wl * (c0 - s_a[o - 1]) : FT(0), fh = hi ? wh * (s_a[o + 1] - c0) : FT(0);
+        gT[(1 * 16 + n) * nv + v] += (fh - fl) * sir;
+      }
+      {
+        const FT c0 = s_b[o];
+        const FT fl = lo ? wl * (c0 - s_b[o - 1]) : FT(0), fh = hi ? wh * (s_b[o + 1] - c0) : FT(0);
+        gT[(2 * 16 + n) * nv + v] += (fh - fl) * sir;
+      }
+    }
+  }
+  for (int q = 4; q < P.ncf; ++q) {
+    __syncthreads();
+    if (act) s_c[o] = gY[(size_t)(q * 16 + n) * nv + v] / rho;
+    __syncthreads();
+    if (act) {
+      const FT c0 = s_c[o];
+      const FT fl = lo ? wl * (c0 - s_c[o - 1]) : FT(0), fh = hi ? wh * (s_c[o + 1] - c0) : FT(0);
+      gT[(size_t)(q * 16 + n) * nv + v] += (fh - fl) * rm;
+    }
+  }
+}
+
 template <class FT>
 __global__ void __launch_bounds__(NT) k_vdiff_jac(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
                                                   const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,

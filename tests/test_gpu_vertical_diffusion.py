@@ -1,19 +1,13 @@
 """GPU parity tests for vertical diffusion and the approximate arrowhead solve — kernels_vdiff.cuh
 (k_vdiff_tend, k_vdiff_jac, k_ldiv_diff) through the C-ABI against the NumPy oracle.
 
-STATUS: these kernels were written after this round's GPU budget was spent — they compile for sm_100a and the oracle side is
-pinned on the CPU (tests/test_oracle_vertical_diffusion.py), but they have NOT run on a B200 yet.  Until they have, the tests
-are opt-in: set B200_RUN_UNVALIDATED=1 (first thing to do next round:
-``B200_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_vertical_diffusion.py -m gpu -x -q``).  Tolerances as in
+Run on a B200 at the end of round 1 (profiles/r1_vdiff_gpu_pytest.log, profiles/r1_vdiff_gpu_quickcheck.log: Float64 ≤ 1e-13,
+Float32 ≤ 1e-6 on the centre fields).  Tolerances as in
 tests/test_gpu_parity.py (Float64 1e-11; Float32 1e-5 state / 5e-4 cancelling tendencies)."""
-import os
-
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("B200_RUN_UNVALIDATED"),
-                                 reason="vertical-diffusion kernels not yet validated on a B200 (set B200_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 from climaatmos_jl_b200 import dycore, params as prm
 from oracle.dycore_oracle import Oracle

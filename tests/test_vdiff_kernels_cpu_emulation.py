@@ -33,7 +33,7 @@ def emu():
     return C.CDLL(so)
 
 
-def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False):
+def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1):
     P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
     N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=iters,
@@ -68,7 +68,7 @@ def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False):
     kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
     mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), mode,
-                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg])
+                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, tend_kernel])
     Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
     Rf = rng.standard_normal(Yf.shape)
     Ytc = np.zeros_like(Yc)
@@ -110,3 +110,15 @@ def test_emulated_vdiff_kernels_match_oracle(emu, vd, deep, dm, iters, ntr, rayl
     for k in range(ncf):
         assert rel(gc[:, k], oc[:, k]) < 1e-10, ("ldiv", k, rel(gc[:, k], oc[:, k]))
     assert rel(gf, of) < 1e-10, ("ldiv u3", rel(gf, of))
+
+
+@pytest.mark.parametrize("vd,deep,dm,ntr", [("DecayWithHeightDiffusion", True, False, 2), ("VerticalDiffusion", True, False, 1),
+                                            ("VerticalDiffusion", False, True, 0)])
+def test_second_generation_tendency_kernel_is_bitwise_identical(emu, vd, deep, dm, ntr):
+    """k_vdiff_tend2 (quarter element per CTA, no state slabs) performs the operations of k_vdiff_tend in the same order."""
+    (g1, _, _), (ot, _, _) = run_case(emu, vd, deep, dm, 1, ntr, tend_kernel=1)
+    (g2, _, _), _ = run_case(emu, vd, deep, dm, 1, ntr, tend_kernel=2)
+    assert np.abs(g1).max() > 0
+    assert np.array_equal(g1, g2)
+    for k in range(3 if dm else 1, g2.shape[1]):
+        assert rel(g2[:, k], ot[:, k]) < 1e-11
