@@ -141,7 +141,7 @@ struct b200_ctx {
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
   int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
   int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
-  int vdiff_kernel = 1;  // B200_VDIFF_KERNEL=1|2: k_vdiff_tend (element slabs) or k_vdiff_tend2 (quarter element, no slabs)
+  int vdiff_kernel = 2;  // B200_VDIFF_KERNEL=2|1: k_vdiff_tend2 (quarter element per CTA, no state slabs; 77 µs at he30) or k_vdiff_tend (element slabs, 267 µs)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   int ncf() const { return 4 + dims.n_tracers; }
   size_t nc() const { return (size_t)dims.nh * ncf() * 16 * dims.nv; }
