@@ -44,6 +44,9 @@ def workload(n_gpus, config="weak"):
     w = dict(h_elem=h, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=dt, scaling="weak", name="dry_baroclinic_wave")
     if config == "tracer":
         w.update(tracers=1, name="dry_baroclinic_wave + 1 passive tracer")
+    if config in ("vdiff", "vdiff_implicit"):
+        w.update(vert_diff="DecayWithHeightDiffusion", implicit_diffusion=(config == "vdiff_implicit"),
+                 name="dry_baroclinic_wave + vertical diffusion (" + ("implicit, 2 solver iterations" if config == "vdiff_implicit" else "explicit") + ")")
     return w
 
 
@@ -113,7 +116,7 @@ def run_reference(args):
     from oracle.dycore_oracle import Oracle
 
     w = workload(args.gpus)
-    P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD)
+    P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD, D_0_diffusion=5.0, H_diffusion=800.0)
     # bounded sample: a full-depth (ze63) sphere at reduced horizontal resolution, cost ∝ columns
     h_s = min(w["h_elem"], args.ref_h_elem)
     g = G.make_sphere_grid(FT=np.float32, h_elem=h_s, z_elem=w["z_elem"], z_max=w["z_max"], dz_bottom=w["dz_bottom"],
@@ -156,7 +159,7 @@ def main():
     ap.add_argument("--ref-h-elem", type=int, default=16, help="horizontal resolution of the bounded CPU sample")
     ap.add_argument("--cpu-threads", type=int, default=16, help="upper bound on host threads used by the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="weak", choices=["weak", "strong", "he16", "tracer", "hs"], help="BASELINE.json config (default: the north-star weak series)")
+    ap.add_argument("--config", default="weak", choices=["weak", "strong", "he16", "tracer", "hs", "vdiff", "vdiff_implicit"], help="BASELINE.json config (default: the north-star weak series)")
     ap.add_argument("--unfused", action="store_true", help="hook-by-hook implicit stage instead of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -173,12 +176,13 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     w = workload(nranks, args.config)
-    P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD)
+    P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD, D_0_diffusion=5.0, H_diffusion=800.0)
     sponge = w.get("sponge", True)
     ntr = w.get("tracers", 0)
     tracers = [lambda lat, lon, z: 0.5 * (1 + np.sin(np.radians(lat)) * np.cos(np.radians(lon))) * np.exp(-z / 8000.0)] * ntr or None
     sim = dycore.AtmosSimulation(FT=np.float32, h_elem=w["h_elem"], z_elem=w["z_elem"], z_max=w["z_max"], dz_bottom=w["dz_bottom"],
                                  dt=w["dt"], rayleigh_sponge=sponge, viscous_sponge=sponge, params=P, rad=w.get("rad"), tracers=tracers,
+                                 vert_diff=w.get("vert_diff"), implicit_diffusion=w.get("implicit_diffusion", False), approximate_linear_solve_iters=2,
                                  comms=comms if nranks > 1 else None)
     fused = not args.unfused
     nh_local = sim.Y.c.shape[0]
