@@ -50,7 +50,8 @@ class Params(C.Structure):
         ("tracer_upwinding", C.c_int32), ("held_suarez", C.c_int32)] + [(n, C.c_double) for n in ("hs_day", "hs_sigma_b", "hs_dT_y", "hs_T_equator",
                                                                "hs_dtheta_z", "hs_T_min", "MSLP")] + [("sem_quasimonotone_limiter", C.c_int32)] + [
         (n, C.c_int32) for n in ("vert_diff", "implicit_diffusion", "approximate_linear_solve_iters",
-                                 "disable_momentum_vertical_diffusion")] + [(n, C.c_double) for n in ("C_E", "H_diffusion", "D_0_diffusion")]
+                                 "disable_momentum_vertical_diffusion")] + [(n, C.c_double) for n in ("C_E", "H_diffusion", "D_0_diffusion")] + [
+        ("vertical_water_borrowing_limiter", C.c_int32)]
 
 
 class CachePtrs(C.Structure):
@@ -144,7 +145,8 @@ def make_params(P, N, grid) -> Params:
         implicit_diffusion=int(getattr(N, "implicit_diffusion", False)),
         approximate_linear_solve_iters=int(getattr(N, "approximate_linear_solve_iters", 1)),
         disable_momentum_vertical_diffusion=int(getattr(N, "disable_momentum_vertical_diffusion", False)),
-        C_E=getattr(P, "C_E", 0.0), H_diffusion=getattr(P, "H_diffusion", 1.0), D_0_diffusion=getattr(P, "D_0_diffusion", 0.0))
+        C_E=getattr(P, "C_E", 0.0), H_diffusion=getattr(P, "H_diffusion", 1.0), D_0_diffusion=getattr(P, "D_0_diffusion", 0.0),
+        vertical_water_borrowing_limiter=int(getattr(N, "tracer_nonnegativity_method", None) == "vertical_water_borrowing"))
 
 
 def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1, n_tracers: int = 0):

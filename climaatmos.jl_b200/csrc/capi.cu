@@ -432,6 +432,7 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k_ldiv<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_t_post_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
   CK(cudaFuncSetAttribute(k_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(18)));
+  CK(cudaFuncSetAttribute(k_lim_vborrow<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_vdiff_tend<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
@@ -1081,7 +1082,15 @@ static int launch_diff_scale(b200_ctx* c, FT* out, const FT* a, const FT* b, FT 
 template <class FT>
 static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
   const int ntr = c->dims.n_tracers, nh = c->dims.nh, nv = c->dims.nv, ng = c->dims.nh_ghost;
-  if (!c->prm.sem_quasimonotone_limiter || ntr == 0) return 0;
+  if (ntr == 0) return 0;
+  // second branch of lim! (limited_tendencies.jl:95-121): vertical mass borrowing, column-local, after the SEM limiter
+  auto vborrow = [&]() -> int {
+    if (!c->prm.vertical_water_borrowing_limiter) return 0;
+    k_lim_vborrow<FT><<<dim3(nh, ntr), NT, 2 * SLAB * sizeof(FT), s>>>((const VLev<FT>*)c->d_vlev, (FT*)Yc, c->ncf(), nv, (FT)0);
+    LAUNCH_CHECK(c);
+    return 0;
+  };
+  if (!c->prm.sem_quasimonotone_limiter) return vborrow();
   const bool multi = c->nranks > 1 && !c->nbr.empty();
   if (multi && (!c->p2p_ready || getenv("B200_HALO_NCCL")))
     return fail("b200_lim: on multi-rank contexts the limiter needs the peer-memory halo (neighbour bounds travel through it)");
@@ -1110,7 +1119,7 @@ static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
   k_lim_apply<FT><<<dim3(nh, ntr), 64, 0, s>>>((FT*)Yc, c->ncf(), nv, nh, (const FT*)c->d_lim_bnd, c->d_lim_nbr_off, c->d_lim_nbr, (const FT*)c->d_hgeo,
                                             multi ? (const FT*)c->p2p_buf : nullptr, (long long)c->p2p_cap, c->d_p2p_seq, c->d_lim_ghost_node, ntr);
   LAUNCH_CHECK(c);
-  return 0;
+  return vborrow();
 }
 extern "C" int b200_lim(b200_ctx* c, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double, void* stream) {
   (void)Yf; (void)ref_Yf;
@@ -1234,7 +1243,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   const Tableau tb = ars343();
   const double dt = c->prm.dt;
   // lim! between the limited and the unlimited increments (CTS update_stage!): only when a limiter is configured AND tracers exist
-  const bool limiter = c->prm.sem_quasimonotone_limiter && c->dims.n_tracers > 0;
+  const bool limiter = (c->prm.sem_quasimonotone_limiter || c->prm.vertical_water_borrowing_limiter) && c->dims.n_tracers > 0;
   if (limiter)
     for (int i = 0; i < 4; ++i)
       if (!c->Tlc[i]) CK(cudaMalloc(&c->Tlc[i], bc));

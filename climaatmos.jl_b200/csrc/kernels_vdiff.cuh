@@ -431,4 +431,45 @@ __global__ void __launch_bounds__(NT) k_ldiv_diff(Par<FT> P, VDiff<FT> D, const 
   VD_FOR_POINTS(n, v) { if (v < nv) gdc[(3 * 16 + n) * nv + v] = ye[n * LVP + v]; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// lim!, second branch (src/prognostic_equations/limited_tendencies.jl:95-121): ClimaCore Limiters.VerticalMassBorrowingLimiter((0,))
+// applied to χ = ρχ/ρ of every tracer, then ρχ = χ·ρ [UPSTREAM-RECALL ClimaCore 0.15.1 src/Limiters/vertical_mass_borrowing_limiter.jl,
+// after E3SM's massborrow]: per column, sweep level 1 → Nv carrying the mass deficit (weights ρ·Δz), then Nv → 1 while a deficit
+// remains.  One (element, tracer) per CTA: the two slabs are staged with coalesced loads, 16 lanes do the two sweeps.
+template <class FT>
+__global__ void __launch_bounds__(NT) k_lim_vborrow(const VLev<FT>* __restrict__ vlev, FT* Yc, int ncf, int nv, FT qmin) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  FT* sq = sm.take(SLAB); FT* sr = sm.take(SLAB);
+  const int h = blockIdx.x, t = blockIdx.y;
+  FT* gY = Yc + (size_t)h * ncf * 16 * nv;
+  FT* gq = gY + (size_t)(4 + t) * 16 * nv;
+  load_slab(sr, gY, nv); load_slab(sq, gq, nv);
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    FT* q = sq + threadIdx.x * LVP;
+    const FT* r = sr + threadIdx.x * LVP;
+    FT bmass = FT(0);
+    for (int v = 0; v < nv; ++v) {
+      const FT m = r[v] * vlev->dzc[v];
+      const FT nmass = q[v] / r[v] + bmass / m;
+      if (nmass > qmin) { q[v] = nmass; bmass = FT(0); }
+      else { bmass = (nmass - qmin) * m; q[v] = qmin; }
+    }
+    for (int v = nv - 1; v >= 0; --v) {
+      if (bmass < FT(0)) {
+        const FT m = r[v] * vlev->dzc[v];
+        const FT nmass = q[v] + bmass / m;
+        if (nmass > qmin) { q[v] = nmass; bmass = FT(0); }
+        else { bmass = (nmass - qmin) * m; q[v] = qmin; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    if (v < nv) gq[n * nv + v] = sq[n * LVP + v] * sr[n * LVP + v];
+  }
+}
+
 }  // namespace b200

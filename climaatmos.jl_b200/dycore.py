@@ -65,7 +65,7 @@ class AtmosSimulation:
                  rayleigh_sponge=False, viscous_sponge=False, hyperdiff=True, deep_atmosphere=True,
                  initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter", rad=None,
                  tracers=None, tracer_upwinding="vanleer_limiter", apply_sem_quasimonotone_limiter=False,
-                 vert_diff=None, implicit_diffusion=False, approximate_linear_solve_iters=1,
+                 vert_diff=None, implicit_diffusion=False, approximate_linear_solve_iters=1, tracer_nonnegativity_method=None,
                  params: DycoreParams | None = None, device=None, comms=None, grid=None):
         torch = _torch()
         self.torch = torch
@@ -79,7 +79,8 @@ class AtmosSimulation:
                                        # 397-402; momentum diffusion is off for Held–Suarez runs (type_getters.jl:46)
                                        vert_diff=vert_diff, implicit_diffusion=bool(implicit_diffusion),
                                        approximate_linear_solve_iters=int(approximate_linear_solve_iters),
-                                       disable_momentum_vertical_diffusion=(rad == "held_suarez"))
+                                       disable_momentum_vertical_diffusion=(rad == "held_suarez"),
+                                       tracer_nonnegativity_method=tracer_nonnegativity_method)
         self.grid = grid or make_sphere_grid(FT=self.FT, h_elem=h_elem, z_elem=z_elem, z_max=z_max, dz_bottom=dz_bottom,
                                              radius=self.params.planet_radius, deep_atmosphere=deep_atmosphere)
         self.comms = comms  # parallel.DistributedComms or None

@@ -66,6 +66,8 @@ class DycoreNumerics:
     tracer_upwinding: str = "vanleer_limiter"  # default_config.yml:321-323
     apply_sem_quasimonotone_limiter: bool = False  # default_config.yml (Limiters.QuasiMonotoneLimiter in lim!, type_getters.jl:129)
     held_suarez: bool = False
+    # default_config.yml:190-198: None | "vertical_water_borrowing" (Limiters.VerticalMassBorrowingLimiter in lim!, cache.jl:216-219)
+    tracer_nonnegativity_method: str | None = None
     # vertical diffusion: vert_diff ∈ {None, "VerticalDiffusion", "DecayWithHeightDiffusion"}
     # (default_config.yml:166-168, model_getters.jl:332-358); implicit_diffusion → diff_mode (type_getters.jl:131);
     # approximate_linear_solve_iters (default_config.yml:397-402); momentum diffusion is disabled for Held–Suarez runs

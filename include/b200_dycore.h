@@ -92,6 +92,9 @@ typedef struct {
    * disable_momentum_vertical_diffusion: scalars only (Held–Suarez runs, type_getters.jl:46). */
   int32_t vert_diff, implicit_diffusion, approximate_linear_solve_iters, disable_momentum_vertical_diffusion;
   double C_E, H_diffusion, D_0_diffusion;
+  /* tracer_nonnegativity_method: vertical_water_borrowing (default_config.yml:190-198; src/cache/cache.jl:216-219): lim! also applies
+   * ClimaCore's Limiters.VerticalMassBorrowingLimiter((0,)) to χ = ρχ/ρ of every tracer (limited_tendencies.jl:95-121); 0 = off */
+  int32_t vertical_water_borrowing_limiter;
 } b200_params;
 
 /* Optional device pointers to p.precomputed fields written by b200_cache_imp (any may be NULL).
@@ -151,8 +154,9 @@ int b200_axpy_n(b200_ctx*, void* Uc, void* Uf, const void* uc, const void* uf, i
  * state (Yc, Yf) is advanced in place. `fused` selects the fused implicit-stage kernel. */
 int b200_step_ars343(b200_ctx*, void* Yc, void* Yf, double t, int32_t fused, void* stream);
 /* lim!(Y, p, t, ref_Y) (src/prognostic_equations/limited_tendencies.jl:64-122): SEM quasi-monotone limiter of every tracer ρχ of
- * Y.c (in place) with bounds from ref_Y (element min/max of χ widened over the vertex neighbours).  No-op unless
- * params.sem_quasimonotone_limiter and n_tracers > 0.  Multi-rank contexts: needs the peer-memory halo (b200_halo_import), which
+ * Y.c (in place) with bounds from ref_Y (element min/max of χ widened over the vertex neighbours), then — with
+ * params.vertical_water_borrowing_limiter — the column-wise vertical mass-borrowing limiter.  No-op unless one of the two is set
+ * and n_tracers > 0.  Multi-rank contexts: needs the peer-memory halo (b200_halo_import), which
  * carries the bounds of the ghost elements. */
 int b200_lim(b200_ctx*, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double t, void* stream);
 /* One fused implicit stage = one Newton iteration of ClimaTimeSteppers' implicit solve on the stage problem

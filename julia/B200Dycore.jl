@@ -53,6 +53,7 @@ struct ParamsC
     approximate_linear_solve_iters::Int32
     disable_momentum_vertical_diffusion::Int32
     C_E::Float64; H_diffusion::Float64; D_0_diffusion::Float64
+    vertical_water_borrowing_limiter::Int32
 end
 struct CachePtrs
     u_c::Ptr{Cvoid}; u3_f::Ptr{Cvoid}; K_c::Ptr{Cvoid}; T_c::Ptr{Cvoid}; p_c::Ptr{Cvoid}; h_tot_c::Ptr{Cvoid}
@@ -128,7 +129,8 @@ function create(Y, p; approximate_solve_iters = 1)   # = B200Jacobian(...).appro
                   Int32(approximate_solve_iters), CA.disable_momentum_vertical_diffusion(vd) ? 1 : 0,
                   vd isa CA.VerticalDiffusion ? Float64(vd.C_E) : 0.0,
                   vd isa CA.DecayWithHeightDiffusion ? Float64(vd.H) : 1.0,
-                  vd isa CA.DecayWithHeightDiffusion ? Float64(vd.D₀) : 0.0)
+                  vd isa CA.DecayWithHeightDiffusion ? Float64(vd.D₀) : 0.0,
+                  p.numerics.vertical_water_borrowing_limiter === nothing ? 0 : 1)                # cache.jl:213-219
     comms = ClimaComms.context(Y.c)
     rank, nranks = ClimaComms.mypid(comms) - 1, ClimaComms.nprocs(comms)
     id = zeros(UInt8, 128)

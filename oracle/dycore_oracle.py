@@ -791,13 +791,45 @@ class Oracle:
         rhoq[...] = x.reshape(rhoq.shape)
 
     def limiters_func(self, Yc, ref_Yc):
-        """lim!(Y, p, t, ref_Y) (limited_tendencies.jl:64-122) for the SEM quasi-monotone limiter: bounds from ref_Y, applied to
-        every tracer of Y.c in place.  No-op unless ``apply_sem_quasimonotone_limiter``."""
-        if not getattr(self.N, "apply_sem_quasimonotone_limiter", False):
-            return
-        for q in range(4, Yc.shape[1]):
-            qmin, qmax = self.limiter_bounds(ref_Yc[:, q], ref_Yc[:, 0])
-            self.apply_limiter(Yc[:, q], Yc[:, 0], qmin, qmax)
+        """lim!(Y, p, t, ref_Y) (limited_tendencies.jl:64-122): the SEM quasi-monotone limiter (bounds from ref_Y, applied to every
+        tracer of Y.c in place; ``apply_sem_quasimonotone_limiter``), then the vertical mass-borrowing limiter
+        (``tracer_nonnegativity_method: vertical_water_borrowing``).  No-op when neither is configured."""
+        if getattr(self.N, "apply_sem_quasimonotone_limiter", False):
+            for q in range(4, Yc.shape[1]):
+                qmin, qmax = self.limiter_bounds(ref_Yc[:, q], ref_Yc[:, 0])
+                self.apply_limiter(Yc[:, q], Yc[:, 0], qmin, qmax)
+        # :95-121 vertical water borrowing (tracer_nonnegativity_method: vertical_water_borrowing, cache.jl:216-219):
+        # χ = ρχ/ρ in scratch, Limiters.apply_limiter!(χ, ρ, VerticalMassBorrowingLimiter((0,))), ρχ = χ·ρ; all tracers
+        # (vertical_water_borrowing_species = nothing)
+        if getattr(self.N, "tracer_nonnegativity_method", None) == "vertical_water_borrowing":
+            rho = Yc[:, 0]
+            for q in range(4, Yc.shape[1]):
+                chi = Yc[:, q] / rho
+                self.vertical_mass_borrowing(chi, rho)
+                Yc[:, q] = chi * rho
+
+    def vertical_mass_borrowing(self, q, rho, qmin=0.0):
+        """ClimaCore ``Limiters.apply_limiter!(q, ρ, ::VerticalMassBorrowingLimiter)`` [UPSTREAM-RECALL ClimaCore 0.15.1
+        src/Limiters/vertical_mass_borrowing_limiter.jl, after E3SM's ``massborrow``]: per column, sweep level 1 → Nv carrying the
+        mass deficit ``bmass`` (weights ρ·Δz) — a level that would end below ``qmin`` is set to ``qmin`` and passes its deficit on —
+        then sweep Nv → 1 while a deficit remains.  In place on ``q``."""
+        FT = self.FT
+        m = rho * np.asarray(self.grid.dz_c, dtype=FT)  # ρ · Fields.Δz_field
+        qm = FT(qmin)
+        bmass = np.zeros_like(q[..., 0])
+        nv = q.shape[-1]
+        for v in range(nv):
+            nmass = q[..., v] + bmass / m[..., v]
+            pos = nmass > qm
+            q[..., v] = np.where(pos, nmass, qm)
+            bmass = np.where(pos, FT(0), (nmass - qm) * m[..., v])
+        for v in range(nv - 1, -1, -1):
+            need = bmass < 0
+            nmass = q[..., v] + bmass / m[..., v]
+            pos = nmass > qm
+            q[..., v] = np.where(need, np.where(pos, nmass, qm), q[..., v])
+            bmass = np.where(need, np.where(pos, FT(0), (nmass - qm) * m[..., v]), bmass)
+        return q
 
     # ------------------------------------------------------------------ T_exp_T_lim!
     def vector_laplacian(self, u1, u2, u3, G):
@@ -995,7 +1027,8 @@ class Oracle:
         uc, uf = Yc, Yf
         nel = Yc.shape[0]
         Texp, Timp, Tlim = [None] * 4, [None] * 4, [None] * 4
-        limiter = bool(getattr(self.N, "apply_sem_quasimonotone_limiter", False)) and Yc.shape[1] > 4
+        limiter = (bool(getattr(self.N, "apply_sem_quasimonotone_limiter", False))
+                   or getattr(self.N, "tracer_nonnegativity_method", None) == "vertical_water_borrowing") and Yc.shape[1] > 4
         log = (lambda s: trace.append(s)) if trace is not None else (lambda s: None)
         nolog = lambda s: None
         if pool is not None and nchunks > 1:

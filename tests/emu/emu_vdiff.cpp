@@ -60,3 +60,26 @@ extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, 
   run_grid(nh, [&] { k_ldiv_diff<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
   return 0;
 }
+
+// k_lim_vborrow on every (element, tracer): Yc in place; dzc [64]
+extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv, int ncf, const double* dzc, double* Yc) {
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  memcpy(V.dzc, dzc, 64 * sizeof(FT));
+  for (int t = 0; t < ncf - 4; ++t) {
+    std::barrier<> bar(NT);
+    g_cta_barrier = &bar;
+    std::vector<std::thread> th;
+    for (int k = 0; k < NT; ++k)
+      th.emplace_back([&, k] {
+        for (int b = 0; b < nh; ++b) {
+          threadIdx = {(unsigned)k, 0, 0};
+          blockIdx = {(unsigned)b, (unsigned)t, 0};
+          k_lim_vborrow<FT>(&V, Yc, ncf, nv, 0.0);
+          bar.arrive_and_wait();
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  return 0;
+}

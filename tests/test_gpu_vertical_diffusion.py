@@ -147,3 +147,35 @@ def test_step_with_vertical_diffusion_matches_oracle(FT, implicit):
     assert rel(hc, gc) <= (1e-12 if t64 else 1e-5)
     sim.close()
     sim2.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
+                    reason="k_lim_vborrow was written after the round's GPU budget was spent: it matches the oracle bit for bit in the CPU "
+                           "CTA emulator (tests/test_vdiff_kernels_cpu_emulation.py) but has not run on a B200 yet (set B200_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_vertical_mass_borrowing_limiter_matches_oracle(FT):
+    """lim! with tracer_nonnegativity_method: vertical_water_borrowing (limited_tendencies.jl:95-121) through b200_lim, and a step."""
+    P = prm.DycoreParams()
+    tr = [lambda lat, lon, z: 4e-4 + 1e-3 * np.cos(z / 700.0) * np.cos(3 * np.radians(lat)) + 0 * lon]
+    sim = dycore.AtmosSimulation(FT=FT, h_elem=3, z_elem=10, z_max=30000.0, dz_bottom=500.0, dt=200.0, params=P, tracers=tr,
+                                 tracer_nonnegativity_method="vertical_water_borrowing")
+    o = Oracle(sim.grid, P, sim.numerics, FT)
+    Yc, Yf = sim.Y.cpu()
+    assert (Yc[:, 4] < 0).any()
+    ref = Yc.copy()
+    o.limiters_func(ref, Yc)
+    Y = sim.to_device(Yc, Yf)
+    sim.limiters_func(Y, 0.0, Y)
+    gc, _ = Y.cpu()
+    assert (gc[:, 4] >= 0).all()
+    assert np.array_equal(gc[:, :4], Yc[:, :4])
+    assert rel(gc[:, 4], ref[:, 4]) <= (1e-14 if FT == np.float64 else 1e-6)
+    Yc0, Yf0 = sim.Y.cpu()
+    sim.step(fused=True)
+    torch.cuda.synchronize()
+    gc, gf = sim.Y.cpu()
+    o64 = Oracle(sim.grid, P, sim.numerics, np.float64)
+    oc, of = o64.step(Yc0.astype(np.float64), Yf0.astype(np.float64))
+    for k in range(5):
+        assert rel(gc[:, k], oc[:, k]) <= (1e-11 if FT == np.float64 else (1e-5 if k < 4 else 1e-4)), k
+    sim.close()

@@ -122,3 +122,24 @@ def test_second_generation_tendency_kernel_is_bitwise_identical(emu, vd, deep, d
     assert np.array_equal(g1, g2)
     for k in range(3 if dm else 1, g2.shape[1]):
         assert rel(g2[:, k], ot[:, k]) < 1e-11
+
+
+def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
+    """k_lim_vborrow (lim!, vertical_water_borrowing) on the CPU emulator against the oracle, bit for bit (same operation order)."""
+    P = prm.DycoreParams()
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius)
+    N = prm.DycoreNumerics(dt=100.0, tracer_nonnegativity_method="vertical_water_borrowing")
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(7)
+    chi = [1e-3 * rng.standard_normal(Yc[:, 0].shape) + 4e-4, 1e-3 * rng.standard_normal(Yc[:, 0].shape) - 2e-4]
+    Yc = np.ascontiguousarray(np.concatenate([Yc] + [(Yc[:, 0] * c)[:, None] for c in chi], axis=1))
+    ref = Yc.copy()
+    o.limiters_func(ref, Yc)
+    got = Yc.copy()
+    dzc = np.concatenate([g.dz_c, np.zeros(64 - g.nv)])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emu.emu_vborrow(Yc.shape[0], g.nv, Yc.shape[1], p(dzc), p(got)) == 0
+    assert (got[:, 4:] >= 0).all() and (Yc[:, 4:] < 0).any()
+    assert np.array_equal(got[:, :4], Yc[:, :4])
+    assert np.array_equal(got, ref)
