@@ -299,3 +299,33 @@ def test_vertical_mass_borrowing_limiter():
     assert np.isfinite(c1).all()
     W = o2.c.WJ
     assert abs((W * c1[:, 4]).sum() - (W * Y2[:, 4]).sum()) < 1e-3 * (W * np.abs(Y2[:, 4])).sum()
+
+
+def test_reference_vertical_water_borrowing_case():
+    """test/prognostic_equations/vertical_water_borrowing_tests.jl:22-58 restated: q ≡ 0 (DecayingProfile has no water), the last
+    20 % of the column set to −1e-7, lim! → minimum ≥ 0.  (The reference's mass check is skipped there because the total is negative;
+    it pins non-negativity only, not the ρ·Δz weights, which stay [UPSTREAM-RECALL].)"""
+    g, P, N, o, Yc, Yf, rng = make(None, implicit=False, ntr=1)
+    N2 = dataclasses.replace(N, tracer_nonnegativity_method="vertical_water_borrowing")
+    o2 = Oracle(g, P, N2, np.float64)
+    Y = Yc.copy()
+    Y[:, 4] = 0.0
+    Y[:, 4, ..., -2:] = -1e-7
+    assert Y[:, 4].min() < 0
+    o2.limiters_func(Y, Yc)
+    assert Y[:, 4].min() >= 0
+    assert np.array_equal(Y[:, :4], Yc[:, :4])
+
+
+def test_reference_vertical_diffusion_structure():
+    """test/prognostic_equations/vertical_diffusion_tests.jl:17-101, the parts that exist on the dry + passive-tracer path:
+    DecayWithHeightDiffusion(disable_momentum_vertical_diffusion = true, H = 1, D₀ = 1): ρe_tot receives the dry-static-energy
+    contribution (:86), the passive grid-scale tracer diffuses with the full K_h (:100), ρ gets nothing without ρq_tot (:83)."""
+    g, P, N, o, Yc, Yf, rng = make("DecayWithHeightDiffusion", dm=True, D0=1.0, H=1.0)
+    rho = Yc[:, 0]
+    Yc[:, 4] = rho * np.cos(o.c.z / 3000.0)
+    pc = o.set_implicit_precomputed_quantities(Yc[:, :4], Yf)
+    Yt = np.zeros_like(Yc)
+    o.vertical_diffusion_boundary_layer_tendency(Yt, Yc, pc)
+    assert np.abs(Yt[:, 3]).max() > 0 and np.abs(Yt[:, 4]).max() > 0
+    assert np.all(Yt[:, 0] == 0) and np.all(Yt[:, 1:3] == 0)
