@@ -212,6 +212,7 @@ extern "C" int b200_build_dss_csr(const b200_topology* T, int32_t* off_out, int3
 }
 
 extern "C" int b200_debug_dss_csr(b200_ctx* c, const int32_t** off, const int32_t** mem, int32_t* nnodes, int32_t* nmem) {
+  if (!c) return fail("b200_debug_dss_csr: null context");
   *off = c->h_off.data(); *mem = c->h_mem.data();
   *nnodes = c->nnodes; *nmem = (int32_t)c->h_mem.size();
   return 0;
@@ -617,6 +618,7 @@ static int impl_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs*
   return 0;
 }
 extern "C" int b200_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs* o, void* stream) {
+  if (!c) return fail("b200_cache_imp: null context");
   return c->ft == 4 ? impl_cache_imp<float>(c, Yc, Yf, o, (cudaStream_t)stream) : impl_cache_imp<double>(c, Yc, Yf, o, (cudaStream_t)stream);
 }
 
@@ -643,6 +645,7 @@ static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const v
   return 0;
 }
 extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
+  if (!c) return fail("b200_t_imp: null context");
   return c->ft == 4 ? impl_t_imp<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_imp<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
 
@@ -662,6 +665,7 @@ static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, c
   return 0;
 }
 extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, double, void* stream) {
+  if (!c) return fail("b200_wfact: null context");
   return c->ft == 4 ? impl_wfact<float>(c, Yc, Yf, dtg, (cudaStream_t)stream) : impl_wfact<double>(c, Yc, Yf, dtg, (cudaStream_t)stream);
 }
 
@@ -682,6 +686,7 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
   return 0;
 }
 extern "C" int b200_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, void* stream) {
+  if (!c) return fail("b200_ldiv: null context");
   return c->ft == 4 ? impl_ldiv<float>(c, dYc, dYf, Rc, Rf, (cudaStream_t)stream) : impl_ldiv<double>(c, dYc, dYf, Rc, Rf, (cudaStream_t)stream);
 }
 
@@ -693,6 +698,7 @@ static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const 
   return 0;
 }
 extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
+  if (!c) return fail("b200_t_post_imp: null context");
   return c->ft == 4 ? impl_t_post<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_post<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
 
@@ -700,6 +706,7 @@ extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc
 // Peer-memory halo set-up
 static size_t p2p_state_slab(const b200_ctx* c) { return (size_t)(c->ncf() * 16 * c->dims.nv + 16 * (c->dims.nv + 1)); }
 extern "C" int b200_halo_export(b200_ctx* c, void* handle64_out) {
+  if (!c) return fail("b200_halo_export: null context");
   if (c->nbr.empty()) return fail("b200_halo_export: context has no neighbours");
   if (!c->p2p_buf) {
     c->p2p_cap = p2p_state_slab(c) * (size_t)std::max(1, (int)c->dims.nh_ghost) * c->ft;
@@ -714,6 +721,7 @@ extern "C" int b200_halo_export(b200_ctx* c, void* handle64_out) {
   return 0;
 }
 extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t* their_recv_offset, const int32_t* their_nh_ghost) {
+  if (!c) return fail("b200_halo_import: null context");
   if (!c->p2p_buf) return fail("b200_halo_import: call b200_halo_export first");
   const int nn = (int)c->nbr.size();
   std::vector<int*> flags(nn);
@@ -924,6 +932,7 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
 }
 extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, const int32_t* is_face, const int32_t* kind,
                         int32_t nfields, void* stream) {
+  if (!c) return fail("b200_dss: null context");
   if (nfields > 8) return fail("b200_dss: at most 8 fields per call");
   DssField F[8];
   for (int k = 0; k < nfields; ++k) F[k] = {fields[k], nf[k], is_face[k], kind[k]};
@@ -958,6 +967,7 @@ static int impl_axpy(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void
 }
 extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int32_t n, const void* const* Tc,
                            const void* const* Tf, const double* coef, void* stream) {
+  if (!c) return fail("b200_axpy_n: null context");
   return c->ft == 4 ? impl_axpy<float>(c, Uc, Uf, uc, uf, n, Tc, Tf, coef, (cudaStream_t)stream)
                     : impl_axpy<double>(c, Uc, Uf, uc, uf, n, Tc, Tf, coef, (cudaStream_t)stream);
 }
@@ -1030,6 +1040,7 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
   return 0;
 }
 extern "C" int b200_t_exp_phase(b200_ctx* c, int32_t phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, void* stream) {
+  if (!c) return fail("b200_t_exp_phase: null context");
   return c->ft == 4 ? impl_t_exp_phase<float>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream)
                     : impl_t_exp_phase<double>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
@@ -1046,6 +1057,7 @@ static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, c
 }
 extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, double,
                               void* stream) {
+  if (!c) return fail("b200_t_exp_lim: null context");
   return c->ft == 4 ? impl_t_exp<float>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream)
                     : impl_t_exp<double>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream);
 }
@@ -1122,6 +1134,7 @@ static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
   return vborrow();
 }
 extern "C" int b200_lim(b200_ctx* c, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double, void* stream) {
+  if (!c) return fail("b200_lim: null context");
   (void)Yf; (void)ref_Yf;
   return c->ft == 4 ? impl_lim<float>(c, Yc, ref_Yc, (cudaStream_t)stream) : impl_lim<double>(c, Yc, ref_Yc, (cudaStream_t)stream);
 }
@@ -1224,7 +1237,8 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
   return 0;
 }
 extern "C" int b200_implicit_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtgamma, void* stream) {
-  if (c && vdiff_implicit(c)) return fail("b200_implicit_stage: implicit vertical diffusion is served by the hook entry points (b200_wfact, b200_t_imp, b200_ldiv)");
+  if (!c) return fail("b200_implicit_stage: null context");
+  if (vdiff_implicit(c)) return fail("b200_implicit_stage: implicit vertical diffusion is served by the hook entry points (b200_wfact, b200_t_imp, b200_ldiv)");
   return c->ft == 4 ? impl_imp_stage<float>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream)
                     : impl_imp_stage<double>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream);
 }
@@ -1399,6 +1413,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   return fused ? 0 : impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
 }
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
+  if (!c) return fail("b200_step_ars343: null context");
   cudaStream_t s = (cudaStream_t)stream;
   // implicit vertical diffusion: the fused implicit-stage kernel does not carry the diffusion blocks yet — the stage runs through
   // the hook sequence (cache_imp!, Wfact, T_imp!, ldiv!, T_post_imp!) of the literal path

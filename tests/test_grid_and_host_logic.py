@@ -147,6 +147,31 @@ def test_create_without_gpu_fails_loudly(lib):
         dycore.AtmosSimulation(h_elem=2, z_elem=4)
 
 
+def test_entry_points_reject_a_null_context(lib):
+    """Error convention of the C-ABI (include/b200_dycore.h): <0 and a message via b200_last_error, nothing crosses as a crash —
+    the glue turns it into the exception solve_atmos! catches (src/simulation/solve.jl:140-149).  No device is touched."""
+    import ctypes as C
+    from climaatmos_jl_b200 import capi
+
+    lib = C.CDLL(capi.LIB_PATH)  # a handle without the argtypes of capi.load(): every argument is passed as a raw pointer / scalar
+    z = C.c_void_p(None)
+    calls = {
+        "b200_cache_imp": (z, z, z, z, z), "b200_t_imp": (z, z, z, z, z, C.c_double(0), z),
+        "b200_wfact": (z, z, z, C.c_double(1), C.c_double(0), z), "b200_ldiv": (z, z, z, z, z, z),
+        "b200_t_post_imp": (z, z, z, z, z, C.c_double(0), z), "b200_t_exp_lim": (z, z, z, z, z, z, z, C.c_double(0), z),
+        "b200_dss": (z, z, z, z, z, C.c_int32(0), z), "b200_axpy_n": (z, z, z, z, z, C.c_int32(0), z, z, z, z),
+        "b200_lim": (z, z, z, z, z, C.c_double(0), z), "b200_implicit_stage": (z, z, z, z, z, C.c_double(1), z),
+        "b200_step_ars343": (z, z, z, C.c_double(0), C.c_int32(1), z), "b200_halo_export": (z, z), "b200_halo_import": (z, z, z, z),
+    }
+    lib.b200_last_error.restype = C.c_char_p
+    for name, args in calls.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        assert fn(*args) < 0, name
+        assert name.encode() in lib.b200_last_error() and b"null context" in lib.b200_last_error()
+    assert lib.b200_destroy(z) == 0
+
+
 def test_ctypes_mirrors_match_the_c_structs(tmp_path):
     """The drop-in boundary is plain C structs: the ctypes mirrors in capi.py (what the tests and bench.py bind through, and the
     template for the Julia `struct` mirrors of INTEGRATION.md) must have exactly the size and field offsets gcc gives the structs of
