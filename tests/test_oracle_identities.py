@@ -272,6 +272,17 @@ def test_golden_regression():
     assert np.linalg.norm(Yf - d["Yf"]) <= 1e-11 * np.linalg.norm(d["Yf"])
 
 
+def test_golden_regression_vertical_diffusion_and_limiters():
+    """Second committed fixture: implicit VerticalDiffusion (2 solver iterations) + one tracer + the vertical mass-borrowing limiter."""
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_step_vdiff_he2_ze8_f64.npz"))
+    from tests.golden.make_golden import run_case_vdiff
+
+    Yc, Yf = run_case_vdiff()
+    for k in range(5):
+        assert np.linalg.norm(Yc[:, k] - d["Yc"][:, k]) <= 1e-12 * np.linalg.norm(d["Yc"][:, k])
+    assert np.linalg.norm(Yf - d["Yf"]) <= 1e-11 * np.linalg.norm(d["Yf"])
+
+
 def _with_tracers(case, nq=2):
     g, P, N, o, Yc, Yf, rng = case
     zz = np.broadcast_to(g.z_c, Yc[:, 0].shape)
