@@ -692,6 +692,11 @@ extern "C" int b200_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, cons
 
 template <class FT>
 static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
+  if (c->prm.energy_upwinding == 0) {  // vtt(:none) − vtt(:none) ≡ 0 (the reference does not even wire the hook, integrator.jl:212-214)
+    CK(cudaMemsetAsync(Ytc, 0, c->nc() * sizeof(FT), s));
+    CK(cudaMemsetAsync(Ytf, 0, c->nf() * sizeof(FT), s));
+    return 0;
+  }
   k_t_post_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                             (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);

@@ -83,3 +83,34 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
   }
   return 0;
 }
+
+// The dry hook kernels of kernels_implicit.cuh (validated on the B200; emulated here so that the CPU test tier exercises the
+// product source too): cache_imp! → T_imp! → Wfact → ldiv! → T_post_imp!, and the fused k_imp_stage on a copy of the state.
+// sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
+// Ytc/Ytf (T_imp), dYc/dYf (ldiv of Rc/Rf), Ypc (T_post_imp centres), Sc/Sf (state after the fused stage).
+extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, int ncf, const double* sc, const double* vl,
+                                                                const double* hgeo, const double* Yc, double* Yf, const double* Rc,
+                                                                const double* Rf, double* Kc, double* Tc, double* pc, double* hc,
+                                                                double* Ytc, double* Ytf, double* jac, double* dYc, double* dYf,
+                                                                double* Ypc, double* Ypf, double* Sc, double* Sf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = ncf; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[16];
+  const FT dtg = sc[14];
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  run_grid(nh, [&] { k_cache_imp<FT>(P, hgeo, &V, Yc, Yf, (FT*)nullptr, (FT*)nullptr, Kc, Tc, pc, hc); });
+  run_grid(nh, [&] { k_t_imp<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+  run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+  run_grid(nh, [&] { k_ldiv<FT>(P, jac, Rc, Rf, dYc, dYf); });
+  run_grid(nh, [&] { k_t_post_imp<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  const size_t nc = (size_t)nh * ncf * 16 * nv, nf = (size_t)nh * 16 * (nv + 1);
+  memcpy(Sc, Yc, nc * sizeof(FT));
+  memcpy(Sf, Yf, nf * sizeof(FT));
+  run_grid(nh, [&] { k_imp_stage<FT>(P, hgeo, &V, Sc, Sf, dtg); });
+  return 0;
+}

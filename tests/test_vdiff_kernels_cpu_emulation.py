@@ -143,3 +143,67 @@ def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
     assert (got[:, 4:] >= 0).all() and (Yc[:, 4:] < 0).any()
     assert np.array_equal(got[:, :4], Yc[:, :4])
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("upw,rayleigh,deep", [("vanleer_limiter", True, True), ("first_order", False, False), ("none", False, True)])
+def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
+    """k_cache_imp, k_t_imp, k_wfact → k_ldiv, k_t_post_imp and the fused k_imp_stage (kernels_implicit.cuh) on the CPU emulator against
+    the oracle's cache_imp! / T_imp! / Wfact + ldiv! / T_post_imp! / one Newton iteration of the implicit stage (Float64)."""
+    P = prm.DycoreParams(zd_rayleigh=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
+    N = prm.DycoreNumerics(dt=250.0, rayleigh_sponge=rayleigh, energy_upwinding=upw)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(99)
+    Yc = np.ascontiguousarray(Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape)))
+    Yf = np.ascontiguousarray(0.3 * g.dz_f * rng.standard_normal(Yf.shape))  # boundary faces non-zero: cache_imp! must filter them
+    nh, ncf, nv = Yc.shape[0], Yc.shape[1], g.nv
+    dtg = 0.4358665215084590 * N.dt
+    s_c = (g.radius + g.z_c) / g.radius if deep else np.ones(nv)
+    s_f = (g.radius + g.z_f) / g.radius if deep else np.ones(nv + 1)
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    brw = o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if rayleigh else np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif), pad(brw)])
+    A = g.dxdxi
+    Ginv = np.linalg.inv(np.einsum("...ab,...ac->...bc", A, A))
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), 0, 0, 0, 0, dtg,
+                   0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw]])
+    Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
+    Rf = rng.standard_normal(Yf.shape)
+    z4 = lambda: np.zeros((nh, 16, nv))
+    Kc, Tc, pc_, hc = z4(), z4(), z4(), z4()
+    Ytc, Ytf, dYc, dYf, Ypc, Ypf, Sc, Sf = (np.zeros_like(a) for a in (Yc, Yf, Yc, Yf, Yc, Yf, Yc, Yf))
+    jac = np.zeros((nh, 15, 16, nv + 1))
+    gYf = Yf.copy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emu.emu_hooks(nh, nv, ncf, p(sc), p(vl), p(hgeo), p(Yc), p(gYf), p(Rc), p(Rf), p(Kc), p(Tc), p(pc_), p(hc), p(Ytc), p(Ytf), p(jac),
+                         p(dYc), p(dYf), p(Ypc), p(Ypf), p(Sc), p(Sf)) == 0
+    oc, of = Yc.copy(), Yf.copy()
+    pc = o.set_implicit_precomputed_quantities(oc, of)
+    assert np.array_equal(gYf, of) and np.all(gYf[..., 0] == 0) and np.all(gYf[..., -1] == 0)
+    sh = Yc[:, 0].shape
+    for got, key in ((Kc, "K"), (Tc, "T"), (pc_, "p"), (hc, "h_tot")):
+        assert rel(got.reshape(sh), pc[key]) < 1e-13, key
+    tc, tf = o.implicit_tendency(oc, of, pc)
+    assert rel(Ytc[:, 0], tc[:, 0]) < 1e-12 and rel(Ytc[:, 3], tc[:, 3]) < 1e-12 and rel(Ytf, tf) < 1e-11
+    assert np.all(Ytc[:, 1:3] == 0)
+    Jm = o.update_jacobian(oc, of, pc, dtg)
+    dc, df = o.ldiv(Jm, Rc, Rf)
+    for k in range(4):
+        assert rel(dYc[:, k], dc[:, k]) < 1e-11, k
+    assert rel(dYf, df) < 1e-11
+    pc_c, pc_f = o.correct_implicit_advection_tendency(oc, of, pc)
+    if upw != "none":  # with :none the host returns zeros without launching the kernel (capi.cu: impl_t_post)
+        assert rel(Ypc[:, 3], pc_c[:, 3]) < 1e-10
+    assert np.all(Ypc[:, :3] == 0) and np.all(Ypf == 0)
+    Uc, Uf = Yc.copy(), Yf.copy()
+    o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
+    for k in range(4):
+        assert rel(Sc[:, k], Uc[:, k]) < 1e-12, k
+    assert rel(Sf, Uf) < 1e-10
