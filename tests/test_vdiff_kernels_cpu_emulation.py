@@ -33,9 +33,9 @@ def emu():
     return C.CDLL(so)
 
 
-def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1):
+def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12, dzb=400.0):
     P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
-    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
     N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=iters,
                            disable_momentum_vertical_diffusion=dm, rayleigh_sponge=rayleigh)
     o = Oracle(g, P, N, np.float64)
@@ -207,3 +207,15 @@ def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
     for k in range(4):
         assert rel(Sc[:, k], Uc[:, k]) < 1e-12, k
     assert rel(Sf, Uf) < 1e-10
+
+
+@pytest.mark.parametrize("ze,dzb", [(2, 15000.0), (3, 5000.0), (63, 30.0)])
+@pytest.mark.parametrize("tend_kernel", [1, 2])
+def test_emulated_vdiff_kernels_at_the_column_height_limits(emu, ze, dzb, tend_kernel):
+    """Minimum (2, 3 levels) and maximum (63 levels = 64 faces, the LV = 64 limit of the slab layout) column heights."""
+    (gt, gc, gf), (ot, oc, of) = run_case(emu, "VerticalDiffusion", True, False, 2, 1, tend_kernel=tend_kernel, ze=ze, dzb=dzb)
+    for k in range(1, gt.shape[1]):
+        assert rel(gt[:, k], ot[:, k]) < 1e-10, ("tend", k)
+    for k in range(gc.shape[1]):
+        assert rel(gc[:, k], oc[:, k]) < 1e-9, ("ldiv", k)
+    assert rel(gf, of) < 1e-9
