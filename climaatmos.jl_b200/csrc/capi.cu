@@ -141,6 +141,8 @@ struct b200_ctx {
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
   int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
   int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
+  int ldiv_diff = 1;     // B200_LDIV_DIFF=1|2: k_vdiff_jac + k_ldiv_diff (Thomas sweeps by 16 lanes; validated on B200) or k_vdiff_jac2 + k_ldiv_diff2 (no slabs / parallel cyclic reduction;
+                         // matches the oracle in the CPU CTA emulator, not yet run on a B200)
   int vdiff_kernel = 2;  // B200_VDIFF_KERNEL=2|1: k_vdiff_tend2 (quarter element per CTA, no state slabs; 77 µs at he30) or k_vdiff_tend (element slabs, 267 µs)
   int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
   int ncf() const { return 4 + dims.n_tracers; }
@@ -437,6 +439,7 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k_vdiff_tend<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
+  CK(cudaFuncSetAttribute(k_ldiv_diff2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((24 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_texp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(22)));
   CK(cudaFuncSetAttribute(k_texp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
   return 0;
@@ -470,6 +473,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
   if (const char* e = getenv("B200_VDIFF_KERNEL")) c->vdiff_kernel = atoi(e);
+  if (const char* e = getenv("B200_LDIV_DIFF")) c->ldiv_diff = atoi(e);
   if (d->n_tracers > 0 && (c->legacy || (c->imp_kernel != 2 && c->imp_kernel != 5))) {
     delete c;
     return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
@@ -657,9 +661,14 @@ static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, c
   LAUNCH_CHECK(c);
   if (vdiff_implicit(c)) {  // update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261)
     if (!c->d_jacd) CK(cudaMalloc(&c->d_jacd, (size_t)c->dims.nh * JD_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
-    k_vdiff_jac<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-                                                             (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT)dtg,
-                                                             (FT*)c->d_jacd);
+    if (c->ldiv_diff == 2)  // quarter element per CTA, no state slabs (same planes)
+      k_vdiff_jac2<FT><<<c->dims.nh * 4, NT, 2 * 4 * VD2_ST * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                                            (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf,
+                                                                            (FT)dtg, (FT*)c->d_jacd);
+    else
+      k_vdiff_jac<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                               (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT)dtg,
+                                                               (FT*)c->d_jacd);
     LAUNCH_CHECK(c);
   }
   return 0;
@@ -674,9 +683,14 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
   if (!c->d_jac) return fail("b200_ldiv: b200_wfact has not been called");
   if (vdiff_implicit(c)) {  // ApproximateBlockArrowheadIterativeSolve (manual_sparse_jacobian.jl:538-578)
     if (!c->d_jacd) return fail("b200_ldiv: b200_wfact has not been called");
-    k_ldiv_diff<FT><<<c->dims.nh, NT, (22 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
-                                                                 (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
-                                                                 (const FT*)Rf, (FT*)dYc, (FT*)dYf);
+    if (c->ldiv_diff == 2)  // parallel cyclic reduction instead of 16-lane Thomas sweeps
+      k_ldiv_diff2<FT><<<c->dims.nh, NT, (24 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
+                                                                    (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
+                                                                    (const FT*)Rf, (FT*)dYc, (FT*)dYf);
+    else
+      k_ldiv_diff<FT><<<c->dims.nh, NT, (22 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
+                                                                   (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
+                                                                   (const FT*)Rf, (FT*)dYc, (FT*)dYf);
     LAUNCH_CHECK(c);
     return 0;
   }

@@ -35,7 +35,7 @@ static void run_grid(int nblocks, F&& body) {
   for (auto& x : th) x.join();
 }
 
-// sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ, tendency kernel (1|2)
+// sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ, tendency kernel (1|2), [16] unused here, [17] ldiv kernel (1 Thomas | 2 PCR)
 // vl: [11][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw ; hgeo: [nh][HG_N][16] ; kdec [64]
 extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, int ncf, const double* sc, const double* vl, const double* hgeo, const double* kdec,
                          const double* Yc, const double* Yf, const double* Rc, const double* Rf, double* Ytc, double* jac,
@@ -56,8 +56,10 @@ extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, 
   if ((int)sc[15] == 2) run_grid(nh * 4, [&] { k_vdiff_tend2<FT>(P, D, hgeo, &V, Yc, Yf, Ytc); });
   else run_grid(nh, [&] { k_vdiff_tend<FT>(P, D, hgeo, &V, Yc, Yf, Ytc); });
   run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
-  run_grid(nh, [&] { k_vdiff_jac<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
-  run_grid(nh, [&] { k_ldiv_diff<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
+  if ((int)sc[17] == 2) run_grid(nh * 4, [&] { k_vdiff_jac2<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
+  else run_grid(nh, [&] { k_vdiff_jac<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
+  if ((int)sc[17] == 2) run_grid(nh, [&] { k_ldiv_diff2<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
+  else run_grid(nh, [&] { k_ldiv_diff<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
   return 0;
 }
 

@@ -179,3 +179,37 @@ def test_vertical_mass_borrowing_limiter_matches_oracle(FT):
     for k in range(5):
         assert rel(gc[:, k], oc[:, k]) <= (1e-11 if FT == np.float64 else (1e-5 if k < 4 else 1e-4)), k
     sim.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
+                    reason="k_vdiff_jac2 / k_ldiv_diff2 (B200_LDIV_DIFF=2) match the oracle in the CPU CTA emulator but have not run on a B200 yet "
+                           "(set B200_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_pcr_variant_of_the_iterative_solve(FT, monkeypatch):
+    """B200_LDIV_DIFF=2: Wfact planes from k_vdiff_jac2 and ldiv! by parallel cyclic reduction (k_ldiv_diff2), against the oracle and a step."""
+    monkeypatch.setenv("B200_LDIV_DIFF", "2")
+    sim, o, Yc, Yf, rng = make(FT, "VerticalDiffusion", True)
+    Y = sim.to_device(Yc, Yf)
+    pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
+    dtg = sim.dt * 0.4358665215
+    sim.update_jacobian(Y, dtg)
+    Jm = o.update_jacobian(Yc, Yf, pc, dtg)
+    Rc = (rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3).astype(FT)
+    Rf = rng.standard_normal(Yf.shape).astype(FT)
+    R = sim.to_device(Rc, Rf)
+    dY = R.zeros_like()
+    sim.ldiv(dY, R)
+    dc, df = o.ldiv(Jm, Rc, Rf)
+    gc, gf = dY.cpu()
+    t64 = FT == np.float64
+    for k in range(5):
+        assert rel(gc[:, k], dc[:, k]) <= (1e-10 if t64 else 5e-5), k
+    assert rel(gf, df) <= (1e-10 if t64 else 5e-5)
+    Yc0, Yf0 = sim.Y.cpu()
+    sim.step(fused=True)
+    torch.cuda.synchronize()
+    gc, gf = sim.Y.cpu()
+    oc, of = Oracle(sim.grid, sim.params, sim.numerics, np.float64).step(Yc0.astype(np.float64), Yf0.astype(np.float64))
+    for k in range(5):
+        assert rel(gc[:, k], oc[:, k]) <= (1e-11 if t64 else 1e-5), k
+    sim.close()

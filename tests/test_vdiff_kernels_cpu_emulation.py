@@ -33,7 +33,7 @@ def emu():
     return C.CDLL(so)
 
 
-def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12, dzb=400.0):
+def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12, dzb=400.0, ldiv_kernel=1):
     P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
     N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=iters,
@@ -68,7 +68,7 @@ def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12
     kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
     mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), mode,
-                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, tend_kernel])
+                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, tend_kernel, 0, ldiv_kernel])
     Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
     Rf = rng.standard_normal(Yf.shape)
     Ytc = np.zeros_like(Yc)
@@ -219,3 +219,19 @@ def test_emulated_vdiff_kernels_at_the_column_height_limits(emu, ze, dzb, tend_k
     for k in range(gc.shape[1]):
         assert rel(gc[:, k], oc[:, k]) < 1e-9, ("ldiv", k)
     assert rel(gf, of) < 1e-9
+
+
+@pytest.mark.parametrize("vd,deep,dm,iters,ntr,ze,dzb", [
+    ("DecayWithHeightDiffusion", True, False, 2, 1, 12, 400.0), ("VerticalDiffusion", False, True, 3, 0, 12, 400.0),
+    ("VerticalDiffusion", True, False, 1, 2, 63, 30.0), ("DecayWithHeightDiffusion", True, False, 0, 1, 2, 15000.0),
+    ("DecayWithHeightDiffusion", True, False, 2, 1, 5, 3000.0),
+])
+def test_emulated_pcr_variant_of_the_iterative_solve(emu, vd, deep, dm, iters, ntr, ze, dzb):
+    """k_ldiv_diff2: every Thomas sweep replaced by parallel cyclic reduction over all threads (pcr_slab).  Same algorithm: agrees with
+    the oracle and with k_ldiv_diff to round-off, for column heights that are and are not powers of two."""
+    (_, c1, f1), (_, oc, of) = run_case(emu, vd, deep, dm, iters, ntr, ze=ze, dzb=dzb, ldiv_kernel=1)
+    (_, c2, f2), _ = run_case(emu, vd, deep, dm, iters, ntr, ze=ze, dzb=dzb, ldiv_kernel=2)
+    for k in range(c2.shape[1]):
+        assert rel(c2[:, k], oc[:, k]) < 1e-9, ("ldiv2 vs oracle", k, rel(c2[:, k], oc[:, k]))
+        assert rel(c2[:, k], c1[:, k]) < 1e-9
+    assert rel(f2, of) < 1e-9 and rel(f2, f1) < 1e-9
