@@ -141,6 +141,8 @@ struct b200_ctx {
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
   int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
   int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
+  int hook_kernels = 1;  // B200_HOOK_KERNELS=1|2: first-generation hook kernels (element slabs; validated on B200) or k_t_imp2 / k_wfact2 / k_ldiv2 /
+                         // k_t_post_imp2 (quarter element per CTA, PCR; equal to generation 1 in the CPU CTA emulator, not yet run on a B200)
   int ldiv_diff = 1;     // B200_LDIV_DIFF=1|2: k_vdiff_jac + k_ldiv_diff (Thomas sweeps by 16 lanes; validated on B200) or k_vdiff_jac2 + k_ldiv_diff2 (no slabs / parallel cyclic reduction;
                          // matches the oracle in the CPU CTA emulator, not yet run on a B200)
   int vdiff_kernel = 2;  // B200_VDIFF_KERNEL=2|1: k_vdiff_tend2 (quarter element per CTA, no state slabs; 77 µs at he30) or k_vdiff_tend (element slabs, 267 µs)
@@ -439,6 +441,7 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k_vdiff_tend<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
+  CK(cudaFuncSetAttribute(k_ldiv2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(11 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_ldiv_diff2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((24 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_texp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(22)));
   CK(cudaFuncSetAttribute(k_texp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
@@ -474,6 +477,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
   if (const char* e = getenv("B200_VDIFF_KERNEL")) c->vdiff_kernel = atoi(e);
   if (const char* e = getenv("B200_LDIV_DIFF")) c->ldiv_diff = atoi(e);
+  if (const char* e = getenv("B200_HOOK_KERNELS")) c->hook_kernels = atoi(e);
   if (d->n_tracers > 0 && (c->legacy || (c->imp_kernel != 2 && c->imp_kernel != 5))) {
     delete c;
     return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
@@ -642,8 +646,12 @@ static int launch_vdiff_tend(b200_ctx* c, void* Ytc, const void* Yc, const void*
 
 template <class FT>
 static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
-  k_t_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                       (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  if (c->hook_kernels == 2)
+    k_t_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  else
+    k_t_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                         (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
   if (vdiff_implicit(c)) return launch_vdiff_tend<FT>(c, Ytc, Yc, Yf, s);  // implicit_tendency.jl:69-78
   return 0;
@@ -656,8 +664,12 @@ extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, con
 template <class FT>
 static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, cudaStream_t s) {
   if (!c->d_jac) CK(cudaMalloc(&c->d_jac, (size_t)c->dims.nh * JC_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
-  k_wfact<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                       (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
+  if (c->hook_kernels == 2)
+    k_wfact2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
+  else
+    k_wfact<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                         (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
   LAUNCH_CHECK(c);
   if (vdiff_implicit(c)) {  // update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261)
     if (!c->d_jacd) CK(cudaMalloc(&c->d_jacd, (size_t)c->dims.nh * JD_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
@@ -694,8 +706,12 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
     LAUNCH_CHECK(c);
     return 0;
   }
-  k_ldiv<FT><<<c->dims.nh, NT, 8 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
-                                                         (FT*)dYc, (FT*)dYf);
+  if (c->hook_kernels == 2)
+    k_ldiv2<FT><<<c->dims.nh, NT, 11 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
+                                                             (FT*)dYc, (FT*)dYf);
+  else
+    k_ldiv<FT><<<c->dims.nh, NT, 8 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
+                                                           (FT*)dYc, (FT*)dYf);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -711,8 +727,12 @@ static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const 
     CK(cudaMemsetAsync(Ytf, 0, c->nf() * sizeof(FT), s));
     return 0;
   }
-  k_t_post_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                            (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  if (c->hook_kernels == 2)
+    k_t_post_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                     (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  else
+    k_t_post_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
   return 0;
 }

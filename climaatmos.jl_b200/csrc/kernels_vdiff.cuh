@@ -704,4 +704,161 @@ __global__ void __launch_bounds__(NT) k_lim_vborrow(const VLev<FT>* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second generation of the dry hook kernels (B200_HOOK_KERNELS=2; matched against the first generation bit for bit in the CPU CTA
+// emulator, not yet run on a B200): a QUARTER element (4 columns × 64 levels) per CTA, one point per thread, and only the column
+// profiles that the vertical stencils need in shared memory (12 arrays of 4·LVP words = 12.5 KB in Float32, so 8 CTAs/SM instead of
+// the 2 that the 12 whole-element slabs of the first generation allow).  The per-point device functions of kernels_implicit.cuh
+// (timp_center, timp_face, face_coef, center_coef, upwind_minus_central) are reused unchanged: they address a profile as
+// p[n·LVP + v] with the element node n, so the ImpSlabs pointers are shifted by −4·quarter·LVP.
+template <class FT>
+__device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, const FT* hg, const FT* __restrict__ Yc,
+                                          const FT* __restrict__ Yf, int h, int quarter, FT* base, ImpSlabs<FT>& S) {
+  const int nl = threadIdx.x >> 6, n = quarter * 4 + nl, v = threadIdx.x & 63, nv = P.nv, nf = nv + 1;
+  FT** f[12] = {&S.rho, &S.u1, &S.u2, &S.re, &S.u3, &S.K, &S.h, &S.Pi, &S.thv, &S.thp, &S.phr, &S.T};
+  for (int k = 0; k < 12; ++k) *f[k] = base + k * 4 * LVP - quarter * 4 * LVP;
+  const FT* gY = Yc + (size_t)h * P.ncf * 16 * nv;
+  const int o = n * LVP + v;
+  if (v < nv) {
+    S.rho[o] = gY[(0 * 16 + n) * nv + v]; S.u1[o] = gY[(1 * 16 + n) * nv + v];
+    S.u2[o] = gY[(2 * 16 + n) * nv + v]; S.re[o] = gY[(3 * 16 + n) * nv + v];
+  }
+  if (v < nf) S.u3[o] = Yf[(size_t)h * 16 * nf + (size_t)n * nf + v];
+  __syncthreads();
+  if (v < nv) {
+    FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
+    Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
+    S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = t.phir; S.T[o] = t.T;
+  }
+  __syncthreads();
+}
+constexpr int Q_WORDS = 13 * 4 * LVP;  // 12 profiles + one scratch profile
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_t_imp2(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                               const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int h = blockIdx.x >> 2, quarter = blockIdx.x & 3, n = quarter * 4 + (threadIdx.x >> 6), v = threadIdx.x & 63;
+  const int nv = P.nv, nf = nv + 1;
+  const VLev<FT>& V = *vlev;
+  const FT* hg = hgeo + (size_t)h * HG_N * 16;
+  ImpSlabs<FT> S;
+  q_prepare(P, V, hg, Yc, Yf, h, quarter, reinterpret_cast<FT*>(smem_raw), S);
+  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
+  FT* gF = Ytf + (size_t)h * 16 * nf;
+  if (v < nv) {
+    FT rt, et; timp_center(V, S, n, v, nv, rt, et);
+    gT[(0 * 16 + n) * nv + v] = rt; gT[(1 * 16 + n) * nv + v] = FT(0);
+    gT[(2 * 16 + n) * nv + v] = FT(0); gT[(3 * 16 + n) * nv + v] = et;
+    for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
+  }
+  if (v < nf) gF[n * nf + v] = timp_face(P, V, S, n, v, nv);
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_wfact2(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                               const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT dtg, FT* jac) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int h = blockIdx.x >> 2, quarter = blockIdx.x & 3, n = quarter * 4 + (threadIdx.x >> 6), v = threadIdx.x & 63;
+  const int nv = P.nv, nf = nv + 1;
+  const VLev<FT>& V = *vlev;
+  const FT* hg = hgeo + (size_t)h * HG_N * 16;
+  ImpSlabs<FT> S;
+  q_prepare(P, V, hg, Yc, Yf, h, quarter, reinterpret_cast<FT*>(smem_raw), S);
+  if (v >= nf) return;
+  FT* gj = jac + (size_t)h * JC_N * 16 * nf;
+  FaceCoef<FT> c = face_coef(P, hg, V, S, dtg, n, v, nv);
+  const size_t o = (size_t)n * nf + v, pl = (size_t)16 * nf;
+  gj[JC_L * pl + o] = c.l; gj[JC_D * pl + o] = c.d; gj[JC_U * pl + o] = c.u;
+  gj[JC_UR_LO * pl + o] = c.ur_lo; gj[JC_UR_HI * pl + o] = c.ur_hi;
+  gj[JC_UE_LO * pl + o] = c.ue_lo; gj[JC_UE_HI * pl + o] = c.ue_hi;
+  gj[JC_U1_LO * pl + o] = c.u1_lo; gj[JC_U1_HI * pl + o] = c.u1_hi;
+  gj[JC_U2_LO * pl + o] = c.u2_lo; gj[JC_U2_HI * pl + o] = c.u2_hi;
+  FT a = FT(0), b = FT(0), cc = FT(0), dd = FT(0);
+  if (v < nv) center_coef(V, S, dtg, n, v, nv, a, b, cc, dd);
+  gj[JC_RU_LO * pl + o] = a; gj[JC_RU_HI * pl + o] = b; gj[JC_EU_LO * pl + o] = cc; gj[JC_EU_HI * pl + o] = dd;
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
+                                                    const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int h = blockIdx.x >> 2, quarter = blockIdx.x & 3, n = quarter * 4 + (threadIdx.x >> 6), v = threadIdx.x & 63;
+  const int nv = P.nv, nf = nv + 1;
+  const VLev<FT>& V = *vlev;
+  const FT* hg = hgeo + (size_t)h * HG_N * 16;
+  ImpSlabs<FT> S;
+  FT* base = reinterpret_cast<FT*>(smem_raw);
+  q_prepare(P, V, hg, Yc, Yf, h, quarter, base, S);
+  FT* flx = base + 12 * 4 * LVP - quarter * 4 * LVP;
+  const int o = n * LVP + v;
+  if (v < nf) {
+    FT r = FT(0);
+    if (v > 0 && v < nv) {
+      FT w = V.g33f[v] * S.u3[o];
+      r = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, S.h, o, v, nv, w);
+    }
+    flx[o] = r;
+  }
+  __syncthreads();
+  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
+  FT* gF = Ytf + (size_t)h * 16 * nf;
+  if (v < nv) {
+    gT[(0 * 16 + n) * nv + v] = FT(0); gT[(1 * 16 + n) * nv + v] = FT(0); gT[(2 * 16 + n) * nv + v] = FT(0);
+    gT[(3 * 16 + n) * nv + v] = -(flx[o + 1] - flx[o]) / V.mc[v];
+    for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
+  }
+  if (v < nf) gF[n * nf + v] = FT(0);
+}
+
+// k_ldiv with the 16-lane Thomas sweep replaced by parallel cyclic reduction over all threads (pcr_slab); round-off differences only.
+template <class FT>
+__global__ void __launch_bounds__(NT) k_ldiv2(Par<FT> P, const FT* __restrict__ jac, const FT* __restrict__ Rc,
+                                              const FT* __restrict__ Rf, FT* dYc, FT* dYf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<FT> sm(smem_raw);
+  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
+  FT* rr = sm.take(SLAB); FT* r1 = sm.take(SLAB); FT* r2 = sm.take(SLAB); FT* re = sm.take(SLAB);
+  FT* wa = sm.take(SLAB); FT* wb = sm.take(SLAB); FT* wc = sm.take(SLAB);
+  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
+  const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
+  const size_t pl = (size_t)16 * nf;
+  const FT* gRc = Rc + (size_t)h * P.ncf * 16 * nv;
+  load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
+  load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
+  __syncthreads();
+  const FT* gRf = Rf + (size_t)h * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, f = idx & 63;
+    if (f >= nf) continue;
+    size_t o = (size_t)n * nf + f;
+    int s = n * LVP + f;
+    FT rhs = gRf[o];
+    if (f > 0 && f < nv) {
+      rhs += gj[JC_UR_LO * pl + o] * rr[s - 1] + gj[JC_UR_HI * pl + o] * rr[s];
+      rhs += gj[JC_UE_LO * pl + o] * re[s - 1] + gj[JC_UE_HI * pl + o] * re[s];
+      rhs += gj[JC_U1_LO * pl + o] * r1[s - 1] + gj[JC_U1_HI * pl + o] * r1[s];
+      rhs += gj[JC_U2_LO * pl + o] * r2[s - 1] + gj[JC_U2_HI * pl + o] * r2[s];
+    }
+    sr[s] = rhs;
+  }
+  pcr_slab(sl, sd, su, sr, nf, wa, wb, wc);
+  FT* gdc = dYc + (size_t)h * P.ncf * 16 * nv;
+  FT* gdf = dYf + (size_t)h * 16 * nf;
+  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
+    int n = idx >> 6, v = idx & 63;
+    int s = n * LVP + v;
+    size_t o = (size_t)n * nf + v;
+    if (v < nf) gdf[o] = sr[s];
+    if (v < nv) {
+      FT x0 = sr[s], x1 = sr[s + 1];
+      gdc[(0 * 16 + n) * nv + v] = gj[JC_RU_LO * pl + o] * x0 + gj[JC_RU_HI * pl + o] * x1 - rr[s];
+      gdc[(1 * 16 + n) * nv + v] = -r1[s];
+      gdc[(2 * 16 + n) * nv + v] = -r2[s];
+      gdc[(3 * 16 + n) * nv + v] = gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1 - re[s];
+      for (int q = 4; q < P.ncf; ++q) gdc[(q * 16 + n) * nv + v] = -gRc[(q * 16 + n) * nv + v];
+    }
+  }
+}
+
 }  // namespace b200

@@ -88,7 +88,7 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
 
 // The dry hook kernels of kernels_implicit.cuh (validated on the B200; emulated here so that the CPU test tier exercises the
 // product source too): cache_imp! → T_imp! → Wfact → ldiv! → T_post_imp!, and the fused k_imp_stage on a copy of the state.
-// sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
+// sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3), sc[17] = hook kernel generation (1 | 2).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
 // Ytc/Ytf (T_imp), dYc/dYf (ldiv of Rc/Rf), Ypc (T_post_imp centres), Sc/Sf (state after the fused stage).
 extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, int ncf, const double* sc, const double* vl,
                                                                 const double* hgeo, const double* Yc, double* Yf, const double* Rc,
@@ -106,10 +106,17 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
   run_grid(nh, [&] { k_cache_imp<FT>(P, hgeo, &V, Yc, Yf, (FT*)nullptr, (FT*)nullptr, Kc, Tc, pc, hc); });
-  run_grid(nh, [&] { k_t_imp<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
-  run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
-  run_grid(nh, [&] { k_ldiv<FT>(P, jac, Rc, Rf, dYc, dYf); });
-  run_grid(nh, [&] { k_t_post_imp<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  if ((int)sc[17] == 2) {  // second generation (quarter element per CTA; PCR)
+    run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+    run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+    run_grid(nh, [&] { k_ldiv2<FT>(P, jac, Rc, Rf, dYc, dYf); });
+    run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  } else {
+    run_grid(nh, [&] { k_t_imp<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+    run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+    run_grid(nh, [&] { k_ldiv<FT>(P, jac, Rc, Rf, dYc, dYf); });
+    run_grid(nh, [&] { k_t_post_imp<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  }
   const size_t nc = (size_t)nh * ncf * 16 * nv, nf = (size_t)nh * 16 * (nv + 1);
   memcpy(Sc, Yc, nc * sizeof(FT));
   memcpy(Sf, Yf, nf * sizeof(FT));

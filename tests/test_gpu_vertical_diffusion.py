@@ -213,3 +213,56 @@ def test_pcr_variant_of_the_iterative_solve(FT, monkeypatch):
     for k in range(5):
         assert rel(gc[:, k], oc[:, k]) <= (1e-11 if t64 else 1e-5), k
     sim.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
+                    reason="second-generation hook kernels (B200_HOOK_KERNELS=2) match the oracle in the CPU CTA emulator but have not run on a "
+                           "B200 yet (set B200_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+@pytest.mark.parametrize("ze,zmax,dzb", [(10, 30000.0, 500.0), (63, 60000.0, 30.0), (2, 10000.0, 5000.0)])
+def test_second_generation_hook_kernels(FT, ze, zmax, dzb, monkeypatch):
+    """B200_HOOK_KERNELS=2: T_imp!, Wfact + ldiv!, T_post_imp! against the oracle, and the hook-by-hook step against the fused step."""
+    monkeypatch.setenv("B200_HOOK_KERNELS", "2")
+    P = prm.DycoreParams(zd_rayleigh=0.66 * zmax, zd_viscous=0.66 * zmax)
+    sim = dycore.AtmosSimulation(FT=FT, h_elem=3, z_elem=ze, z_max=zmax, dz_bottom=dzb, dt=150.0, rayleigh_sponge=True, viscous_sponge=True, params=P)
+    o = Oracle(sim.grid, P, sim.numerics, FT)
+    Yc0, Yf0 = sim.Y.cpu()
+    rng = np.random.default_rng(1234)
+    Yc = (Yc0.astype(np.float64) * (1 + 1e-3 * rng.standard_normal(Yc0.shape))).astype(FT)
+    Yf = (0.5 * sim.grid.dz_f * rng.standard_normal(Yf0.shape)).astype(FT)
+    Yf[..., 0] = 0
+    Yf[..., -1] = 0
+    Y = sim.to_device(Yc, Yf)
+    pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
+    t64 = FT == np.float64
+    Yt = Y.zeros_like()
+    sim.implicit_tendency(Yt, Y)
+    tc, tf = o.implicit_tendency(Yc, Yf, pc)
+    gc, gf = Yt.cpu()
+    assert rel(gc[:, 0], tc[:, 0]) <= (1e-11 if t64 else 1e-5) and rel(gc[:, 3], tc[:, 3]) <= (1e-11 if t64 else 1e-4)
+    assert rel(gf, tf) <= (1e-11 if t64 else 5e-4)
+    dtg = sim.dt * 0.4358665215
+    sim.update_jacobian(Y, dtg)
+    Jm = o.update_jacobian(Yc, Yf, pc, dtg)
+    Rc = (rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3).astype(FT)
+    Rf = rng.standard_normal(Yf.shape).astype(FT)
+    R = sim.to_device(Rc, Rf)
+    dY = R.zeros_like()
+    sim.ldiv(dY, R)
+    dc, df = o.ldiv(Jm, Rc, Rf)
+    gc, gf = dY.cpu()
+    for k in range(4):
+        assert rel(gc[:, k], dc[:, k]) <= (1e-10 if t64 else 5e-5), k
+    assert rel(gf, df) <= (1e-10 if t64 else 5e-5)
+    sim.correct_implicit_advection_tendency(Yt, Y)
+    pcc, _ = o.correct_implicit_advection_tendency(Yc, Yf, pc)
+    gc, gf = Yt.cpu()
+    assert rel(gc[:, 3], pcc[:, 3]) <= (1e-10 if t64 else 5e-4)
+    sim.Y = sim.to_device(Yc0, Yf0)
+    sim.step(fused=False)
+    hc, hf = sim.Y.cpu()
+    sim.Y = sim.to_device(Yc0, Yf0)
+    sim.step(fused=True)
+    fc, ff = sim.Y.cpu()
+    assert rel(hc, fc) <= (1e-12 if t64 else 1e-5)
+    sim.close()

@@ -145,9 +145,11 @@ def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("gen", [1, 2])
 @pytest.mark.parametrize("upw,rayleigh,deep", [("vanleer_limiter", True, True), ("first_order", False, False), ("none", False, True)])
-def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
-    """k_cache_imp, k_t_imp, k_wfact → k_ldiv, k_t_post_imp and the fused k_imp_stage (kernels_implicit.cuh) on the CPU emulator against
+def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep, gen):
+    """gen 1: k_cache_imp, k_t_imp, k_wfact → k_ldiv, k_t_post_imp and the fused k_imp_stage (kernels_implicit.cuh); gen 2: k_t_imp2,
+    k_wfact2 → k_ldiv2, k_t_post_imp2 (quarter element per CTA, parallel cyclic reduction; B200_HOOK_KERNELS=2) — on the CPU emulator against
     the oracle's cache_imp! / T_imp! / Wfact + ldiv! / T_post_imp! / one Newton iteration of the implicit stage (Float64)."""
     P = prm.DycoreParams(zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
@@ -173,7 +175,7 @@ def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
     hgeo = np.zeros((nh, HG_N, 16))
     hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), 0, 0, 0, 0, dtg,
-                   0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw]])
+                   0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw], gen])
     Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
     Rf = rng.standard_normal(Yf.shape)
     z4 = lambda: np.zeros((nh, 16, nv))
