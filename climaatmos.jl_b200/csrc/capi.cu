@@ -141,6 +141,8 @@ struct b200_ctx {
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
   int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
   int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
+  int vdiff_fused = 0;   // B200_VDIFF_FUSED=1: fused implicit stage with implicit vertical diffusion (k_imp_stage_diff; matches the oracle in the CPU CTA
+                         // emulator, not yet run on a B200) in b200_implicit_stage and the fused stepper instead of the hook sequence
   int hook_kernels = 1;  // B200_HOOK_KERNELS=1|2: first-generation hook kernels (element slabs; validated on B200) or k_t_imp2 / k_wfact2 / k_ldiv2 /
                          // k_t_post_imp2 (quarter element per CTA, PCR; equal to generation 1 in the CPU CTA emulator, not yet run on a B200)
   int ldiv_diff = 1;     // B200_LDIV_DIFF=1|2: k_vdiff_jac + k_ldiv_diff (Thomas sweeps by 16 lanes; validated on B200) or k_vdiff_jac2 + k_ldiv_diff2 (no slabs / parallel cyclic reduction;
@@ -441,6 +443,7 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k_vdiff_tend<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
+  CK(cudaFuncSetAttribute(k_imp_stage_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_PROFILES * 4 * LVP * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_ldiv2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(11 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_ldiv_diff2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((24 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_texp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(22)));
@@ -478,6 +481,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (const char* e = getenv("B200_VDIFF_KERNEL")) c->vdiff_kernel = atoi(e);
   if (const char* e = getenv("B200_LDIV_DIFF")) c->ldiv_diff = atoi(e);
   if (const char* e = getenv("B200_HOOK_KERNELS")) c->hook_kernels = atoi(e);
+  if (const char* e = getenv("B200_VDIFF_FUSED")) c->vdiff_fused = atoi(e);
   if (d->n_tracers > 0 && (c->legacy || (c->imp_kernel != 2 && c->imp_kernel != 5))) {
     delete c;
     return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
@@ -1239,6 +1243,13 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
 template <class FT>
 static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtg, cudaStream_t s) {
   const size_t bc = c->nc() * sizeof(FT), bf = c->nf() * sizeof(FT);
+  if (vdiff_implicit(c)) {  // implicit vertical diffusion: the fused stage with the diffusion blocks and the approximate arrowhead iteration
+    if (!c->vdiff_fused) return fail("implicit vertical diffusion: the fused stage kernel is opt-in (B200_VDIFF_FUSED=1); use the hook entry points");
+    k_imp_stage_diff<FT><<<c->dims.nh * 4, NT, (size_t)QD_PROFILES * 4 * LVP * sizeof(FT), s>>>(
+        make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+    LAUNCH_CHECK(c);
+    return 0;
+  }
   if (c->legacy == 1 || c->legacy == 2) {
     CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
@@ -1277,7 +1288,8 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
 }
 extern "C" int b200_implicit_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtgamma, void* stream) {
   if (!c) return fail("b200_implicit_stage: null context");
-  if (vdiff_implicit(c)) return fail("b200_implicit_stage: implicit vertical diffusion is served by the hook entry points (b200_wfact, b200_t_imp, b200_ldiv)");
+  if (vdiff_implicit(c) && !c->vdiff_fused)
+    return fail("b200_implicit_stage: implicit vertical diffusion is served by the hook entry points (b200_wfact, b200_t_imp, b200_ldiv) unless B200_VDIFF_FUSED=1");
   return c->ft == 4 ? impl_imp_stage<float>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream)
                     : impl_imp_stage<double>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream);
 }
@@ -1456,7 +1468,7 @@ extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t
   cudaStream_t s = (cudaStream_t)stream;
   // implicit vertical diffusion: the fused implicit-stage kernel does not carry the diffusion blocks yet — the stage runs through
   // the hook sequence (cache_imp!, Wfact, T_imp!, ldiv!, T_post_imp!) of the literal path
-  if (vdiff_implicit(c)) fused = 0;
+  if (vdiff_implicit(c) && !c->vdiff_fused) fused = 0;  // B200_VDIFF_FUSED=1: k_imp_stage_diff serves the fused path
   auto run = [&](cudaStream_t q) { return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, q) : impl_step<double>(c, Yc, Yf, fused, q); };
   // One CUDA graph per state buffer: ≈35 kernel launches, the side-stream fork/join and the memsets replay as one launch.
   // Multi-rank contexts replay too when the halo runs over peer memory (its exchange number lives in device memory); the NCCL

@@ -861,4 +861,242 @@ __global__ void __launch_bounds__(NT) k_ldiv2(Par<FT> P, const FT* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused implicit stage WITH implicit vertical diffusion (B200_VDIFF_FUSED=1; matches the oracle's stage in the CPU CTA emulator, not
+// yet run on a B200): what b200_implicit_stage / k5_imp_stage do for the dry Jacobian, extended by the diffusion tendency, the
+// diffusion blocks and the approximate arrowhead iteration — cache_imp! (u₃ filter) → Wfact → R = dtγ·T_imp(U) → ldiv! → N = U − ΔU →
+// cache_imp! → T_post_imp! — in ONE kernel, out of place.  Quarter element per CTA, one point per thread; every coefficient profile
+// lives in shared memory (48 profiles of 4·LVP words: 50 KB in Float32), tridiagonal solves by parallel cyclic reduction with one row
+// per thread.  Algebra as in k_ldiv_diff (T-based Schur operator and preconditioner).
+constexpr int QD_PROFILES = 48;
+
+// PCR over the 4 columns of the CTA, one row per thread: thread (column, v) owns row v at index o; see pcr_slab.
+template <class FT>
+__device__ __forceinline__ void pcr_q(const FT* l, const FT* d, const FT* u, FT* x, int n, int o, int v, FT* wa, FT* wb, FT* wc) {
+  __syncthreads();
+  const bool act = v < n;
+  if (act) { wa[o] = l[o]; wb[o] = d[o]; wc[o] = u[o]; }
+  __syncthreads();
+  for (int s = 1; s < n; s <<= 1) {
+    FT A = FT(0), B = FT(1), C = FT(0), Dd = FT(0);
+    if (act) {
+      B = wb[o]; Dd = x[o];
+      if (v - s >= 0) { const FT r = wa[o] / wb[o - s]; A = -r * wa[o - s]; B -= r * wc[o - s]; Dd -= r * x[o - s]; }
+      if (v + s < n) { const FT r = wc[o] / wb[o + s]; C = -r * wc[o + s]; B -= r * wa[o + s]; Dd -= r * x[o + s]; }
+    }
+    __syncthreads();
+    if (act) { wa[o] = A; wb[o] = B; wc[o] = C; x[o] = Dd; }
+    __syncthreads();
+  }
+  if (act) x[o] = x[o] / wb[o];
+  __syncthreads();
+}
+
+template <class FT>
+__global__ void __launch_bounds__(NT) k_imp_stage_diff(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
+                                                       const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Uc,
+                                                       const FT* __restrict__ Uf, FT* Nc, FT* Nf, FT dtg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int h = blockIdx.x >> 2, quarter = blockIdx.x & 3, n = quarter * 4 + (threadIdx.x >> 6), v = threadIdx.x & 63;
+  const int nv = P.nv, nf = nv + 1, o = n * LVP + v;
+  const bool cen = v < nv, fac_ = v < nf, inner = v > 0 && v < nv;
+  const VLev<FT>& V = *vlev;
+  const FT* hg = hgeo + (size_t)h * HG_N * 16;
+  FT* base = reinterpret_cast<FT*>(smem_raw);
+  int np = 0;
+  auto take = [&]() { FT* p = base + (np++) * 4 * LVP - quarter * 4 * LVP; return p; };
+  ImpSlabs<FT> S;
+  S.rho = take(); S.u1 = take(); S.u2 = take(); S.re = take(); S.u3 = take(); S.K = take(); S.h = take(); S.Pi = take();
+  S.thv = take(); S.thp = take(); S.phr = take(); S.T = take();
+  FT *pw = take(), *ir = take(), *rr = take(), *rre = take(), *r1 = take(), *r2 = take();
+  FT *sl = take(), *sd = take(), *su = take();
+  FT *url = take(), *urh = take(), *uel = take(), *ueh = take(), *u1l = take(), *u1h = take(), *u2l = take(), *u2h = take();
+  FT *rul = take(), *ruh = take(), *eul = take(), *euh = take();
+  FT *pl_ = take(), *pd = take(), *pu = take(), *el = take(), *ed = take(), *eu = take(), *fc = take();
+  FT *wa = take(), *wb = take(), *wc = take(), *ye = take(), *zz = take(), *b3 = take(), *x3 = take(), *r3 = take();
+  // ---- cache_imp!(U): stage the columns, u₃ boundary filter on load, thermodynamics
+  const FT* gU = Uc + (size_t)h * P.ncf * 16 * nv;
+  FT* gN = Nc + (size_t)h * P.ncf * 16 * nv;
+  if (cen) {
+    S.rho[o] = gU[(0 * 16 + n) * nv + v]; S.u1[o] = gU[(1 * 16 + n) * nv + v];
+    S.u2[o] = gU[(2 * 16 + n) * nv + v]; S.re[o] = gU[(3 * 16 + n) * nv + v];
+  }
+  if (fac_) S.u3[o] = inner ? Uf[(size_t)h * 16 * nf + (size_t)n * nf + v] : FT(0);
+  __syncthreads();
+  if (cen) {
+    FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
+    Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
+    S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = t.phir; S.T[o] = t.T;
+  }
+  __syncthreads();
+  // ---- eddy diffusivity → zz
+  if (cen) {
+    FT kh;
+    if (D.mode == 2) {
+      kh = D.kdec[v];
+    } else {
+      const FT a = S.u1[n * LVP], b = S.u2[n * LVP];
+      const FT g11 = hg[HG_GI11 * 16 + n], g12 = hg[HG_GI12 * 16 + n], g22 = hg[HG_GI22 * 16 + n];
+      const FT nrm = sqrt((a * (g11 * a + g12 * b) + b * (g12 * a + g22 * b)) * V.sc2i[0]);
+      const FT KE = D.ce_za * nrm;
+      const FT p = S.rho[o] * P.R_d * S.T[o];
+      const FT x = (FT(85000) - p) / FT(10000);
+      kh = p > FT(85000) ? KE : KE * exp_(-(x * x));
+    }
+    zz[o] = kh;
+  }
+  __syncthreads();
+  // ---- dtγ·(J g³³ ᶠρK)/J2, 1/ρ; advective residuals and centre-row coefficients
+  FT rre0 = FT(0);
+  if (fac_) {
+    FT w = FT(0);
+    if (inner) {
+      const FT rf = FT(0.5) * (S.rho[o - 1] + S.rho[o]);
+      const FT ik = FT(0.5) * (FT(1) / fmax_(zz[o - 1], D.eps) + FT(1) / fmax_(zz[o], D.eps));
+      w = dtg * (V.dzf[v] * V.g33f[v] / V.sf2i[v]) * (rf / ik);
+    }
+    pw[o] = w;
+  }
+  if (cen) {
+    ir[o] = FT(1) / S.rho[o];
+    FT rt, et; timp_center(V, S, n, v, nv, rt, et);
+    rr[o] = dtg * rt; rre0 = dtg * et;
+    FT a, b, c, d; center_coef(V, S, dtg, n, v, nv, a, b, c, d);
+    rul[o] = a; ruh[o] = b; eul[o] = c; euh[o] = d;
+  }
+  __syncthreads();
+  // ---- diffusive residuals (pw carries dtγ), face-row coefficients, A_ee, (uₕ,uₕ)
+  const bool lo = v > 0, hi = v < nv - 1;
+  const FT wl = (cen && lo) ? pw[o] : FT(0), wh = (cen && hi) ? pw[o + 1] : FT(0);
+  const FT rm = cen ? V.rmc[v] : FT(0);
+  if (cen) {
+    {
+      const FT s0 = P.cp_d * (S.T[o] - P.T_0) + V.phic[v];
+      const FT fl = lo ? wl * (s0 - (P.cp_d * (S.T[o - 1] - P.T_0) + V.phic[v - 1])) : FT(0);
+      const FT fh = hi ? wh * ((P.cp_d * (S.T[o + 1] - P.T_0) + V.phic[v + 1]) - s0) : FT(0);
+      rre[o] = rre0 + (fh - fl) * rm;
+    }
+    FT q1 = FT(0), q2 = FT(0);
+    if (D.momentum) {
+      const FT is0 = sqrt(V.sc2i[v]);
+      const FT isl = lo ? sqrt(V.sc2i[v - 1]) : FT(0), ish = hi ? sqrt(V.sc2i[v + 1]) : FT(0);
+      const FT sir = rm / (is0 * S.rho[o]);
+      { const FT c0 = S.u1[o] * is0; const FT fl = lo ? wl * (c0 - S.u1[o - 1] * isl) : FT(0), fh = hi ? wh * (S.u1[o + 1] * ish - c0) : FT(0); q1 = (fh - fl) * sir; }
+      { const FT c0 = S.u2[o] * is0; const FT fl = lo ? wl * (c0 - S.u2[o - 1] * isl) : FT(0), fh = hi ? wh * (S.u2[o + 1] * ish - c0) : FT(0); q2 = (fh - fl) * sir; }
+    }
+    r1[o] = q1; r2[o] = q2;
+    const FT l_ = lo ? pw[o] * rm : FT(0), h_ = hi ? pw[o + 1] * rm : FT(0);
+    const FT dg = -(l_ + h_);
+    const FT m = dg * (D.cpcv * ir[o]);
+    el[o] = lo ? l_ * (D.cpcv * ir[o - 1]) : FT(0);
+    ed[o] = m - FT(1);
+    eu[o] = hi ? h_ * (D.cpcv * ir[o + 1]) : FT(0);
+    fc[o] = m / (m - FT(1));
+    pl_[o] = l_ * ir[o]; pd[o] = dg * ir[o] - FT(1); pu[o] = h_ * ir[o];
+    ye[o] = rre[o];
+  }
+  if (fac_) {
+    FaceCoef<FT> c = face_coef(P, hg, V, S, dtg, n, v, nv);
+    sl[o] = c.l; sd[o] = c.d; su[o] = c.u;
+    url[o] = c.ur_lo; urh[o] = c.ur_hi; uel[o] = c.ue_lo; ueh[o] = c.ue_hi;
+    u1l[o] = c.u1_lo; u1h[o] = c.u1_hi; u2l[o] = c.u2_lo; u2h[o] = c.u2_hi;
+    b3[o] = dtg * timp_face(P, V, S, n, v, nv);
+  }
+  // ---- Δuₕ (exact tridiagonal solves, or −R = 0 without momentum diffusion) and y_e = A_ee⁻¹ R_ρe
+  if (D.momentum) {
+    pcr_q(pl_, pd, pu, r1, nv, o, v, wa, wb, wc);
+    pcr_q(pl_, pd, pu, r2, nv, o, v, wa, wb, wc);
+  }
+  pcr_q(el, ed, eu, ye, nv, o, v, wa, wb, wc);
+  // ---- Schur right-hand side and preconditioner
+  if (fac_) {
+    FT rhs = b3[o], l = sl[o], d = sd[o], u = su[o];
+    if (inner) {
+      rhs += url[o] * rr[o - 1] + urh[o] * rr[o];
+      rhs -= uel[o] * ye[o - 1] + ueh[o] * ye[o];
+      rhs -= u1l[o] * r1[o - 1] + u1h[o] * r1[o];
+      rhs -= u2l[o] * r2[o - 1] + u2h[o] * r2[o];
+      const FT a = uel[o] * fc[o - 1], b = ueh[o] * fc[o];
+      l -= a * eul[o - 1];
+      d -= a * euh[o - 1] + b * eul[o];
+      u -= b * euh[o];
+    }
+    b3[o] = rhs; x3[o] = rhs;
+    pl_[o] = l; pd[o] = d; pu[o] = u;
+  }
+  pcr_q(pl_, pd, pu, x3, nf, o, v, wa, wb, wc);
+  for (int it = 0; it < D.n_iters; ++it) {
+    if (cen) { const FT y = eul[o] * x3[o] + euh[o] * x3[o + 1]; ye[o] = y; zz[o] = y; }
+    pcr_q(el, ed, eu, zz, nv, o, v, wa, wb, wc);
+    if (fac_) {
+      FT tx = sd[o] * x3[o];
+      if (v > 0) tx += sl[o] * x3[o - 1];
+      if (v < nv) tx += su[o] * x3[o + 1];
+      FT r = b3[o] - tx;
+      if (inner) r += uel[o] * (zz[o - 1] + ye[o - 1]) + ueh[o] * (zz[o] + ye[o]);
+      r3[o] = r;
+    }
+    pcr_q(pl_, pd, pu, r3, nf, o, v, wa, wb, wc);
+    if (fac_) x3[o] += r3[o];
+    __syncthreads();
+  }
+  // ---- Δρ, Δρe_tot and the Newton update N = U − ΔU (profiles of S become N)
+  FT drho = FT(0);
+  if (cen) {
+    const FT x0 = x3[o], x1 = x3[o + 1];
+    drho = rul[o] * x0 + ruh[o] * x1 - rr[o];
+    ye[o] = rre[o] - (eul[o] * x0 + euh[o] * x1);
+  }
+  pcr_q(el, ed, eu, ye, nv, o, v, wa, wb, wc);
+  // passive tracers: Δ(ρχ) = (dtγ D⋅Diag(1/ρ) − I)⁻¹ dtγ D χ with the OLD 1/ρ (ir) — before S.rho is overwritten nothing else needs it
+  for (int q = 4; q < P.ncf; ++q) {
+    __syncthreads();
+    if (cen) {
+      const FT l_ = lo ? pw[o] * rm : FT(0), h_ = hi ? pw[o + 1] * rm : FT(0);
+      pl_[o] = lo ? l_ * ir[o - 1] : FT(0); pd[o] = -(l_ + h_) * ir[o] - FT(1); pu[o] = hi ? h_ * ir[o + 1] : FT(0);
+      r3[o] = gU[(size_t)(q * 16 + n) * nv + v] * ir[o];  // χ
+    }
+    __syncthreads();
+    if (cen) {
+      const FT c0 = r3[o];
+      const FT fl = lo ? wl * (c0 - r3[o - 1]) : FT(0), fh = hi ? wh * (r3[o + 1] - c0) : FT(0);
+      zz[o] = (fh - fl) * rm;
+    }
+    pcr_q(pl_, pd, pu, zz, nv, o, v, wa, wb, wc);
+    if (cen) gN[(size_t)(q * 16 + n) * nv + v] = gU[(size_t)(q * 16 + n) * nv + v] - zz[o];
+  }
+  __syncthreads();
+  if (cen) {
+    S.rho[o] = S.rho[o] - drho; S.re[o] = S.re[o] - ye[o];
+    S.u1[o] = S.u1[o] - r1[o]; S.u2[o] = S.u2[o] - r2[o];
+  }
+  if (fac_) S.u3[o] = inner ? S.u3[o] - x3[o] : FT(0);
+  __syncthreads();
+  // ---- cache_imp!(N), T_post_imp!
+  FT e_new = cen ? S.re[o] : FT(0);
+  if (P.upwinding != 0) {
+    if (cen) {
+      FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
+      Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
+      S.h[o] = t.h;
+    }
+    __syncthreads();
+    if (fac_) {
+      FT r = FT(0);
+      if (inner) {
+        const FT w = V.g33f[v] * S.u3[o];
+        r = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, S.h, o, v, nv, w);
+      }
+      b3[o] = r;
+    }
+    __syncthreads();
+    if (cen) e_new += dtg * (-(b3[o + 1] - b3[o]) / V.mc[v]);
+  }
+  if (cen) {
+    gN[(0 * 16 + n) * nv + v] = S.rho[o]; gN[(1 * 16 + n) * nv + v] = S.u1[o];
+    gN[(2 * 16 + n) * nv + v] = S.u2[o]; gN[(3 * 16 + n) * nv + v] = e_new;
+  }
+  if (fac_) Nf[(size_t)h * 16 * nf + (size_t)n * nf + v] = S.u3[o];
+}
+
 }  // namespace b200

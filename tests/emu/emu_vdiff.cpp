@@ -123,3 +123,23 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
   run_grid(nh, [&] { k_imp_stage<FT>(P, hgeo, &V, Sc, Sf, dtg); });
   return 0;
 }
+
+// k_imp_stage_diff: N ← fused implicit stage with implicit vertical diffusion of U (sc as in emu_vdiff, sc[16] = energy upwinding)
+extern "C" __attribute__((visibility("default"))) int emu_stage_diff(int nh, int nv, int ncf, const double* sc, const double* vl,
+                                                                     const double* hgeo, const double* kdec, const double* Uc,
+                                                                     const double* Uf, double* Nc, double* Nf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = ncf; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[16];
+  VDiff<FT> D;
+  D.mode = (int)sc[10]; D.momentum = (int)sc[11]; D.n_iters = (int)sc[12]; D.ce_za = sc[13]; D.eps = 2.220446049250313e-16;
+  D.cpcv = sc[1] / sc[2]; D.kdec = kdec;
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  run_grid(nh * 4, [&] { k_imp_stage_diff<FT>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[14]); });
+  return 0;
+}

@@ -266,3 +266,40 @@ def test_second_generation_hook_kernels(FT, ze, zmax, dzb, monkeypatch):
     fc, ff = sim.Y.cpu()
     assert rel(hc, fc) <= (1e-12 if t64 else 1e-5)
     sim.close()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
+                    reason="k_imp_stage_diff (B200_VDIFF_FUSED=1) matches the oracle's stage in the CPU CTA emulator but has not run on a B200 yet "
+                           "(set B200_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+@pytest.mark.parametrize("vd", ["DecayWithHeightDiffusion", "VerticalDiffusion"])
+def test_fused_implicit_diffusion_stage(FT, vd, monkeypatch):
+    """B200_VDIFF_FUSED=1: b200_implicit_stage with implicit diffusion as one kernel against the oracle's hook sequence, and the fused,
+    graph-replayed step against the oracle and against the hook-by-hook step."""
+    monkeypatch.setenv("B200_VDIFF_FUSED", "1")
+    sim, o, Yc, Yf, rng = make(FT, vd, True)
+    U = sim.to_device(Yc, Yf)
+    N = U.zeros_like()
+    dtg = sim.dt * 0.4358665215
+    sim.implicit_stage(N, U, dtg)
+    torch.cuda.synchronize()
+    oc, of = Yc.astype(np.float64), Yf.astype(np.float64)
+    o64 = Oracle(sim.grid, sim.params, sim.numerics, np.float64)
+    o64._implicit_stage_local(oc, of, dtg, lambda s: None)
+    gc, gf = N.cpu()
+    t64 = FT == np.float64
+    for k in range(5):
+        assert rel(gc[:, k], oc[:, k]) <= (1e-12 if t64 else 2e-6), k
+    assert rel(gf, of) <= (1e-10 if t64 else 2e-4)
+    Yc0, Yf0 = sim.Y.cpu()
+    for _ in range(3):  # eager step, graph capture, graph replay
+        sim.Y = sim.to_device(Yc0, Yf0)
+        sim.step(fused=True)
+        torch.cuda.synchronize()
+        gc, gf = sim.Y.cpu()
+        if _ == 0:
+            oc, of = o64.step(Yc0.astype(np.float64), Yf0.astype(np.float64))
+        for k in range(5):
+            assert rel(gc[:, k], oc[:, k]) <= (1e-11 if t64 else 1e-5), (_, k)
+        assert rel(gf, of) <= (1e-11 if t64 else 2e-4)
+    sim.close()

@@ -237,3 +237,56 @@ def test_emulated_pcr_variant_of_the_iterative_solve(emu, vd, deep, dm, iters, n
         assert rel(c2[:, k], oc[:, k]) < 1e-9, ("ldiv2 vs oracle", k, rel(c2[:, k], oc[:, k]))
         assert rel(c2[:, k], c1[:, k]) < 1e-9
     assert rel(f2, of) < 1e-9 and rel(f2, f1) < 1e-9
+
+
+@pytest.mark.parametrize("vd,deep,dm,iters,ntr,upw,rayleigh,ze,dzb", [
+    ("DecayWithHeightDiffusion", True, False, 2, 1, "vanleer_limiter", True, 12, 400.0),
+    ("VerticalDiffusion", False, False, 1, 2, "first_order", False, 12, 400.0),
+    ("VerticalDiffusion", True, True, 3, 0, "none", False, 12, 400.0),
+    ("DecayWithHeightDiffusion", True, False, 2, 1, "vanleer_limiter", True, 63, 30.0),
+    ("DecayWithHeightDiffusion", True, False, 0, 1, "vanleer_limiter", False, 2, 15000.0),
+])
+def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, dm, iters, ntr, upw, rayleigh, ze, dzb):
+    """k_imp_stage_diff (B200_VDIFF_FUSED=1): cache_imp! → Wfact → T_imp! → ldiv! (approximate arrowhead iteration) → U −= ΔU → cache_imp! →
+    T_post_imp! with implicit vertical diffusion in ONE kernel, against the oracle's hook sequence (Float64).  The input state has
+    non-zero u₃ on the boundary faces: the kernel must treat them as zero like cache_imp!."""
+    P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
+    N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=iters,
+                           disable_momentum_vertical_diffusion=dm, rayleigh_sponge=rayleigh, energy_upwinding=upw)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(4321)
+    Yc = Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    Yc = np.ascontiguousarray(np.concatenate([Yc] + [Yc[:, :1] * 1e-2 * (1 + 0.5 * rng.random(Yc[:, :1].shape)) for _ in range(ntr)], axis=1))
+    Yf = np.ascontiguousarray(Yf)
+    nh, ncf, nv = Yc.shape[0], Yc.shape[1], g.nv
+    dtg = 0.4358665215084590 * N.dt
+    s_c = (g.radius + g.z_c) / g.radius if deep else np.ones(nv)
+    s_f = (g.radius + g.z_f) / g.radius if deep else np.ones(nv + 1)
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    brw = o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if rayleigh else np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif), pad(brw)])
+    A = g.dxdxi
+    Ginv = np.linalg.inv(np.einsum("...ab,...ac->...bc", A, A))
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
+    kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
+    mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), mode,
+                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, 0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw]])
+    Nc, Nf = np.zeros_like(Yc), np.zeros_like(Yf)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emu.emu_stage_diff(nh, nv, ncf, p(sc), p(vl), p(hgeo), p(kdec), p(Yc), p(Yf), p(Nc), p(Nf)) == 0
+    Uc, Uf = Yc.copy(), Yf.copy()
+    o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
+    assert np.abs(Uc - Yc).max() > 0
+    for k in range(ncf):
+        assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
+        assert rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8 or np.abs(Uc[:, k] - Yc[:, k]).max() == 0, ("increment", k)
+    assert rel(Nf, Uf) < 1e-10
