@@ -16,7 +16,10 @@ namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
 #include "kernels_vdiff.cuh"
 
 using namespace b200;
-typedef double FT;
+#ifndef EMU_FT
+#define EMU_FT double
+#endif
+typedef EMU_FT FT;  // -DEMU_FT=float builds the Float32 instantiations (arrays are FT, the scalar block sc stays double)
 
 template <class F>
 static void run_grid(int nblocks, F&& body) {
@@ -37,16 +40,16 @@ static void run_grid(int nblocks, F&& body) {
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ, tendency kernel (1|2), [16] unused here, [17] ldiv kernel (1 Thomas | 2 PCR)
 // vl: [11][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw ; hgeo: [nh][HG_N][16] ; kdec [64]
-extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, int ncf, const double* sc, const double* vl, const double* hgeo, const double* kdec,
-                         const double* Yc, const double* Yf, const double* Rc, const double* Rf, double* Ytc, double* jac,
-                         double* jacd, double* dYc, double* dYf) {
+extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, int ncf, const double* sc, const FT* vl, const FT* hgeo, const FT* kdec,
+                         const FT* Yc, const FT* Yf, const FT* Rc, const FT* Rf, FT* Ytc, FT* jac,
+                         FT* jacd, FT* dYc, FT* dYf) {
   Par<FT> P;
   memset(&P, 0, sizeof(P));
   P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
   P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
   P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = ncf; P.rayleigh = (int)sc[9];
   VDiff<FT> D;
-  D.mode = (int)sc[10]; D.momentum = (int)sc[11]; D.n_iters = (int)sc[12]; D.ce_za = sc[13]; D.eps = 2.220446049250313e-16;
+  D.mode = (int)sc[10]; D.momentum = (int)sc[11]; D.n_iters = (int)sc[12]; D.ce_za = sc[13]; D.eps = sizeof(FT) == 4 ? (FT)1.1920928955078125e-7 : (FT)2.220446049250313e-16;
   D.cpcv = sc[1] / sc[2]; D.kdec = kdec;
   const FT dtg = sc[14];
   static VLev<FT> V;
@@ -64,7 +67,7 @@ extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, 
 }
 
 // k_lim_vborrow on every (element, tracer): Yc in place; dzc [64]
-extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv, int ncf, const double* dzc, double* Yc) {
+extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv, int ncf, const FT* dzc, FT* Yc) {
   static VLev<FT> V;
   memset(&V, 0, sizeof(V));
   memcpy(V.dzc, dzc, 64 * sizeof(FT));
@@ -77,7 +80,7 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
         for (int b = 0; b < nh; ++b) {
           threadIdx = {(unsigned)k, 0, 0};
           blockIdx = {(unsigned)b, (unsigned)t, 0};
-          k_lim_vborrow<FT>(&V, Yc, ncf, nv, 0.0);
+          k_lim_vborrow<FT>(&V, Yc, ncf, nv, (FT)0);
           bar.arrive_and_wait();
         }
       });
@@ -90,11 +93,11 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
 // product source too): cache_imp! → T_imp! → Wfact → ldiv! → T_post_imp!, and the fused k_imp_stage on a copy of the state.
 // sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3), sc[17] = hook kernel generation (1 | 2).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
 // Ytc/Ytf (T_imp), dYc/dYf (ldiv of Rc/Rf), Ypc (T_post_imp centres), Sc/Sf (state after the fused stage).
-extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, int ncf, const double* sc, const double* vl,
-                                                                const double* hgeo, const double* Yc, double* Yf, const double* Rc,
-                                                                const double* Rf, double* Kc, double* Tc, double* pc, double* hc,
-                                                                double* Ytc, double* Ytf, double* jac, double* dYc, double* dYf,
-                                                                double* Ypc, double* Ypf, double* Sc, double* Sf) {
+extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, int ncf, const double* sc, const FT* vl,
+                                                                const FT* hgeo, const FT* Yc, FT* Yf, const FT* Rc,
+                                                                const FT* Rf, FT* Kc, FT* Tc, FT* pc, FT* hc,
+                                                                FT* Ytc, FT* Ytf, FT* jac, FT* dYc, FT* dYf,
+                                                                FT* Ypc, FT* Ypf, FT* Sc, FT* Sf) {
   Par<FT> P;
   memset(&P, 0, sizeof(P));
   P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
@@ -125,16 +128,16 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
 }
 
 // k_imp_stage_diff: N ← fused implicit stage with implicit vertical diffusion of U (sc as in emu_vdiff, sc[16] = energy upwinding)
-extern "C" __attribute__((visibility("default"))) int emu_stage_diff(int nh, int nv, int ncf, const double* sc, const double* vl,
-                                                                     const double* hgeo, const double* kdec, const double* Uc,
-                                                                     const double* Uf, double* Nc, double* Nf) {
+extern "C" __attribute__((visibility("default"))) int emu_stage_diff(int nh, int nv, int ncf, const double* sc, const FT* vl,
+                                                                     const FT* hgeo, const FT* kdec, const FT* Uc,
+                                                                     const FT* Uf, FT* Nc, FT* Nf) {
   Par<FT> P;
   memset(&P, 0, sizeof(P));
   P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
   P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
   P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = ncf; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[16];
   VDiff<FT> D;
-  D.mode = (int)sc[10]; D.momentum = (int)sc[11]; D.n_iters = (int)sc[12]; D.ce_za = sc[13]; D.eps = 2.220446049250313e-16;
+  D.mode = (int)sc[10]; D.momentum = (int)sc[11]; D.n_iters = (int)sc[12]; D.ce_za = sc[13]; D.eps = sizeof(FT) == 4 ? (FT)1.1920928955078125e-7 : (FT)2.220446049250313e-16;
   D.cpcv = sc[1] / sc[2]; D.kdec = kdec;
   static VLev<FT> V;
   memset(&V, 0, sizeof(V));

@@ -33,6 +33,20 @@ def emu():
     return C.CDLL(so)
 
 
+@pytest.fixture(scope="module")
+def emu32():
+    """The same harness compiled with -DEMU_FT=float: the Float32 instantiations of the kernels."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(HERE, "emu", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_vdiff_f32.so")
+    csrc = os.path.join(os.path.dirname(HERE), "climaatmos.jl_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden", "-DEMU_FT=float", "-I", os.path.join(HERE, "emu"),
+                    "-I", csrc, os.path.join(HERE, "emu", "emu_vdiff.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
 def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12, dzb=400.0, ldiv_kernel=1):
     P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
@@ -290,3 +304,66 @@ def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, d
         assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
         assert rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8 or np.abs(Uc[:, k] - Yc[:, k]).max() == 0, ("increment", k)
     assert rel(Nf, Uf) < 1e-10
+
+
+@pytest.mark.parametrize("vd,upw", [("DecayWithHeightDiffusion", "vanleer_limiter"), ("VerticalDiffusion", "first_order")])
+def test_float32_instantiations_of_the_opt_in_kernels(emu32, vd, upw):
+    """Float32 builds of the kernels whose GPU tests are still opt-in (k_vdiff_jac2 → k_ldiv_diff2, k_imp_stage_diff), on the CPU emulator
+    against the Float64 oracle evaluated on the same Float32-rounded inputs: the errors must sit inside the tolerances those GPU tests use
+    (ldiv! 5e-5; fused stage 2e-6 on the centre fields, 2e-4 on u₃)."""
+    F = np.float32
+    P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius)
+    N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=2, energy_upwinding=upw)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(11)
+    Yc = Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    Yf[..., 0] = 0
+    Yf[..., -1] = 0
+    Yc = np.concatenate([Yc, Yc[:, :1] * 1e-2 * (1 + 0.5 * rng.random(Yc[:, :1].shape))], axis=1)
+    Yc32, Yf32 = np.ascontiguousarray(Yc, dtype=F), np.ascontiguousarray(Yf, dtype=F)
+    Yc, Yf = Yc32.astype(np.float64), Yf32.astype(np.float64)
+    nh, ncf, nv = Yc.shape[0], Yc.shape[1], g.nv
+    dtg = 0.4358665215084590 * N.dt
+    s_c, s_f = (g.radius + g.z_c) / g.radius, (g.radius + g.z_f) / g.radius
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = (phic.astype(F)[1:] - phic.astype(F)[:-1]).astype(np.float64)  # as capi.cu: difference of the rounded values
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif), pad(np.zeros(nv + 1))]).astype(F)
+    A = g.dxdxi
+    Ginv = np.linalg.inv(np.einsum("...ab,...ac->...bc", A, A))
+    hgeo = np.zeros((nh, HG_N, 16), dtype=F)
+    hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
+    kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion)).astype(F)
+    mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, 0.0, mode, 1, 2,
+                   P.C_E * g.dz_c[0] / 2, dtg, 2, {"first_order": 1, "vanleer_limiter": 3}[upw], 2])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    # fused stage
+    Nc, Nf = np.zeros_like(Yc32), np.zeros_like(Yf32)
+    assert emu32.emu_stage_diff(nh, nv, ncf, p(sc), p(vl), p(hgeo), p(kdec), p(Yc32), p(Yf32), p(Nc), p(Nf)) == 0
+    Uc, Uf = Yc.copy(), Yf.copy()
+    o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
+    errs = [rel(Nc[:, k].astype(np.float64), Uc[:, k]) for k in range(ncf)] + [rel(Nf.astype(np.float64), Uf)]
+    assert max(errs[:ncf]) < 2e-6 and errs[-1] < 2e-4, errs
+    # Wfact planes (k_vdiff_jac2) → ldiv! (k_ldiv_diff2) with the tendency kernel k_vdiff_tend2
+    sc2 = sc.copy()
+    sc2[16] = 0
+    Rc = (rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3).astype(F)
+    Rf = rng.standard_normal(Yf.shape).astype(F)
+    Ytc, dYc, dYf = np.zeros_like(Yc32), np.zeros_like(Yc32), np.zeros_like(Yf32)
+    jac, jacd = np.zeros((nh, 15, 16, nv + 1), dtype=F), np.zeros((nh, 2, 16, nv + 1), dtype=F)
+    assert emu32.emu_vdiff(nh, nv, ncf, p(sc2), p(vl), p(hgeo), p(kdec), p(Yc32), p(Yf32), p(Rc), p(Rf), p(Ytc), p(jac), p(jacd), p(dYc), p(dYf)) == 0
+    pc = o.set_implicit_precomputed_quantities(Yc[:, :4].copy(), Yf.copy())
+    Jm = o.update_jacobian(Yc, Yf, pc, dtg)
+    oc, of = o.ldiv(Jm, Rc.astype(np.float64), Rf.astype(np.float64))
+    e2 = [rel(dYc[:, k].astype(np.float64), oc[:, k]) for k in range(ncf)] + [rel(dYf.astype(np.float64), of)]
+    assert max(e2) < 5e-5, e2
+    ot = np.zeros_like(Yc)
+    o.vertical_diffusion_boundary_layer_tendency(ot, Yc, pc)
+    e3 = [rel(Ytc[:, k].astype(np.float64), ot[:, k]) for k in range(1, ncf)]
+    assert max(e3) < 1e-4, e3
