@@ -1,0 +1,57 @@
+// CPU emulation of the DEFAULT fused implicit-stage kernel k5_imp_stage (kernels_imp5.cuh; Float64 instantiation, PCR column solve) —
+// the second-largest kernel of the benchmarked step — with the same CTA emulator as emu_vdiff.cpp.  The kernel source is compiled
+// unchanged; griddepcontrol.* assembles to nothing (empty assembler macros), and the packed-Float32 PTX belongs to specialisations
+// that are not instantiated here.  Test infrastructure only.
+#include <thread>
+#include <vector>
+#define b200 b200_emu5
+#include "cuda_runtime.h"
+thread_local uint3_emu threadIdx, blockIdx;
+std::barrier<>* g_cta_barrier = nullptr;
+namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
+#define __constant__
+#define FULL_MASK_EMU 0xffffffffu
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { __builtin_trap(); return v; }   // only the two-sided Thomas variant shuffles
+template <class T> inline T __shfl_sync(unsigned, T v, int) { __builtin_trap(); return v; }
+inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+// griddepcontrol.* (programmatic dependent launch) is a no-op for a single emulated grid: teach the assembler two empty macros so that
+// the inline PTX statements of common.cuh assemble to nothing
+__asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
+#include "kernels_imp5.cuh"
+
+using namespace b200;
+typedef double FT;
+
+template <class F>
+static void run_grid(int nblocks, F&& body) {
+  std::barrier<> bar(256);
+  g_cta_barrier = &bar;
+  std::vector<std::thread> th;
+  for (int t = 0; t < 256; ++t)
+    th.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; ++b) {
+        threadIdx = {(unsigned)t, 0, 0};
+        blockIdx = {(unsigned)b, 0, 0};
+        body();
+        bar.arrive_and_wait();
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+// sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh, dtγ, energy upwinding, ncf
+extern "C" __attribute__((visibility("default"))) int emu_imp5(int nh, int nv, const double* sc, const double* vl, const double* hgeo,
+                                                               const double* Uc, const double* Uf, double* Nc, double* Nf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = (int)sc[12]; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[11];
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  run_grid(nh, [&] { k5_imp_stage<FT, 2, 0, 2>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  return 0;
+}

@@ -367,3 +367,62 @@ def test_float32_instantiations_of_the_opt_in_kernels(emu32, vd, upw):
     o.vertical_diffusion_boundary_layer_tendency(ot, Yc, pc)
     e3 = [rel(Ytc[:, k].astype(np.float64), ot[:, k]) for k in range(1, ncf)]
     assert max(e3) < 1e-4, e3
+
+
+@pytest.fixture(scope="module")
+def emu5():
+    """tests/emu/emu_imp5.cpp: the DEFAULT fused implicit-stage kernel k5_imp_stage (Float64 instantiation, PCR solve) on the CTA emulator."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(HERE, "emu", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_imp5.so")
+    csrc = os.path.join(os.path.dirname(HERE), "climaatmos.jl_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden", "-I", os.path.join(HERE, "emu"), "-I", csrc,
+                    os.path.join(HERE, "emu", "emu_imp5.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("upw,rayleigh,deep,ze,dzb,ntr", [
+    ("vanleer_limiter", True, True, 12, 400.0, 0), ("first_order", False, False, 12, 400.0, 1), ("none", False, True, 12, 400.0, 0),
+    ("vanleer_limiter", True, True, 63, 30.0, 0), ("vanleer_limiter", False, True, 2, 15000.0, 0), ("vanleer_limiter", False, True, 5, 3000.0, 2),
+])
+def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleigh, deep, ze, dzb, ntr):
+    """k5_imp_stage<double, PCR> — the implicit-stage kernel of the benchmarked step (packed row layout, parallel cyclic reduction) — run on
+    the CPU from its unchanged source against the oracle's cache_imp! → Wfact → T_imp! → ldiv! → U −= ΔU → cache_imp! → T_post_imp!."""
+    P = prm.DycoreParams(zd_rayleigh=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
+    N = prm.DycoreNumerics(dt=250.0, rayleigh_sponge=rayleigh, energy_upwinding=upw)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(5)
+    Yc = Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)  # non-zero boundary faces: the kernel filters them on load
+    Yc = np.ascontiguousarray(np.concatenate([Yc] + [Yc[:, :1] * 1e-2 * (1 + 0.5 * rng.random(Yc[:, :1].shape)) for _ in range(ntr)], axis=1))
+    Yf = np.ascontiguousarray(Yf)
+    nh, ncf, nv = Yc.shape[0], Yc.shape[1], g.nv
+    dtg = 0.4358665215084590 * N.dt
+    s_c = (g.radius + g.z_c) / g.radius if deep else np.ones(nv)
+    s_f = (g.radius + g.z_f) / g.radius if deep else np.ones(nv + 1)
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    brw = o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if rayleigh else np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif), pad(brw)])
+    A = g.dxdxi
+    Ginv = np.linalg.inv(np.einsum("...ab,...ac->...bc", A, A))
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), dtg,
+                   {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw], ncf])
+    Nc, Nf = np.zeros_like(Yc), np.zeros_like(Yf)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emu5.emu_imp5(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf), p(Nc), p(Nf)) == 0
+    Uc, Uf = Yc.copy(), Yf.copy()
+    o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
+    for k in range(ncf):
+        assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
+    assert rel(Nc[:, 0] - Yc[:, 0], Uc[:, 0] - Yc[:, 0]) < 1e-8 and rel(Nc[:, 3] - Yc[:, 3], Uc[:, 3] - Yc[:, 3]) < 1e-8
+    assert rel(Nf, Uf) < 1e-10
