@@ -426,3 +426,86 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
         assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
     assert rel(Nc[:, 0] - Yc[:, 0], Uc[:, 0] - Yc[:, 0]) < 1e-8 and rel(Nc[:, 3] - Yc[:, 3], Uc[:, 3] - Yc[:, 3]) < 1e-8
     assert rel(Nf, Uf) < 1e-10
+
+
+@pytest.fixture(scope="module")
+def emux():
+    """tests/emu/emu_exp5.cpp: k5_exp_a / k5_exp_c (Float64 instantiations) on the CTA emulator with emulated warp shuffles."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(HERE, "emu", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_exp5.so")
+    csrc = os.path.join(os.path.dirname(HERE), "climaatmos.jl_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden", "-I", os.path.join(HERE, "emu"), "-I", csrc,
+                    os.path.join(HERE, "emu", "emu_exp5.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
+def _full_hgeo(g, P, deep):
+    """hgeo[h][HG_N][16] as capi.cu:create_geo fills the components the element kernels stage (J2 … COS2)."""
+    nh = g.J2.shape[0]
+    A = g.dxdxi.reshape(nh, 16, 2, 2)
+    a00, a01, a10, a11 = A[..., 0, 0], A[..., 0, 1], A[..., 1, 0], A[..., 1, 1]
+    gc11, gc12, gc22 = a00 * a00 + a10 * a10, a00 * a01 + a10 * a11, a01 * a01 + a11 * a11
+    det, dA = gc11 * gc22 - gc12 * gc12, a00 * a11 - a01 * a10
+    lat = np.radians(g.lat.reshape(nh, 16))
+    fv, fw = 2 * P.Omega * np.cos(lat), 2 * P.Omega * np.sin(lat)
+    ai01, ai11 = -a01 / dA, a00 / dA
+    J2 = g.J2.reshape(nh, 16)
+    hg = np.zeros((nh, HG_N, 16))
+    for k, val in enumerate([J2, 1 / J2, gc22 / det, -gc12 / det, gc11 / det, gc11, gc12, gc22, ai01 * fv if deep else 0 * fv,
+                             ai11 * fv if deep else 0 * fv, fw, np.sin(lat) ** 2, np.cos(lat) ** 2]):
+        hg[:, k] = val
+    return hg
+
+
+@pytest.mark.parametrize("deep,sponge,ze,dzb", [(True, True, 12, 400.0), (False, False, 12, 400.0), (True, True, 63, 30.0), (True, False, 3, 8000.0)])
+def test_emulated_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze, dzb):
+    """k5_exp_a and k5_exp_c — the two explicit-tendency kernels of the benchmarked step (packed row layout, ξ² contractions by warp
+    shuffles) — run on the CPU from their unchanged source (Float64 instantiation): the pre-DSS tendencies and ∇² fields against the
+    oracle's element-local `_rt_pre`, the hyperdiffusion apply against `_rt_post` on the same ∇² fields."""
+    P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
+    N = prm.DycoreNumerics(dt=250.0, rayleigh_sponge=sponge, viscous_sponge=sponge)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(17)
+    Yc = np.ascontiguousarray(Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape)))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    Yf[..., 0] = 0
+    Yf[..., -1] = 0
+    Yf = np.ascontiguousarray(Yf)
+    nh, nv = Yc.shape[0], g.nv
+    s_c = (g.radius + g.z_c) / g.radius if deep else np.ones(nv)
+    s_f = (g.radius + g.z_f) / g.radius if deep else np.ones(nv + 1)
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    z0 = np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif),
+                   pad(o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if sponge else z0), pad(o.beta_rayleigh(g.z_c, P.alpha_rayleigh_uh) if sponge else z0[:-1]),
+                   pad(o.beta_viscous(g.z_c) if sponge else z0[:-1]), pad(o.beta_viscous(g.z_f) if sponge else z0)])
+    hgeo = _full_hgeo(g, P, deep)
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(o.nu4_vort), float(o.nu4_scalar),
+                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, 4])
+    Dm, wq = np.ascontiguousarray(g.D, dtype=np.float64), np.ascontiguousarray(g.wq, dtype=np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    Ytc, Ytf, H = np.zeros_like(Yc), np.zeros_like(Yf), np.zeros_like(Yc)
+    assert emux.emu_exp5(0, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H)) == 0
+    pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
+    tc, tf, L = o._rt_pre(Yc, Yf, pc)
+    for k in range(4):
+        assert rel(Ytc[:, k], tc[:, k]) < 1e-10, ("exp_a tendency", k, rel(Ytc[:, k], tc[:, k]))
+    assert rel(Ytf, tf) < 1e-9, ("exp_a u3 tendency", rel(Ytf, tf))
+    for k in range(4):
+        assert rel(H[:, k], L[k]) < 1e-10, ("exp_a laplacian", k, rel(H[:, k], L[k]))
+    # hyperdiffusion apply on the (un-DSSed) ∇² fields: any H is a valid input for an element-local comparison
+    Hin = np.ascontiguousarray(np.stack(L, axis=1))
+    o._rt_post(tc, tf, Yc, L)
+    assert emux.emu_exp5(1, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin)) == 0
+    for k in range(4):
+        assert rel(Ytc[:, k], tc[:, k]) < 1e-10, ("exp_c", k, rel(Ytc[:, k], tc[:, k]))
+    assert rel(Ytf, tf) < 1e-9, ("exp_c u3", rel(Ytf, tf))
