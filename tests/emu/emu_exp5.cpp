@@ -65,11 +65,11 @@ static void run_grid(int nx, int ny, F&& body) {
 }
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, ν₄ᵥ, ν₄ₛ, divergence damping factor, hyperdiff, rayleigh, viscous,
-//     energy upwinding, ncf ; vl: [14][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw, bruh, bvc, bvf ; D [16], w [4]
-// which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k5_exp_c (reads H, updates Ytc, Ytf)
+//     energy upwinding, ncf, tracer upwinding ; vl: [14][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw, bruh, bvc, bvf ; D [16], w [4]
+// which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k5_exp_c (reads H, updates Ytc, Ytf), 2 / 3 = k5_tracer_a / k5_tracer_c
 extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh, int nv, const double* sc, const double* vl, const double* Dm,
                                                                const double* w, const double* hgeo, const double* Yc, const double* Yf,
-                                                               double* Ytc, double* Ytf, double* H) {
+                                                               double* Ytc, double* Ytf, double* H, double* Ylc) {
   Par<FT> P;
   memset(&P, 0, sizeof(P));
   P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
@@ -94,7 +94,12 @@ extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh
         c_Pd[(ww * 4 + k) * 2 + pp].x = md[ww * 16 + (2 * pp) * 4 + k];
         c_Pd[(ww * 4 + k) * 2 + pp].y = md[ww * 16 + (2 * pp + 1) * 4 + k];
       }
+  P.tupw = (int)sc[17];
+  const int ntr = P.ncf - 4;
   if (which == 0) run_grid(nh, 1, [&] { k5_exp_a<FT, 0>(P, hgeo, &V, Yc, Yf, Ytc, Ytf, H); });
-  else run_grid(nh, 3, [&] { k5_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
+  else if (which == 1) run_grid(nh, 3, [&] { k5_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
+  // passive tracers (grid = elements × tracers): 2 = k5_tracer_a (Yₜ, Yₜ_lim, ∇²χ → H), 3 = k5_tracer_c (tracer hyperdiffusion → Yₜ_lim)
+  else if (which == 2) run_grid(nh, ntr, [&] { k5_tracer_a<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ylc, H); });
+  else run_grid(nh, ntr, [&] { k5_tracer_c<FT>(P, hgeo, &V, Yc, H, Ylc); });
   return 0;
 }

@@ -490,11 +490,11 @@ def test_emulated_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze,
                    pad(o.beta_viscous(g.z_c) if sponge else z0[:-1]), pad(o.beta_viscous(g.z_f) if sponge else z0)])
     hgeo = _full_hgeo(g, P, deep)
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(o.nu4_vort), float(o.nu4_scalar),
-                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, 4])
+                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, 4, 3])
     Dm, wq = np.ascontiguousarray(g.D, dtype=np.float64), np.ascontiguousarray(g.wq, dtype=np.float64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     Ytc, Ytf, H = np.zeros_like(Yc), np.zeros_like(Yf), np.zeros_like(Yc)
-    assert emux.emu_exp5(0, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H)) == 0
+    assert emux.emu_exp5(0, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), None) == 0
     pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
     tc, tf, L = o._rt_pre(Yc, Yf, pc)
     for k in range(4):
@@ -505,7 +505,60 @@ def test_emulated_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze,
     # hyperdiffusion apply on the (un-DSSed) ∇² fields: any H is a valid input for an element-local comparison
     Hin = np.ascontiguousarray(np.stack(L, axis=1))
     o._rt_post(tc, tf, Yc, L)
-    assert emux.emu_exp5(1, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin)) == 0
+    assert emux.emu_exp5(1, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), None) == 0
     for k in range(4):
         assert rel(Ytc[:, k], tc[:, k]) < 1e-10, ("exp_c", k, rel(Ytc[:, k], tc[:, k]))
     assert rel(Ytf, tf) < 1e-9, ("exp_c u3", rel(Ytf, tf))
+
+
+@pytest.mark.parametrize("tupw,sponge,ze,dzb", [("vanleer_limiter", True, 12, 400.0), ("first_order", False, 12, 400.0), ("none", True, 63, 30.0),
+                                                ("vanleer_limiter", False, 3, 8000.0)])
+def test_emulated_tracer_kernels_match_oracle(emux, tupw, sponge, ze, dzb):
+    """k5_tracer_a / k5_tracer_c (passive tracers: horizontal advection into Yₜ_lim, ∇²χ, explicit vertical transport with tracer_upwinding,
+    viscous sponge; tracer hyperdiffusion) on the CPU emulator against the oracle's `_tracer_pre`, `_tracer_laplacians`, `_tracer_post`."""
+    P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius)
+    N = prm.DycoreNumerics(dt=250.0, rayleigh_sponge=sponge, viscous_sponge=sponge, tracer_upwinding=tupw)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(23)
+    Yc = Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    Yf[..., 0] = 0
+    Yf[..., -1] = 0
+    chis = [1e-2 * (1 + 0.5 * rng.random(Yc[:, 0].shape)), 0.5 * (1 + np.sin(np.radians(g.lat))[..., None] * np.exp(-o.c.z / 8000.0))]
+    Yc = np.ascontiguousarray(np.concatenate([Yc] + [(Yc[:, 0] * c)[:, None] for c in chis], axis=1))
+    Yf = np.ascontiguousarray(Yf)
+    nh, nv, ncf = Yc.shape[0], g.nv, Yc.shape[1]
+    s_c, s_f = (g.radius + g.z_c) / g.radius, (g.radius + g.z_f) / g.radius
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    z0 = np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif),
+                   pad(o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if sponge else z0), pad(o.beta_rayleigh(g.z_c, P.alpha_rayleigh_uh) if sponge else z0[:-1]),
+                   pad(o.beta_viscous(g.z_c) if sponge else z0[:-1]), pad(o.beta_viscous(g.z_f) if sponge else z0)])
+    hgeo = _full_hgeo(g, P, True)
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(o.nu4_vort), float(o.nu4_scalar),
+                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, ncf, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[tupw]])
+    Dm, wq = np.ascontiguousarray(g.D, dtype=np.float64), np.ascontiguousarray(g.wq, dtype=np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    Ytc, Ylc, H, Ytf = np.zeros_like(Yc), np.zeros_like(Yc), np.zeros_like(Yc), np.zeros_like(Yf)
+    assert emux.emu_exp5(2, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), p(Ylc)) == 0
+    pc = o.set_implicit_precomputed_quantities(Yc[:, :4].copy(), Yf.copy())
+    tc, lc = np.zeros_like(Yc), np.zeros_like(Yc)
+    o._tracer_pre(tc, lc, Yc, Yf, pc)
+    Lq = o._tracer_laplacians(Yc)
+    for k, q in enumerate(range(4, ncf)):
+        assert rel(Ylc[:, q], lc[:, q]) < 1e-10, ("T_lim", q, rel(Ylc[:, q], lc[:, q]))
+        assert rel(Ytc[:, q], tc[:, q]) < 1e-9, ("T_exp", q, rel(Ytc[:, q], tc[:, q]))
+        assert rel(H[:, q], Lq[k]) < 1e-10, ("laplacian", q)
+    Hin = np.zeros_like(Yc)
+    for k, q in enumerate(range(4, ncf)):
+        Hin[:, q] = Lq[k]
+    o._tracer_post(lc, Yc, Lq)
+    assert emux.emu_exp5(3, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), p(Ylc)) == 0
+    for q in range(4, ncf):
+        assert rel(Ylc[:, q], lc[:, q]) < 1e-10, ("T_lim after hyperdiffusion", q, rel(Ylc[:, q], lc[:, q]))
