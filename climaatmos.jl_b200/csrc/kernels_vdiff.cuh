@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(NT) k_vdiff_tend(Par<FT> P, VDiff<FT> D, const
 // Second generation of k_vdiff_tend: a quarter element (4 columns × 64 levels) per CTA, no state slabs — each thread loads its own
 // point, computes T (and K_h) once, and only the six per-column profiles the vertical differences need (ρ, K_h, s_d, uₕ/s_c, χ) and the
 // face weights go through 7.4 KB of shared memory, so the kernel is HBM-bound (read Y, read-modify-write Yₜ) instead of latency-bound.
-// Same operations in the same order as k_vdiff_tend: bitwise identical in the CPU emulator (tests/test_vdiff_kernels_cpu_emulation.py);
+// Same operations in the same order as k_vdiff_tend: bitwise identical in the CPU emulator (tests/test_kernels_cpu_emulation.py);
 // on the GPU the two differ by FMA contraction only (both ≤ 1.2e-13 from the Float64 oracle).  Measured on B200, he30/ze63 Float32:
 // 77 µs per launch against 267 µs for k_vdiff_tend (profiles/r1_vdiff_timing.jsonl).
 constexpr int VD2_ST = 66;  // column stride

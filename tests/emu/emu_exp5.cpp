@@ -2,7 +2,7 @@
 // instantiations), from their unchanged source.  On top of the CTA emulator of emu_vdiff.cpp this one emulates warp shuffles: the 32
 // host threads of a warp meet at a per-warp barrier, publish their value, and read the source lane's (all shuffles of these kernels are
 // executed by full, converged warps).  griddepcontrol.* assembles to nothing; the packed-Float32 PTX is not instantiated.
-// Test infrastructure only (tests/test_vdiff_kernels_cpu_emulation.py).
+// Test infrastructure only (tests/test_kernels_cpu_emulation.py).
 #include <thread>
 #include <vector>
 #define b200 b200_emux

@@ -1,6 +1,6 @@
 // CPU emulation of single CTAs running the vertical-diffusion kernels of climaatmos.jl_b200/csrc/kernels_vdiff.cuh (and k_wfact, whose
 // planes k_ldiv_diff consumes) — the kernel source is compiled unchanged by g++ against the stub cuda_runtime.h in this directory;
-// 256 host threads play the threads of a block.  Test infrastructure only (tests/test_vdiff_kernels_cpu_emulation.py): it checks
+// 256 host threads play the threads of a block.  Test infrastructure only (tests/test_kernels_cpu_emulation.py): it checks
 // indexing, barriers-as-phases and arithmetic of the kernels against the oracle when no GPU is at hand.  It is NOT a product path.
 #include <thread>
 #include <vector>

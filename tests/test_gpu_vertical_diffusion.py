@@ -151,7 +151,7 @@ def test_step_with_vertical_diffusion_matches_oracle(FT, implicit):
 
 @pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
                     reason="k_lim_vborrow was written after the round's GPU budget was spent: it matches the oracle bit for bit in the CPU "
-                           "CTA emulator (tests/test_vdiff_kernels_cpu_emulation.py) but has not run on a B200 yet (set B200_RUN_UNVALIDATED=1)")
+                           "CTA emulator (tests/test_kernels_cpu_emulation.py) but has not run on a B200 yet (set B200_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_vertical_mass_borrowing_limiter_matches_oracle(FT):
     """lim! with tracer_nonnegativity_method: vertical_water_borrowing (limited_tendencies.jl:95-121) through b200_lim, and a step."""

@@ -1,9 +1,13 @@
-"""The vertical-diffusion CUDA kernels (csrc/kernels_vdiff.cuh), executed on the CPU: tests/emu/ compiles the kernel SOURCE
-unchanged with g++ against a stub cuda_runtime.h and runs each CTA with 256 host threads and a std::barrier for
-__syncthreads().  k_vdiff_tend, k_wfact → k_vdiff_jac → k_ldiv_diff are then compared with the oracle (Float64).
+"""The CUDA kernel sources of climaatmos.jl_b200/csrc, executed on the CPU: tests/emu/ compiles the kernel headers UNCHANGED with g++
+against a stub cuda_runtime.h and runs each CTA with 256 host threads — a std::barrier for __syncthreads(), per-warp barriers and an
+exchange buffer for warp shuffles / votes / __syncwarp (emu_exp5.cpp) — and the results are compared with the oracle (Float64
+instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k5_exp_c, k5_tracer_a, k5_tracer_c,
+k5_imp_stage (the compute kernels of the benchmarked step), the hook kernels of kernels_implicit.cuh and their second generation, and
+the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
-This is a stand-in for the GPU parity run of these kernels (tests/test_gpu_vertical_diffusion.py), written when the round's GPU
-budget was spent: it exercises the indexing, phase structure and arithmetic of the very same code, not warp-level behaviour."""
+Test infrastructure only: it checks indexing, phase structure and arithmetic of the very code that runs on the B200, not timing and
+not the packed-Float32 PTX specialisations.  It was written when the round's GPU budget was spent and is how the kernels of
+kernels_vdiff.cuh were debugged before their GPU runs."""
 import ctypes as C
 import os
 import shutil
