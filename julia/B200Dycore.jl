@@ -68,7 +68,8 @@ check(rc, what) = rc == 0 || error("$what: " * unsafe_string(ccall((:b200_last_e
 # VIJFH parent array of a field on the device: (Nv, 4, 4, Nf, Nh), level fastest
 dptr(f) = reinterpret(Ptr{Cvoid}, pointer(parent(Fields.field_values(f))))
 stream() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
-upw(x) = x == Val(:none) ? Int32(0) : x == Val(:first_order) ? Int32(1) : Int32(3)
+# 0 none, 1 first_order, 2 third_order (b200_create rejects it: not built), 3 vanleer_limiter
+upw(x) = x == Val(:none) ? Int32(0) : x == Val(:first_order) ? Int32(1) : x == Val(:third_order) ? Int32(2) : Int32(3)
 
 """
     create(Y, p; approximate_solve_iters = 1) -> Ctx

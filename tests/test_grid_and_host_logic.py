@@ -147,6 +147,18 @@ def test_create_without_gpu_fails_loudly(lib):
         dycore.AtmosSimulation(h_elem=2, z_elem=4)
 
 
+def test_create_validates_parameters_before_touching_a_device(lib):
+    """Configuration errors are reported by b200_create itself (no device needed): implicit_diffusion without a vert_diff model — the
+    reference's update_diffusion_jacobian! has no diffusivity then — and more tracers than the documented maximum."""
+    from climaatmos_jl_b200 import capi
+
+    g = G.make_sphere_grid(h_elem=2, z_elem=4)
+    with pytest.raises(RuntimeError, match="implicit_diffusion needs a vert_diff model"):
+        capi.create_context(g, params.DycoreParams(), params.DycoreNumerics(implicit_diffusion=True))
+    with pytest.raises(RuntimeError, match="n_tracers"):
+        capi.create_context(g, params.DycoreParams(), params.DycoreNumerics(), n_tracers=5)
+
+
 def test_entry_points_reject_a_null_context(lib):
     """Error convention of the C-ABI (include/b200_dycore.h): <0 and a message via b200_last_error, nothing crosses as a crash —
     the glue turns it into the exception solve_atmos! catches (src/simulation/solve.jl:140-149).  No device is touched."""
