@@ -1,0 +1,70 @@
+// CPU emulation of the weighted-DSS kernel of the benchmarked step, k_dss2 (kernels_dss.cuh; Float64 instantiation, single-rank path),
+// from its unchanged source, with the node records built like capi.cu:create_geo builds them.  Test infrastructure only.
+#include <thread>
+#include <vector>
+#define b200 b200_emud
+#include "cuda_runtime.h"
+thread_local uint3_emu threadIdx, blockIdx;
+std::barrier<>* g_cta_barrier = nullptr;
+// static __shared__ arrays of these kernels: one instance per kernel instantiation, shared by the 256 host threads of the emulated CTA
+#undef __shared__
+#define __shared__ static
+struct dim3_emu { unsigned x, y, z; };
+static dim3_emu gridDim{1, 1, 1}, blockDim{64, 4, 1};
+inline void __threadfence_system() {}
+inline void __threadfence() {}
+inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline long long clock64() { return 0; }
+inline void __nanosleep(unsigned) {}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline void __trap() { __builtin_trap(); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+__asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
+#include "kernels_dss.cuh"
+
+using namespace b200;
+typedef double FT;
+
+// state DSS (ρ, (uₕ₁,uₕ₂) as a Covariant12 pair, ρe_tot, u₃): off/mem = CSR of the unique perimeter nodes (mem = elem·16 + node),
+// hgeo [nh][HG_N][16] with HG_DSSW, HG_A**, HG_AI** filled
+extern "C" __attribute__((visibility("default"))) int emu_dss_state(int nh, int nv, int nnodes, const int* off, const int* mem,
+                                                                    const double* hgeo, double* Yc, double* Yf) {
+  std::vector<DssNode<FT>> rec((size_t)nnodes);
+  memset(rec.data(), 0, rec.size() * sizeof(DssNode<FT>));
+  for (int nd = 0; nd < nnodes; ++nd) {
+    DssNode<FT>& R = rec[nd];
+    R.cnt = off[nd + 1] - off[nd];
+    for (int q = 0; q < R.cnt; ++q) {
+      const int m = mem[off[nd] + q];
+      const FT* o = hgeo + (size_t)(m >> 4) * HG_N * 16 + (m & 15);
+      R.mem[q] = m;
+      R.w[q] = o[HG_DSSW * 16];
+      R.ai[q][0] = o[HG_AI00 * 16]; R.ai[q][1] = o[HG_AI10 * 16]; R.ai[q][2] = o[HG_AI01 * 16]; R.ai[q][3] = o[HG_AI11 * 16];
+      R.a[q][0] = o[HG_A00 * 16]; R.a[q][1] = o[HG_A10 * 16]; R.a[q][2] = o[HG_A01 * 16]; R.a[q][3] = o[HG_A11 * 16];
+    }
+  }
+  DssArgs A;
+  memset(&A, 0, sizeof(A));
+  const int cs = 16 * nv;
+  A.n = 4;
+  A.it[0] = DssItem{Yc, nullptr, nullptr, nullptr, nv, 4 * cs, 0};
+  A.it[1] = DssItem{Yc + cs, Yc + 2 * cs, nullptr, nullptr, nv, 4 * cs, 0};
+  A.it[2] = DssItem{Yc + 3 * cs, nullptr, nullptr, nullptr, nv, 4 * cs, 0};
+  A.it[3] = DssItem{Yf, nullptr, nullptr, nullptr, nv + 1, 16 * (nv + 1), 0};
+  P2PWait W{nullptr, nullptr, nullptr, 0};
+  const int nblocks = (nnodes + 3) / 4;
+  std::barrier<> bar(256);
+  g_cta_barrier = &bar;
+  std::vector<std::thread> th;
+  for (int t = 0; t < 256; ++t)
+    th.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; ++b) {
+        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
+        blockIdx = {(unsigned)b, 0, 0};
+        k_dss2<FT, 4, 0x2, false, false>(A, rec.data(), 0, nnodes, nh, W);
+        bar.arrive_and_wait();
+      }
+    });
+  for (auto& x : th) x.join();
+  return 0;
+}

@@ -566,3 +566,57 @@ def test_emulated_tracer_kernels_match_oracle(emux, tupw, sponge, ze, dzb):
     assert emux.emu_exp5(3, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), p(Ylc)) == 0
     for q in range(4, ncf):
         assert rel(Ylc[:, q], lc[:, q]) < 1e-10, ("T_lim after hyperdiffusion", q, rel(Ylc[:, q], lc[:, q]))
+
+
+@pytest.fixture(scope="module")
+def emud():
+    """tests/emu/emu_dss.cpp: k_dss2 (Float64 instantiation, single-rank path) on the CTA emulator."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = os.path.join(HERE, "emu", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemu_dss.so")
+    csrc = os.path.join(os.path.dirname(HERE), "climaatmos.jl_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden", "-I", os.path.join(HERE, "emu"), "-I", csrc,
+                    os.path.join(HERE, "emu", "emu_dss.cpp"), "-o", so], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("he,ze", [(2, 5), (3, 12), (4, 63)])
+def test_emulated_state_dss_matches_oracle(emud, he, ze):
+    """k_dss2 — the weighted DSS of the state (ρ and ρe_tot as scalars, uₕ as a Covariant12 vector summed in the local physical basis, u₃
+    on faces) with the per-node records of capi.cu:create_geo — on the CPU emulator against the oracle's Spaces.weighted_dss! restatement,
+    including the pole and cube-corner elements (3-member vertices)."""
+    HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
+    P = prm.DycoreParams()
+    g = G.make_sphere_grid(FT=np.float64, h_elem=he, z_elem=ze, z_max=30000.0, dz_bottom=30.0 if ze == 63 else 500.0, radius=P.planet_radius)
+    o = Oracle(g, P, prm.DycoreNumerics(), np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(31)
+    Yc = np.ascontiguousarray(Yc * (1 + 1e-2 * rng.standard_normal(Yc.shape)))  # discontinuous across elements
+    Yf = np.ascontiguousarray(0.3 * g.dz_f * rng.standard_normal(Yf.shape))
+    nh, nv = Yc.shape[0], g.nv
+    offs, mem = G.dss_node_csr(g.topology, 4)
+    off = np.ascontiguousarray(offs, dtype=np.int32)
+    m32 = np.ascontiguousarray(mem[:, 0] * 16 + mem[:, 2] * 4 + mem[:, 1], dtype=np.int32)  # (elem, i, j) → elem·16 + j·4 + i
+    A = g.dxdxi.reshape(nh, 16, 2, 2)
+    dA = A[..., 0, 0] * A[..., 1, 1] - A[..., 0, 1] * A[..., 1, 0]
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_DSSW] = o.dss_w.reshape(nh, 16)
+    hgeo[:, HG_A00], hgeo[:, HG_A00 + 1], hgeo[:, HG_A00 + 2], hgeo[:, HG_A00 + 3] = A[..., 0, 0], A[..., 0, 1], A[..., 1, 0], A[..., 1, 1]
+    hgeo[:, HG_AI00], hgeo[:, HG_AI00 + 1] = A[..., 1, 1] / dA, -A[..., 0, 1] / dA
+    hgeo[:, HG_AI00 + 2], hgeo[:, HG_AI00 + 3] = -A[..., 1, 0] / dA, A[..., 0, 0] / dA
+    gc, gf = Yc.copy(), Yf.copy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emud.emu_dss_state(nh, nv, len(off) - 1, p(off), p(m32), p(hgeo), p(gc), p(gf)) == 0
+    oc, of = Yc.copy(), Yf.copy()
+    o.dss_state(oc, of)
+    assert np.abs(oc - Yc).max() > 0
+    for k in range(4):
+        assert rel(gc[:, k], oc[:, k]) < 1e-14, (k, rel(gc[:, k], oc[:, k]))
+    assert rel(gf, of) < 1e-14
+    # interior nodes untouched, and the result is continuous: a second DSS changes nothing beyond round-off
+    assert np.array_equal(gc[:, :, 1:3, 1:3], Yc[:, :, 1:3, 1:3])
+    g2c, g2f = gc.copy(), gf.copy()
+    assert emud.emu_dss_state(nh, nv, len(off) - 1, p(off), p(m32), p(hgeo), p(g2c), p(g2f)) == 0
+    assert rel(g2c, gc) < 1e-14 and rel(g2f, gf) < 1e-14
