@@ -68,3 +68,53 @@ extern "C" __attribute__((visibility("default"))) int emu_dss_state(int nh, int 
   for (auto& x : th) x.join();
   return 0;
 }
+
+static std::vector<DssNode<FT>> build_records(int nnodes, const int* off, const int* mem, const double* hgeo) {
+  std::vector<DssNode<FT>> rec((size_t)nnodes);
+  memset(rec.data(), 0, rec.size() * sizeof(DssNode<FT>));
+  for (int nd = 0; nd < nnodes; ++nd) {
+    DssNode<FT>& R = rec[nd];
+    R.cnt = off[nd + 1] - off[nd];
+    for (int q = 0; q < R.cnt; ++q) {
+      const int m = mem[off[nd] + q];
+      const FT* o = hgeo + (size_t)(m >> 4) * HG_N * 16 + (m & 15);
+      R.mem[q] = m;
+      R.w[q] = o[HG_DSSW * 16];
+      R.ai[q][0] = o[HG_AI00 * 16]; R.ai[q][1] = o[HG_AI10 * 16]; R.ai[q][2] = o[HG_AI01 * 16]; R.ai[q][3] = o[HG_AI11 * 16];
+      R.a[q][0] = o[HG_A00 * 16]; R.a[q][1] = o[HG_A10 * 16]; R.a[q][2] = o[HG_A01 * 16]; R.a[q][3] = o[HG_A11 * 16];
+    }
+  }
+  return rec;
+}
+
+// k_axpy_dss<FT, 3>: out = dss!(filter(base + Σ_{k<3} c_k T_k)) — the stage increment fused with the state DSS (single rank): node blocks
+// interleaved with one interior block per element.  T: three (Tc, Tf) pairs; dmask as in AxDssArgs.
+extern "C" __attribute__((visibility("default"))) int emu_axpy_dss3(int nh, int nv, int ncf, int nnodes, const int* off, const int* mem,
+                                                                    const double* hgeo, const double* base_c, const double* base_f,
+                                                                    const double* T0c, const double* T0f, const double* T1c, const double* T1f,
+                                                                    const double* T2c, const double* T2f, const double* coef, unsigned dmask,
+                                                                    double* out_c, double* out_f) {
+  std::vector<DssNode<FT>> rec = build_records(nnodes, off, mem, hgeo);
+  AxDssArgs<FT> A;
+  memset(&A, 0, sizeof(A));
+  A.out_c = out_c; A.out_f = out_f; A.base_c = base_c; A.base_f = base_f;
+  A.Tc[0] = T0c; A.Tf[0] = T0f; A.Tc[1] = T1c; A.Tf[1] = T1f; A.Tc[2] = T2c; A.Tf[2] = T2f;
+  for (int k = 0; k < 3; ++k) A.c[k] = coef[k];
+  A.dmask = dmask; A.ncf = ncf; A.nv = nv; A.nh = nh;
+  P2PWait W{nullptr, nullptr, nullptr, 0};
+  const int nbn = (nnodes + 3) / 4, nint = nh, nblocks = nbn + nint;
+  std::barrier<> bar(256);
+  g_cta_barrier = &bar;
+  std::vector<std::thread> th;
+  for (int t = 0; t < 256; ++t)
+    th.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; ++b) {
+        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
+        blockIdx = {(unsigned)b, 0, 0};
+        k_axpy_dss<FT, 3, false, false>(A, rec.data(), 0, nnodes, nbn, nint, W);
+        bar.arrive_and_wait();
+      }
+    });
+  for (auto& x : th) x.join();
+  return 0;
+}

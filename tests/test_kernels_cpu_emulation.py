@@ -1,8 +1,7 @@
 """The CUDA kernel sources of climaatmos.jl_b200/csrc, executed on the CPU: tests/emu/ compiles the kernel headers UNCHANGED with g++
 against a stub cuda_runtime.h and runs each CTA with 256 host threads — a std::barrier for __syncthreads(), per-warp barriers and an
 exchange buffer for warp shuffles / votes / __syncwarp (emu_exp5.cpp) — and the results are compared with the oracle (Float64
-instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k5_exp_c, k5_tracer_a, k5_tracer_c,
-k5_imp_stage (the compute kernels of the benchmarked step), the hook kernels of kernels_implicit.cuh and their second generation, and
+instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k5_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the hook kernels of kernels_implicit.cuh and their second generation, and
 the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
 Test infrastructure only: it checks indexing, phase structure and arithmetic of the very code that runs on the B200, not timing and
@@ -620,3 +619,52 @@ def test_emulated_state_dss_matches_oracle(emud, he, ze):
     g2c, g2f = gc.copy(), gf.copy()
     assert emud.emu_dss_state(nh, nv, len(off) - 1, p(off), p(m32), p(hgeo), p(g2c), p(g2f)) == 0
     assert rel(g2c, gc) < 1e-14 and rel(g2f, gf) < 1e-14
+
+
+@pytest.mark.parametrize("he,ze,ntr,dmask", [(2, 5, 0, 0), (3, 12, 1, 0b001), (2, 63, 0, 0b011)])
+def test_emulated_fused_increment_dss_matches_oracle(emud, he, ze, ntr, dmask):
+    """k_axpy_dss<3 terms> — the stage increment U = u + Σ cₖTₖ (terms flagged in dmask enter as cₖ·(Tₖ − u): the stage-solution form),
+    the u₃ boundary filter and the state DSS in one kernel — on the CPU emulator against NumPy increment + filter + the oracle's dss!."""
+    HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
+    P = prm.DycoreParams()
+    g = G.make_sphere_grid(FT=np.float64, h_elem=he, z_elem=ze, z_max=30000.0, dz_bottom=30.0 if ze == 63 else 500.0, radius=P.planet_radius)
+    o = Oracle(g, P, prm.DycoreNumerics(), np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(37)
+    Yc = np.concatenate([Yc] + [Yc[:, :1] * 1e-2 * (1 + 0.5 * rng.random(Yc[:, :1].shape)) for _ in range(ntr)], axis=1)
+    base_c = np.ascontiguousarray(Yc * (1 + 1e-2 * rng.standard_normal(Yc.shape)))
+    base_f = np.ascontiguousarray(0.3 * g.dz_f * rng.standard_normal(Yf.shape))
+    nh, nv, ncf = Yc.shape[0], g.nv, Yc.shape[1]
+    T = []
+    for k in range(3):
+        if dmask >> k & 1:  # a stage solution close to the base state
+            T.append((np.ascontiguousarray(base_c * (1 + 1e-3 * rng.standard_normal(Yc.shape))), np.ascontiguousarray(base_f + 0.01 * g.dz_f * rng.standard_normal(Yf.shape))))
+        else:  # a tendency
+            T.append((np.ascontiguousarray(1e-4 * base_c * rng.standard_normal(Yc.shape)), np.ascontiguousarray(1e-3 * g.dz_f * rng.standard_normal(Yf.shape))))
+    coef = np.array([0.37 if dmask & 1 else 120.0, -0.21 if dmask & 2 else 55.0, 80.0])
+    offs, mem = G.dss_node_csr(g.topology, 4)
+    off = np.ascontiguousarray(offs, dtype=np.int32)
+    m32 = np.ascontiguousarray(mem[:, 0] * 16 + mem[:, 2] * 4 + mem[:, 1], dtype=np.int32)
+    A = g.dxdxi.reshape(nh, 16, 2, 2)
+    dA = A[..., 0, 0] * A[..., 1, 1] - A[..., 0, 1] * A[..., 1, 0]
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_DSSW] = o.dss_w.reshape(nh, 16)
+    hgeo[:, HG_A00], hgeo[:, HG_A00 + 1], hgeo[:, HG_A00 + 2], hgeo[:, HG_A00 + 3] = A[..., 0, 0], A[..., 0, 1], A[..., 1, 0], A[..., 1, 1]
+    hgeo[:, HG_AI00], hgeo[:, HG_AI00 + 1] = A[..., 1, 1] / dA, -A[..., 0, 1] / dA
+    hgeo[:, HG_AI00 + 2], hgeo[:, HG_AI00 + 3] = -A[..., 1, 0] / dA, A[..., 0, 0] / dA
+    out_c, out_f = np.full_like(base_c, np.nan), np.full_like(base_f, np.nan)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emud.emu_axpy_dss3(nh, nv, ncf, len(off) - 1, p(off), p(m32), p(hgeo), p(base_c), p(base_f), p(T[0][0]), p(T[0][1]), p(T[1][0]), p(T[1][1]),
+                              p(T[2][0]), p(T[2][1]), p(coef), C.c_uint(dmask), p(out_c), p(out_f)) == 0
+    Uc, Uf = base_c.copy(), base_f.copy()
+    for k in range(3):
+        Uc += coef[k] * ((T[k][0] - base_c) if dmask >> k & 1 else T[k][0])
+        Uf += coef[k] * ((T[k][1] - base_f) if dmask >> k & 1 else T[k][1])
+    Uf[..., 0] = 0
+    Uf[..., -1] = 0
+    o.dss_state(Uc, Uf)
+    assert np.isfinite(out_c).all() and np.isfinite(out_f).all()  # every point written exactly once
+    for k in range(ncf):
+        assert rel(out_c[:, k], Uc[:, k]) < 1e-13, (k, rel(out_c[:, k], Uc[:, k]))
+    assert rel(out_f, Uf) < 1e-12
+    assert np.all(out_f[..., 0] == 0) and np.all(out_f[..., -1] == 0)
