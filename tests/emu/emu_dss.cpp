@@ -118,3 +118,33 @@ extern "C" __attribute__((visibility("default"))) int emu_axpy_dss3(int nh, int 
   for (auto& x : th) x.join();
   return 0;
 }
+
+// DSS of the ∇² fields inside T_exp (remaining_tendency.jl:18-21): (∇²u₁, ∇²u₂) as a Covariant12 pair, ∇²u₃ and ∇²s_d as scalars —
+// k_dss2<FT, 3, 0x1> on H [nh][ncf][16][nv]
+extern "C" __attribute__((visibility("default"))) int emu_dss_h(int nh, int nv, int ncf, int nnodes, const int* off, const int* mem,
+                                                                const double* hgeo, double* H) {
+  std::vector<DssNode<FT>> rec = build_records(nnodes, off, mem, hgeo);
+  DssArgs A;
+  memset(&A, 0, sizeof(A));
+  const int cs = 16 * nv;
+  A.n = 3;
+  A.it[0] = DssItem{H, H + cs, nullptr, nullptr, nv, ncf * cs, 0};
+  A.it[1] = DssItem{H + 2 * cs, nullptr, nullptr, nullptr, nv, ncf * cs, 0};
+  A.it[2] = DssItem{H + 3 * cs, nullptr, nullptr, nullptr, nv, ncf * cs, 0};
+  P2PWait W{nullptr, nullptr, nullptr, 0};
+  const int nblocks = (nnodes + 3) / 4;
+  std::barrier<> bar(256);
+  g_cta_barrier = &bar;
+  std::vector<std::thread> th;
+  for (int t = 0; t < 256; ++t)
+    th.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; ++b) {
+        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
+        blockIdx = {(unsigned)b, 0, 0};
+        k_dss2<FT, 3, 0x1, false, false>(A, rec.data(), 0, nnodes, nh, W);
+        bar.arrive_and_wait();
+      }
+    });
+  for (auto& x : th) x.join();
+  return 0;
+}

@@ -668,3 +668,57 @@ def test_emulated_fused_increment_dss_matches_oracle(emud, he, ze, ntr, dmask):
         assert rel(out_c[:, k], Uc[:, k]) < 1e-13, (k, rel(out_c[:, k], Uc[:, k]))
     assert rel(out_f, Uf) < 1e-12
     assert np.all(out_f[..., 0] == 0) and np.all(out_f[..., -1] == 0)
+
+
+@pytest.mark.parametrize("deep,sponge,he,ze,dzb", [(True, True, 2, 12, 400.0), (False, False, 3, 5, 3000.0)])
+def test_emulated_t_exp_composite_matches_oracle(emux, emud, deep, sponge, he, ze, dzb):
+    """T_exp_T_lim! as the library launches it — k5_exp_a → k_dss2 of the ∇² fields → k5_exp_c — entirely on the CPU emulator, against the
+    oracle's remaining_tendency! (which includes its own weighted DSS of the ∇² fields)."""
+    HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
+    P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=he, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
+    N = prm.DycoreNumerics(dt=250.0, rayleigh_sponge=sponge, viscous_sponge=sponge)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(41)
+    Yc = Yc * (1 + 1e-3 * rng.standard_normal(Yc.shape))
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    o.dss_state(Yc, Yf)  # a continuous state, as T_exp sees it
+    Yf[..., 0] = 0
+    Yf[..., -1] = 0
+    Yc, Yf = np.ascontiguousarray(Yc), np.ascontiguousarray(Yf)
+    nh, nv = Yc.shape[0], g.nv
+    s_c = (g.radius + g.z_c) / g.radius if deep else np.ones(nv)
+    s_f = (g.radius + g.z_f) / g.radius if deep else np.ones(nv + 1)
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    z0 = np.zeros(nv + 1)
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif),
+                   pad(o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w) if sponge else z0), pad(o.beta_rayleigh(g.z_c, P.alpha_rayleigh_uh) if sponge else z0[:-1]),
+                   pad(o.beta_viscous(g.z_c) if sponge else z0[:-1]), pad(o.beta_viscous(g.z_f) if sponge else z0)])
+    hgeo = _full_hgeo(g, P, deep)
+    A = g.dxdxi.reshape(nh, 16, 2, 2)
+    dA = A[..., 0, 0] * A[..., 1, 1] - A[..., 0, 1] * A[..., 1, 0]
+    hgeo[:, HG_DSSW] = o.dss_w.reshape(nh, 16)
+    hgeo[:, HG_A00], hgeo[:, HG_A00 + 1], hgeo[:, HG_A00 + 2], hgeo[:, HG_A00 + 3] = A[..., 0, 0], A[..., 0, 1], A[..., 1, 0], A[..., 1, 1]
+    hgeo[:, HG_AI00], hgeo[:, HG_AI00 + 1] = A[..., 1, 1] / dA, -A[..., 0, 1] / dA
+    hgeo[:, HG_AI00 + 2], hgeo[:, HG_AI00 + 3] = -A[..., 1, 0] / dA, A[..., 0, 0] / dA
+    sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(o.nu4_vort), float(o.nu4_scalar),
+                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, 4, 3])
+    Dm, wq = np.ascontiguousarray(g.D, dtype=np.float64), np.ascontiguousarray(g.wq, dtype=np.float64)
+    offs, mem = G.dss_node_csr(g.topology, 4)
+    off = np.ascontiguousarray(offs, dtype=np.int32)
+    m32 = np.ascontiguousarray(mem[:, 0] * 16 + mem[:, 2] * 4 + mem[:, 1], dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    Ytc, Ytf, H = np.zeros_like(Yc), np.zeros_like(Yf), np.zeros_like(Yc)
+    assert emux.emu_exp5(0, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), None) == 0
+    assert emud.emu_dss_h(nh, nv, 4, len(off) - 1, p(off), p(m32), p(hgeo), p(H)) == 0
+    assert emux.emu_exp5(1, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), None) == 0
+    pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
+    tc, tf = o.remaining_tendency(Yc, Yf, pc)
+    for k in range(4):
+        assert rel(Ytc[:, k], tc[:, k]) < 1e-10, (k, rel(Ytc[:, k], tc[:, k]))
+    assert rel(Ytf, tf) < 1e-9
