@@ -148,3 +148,44 @@ extern "C" __attribute__((visibility("default"))) int emu_dss_h(int nh, int nv, 
   for (auto& x : th) x.join();
   return 0;
 }
+
+// k_axpy_dss with n = 1..6 terms (pointer arrays Tc[n], Tf[n]); otherwise as emu_axpy_dss3
+template <int N>
+static void run_axdss(const AxDssArgs<FT>& A, const std::vector<DssNode<FT>>& rec, int nnodes, int nh) {
+  P2PWait W{nullptr, nullptr, nullptr, 0};
+  const int nbn = (nnodes + 3) / 4, nint = nh, nblocks = nbn + nint;
+  std::barrier<> bar(256);
+  g_cta_barrier = &bar;
+  std::vector<std::thread> th;
+  for (int t = 0; t < 256; ++t)
+    th.emplace_back([&, t] {
+      for (int b = 0; b < nblocks; ++b) {
+        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
+        blockIdx = {(unsigned)b, 0, 0};
+        k_axpy_dss<FT, N, false, false>(A, rec.data(), 0, nnodes, nbn, nint, W);
+        bar.arrive_and_wait();
+      }
+    });
+  for (auto& x : th) x.join();
+}
+extern "C" __attribute__((visibility("default"))) int emu_axpy_dss_n(int n, int nh, int nv, int ncf, int nnodes, const int* off, const int* mem,
+                                                                     const double* hgeo, const double* base_c, const double* base_f,
+                                                                     const double* const* Tc, const double* const* Tf, const double* coef,
+                                                                     unsigned dmask, double* out_c, double* out_f) {
+  std::vector<DssNode<FT>> rec = build_records(nnodes, off, mem, hgeo);
+  AxDssArgs<FT> A;
+  memset(&A, 0, sizeof(A));
+  A.out_c = out_c; A.out_f = out_f; A.base_c = base_c; A.base_f = base_f;
+  for (int k = 0; k < n; ++k) { A.Tc[k] = Tc[k]; A.Tf[k] = Tf[k]; A.c[k] = coef[k]; }
+  A.dmask = dmask; A.ncf = ncf; A.nv = nv; A.nh = nh;
+  switch (n) {
+    case 1: run_axdss<1>(A, rec, nnodes, nh); break;
+    case 2: run_axdss<2>(A, rec, nnodes, nh); break;
+    case 3: run_axdss<3>(A, rec, nnodes, nh); break;
+    case 4: run_axdss<4>(A, rec, nnodes, nh); break;
+    case 5: run_axdss<5>(A, rec, nnodes, nh); break;
+    case 6: run_axdss<6>(A, rec, nnodes, nh); break;
+    default: return -1;
+  }
+  return 0;
+}

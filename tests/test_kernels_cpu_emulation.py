@@ -722,3 +722,106 @@ def test_emulated_t_exp_composite_matches_oracle(emux, emud, deep, sponge, he, z
     for k in range(4):
         assert rel(Ytc[:, k], tc[:, k]) < 1e-10, (k, rel(Ytc[:, k], tc[:, k]))
     assert rel(Ytf, tf) < 1e-9
+
+
+def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5):
+    """One ARS343 step assembled from the emulated PRODUCT kernels in the data flow of the fused stepper (capi.cu: impl_step, fused path):
+    stage-solution form of the increments (U_i = u + Σ α_ij (N_j − u) + dt Σ β_ij T_exp[j], k_axpy_dss with dmask), k5_imp_stage → k_dss2,
+    T_exp = k5_exp_a → k_dss2(∇²) → k5_exp_c, and the stiffly-accurate final increment from N₄ — against the oracle's LITERAL step
+    (u + dt Σ bⱼ (T_exp[j] + T_imp[j]) with T_imp formed explicitly).  The host orchestration below restates impl_step's coefficient
+    recursion; the arithmetic on the fields is all done by the kernels' own source."""
+    HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
+    P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=8, z_max=30000.0, dz_bottom=500.0, radius=P.planet_radius)
+    N = prm.DycoreNumerics(dt=300.0, rayleigh_sponge=True, viscous_sponge=True)
+    o = Oracle(g, P, N, np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    Yc, Yf = np.ascontiguousarray(Yc), np.ascontiguousarray(Yf)
+    nh, nv, ncf = Yc.shape[0], g.nv, 4
+    dt = N.dt
+    s_c, s_f = (g.radius + g.z_c) / g.radius, (g.radius + g.z_f) / g.radius
+    pad = lambda a: np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(64 - len(a))])
+    phic = P.grav * g.z_c
+    dphif = np.zeros(nv + 1)
+    dphif[1:-1] = phic[1:] - phic[:-1]
+    vl = np.stack([pad(1 / s_c**2), pad(1 / s_f**2), pad(s_f), pad(g.dz_c), pad(g.dz_f), pad(s_c**2 * g.dz_c), pad(1 / (s_c**2 * g.dz_c)),
+                   pad(1 / g.dz_f**2), pad(phic), pad(dphif), pad(o.beta_rayleigh(g.z_f, P.alpha_rayleigh_w)),
+                   pad(o.beta_rayleigh(g.z_c, P.alpha_rayleigh_uh)), pad(o.beta_viscous(g.z_c)), pad(o.beta_viscous(g.z_f))])
+    hgeo = _full_hgeo(g, P, True)
+    A = g.dxdxi.reshape(nh, 16, 2, 2)
+    dA = A[..., 0, 0] * A[..., 1, 1] - A[..., 0, 1] * A[..., 1, 0]
+    hgeo[:, HG_DSSW] = o.dss_w.reshape(nh, 16)
+    hgeo[:, HG_A00], hgeo[:, HG_A00 + 1], hgeo[:, HG_A00 + 2], hgeo[:, HG_A00 + 3] = A[..., 0, 0], A[..., 0, 1], A[..., 1, 0], A[..., 1, 1]
+    hgeo[:, HG_AI00], hgeo[:, HG_AI00 + 1] = A[..., 1, 1] / dA, -A[..., 0, 1] / dA
+    hgeo[:, HG_AI00 + 2], hgeo[:, HG_AI00 + 3] = -A[..., 1, 0] / dA, A[..., 0, 0] / dA
+    sc_exp = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, dt, float(o.nu4_vort), float(o.nu4_scalar),
+                       N.divergence_damping_factor, 1, 1.0, 1.0, 3, 4, 3])
+    Dm, wq = np.ascontiguousarray(g.D, dtype=np.float64), np.ascontiguousarray(g.wq, dtype=np.float64)
+    offs, mem = G.dss_node_csr(g.topology, 4)
+    off = np.ascontiguousarray(offs, dtype=np.int32)
+    m32 = np.ascontiguousarray(mem[:, 0] * 16 + mem[:, 2] * 4 + mem[:, 1], dtype=np.int32)
+    nn = len(off) - 1
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def t_exp(Uc, Uf):
+        Tc, Tf, H = np.zeros_like(Uc), np.zeros_like(Uf), np.zeros_like(Uc)
+        assert emux.emu_exp5(0, nh, nv, p(sc_exp), p(vl), p(Dm), p(wq), p(hgeo), p(Uc), p(Uf), p(Tc), p(Tf), p(H), None) == 0
+        assert emud.emu_dss_h(nh, nv, 4, nn, p(off), p(m32), p(hgeo), p(H)) == 0
+        assert emux.emu_exp5(1, nh, nv, p(sc_exp), p(vl), p(Dm), p(wq), p(hgeo), p(Uc), p(Uf), p(Tc), p(Tf), p(H), None) == 0
+        return Tc, Tf
+
+    def axpy_dss(base, terms, coefs, dmask):
+        n = len(terms)
+        Tc = (C.c_void_p * n)(*[t[0].ctypes.data for t in terms])
+        Tf = (C.c_void_p * n)(*[t[1].ctypes.data for t in terms])
+        cf = np.array(coefs, dtype=np.float64)
+        oc, of = np.empty_like(base[0]), np.empty_like(base[1])
+        assert emud.emu_axpy_dss_n(n, nh, nv, ncf, nn, p(off), p(m32), p(hgeo), p(base[0]), p(base[1]), Tc, Tf, p(cf), C.c_uint(dmask), p(oc), p(of)) == 0
+        return oc, of
+
+    def imp_stage(U, dtg):
+        sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, dt, 1.0, dtg, 3, ncf])
+        Nc, Nf = np.zeros_like(U[0]), np.zeros_like(U[1])
+        assert emu5.emu_imp5(nh, nv, p(sc), p(vl[:11]), p(hgeo), p(U[0]), p(U[1]), p(Nc), p(Nf)) == 0
+        assert emud.emu_dss_state(nh, nv, nn, p(off), p(m32), p(hgeo), p(Nc), p(Nf)) == 0
+        return Nc, Nf
+
+    ae, ai, be, bi, gam = prm.ars343()
+    # stage-solution coefficients (capi.cu: impl_step, zform)
+    al, bt = np.zeros((4, 4)), np.zeros((4, 4))
+    for i in range(1, 4):
+        for j in range(i):
+            bt[i, j] = ae[i][j]
+        for j in range(1, i):
+            if ai[i][j] == 0:
+                continue
+            w = ai[i][j] / ai[j][j]
+            al[i, j] += w
+            for k in range(j):
+                al[i, k] -= w * al[j, k]
+                bt[i, k] -= w * bt[j, k]
+    u = (Yc, Yf)
+    Ns, Te = [None] * 4, [None] * 4
+    Te[0] = t_exp(*u)
+    for i in range(1, 4):
+        terms, coefs, dmask = [], [], 0
+        for j in range(1, i):
+            if al[i, j] != 0:
+                dmask |= 1 << len(terms)
+                terms.append(Ns[j])
+                coefs.append(al[i, j])
+        for j in range(i):
+            if bt[i, j] != 0:
+                terms.append(Te[j])
+                coefs.append(dt * bt[i, j])
+        U = axpy_dss(u, terms, coefs, dmask)
+        Ns[i] = imp_stage(U, dt * ai[i][i])
+        Te[i] = t_exp(*Ns[i])
+    terms = [Te[j] for j in range(4) if be[j] - ae[3][j] != 0]
+    coefs = [dt * (be[j] - ae[3][j]) for j in range(4) if be[j] - ae[3][j] != 0]
+    new_c, new_f = axpy_dss(Ns[3], terms, coefs, 0)
+    oc, of = o.step(Yc.copy(), Yf.copy())
+    for k in range(4):
+        assert rel(new_c[:, k], oc[:, k]) < 1e-11, (k, rel(new_c[:, k], oc[:, k]))
+    assert rel(new_f, of) < 1e-9, rel(new_f, of)
+    assert rel(new_c - Yc, oc - Yc) < 1e-7  # the step increment itself, not only the state
