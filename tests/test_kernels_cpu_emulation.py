@@ -724,16 +724,19 @@ def test_emulated_t_exp_composite_matches_oracle(emux, emud, deep, sponge, he, z
     assert rel(Ytf, tf) < 1e-9
 
 
-def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5):
+@pytest.mark.parametrize("vdiff", [None, "explicit", "implicit"])
+def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5, emu, vdiff):
     """One ARS343 step assembled from the emulated PRODUCT kernels in the data flow of the fused stepper (capi.cu: impl_step, fused path):
     stage-solution form of the increments (U_i = u + Σ α_ij (N_j − u) + dt Σ β_ij T_exp[j], k_axpy_dss with dmask), k5_imp_stage → k_dss2,
     T_exp = k5_exp_a → k_dss2(∇²) → k5_exp_c, and the stiffly-accurate final increment from N₄ — against the oracle's LITERAL step
     (u + dt Σ bⱼ (T_exp[j] + T_imp[j]) with T_imp formed explicitly).  The host orchestration below restates impl_step's coefficient
-    recursion; the arithmetic on the fields is all done by the kernels' own source."""
+    recursion; the arithmetic on the fields is all done by the kernels' own source.  With vertical diffusion: explicit → k_vdiff_tend2
+    after k5_exp_c; implicit → k_imp_stage_diff in place of k5_imp_stage (the B200_VDIFF_FUSED=1 data flow)."""
     HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
-    P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
+    P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0, D_0_diffusion=40.0, H_diffusion=6000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=8, z_max=30000.0, dz_bottom=500.0, radius=P.planet_radius)
-    N = prm.DycoreNumerics(dt=300.0, rayleigh_sponge=True, viscous_sponge=True)
+    N = prm.DycoreNumerics(dt=300.0, rayleigh_sponge=True, viscous_sponge=True, vert_diff="VerticalDiffusion" if vdiff else None,
+                           implicit_diffusion=(vdiff == "implicit"), approximate_linear_solve_iters=2)
     o = Oracle(g, P, N, np.float64)
     Yc, Yf = setups.dry_baroclinic_wave(g, P)
     Yc, Yf = np.ascontiguousarray(Yc), np.ascontiguousarray(Yf)
@@ -768,7 +771,16 @@ def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5):
         assert emux.emu_exp5(0, nh, nv, p(sc_exp), p(vl), p(Dm), p(wq), p(hgeo), p(Uc), p(Uf), p(Tc), p(Tf), p(H), None) == 0
         assert emud.emu_dss_h(nh, nv, 4, nn, p(off), p(m32), p(hgeo), p(H)) == 0
         assert emux.emu_exp5(1, nh, nv, p(sc_exp), p(vl), p(Dm), p(wq), p(hgeo), p(Uc), p(Uf), p(Tc), p(Tf), p(H), None) == 0
+        if vdiff == "explicit":  # k_vdiff_tend2 accumulates into Yₜ.c (the solver part of emu_vdiff is not used here)
+            z = lambda a: np.zeros_like(a)
+            jac, jacd = np.zeros((nh, 15, 16, nv + 1)), np.zeros((nh, 2, 16, nv + 1))
+            assert emu.emu_vdiff(nh, nv, ncf, p(sc_vd), p(vl[:11]), p(hgeo), p(kdec), p(Uc), p(Uf), p(z(Uc)), p(z(Uf)), p(Tc), p(jac), p(jacd),
+                                 p(z(Uc)), p(z(Uf))) == 0
         return Tc, Tf
+
+    kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
+    sc_vd = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, dt, 1.0, 1, 1, 2, P.C_E * g.dz_c[0] / 2,
+                      1.0, 2, 3, 1])
 
     def axpy_dss(base, terms, coefs, dmask):
         n = len(terms)
@@ -782,7 +794,12 @@ def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5):
     def imp_stage(U, dtg):
         sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, dt, 1.0, dtg, 3, ncf])
         Nc, Nf = np.zeros_like(U[0]), np.zeros_like(U[1])
-        assert emu5.emu_imp5(nh, nv, p(sc), p(vl[:11]), p(hgeo), p(U[0]), p(U[1]), p(Nc), p(Nf)) == 0
+        if vdiff == "implicit":
+            scd = sc_vd.copy()
+            scd[14] = dtg
+            assert emu.emu_stage_diff(nh, nv, ncf, p(scd), p(vl[:11]), p(hgeo), p(kdec), p(U[0]), p(U[1]), p(Nc), p(Nf)) == 0
+        else:
+            assert emu5.emu_imp5(nh, nv, p(sc), p(vl[:11]), p(hgeo), p(U[0]), p(U[1]), p(Nc), p(Nf)) == 0
         assert emud.emu_dss_state(nh, nv, nn, p(off), p(m32), p(hgeo), p(Nc), p(Nf)) == 0
         return Nc, Nf
 
