@@ -14,6 +14,7 @@ std::barrier<>* g_cta_barrier = nullptr;
 namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
 
 #include "kernels_vdiff.cuh"
+#include "kernels_limiter.cuh"
 
 using namespace b200;
 #ifndef EMU_FT
@@ -144,5 +145,23 @@ extern "C" __attribute__((visibility("default"))) int emu_stage_diff(int nh, int
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
   run_grid(nh * 4, [&] { k_imp_stage_diff<FT>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[14]); });
+  return 0;
+}
+
+// lim!, first branch: k_lim_bounds then k_lim_apply (kernels_limiter.cuh; no barriers — the threads are simply run one after the other).
+// nbr_off/nbr: vertex neighbours of every element (CSR); hgeo with HG_WJ filled; bounds from ref_c, limiter applied to Yc in place.
+extern "C" __attribute__((visibility("default"))) int emu_sem_limiter(int nh, int nv, int ncf, const int* nbr_off, const int* nbr,
+                                                                      const FT* hgeo, const FT* ref_c, FT* Yc) {
+  const int ntr = ncf - 4;
+  std::vector<FT> bnd((size_t)ntr * nh * 2 * LV, FT(0));
+  for (int pass = 0; pass < 2; ++pass)
+    for (int t = 0; t < ntr; ++t)
+      for (int e = 0; e < nh; ++e)
+        for (int v = 0; v < 64; ++v) {
+          threadIdx = {(unsigned)v, 0, 0};
+          blockIdx = {(unsigned)e, (unsigned)t, 0};
+          if (pass == 0) k_lim_bounds<FT>(ref_c, ncf, nv, nh, bnd.data(), (FT*)nullptr, ntr);
+          else k_lim_apply<FT>(Yc, ncf, nv, nh, bnd.data(), nbr_off, nbr, hgeo, (const FT*)nullptr, 0ll, (const int*)nullptr, (const int*)nullptr, ntr);
+        }
   return 0;
 }

@@ -842,3 +842,37 @@ def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5, emu, vdiff):
         assert rel(new_c[:, k], oc[:, k]) < 1e-11, (k, rel(new_c[:, k], oc[:, k]))
     assert rel(new_f, of) < 1e-9, rel(new_f, of)
     assert rel(new_c - Yc, oc - Yc) < 1e-7  # the step increment itself, not only the state
+
+
+def test_emulated_sem_quasimonotone_limiter_matches_oracle(emu):
+    """k_lim_bounds / k_lim_apply (lim!, apply_sem_quasimonotone_limiter) on the CPU emulator against the oracle's restatement of
+    Limiters.QuasiMonotoneLimiter: bounds from the reference state widened over the vertex neighbours, clip-and-redistribute per slab."""
+    HG_WJ = 22
+    P = prm.DycoreParams()
+    g = G.make_sphere_grid(FT=np.float64, h_elem=3, z_elem=7, z_max=30000.0, dz_bottom=500.0, radius=P.planet_radius)
+    N = prm.DycoreNumerics(dt=100.0, apply_sem_quasimonotone_limiter=True)
+    o = Oracle(g, P, N, np.float64)
+    Yc, _ = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(43)
+    rho = Yc[:, 0]
+    ref = np.ascontiguousarray(np.concatenate([Yc, (rho * (0.5 + 0.3 * rng.random(rho.shape)))[:, None], (rho * 1e-2 * rng.random(rho.shape))[:, None]], axis=1))
+    Y = ref.copy()
+    Y[:, 4] = rho * (0.5 + 0.6 * (rng.random(rho.shape) - 0.3))  # over- and undershoots relative to the reference bounds
+    Y[:, 5] = rho * 1e-2 * (rng.random(rho.shape) * 1.5 - 0.2)
+    Y = np.ascontiguousarray(Y)
+    nh, nv, ncf = Y.shape[0], g.nv, Y.shape[1]
+    nbrs = o.neighboring_elements()
+    nbr_off = np.zeros(nh + 1, dtype=np.int32)
+    nbr_off[1:] = np.cumsum([len(x) for x in nbrs])
+    nbr = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.int32) for x in nbrs]))
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_WJ] = (g.W * g.J2).reshape(nh, 16)
+    got = Y.copy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emu.emu_sem_limiter(nh, nv, ncf, p(nbr_off), p(nbr), p(hgeo), p(ref), p(got)) == 0
+    want = Y.copy()
+    o.limiters_func(want, ref)
+    assert np.abs(want[:, 4:] - Y[:, 4:]).max() > 0
+    assert np.array_equal(got[:, :4], Y[:, :4])
+    for q in (4, 5):
+        assert rel(got[:, q], want[:, q]) < 1e-13, (q, rel(got[:, q], want[:, q]))
