@@ -189,3 +189,28 @@ extern "C" __attribute__((visibility("default"))) int emu_axpy_dss_n(int n, int 
   }
   return 0;
 }
+
+// The generic k_dss (one item per blockIdx.y, CSR + hgeo instead of node records): the fallback of impl_dss for states with more than two
+// tracers.  State items: ρ, (uₕ₁,uₕ₂), ρe_tot, ρχ₁…, u₃.  No barriers: the threads are run one after the other.
+extern "C" __attribute__((visibility("default"))) int emu_dss_generic(int nh, int nv, int ncf, int nnodes, const int* off, const int* mem,
+                                                                      const double* hgeo, double* Yc, double* Yf) {
+  DssArgs A;
+  memset(&A, 0, sizeof(A));
+  const int cs = 16 * nv, es = ncf * cs;
+  int n = 0;
+  A.it[n++] = DssItem{Yc, nullptr, nullptr, nullptr, nv, es, 0};
+  A.it[n++] = DssItem{Yc + cs, Yc + 2 * cs, nullptr, nullptr, nv, es, 0};
+  for (int q = 3; q < ncf; ++q) A.it[n++] = DssItem{Yc + q * cs, nullptr, nullptr, nullptr, nv, es, 0};
+  A.it[n++] = DssItem{Yf, nullptr, nullptr, nullptr, nv + 1, 16 * (nv + 1), 0};
+  A.n = n;
+  if (n > DSS_MAX_ITEMS) return -1;
+  const int nblocks = (nnodes + 3) / 4;
+  for (int k = 0; k < n; ++k)
+    for (int b = 0; b < nblocks; ++b)
+      for (int t = 0; t < 256; ++t) {
+        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
+        blockIdx = {(unsigned)b, (unsigned)k, 0};
+        k_dss<FT>(A, off, mem, hgeo, nnodes, nh);
+      }
+  return 0;
+}

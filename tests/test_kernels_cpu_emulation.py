@@ -876,3 +876,37 @@ def test_emulated_sem_quasimonotone_limiter_matches_oracle(emu):
     assert np.array_equal(got[:, :4], Y[:, :4])
     for q in (4, 5):
         assert rel(got[:, q], want[:, q]) < 1e-13, (q, rel(got[:, q], want[:, q]))
+
+
+@pytest.mark.parametrize("ntr", [3, 4])
+def test_emulated_generic_dss_matches_oracle(emud, ntr):
+    """The generic k_dss — impl_dss falls back to it for states with more than two tracers (n_tracers = 3, 4: 7 and 8 DSS items) — on the CPU
+    emulator against the oracle's dss! of the state and a scalar weighted DSS of each tracer."""
+    HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
+    P = prm.DycoreParams()
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=6, z_max=30000.0, dz_bottom=500.0, radius=P.planet_radius)
+    o = Oracle(g, P, prm.DycoreNumerics(), np.float64)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    rng = np.random.default_rng(47)
+    Yc = np.concatenate([Yc] + [Yc[:, :1] * 1e-2 * (k + 1) * rng.random(Yc[:, :1].shape) for k in range(ntr)], axis=1)
+    Yc = np.ascontiguousarray(Yc * (1 + 1e-2 * rng.standard_normal(Yc.shape)))
+    Yf = np.ascontiguousarray(0.3 * g.dz_f * rng.standard_normal(Yf.shape))
+    nh, nv, ncf = Yc.shape[0], g.nv, Yc.shape[1]
+    offs, mem = G.dss_node_csr(g.topology, 4)
+    off = np.ascontiguousarray(offs, dtype=np.int32)
+    m32 = np.ascontiguousarray(mem[:, 0] * 16 + mem[:, 2] * 4 + mem[:, 1], dtype=np.int32)
+    A = g.dxdxi.reshape(nh, 16, 2, 2)
+    dA = A[..., 0, 0] * A[..., 1, 1] - A[..., 0, 1] * A[..., 1, 0]
+    hgeo = np.zeros((nh, HG_N, 16))
+    hgeo[:, HG_DSSW] = o.dss_w.reshape(nh, 16)
+    hgeo[:, HG_A00], hgeo[:, HG_A00 + 1], hgeo[:, HG_A00 + 2], hgeo[:, HG_A00 + 3] = A[..., 0, 0], A[..., 0, 1], A[..., 1, 0], A[..., 1, 1]
+    hgeo[:, HG_AI00], hgeo[:, HG_AI00 + 1] = A[..., 1, 1] / dA, -A[..., 0, 1] / dA
+    hgeo[:, HG_AI00 + 2], hgeo[:, HG_AI00 + 3] = -A[..., 1, 0] / dA, A[..., 0, 0] / dA
+    gc, gf = Yc.copy(), Yf.copy()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emud.emu_dss_generic(nh, nv, ncf, len(off) - 1, p(off), p(m32), p(hgeo), p(gc), p(gf)) == 0
+    oc, of = Yc.copy(), Yf.copy()
+    o.dss_state(oc, of)
+    for k in range(ncf):
+        assert rel(gc[:, k], oc[:, k]) < 1e-14, (k, rel(gc[:, k], oc[:, k]))
+    assert rel(gf, of) < 1e-14
