@@ -11,6 +11,14 @@
 //                  alg₂ = BlockLowerTriangularSolve(uₕ), P_alg₁ = MainDiagonalPreconditioner(), n_iters)
 //                  (manual_sparse_jacobian.jl:538-578; ClimaCore MatrixFields field_matrix_solver.jl [UPSTREAM-RECALL])
 //
+// Index of this file (status: [B200] = parity-green on a B200, [emu] = matched against the oracle in the CPU CTA emulator only, opt-in):
+//   k_vdiff_tend [B200], k_vdiff_tend2 [B200, default]      diffusion tendency (element slabs / quarter element, no slabs)
+//   k_vdiff_jac [B200, default], k_vdiff_jac2 [emu]         diffusion Jacobian planes                       (B200_LDIV_DIFF=2 selects *2)
+//   k_ldiv_diff [B200, default], k_ldiv_diff2 [emu]         approximate arrowhead solve, Thomas / PCR (pcr_slab)
+//   k_imp_stage_diff [emu]                                  fused implicit stage with implicit diffusion    (B200_VDIFF_FUSED=1)
+//   k_lim_vborrow [emu]                                     lim!: vertical mass-borrowing limiter           (off unless configured)
+//   k_t_imp2, k_wfact2, k_t_post_imp2, k_ldiv2 [emu]        second generation of the dry hook kernels      (B200_HOOK_KERNELS=2)
+//
 // Eddy diffusivity (src/cache/eddy_diffusivity_coefficient.jl:16-42, src/cache/precomputed_quantities.jl:652-676): K_u = K_h;
 // DecayWithHeightDiffusion K = D₀ exp(−(z − z_sfc)/H) (host table per level), VerticalDiffusion K = C_E |uₕ(level 1)| Δz₁/2 below
 // 850 hPa, Gaussian taper in pressure above.  Face value: harmonic mean ᶠinterp(ρ)/ᶠinterp(1/max(K, ε)).
