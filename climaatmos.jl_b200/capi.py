@@ -92,6 +92,7 @@ def load():
         raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback)")
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     lib.b200_last_error.restype = C.c_char_p
+    lib.b200_last_error.argtypes = [C.c_void_p]
     lib.b200_launch_count.restype = C.c_int64
     lib.b200_launch_count.argtypes = [C.c_void_p]
     vp, dbl, i32 = C.c_void_p, C.c_double, C.c_int32
@@ -118,9 +119,10 @@ def load():
     return lib
 
 
-def check(status: int, what: str):
+def check(status: int, what: str, ctx=None):
+    """Raise on a non-zero status with the message of `ctx` (per-context, include/b200_dycore.h) or of the calling thread."""
     if status != 0:
-        raise RuntimeError(f"{what} failed: {load().b200_last_error().decode()}")
+        raise RuntimeError(f"{what} failed: {load().b200_last_error(ctx).decode()}")
 
 
 def _ptr(a: np.ndarray):
@@ -227,7 +229,7 @@ def setup_peer_halo(ctx, part, comms):
     rc = lib.b200_halo_import(ctx, C.cast(hb, C.c_void_p), _ptr(their_off), _ptr(their_nhg))
     ok = comms.all_true(rc == 0)
     if not ok and comms.rank == 0:
-        print("warning: peer-memory halo unavailable (" + lib.b200_last_error().decode() + "); using NCCL send/recv")
+        print("warning: peer-memory halo unavailable (" + lib.b200_last_error(ctx).decode() + "); using NCCL send/recv")
     return ok
 
 

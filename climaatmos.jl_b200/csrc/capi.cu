@@ -14,9 +14,7 @@
 
 #include "../../include/b200_dycore.h"
 #include "kernels_dss.cuh"
-#include "kernels_explicit.cuh"
 #include "kernels_implicit.cuh"
-#include "kernels_reg.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_imp5.cuh"
@@ -26,7 +24,18 @@
 using namespace b200;
 
 static thread_local std::string g_err;
-static int fail(const std::string& m) { g_err = m; return -1; }
+static thread_local b200_ctx* g_cur = nullptr;  // context of the entry point being executed on this thread
+static void ctx_set_err(b200_ctx* c, const std::string& m);
+static int fail(const std::string& m) {
+  g_err = m;
+  if (g_cur) ctx_set_err(g_cur, m);
+  return -1;
+}
+struct CtxScope {
+  b200_ctx* prev;
+  explicit CtxScope(b200_ctx* c) : prev(g_cur) { g_cur = c; }
+  ~CtxScope() { g_cur = prev; }
+};
 #define CK(x)                                                                          \
   do {                                                                                 \
     cudaError_t e_ = (x);                                                              \
@@ -77,6 +86,7 @@ static int nccl_load() {
   } while (0)
 
 struct b200_ctx {
+  std::string err;  // message of the last failing call on this context (b200_last_error)
   b200_dims dims;
   b200_params prm;
   int ft = 4;
@@ -136,25 +146,16 @@ struct b200_ctx {
   int eager_steps = 0;
   cudaStream_t side = nullptr;           // side stream: T_imp = (U − temp)/dtγ runs concurrently with the T_exp kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int exp_kernel = 5;  // B200_EXP_KERNEL=2|5: scalar row kernels (k2_*) or packed FFMA2 row kernels (k5_*)
-  int imp_kernel = 5;  // B200_IMP_KERNEL=5|2|3|4: fused implicit-stage kernel (5: packed row layout; 2, 3, 4 kept as A/B evidence)
-  int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (A/B and test coverage)
-  int imp_minb = 2;    // B200_IMP_MINB=2|3|4: CTAs/SM the nv=63 k5_imp_stage is compiled for (126 regs no spills, 80, 64; measured 127/149/181 µs)
-  int imp_solver = 2;  // B200_IMP_SOLVER=2|1|0: k5_imp_stage column solver (parallel cyclic reduction, two-sided Thomas, one-sided Thomas)
-  int vdiff_fused = 0;   // B200_VDIFF_FUSED=1: fused implicit stage with implicit vertical diffusion (k_imp_stage_diff; matches the oracle in the CPU CTA
-                         // emulator, not yet run on a B200) in b200_implicit_stage and the fused stepper instead of the hook sequence
-  int hook_kernels = 1;  // B200_HOOK_KERNELS=1|2: first-generation hook kernels (element slabs; validated on B200) or k_t_imp2 / k_wfact2 / k_ldiv2 /
-                         // k_t_post_imp2 (quarter element per CTA, PCR; equal to generation 1 in the CPU CTA emulator, not yet run on a B200)
-  int ldiv_diff = 1;     // B200_LDIV_DIFF=1|2: k_vdiff_jac + k_ldiv_diff (Thomas sweeps by 16 lanes; validated on B200) or k_vdiff_jac2 + k_ldiv_diff2 (no slabs / parallel cyclic reduction;
-                         // matches the oracle in the CPU CTA emulator, not yet run on a B200)
-  int vdiff_kernel = 2;  // B200_VDIFF_KERNEL=2|1: k_vdiff_tend2 (quarter element per CTA, no state slabs; 77 µs at he30) or k_vdiff_tend (element slabs, 267 µs)
-  int legacy = 0;  // B200_LEGACY_KERNELS=1: shared-memory-staged first-generation kernels (A/B comparisons)
+  int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (test coverage of the run-time-nv builds)
   int ncf() const { return 4 + dims.n_tracers; }
   size_t nc() const { return (size_t)dims.nh * ncf() * 16 * dims.nv; }
   size_t nf() const { return (size_t)dims.nh * 16 * (dims.nv + 1); }
 };
 
-extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+// Error text: per context — every entry point that takes a context opens a CtxScope, so fail() records the message in
+// that context; ctx == NULL returns the calling thread's last message (b200_create failures, host-only helpers).
+extern "C" const char* b200_last_error(const b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+static void ctx_set_err(b200_ctx* c, const std::string& m) { c->err = m; }
 
 extern "C" int b200_nccl_unique_id(void* out128) {
   if (nccl_load()) return -1;
@@ -218,6 +219,7 @@ extern "C" int b200_build_dss_csr(const b200_topology* T, int32_t* off_out, int3
 }
 
 extern "C" int b200_debug_dss_csr(b200_ctx* c, const int32_t** off, const int32_t** mem, int32_t* nnodes, int32_t* nmem) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_debug_dss_csr: null context");
   *off = c->h_off.data(); *mem = c->h_mem.data();
   *nnodes = c->nnodes; *nmem = (int32_t)c->h_mem.size();
@@ -418,77 +420,32 @@ template <class FT> static size_t smem_rowq(int n) { return (HG_ELEM * 16 + (siz
 
 template <class FT>
 static int set_attrs() {
-  CK(cudaFuncSetAttribute(k2_exp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(9)));
-  CK(cudaFuncSetAttribute(k2_exp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(2)));
   CK(cudaFuncSetAttribute(k5_exp_a<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
   CK(cudaFuncSetAttribute(k5_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
   CK(cudaFuncSetAttribute(k5_exp_a<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
   CK(cudaFuncSetAttribute(k5_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
-  CK(cudaFuncSetAttribute(k2_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(11)));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 1, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 1, 63, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 2, 63, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
-  CK(cudaFuncSetAttribute(k_t_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
-  CK(cudaFuncSetAttribute(k_wfact<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(12)));
-  CK(cudaFuncSetAttribute(k_ldiv<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * SLAB * sizeof(FT))));
-  CK(cudaFuncSetAttribute(k_t_post_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
-  CK(cudaFuncSetAttribute(k_imp_stage<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(18)));
   CK(cudaFuncSetAttribute(k_lim_vborrow<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SLAB * sizeof(FT))));
-  CK(cudaFuncSetAttribute(k_vdiff_tend<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_imp_stage_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_PROFILES * 4 * LVP * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_ldiv2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(11 * SLAB * sizeof(FT))));
-  CK(cudaFuncSetAttribute(k_ldiv_diff2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((24 * SLAB + LV) * sizeof(FT))));
-  CK(cudaFuncSetAttribute(k_texp_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(22)));
-  CK(cudaFuncSetAttribute(k_texp_c<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(13)));
   return 0;
 }
 
-extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geometry* G, const b200_topology* T,
-                           const b200_params* p, const void* nccl_id, int rank, int nranks) {
-  if (!out || !d || !G || !T || !p) return fail("b200_create: null argument");
-  if (d->nq != 4) return fail("b200_create: only Nq = 4 (nh_poly = 3) is supported");
-  if (d->nv + 1 > LV || d->nv < 2) return fail("b200_create: need 2 <= nv <= 63");
-  if (d->ft_bytes != 4 && d->ft_bytes != 8) return fail("b200_create: ft_bytes must be 4 or 8");
-  if (d->n_tracers < 0 || d->n_tracers > 4) return fail("b200_create: 0 <= n_tracers <= 4");
-  for (int u : {p->energy_upwinding, p->tracer_upwinding})
-    if (u != 0 && u != 1 && u != 3)
-      return fail("b200_create: upwinding must be 0 (none), 1 (first_order) or 3 (vanleer_limiter); third_order (2) is not built");
-  if (p->vert_diff < 0 || p->vert_diff > 2) return fail("b200_create: vert_diff must be 0 (none), 1 (VerticalDiffusion) or 2 (DecayWithHeightDiffusion)");
-  if (p->implicit_diffusion && !p->vert_diff)
-    return fail("b200_create: implicit_diffusion needs a vert_diff model (the reference's update_diffusion_jacobian! has no diffusivity otherwise)");
-  if (p->vert_diff && p->approximate_linear_solve_iters < 0) return fail("b200_create: approximate_linear_solve_iters < 0");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail("b200_create: no CUDA device (this library has no CPU fallback)");
-  b200_ctx* c = new b200_ctx();
+extern "C" int b200_destroy(b200_ctx* c);
+static int create_body(b200_ctx* c, const b200_dims* d, const b200_geometry* G, const b200_topology* T, const b200_params* p,
+                       const void* nccl_id, int rank, int nranks) {
   c->dims = *d; c->prm = *p; c->ft = d->ft_bytes; c->rank = rank; c->nranks = nranks;
-  if (const char* e = getenv("B200_LEGACY_KERNELS")) c->legacy = atoi(e);
-  if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
-  if (const char* e = getenv("B200_IMP_SOLVER")) c->imp_solver = atoi(e);
   if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
   if (const char* e = getenv("B200_PDL")) c->pdl = atoi(e);
   if (const char* e = getenv("B200_STIFF_FINAL")) c->stiff_final = atoi(e);
   if (const char* e = getenv("B200_ZFORM")) c->zform = atoi(e);
   if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
-  if (const char* e = getenv("B200_IMP_MINB")) c->imp_minb = atoi(e);
-  if (const char* e = getenv("B200_EXP_KERNEL")) c->exp_kernel = atoi(e);
-  if (const char* e = getenv("B200_VDIFF_KERNEL")) c->vdiff_kernel = atoi(e);
-  if (const char* e = getenv("B200_LDIV_DIFF")) c->ldiv_diff = atoi(e);
-  if (const char* e = getenv("B200_HOOK_KERNELS")) c->hook_kernels = atoi(e);
-  if (const char* e = getenv("B200_VDIFF_FUSED")) c->vdiff_fused = atoi(e);
-  if (d->n_tracers > 0 && (c->legacy || (c->imp_kernel != 2 && c->imp_kernel != 5))) {
-    delete c;
-    return fail("b200_create: passive tracers need the current kernels (unset B200_LEGACY_KERNELS / B200_IMP_KERNEL)");
-  }
   build_csr(T, c->h_off, c->h_mem);
   {  // Topologies.local_neighboring_elements: elements sharing a vertex, from the vertex tables (limiter bounds)
     const int nh = d->nh;
@@ -507,9 +464,9 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
       off[e + 1] = (int32_t)lst.size();
     }
     if (cudaMalloc(&c->d_lim_nbr_off, off.size() * sizeof(int32_t)) != cudaSuccess ||
-        cudaMalloc(&c->d_lim_nbr, std::max<size_t>(1, lst.size()) * sizeof(int32_t)) != cudaSuccess) { delete c; return fail("b200_create: cudaMalloc (limiter tables)"); }
-    cudaMemcpy(c->d_lim_nbr_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-    cudaMemcpy(c->d_lim_nbr, lst.data(), lst.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+        cudaMalloc(&c->d_lim_nbr, std::max<size_t>(1, lst.size()) * sizeof(int32_t)) != cudaSuccess) return fail("b200_create: cudaMalloc (limiter tables)");
+    CK(cudaMemcpy(c->d_lim_nbr_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_lim_nbr, lst.data(), lst.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   c->nnodes = (int)c->h_off.size() - 1;
   // keep only nodes with at least one local member
@@ -526,19 +483,19 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
     c->nnodes = (int)c->h_off.size() - 1;
   }
   for (int n = 0; n < c->nnodes; ++n)
-    if (c->h_off[n + 1] - c->h_off[n] > 4) { delete c; return fail("b200_create: node shared by more than 4 elements"); }
+    if (c->h_off[n + 1] - c->h_off[n] > 4) return fail("b200_create: node shared by more than 4 elements");
   CK(cudaMalloc(&c->d_off, c->h_off.size() * sizeof(int)));
   CK(cudaMalloc(&c->d_mem, std::max<size_t>(1, c->h_mem.size()) * sizeof(int)));
   CK(cudaMemcpy(c->d_off, c->h_off.data(), c->h_off.size() * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_mem, c->h_mem.data(), c->h_mem.size() * sizeof(int), cudaMemcpyHostToDevice));
   int r = (c->ft == 4) ? create_geo<float>(c, G, p) : create_geo<double>(c, G, p);
-  if (r) { delete c; return r; }
+  if (r) return r;
   r = (c->ft == 4) ? set_attrs<float>() : set_attrs<double>();
-  if (r) { delete c; return r; }
+  if (r) return r;
   // halo plan
   if (nranks > 1 && T->n_neighbors > 0) {
-    if (!nccl_id) { delete c; return fail("b200_create: nccl_unique_id required for nranks > 1"); }
-    if (nccl_load()) { delete c; return -1; }
+    if (!nccl_id) return fail("b200_create: nccl_unique_id required for nranks > 1");
+    if (nccl_load()) return -1;
     c->nbr.assign(T->neighbor_ranks, T->neighbor_ranks + T->n_neighbors);
     c->send_off.assign(T->send_offset, T->send_offset + T->n_neighbors + 1);
     c->recv_off.assign(T->recv_offset, T->recv_offset + T->n_neighbors + 1);
@@ -573,6 +530,35 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
     Id128 id;
     memcpy(&id, nccl_id, 128);
     NK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+  }
+  return 0;
+}
+
+
+extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geometry* G, const b200_topology* T,
+                           const b200_params* p, const void* nccl_id, int rank, int nranks) {
+  if (!out || !d || !G || !T || !p) return fail("b200_create: null argument");
+  if (d->nq != 4) return fail("b200_create: only Nq = 4 (nh_poly = 3) is supported");
+  if (d->nh <= 0 || d->nh_ghost < 0) return fail("b200_create: need nh > 0 and nh_ghost >= 0");
+  if (T->n_neighbors < 0 || T->n_neighbors > 32) return fail("b200_create: 0 <= n_neighbors <= 32 (neighbour bit mask)");
+  if (d->nv + 1 > LV || d->nv < 2) return fail("b200_create: need 2 <= nv <= 63");
+  if (d->ft_bytes != 4 && d->ft_bytes != 8) return fail("b200_create: ft_bytes must be 4 or 8");
+  if (d->n_tracers < 0 || d->n_tracers > 4) return fail("b200_create: 0 <= n_tracers <= 4");
+  for (int u : {p->energy_upwinding, p->tracer_upwinding})
+    if (u != 0 && u != 1 && u != 3)
+      return fail("b200_create: upwinding must be 0 (none), 1 (first_order) or 3 (vanleer_limiter); third_order (2) is not built");
+  if (p->vert_diff < 0 || p->vert_diff > 2) return fail("b200_create: vert_diff must be 0 (none), 1 (VerticalDiffusion) or 2 (DecayWithHeightDiffusion)");
+  if (p->implicit_diffusion && !p->vert_diff)
+    return fail("b200_create: implicit_diffusion needs a vert_diff model (the reference's update_diffusion_jacobian! has no diffusivity otherwise)");
+  if (p->vert_diff && p->approximate_linear_solve_iters < 0) return fail("b200_create: approximate_linear_solve_iters < 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("b200_create: no CUDA device (this library has no CPU fallback)");
+  b200_ctx* c = new b200_ctx();
+  const int rc = create_body(c, d, G, T, p, nccl_id, rank, nranks);
+  if (rc != 0) {  // one cleanup path: everything allocated so far is released by b200_destroy
+    b200_destroy(c);
+    return rc;
   }
   *out = c;
   return 0;
@@ -633,6 +619,7 @@ static int impl_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs*
   return 0;
 }
 extern "C" int b200_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs* o, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_cache_imp: null context");
   return c->ft == 4 ? impl_cache_imp<float>(c, Yc, Yf, o, (cudaStream_t)stream) : impl_cache_imp<double>(c, Yc, Yf, o, (cudaStream_t)stream);
 }
@@ -640,30 +627,24 @@ extern "C" int b200_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cachep
 // Yₜ.c += vertical_diffusion_boundary_layer_tendency!(Y)  (kernels_vdiff.cuh)
 template <class FT>
 static int launch_vdiff_tend(b200_ctx* c, void* Ytc, const void* Yc, const void* Yf, cudaStream_t s) {
-  if (c->vdiff_kernel == 2)  // quarter element per CTA, HBM-bound (bitwise identical to k_vdiff_tend)
-    k_vdiff_tend2<FT><<<c->dims.nh * 4, NT, VD2_ARR * 4 * VD2_ST * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-                                                                                 (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                                                 (const FT*)Yf, (FT*)Ytc);
-  else
-    k_vdiff_tend<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-                                                              (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT*)Ytc);
+  // quarter element per CTA, no state slabs (HBM-bound; the element-slab first generation took 267 µs against 77 µs)
+  k_vdiff_tend2<FT><<<c->dims.nh * 4, NT, VD2_ARR * 4 * VD2_ST * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                                               (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                                               (const FT*)Yf, (FT*)Ytc);
   LAUNCH_CHECK(c);
   return 0;
 }
 
 template <class FT>
 static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
-  if (c->hook_kernels == 2)
-    k_t_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
-  else
-    k_t_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                         (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  k_t_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
   if (vdiff_implicit(c)) return launch_vdiff_tend<FT>(c, Ytc, Yc, Yf, s);  // implicit_tendency.jl:69-78
   return 0;
 }
 extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_t_imp: null context");
   return c->ft == 4 ? impl_t_imp<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_imp<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
@@ -671,28 +652,20 @@ extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, con
 template <class FT>
 static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, cudaStream_t s) {
   if (!c->d_jac) CK(cudaMalloc(&c->d_jac, (size_t)c->dims.nh * JC_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
-  if (c->hook_kernels == 2)
-    k_wfact2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
-  else
-    k_wfact<FT><<<c->dims.nh, NT, smem_slabs<FT>(12), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                         (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
+  k_wfact2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                              (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
   LAUNCH_CHECK(c);
   if (vdiff_implicit(c)) {  // update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261)
     if (!c->d_jacd) CK(cudaMalloc(&c->d_jacd, (size_t)c->dims.nh * JD_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
-    if (c->ldiv_diff == 2)  // quarter element per CTA, no state slabs (same planes)
-      k_vdiff_jac2<FT><<<c->dims.nh * 4, NT, 2 * 4 * VD2_ST * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-                                                                            (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf,
-                                                                            (FT)dtg, (FT*)c->d_jacd);
-    else
-      k_vdiff_jac<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-                                                               (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT)dtg,
-                                                               (FT*)c->d_jacd);
+    k_vdiff_jac<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+                                                             (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT)dtg,
+                                                             (FT*)c->d_jacd);
     LAUNCH_CHECK(c);
   }
   return 0;
 }
 extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, double, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_wfact: null context");
   return c->ft == 4 ? impl_wfact<float>(c, Yc, Yf, dtg, (cudaStream_t)stream) : impl_wfact<double>(c, Yc, Yf, dtg, (cudaStream_t)stream);
 }
@@ -702,27 +675,20 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
   if (!c->d_jac) return fail("b200_ldiv: b200_wfact has not been called");
   if (vdiff_implicit(c)) {  // ApproximateBlockArrowheadIterativeSolve (manual_sparse_jacobian.jl:538-578)
     if (!c->d_jacd) return fail("b200_ldiv: b200_wfact has not been called");
-    if (c->ldiv_diff == 2)  // parallel cyclic reduction instead of 16-lane Thomas sweeps
-      k_ldiv_diff2<FT><<<c->dims.nh, NT, (24 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
-                                                                    (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
-                                                                    (const FT*)Rf, (FT*)dYc, (FT*)dYf);
-    else
-      k_ldiv_diff<FT><<<c->dims.nh, NT, (22 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
-                                                                   (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
-                                                                   (const FT*)Rf, (FT*)dYc, (FT*)dYf);
+    // 16-lane Thomas sweeps (a parallel-cyclic-reduction version measured slower on B200: 15.2 vs 10.5 ms/step, profiles/r2_opt_in_validation.md)
+    k_ldiv_diff<FT><<<c->dims.nh, NT, (22 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
+                                                                 (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
+                                                                 (const FT*)Rf, (FT*)dYc, (FT*)dYf);
     LAUNCH_CHECK(c);
     return 0;
   }
-  if (c->hook_kernels == 2)
-    k_ldiv2<FT><<<c->dims.nh, NT, 11 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
-                                                             (FT*)dYc, (FT*)dYf);
-  else
-    k_ldiv<FT><<<c->dims.nh, NT, 8 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
+  k_ldiv2<FT><<<c->dims.nh, NT, 11 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
                                                            (FT*)dYc, (FT*)dYf);
   LAUNCH_CHECK(c);
   return 0;
 }
 extern "C" int b200_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_ldiv: null context");
   return c->ft == 4 ? impl_ldiv<float>(c, dYc, dYf, Rc, Rf, (cudaStream_t)stream) : impl_ldiv<double>(c, dYc, dYf, Rc, Rf, (cudaStream_t)stream);
 }
@@ -734,16 +700,13 @@ static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const 
     CK(cudaMemsetAsync(Ytf, 0, c->nf() * sizeof(FT), s));
     return 0;
   }
-  if (c->hook_kernels == 2)
-    k_t_post_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                     (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
-  else
-    k_t_post_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  k_t_post_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                   (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
   return 0;
 }
 extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, double, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_t_post_imp: null context");
   return c->ft == 4 ? impl_t_post<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_post<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
@@ -752,6 +715,7 @@ extern "C" int b200_t_post_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc
 // Peer-memory halo set-up
 static size_t p2p_state_slab(const b200_ctx* c) { return (size_t)(c->ncf() * 16 * c->dims.nv + 16 * (c->dims.nv + 1)); }
 extern "C" int b200_halo_export(b200_ctx* c, void* handle64_out) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_halo_export: null context");
   if (c->nbr.empty()) return fail("b200_halo_export: context has no neighbours");
   if (!c->p2p_buf) {
@@ -767,6 +731,7 @@ extern "C" int b200_halo_export(b200_ctx* c, void* handle64_out) {
   return 0;
 }
 extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t* their_recv_offset, const int32_t* their_nh_ghost) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_halo_import: null context");
   if (!c->p2p_buf) return fail("b200_halo_import: call b200_halo_export first");
   const int nn = (int)c->nbr.size();
@@ -951,7 +916,7 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
   const bool special = (A.n == 4 && pairs == 0x2) || (A.n == 3 && pairs == 0x1) || (A.n == 5 && pairs == 0x2) || (A.n == 4 && pairs == 0x1) ||
                        (A.n == 6 && pairs == 0x2) || (A.n == 5 && pairs == 0x1) || (A.n == 1 && pairs == 0x0) || (A.n == 1 && pairs == 0x1) ||
                        (A.n == 2 && pairs == 0x0);
-  if (c->legacy || !small || !special) {
+  if (!small || !special) {
     if (p2p && (pack_alone() || wait_p2p())) return -1;
     grd.y = A.n;
     k_dss<FT><<<grd, blk, 0, s>>>(A, c->d_off, c->d_mem, (const FT*)c->d_hgeo, c->nnodes, nh);
@@ -978,6 +943,7 @@ static int impl_dss(b200_ctx* c, const DssField* F, int nfields, cudaStream_t s)
 }
 extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, const int32_t* is_face, const int32_t* kind,
                         int32_t nfields, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_dss: null context");
   if (nfields > 8) return fail("b200_dss: at most 8 fields per call");
   DssField F[8];
@@ -1013,6 +979,7 @@ static int impl_axpy(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void
 }
 extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, const void* uf, int32_t n, const void* const* Tc,
                            const void* const* Tf, const double* coef, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_axpy_n: null context");
   return c->ft == 4 ? impl_axpy<float>(c, Uc, Uf, uc, uf, n, Tc, Tf, coef, (cudaStream_t)stream)
                     : impl_axpy<double>(c, Uc, Uf, uc, uf, n, Tc, Tf, coef, (cudaStream_t)stream);
@@ -1024,20 +991,9 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
                             void* Ylc = nullptr) {
   const bool hd = c->prm.hyperdiff != 0;
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
-  if (c->legacy && c->prm.held_suarez) return fail("Held-Suarez forcing is only implemented in the current (row-layout) kernels");
-  if (phase == 0 && c->legacy) {
-    k_texp_a<FT><<<c->dims.nh, NT, smem_slabs<FT>(22), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                          (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
-    LAUNCH_CHECK(c);
-  } else if (phase == 0 && c->legacy == 2) {
-    k_exp_s<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                        (const FT*)Yf, (FT*)Ytc, hd ? (FT*)c->H : nullptr);
-    LAUNCH_CHECK(c);
-    k_exp_m<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                        (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
-    LAUNCH_CHECK(c);
-  } else if (phase == 0 && c->exp_kernel == 5) {
-    if (c->dims.nv == 63 && !c->generic_nv)
+  const bool nv63 = c->dims.nv == 63 && !c->generic_nv;
+  if (phase == 0) {
+    if (nv63)
       launchx(c->pdl & 1, k5_exp_a<FT, 63>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                              (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
     else
@@ -1050,19 +1006,11 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
           hd ? (FT*)c->H : nullptr);
       LAUNCH_CHECK(c);
     }
-  } else if (phase == 0) {
-    k2_exp_a<FT><<<c->dims.nh, CT, smem_row<FT>(9), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                       (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
-    LAUNCH_CHECK(c);
   } else if (phase == 1 && hd) {
     DssField F = {c->H, c->ncf(), 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d, ∇²χ…
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
-  } else if (phase == 2 && hd && c->legacy == 2) {
-    k_exp_c<FT><<<c->dims.nh, RT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                        (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
-    LAUNCH_CHECK(c);
-  } else if (phase == 2 && hd && !c->legacy && c->exp_kernel == 5) {
-    if (c->dims.nv == 63 && !c->generic_nv)
+  } else if (phase == 2 && hd) {
+    if (nv63)
       launchx(c->pdl & 2, k5_exp_c<FT, 63>, dim3(c->dims.nh, 3), CT, smem_rowq<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                       (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     else
@@ -1074,18 +1022,11 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
           make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)c->H, (FT*)(Ylc ? Ylc : Ytc));
       LAUNCH_CHECK(c);
     }
-  } else if (phase == 2 && hd && !c->legacy) {
-    k2_exp_c<FT><<<dim3(c->dims.nh, 3), CT, smem_row<FT>(2), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                       (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
-    LAUNCH_CHECK(c);
-  } else if (phase == 2 && hd) {
-    k_texp_c<FT><<<c->dims.nh, NT, smem_slabs<FT>(13), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                          (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
-    LAUNCH_CHECK(c);
   }
   return 0;
 }
 extern "C" int b200_t_exp_phase(b200_ctx* c, int32_t phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_t_exp_phase: null context");
   return c->ft == 4 ? impl_t_exp_phase<float>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream)
                     : impl_t_exp_phase<double>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
@@ -1095,7 +1036,6 @@ template <class FT>
 static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, cudaStream_t s) {
   if (Ylc) CK(cudaMemsetAsync(Ylc, 0, c->nc() * sizeof(FT), s));
   if (Ylf) CK(cudaMemsetAsync(Ylf, 0, c->nf() * sizeof(FT), s));
-  if (c->dims.n_tracers > 0 && c->exp_kernel != 5) return fail("passive tracers need B200_EXP_KERNEL=5 (default)");
   for (int ph = 0; ph < 3; ++ph)
     if (impl_t_exp_phase<FT>(c, ph, Ytc, Ytf, Yc, Yf, s, Ylc)) return -1;
   if (vdiff_explicit(c)) return launch_vdiff_tend<FT>(c, Ytc, Yc, Yf, s);  // additional_tendency! (remaining_tendency.jl:185-195)
@@ -1103,6 +1043,7 @@ static int impl_t_exp(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, c
 }
 extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void* Ylf, const void* Yc, const void* Yf, double,
                               void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_t_exp_lim: null context");
   return c->ft == 4 ? impl_t_exp<float>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream)
                     : impl_t_exp<double>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream);
@@ -1180,6 +1121,7 @@ static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
   return vborrow();
 }
 extern "C" int b200_lim(b200_ctx* c, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_lim: null context");
   (void)Yf; (void)ref_Yf;
   return c->ft == 4 ? impl_lim<float>(c, Yc, ref_Yc, (cudaStream_t)stream) : impl_lim<double>(c, Yc, ref_Yc, (cudaStream_t)stream);
@@ -1196,7 +1138,7 @@ static int impl_axpy_dss(b200_ctx* c, void* Uc, void* Uf, const void* uc, const 
   const bool small = (size_t)(nh + c->dims.nh_ghost) * c->ncf() * 16 * (size_t)(nv + 1) < (size_t)INT32_MAX;
   const bool multi = c->comm != nullptr || !c->nbr.empty() || c->dims.nh_ghost > 0;
   const bool p2p = multi && c->p2p_ready && !getenv("B200_HALO_NCCL");
-  if (!c->fuse_axdss || c->legacy || (multi && !p2p) || !small) return 1;
+  if (!c->fuse_axdss || (multi && !p2p) || !small) return 1;
   AxDssArgs<FT> A;
   int m = 0;
   A.dmask = 0;
@@ -1247,52 +1189,23 @@ template <class FT>
 static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtg, cudaStream_t s) {
   const size_t bc = c->nc() * sizeof(FT), bf = c->nf() * sizeof(FT);
   if (vdiff_implicit(c)) {  // implicit vertical diffusion: the fused stage with the diffusion blocks and the approximate arrowhead iteration
-    if (!c->vdiff_fused) return fail("implicit vertical diffusion: the fused stage kernel is opt-in (B200_VDIFF_FUSED=1); use the hook entry points");
     k_imp_stage_diff<FT><<<c->dims.nh * 4, NT, (size_t)QD_PROFILES * 4 * LVP * sizeof(FT), s>>>(
         make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
     LAUNCH_CHECK(c);
     return 0;
   }
-  if (c->legacy == 1 || c->legacy == 2) {
-    CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
-    k_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(18), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                             (FT*)Nc, (FT*)Nf, (FT)dtg);
-    LAUNCH_CHECK(c);
-  } else if (c->imp_kernel == 4) {
-    k4_imp_stage<FT><<<c->dims.nh * 4, QT, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
-                                                 (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
-    LAUNCH_CHECK(c);
-  } else if (c->imp_kernel == 3) {
-    const int ncols = c->dims.nh * 16;
-    k3_imp_stage<FT><<<(ncols + 7) / 8, 256, 0, s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc,
-                                                   (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, ncols);
-    LAUNCH_CHECK(c);
-  } else if (c->imp_kernel == 5) {
-#define IMP5_LAUNCH(TS, NVC_, MB)                                                                                          \
-  launchx(c->pdl & 16, k5_imp_stage<FT, TS, NVC_, MB>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, \
-                                                                      (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg)
-    const bool nv63 = c->dims.nv == 63 && !c->generic_nv;
-    if (c->imp_solver == 0) IMP5_LAUNCH(0, 0, 4);
-    else if (c->imp_solver == 1 && nv63) IMP5_LAUNCH(1, 63, 3);
-    else if (c->imp_solver == 1) IMP5_LAUNCH(1, 0, 4);
-    else if (nv63 && c->imp_minb == 4) IMP5_LAUNCH(2, 63, 4);
-    else if (nv63 && c->imp_minb == 3) IMP5_LAUNCH(2, 63, 3);
-    else if (nv63) IMP5_LAUNCH(2, 63, 2);
-    else IMP5_LAUNCH(2, 0, 2);
-#undef IMP5_LAUNCH
-    LAUNCH_CHECK(c);
-  } else {
-    k2_imp_stage<FT><<<c->dims.nh, NT, smem_slabs<FT>(11), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                              (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
-    LAUNCH_CHECK(c);
-  }
+  if (c->dims.nv == 63 && !c->generic_nv)
+    launchx(c->pdl & 16, k5_imp_stage<FT, 63>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+  else
+    launchx(c->pdl & 16, k5_imp_stage<FT, 0>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+  LAUNCH_CHECK(c);
   return 0;
 }
 extern "C" int b200_implicit_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtgamma, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_implicit_stage: null context");
-  if (vdiff_implicit(c) && !c->vdiff_fused)
-    return fail("b200_implicit_stage: implicit vertical diffusion is served by the hook entry points (b200_wfact, b200_t_imp, b200_ldiv) unless B200_VDIFF_FUSED=1");
   return c->ft == 4 ? impl_imp_stage<float>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream)
                     : impl_imp_stage<double>(c, Nc, Nf, Uc, Uf, dtgamma, (cudaStream_t)stream);
 }
@@ -1324,7 +1237,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
     if (launch_axpy<FT>(c, (FT*)Uf_, (const FT*)Yf, 0, (const FT* const*)Tl, cl, c->nf(), s)) return -1;
     return nl > 0 ? impl_lim<FT>(c, Uc_, Yc, s) : 0;
   };
-  bool stiff = fused && !c->legacy && c->stiff_final && !limiter;
+  bool stiff = fused && c->stiff_final && !limiter;
   for (int j = 0; j < 4; ++j) stiff = stiff && tb.bi[j] == tb.ai[3][j];
   // Stage-solution form of the increments (fused path, stiffly accurate tableau).  T_imp[j] ≡ (N_j − U_j)/(dt·a_imp[j][j]) only
   // ever enters later increments, and U_j is itself an increment, so by recursion every stage state is
@@ -1351,6 +1264,12 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
     DssField F[2] = {{ac, c->ncf(), 0, 2}, {af, 1, 1, 0}};
     return impl_dss<FT>(c, F, 2, s);
   };
+  if (fused) {  // stage 1 evaluates T_exp(u) directly: apply cache_imp!'s u₃ boundary filter to the incoming state (the literal path calls
+                // impl_cache_imp below; later stages get it from the increment kernels)
+    const int ncols = c->dims.nh * 16;
+    launchx(c->pdl & 8, k_u3_filter<FT>, dim3((2 * ncols + 255) / 256), dim3(256), 0, s, (FT*)Yf, ncols, c->dims.nv + 1);
+    LAUNCH_CHECK(c);
+  }
   for (int i = 0; i < 4; ++i) {
     void *Uc = Yc, *Uf = Yf;  // stage 1: U = u
     if (i > 0) {
@@ -1417,7 +1336,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
       // path neither forms T_imp[4] nor reads u and the three T_imp vectors in the final increment (5 vectors instead of 7).
       if (zform || (stiff && i == 3)) { Uc = Nc; Uf = Nf; goto t_exp_of_stage; }
       cudaStream_t sd = s;
-      if (fused && !c->legacy) {
+      if (fused) {
         if (!c->side) {
           CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
           CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -1436,7 +1355,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
     }
   t_exp_of_stage:
     if (impl_t_exp<FT>(c, c->Tec[i], c->Tef[i], limiter ? c->Tlc[i] : nullptr, nullptr, Uc, Uf, s)) return -1;
-    if (i > 0 && fused && !c->legacy && !zform && !(stiff && i == 3)) CK(cudaStreamWaitEvent(s, c->ev_join, 0));  // join the side stream
+    if (i > 0 && fused && !zform && !(stiff && i == 3)) CK(cudaStreamWaitEvent(s, c->ev_join, 0));  // join the side stream
   }
   {
     const void* Tc[8]; const void* Tf[8]; double cf[8]; int n = 0;
@@ -1467,16 +1386,14 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
   return fused ? 0 : impl_cache_imp<FT>(c, Yc, Yf, nullptr, s);
 }
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
+  CtxScope scope_(c);
   if (!c) return fail("b200_step_ars343: null context");
   cudaStream_t s = (cudaStream_t)stream;
-  // implicit vertical diffusion: the fused implicit-stage kernel does not carry the diffusion blocks yet — the stage runs through
-  // the hook sequence (cache_imp!, Wfact, T_imp!, ldiv!, T_post_imp!) of the literal path
-  if (vdiff_implicit(c) && !c->vdiff_fused) fused = 0;  // B200_VDIFF_FUSED=1: k_imp_stage_diff serves the fused path
   auto run = [&](cudaStream_t q) { return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, q) : impl_step<double>(c, Yc, Yf, fused, q); };
   // One CUDA graph per state buffer: ≈35 kernel launches, the side-stream fork/join and the memsets replay as one launch.
   // Multi-rank contexts replay too when the halo runs over peer memory (its exchange number lives in device memory); the NCCL
   // halo stays eager.
-  const bool graphable = c->use_graph && fused && !c->legacy && (c->nbr.empty() || (c->p2p_ready && !getenv("B200_HALO_NCCL")));
+  const bool graphable = c->use_graph && fused && (c->nbr.empty() || (c->p2p_ready && !getenv("B200_HALO_NCCL")));
   if (!graphable) return run(s);
   if (c->eager_steps < 1) { c->eager_steps++; return run(s); }  // first step eager: performs the lazy allocations
   // the legacy default stream cannot be captured: order an internal stream after/before it with events instead

@@ -344,6 +344,16 @@ __global__ void k_pack(const FT* __restrict__ src, FT* __restrict__ dst, const i
   for (int i = threadIdx.x; i < slab; i += blockDim.x) d[i] = s[i];
 }
 
+// u₃ boundary filter of cache_imp! (precomputed_quantities.jl:486-554, flat surface: ᶠuₕ³ = 0 ⇒ Y.f.u₃ = 0 on faces ½ and Nv+½), in place:
+// the fused stepper applies it to the incoming state so that a C-ABI caller need not have called b200_cache_imp first.
+template <class FT>
+__global__ void __launch_bounds__(256) k_u3_filter(FT* Yf, int ncols, int nlev) {
+  pdl_launch();
+  pdl_wait(Yf);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * ncols) Yf[(size_t)(i >> 1) * nlev + ((i & 1) ? nlev - 1 : 0)] = FT(0);
+}
+
 constexpr int AXPY_MAX = 8;
 template <class FT>
 struct AxpyArgs {

@@ -11,13 +11,13 @@
 //     s[jp][v] (jp = 2j + p, stride 65 pairs: conflict-free for level-major and for column-sequential access);
 //   * level constants and the three metric terms come straight from global memory (L1 broadcast);
 //   * the 16 Schur tridiagonal systems are solved by PARALLEL CYCLIC REDUCTION in the same thread layout (six
-//     steps of 2^k-strided eliminations on normalised rows, every thread busy) — the one-sided Thomas sweep by 16
-//     lanes cost ≈60 µs of the 220 µs kernel and the two-sided one ≈30 µs (measured; both kept as SOLVER 0/1).
+//     steps of 2^k-strided eliminations on normalised rows, every thread busy) — a one-sided Thomas sweep by 16
+//     lanes cost ≈60 µs of the 220 µs kernel and a two-sided one ≈30 µs (measured in round 1, profiles/r1_ncu_summary.md).
 // 13 pair slabs (54 KB Float32) ⇒ 4 CTAs/SM.
 #pragma once
 #include "common.cuh"
 #include "kernels_implicit.cuh"
-#include "kernels_reg.cuh"
+#include "kernels_row.cuh"
 #include "pair.cuh"
 #include "thermo2.cuh"
 
@@ -28,7 +28,6 @@ constexpr int PSLAB = 8 * PLV;   // pairs per slab (8 pair-columns × 65)
 constexpr int IMP5_SLABS = 13;
 template <class FT> constexpr size_t smem_imp5() { return (size_t)IMP5_SLABS * PSLAB * sizeof(P2<FT>); }
 
-template <class FT> __device__ __forceinline__ P2<FT> rcp2(P2<FT> a) { return P2<FT>(rcp_(a.lo()), rcp_(a.hi())); }
 // van Leer limited slope (same value as vl_slope in kernels_implicit.cuh, written with min/max instructions)
 template <class FT>
 __device__ __forceinline__ FT vl_slope5(FT am, FT a0, FT ap) {
@@ -51,63 +50,9 @@ __device__ __forceinline__ void st2g(const P2<FT> (&a)[2], FT* __restrict__ g, i
   g[0] = a[0].lo(); g[nlev] = a[0].hi(); g[2 * nlev] = a[1].lo(); g[3 * nlev] = a[1].hi();
 }
 
-// Two-sided Thomas solve of 16 tridiagonal systems held in pair slabs (column c: pair-column c>>1, half c&1).
-// Lanes 0..15 eliminate rows 0..m-1 downwards, lanes 16..31 rows n-1..m upwards; x_{m-1}, x_m from the 2×2 meeting
-// system; both halves then substitute outwards.  x overwrites r.  `twosided = false` is the plain one-sided sweep.
-template <class FT, bool TWOSIDED>
-__device__ __forceinline__ void thomas16(const FT* __restrict__ sl, const FT* __restrict__ sd, FT* __restrict__ su,
-                                         FT* __restrict__ sr, int n, int lane) {
-  const int c = lane & 15;
-  const int base = (c >> 1) * PLV * 2 + (c & 1);
-  const FT *l = sl + base, *d = sd + base;
-  FT *u = su + base, *r = sr + base;
-  if (!TWOSIDED) {
-    if (lane >= 16) return;
-    FT rd = rcp_(d[0]);
-    FT cp = u[0] * rd, dp = r[0] * rd;
-    u[0] = cp; r[0] = dp;
-    for (int i = 1; i < n; ++i) {
-      FT li = l[2 * i];
-      rd = rcp_(d[2 * i] - li * cp);
-      cp = u[2 * i] * rd;
-      dp = (r[2 * i] - li * dp) * rd;
-      u[2 * i] = cp; r[2 * i] = dp;
-    }
-    FT x = dp;
-    for (int i = n - 2; i >= 0; --i) { x = r[2 * i] - u[2 * i] * x; r[2 * i] = x; }
-    return;
-  }
-  const bool up = lane >= 16;           // eliminating upwards from the bottom row
-  const int m = n >> 1;                  // rows 0..m-1 belong to the downward half
-  const int cnt = up ? n - m : m;        // rows of this half
-  const int i0 = up ? n - 1 : 0, st = up ? -1 : 1;
-  // "in" coefficient couples to the previously eliminated row, "out" to the next one
-  const FT* cin = up ? (const FT*)u : l;
-  FT* cout = up ? const_cast<FT*>(l) : u;  // normalised out-coefficient overwrites the slab it came from
-  FT cp = FT(0), dp = FT(0);
-  for (int k = 0; k < cnt; ++k) {
-    const int i = i0 + st * k;
-    const FT a = (k == 0) ? FT(0) : cin[2 * i];
-    const FT rd = rcp_(d[2 * i] - a * cp);
-    cp = cout[2 * i] * rd;
-    dp = (r[2 * i] - a * dp) * rd;
-    cout[2 * i] = cp; r[2 * i] = dp;
-  }
-  // meeting rows: x_{m-1} = dpD − cpD·x_m,  x_m = dpU − cpU·x_{m-1}
-  const FT cpo = __shfl_xor_sync(FULLM, cp, 16), dpo = __shfl_xor_sync(FULLM, dp, 16);
-  FT x = (dp - cp * dpo) / (FT(1) - cp * cpo);  // own meeting unknown (x_{m-1} for the downward half, x_m for the upward half)
-  r[2 * (i0 + st * (cnt - 1))] = x;
-  for (int k = cnt - 2; k >= 0; --k) {
-    const int i = i0 + st * k;
-    x = r[2 * i] - cout[2 * i] * x;
-    r[2 * i] = x;
-  }
-}
-
 // NVC: compile-time number of levels (63 for every production configuration: all global offsets become immediates); 0 = run-time
-// SOLVER: 0 one-sided Thomas (16 lanes), 1 two-sided Thomas (32 lanes), 2 parallel cyclic reduction (all 256 threads)
-template <class FT, int SOLVER, int NVC, int MINB>
-__global__ void __launch_bounds__(256, (sizeof(FT) == 4 ? MINB : 2))
+template <class FT, int NVC>
+__global__ void __launch_bounds__(256, 2)
 k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
              const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg) {
   using V2 = P2<FT>;
@@ -117,7 +62,6 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   V2 *s_rho = sb, *s_u3 = sb + PSLAB, *s_h = sb + 2 * PSLAB, *s_A = sb + 3 * PSLAB, *s_M = sb + 4 * PSLAB,
      *s_dp = sb + 5 * PSLAB, *s_Pi = sb + 6 * PSLAB, *s_thv = sb + 7 * PSLAB, *s_thp = sb + 8 * PSLAB,
      *s_phr = sb + 9 * PSLAB, *s_d = sb + 10 * PSLAB, *s_u = sb + 11 * PSLAB, *s_r = sb + 12 * PSLAB;
-  V2* s_l = s_rho;  // ρ is not read between the second and the fourth barrier
   const int e = blockIdx.x, v = threadIdx.x & 63, j = threadIdx.x >> 6, n0 = j * 4, nv = NVC ? NVC : P.nv, nf = nv + 1;
   const bool cv = v < nv, fv = v < nf, interior = v > 0 && v < nv;
   const int vm = v > 0 ? v - 1 : 0, vm2 = v > 1 ? v - 2 : 0, vp = v < LV - 1 ? v + 1 : v;
@@ -162,12 +106,12 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   for (int p = 0; p < 2; ++p) {
     u3h[p] = s_u3[o0 + p * PLV - v + vp];
     rlo[p] = s_rho[o0 + p * PLV - v + vm];
-    V2 Pi(FT(1)), thv(FT(0)), thp(FT(0)), phr(FT(0)), dp(FT(0));
+    V2 Pi(FT(1)), thv(FT(0)), thp(FT(0)), phr(FT(1)), dp(FT(0));
     h[p] = V2(FT(0));
     if (cv) {
       const V2 K = Kh[p] + (u3[p] * (u3[p] * g33lo) + u3h[p] * (u3h[p] * g33hi)) * FT(0.25);
       const Pt2<FT> t = thermo2(P, rho[p], re[p], K, phi);
-      h[p] = t.h; Pi = t.Pi; thv = t.thv; thp = t.thp; phr = t.phir;
+      h[p] = t.h; Pi = t.Pi; thv = t.thv; thp = t.thp; phr = pgf_aux2(t);  // Φ_r (Float64) or p (Float32), see thermo2.cuh
       // ∂p/∂ρ at fixed ρe_tot (manual_sparse_jacobian.jl:816-818)
       dp = fma2(t.T, V2(P.R_d - kap * P.cv_d), ((V2(P.T_0 * P.cp_d) - K) - phi) * kap);
     }
@@ -205,7 +149,8 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       const V2 Pil = s_Pi[om], thvl = s_thv[om], thpl = s_thp[om], phrl = s_phr[om], dpl = s_dp[om];
       const V2 Pi = s_Pi[o], thv = s_thv[o], thp = s_thp[o], phr = s_phr[o], dp = s_dp[o];
       const V2 irf = rcpn2((rlo[p] + rho[p]) * FT(0.5));
-      const V2 dPi = Pi - Pil;
+      V2 dPi, dphr;
+      pgf_diff2(P, Pil, Pi, phrl, phr, dPi, dphr);
       const V2 buoy = ((((thvl + thv) * FT(0.5)) * P.cp_d) * dPi) * irf;
       const V2 hb = buoy * FT(0.5);
       const V2 ur_lo = fma2(irf, dpl, hb) * dtg, ur_hi = (hb - irf * dp) * dtg;
@@ -224,13 +169,13 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       const V2 rr_a = ((M[p] - Mm) * (-dtg)) * rmclo, rr_b = ((Mp - M[p]) * (-dtg)) * rmc;
       const V2 Mh0 = M[p] * hf0;
       const V2 re_a = ((Mh0 - Mm * hfm) * (-dtg)) * rmclo, re_b = ((Mp * hfp - Mh0) * (-dtg)) * rmc;
-      const V2 tf = -((V2(dphif) - (phr - phrl)) + (((thpl + thp) * FT(0.5)) * P.cp_d) * dPi) - u3[p] * beta;
+      const V2 tf = -((V2(dphif) - dphr) + (((thpl + thp) * FT(0.5)) * P.cp_d) * dPi) - u3[p] * beta;
       cl[p] = l; cd[p] = d; cu[p] = u;
       cr[p] = fma2(tf, V2(dtg), fma2(ur_lo, rr_a, ur_hi * rr_b) + fma2(ue_lo, re_a, ue_hi * re_b));
     }
   }
   V2 x0[2], x1[2];  // ΔU.f.u₃ at faces v and v+1
-  if (SOLVER == 2) {
+  {
     // ---- parallel cyclic reduction on the normalised rows a·x[v−s] + x[v] + c·x[v+s] = y, s = 1, 2, 4, …: every
     // thread reduces its own four rows, no serial sweep.  Double-buffered slabs, one barrier per step.
     V2 a[2], c[2], y[2];
@@ -265,16 +210,6 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     __syncthreads();
 #pragma unroll
     for (int p = 0; p < 2; ++p) x1[p] = bx[o0 + p * PLV - v + vp];
-  } else {
-#pragma unroll
-    for (int p = 0; p < 2; ++p) { const int o = o0 + p * PLV; s_l[o] = cl[p]; s_d[o] = cd[p]; s_u[o] = cu[p]; s_r[o] = cr[p]; }
-    __syncthreads();  // (3) solver slabs
-    if (threadIdx.x < 32)
-      thomas16<FT, SOLVER == 1>(reinterpret_cast<const FT*>(s_l), reinterpret_cast<const FT*>(s_d), reinterpret_cast<FT*>(s_u),
-                                reinterpret_cast<FT*>(s_r), nf, threadIdx.x);
-    __syncthreads();  // (4) ΔU.f.u₃ in s_r
-#pragma unroll
-    for (int p = 0; p < 2; ++p) { x0[p] = s_r[o0 + p * PLV]; x1[p] = s_r[o0 + p * PLV - v + vp]; }
   }
   // ---- U ← U − ΔU (back-substitution of the scalar rows)
   V2 nr[2], nre[2], nu[2], nu1[2];

@@ -121,7 +121,7 @@ __device__ __forceinline__ void imp_thermo(const Par<FT>& P, const FT* hg, const
       int o = n * LVP + v;
       FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
       Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
-      S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = t.phir; S.T[o] = t.T;
+      S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = pgf_aux(t); S.T[o] = t.T;
     }
   }
 }
@@ -149,39 +149,14 @@ __device__ __forceinline__ FT timp_face(const Par<FT>& P, const VLev<FT>& V, con
   int o = n * LVP + f;
   FT r = FT(0);
   if (f > 0 && f < nv) {
-    r = -(V.dphif[f] - (S.phr[o] - S.phr[o - 1]) +
-          P.cp_d * (FT(0.5) * (S.thp[o - 1] + S.thp[o])) * (S.Pi[o] - S.Pi[o - 1]));
+    FT dPi, dphr;  // S.phr carries Φ_r (Float64) or p (Float32): common.cuh pgf_diff
+    pgf_diff(P, S.Pi[o - 1], S.Pi[o], S.phr[o - 1], S.phr[o], dPi, dphr);
+    r = -(V.dphif[f] - dphr + P.cp_d * (FT(0.5) * (S.thp[o - 1] + S.thp[o])) * dPi);
   }
   if (P.rayleigh) r += -V.brw[f] * S.u3[o];
   return r;
 }
 
-template <class FT>
-__global__ void __launch_bounds__(NT) k_t_imp(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
-                                              const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
-  FT* hg = sm.take(HG_ELEM * 16);
-  ImpSlabs<FT> S; imp_carve(sm, S);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
-  __syncthreads();
-  imp_thermo(P, hg, V, S);
-  __syncthreads();
-  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
-  FT* gF = Ytf + (size_t)h * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    if (v < nv) {
-      FT rt, et; timp_center(V, S, n, v, nv, rt, et);
-      gT[(0 * 16 + n) * nv + v] = rt; gT[(1 * 16 + n) * nv + v] = FT(0);
-      gT[(2 * 16 + n) * nv + v] = FT(0); gT[(3 * 16 + n) * nv + v] = et;
-      for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);  // passive tracers are advected explicitly
-    }
-    if (v < nf) gF[n * nf + v] = timp_face(P, V, S, n, v, nv);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Jacobian coefficients at face f / centre v (manual_sparse_jacobian.jl:746-868, dry flat grid).
@@ -218,7 +193,9 @@ __device__ __forceinline__ FaceCoef<FT> face_coef(const Par<FT>& P, const FT* hg
   FT pg_lo = FT(1) / rf, pg_hi = -FT(1) / rf;
   FT dp_lo = kap * (P.T_0 * P.cp_d - S.K[o - 1] - V.phic[f - 1]) + (P.R_d - kap * P.cv_d) * S.T[o - 1];
   FT dp_hi = kap * (P.T_0 * P.cp_d - S.K[o] - V.phic[f]) + (P.R_d - kap * P.cv_d) * S.T[o];
-  FT buoy = P.cp_d * (FT(0.5) * (S.thv[o - 1] + S.thv[o])) * (S.Pi[o] - S.Pi[o - 1]) / rf;
+  FT dPi, dphr_;
+  pgf_diff(P, S.Pi[o - 1], S.Pi[o], S.phr[o - 1], S.phr[o], dPi, dphr_);
+  FT buoy = P.cp_d * (FT(0.5) * (S.thv[o - 1] + S.thv[o])) * dPi / rf;
   c.ur_lo = dtg * (pg_lo * dp_lo + buoy * FT(0.5));
   c.ur_hi = dtg * (pg_hi * dp_hi + buoy * FT(0.5));
   c.ue_lo = dtg * pg_lo * kap;
@@ -247,109 +224,8 @@ __device__ __forceinline__ FaceCoef<FT> face_coef(const Par<FT>& P, const FT* hg
   return c;
 }
 
-template <class FT>
-__global__ void __launch_bounds__(NT) k_wfact(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
-                                              const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT dtg, FT* jac) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
-  FT* hg = sm.take(HG_ELEM * 16);
-  ImpSlabs<FT> S; imp_carve(sm, S);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
-  __syncthreads();
-  imp_thermo(P, hg, V, S);
-  __syncthreads();
-  FT* gj = jac + (size_t)h * JC_N * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    if (v >= nf) continue;
-    FaceCoef<FT> c = face_coef(P, hg, V, S, dtg, n, v, nv);
-    size_t o = (size_t)n * nf + v, pl = (size_t)16 * nf;
-    gj[JC_L * pl + o] = c.l; gj[JC_D * pl + o] = c.d; gj[JC_U * pl + o] = c.u;
-    gj[JC_UR_LO * pl + o] = c.ur_lo; gj[JC_UR_HI * pl + o] = c.ur_hi;
-    gj[JC_UE_LO * pl + o] = c.ue_lo; gj[JC_UE_HI * pl + o] = c.ue_hi;
-    gj[JC_U1_LO * pl + o] = c.u1_lo; gj[JC_U1_HI * pl + o] = c.u1_hi;
-    gj[JC_U2_LO * pl + o] = c.u2_lo; gj[JC_U2_HI * pl + o] = c.u2_hi;
-    FT a = FT(0), b = FT(0), cc = FT(0), dd = FT(0);
-    if (v < nv) center_coef(V, S, dtg, n, v, nv, a, b, cc, dd);
-    gj[JC_RU_LO * pl + o] = a; gj[JC_RU_HI * pl + o] = b; gj[JC_EU_LO * pl + o] = cc; gj[JC_EU_HI * pl + o] = dd;
-  }
-}
 
-// Thomas algorithm over one column held in shared memory (stride-1 in v, node stride LVP):
-// overwrites u with c', rhs with the solution.
-template <class FT>
-__device__ __forceinline__ void thomas_column(const FT* l, const FT* d, FT* u, FT* rhs, int nf) {
-  FT cp = u[0] / d[0];
-  FT dp = rhs[0] / d[0];
-  u[0] = cp; rhs[0] = dp;
-  for (int i = 1; i < nf; ++i) {
-    FT li = l[i];
-    FT den = d[i] - li * cp;
-    cp = u[i] / den;
-    dp = (rhs[i] - li * dp) / den;
-    u[i] = cp; rhs[i] = dp;
-  }
-  FT x = dp;
-  for (int i = nf - 2; i >= 0; --i) {
-    x = rhs[i] - u[i] * x;
-    rhs[i] = x;
-  }
-}
 
-template <class FT>
-__global__ void __launch_bounds__(NT) k_ldiv(Par<FT> P, const FT* __restrict__ jac, const FT* __restrict__ Rc,
-                                             const FT* __restrict__ Rf, FT* dYc, FT* dYf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
-  FT* rr = sm.take(SLAB); FT* r1 = sm.take(SLAB); FT* r2 = sm.take(SLAB); FT* re = sm.take(SLAB);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
-  const size_t pl = (size_t)16 * nf;
-  const FT* gRc = Rc + (size_t)h * P.ncf * 16 * nv;
-  load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
-  load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
-  __syncthreads();
-  const FT* gRf = Rf + (size_t)h * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, f = idx & 63;
-    if (f >= nf) continue;
-    size_t o = (size_t)n * nf + f;
-    int s = n * LVP + f;
-    FT rhs = gRf[o];
-    if (f > 0 && f < nv) {
-      rhs += gj[JC_UR_LO * pl + o] * rr[s - 1] + gj[JC_UR_HI * pl + o] * rr[s];
-      rhs += gj[JC_UE_LO * pl + o] * re[s - 1] + gj[JC_UE_HI * pl + o] * re[s];
-      rhs += gj[JC_U1_LO * pl + o] * r1[s - 1] + gj[JC_U1_HI * pl + o] * r1[s];
-      rhs += gj[JC_U2_LO * pl + o] * r2[s - 1] + gj[JC_U2_HI * pl + o] * r2[s];
-    }
-    sr[s] = rhs;
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    int n = threadIdx.x;
-    thomas_column(sl + n * LVP, sd + n * LVP, su + n * LVP, sr + n * LVP, nf);
-  }
-  __syncthreads();
-  FT* gdc = dYc + (size_t)h * P.ncf * 16 * nv;
-  FT* gdf = dYf + (size_t)h * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    int s = n * LVP + v;
-    size_t o = (size_t)n * nf + v;
-    if (v < nf) gdf[o] = sr[s];
-    if (v < nv) {
-      FT x0 = sr[s], x1 = sr[s + 1];
-      gdc[(0 * 16 + n) * nv + v] = gj[JC_RU_LO * pl + o] * x0 + gj[JC_RU_HI * pl + o] * x1 - rr[s];
-      gdc[(1 * 16 + n) * nv + v] = -r1[s];
-      gdc[(2 * 16 + n) * nv + v] = -r2[s];
-      gdc[(3 * 16 + n) * nv + v] = gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1 - re[s];
-      for (int q = 4; q < P.ncf; ++q) gdc[(q * 16 + n) * nv + v] = -gRc[(q * 16 + n) * nv + v];  // fallback −I block
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // van Leer (Lin 1994, MonotoneLocalExtrema) face value of χ upwinded with u³ (abbreviations.jl:250-256)
@@ -375,143 +251,7 @@ __device__ __forceinline__ FT upwind_minus_central(const Par<FT>& P, const FT* c
   return up - cen;
 }
 
-template <class FT>
-__global__ void __launch_bounds__(NT) k_t_post_imp(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
-                                                   const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
-  FT* hg = sm.take(HG_ELEM * 16);
-  ImpSlabs<FT> S; imp_carve(sm, S);
-  FT* flx = sm.take(SLAB);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
-  __syncthreads();
-  imp_thermo(P, hg, V, S);
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, f = idx & 63;
-    if (f >= nf) continue;
-    int o = n * LVP + f;
-    FT r = FT(0);
-    if (f > 0 && f < nv) {
-      FT w = V.g33f[f] * S.u3[o];
-      r = rho_mface(V, S.rho, o, f) * w * upwind_minus_central(P, S.h, o, f, nv, w);
-    }
-    flx[o] = r;
-  }
-  __syncthreads();
-  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
-  FT* gF = Ytf + (size_t)h * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    int o = n * LVP + v;
-    if (v < nv) {
-      gT[(0 * 16 + n) * nv + v] = FT(0); gT[(1 * 16 + n) * nv + v] = FT(0); gT[(2 * 16 + n) * nv + v] = FT(0);
-      gT[(3 * 16 + n) * nv + v] = -(flx[o + 1] - flx[o]) / V.mc[v];
-      for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
-    }
-    if (v < nf) gF[n * nf + v] = FT(0);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
-// Fused implicit stage (native stepper): given the DSSed stage state U this performs, in one pass
-// over the element, cache_imp! (u₃ boundary filter) → Wfact → T_imp! residual → ldiv! → U -= ΔU →
-// cache_imp! → T_post_imp! (U += dtγ·correction).  Output: U (in place).  temp == U on entry, so
-// the Newton residual is R = dtγ·T_imp(U) (ClimaTimeSteppers, one Newton iteration).
-template <class FT>
-__global__ void __launch_bounds__(NT) k_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
-                                                  FT* Yc, FT* Yf, FT dtg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
-  FT* hg = sm.take(HG_ELEM * 16);
-  ImpSlabs<FT> S; imp_carve(sm, S);
-  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
-  FT* rr = sm.take(SLAB); FT* rre = sm.take(SLAB);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
-  __syncthreads();
-  if (threadIdx.x < 16) { S.u3[threadIdx.x * LVP] = FT(0); S.u3[threadIdx.x * LVP + nv] = FT(0); }
-  __syncthreads();
-  imp_thermo(P, hg, V, S);
-  __syncthreads();
-  // residual of the scalars at centres: R = dtγ·T_imp
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    if (v < nv) {
-      FT rt, et; timp_center(V, S, n, v, nv, rt, et);
-      rr[n * LVP + v] = dtg * rt; rre[n * LVP + v] = dtg * et;
-    }
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, f = idx & 63;
-    if (f >= nf) continue;
-    int s = n * LVP + f;
-    FaceCoef<FT> c = face_coef(P, hg, V, S, dtg, n, f, nv);
-    FT rhs = dtg * timp_face(P, V, S, n, f, nv);
-    if (f > 0 && f < nv) {
-      rhs += c.ur_lo * rr[s - 1] + c.ur_hi * rr[s] + c.ue_lo * rre[s - 1] + c.ue_hi * rre[s];
-      // R_uₕ = dtγ·0 = 0 ⇒ no (u₃,uₕ) contribution and Δuₕ = 0
-    }
-    sl[s] = c.l; sd[s] = c.d; su[s] = c.u; sr[s] = rhs;
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    int n = threadIdx.x;
-    thomas_column(sl + n * LVP, sd + n * LVP, su + n * LVP, sr + n * LVP, nf);
-  }
-  __syncthreads();
-  // back-substitute and update U (sl/sd reused for new ρ, ρe)
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    int s = n * LVP + v;
-    if (v < nv) {
-      FT a, b, c, d; center_coef(V, S, dtg, n, v, nv, a, b, c, d);
-      FT x0 = sr[s], x1 = sr[s + 1];
-      sl[s] = S.rho[s] - (a * x0 + b * x1 - rr[s]);
-      sd[s] = S.re[s] - (c * x0 + d * x1 - rre[s]);
-    }
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    int s = n * LVP + v;
-    if (v < nv) { S.rho[s] = sl[s]; S.re[s] = sd[s]; }
-    if (v < nf) S.u3[s] = (v == 0 || v == nv) ? FT(0) : S.u3[s] - sr[s];
-  }
-  __syncthreads();
-  FT* gYc = Yc + (size_t)h * P.ncf * 16 * nv;
-  FT* gYf = Yf + (size_t)h * 16 * nf;
-  if (P.upwinding != 0) {
-    imp_thermo(P, hg, V, S);  // cache_imp!(U) after the Newton update
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-      int n = idx >> 6, f = idx & 63;
-      if (f >= nf) continue;
-      int o = n * LVP + f;
-      FT r = FT(0);
-      if (f > 0 && f < nv) {
-        FT w = V.g33f[f] * S.u3[o];
-        r = rho_mface(V, S.rho, o, f) * w * upwind_minus_central(P, S.h, o, f, nv, w);
-      }
-      su[o] = r;
-    }
-    __syncthreads();
-  }
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    int s = n * LVP + v;
-    if (v < nv) {
-      gYc[(0 * 16 + n) * nv + v] = S.rho[s];
-      FT e = S.re[s];
-      if (P.upwinding != 0) e += dtg * (-(su[s + 1] - su[s]) / V.mc[v]);
-      gYc[(3 * 16 + n) * nv + v] = e;
-    }
-    if (v < nf) gYf[n * nf + v] = S.u3[s];
-  }
-}
 
 }  // namespace b200

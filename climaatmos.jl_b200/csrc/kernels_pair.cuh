@@ -28,10 +28,6 @@ __device__ __forceinline__ void dxi4p(const P2<FT> (&a)[2], P2<FT> (&o)[2]) {
   for (int p = 0; p < 2; ++p)
     o[p] = fma2(cP<FT>((W * 4 + 3) * 2 + p), a3, fma2(cP<FT>((W * 4 + 2) * 2 + p), a2, fma2(cP<FT>((W * 4 + 1) * 2 + p), a1, cP<FT>((W * 4 + 0) * 2 + p) * a0)));
 }
-template <class FT>
-__device__ __forceinline__ P2<FT> shflp(const P2<FT>& a, int src) {
-  return P2<FT>(__shfl_sync(FULLM, a.lo(), src), __shfl_sync(FULLM, a.hi(), src));
-}
 // ξ²-contraction o_j = Σ_k M[j][k]·a_k over the four lanes j = lane>>3 of a level, as a REDUCE-SCATTER: every lane multiplies its
 // own row by the matrix COLUMN it owns and the partial sums travel in two butterfly steps (lanes ^16, then ^8) — 3 shuffles per
 // value instead of the 4 of a gather (ncu: the LSU pipe, i.e. the shuffles, is the busiest pipe of k5_exp_a / k5_exp_c).
@@ -88,11 +84,6 @@ template <class FT>
 __device__ __forceinline__ void sputp(FT* s, const P2<FT> (&a)[2], int j, int v) {
   s[(j * 4 + 0) * LVP + v] = a[0].lo(); s[(j * 4 + 1) * LVP + v] = a[0].hi();
   s[(j * 4 + 2) * LVP + v] = a[1].lo(); s[(j * 4 + 3) * LVP + v] = a[1].hi();
-}
-template <class FT>
-__device__ __forceinline__ void sgetp(const FT* s, P2<FT> (&a)[2], int j, int v) {
-  a[0] = P2<FT>(s[(j * 4 + 0) * LVP + v], s[(j * 4 + 1) * LVP + v]);
-  a[1] = P2<FT>(s[(j * 4 + 2) * LVP + v], s[(j * 4 + 3) * LVP + v]);
 }
 // Pair-layout exchange slabs for k5_exp_a / k5_exp_c: s[(2j + p)·XLV + v] holds the pair p of row j at level v as ONE 64-bit word
 // (STS.64 / LDS.64: half the LSU instructions of the scalar slabs).  XLV = 68: the row stride 2·XLV pairs = 272 words ≡ 16 (mod 32)

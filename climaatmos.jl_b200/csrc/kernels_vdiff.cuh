@@ -1,7 +1,7 @@
 // kernels_vdiff.cuh — vertical (K-theory) diffusion and the approximate arrowhead solve that implicit diffusion switches on
 // (SURVEY.md §8f n2), hook level, one element (16 columns) per CTA in the slab layout of kernels_implicit.cuh.
 //
-//   k_vdiff_tend   vertical_diffusion_boundary_layer_tendency!  (src/prognostic_equations/vertical_diffusion_boundary_layer.jl:64-154,
+//   k_vdiff_tend2  vertical_diffusion_boundary_layer_tendency!  (src/prognostic_equations/vertical_diffusion_boundary_layer.jl:64-154,
 //                  dry branch + passive tracers) — ADDS to Yₜ.c; appended to T_exp (diff_mode Explicit, remaining_tendency.jl:185-195)
 //                  or to T_imp (diff_mode Implicit, implicit/implicit_tendency.jl:69-78)
 //   k_vdiff_jac    update_diffusion_jacobian!  (implicit/manual_sparse_jacobian.jl:1031-1261, dry non-EDMF branch): two planes per
@@ -11,13 +11,15 @@
 //                  alg₂ = BlockLowerTriangularSolve(uₕ), P_alg₁ = MainDiagonalPreconditioner(), n_iters)
 //                  (manual_sparse_jacobian.jl:538-578; ClimaCore MatrixFields field_matrix_solver.jl [UPSTREAM-RECALL])
 //
-// Index of this file (status: [B200] = parity-green on a B200, [emu] = matched against the oracle in the CPU CTA emulator only, opt-in):
-//   k_vdiff_tend [B200], k_vdiff_tend2 [B200, default]      diffusion tendency (element slabs / quarter element, no slabs)
-//   k_vdiff_jac [B200, default], k_vdiff_jac2 [emu]         diffusion Jacobian planes                       (B200_LDIV_DIFF=2 selects *2)
-//   k_ldiv_diff [B200, default], k_ldiv_diff2 [emu]         approximate arrowhead solve, Thomas / PCR (pcr_slab)
-//   k_imp_stage_diff [emu]                                  fused implicit stage with implicit diffusion    (B200_VDIFF_FUSED=1)
-//   k_lim_vborrow [emu]                                     lim!: vertical mass-borrowing limiter           (off unless configured)
-//   k_t_imp2, k_wfact2, k_t_post_imp2, k_ldiv2 [emu]        second generation of the dry hook kernels      (B200_HOOK_KERNELS=2)
+// Index of this file (every kernel is parity-green on a B200, tests/test_gpu_vertical_diffusion.py; round-2 validation record in
+// profiles/r2_opt_in_validation.md):
+//   k_vdiff_tend2                                diffusion tendency, quarter element per CTA, no state slabs
+//   k_vdiff_jac, k_ldiv_diff                     diffusion Jacobian planes; approximate arrowhead solve (16-lane Thomas sweeps)
+//   k_imp_stage_diff                             fused implicit stage with implicit diffusion (b200_implicit_stage, the fused stepper)
+//   k_lim_vborrow                                lim!: vertical mass-borrowing limiter (off unless configured)
+//   k_t_imp2, k_wfact2, k_t_post_imp2, k_ldiv2   the dry hook kernels (quarter element per CTA; PCR column solve)
+// Removed in round 2 after the A/B record was committed: the element-slab first generation (k_vdiff_tend, k_t_imp, k_wfact, k_ldiv,
+// k_t_post_imp: slower) and the PCR variants of the diffusion solve (k_vdiff_jac2 + k_ldiv_diff2: 15.2 vs 10.5 ms/step).
 //
 // Eddy diffusivity (src/cache/eddy_diffusivity_coefficient.jl:16-42, src/cache/precomputed_quantities.jl:652-676): K_u = K_h;
 // DecayWithHeightDiffusion K = D₀ exp(−(z − z_sfc)/H) (host table per level), VerticalDiffusion K = C_E |uₕ(level 1)| Δz₁/2 below
@@ -87,66 +89,6 @@ __device__ __forceinline__ void vdiff_pw(const Par<FT>& P, const VDiff<FT>& D, c
   }
 }
 
-template <class FT>
-__global__ void __launch_bounds__(NT) k_vdiff_tend(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
-                                                   const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-                                                   const FT* __restrict__ Yf, FT* Ytc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  VLev<FT>& V = *reinterpret_cast<VLev<FT>*>(sm.take(sizeof(VLev<FT>) / sizeof(FT)));
-  FT* hg = sm.take(HG_ELEM * 16);
-  ImpSlabs<FT> S; imp_carve(sm, S);
-  FT* kh = sm.take(SLAB); FT* pw = sm.take(SLAB);
-  const int h = blockIdx.x, nv = P.nv;
-  load_vlev(&V, vlev); load_hgeo(hg, hgeo, h); imp_load_state(S, Yc, Yf, h, nv, P.ncf);
-  __syncthreads();
-  imp_thermo(P, hg, V, S);
-  __syncthreads();
-  vdiff_kh(P, D, hg, V, S, kh);
-  __syncthreads();
-  vdiff_pw(P, D, V, S, kh, pw, FT(1));
-  __syncthreads();
-  const FT* gY = Yc + (size_t)h * P.ncf * 16 * nv;
-  FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    if (v >= nv) continue;
-    const int o = n * LVP + v;
-    const bool lo = v > 0, hi = v < nv - 1;
-    const FT wl = lo ? pw[o] : FT(0), wh = hi ? pw[o + 1] : FT(0);
-    const FT rm = V.rmc[v];
-    // ρe_tot: dry static energy s_d = cp_d (T − T_0) + Φ  (:101-102)
-    {
-      FT s0 = P.cp_d * (S.T[o] - P.T_0) + V.phic[v];
-      FT fl = lo ? wl * (s0 - (P.cp_d * (S.T[o - 1] - P.T_0) + V.phic[v - 1])) : FT(0);
-      FT fh = hi ? wh * ((P.cp_d * (S.T[o + 1] - P.T_0) + V.phic[v + 1]) - s0) : FT(0);
-      gT[(3 * 16 + n) * nv + v] += (fh - fl) * rm;
-    }
-    // uₕ: −C12(ᶜdivᵥ(−2 ᶠρK ε)/ρ) (:91-96) = s_c/(ρ J_c) δ(J g³³ ᶠρK δ(uₕ/s_c)) per covariant component
-    if (D.momentum) {
-      FT is0 = sqrt(V.sc2i[v]);  // 1/s_c
-      FT isl = lo ? sqrt(V.sc2i[v - 1]) : FT(0), ish = hi ? sqrt(V.sc2i[v + 1]) : FT(0);
-      FT sir = rm / (is0 * S.rho[o]);
-      {
-        FT c0 = S.u1[o] * is0;
-        FT fl = lo ? wl * (c0 - S.u1[o - 1] * isl) : FT(0), fh = hi ? wh * (S.u1[o + 1] * ish - c0) : FT(0);
-        gT[(1 * 16 + n) * nv + v] += (fh - fl) * sir;
-      }
-      {
-        FT c0 = S.u2[o] * is0;
-        FT fl = lo ? wl * (c0 - S.u2[o - 1] * isl) : FT(0), fh = hi ? wh * (S.u2[o + 1] * ish - c0) : FT(0);
-        gT[(2 * 16 + n) * nv + v] += (fh - fl) * sir;
-      }
-    }
-    // passive grid-scale tracers χ = ρχ/ρ (:150-153)
-    for (int q = 4; q < P.ncf; ++q) {
-      const FT* gq = gY + (size_t)(q * 16 + n) * nv;
-      FT c0 = gq[v] / S.rho[o];
-      FT fl = lo ? wl * (c0 - gq[v - 1] / S.rho[o - 1]) : FT(0), fh = hi ? wh * (gq[v + 1] / S.rho[o + 1] - c0) : FT(0);
-      gT[(q * 16 + n) * nv + v] += (fh - fl) * rm;
-    }
-  }
-}
 
 // Second generation of k_vdiff_tend: a quarter element (4 columns × 64 levels) per CTA, no state slabs — each thread loads its own
 // point, computes T (and K_h) once, and only the six per-column profiles the vertical differences need (ρ, K_h, s_d, uₕ/s_c, χ) and the
@@ -270,55 +212,6 @@ __global__ void __launch_bounds__(NT) k_vdiff_jac(Par<FT> P, VDiff<FT> D, const 
   }
 }
 
-// Second generation of k_vdiff_jac, in the layout of k_vdiff_tend2 (quarter element per CTA, no state slabs): the same two planes.
-template <class FT>
-__global__ void __launch_bounds__(NT) k_vdiff_jac2(Par<FT> P, VDiff<FT> D, const FT* __restrict__ hgeo,
-                                                   const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-                                                   const FT* __restrict__ Yf, FT dtg, FT* jacd) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  FT* s_rho = sm.take(4 * VD2_ST); FT* s_kh = sm.take(4 * VD2_ST);
-  const int h = blockIdx.x >> 2, nl = threadIdx.x >> 6, n = (blockIdx.x & 3) * 4 + nl, v = threadIdx.x & 63, nv = P.nv, nf = nv + 1;
-  const VLev<FT>& V = *vlev;
-  const FT* hg = hgeo + (size_t)h * HG_N * 16;
-  const FT* gY = Yc + (size_t)h * P.ncf * 16 * nv;
-  const bool act = v < nv;
-  const int o = nl * VD2_ST + v;
-  FT rho = FT(1);
-  if (act) {
-    rho = gY[(0 * 16 + n) * nv + v];
-    FT kh;
-    if (D.mode == 2) {
-      kh = D.kdec[v];
-    } else {
-      const FT u1 = gY[(1 * 16 + n) * nv + v], u2 = gY[(2 * 16 + n) * nv + v], re = gY[(3 * 16 + n) * nv + v];
-      const FT* gf = Yf + (size_t)h * 16 * nf + (size_t)n * nf;
-      const FT K = kinetic(hg, V, u1, u2, gf[v], gf[v + 1], n, v);
-      const Pt<FT> t = thermo(P, rho, re, K, V.phic[v]);
-      const FT a = gY[(1 * 16 + n) * nv], b = gY[(2 * 16 + n) * nv];  // Fields.level(ᶜuₕ, 1)
-      const FT g11 = hg[HG_GI11 * 16 + n], g12 = hg[HG_GI12 * 16 + n], g22 = hg[HG_GI22 * 16 + n];
-      const FT nrm = sqrt((a * (g11 * a + g12 * b) + b * (g12 * a + g22 * b)) * V.sc2i[0]);
-      const FT KE = D.ce_za * nrm;
-      const FT p = rho * P.R_d * t.T;
-      const FT x = (FT(85000) - p) / FT(10000);
-      kh = p > FT(85000) ? KE : KE * exp_(-(x * x));
-    }
-    s_rho[o] = rho; s_kh[o] = kh;
-  }
-  __syncthreads();
-  FT* gj = jacd + (size_t)h * JD_N * 16 * nf;
-  const size_t pl = (size_t)16 * nf, og = (size_t)n * nf + v;
-  if (v < nf) {
-    FT w = FT(0);
-    if (v > 0 && v < nv) {
-      const FT rf = FT(0.5) * (s_rho[o - 1] + s_rho[o]);
-      const FT ik = FT(0.5) * (FT(1) / fmax_(s_kh[o - 1], D.eps) + FT(1) / fmax_(s_kh[o], D.eps));
-      w = dtg * (V.dzf[v] * V.g33f[v] / V.sf2i[v]) * (rf / ik);
-    }
-    gj[JD_PW * pl + og] = w;
-    gj[JD_IRHO * pl + og] = act ? FT(1) / rho : FT(0);
-  }
-}
 
 // Thomas algorithm that leaves the matrix untouched: c' goes to cpw, the solution overwrites x (same operation order as the
 // oracle's _tri_solve).
@@ -489,187 +382,7 @@ __global__ void __launch_bounds__(NT) k_ldiv_diff(Par<FT> P, VDiff<FT> D, const 
   VD_FOR_POINTS(n, v) { if (v < nv) gdc[(3 * 16 + n) * nv + v] = ye[n * LVP + v]; }
 }
 
-// Parallel cyclic reduction of the 16 tridiagonal systems of an element in the slab layout (row i of column n at n·LVP + i), by all NT
-// threads: log₂ n elimination steps with strides 1, 2, 4, …; each step every row eliminates its two neighbours at the current stride
-//   r₋ = aᵢ/bᵢ₋ₛ, r₊ = cᵢ/bᵢ₊ₛ:  a′ = −r₋aᵢ₋ₛ, c′ = −r₊cᵢ₊ₛ, b′ = bᵢ − r₋cᵢ₋ₛ − r₊aᵢ₊ₛ, d′ = dᵢ − r₋dᵢ₋ₛ − r₊dᵢ₊ₛ
-// (rows outside [0, n) act as identity rows), then x = d/b.  (l, d, u) are left untouched — the matrix is copied into the work slabs
-// (wa, wb, wc) — and x holds the right-hand side on entry, the solution on exit.  Contains block barriers; starts and ends with one.
-// The systems here are strictly diagonally dominant (−I plus dtγ × a diffusion or acoustic operator), so no pivoting is needed.
-template <class FT>
-__device__ __forceinline__ void pcr_slab(const FT* l, const FT* d, const FT* u, FT* x, int n, FT* wa, FT* wb, FT* wc) {
-  __syncthreads();
-  for (int k = 0; k < NIT; ++k) {
-    const int idx = threadIdx.x + k * NT, o = (idx >> 6) * LVP + (idx & 63);
-    if ((idx & 63) < n) { wa[o] = l[o]; wb[o] = d[o]; wc[o] = u[o]; }
-  }
-  __syncthreads();
-  for (int s = 1; s < n; s <<= 1) {
-    FT na[NIT], nb[NIT], nc[NIT], nd[NIT];
-    for (int k = 0; k < NIT; ++k) {
-      const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
-      na[k] = nc[k] = nd[k] = FT(0); nb[k] = FT(1);
-      if (i < n) {
-        FT A = FT(0), B = wb[o], C = FT(0), Dd = x[o];
-        if (i - s >= 0) { const FT r = wa[o] / wb[o - s]; A = -r * wa[o - s]; B -= r * wc[o - s]; Dd -= r * x[o - s]; }
-        if (i + s < n) { const FT r = wc[o] / wb[o + s]; C = -r * wc[o + s]; B -= r * wa[o + s]; Dd -= r * x[o + s]; }
-        na[k] = A; nb[k] = B; nc[k] = C; nd[k] = Dd;
-      }
-    }
-    __syncthreads();
-    for (int k = 0; k < NIT; ++k) {
-      const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
-      if (i < n) { wa[o] = na[k]; wb[o] = nb[k]; wc[o] = nc[k]; x[o] = nd[k]; }
-    }
-    __syncthreads();
-  }
-  for (int k = 0; k < NIT; ++k) {
-    const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
-    if (i < n) x[o] = x[o] / wb[o];
-  }
-  __syncthreads();
-}
 
-// k_ldiv_diff with every Thomas sweep (16 of the 256 threads, 2n dependent steps) replaced by pcr_slab (all threads, log₂ n steps).
-// Same algorithm and data flow; results differ from k_ldiv_diff by round-off only.  B200_LDIV_DIFF=2 (not yet run on a B200).
-template <class FT>
-__global__ void __launch_bounds__(NT) k_ldiv_diff2(Par<FT> P, VDiff<FT> D, const VLev<FT>* __restrict__ vlev,
-                                                  const FT* __restrict__ jac, const FT* __restrict__ jacd,
-                                                  const FT* __restrict__ Rc, const FT* __restrict__ Rf, FT* dYc, FT* dYf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB);   // T (faces)
-  FT* pl_ = sm.take(SLAB); FT* pd = sm.take(SLAB); FT* pu = sm.take(SLAB);  // (uₕ,uₕ) / tracer blocks, then P (faces)
-  FT* el = sm.take(SLAB); FT* ed = sm.take(SLAB); FT* eu = sm.take(SLAB);   // A_ee (centres)
-  FT* fac = sm.take(SLAB);                                                  // m/(m − 1) (centres)
-  FT* zz = sm.take(SLAB);                                                   // centre scratch
-  FT* wa = sm.take(SLAB); FT* wb = sm.take(SLAB); FT* wc = sm.take(SLAB);   // PCR working copy of the matrix
-  FT* rr = sm.take(SLAB); FT* r1 = sm.take(SLAB); FT* r2 = sm.take(SLAB); FT* re = sm.take(SLAB);
-  FT* ye = sm.take(SLAB); FT* b3 = sm.take(SLAB); FT* x3 = sm.take(SLAB); FT* r3 = sm.take(SLAB);
-  FT* pw = sm.take(SLAB); FT* ir = sm.take(SLAB);
-  FT* s_rmc = sm.take(LV);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
-  const FT* gd = jacd + (size_t)h * JD_N * 16 * nf;
-  const size_t pl = (size_t)16 * nf;
-  const FT* gRc = Rc + (size_t)h * P.ncf * 16 * nv;
-  const FT* gRf = Rf + (size_t)h * 16 * nf;
-  FT* gdc = dYc + (size_t)h * P.ncf * 16 * nv;
-  FT* gdf = dYf + (size_t)h * 16 * nf;
-  if (threadIdx.x < LV) s_rmc[threadIdx.x] = vlev->rmc[threadIdx.x];
-  load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
-  load_slab(pw, gd + JD_PW * pl, nf); load_slab(ir, gd + JD_IRHO * pl, nf);
-  load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
-  __syncthreads();
-  // ---- A_ee, the factor 1 + 1/d_ee, and the (uₕ,uₕ) block dtγ Diag(1/ρ)⋅D − I (:1252-1258)
-  VD_FOR_POINTS(n, v) {
-    if (v >= nv) continue;
-    const int o = n * LVP + v;
-    const FT lo = v > 0 ? pw[o] * s_rmc[v] : FT(0), hi = v < nv - 1 ? pw[o + 1] * s_rmc[v] : FT(0);
-    const FT dg = -(lo + hi);
-    const FT m = dg * (D.cpcv * ir[o]);
-    el[o] = v > 0 ? lo * (D.cpcv * ir[o - 1]) : FT(0);
-    ed[o] = m - FT(1);
-    eu[o] = v < nv - 1 ? hi * (D.cpcv * ir[o + 1]) : FT(0);
-    fac[o] = m / (m - FT(1));
-    pl_[o] = lo * ir[o]; pd[o] = dg * ir[o] - FT(1); pu[o] = hi * ir[o];
-    ye[o] = re[o];
-  }
-  __syncthreads();
-  // ---- uₕ (exact tridiagonal solves or the −I fallback) and y_e = A_ee⁻¹ R_ρe
-  if (D.momentum) {
-    pcr_slab(pl_, pd, pu, r1, nv, wa, wb, wc);
-    pcr_slab(pl_, pd, pu, r2, nv, wa, wb, wc);
-  } else {
-    VD_FOR_POINTS(n, v) { if (v < nv) { int o = n * LVP + v; r1[o] = -r1[o]; r2[o] = -r2[o]; } }
-  }
-  pcr_slab(el, ed, eu, ye, nv, wa, wb, wc);
-  VD_FOR_POINTS(n, v) {
-    if (v < nv) { gdc[(1 * 16 + n) * nv + v] = r1[n * LVP + v]; gdc[(2 * 16 + n) * nv + v] = r2[n * LVP + v]; }
-  }
-  // ---- passive tracers: (ρχ,ρχ) = dtγ D⋅Diag(1/ρ) − I (:1190-1195), exact tridiagonal solve
-  for (int q = 4; q < P.ncf; ++q) {
-    __syncthreads();
-    VD_FOR_POINTS(n, v) {
-      if (v >= nv) continue;
-      const int o = n * LVP + v;
-      const FT lo = v > 0 ? pw[o] * s_rmc[v] : FT(0), hi = v < nv - 1 ? pw[o + 1] * s_rmc[v] : FT(0);
-      pl_[o] = v > 0 ? lo * ir[o - 1] : FT(0); pd[o] = -(lo + hi) * ir[o] - FT(1); pu[o] = v < nv - 1 ? hi * ir[o + 1] : FT(0);
-      zz[o] = gRc[(size_t)(q * 16 + n) * nv + v];
-    }
-    __syncthreads();
-    pcr_slab(pl_, pd, pu, zz, nv, wa, wb, wc);
-    __syncthreads();
-    VD_FOR_POINTS(n, v) { if (v < nv) gdc[(size_t)(q * 16 + n) * nv + v] = zz[n * LVP + v]; }
-  }
-  __syncthreads();
-  // ---- Schur right-hand side b₃ = R₃ + A₃ρR_ρ − A₃e y_e − A₃ₕ xₕ  and the preconditioner P
-  VD_FOR_POINTS(n, f) {
-    if (f >= nf) continue;
-    const size_t o = (size_t)n * nf + f;
-    const int s = n * LVP + f;
-    FT rhs = gRf[o];
-    FT l = sl[s], d = sd[s], u = su[s];
-    if (f > 0 && f < nv) {
-      const FT ue_lo = gj[JC_UE_LO * pl + o], ue_hi = gj[JC_UE_HI * pl + o];
-      rhs += gj[JC_UR_LO * pl + o] * rr[s - 1] + gj[JC_UR_HI * pl + o] * rr[s];
-      rhs -= ue_lo * ye[s - 1] + ue_hi * ye[s];
-      rhs -= gj[JC_U1_LO * pl + o] * r1[s - 1] + gj[JC_U1_HI * pl + o] * r1[s];
-      rhs -= gj[JC_U2_LO * pl + o] * r2[s - 1] + gj[JC_U2_HI * pl + o] * r2[s];
-      const FT a = ue_lo * fac[s - 1], b = ue_hi * fac[s];
-      l -= a * gj[JC_EU_LO * pl + o - 1];
-      d -= a * gj[JC_EU_HI * pl + o - 1] + b * gj[JC_EU_LO * pl + o];
-      u -= b * gj[JC_EU_HI * pl + o];
-    }
-    b3[s] = rhs; x3[s] = rhs;
-    pl_[s] = l; pd[s] = d; pu[s] = u;
-  }
-  __syncthreads();
-  pcr_slab(pl_, pd, pu, x3, nf, wa, wb, wc);  // x[0] = P⁻¹ b
-  __syncthreads();
-  for (int it = 0; it < D.n_iters; ++it) {
-    VD_FOR_POINTS(n, v) {  // y = A_e3 x
-      if (v >= nv) continue;
-      const size_t o = (size_t)n * nf + v;
-      const int s = n * LVP + v;
-      FT y = gj[JC_EU_LO * pl + o] * x3[s] + gj[JC_EU_HI * pl + o] * x3[s + 1];
-      ye[s] = y; zz[s] = y;
-    }
-    __syncthreads();
-    pcr_slab(el, ed, eu, zz, nv, wa, wb, wc);
-    __syncthreads();
-    VD_FOR_POINTS(n, f) {  // r = b − S x
-      if (f >= nf) continue;
-      const size_t o = (size_t)n * nf + f;
-      const int s = n * LVP + f;
-      FT tx = sd[s] * x3[s];
-      if (f > 0) tx += sl[s] * x3[s - 1];
-      if (f < nv) tx += su[s] * x3[s + 1];
-      FT r = b3[s] - tx;
-      if (f > 0 && f < nv) r += gj[JC_UE_LO * pl + o] * (zz[s - 1] + ye[s - 1]) + gj[JC_UE_HI * pl + o] * (zz[s] + ye[s]);
-      r3[s] = r;
-    }
-    __syncthreads();
-    pcr_slab(pl_, pd, pu, r3, nf, wa, wb, wc);
-    __syncthreads();
-    VD_FOR_POINTS(n, f) { if (f < nf) x3[n * LVP + f] += r3[n * LVP + f]; }
-    __syncthreads();
-  }
-  // ---- x₁ = A₁₁⁻¹(b₁ − A₁₂x₂)
-  VD_FOR_POINTS(n, v) {
-    const int s = n * LVP + v;
-    const size_t o = (size_t)n * nf + v;
-    if (v < nf) gdf[o] = x3[s];
-    if (v < nv) {
-      const FT x0 = x3[s], x1 = x3[s + 1];
-      gdc[(0 * 16 + n) * nv + v] = gj[JC_RU_LO * pl + o] * x0 + gj[JC_RU_HI * pl + o] * x1 - rr[s];
-      ye[s] = re[s] - (gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1);
-    }
-  }
-  __syncthreads();
-  pcr_slab(el, ed, eu, ye, nv, wa, wb, wc);
-  __syncthreads();
-  VD_FOR_POINTS(n, v) { if (v < nv) gdc[(3 * 16 + n) * nv + v] = ye[n * LVP + v]; }
-}
 
 // ---------------------------------------------------------------------------------------------
 // lim!, second branch (src/prognostic_equations/limited_tendencies.jl:95-121): ClimaCore Limiters.VerticalMassBorrowingLimiter((0,))
@@ -736,7 +449,7 @@ __device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, c
   if (v < nv) {
     FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
     Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
-    S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = t.phir; S.T[o] = t.T;
+    S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = pgf_aux(t); S.T[o] = t.T;
   }
   __syncthreads();
 }
@@ -817,6 +530,46 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
     for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
   }
   if (v < nf) gF[n * nf + v] = FT(0);
+}
+
+// Parallel cyclic reduction of the 16 tridiagonal systems of an element in the slab layout (row i of column n at n·LVP + i), by all NT
+// threads: log₂ n elimination steps with strides 1, 2, 4, …; each step every row eliminates its two neighbours at the current stride
+//   r₋ = aᵢ/bᵢ₋ₛ, r₊ = cᵢ/bᵢ₊ₛ:  a′ = −r₋aᵢ₋ₛ, c′ = −r₊cᵢ₊ₛ, b′ = bᵢ − r₋cᵢ₋ₛ − r₊aᵢ₊ₛ, d′ = dᵢ − r₋dᵢ₋ₛ − r₊dᵢ₊ₛ
+// (rows outside [0, n) act as identity rows), then x = d/b.  (l, d, u) are left untouched — the matrix is copied into the work slabs
+// (wa, wb, wc) — and x holds the right-hand side on entry, the solution on exit.  Contains block barriers; starts and ends with one.
+// The systems here are strictly diagonally dominant (−I plus dtγ × a diffusion or acoustic operator), so no pivoting is needed.
+template <class FT>
+__device__ __forceinline__ void pcr_slab(const FT* l, const FT* d, const FT* u, FT* x, int n, FT* wa, FT* wb, FT* wc) {
+  __syncthreads();
+  for (int k = 0; k < NIT; ++k) {
+    const int idx = threadIdx.x + k * NT, o = (idx >> 6) * LVP + (idx & 63);
+    if ((idx & 63) < n) { wa[o] = l[o]; wb[o] = d[o]; wc[o] = u[o]; }
+  }
+  __syncthreads();
+  for (int s = 1; s < n; s <<= 1) {
+    FT na[NIT], nb[NIT], nc[NIT], nd[NIT];
+    for (int k = 0; k < NIT; ++k) {
+      const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
+      na[k] = nc[k] = nd[k] = FT(0); nb[k] = FT(1);
+      if (i < n) {
+        FT A = FT(0), B = wb[o], C = FT(0), Dd = x[o];
+        if (i - s >= 0) { const FT r = wa[o] / wb[o - s]; A = -r * wa[o - s]; B -= r * wc[o - s]; Dd -= r * x[o - s]; }
+        if (i + s < n) { const FT r = wc[o] / wb[o + s]; C = -r * wc[o + s]; B -= r * wa[o + s]; Dd -= r * x[o + s]; }
+        na[k] = A; nb[k] = B; nc[k] = C; nd[k] = Dd;
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < NIT; ++k) {
+      const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
+      if (i < n) { wa[o] = na[k]; wb[o] = nb[k]; wc[o] = nc[k]; x[o] = nd[k]; }
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < NIT; ++k) {
+    const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
+    if (i < n) x[o] = x[o] / wb[o];
+  }
+  __syncthreads();
 }
 
 // k_ldiv with the 16-lane Thomas sweep replaced by parallel cyclic reduction over all threads (pcr_slab); round-off differences only.
@@ -934,7 +687,7 @@ __global__ void __launch_bounds__(NT) k_imp_stage_diff(Par<FT> P, VDiff<FT> D, c
   if (cen) {
     FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
     Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
-    S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = t.phir; S.T[o] = t.T;
+    S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = pgf_aux(t); S.T[o] = t.T;
   }
   __syncthreads();
   // ---- eddy diffusivity → zz

@@ -42,4 +42,39 @@ __device__ __forceinline__ Pt2<FT> thermo2(const Par<FT>& P, P2<FT> rho, P2<FT> 
   return o;
 }
 
+// Packed form of pgf_aux / pgf_diff (common.cuh): Float32 evaluates ΔΠ and ΔΦ_r between adjacent levels in difference form from
+// κ·log(p_hi/p_lo); Float64 keeps the literal differences.  expm1 by its Taylor series (|Δ| ≲ 0.35 for any grid with Δz ≤ 8 km:
+// the x¹⁰/10! remainder is < 10⁻¹¹).
+template <class FT> __device__ __forceinline__ P2<FT> pgf_aux2(const Pt2<FT>& t);
+template <> __device__ __forceinline__ P2<double> pgf_aux2<double>(const Pt2<double>& t) { return t.phir; }
+template <> __device__ __forceinline__ P2<float> pgf_aux2<float>(const Pt2<float>& t) { return t.p; }
+__device__ __forceinline__ void pgf_diff2(const Par<double>&, P2<double> Pilo, P2<double> Pihi, P2<double> qlo, P2<double> qhi,
+                                          P2<double>& dPi, P2<double>& dphr) {
+  dPi = Pihi - Pilo; dphr = qhi - qlo;
+}
+__device__ __forceinline__ void pgf_diff2(const Par<float>& P, P2<float> Pilo, P2<float> /*Pihi*/, P2<float> plo, P2<float> phi,
+                                          P2<float>& dPi, P2<float>& dphr) {
+  using V = P2<float>;
+  const V dl = logp(phi * rcpn2(plo)) * P.kappa;
+  V e = fma2(dl, V(1.0f / 362880.0f), V(1.0f / 40320.0f));  // expm1(x) = x(1 + x/2 + x²/6 + … + x⁸/9!)
+  e = fma2(e, dl, V(1.0f / 5040.0f));
+  e = fma2(e, dl, V(1.0f / 720.0f));
+  e = fma2(e, dl, V(1.0f / 120.0f));
+  e = fma2(e, dl, V(1.0f / 24.0f));
+  e = fma2(e, dl, V(1.0f / 6.0f));
+  e = fma2(e, dl, V(0.5f));
+  e = fma2(e, dl, V(1.0f));
+  e = e * dl;
+  dPi = Pilo * e;
+  V q = e + 7.0f;  // (1 + e)⁷ − 1 = e(7 + 21e + 35e² + 35e³ + 21e⁴ + 7e⁵ + e⁶)
+  q = fma2(q, e, V(21.0f));
+  q = fma2(q, e, V(35.0f));
+  q = fma2(q, e, V(35.0f));
+  q = fma2(q, e, V(21.0f));
+  q = fma2(q, e, V(7.0f));
+  const V x2 = Pilo * Pilo, x4 = x2 * x2;
+  const V d7 = ((x4 * x2) * Pilo) * (q * e);
+  dphr = fma2(dl, V(P.Tmin_ref), d7 * P.dTs7) * (-P.cp_d);
+}
+
 }  // namespace b200

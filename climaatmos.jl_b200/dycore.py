@@ -152,45 +152,49 @@ class AtmosSimulation:
         if precomputed:
             for k, v in precomputed.items():
                 setattr(cp, k, v.data_ptr())
-        capi.check(self.lib.b200_cache_imp(self.ctx, _p(Y.c), _p(Y.f), C.byref(cp), self._stream()), "b200_cache_imp")
+        capi.check(self.lib.b200_cache_imp(self.ctx, _p(Y.c), _p(Y.f), C.byref(cp), self._stream()), "b200_cache_imp", self.ctx)
 
     def remaining_tendency(self, Yt, Yt_lim, Y, t=0.0):
         """T_exp_T_lim! (remaining_tendency.jl:48-58)."""
         capi.check(self.lib.b200_t_exp_lim(self.ctx, _p(Yt.c), _p(Yt.f), _p(Yt_lim.c) if Yt_lim else None,
                                            _p(Yt_lim.f) if Yt_lim else None, _p(Y.c), _p(Y.f), float(t), self._stream()),
-                   "b200_t_exp_lim")
+                   "b200_t_exp_lim", self.ctx)
         return Yt
 
     def remaining_tendency_phase(self, phase, Yt, Y):
         """Profiling aid: one phase of T_exp_T_lim! (0 pre-DSS kernel, 1 DSS of ∇² fields, 2 hyperdiffusion apply)."""
         capi.check(self.lib.b200_t_exp_phase(self.ctx, int(phase), _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), self._stream()),
-                   "b200_t_exp_phase")
+                   "b200_t_exp_phase", self.ctx)
 
     def remaining_tendency_phase_a(self, Yt, Y):
         self.remaining_tendency_phase(0, Yt, Y)
+
+    def remaining_tendency_phase_c(self, Yt, Y):
+        """Hyperdiffusion apply kernel alone (uses the ∇² fields left by the last phase 0 / phase 1 of this context)."""
+        self.remaining_tendency_phase(2, Yt, Y)
 
     def implicit_stage(self, N, U, dtgamma):
         """Fused implicit stage (one Newton iteration of the CTS stage solve, integrator.jl:63-120): N ← U − J⁻¹R(U)
         plus the T_post_imp! correction, out of place."""
         capi.check(self.lib.b200_implicit_stage(self.ctx, _p(N.c), _p(N.f), _p(U.c), _p(U.f), float(dtgamma), self._stream()),
-                   "b200_implicit_stage")
+                   "b200_implicit_stage", self.ctx)
 
     def implicit_tendency(self, Yt, Y, t=0.0):
         """T_imp! (implicit_tendency.jl:36-98)."""
-        capi.check(self.lib.b200_t_imp(self.ctx, _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), float(t), self._stream()), "b200_t_imp")
+        capi.check(self.lib.b200_t_imp(self.ctx, _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), float(t), self._stream()), "b200_t_imp", self.ctx)
 
     def update_jacobian(self, Y, dtgamma, t=0.0):
         """Wfact (jacobian.jl:74-75)."""
-        capi.check(self.lib.b200_wfact(self.ctx, _p(Y.c), _p(Y.f), float(dtgamma), float(t), self._stream()), "b200_wfact")
+        capi.check(self.lib.b200_wfact(self.ctx, _p(Y.c), _p(Y.f), float(dtgamma), float(t), self._stream()), "b200_wfact", self.ctx)
 
     def ldiv(self, dY, R):
         """ldiv!(ΔY, jacobian, R) (jacobian.jl:78-82)."""
-        capi.check(self.lib.b200_ldiv(self.ctx, _p(dY.c), _p(dY.f), _p(R.c), _p(R.f), self._stream()), "b200_ldiv")
+        capi.check(self.lib.b200_ldiv(self.ctx, _p(dY.c), _p(dY.f), _p(R.c), _p(R.f), self._stream()), "b200_ldiv", self.ctx)
 
     def correct_implicit_advection_tendency(self, Yt, Y, t=0.0):
         """T_post_imp! (implicit_tendency.jl:322-339)."""
         capi.check(self.lib.b200_t_post_imp(self.ctx, _p(Yt.c), _p(Yt.f), _p(Y.c), _p(Y.f), float(t), self._stream()),
-                   "b200_t_post_imp")
+                   "b200_t_post_imp", self.ctx)
 
     def dss(self, Y, t=0.0):
         """dss! (constrain_state.jl:59-64): weighted DSS of Y.c (uₕ as a Covariant12 vector) and Y.f."""
@@ -203,7 +207,7 @@ class AtmosSimulation:
         nf = (C.c_int32 * n)(*[f[1] for f in fields])
         isf = (C.c_int32 * n)(*[f[2] for f in fields])
         kind = (C.c_int32 * n)(*[f[3] for f in fields])
-        capi.check(self.lib.b200_dss(self.ctx, ptrs, nf, isf, kind, n, self._stream()), "b200_dss")
+        capi.check(self.lib.b200_dss(self.ctx, ptrs, nf, isf, kind, n, self._stream()), "b200_dss", self.ctx)
 
     def constrain_state(self, Y, t=0.0):
         """constrain_state! (constrain_state.jl:34-39): no-op for dry / non-EDMF configurations."""
@@ -211,7 +215,7 @@ class AtmosSimulation:
     def limiters_func(self, Y, t, ref_Y):
         """lim!(Y, p, t, ref_Y) (limited_tendencies.jl:64-122): SEM quasi-monotone limiter of the tracers of Y with bounds from
         ref_Y; the reference's no-op when no limiter is configured (defaults)."""
-        capi.check(self.lib.b200_lim(self.ctx, _p(Y.c), _p(Y.f), _p(ref_Y.c), _p(ref_Y.f), float(t), self._stream()), "b200_lim")
+        capi.check(self.lib.b200_lim(self.ctx, _p(Y.c), _p(Y.f), _p(ref_Y.c), _p(ref_Y.f), float(t), self._stream()), "b200_lim", self.ctx)
 
     def initialize_implicit_stage_problem(self, Y, dtgamma):
         """initialize_imp! (initialize_implicit_problem.jl:33-57): no-op unless PrognosticEDMFX."""
@@ -219,7 +223,7 @@ class AtmosSimulation:
     # ------------------------------------------------------------------ stepping (CTS.step!)
     def step(self, fused=True):
         capi.check(self.lib.b200_step_ars343(self.ctx, _p(self.Y.c), _p(self.Y.f), float(self.t), int(fused), self._stream()),
-                   "b200_step_ars343")
+                   "b200_step_ars343", self.ctx)
         self.t += self.dt
 
 

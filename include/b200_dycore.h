@@ -7,7 +7,7 @@
  *     (`pointer(parent(Fields.field_values(Y.c)))`), never retained beyond the call unless
  *     registered at create time; `stream` is a cudaStream_t passed as void*;
  *   - every call is asynchronous on `stream`; no hidden device synchronisation;
- *   - return 0 on success, <0 on error (message via b200_last_error); nothing throws;
+ *   - return 0 on success, <0 on error (message via b200_last_error(ctx), per context); nothing throws;
  *   - FT is selected at create time (ft_bytes = 4 or 8); state pointers are FT*;
  *   - field layout is ClimaCore VIJFH: parent array (Nv, Ni, Nj, Nf, Nh), first index fastest,
  *     i.e. C order [h][f][j][i][v].  Y.c: Nf = 4 (ρ, uₕ₁, uₕ₂, ρe_tot), Nv levels;
@@ -112,7 +112,8 @@ int b200_create(b200_ctx** out, const b200_dims*, const b200_geometry*, const b2
                 const b200_params*, const void* nccl_unique_id /* NULL for 1 GPU */, int rank,
                 int nranks);
 int b200_destroy(b200_ctx*);
-const char* b200_last_error(void);
+/* Message of the last failing call on `ctx`; ctx == NULL: the calling thread's last message (b200_create failures). */
+const char* b200_last_error(const b200_ctx* ctx);
 /* 128-byte NCCL unique id for the DSS halo communicator (rank 0 calls, host broadcasts). */
 int b200_nccl_unique_id(void* out128);
 

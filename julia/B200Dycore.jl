@@ -64,7 +64,7 @@ mutable struct Ctx
     keep::Any   # host arrays handed to b200_create (it copies them; kept only until create returns)
 end
 
-check(rc, what) = rc == 0 || error("$what: " * unsafe_string(ccall((:b200_last_error, lib), Cstring, ())))
+check(rc, what, ctx = C_NULL) = rc == 0 || error("$what: " * unsafe_string(ccall((:b200_last_error, lib), Cstring, (Ptr{Cvoid},), ctx)))
 # VIJFH parent array of a field on the device: (Nv, 4, 4, Nf, Nh), level fastest
 dptr(f) = reinterpret(Ptr{Cvoid}, pointer(parent(Fields.field_values(f))))
 stream() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)

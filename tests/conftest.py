@@ -18,3 +18,16 @@ def lib():
 
     capi.build()
     return capi.load()
+
+
+def record_parity(name, row):
+    """Append one measured-parity row to gpurun_out/parity_report.jsonl (evidence copied under profiles/ per round); never fails a test."""
+    import json
+
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=name, **row)) + "\n")
+    except Exception:
+        pass

@@ -39,7 +39,7 @@ inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
 #include "kernels_implicit.cuh"
-#include "kernels_reg.cuh"
+#include "kernels_row.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
 

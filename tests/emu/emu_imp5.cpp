@@ -52,6 +52,6 @@ extern "C" __attribute__((visibility("default"))) int emu_imp5(int nh, int nv, c
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
-  run_grid(nh, [&] { k5_imp_stage<FT, 2, 0, 2>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  run_grid(nh, [&] { k5_imp_stage<FT, 0>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
   return 0;
 }

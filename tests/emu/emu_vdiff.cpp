@@ -1,4 +1,4 @@
-// CPU emulation of single CTAs running the vertical-diffusion kernels of climaatmos.jl_b200/csrc/kernels_vdiff.cuh (and k_wfact, whose
+// CPU emulation of single CTAs running the vertical-diffusion kernels of climaatmos.jl_b200/csrc/kernels_vdiff.cuh (and k_wfact2, whose
 // planes k_ldiv_diff consumes) — the kernel source is compiled unchanged by g++ against the stub cuda_runtime.h in this directory;
 // 256 host threads play the threads of a block.  Test infrastructure only (tests/test_kernels_cpu_emulation.py): it checks
 // indexing, barriers-as-phases and arithmetic of the kernels against the oracle when no GPU is at hand.  It is NOT a product path.
@@ -39,7 +39,7 @@ static void run_grid(int nblocks, F&& body) {
   for (auto& x : th) x.join();
 }
 
-// sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ, tendency kernel (1|2), [16] unused here, [17] ldiv kernel (1 Thomas | 2 PCR)
+// sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ, [15]-[17] unused here
 // vl: [11][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw ; hgeo: [nh][HG_N][16] ; kdec [64]
 extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, int ncf, const double* sc, const FT* vl, const FT* hgeo, const FT* kdec,
                          const FT* Yc, const FT* Yf, const FT* Rc, const FT* Rf, FT* Ytc, FT* jac,
@@ -57,13 +57,10 @@ extern "C" __attribute__((visibility("default"))) int emu_vdiff(int nh, int nv, 
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
-  if ((int)sc[15] == 2) run_grid(nh * 4, [&] { k_vdiff_tend2<FT>(P, D, hgeo, &V, Yc, Yf, Ytc); });
-  else run_grid(nh, [&] { k_vdiff_tend<FT>(P, D, hgeo, &V, Yc, Yf, Ytc); });
-  run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
-  if ((int)sc[17] == 2) run_grid(nh * 4, [&] { k_vdiff_jac2<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
-  else run_grid(nh, [&] { k_vdiff_jac<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
-  if ((int)sc[17] == 2) run_grid(nh, [&] { k_ldiv_diff2<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
-  else run_grid(nh, [&] { k_ldiv_diff<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
+  run_grid(nh * 4, [&] { k_vdiff_tend2<FT>(P, D, hgeo, &V, Yc, Yf, Ytc); });
+  run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+  run_grid(nh, [&] { k_vdiff_jac<FT>(P, D, hgeo, &V, Yc, Yf, dtg, jacd); });
+  run_grid(nh, [&] { k_ldiv_diff<FT>(P, D, &V, jac, jacd, Rc, Rf, dYc, dYf); });
   return 0;
 }
 
@@ -90,9 +87,9 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
   return 0;
 }
 
-// The dry hook kernels of kernels_implicit.cuh (validated on the B200; emulated here so that the CPU test tier exercises the
-// product source too): cache_imp! → T_imp! → Wfact → ldiv! → T_post_imp!, and the fused k_imp_stage on a copy of the state.
-// sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3), sc[17] = hook kernel generation (1 | 2).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
+// The dry hook kernels (k_cache_imp of kernels_implicit.cuh; k_t_imp2, k_wfact2, k_ldiv2, k_t_post_imp2 of kernels_vdiff.cuh; validated
+// on the B200, emulated here so that the CPU test tier exercises the product source too): cache_imp! → T_imp! → Wfact → ldiv! → T_post_imp!.
+// sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3).  Sc/Sf are unused (kept for the call signature).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
 // Ytc/Ytf (T_imp), dYc/dYf (ldiv of Rc/Rf), Ypc (T_post_imp centres), Sc/Sf (state after the fused stage).
 extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, int ncf, const double* sc, const FT* vl,
                                                                 const FT* hgeo, const FT* Yc, FT* Yf, const FT* Rc,
@@ -110,21 +107,11 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
   run_grid(nh, [&] { k_cache_imp<FT>(P, hgeo, &V, Yc, Yf, (FT*)nullptr, (FT*)nullptr, Kc, Tc, pc, hc); });
-  if ((int)sc[17] == 2) {  // second generation (quarter element per CTA; PCR)
-    run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
-    run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
-    run_grid(nh, [&] { k_ldiv2<FT>(P, jac, Rc, Rf, dYc, dYf); });
-    run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
-  } else {
-    run_grid(nh, [&] { k_t_imp<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
-    run_grid(nh, [&] { k_wfact<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
-    run_grid(nh, [&] { k_ldiv<FT>(P, jac, Rc, Rf, dYc, dYf); });
-    run_grid(nh, [&] { k_t_post_imp<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
-  }
-  const size_t nc = (size_t)nh * ncf * 16 * nv, nf = (size_t)nh * 16 * (nv + 1);
-  memcpy(Sc, Yc, nc * sizeof(FT));
-  memcpy(Sf, Yf, nf * sizeof(FT));
-  run_grid(nh, [&] { k_imp_stage<FT>(P, hgeo, &V, Sc, Sf, dtg); });
+  run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+  run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+  run_grid(nh, [&] { k_ldiv2<FT>(P, jac, Rc, Rf, dYc, dYf); });
+  run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  (void)Sc; (void)Sf;
   return 0;
 }
 

@@ -149,9 +149,6 @@ def test_step_with_vertical_diffusion_matches_oracle(FT, implicit):
     sim2.close()
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
-                    reason="k_lim_vborrow was written after the round's GPU budget was spent: it matches the oracle bit for bit in the CPU "
-                           "CTA emulator (tests/test_kernels_cpu_emulation.py) but has not run on a B200 yet (set B200_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_vertical_mass_borrowing_limiter_matches_oracle(FT):
     """lim! with tracer_nonnegativity_method: vertical_water_borrowing (limited_tendencies.jl:95-121) through b200_lim, and a step."""
@@ -181,48 +178,11 @@ def test_vertical_mass_borrowing_limiter_matches_oracle(FT):
     sim.close()
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
-                    reason="k_vdiff_jac2 / k_ldiv_diff2 (B200_LDIV_DIFF=2) match the oracle in the CPU CTA emulator but have not run on a B200 yet "
-                           "(set B200_RUN_UNVALIDATED=1)")
-@pytest.mark.parametrize("FT", [np.float64, np.float32])
-def test_pcr_variant_of_the_iterative_solve(FT, monkeypatch):
-    """B200_LDIV_DIFF=2: Wfact planes from k_vdiff_jac2 and ldiv! by parallel cyclic reduction (k_ldiv_diff2), against the oracle and a step."""
-    monkeypatch.setenv("B200_LDIV_DIFF", "2")
-    sim, o, Yc, Yf, rng = make(FT, "VerticalDiffusion", True)
-    Y = sim.to_device(Yc, Yf)
-    pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
-    dtg = sim.dt * 0.4358665215
-    sim.update_jacobian(Y, dtg)
-    Jm = o.update_jacobian(Yc, Yf, pc, dtg)
-    Rc = (rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3).astype(FT)
-    Rf = rng.standard_normal(Yf.shape).astype(FT)
-    R = sim.to_device(Rc, Rf)
-    dY = R.zeros_like()
-    sim.ldiv(dY, R)
-    dc, df = o.ldiv(Jm, Rc, Rf)
-    gc, gf = dY.cpu()
-    t64 = FT == np.float64
-    for k in range(5):
-        assert rel(gc[:, k], dc[:, k]) <= (1e-10 if t64 else 5e-5), k
-    assert rel(gf, df) <= (1e-10 if t64 else 5e-5)
-    Yc0, Yf0 = sim.Y.cpu()
-    sim.step(fused=True)
-    torch.cuda.synchronize()
-    gc, gf = sim.Y.cpu()
-    oc, of = Oracle(sim.grid, sim.params, sim.numerics, np.float64).step(Yc0.astype(np.float64), Yf0.astype(np.float64))
-    for k in range(5):
-        assert rel(gc[:, k], oc[:, k]) <= (1e-11 if t64 else 1e-5), k
-    sim.close()
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
-                    reason="second-generation hook kernels (B200_HOOK_KERNELS=2) match the oracle in the CPU CTA emulator but have not run on a "
-                           "B200 yet (set B200_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 @pytest.mark.parametrize("ze,zmax,dzb", [(10, 30000.0, 500.0), (63, 60000.0, 30.0), (2, 10000.0, 5000.0)])
-def test_second_generation_hook_kernels(FT, ze, zmax, dzb, monkeypatch):
-    """B200_HOOK_KERNELS=2: T_imp!, Wfact + ldiv!, T_post_imp! against the oracle, and the hook-by-hook step against the fused step."""
-    monkeypatch.setenv("B200_HOOK_KERNELS", "2")
+def test_dry_hook_kernels_at_column_height_limits(FT, ze, zmax, dzb):
+    """k_t_imp2, k_wfact2 + k_ldiv2, k_t_post_imp2: T_imp!, Wfact + ldiv!, T_post_imp! against the oracle for nv = 2, 10, 63, and the hook-by-hook
+    step against the fused step."""
     P = prm.DycoreParams(zd_rayleigh=0.66 * zmax, zd_viscous=0.66 * zmax)
     sim = dycore.AtmosSimulation(FT=FT, h_elem=3, z_elem=ze, z_max=zmax, dz_bottom=dzb, dt=150.0, rayleigh_sponge=True, viscous_sponge=True, params=P)
     o = Oracle(sim.grid, P, sim.numerics, FT)
@@ -268,15 +228,11 @@ def test_second_generation_hook_kernels(FT, ze, zmax, dzb, monkeypatch):
     sim.close()
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("B200_RUN_UNVALIDATED"),
-                    reason="k_imp_stage_diff (B200_VDIFF_FUSED=1) matches the oracle's stage in the CPU CTA emulator but has not run on a B200 yet "
-                           "(set B200_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 @pytest.mark.parametrize("vd", ["DecayWithHeightDiffusion", "VerticalDiffusion"])
-def test_fused_implicit_diffusion_stage(FT, vd, monkeypatch):
-    """B200_VDIFF_FUSED=1: b200_implicit_stage with implicit diffusion as one kernel against the oracle's hook sequence, and the fused,
+def test_fused_implicit_diffusion_stage(FT, vd):
+    """k_imp_stage_diff: b200_implicit_stage with implicit diffusion as one kernel against the oracle's hook sequence, and the fused,
     graph-replayed step against the oracle and against the hook-by-hook step."""
-    monkeypatch.setenv("B200_VDIFF_FUSED", "1")
     sim, o, Yc, Yf, rng = make(FT, vd, True)
     U = sim.to_device(Yc, Yf)
     N = U.zeros_like()

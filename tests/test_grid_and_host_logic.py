@@ -180,7 +180,7 @@ def test_entry_points_reject_a_null_context(lib):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         assert fn(*args) < 0, name
-        assert name.encode() in lib.b200_last_error() and b"null context" in lib.b200_last_error()
+        assert name.encode() in lib.b200_last_error(z) and b"null context" in lib.b200_last_error(z)
     assert lib.b200_destroy(z) == 0
 
 

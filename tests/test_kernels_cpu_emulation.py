@@ -1,7 +1,7 @@
 """The CUDA kernel sources of climaatmos.jl_b200/csrc, executed on the CPU: tests/emu/ compiles the kernel headers UNCHANGED with g++
 against a stub cuda_runtime.h and runs each CTA with 256 host threads — a std::barrier for __syncthreads(), per-warp barriers and an
 exchange buffer for warp shuffles / votes / __syncwarp (emu_exp5.cpp) — and the results are compared with the oracle (Float64
-instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k5_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the hook kernels of kernels_implicit.cuh and their second generation, and
+instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k5_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_ldiv2, k_t_post_imp2), and
 the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
 Test infrastructure only: it checks indexing, phase structure and arithmetic of the very code that runs on the B200, not timing and
@@ -50,7 +50,7 @@ def emu32():
     return C.CDLL(so)
 
 
-def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12, dzb=400.0, ldiv_kernel=1):
+def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, ze=12, dzb=400.0):
     P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius, deep_atmosphere=deep)
     N = prm.DycoreNumerics(dt=250.0, vert_diff=vd, implicit_diffusion=True, approximate_linear_solve_iters=iters,
@@ -85,7 +85,7 @@ def run_case(emu, vd, deep, dm, iters, ntr, rayleigh=False, tend_kernel=1, ze=12
     kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
     mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), mode,
-                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, tend_kernel, 0, ldiv_kernel])
+                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, 0, 0, 0])
     Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
     Rf = rng.standard_normal(Yf.shape)
     Ytc = np.zeros_like(Yc)
@@ -129,18 +129,6 @@ def test_emulated_vdiff_kernels_match_oracle(emu, vd, deep, dm, iters, ntr, rayl
     assert rel(gf, of) < 1e-10, ("ldiv u3", rel(gf, of))
 
 
-@pytest.mark.parametrize("vd,deep,dm,ntr", [("DecayWithHeightDiffusion", True, False, 2), ("VerticalDiffusion", True, False, 1),
-                                            ("VerticalDiffusion", False, True, 0)])
-def test_second_generation_tendency_kernel_is_bitwise_identical(emu, vd, deep, dm, ntr):
-    """k_vdiff_tend2 (quarter element per CTA, no state slabs) performs the operations of k_vdiff_tend in the same order."""
-    (g1, _, _), (ot, _, _) = run_case(emu, vd, deep, dm, 1, ntr, tend_kernel=1)
-    (g2, _, _), _ = run_case(emu, vd, deep, dm, 1, ntr, tend_kernel=2)
-    assert np.abs(g1).max() > 0
-    assert np.array_equal(g1, g2)
-    for k in range(3 if dm else 1, g2.shape[1]):
-        assert rel(g2[:, k], ot[:, k]) < 1e-11
-
-
 def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
     """k_lim_vborrow (lim!, vertical_water_borrowing) on the CPU emulator against the oracle, bit for bit (same operation order)."""
     P = prm.DycoreParams()
@@ -162,12 +150,10 @@ def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("gen", [1, 2])
 @pytest.mark.parametrize("upw,rayleigh,deep", [("vanleer_limiter", True, True), ("first_order", False, False), ("none", False, True)])
-def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep, gen):
-    """gen 1: k_cache_imp, k_t_imp, k_wfact → k_ldiv, k_t_post_imp and the fused k_imp_stage (kernels_implicit.cuh); gen 2: k_t_imp2,
-    k_wfact2 → k_ldiv2, k_t_post_imp2 (quarter element per CTA, parallel cyclic reduction; B200_HOOK_KERNELS=2) — on the CPU emulator against
-    the oracle's cache_imp! / T_imp! / Wfact + ldiv! / T_post_imp! / one Newton iteration of the implicit stage (Float64)."""
+def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
+    """k_cache_imp, k_t_imp2, k_wfact2 → k_ldiv2, k_t_post_imp2 (quarter element per CTA, parallel cyclic reduction) on the CPU emulator
+    against the oracle's cache_imp! / T_imp! / Wfact + ldiv! / T_post_imp! (Float64)."""
     P = prm.DycoreParams(zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
     N = prm.DycoreNumerics(dt=250.0, rayleigh_sponge=rayleigh, energy_upwinding=upw)
@@ -192,7 +178,7 @@ def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep, gen):
     hgeo = np.zeros((nh, HG_N, 16))
     hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), 0, 0, 0, 0, dtg,
-                   0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw], gen])
+                   0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw], 0])
     Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
     Rf = rng.standard_normal(Yf.shape)
     z4 = lambda: np.zeros((nh, 16, nv))
@@ -221,39 +207,17 @@ def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep, gen):
     if upw != "none":  # with :none the host returns zeros without launching the kernel (capi.cu: impl_t_post)
         assert rel(Ypc[:, 3], pc_c[:, 3]) < 1e-10
     assert np.all(Ypc[:, :3] == 0) and np.all(Ypf == 0)
-    Uc, Uf = Yc.copy(), Yf.copy()
-    o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
-    for k in range(4):
-        assert rel(Sc[:, k], Uc[:, k]) < 1e-12, k
-    assert rel(Sf, Uf) < 1e-10
 
 
 @pytest.mark.parametrize("ze,dzb", [(2, 15000.0), (3, 5000.0), (63, 30.0)])
-@pytest.mark.parametrize("tend_kernel", [1, 2])
-def test_emulated_vdiff_kernels_at_the_column_height_limits(emu, ze, dzb, tend_kernel):
+def test_emulated_vdiff_kernels_at_the_column_height_limits(emu, ze, dzb):
     """Minimum (2, 3 levels) and maximum (63 levels = 64 faces, the LV = 64 limit of the slab layout) column heights."""
-    (gt, gc, gf), (ot, oc, of) = run_case(emu, "VerticalDiffusion", True, False, 2, 1, tend_kernel=tend_kernel, ze=ze, dzb=dzb)
+    (gt, gc, gf), (ot, oc, of) = run_case(emu, "VerticalDiffusion", True, False, 2, 1, ze=ze, dzb=dzb)
     for k in range(1, gt.shape[1]):
         assert rel(gt[:, k], ot[:, k]) < 1e-10, ("tend", k)
     for k in range(gc.shape[1]):
         assert rel(gc[:, k], oc[:, k]) < 1e-9, ("ldiv", k)
     assert rel(gf, of) < 1e-9
-
-
-@pytest.mark.parametrize("vd,deep,dm,iters,ntr,ze,dzb", [
-    ("DecayWithHeightDiffusion", True, False, 2, 1, 12, 400.0), ("VerticalDiffusion", False, True, 3, 0, 12, 400.0),
-    ("VerticalDiffusion", True, False, 1, 2, 63, 30.0), ("DecayWithHeightDiffusion", True, False, 0, 1, 2, 15000.0),
-    ("DecayWithHeightDiffusion", True, False, 2, 1, 5, 3000.0),
-])
-def test_emulated_pcr_variant_of_the_iterative_solve(emu, vd, deep, dm, iters, ntr, ze, dzb):
-    """k_ldiv_diff2: every Thomas sweep replaced by parallel cyclic reduction over all threads (pcr_slab).  Same algorithm: agrees with
-    the oracle and with k_ldiv_diff to round-off, for column heights that are and are not powers of two."""
-    (_, c1, f1), (_, oc, of) = run_case(emu, vd, deep, dm, iters, ntr, ze=ze, dzb=dzb, ldiv_kernel=1)
-    (_, c2, f2), _ = run_case(emu, vd, deep, dm, iters, ntr, ze=ze, dzb=dzb, ldiv_kernel=2)
-    for k in range(c2.shape[1]):
-        assert rel(c2[:, k], oc[:, k]) < 1e-9, ("ldiv2 vs oracle", k, rel(c2[:, k], oc[:, k]))
-        assert rel(c2[:, k], c1[:, k]) < 1e-9
-    assert rel(f2, of) < 1e-9 and rel(f2, f1) < 1e-9
 
 
 @pytest.mark.parametrize("vd,deep,dm,iters,ntr,upw,rayleigh,ze,dzb", [
@@ -264,7 +228,7 @@ def test_emulated_pcr_variant_of_the_iterative_solve(emu, vd, deep, dm, iters, n
     ("DecayWithHeightDiffusion", True, False, 0, 1, "vanleer_limiter", False, 2, 15000.0),
 ])
 def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, dm, iters, ntr, upw, rayleigh, ze, dzb):
-    """k_imp_stage_diff (B200_VDIFF_FUSED=1): cache_imp! → Wfact → T_imp! → ldiv! (approximate arrowhead iteration) → U −= ΔU → cache_imp! →
+    """k_imp_stage_diff: cache_imp! → Wfact → T_imp! → ldiv! (approximate arrowhead iteration) → U −= ΔU → cache_imp! →
     T_post_imp! with implicit vertical diffusion in ONE kernel, against the oracle's hook sequence (Float64).  The input state has
     non-zero u₃ on the boundary faces: the kernel must treat them as zero like cache_imp!."""
     P = prm.DycoreParams(D_0_diffusion=150.0, H_diffusion=5000.0, C_E=0.0044, zd_rayleigh=12000.0)
@@ -310,8 +274,8 @@ def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, d
 
 
 @pytest.mark.parametrize("vd,upw", [("DecayWithHeightDiffusion", "vanleer_limiter"), ("VerticalDiffusion", "first_order")])
-def test_float32_instantiations_of_the_opt_in_kernels(emu32, vd, upw):
-    """Float32 builds of the kernels whose GPU tests are still opt-in (k_vdiff_jac2 → k_ldiv_diff2, k_imp_stage_diff), on the CPU emulator
+def test_float32_instantiations_of_the_vdiff_kernels(emu32, vd, upw):
+    """Float32 builds of the vertical-diffusion kernels (k_vdiff_jac → k_ldiv_diff, k_vdiff_tend2, k_imp_stage_diff) on the CPU emulator
     against the Float64 oracle evaluated on the same Float32-rounded inputs: the errors must sit inside the tolerances those GPU tests use
     (ldiv! 5e-5; fused stage 2e-6 on the centre fields, 2e-4 on u₃)."""
     F = np.float32
@@ -353,7 +317,7 @@ def test_float32_instantiations_of_the_opt_in_kernels(emu32, vd, upw):
     o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
     errs = [rel(Nc[:, k].astype(np.float64), Uc[:, k]) for k in range(ncf)] + [rel(Nf.astype(np.float64), Uf)]
     assert max(errs[:ncf]) < 2e-6 and errs[-1] < 2e-4, errs
-    # Wfact planes (k_vdiff_jac2) → ldiv! (k_ldiv_diff2) with the tendency kernel k_vdiff_tend2
+    # Wfact planes (k_wfact2, k_vdiff_jac) → ldiv! (k_ldiv_diff) with the tendency kernel k_vdiff_tend2
     sc2 = sc.copy()
     sc2[16] = 0
     Rc = (rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3).astype(F)
@@ -731,7 +695,7 @@ def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5, emu, vdiff):
     T_exp = k5_exp_a → k_dss2(∇²) → k5_exp_c, and the stiffly-accurate final increment from N₄ — against the oracle's LITERAL step
     (u + dt Σ bⱼ (T_exp[j] + T_imp[j]) with T_imp formed explicitly).  The host orchestration below restates impl_step's coefficient
     recursion; the arithmetic on the fields is all done by the kernels' own source.  With vertical diffusion: explicit → k_vdiff_tend2
-    after k5_exp_c; implicit → k_imp_stage_diff in place of k5_imp_stage (the B200_VDIFF_FUSED=1 data flow)."""
+    after k5_exp_c; implicit → k_imp_stage_diff in place of k5_imp_stage (the data flow of the fused stepper)."""
     HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
     P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0, D_0_diffusion=40.0, H_diffusion=6000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=8, z_max=30000.0, dz_bottom=500.0, radius=P.planet_radius)
