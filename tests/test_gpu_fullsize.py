@@ -58,8 +58,11 @@ def test_baseline_configs_one_step_float32_within_1e5(h_elem, dt):
 
 def test_hundred_steps_bounded_drift_ze63_with_u3():
     """Bounded drift over 100 steps (north star) with the vertical grid, sponges and time step class of the ze63 configs (he6/ze63,
-    dt 300 s ≈ the he16 Courant number): Float32 CUDA vs Float64 oracle, all five fields, recorded every 25 steps.  The state error
-    must stay within a fixed multiple of its one-step value (no exponential growth) and far below the physical signal."""
+    dt 300 s ≈ the he16 Courant number): Float32 CUDA vs Float64 oracle, all five fields, recorded at steps 1, 25, 50, 100.
+    Bounds = what Float32 arithmetic itself does to this flow, measured with the oracle (the reference's literal formulation) run
+    in Float32 against itself in Float64 (profiles/r2_drift_float32.md): ρ 3.2e-7, uₕ 2.5e-5 / 4.4e-5, ρe_tot 1.2e-6, and u₃ — a
+    near-zero field whose round-off excites small acoustic/gravity-wave adjustments — 3.5e-2 at step 25, settling to 2.3e-2 at
+    step 100 (no growth).  The CUDA path measures 3.7e-7, 2.9e-5 / 5.1e-5, 1.4e-6, and 2.5e-2 → 1.7e-2 for u₃: the same drift."""
     P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD)
     sim = dycore.AtmosSimulation(FT=np.float32, h_elem=6, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=300.0, rayleigh_sponge=True,
                                  viscous_sponge=True, params=P)
@@ -79,7 +82,10 @@ def test_hundred_steps_bounded_drift_ze63_with_u3():
     assert np.isfinite(gc).all() and np.isfinite(gf).all()
     e1, e100 = hist[1], hist[100]
     assert max(e1.values()) <= 1e-5, e1
-    # bounded: ρ, ρe_tot stay at 1e-5; the velocities (chaotic growth of round-off in the wave) stay below 1e-3 of the field norm
-    assert e100["rho"] <= 2e-5 and e100["rhoe"] <= 2e-5, e100
-    assert e100["u1"] <= 1e-3 and e100["u2"] <= 1e-3 and e100["u3"] <= 5e-3, e100
+    for k in (25, 50, 100):
+        e = hist[k]
+        assert e["rho"] <= 2e-6 and e["rhoe"] <= 5e-6, (k, e)
+        assert e["u1"] <= 1e-4 and e["u2"] <= 1.5e-4, (k, e)
+        assert e["u3"] <= 5e-2, (k, e)
+    assert e100["u3"] <= 1.5 * max(hist[25]["u3"], hist[50]["u3"]), hist  # bounded, not growing
     sim.close()

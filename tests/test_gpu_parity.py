@@ -1,12 +1,17 @@
 """GPU parity tests: the CUDA path, called through the C-ABI, against the NumPy oracle on the same
 seeded inputs, plus size-independent properties at the BASELINE.json sizes.
 
-Tolerances (north star: rel-L2 per prognostic field after one step ≤ 1e-12 Float64 / 1e-5 Float32):
-  * Float64: 1e-11 on every hook and on the full step (measured ≈1e-14).
-  * Float32: 1e-5 on ρ, uₕ, ρe_tot after a step.  u₃ is a near-zero field obtained by cancellation of
-    O(g·Δz) terms; Float32 round-off there is ≈1e-5 of ‖u₃‖ in the oracle itself (oracle-F32 vs
-    oracle-F64 shows the same gap), so u₃ is held to 2e-4.  Tendencies with the same cancellation
-    structure (uₕ explicit tendency, u₃ implicit tendency) are held to 5e-4 in Float32.
+Tolerances (north star: rel-L2 per prognostic field after one step ≤ 1e-12 Float64 / 1e-5 Float32), set from the measured errors
+recorded in profiles/r2_parity_report.jsonl (≈1.5× the measurement):
+  * Float64: 1e-11 on every hook and on the full step (measured ≤ 6e-14).
+  * Float32 state after ONE step: 1e-5 on all five fields for the 63-level vertical grid of the BASELINE configs (measured: ρ 1.4e-7,
+    uₕ 9e-7, ρe_tot 2.2e-7, u₃ 8.1e-6 at he3; he16/he30 in test_gpu_fullsize.py: u₃ 7.2e-6 / 6.1e-6).  u₃ on the coarse 10-level grid of
+    configs[0] (Δz up to 8 km) is held to 2.2e-5: the kernels measure 1.5e-5 there and the reference's own Float32 formulation sits at
+    2.6e-5 (tests/test_oracle_identities.py::test_float32_floor_of_the_reference_formulation) — u₃ is a near-zero field produced by the
+    cancellation of O(g·Δz) terms, the Float32 kernels evaluate those differences in difference form (common.cuh pgf_diff) and land
+    below that floor.  After TWO steps the u₃ bound is 2e-5 (measured 1.1–1.3e-5).
+  * Float32 tendencies with the same cancellation structure (uₕ explicit tendency, u₃ implicit tendency) are held to 2e-4
+    (measured ≤ 6e-5 / ≤ 9e-5).
 """
 import numpy as np
 import pytest
@@ -54,12 +59,17 @@ def perturbed_state(sim, FT):
     return Yc, Yf, rng
 
 
-def tol(FT, kind="state"):
+def tol(FT, kind="state", u3=1e-5):
+    """kind "state": one step (u3 = 1e-5 on the 63-level grid; pass 2.2e-5 for the coarse 10-level grid, 2e-5 for two steps);
+    "tend": hook tendencies; see the module docstring for the measurements behind the numbers."""
     if FT == np.float64:
         return dict(rho=1e-11, u1=1e-11, u2=1e-11, rhoe=1e-11, u3=1e-11)
     if kind == "state":
-        return dict(rho=1e-5, u1=1e-5, u2=1e-5, rhoe=1e-5, u3=2e-4)
-    return dict(rho=1e-5, u1=5e-4, u2=5e-4, rhoe=1e-4, u3=5e-4)
+        return dict(rho=1e-5, u1=1e-5, u2=1e-5, rhoe=1e-5, u3=u3)
+    return dict(rho=1e-5, u1=2e-4, u2=2e-4, rhoe=1e-4, u3=2e-4)
+
+
+U3_COARSE, U3_TWO_STEPS = 2.2e-5, 2e-5
 
 
 def check(gc, gf, oc, of, t, what):
@@ -133,7 +143,7 @@ def test_one_step_matches_oracle(FT, name, fused):
     Yc0, Yf0 = sim.Y.cpu()
     sim.step(fused=fused)
     oc, of = o.step(Yc0.astype(np.float64), Yf0.astype(np.float64))
-    check(*sim.Y.cpu(), oc, of, tol(FT, "state"), f"step {name} fused={fused}")
+    check(*sim.Y.cpu(), oc, of, tol(FT, "state", u3=U3_COARSE if name == "he4ze10" else 1e-5), f"step {name} fused={fused}")
     sim.close()
 
 
@@ -167,7 +177,7 @@ def test_shallow_atmosphere_matches_oracle(FT):
         for _ in range(2):
             sim.step(fused=fused)
             oc, of = o.step(oc, of)
-        check(*sim.Y.cpu(), oc, of, tol(FT, "state"), f"shallow 2 steps fused={fused}")
+        check(*sim.Y.cpu(), oc, of, tol(FT, "state", u3=U3_TWO_STEPS), f"shallow 2 steps fused={fused}")
     sim.close()
 
 
@@ -195,7 +205,7 @@ def test_numerics_options_match_oracle(FT, opts):
             sim.step(fused=fused)
             oc, of = o.step(oc, of)
         gc, gf = sim.Y.cpu()
-        check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state"), f"{opts} fused={fused}")
+        check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state", u3=U3_TWO_STEPS), f"{opts} fused={fused}")
         for q in range(4, gc.shape[1]):
             assert rel(gc[:, q], oc[:, q]) < (1e-11 if FT == np.float64 else 1e-5), f"{opts} tracer {q}"
     sim.close()
@@ -332,7 +342,7 @@ def test_passive_tracers_match_oracle(FT):
         sim.step(fused=True)
         oc, of = o.step(oc, of)
     gc, gf = sim.Y.cpu()
-    check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state"), "2 steps with tracers")
+    check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state", u3=U3_TWO_STEPS), "2 steps with tracers")
     for q in (4, 5):
         assert rel(gc[:, q], oc[:, q]) < (1e-11 if FT == np.float64 else 1e-5), f"tracer {q} after 2 steps"
     # hook-by-hook stepping gives the same state
@@ -504,7 +514,7 @@ def test_implicit_stage_variants_agree(FT):
         got = _steps_with_env(env, FT, "he3ze63", nsteps=2)[0]
         for k in range(4):
             assert rel(got[0][:, k], ref[0][:, k]) < lim, (env, k)
-        assert rel(got[1], ref[1]) < (1e-10 if FT == np.float64 else 2e-4), env
+        assert rel(got[1], ref[1]) < (1e-10 if FT == np.float64 else 5e-5), env
 
 
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
@@ -543,7 +553,7 @@ def test_quasimonotone_limiter_matches_oracle(FT):
         sim.step(fused=True)
         oc, of = o.step(oc, of)
     gc, gf = sim.Y.cpu()
-    check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state"), "2 steps with limiter")
+    check(gc[:, :4], gf, oc[:, :4], of, tol(FT, "state", u3=U3_TWO_STEPS), "2 steps with limiter")
     for q in (4, 5):
         assert rel(gc[:, q], oc[:, q]) < (1e-10 if FT == np.float64 else 2e-5), f"tracer {q} after 2 limited steps: {rel(gc[:, q], oc[:, q])}"
     sim.Y = sim.to_device(Yc0, Yf0)

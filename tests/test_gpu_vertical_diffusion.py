@@ -3,7 +3,7 @@
 
 Run on a B200 at the end of round 1 (profiles/r1_vdiff_gpu_pytest.log, profiles/r1_vdiff_gpu_quickcheck.log: Float64 ≤ 1e-13,
 Float32 ≤ 1e-6 on the centre fields).  Tolerances as in
-tests/test_gpu_parity.py (Float64 1e-11; Float32 1e-5 state / 5e-4 cancelling tendencies)."""
+tests/test_gpu_parity.py (Float64 1e-11; Float32 1e-5 state, u₃ 5e-5 on this 10-level grid with diffusion / 5e-4 cancelling tendencies)."""
 import numpy as np
 import pytest
 
@@ -138,7 +138,7 @@ def test_step_with_vertical_diffusion_matches_oracle(FT, implicit):
     for k in range(5):
         e = rel(gc[:, k], oc[:, k])
         assert e <= (1e-11 if t64 else 1e-5), f"step comp {k}: {e:.3e}"
-    assert rel(gf, of) <= (1e-11 if t64 else 2e-4)
+    assert rel(gf, of) <= (1e-11 if t64 else 5e-5)
     # literal hook-by-hook step agrees with the fused entry point
     sim2, _, _, _, _ = make(FT, "DecayWithHeightDiffusion", implicit)
     sim2.step(fused=False)
@@ -246,7 +246,7 @@ def test_fused_implicit_diffusion_stage(FT, vd):
     t64 = FT == np.float64
     for k in range(5):
         assert rel(gc[:, k], oc[:, k]) <= (1e-12 if t64 else 2e-6), k
-    assert rel(gf, of) <= (1e-10 if t64 else 2e-4)
+    assert rel(gf, of) <= (1e-10 if t64 else 5e-5)
     Yc0, Yf0 = sim.Y.cpu()
     for _ in range(3):  # eager step, graph capture, graph replay
         sim.Y = sim.to_device(Yc0, Yf0)
@@ -257,5 +257,5 @@ def test_fused_implicit_diffusion_stage(FT, vd):
             oc, of = o64.step(Yc0.astype(np.float64), Yf0.astype(np.float64))
         for k in range(5):
             assert rel(gc[:, k], oc[:, k]) <= (1e-11 if t64 else 1e-5), (_, k)
-        assert rel(gf, of) <= (1e-11 if t64 else 2e-4)
+        assert rel(gf, of) <= (1e-11 if t64 else 5e-5)
     sim.close()
