@@ -132,7 +132,7 @@ def _ptr(a: np.ndarray):
 def make_params(P, N, grid) -> Params:
     h = grid.node_horizontal_length_scale()
     nu4v = N.nu4_vorticity_coeff * h**3 if N.hyperdiff else 0.0
-    up = {"none": 0, "first_order": 1, "vanleer_limiter": 3}[N.energy_upwinding]
+    up = {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[N.energy_upwinding]
     return Params(
         R_d=P.R_d, cp_d=P.cp_d, cv_d=P.cv_d, T_0=P.T_0, grav=P.grav, Omega=P.Omega, p_ref_theta=P.p_ref_theta,
         T_surf_ref=P.T_surf_ref, T_min_ref=P.T_min_ref, T_min_sgs=P.T_min_sgs, dt=N.dt, nu4_vorticity=nu4v,
@@ -140,7 +140,7 @@ def make_params(P, N, grid) -> Params:
         hyperdiff=int(N.hyperdiff), rayleigh_sponge=int(N.rayleigh_sponge), zd_rayleigh=P.zd_rayleigh,
         alpha_rayleigh_uh=P.alpha_rayleigh_uh, alpha_rayleigh_w=P.alpha_rayleigh_w,
         viscous_sponge=int(N.viscous_sponge), zd_viscous=P.zd_viscous, kappa_2_sponge=P.kappa_2_sponge,
-        energy_upwinding=up, tracer_upwinding={"none": 0, "first_order": 1, "vanleer_limiter": 3}[N.tracer_upwinding], held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
+        energy_upwinding=up, tracer_upwinding={"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[N.tracer_upwinding], held_suarez=int(N.held_suarez), hs_day=P.day, hs_sigma_b=P.sigma_b, hs_dT_y=P.dT_y_dry,
         hs_T_equator=P.T_equator_dry, hs_dtheta_z=P.dtheta_z, hs_T_min=P.T_min_hs, MSLP=P.MSLP,
         sem_quasimonotone_limiter=int(getattr(N, "apply_sem_quasimonotone_limiter", False)),
         vert_diff={None: 0, "VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[getattr(N, "vert_diff", None)],

@@ -545,8 +545,7 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (d->ft_bytes != 4 && d->ft_bytes != 8) return fail("b200_create: ft_bytes must be 4 or 8");
   if (d->n_tracers < 0 || d->n_tracers > 4) return fail("b200_create: 0 <= n_tracers <= 4");
   for (int u : {p->energy_upwinding, p->tracer_upwinding})
-    if (u != 0 && u != 1 && u != 3)
-      return fail("b200_create: upwinding must be 0 (none), 1 (first_order) or 3 (vanleer_limiter); third_order (2) is not built");
+    if (u < 0 || u > 3) return fail("b200_create: upwinding must be 0 (none), 1 (first_order), 2 (third_order) or 3 (vanleer_limiter)");
   if (p->vert_diff < 0 || p->vert_diff > 2) return fail("b200_create: vert_diff must be 0 (none), 1 (VerticalDiffusion) or 2 (DecayWithHeightDiffusion)");
   if (p->implicit_diffusion && !p->vert_diff)
     return fail("b200_create: implicit_diffusion needs a vert_diff model (the reference's update_diffusion_jacobian! has no diffusivity otherwise)");

@@ -256,6 +256,7 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
           const FT y0 = pos ? a_m2 : a_p2, y1 = pos ? a_m : a_p, y2 = pos ? a_p : a_m;
           FT upv = y1;
           if (P.upwinding == 3 && v >= 2 && v <= nv - 2) upv = y1 + vl_slope5(y0, y1, y2) / FT(2) * (FT(1) - abs_(wk) * P.dt);
+          else if (P.upwinding == 2 && nv >= 3) upv = upwind3_face(a_m2, a_m, a_p, a_p2, v, nv, wk);  // ᶠupwind3 (third_order)
           d[k] = upv - FT(0.5) * (a_m + a_p);
         }
         flx[p] = (mr * w) * V2(d[0], d[1]);

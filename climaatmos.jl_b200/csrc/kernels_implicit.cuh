@@ -236,6 +236,15 @@ __device__ __forceinline__ FT vl_slope(FT am, FT a0, FT ap) {
   FT lim = fmin_(abs_(d), fmin_(FT(2) * (a0 - mn), FT(2) * (mx - a0)));
   return d > FT(0) ? lim : (d < FT(0) ? -lim : FT(0));
 }
+// ᶠupwind3 face value (abbreviations.jl:229-240; Upwind3rdOrderBiasedProductC2F with ThirdOrderOneSided closures [UPSTREAM-RECALL]):
+// interior faces 2..nv−2 the upwind-biased (−a⁻⁻ + 5a⁻ + 2a⁺)/6 (mirror image for w < 0); the first interior face the right-biased
+// (4a⁻ + 10a⁺ − 2a⁺⁺)/12 and the last one the left-biased (−2a⁻⁻ + 10a⁻ + 4a⁺)/12, whatever the sign of w.  Needs nv ≥ 3.
+template <class FT>
+__device__ __forceinline__ FT upwind3_face(FT amm, FT am, FT ap, FT app, int f, int nv, FT w) {
+  if (f == 1) return (FT(4) * am + FT(10) * ap - FT(2) * app) / FT(12);
+  if (f == nv - 1) return (-FT(2) * amm + FT(10) * am + FT(4) * ap) / FT(12);
+  return w >= FT(0) ? (-amm + FT(5) * am + FT(2) * ap) / FT(6) : (FT(2) * am + FT(5) * ap - app) / FT(6);
+}
 // returns (upwinded χ - centred χ) at interior face f for contravariant velocity w
 template <class FT>
 __device__ __forceinline__ FT upwind_minus_central(const Par<FT>& P, const FT* chi, int o, int f, int nv, FT w) {
@@ -245,6 +254,8 @@ __device__ __forceinline__ FT upwind_minus_central(const Par<FT>& P, const FT* c
   if (P.upwinding == 3 && f >= 2 && f <= nv - 2) {
     if (w >= FT(0)) up = am + vl_slope(chi[o - 2], am, ap) / FT(2) * (FT(1) - w * P.dt);
     else up = ap - vl_slope(am, ap, chi[o + 1]) / FT(2) * (FT(1) + w * P.dt);
+  } else if (P.upwinding == 2 && nv >= 3) {
+    up = upwind3_face(f >= 2 ? chi[o - 2] : am, am, ap, f <= nv - 2 ? chi[o + 1] : ap, f, nv, w);
   } else {
     up = w >= FT(0) ? am : ap;  // first order (also the FirstOrderOneSided boundary closure)
   }

@@ -522,6 +522,8 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
         if (P.tupw == 3 && v >= 2 && v <= nv - 2) {
           if (w >= FT(0)) face = am + vl_slope(s_chi[o + vm2], am, ap) / FT(2) * (FT(1) - w * P.dt);
           else face = ap - vl_slope(am, ap, s_chi[o + vp]) / FT(2) * (FT(1) + w * P.dt);
+        } else if (P.tupw == 2 && nv >= 3) {  // ᶠupwind3 (tracer_upwinding: third_order)
+          face = upwind3_face(s_chi[o + vm2], am, ap, s_chi[o + vp], v, nv, w);
         } else if (P.tupw == 0) {
           face = FT(0.5) * (am + ap);
         } else {

@@ -77,7 +77,7 @@ typedef struct {
   int32_t hyperdiff;
   int32_t rayleigh_sponge; double zd_rayleigh, alpha_rayleigh_uh, alpha_rayleigh_w;
   int32_t viscous_sponge;  double zd_viscous, kappa_2_sponge;
-  int32_t energy_upwinding; /* 0 none, 1 first_order, 3 vanleer_limiter (2 = third_order is rejected by b200_create: not built) */
+  int32_t energy_upwinding; /* 0 none, 1 first_order, 2 third_order (ᶠupwind3, abbreviations.jl:229-240), 3 vanleer_limiter */
   int32_t tracer_upwinding; /* same encoding (default_config.yml:321-323) */
   /* Held–Suarez forcing (src/parameterized_tendencies/radiation/held_suarez.jl:111-296); flat surface */
   int32_t held_suarez; double hs_day, hs_sigma_b, hs_dT_y, hs_T_equator, hs_dtheta_z, hs_T_min, MSLP;

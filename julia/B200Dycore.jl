@@ -46,7 +46,7 @@ struct ParamsC
     hyperdiff::Int32
     rayleigh_sponge::Int32; zd_rayleigh::Float64; alpha_rayleigh_uh::Float64; alpha_rayleigh_w::Float64
     viscous_sponge::Int32; zd_viscous::Float64; kappa_2_sponge::Float64
-    energy_upwinding::Int32      # 0 none, 1 first_order, 3 vanleer_limiter
+    energy_upwinding::Int32      # 0 none, 1 first_order, 2 third_order, 3 vanleer_limiter
     tracer_upwinding::Int32
     held_suarez::Int32
     hs_day::Float64; hs_sigma_b::Float64; hs_dT_y::Float64; hs_T_equator::Float64; hs_dtheta_z::Float64; hs_T_min::Float64
@@ -75,7 +75,7 @@ check(rc, what, ctx = C_NULL) = rc == 0 || error("$what: " * unsafe_string(ccall
 # VIJFH parent array of a field on the device: (Nv, 4, 4, Nf, Nh), level fastest
 dptr(f) = reinterpret(Ptr{Cvoid}, pointer(parent(Fields.field_values(f))))
 stream() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
-# 0 none, 1 first_order, 2 third_order (b200_create rejects it: not built), 3 vanleer_limiter
+# 0 none, 1 first_order, 2 third_order, 3 vanleer_limiter (default_config.yml:321-326)
 upw(x) = x == Val(:none) ? Int32(0) : x == Val(:first_order) ? Int32(1) : x == Val(:third_order) ? Int32(2) : Int32(3)
 
 """

@@ -243,6 +243,27 @@ class Oracle:
         out[..., 2:-2] = vf * np.where(vf >= 0, pos, neg)
         return out
 
+    def upwind3(self, v, a):
+        """ᶠupwind3 = Upwind3rdOrderBiasedProductC2F(bottom = ThirdOrderOneSided(), top = ThirdOrderOneSided())
+        (abbreviations.jl:229-240) [UPSTREAM-RECALL ClimaCore 0.15.1 finite_difference.jl]: interior faces (four-point stencil available)
+            (v·(7(a⁺ + a⁻) − (a⁺⁺ + a⁻⁻)) − |v|·(3(a⁺ − a⁻) − (a⁺⁺ − a⁻⁻))) / 12,
+        i.e. the upwind-biased cubic-accurate face value (−a⁻⁻ + 5a⁻ + 2a⁺)/6 for v > 0 and its mirror image for v < 0; the first
+        interior face uses the one-sided right-biased reconstruction v·(4a⁻ + 10a⁺ − 2a⁺⁺)/12 and the last one the left-biased
+        v·(−2a⁻⁻ + 10a⁻ + 4a⁺)/12 whatever the sign of v (boundary_width 2); the two boundary faces carry no flux (ᶜadvdivᵥ SetValue(0)).
+        Columns with fewer than three levels fall back to first-order upwinding."""
+        FT = self.FT
+        out = self.upwind1(v, a)
+        nv = a.shape[-1]
+        if nv < 3:
+            return out
+        out[..., 1] = v[..., 1] * (FT(4) * a[..., 0] + FT(10) * a[..., 1] - FT(2) * a[..., 2]) / FT(12)
+        out[..., nv - 1] = v[..., nv - 1] * (-FT(2) * a[..., nv - 3] + FT(10) * a[..., nv - 2] + FT(4) * a[..., nv - 1]) / FT(12)
+        if nv >= 4:
+            amm, am, ap, app = a[..., :-3], a[..., 1:-2], a[..., 2:-1], a[..., 3:]
+            vf = v[..., 2:-2]
+            out[..., 2:-2] = (vf * (FT(7) * (ap + am) - (app + amm)) - np.abs(vf) * (FT(3) * (ap - am) - (app - amm))) / FT(12)
+        return out
+
     # ------------------------------------------------------------------ thermodynamics (A.4)
     def exner(self, p):
         return (p / self.FT(self.P.p_ref_theta)) ** self.FT(self.P.kappa_d)
@@ -309,6 +330,8 @@ class Oracle:
             return -self.advdiv_f2c(rJf * self.upwind1(fu3, chi))
         if upwinding == "vanleer_limiter":
             return -self.advdiv_f2c(rJf * self.lin_vanleer(fu3, chi, dt))
+        if upwinding == "third_order":
+            return -self.advdiv_f2c(rJf * self.upwind3(fu3, chi))
         raise ValueError(upwinding)
 
     def theta_v(self, T, p):

@@ -184,14 +184,16 @@ def test_shallow_atmosphere_matches_oracle(FT):
 @pytest.mark.parametrize("opts", [
     dict(energy_q_tot_upwinding="none"),            # T_post_imp! = nothing (integrator.jl:212-214)
     dict(energy_q_tot_upwinding="first_order"),
+    dict(energy_q_tot_upwinding="third_order"),      # ᶠupwind3 (abbreviations.jl:229-240)
     dict(hyperdiff=False),                           # no ∇⁴, no DSS inside T_exp (remaining_tendency.jl:15-24)
     dict(tracer_upwinding="none", tracers=True),
     dict(tracer_upwinding="first_order", tracers=True),
+    dict(tracer_upwinding="third_order", tracers=True),
 ])
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_numerics_options_match_oracle(FT, opts):
     """The upwinding / hyperdiffusion switches of config/default_configs/default_config.yml (energy_q_tot_upwinding,
-    tracer_upwinding ∈ none | first_order | vanleer_limiter; hyperdiff): two ARS343 steps, fused and hook-by-hook, against the oracle."""
+    tracer_upwinding ∈ none | first_order | third_order | vanleer_limiter; hyperdiff): two ARS343 steps, fused and hook-by-hook, against the oracle."""
     kw = dict(opts)
     if kw.pop("tracers", False):
         kw["tracers"] = _tracer_fns()

@@ -150,7 +150,7 @@ def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("upw,rayleigh,deep", [("vanleer_limiter", True, True), ("first_order", False, False), ("none", False, True)])
+@pytest.mark.parametrize("upw,rayleigh,deep", [("vanleer_limiter", True, True), ("first_order", False, False), ("none", False, True), ("third_order", True, True)])
 def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
     """k_cache_imp, k_t_imp2, k_wfact2 → k_ldiv2, k_t_post_imp2 (quarter element per CTA, parallel cyclic reduction) on the CPU emulator
     against the oracle's cache_imp! / T_imp! / Wfact + ldiv! / T_post_imp! (Float64)."""
@@ -178,7 +178,7 @@ def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
     hgeo = np.zeros((nh, HG_N, 16))
     hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), 0, 0, 0, 0, dtg,
-                   0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw], 0])
+                   0, {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[upw], 0])
     Rc = rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3
     Rf = rng.standard_normal(Yf.shape)
     z4 = lambda: np.zeros((nh, 16, nv))
@@ -223,6 +223,7 @@ def test_emulated_vdiff_kernels_at_the_column_height_limits(emu, ze, dzb):
 @pytest.mark.parametrize("vd,deep,dm,iters,ntr,upw,rayleigh,ze,dzb", [
     ("DecayWithHeightDiffusion", True, False, 2, 1, "vanleer_limiter", True, 12, 400.0),
     ("VerticalDiffusion", False, False, 1, 2, "first_order", False, 12, 400.0),
+    ("DecayWithHeightDiffusion", True, False, 2, 1, "third_order", True, 12, 400.0),
     ("VerticalDiffusion", True, True, 3, 0, "none", False, 12, 400.0),
     ("DecayWithHeightDiffusion", True, False, 2, 1, "vanleer_limiter", True, 63, 30.0),
     ("DecayWithHeightDiffusion", True, False, 0, 1, "vanleer_limiter", False, 2, 15000.0),
@@ -260,7 +261,7 @@ def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, d
     kdec = pad(P.D_0_diffusion * np.exp(-(g.z_c - g.z_f[0]) / P.H_diffusion))
     mode = {"VerticalDiffusion": 1, "DecayWithHeightDiffusion": 2}[vd]
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), mode,
-                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, 0, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw]])
+                   0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, dtg, 0, {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[upw]])
     Nc, Nf = np.zeros_like(Yc), np.zeros_like(Yf)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     assert emu.emu_stage_diff(nh, nv, ncf, p(sc), p(vl), p(hgeo), p(kdec), p(Yc), p(Yf), p(Nc), p(Nf)) == 0
@@ -353,6 +354,7 @@ def emu5():
 @pytest.mark.parametrize("upw,rayleigh,deep,ze,dzb,ntr", [
     ("vanleer_limiter", True, True, 12, 400.0, 0), ("first_order", False, False, 12, 400.0, 1), ("none", False, True, 12, 400.0, 0),
     ("vanleer_limiter", True, True, 63, 30.0, 0), ("vanleer_limiter", False, True, 2, 15000.0, 0), ("vanleer_limiter", False, True, 5, 3000.0, 2),
+    ("third_order", True, True, 12, 400.0, 0), ("third_order", False, True, 3, 8000.0, 1), ("third_order", False, False, 63, 30.0, 0), ("third_order", False, True, 2, 15000.0, 0),
 ])
 def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleigh, deep, ze, dzb, ntr):
     """k5_imp_stage<double, PCR> — the implicit-stage kernel of the benchmarked step (packed row layout, parallel cyclic reduction) — run on
@@ -383,7 +385,7 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
     hgeo = np.zeros((nh, HG_N, 16))
     hgeo[:, HG_GI11], hgeo[:, HG_GI12], hgeo[:, HG_GI22] = (Ginv[..., a, b].reshape(nh, 16) for a, b in ((0, 0), (0, 1), (1, 1)))
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), dtg,
-                   {"none": 0, "first_order": 1, "vanleer_limiter": 3}[upw], ncf])
+                   {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[upw], ncf])
     Nc, Nf = np.zeros_like(Yc), np.zeros_like(Yf)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     assert emu5.emu_imp5(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf), p(Nc), p(Nf)) == 0
@@ -479,7 +481,8 @@ def test_emulated_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze,
 
 
 @pytest.mark.parametrize("tupw,sponge,ze,dzb", [("vanleer_limiter", True, 12, 400.0), ("first_order", False, 12, 400.0), ("none", True, 63, 30.0),
-                                                ("vanleer_limiter", False, 3, 8000.0)])
+                                                ("vanleer_limiter", False, 3, 8000.0), ("third_order", True, 12, 400.0), ("third_order", False, 3, 8000.0),
+                                                ("third_order", False, 4, 6000.0)])
 def test_emulated_tracer_kernels_match_oracle(emux, tupw, sponge, ze, dzb):
     """k5_tracer_a / k5_tracer_c (passive tracers: horizontal advection into Yₜ_lim, ∇²χ, explicit vertical transport with tracer_upwinding,
     viscous sponge; tracer hyperdiffusion) on the CPU emulator against the oracle's `_tracer_pre`, `_tracer_laplacians`, `_tracer_post`."""
@@ -509,7 +512,7 @@ def test_emulated_tracer_kernels_match_oracle(emux, tupw, sponge, ze, dzb):
                    pad(o.beta_viscous(g.z_c) if sponge else z0[:-1]), pad(o.beta_viscous(g.z_f) if sponge else z0)])
     hgeo = _full_hgeo(g, P, True)
     sc = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(o.nu4_vort), float(o.nu4_scalar),
-                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, ncf, {"none": 0, "first_order": 1, "vanleer_limiter": 3}[tupw]])
+                   N.divergence_damping_factor, 1, float(sponge), float(sponge), 3, ncf, {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[tupw]])
     Dm, wq = np.ascontiguousarray(g.D, dtype=np.float64), np.ascontiguousarray(g.wq, dtype=np.float64)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     Ytc, Ylc, H, Ytf = np.zeros_like(Yc), np.zeros_like(Yc), np.zeros_like(Yc), np.zeros_like(Yf)

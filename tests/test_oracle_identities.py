@@ -63,7 +63,7 @@ def test_split_divergence_unit_tracer(case):
     assert np.abs(a - b).max() <= 100 * np.finfo(float).eps * np.abs(b).max()
     pc = o.set_implicit_precomputed_quantities(Yc, Yf)
     mass = -o.advdiv_f2c(o.interp_c2f(rho * o.c.J) / o.f.J * pc["fu3"])
-    for up in ("none", "first_order", "vanleer_limiter"):
+    for up in ("none", "first_order", "third_order", "vanleer_limiter"):
         t = o.vertical_transport(rho, pc["fu3"], one, N.dt, up)
         assert np.abs(t - mass).max() <= 100 * np.finfo(float).eps * np.abs(mass).max()
 
@@ -461,3 +461,40 @@ def test_float32_floor_of_the_reference_formulation(name, he, ze, zmax, dzb, dt,
         assert rel(c32[:, k], c64[:, k]) < 5e-6, k
     gap = rel(f32, f64)
     assert 1.0e-5 < gap < 4e-5, gap  # the floor: above the 1e-5 bar, which is why the bar needs the difference form
+
+
+
+def test_third_order_upwinding_reconstruction():
+    """ᶠupwind3 (abbreviations.jl:229-240): on a uniform column the interior stencil and the two one-sided closures are finite-volume
+    reconstructions — from the cell averages of a quadratic profile they return its face values exactly (third-order accuracy);
+    the interior value is the upwind-biased one; and `corrected + central == upwind` holds for :third_order like for the other
+    schemes (correct_implicit_advection_tests.jl:40-67)."""
+    P = prm.DycoreParams()
+    g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=9, z_max=9000.0, dz_bottom=1000.0, radius=P.planet_radius)  # dz_bottom = z_max/z_elem: uniform
+    assert np.allclose(np.diff(g.z_f), 1000.0)
+    N = prm.DycoreNumerics(dt=100.0, energy_upwinding="third_order")
+    o = Oracle(g, P, N, np.float64)
+    zc, zf = g.z_c / 1000.0, g.z_f / 1000.0  # h = 1
+    q2 = 0.13
+    quad = lambda z: 2.0 - 0.7 * z + q2 * z * z
+    cell_avg = quad(zc) + 2 * q2 / 24.0  # average of a quadratic over a cell of width 1 = midpoint value + h² q''/24
+    a = np.broadcast_to(cell_avg, (g.nelems, 4, 4, g.nv)).copy()
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((g.nelems, 4, 4, g.nv + 1))
+    rec = o.upwind3(v, a)[..., 1:-1] / v[..., 1:-1]
+    assert np.abs(rec - quad(zf)[1:-1]).max() < 1e-12  # every interior face, both closures included, either sign of v
+    # interior: upwind-biased
+    b = rng.standard_normal(a.shape)
+    f3 = o.upwind3(v, b)[..., 2:-2]
+    amm, am, ap, app = b[..., :-3], b[..., 1:-2], b[..., 2:-1], b[..., 3:]
+    vf = v[..., 2:-2]
+    up = np.where(vf >= 0, (-amm + 5 * am + 2 * ap) / 6, (2 * am + 5 * ap - app) / 6)
+    assert np.abs(f3 - vf * up).max() < 1e-13
+    # corrected + central == upwind (T_post_imp! contract)
+    Yc, Yf = setups.dry_baroclinic_wave(g, P)
+    Yf = 0.3 * g.dz_f * rng.standard_normal(Yf.shape)
+    pc = o.set_implicit_precomputed_quantities(Yc, Yf)
+    corr, _ = o.correct_implicit_advection_tendency(Yc, Yf, pc)
+    cen = o.vertical_transport(Yc[:, 0], pc["fu3"], pc["h_tot"], N.dt, "none")
+    upw = o.vertical_transport(Yc[:, 0], pc["fu3"], pc["h_tot"], N.dt, "third_order")
+    assert np.abs(corr[:, 3] + cen - upw).max() <= 1e-10 * np.abs(upw).max()
