@@ -17,7 +17,6 @@
 #include "kernels_implicit.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
-#include "kernels_tma.cuh"
 #include "kernels_imp5.cuh"
 #include "kernels_limiter.cuh"
 #include "kernels_vdiff.cuh"
@@ -147,8 +146,6 @@ struct b200_ctx {
   int eager_steps = 0;
   cudaStream_t side = nullptr;           // side stream: T_imp = (U − temp)/dtγ runs concurrently with the T_exp kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int tma = 1;         // B200_TMA=0: one-CTA-per-element kernels with direct global loads instead of the persistent bulk-copy-fed ones (A/B, bitwise identical)
-  int num_sms = 148;   // multiprocessors of the device (persistent grids)
   int generic_nv = 0;  // B200_GENERIC_NV=1: do not use the kernels specialised for nv = 63 (test coverage of the run-time-nv builds)
   int ncf() const { return 4 + dims.n_tracers; }
   size_t nc() const { return (size_t)dims.nh * ncf() * 16 * dims.nv; }
@@ -427,8 +424,6 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k5_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
   CK(cudaFuncSetAttribute(k5_exp_a<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
   CK(cudaFuncSetAttribute(k5_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
-  CK(cudaFuncSetAttribute(k6_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k6c<FT>()));
-  CK(cudaFuncSetAttribute(k6_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k6c<FT>()));
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
@@ -451,12 +446,6 @@ static int create_body(b200_ctx* c, const b200_dims* d, const b200_geometry* G, 
   if (const char* e = getenv("B200_ZFORM")) c->zform = atoi(e);
   if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
-  if (const char* e = getenv("B200_TMA")) c->tma = atoi(e);
-  {
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   build_csr(T, c->h_off, c->h_mem);
   {  // Topologies.local_neighboring_elements: elements sharing a vertex, from the vertex tables (limiter bounds)
     const int nh = d->nh;
@@ -996,15 +985,6 @@ extern "C" int b200_axpy_n(b200_ctx* c, void* Uc, void* Uf, const void* uc, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// bulk asynchronous copies need 16-byte-aligned global addresses (element strides are multiples of 64·nv bytes, so the bases decide)
-template <class... P>
-static bool aligned16(const P*... p) { return (((uintptr_t)p | ...) & 15) == 0; }
-// persistent grid: at most `max_ctas` CTAs, every CTA the same number of work items (± 1)
-static int persistent_grid(int items, int max_ctas) {
-  const int iters = (items + max_ctas - 1) / max_ctas;
-  return (items + iters - 1) / iters;
-}
-
 template <class FT>
 static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s,
                             void* Ylc = nullptr) {
@@ -1028,25 +1008,6 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
   } else if (phase == 1 && hd) {
     DssField F = {c->H, c->ncf(), 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d, ∇²χ…
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
-  } else if (phase == 2 && hd && c->tma && aligned16(Yc, c->H, Ytc, Ytf, c->d_hgeo)) {
-    // persistent, bulk-copy-fed kernel (kernels_tma.cuh): CTAs resident per SM × SMs, split over the three parts, every CTA the same
-    // number of elements (± 1)
-    int per_sm = 0;
-    if (nv63) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_exp_c<FT, 63>, CT, smem_k6c<FT>()));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_exp_c<FT, 0>, CT, smem_k6c<FT>()));
-    const int gx = persistent_grid(c->dims.nh, std::max(1, per_sm * c->num_sms / 3));
-    if (nv63)
-      launchx(c->pdl & 2, k6_exp_c<FT, 63>, dim3(gx, 3), CT, smem_k6c<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
-    else
-      launchx(c->pdl & 2, k6_exp_c<FT, 0>, dim3(gx, 3), CT, smem_k6c<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
-    LAUNCH_CHECK(c);
-    if (c->dims.n_tracers > 0) {
-      k5_tracer_c<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(0), s>>>(
-          make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)c->H, (FT*)(Ylc ? Ylc : Ytc));
-      LAUNCH_CHECK(c);
-    }
   } else if (phase == 2 && hd) {
     if (nv63)
       launchx(c->pdl & 2, k5_exp_c<FT, 63>, dim3(c->dims.nh, 3), CT, smem_rowq<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,

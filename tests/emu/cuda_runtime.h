@@ -19,7 +19,6 @@
 
 struct uint3_emu { unsigned x, y, z; };
 extern thread_local uint3_emu threadIdx, blockIdx;
-extern uint3_emu gridDim;  // only the persistent kernels read it (defined by the harness that runs them)
 extern std::barrier<>* g_cta_barrier;
 inline void __syncthreads() { g_cta_barrier->arrive_and_wait(); }
 struct float2 { float x, y; };

@@ -8,7 +8,6 @@
 #define b200 b200_emux
 #include "cuda_runtime.h"
 thread_local uint3_emu threadIdx, blockIdx;
-uint3_emu gridDim = {1, 1, 1};
 std::barrier<>* g_cta_barrier = nullptr;
 namespace b200 { alignas(128) unsigned char smem_raw[256 * 1024]; }
 #define __constant__
@@ -43,7 +42,6 @@ __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.w
 #include "kernels_row.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
-#include "kernels_tma.cuh"
 
 using namespace b200;
 typedef double FT;
@@ -65,18 +63,10 @@ static void run_grid(int nx, int ny, F&& body) {
     });
   for (auto& x : th) x.join();
 }
-// persistent kernels: the grid IS the set of CTAs (gridDim.x of them per part), each walks its elements itself
-template <class F>
-static void run_persistent(int gx, int ny, F&& body) {
-  gridDim = {(unsigned)gx, (unsigned)ny, 1};
-  run_grid(gx, ny, body);
-  gridDim = {1, 1, 1};
-}
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, ν₄ᵥ, ν₄ₛ, divergence damping factor, hyperdiff, rayleigh, viscous,
 //     energy upwinding, ncf, tracer upwinding ; vl: [14][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw, bruh, bvc, bvf ; D [16], w [4]
-// which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k5_exp_c (reads H, updates Ytc, Ytf), 2 / 3 = k5_tracer_a / k5_tracer_c,
-//        11 = k6_exp_c (persistent, bulk-copy-fed twin of k5_exp_c; 3 CTAs per part walk the elements)
+// which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k5_exp_c (reads H, updates Ytc, Ytf), 2 / 3 = k5_tracer_a / k5_tracer_c
 extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh, int nv, const double* sc, const double* vl, const double* Dm,
                                                                const double* w, const double* hgeo, const double* Yc, const double* Yf,
                                                                double* Ytc, double* Ytf, double* H, double* Ylc) {
@@ -108,7 +98,6 @@ extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh
   const int ntr = P.ncf - 4;
   if (which == 0) run_grid(nh, 1, [&] { k5_exp_a<FT, 0>(P, hgeo, &V, Yc, Yf, Ytc, Ytf, H); });
   else if (which == 1) run_grid(nh, 3, [&] { k5_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
-  else if (which == 11) run_persistent(nh < 3 ? nh : 3, 3, [&] { k6_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
   // passive tracers (grid = elements × tracers): 2 = k5_tracer_a (Yₜ, Yₜ_lim, ∇²χ → H), 3 = k5_tracer_c (tracer hyperdiffusion → Yₜ_lim)
   else if (which == 2) run_grid(nh, ntr, [&] { k5_tracer_a<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ylc, H); });
   else run_grid(nh, ntr, [&] { k5_tracer_c<FT>(P, hgeo, &V, Yc, H, Ylc); });

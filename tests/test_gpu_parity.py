@@ -468,7 +468,7 @@ def test_full_size_properties_he30_ze63_f32():
 def _steps_with_env(env, FT, name, nsteps=3, **kw):
     import os
 
-    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_GENERIC_NV", "B200_ZFORM", "B200_STIFF_FINAL", "B200_PDL", "B200_TMA")
+    keys = ("B200_FUSE_AXDSS", "B200_GRAPH", "B200_GENERIC_NV", "B200_ZFORM", "B200_STIFF_FINAL", "B200_PDL")
     old = {k: os.environ.pop(k, None) for k in keys}
     os.environ.update(env)
     try:
@@ -500,20 +500,6 @@ def test_fused_increment_dss_and_graph_are_bitwise_neutral(FT, name):
     (tc, tf), _ = _steps_with_env({"B200_FUSE_AXDSS": "0", "B200_GRAPH": "0"}, FT, name, tracers=_tracer_fns())
     (hc, hf), _ = _steps_with_env({}, FT, name, tracers=_tracer_fns())
     assert np.array_equal(tc, hc) and np.array_equal(tf, hf)
-
-
-@pytest.mark.parametrize("FT", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["he4ze10", "he3ze63", "he2ze2"])
-def test_persistent_bulk_copy_kernels_are_bitwise_identical(FT, name):
-    """kernels_tma.cuh: the persistent kernels fed by cp.async.bulk + mbarrier (the default) perform the arithmetic of the
-    one-CTA-per-element kernels with direct global loads (B200_TMA=0) in the same order — three steps give bitwise the same state,
-    with the nv = 63 specialisation and with the run-time-nv build."""
-    (rc, rf), _ = _steps_with_env({"B200_TMA": "0"}, FT, name)
-    (gc, gf), _ = _steps_with_env({}, FT, name)
-    assert np.array_equal(rc, gc) and np.array_equal(rf, gf)
-    (hc, hf), _ = _steps_with_env({"B200_GENERIC_NV": "1"}, FT, name)
-    (kc, kf), _ = _steps_with_env({"B200_GENERIC_NV": "1", "B200_TMA": "0"}, FT, name)
-    assert np.array_equal(hc, kc) and np.array_equal(hf, kf)
 
 
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
