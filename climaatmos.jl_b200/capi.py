@@ -19,7 +19,7 @@ REPO_ROOT = os.path.dirname(_HERE)
 SYMBOLS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_nccl_unique_id", "b200_cache_imp",
     "b200_t_exp_lim", "b200_t_imp", "b200_wfact", "b200_ldiv", "b200_t_post_imp", "b200_dss",
-    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase", "b200_implicit_stage", "b200_lim",
+    "b200_axpy_n", "b200_step_ars343", "b200_launch_count", "b200_halo_export", "b200_halo_import", "b200_build_dss_csr", "b200_debug_dss_csr", "b200_t_exp_phase", "b200_implicit_stage", "b200_lim", "b200_debug_jacobian",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     lib.b200_dss.argtypes = [vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, vp]
     lib.b200_axpy_n.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(dbl), vp]
     lib.b200_step_ars343.argtypes = [vp, vp, vp, dbl, i32, vp]
+    lib.b200_debug_jacobian.argtypes = [vp, vp, C.c_int64, vp]
     lib.b200_debug_dss_csr.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     lib.b200_build_dss_csr.argtypes = [C.POINTER(Topology), vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)]
     _lib = lib

@@ -686,6 +686,18 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
   LAUNCH_CHECK(c);
   return 0;
 }
+// Debug/test aid: copy the Jacobian coefficient planes stored by the last b200_wfact — [nh][15][16][nv+1] values of FT in the order of
+// the JC_* enum (kernels_implicit.cuh): Schur tridiagonal l, d, u of the u₃ rows; (u₃,ρ), (u₃,ρe_tot), (u₃,uₕ₁), (u₃,uₕ₂) bidiagonals
+// (lo, hi = centres f−1, f); (ρ,u₃), (ρe_tot,u₃) bidiagonals (lo, hi = faces k, k+1) — into a caller-owned DEVICE buffer.
+extern "C" int b200_debug_jacobian(b200_ctx* c, void* dst, int64_t capacity_bytes, void* stream) {
+  CtxScope scope_(c);
+  if (!c) return fail("b200_debug_jacobian: null context");
+  if (!c->d_jac) return fail("b200_debug_jacobian: b200_wfact has not been called");
+  const size_t bytes = (size_t)c->dims.nh * JC_N * 16 * (c->dims.nv + 1) * (size_t)c->ft;
+  if ((size_t)capacity_bytes < bytes) return fail("b200_debug_jacobian: destination too small");
+  CK(cudaMemcpyAsync(dst, c->d_jac, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
 extern "C" int b200_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_ldiv: null context");

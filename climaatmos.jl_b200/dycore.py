@@ -187,6 +187,14 @@ class AtmosSimulation:
         """Wfact (jacobian.jl:74-75)."""
         capi.check(self.lib.b200_wfact(self.ctx, _p(Y.c), _p(Y.f), float(dtgamma), float(t), self._stream()), "b200_wfact", self.ctx)
 
+    def jacobian_planes(self):
+        """Debug/test aid: the coefficient planes stored by the last Wfact as a tensor [nh, 15, 16, nv + 1] (b200_debug_jacobian)."""
+        nh, nf = int(self.Y.c.shape[0]), self.grid.nv + 1
+        out = self.torch.empty((nh, 15, 16, nf), dtype=self.Y.c.dtype, device=self.device)
+        capi.check(self.lib.b200_debug_jacobian(self.ctx, C.c_void_p(out.data_ptr()), out.numel() * out.element_size(), self._stream()),
+                   "b200_debug_jacobian", self.ctx)
+        return out
+
     def ldiv(self, dY, R):
         """ldiv!(ΔY, jacobian, R) (jacobian.jl:78-82)."""
         capi.check(self.lib.b200_ldiv(self.ctx, _p(dY.c), _p(dY.f), _p(R.c), _p(R.f), self._stream()), "b200_ldiv", self.ctx)

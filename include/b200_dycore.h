@@ -178,6 +178,11 @@ int b200_build_dss_csr(const b200_topology*, int32_t* off_out, int32_t cap_nodes
 /* Debug: the CSR actually held by a context (after dropping nodes without a local member). */
 int b200_debug_dss_csr(b200_ctx*, const int32_t** off, const int32_t** mem, int32_t* nnodes,
                        int32_t* nmem);
+/* Debug/test aid: copy the Jacobian coefficient planes of the last b200_wfact into a caller-owned DEVICE buffer of FT:
+ * [nh][15][16][nv+1] = Schur tridiagonal (l, d, u) of the u₃ rows; the (u₃,ρ), (u₃,ρe_tot), (u₃,uₕ₁), (u₃,uₕ₂) bidiagonals
+ * (lo, hi = centres f−1, f); the (ρ,u₃), (ρe_tot,u₃) bidiagonals (lo, hi = faces k, k+1) — the blocks of
+ * manual_sparse_jacobian.jl:746-868, so that Wfact can be tested on its own and not only through ldiv!. */
+int b200_debug_jacobian(b200_ctx*, void* dst_device, int64_t capacity_bytes, void* stream);
 /* Number of kernels launched by this context since creation (bench evidence). */
 int64_t b200_launch_count(b200_ctx*);
 
