@@ -17,6 +17,7 @@
 #include "kernels_implicit.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_lvl.cuh"
 #include "kernels_imp5.cuh"
 #include "kernels_limiter.cuh"
 #include "kernels_vdiff.cuh"
@@ -421,9 +422,7 @@ template <class FT> static size_t smem_rowq(int n) { return (HG_ELEM * 16 + (siz
 template <class FT>
 static int set_attrs() {
   CK(cudaFuncSetAttribute(k5_exp_a<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
-  CK(cudaFuncSetAttribute(k5_exp_c<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
   CK(cudaFuncSetAttribute(k5_exp_a<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
-  CK(cudaFuncSetAttribute(k5_exp_c<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(2)));
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
@@ -1021,12 +1020,14 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     DssField F = {c->H, c->ncf(), 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d, ∇²χ…
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
   } else if (phase == 2 && hd) {
+    const dim3 g7((c->dims.nh + LVL_EPB - 1) / LVL_EPB, 3);
+    const size_t sm7 = LVL_EPB * 16 * sizeof(FT);
     if (nv63)
-      launchx(c->pdl & 2, k5_exp_c<FT, 63>, dim3(c->dims.nh, 3), CT, smem_rowq<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                      (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+      launchx(c->pdl & 2, k7_exp_c<FT, 63>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     else
-      launchx(c->pdl & 2, k5_exp_c<FT, 0>, dim3(c->dims.nh, 3), CT, smem_rowq<FT>(2), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                     (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+      launchx(c->pdl & 2, k7_exp_c<FT, 0>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
       k5_tracer_c<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(0), s>>>(

@@ -30,7 +30,7 @@ __device__ __forceinline__ void dxi4p(const P2<FT> (&a)[2], P2<FT> (&o)[2]) {
 }
 // ξ²-contraction o_j = Σ_k M[j][k]·a_k over the four lanes j = lane>>3 of a level, as a REDUCE-SCATTER: every lane multiplies its
 // own row by the matrix COLUMN it owns and the partial sums travel in two butterfly steps (lanes ^16, then ^8) — 3 shuffles per
-// value instead of the 4 of a gather (ncu: the LSU pipe, i.e. the shuffles, is the busiest pipe of k5_exp_a / k5_exp_c).
+// value instead of the 4 of a gather (ncu: the LSU pipe, i.e. the shuffles, is the busiest pipe of k5_exp_a).
 // `m` is the column in butterfly order (ROW_COLUMNS below): m[k] = M[j ^ k][j].
 template <class FT>
 __device__ __forceinline__ P2<FT> shflxp(const P2<FT>& a, int mask) {
@@ -85,12 +85,9 @@ __device__ __forceinline__ void sputp(FT* s, const P2<FT> (&a)[2], int j, int v)
   s[(j * 4 + 0) * LVP + v] = a[0].lo(); s[(j * 4 + 1) * LVP + v] = a[0].hi();
   s[(j * 4 + 2) * LVP + v] = a[1].lo(); s[(j * 4 + 3) * LVP + v] = a[1].hi();
 }
-// Pair-layout exchange slabs for k5_exp_a / k5_exp_c: s[(2j + p)·XLV + v] holds the pair p of row j at level v as ONE 64-bit word
+// Pair-layout exchange slabs for k5_exp_a: s[(2j + p)·XLV + v] holds the pair p of row j at level v as ONE 64-bit word
 // (STS.64 / LDS.64: half the LSU instructions of the scalar slabs).  XLV = 68: the row stride 2·XLV pairs = 272 words ≡ 16 (mod 32)
 // puts the two rows of a half-warp on disjoint banks (the scalar slabs with stride 65 were 2-way conflicted).
-#ifndef EXPC_MINB
-#define EXPC_MINB 5  // 47 registers, no spills: 5 CTAs/SM (73.2 → 70.6 µs; 6 CTAs/SM spills: 74.7 µs)
-#endif
 constexpr int XLV = 68;
 constexpr int XSLAB = 8 * XLV * 2;  // FT words per pair slab
 template <class FT>
@@ -336,101 +333,6 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     }
     st4q(t1, gT + 16 * nv, nv);
     st4q(t2, gT + 32 * nv, nv);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-template <class FT, int NVC>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? EXPC_MINB : 2))
-k5_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
-  using V = P2<FT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FT* hg = reinterpret_cast<FT*>(smem_raw);
-  FT* s_w = hg + HG_ELEM * 16;
-  FT* s_a = s_w + XSLAB;
-  pdl_launch();
-  B200_ROW_PROLOGUE_NV(NVC)
-  ROW_COLUMNS
-  pdl_wait(Yc, H, Ytc, Ytf);
-  const int part = blockIdx.y;
-  const size_t offc = (size_t)e * P.ncf * 16 * nv + (n0 * nv + v);
-  const FT* gH = H + offc;
-  FT* gT = Ytc + offc;
-  FT* gF = Ytf + ((size_t)e * 16 * nf + (n0 * nf + v));
-  V a[2], b[2], g1[2];
-  if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
-    V L1[2], L2[2], old1[2], old2[2];
-    ld4q(L1, gH, nv, cv, FT(0)); ld4q(L2, gH + 16 * nv, nv, cv, FT(0));
-    ld4q(old1, gT + 16 * nv, nv, cv, FT(0)); ld4q(old2, gT + 32 * nv, nv, cv, FT(0));
-    __syncthreads();
-    V U1[2], U2[2], D2[2], ze[2], dD1[2], dz1[2];
-    METRIC_FLUX(U1, U2, L1, L2, HGP(HG_J2, p))
-    div4p<FT, 0>(U1, U2, md, vl, D2);
-    deta4p(L1, md, vl, a);
-    dxi4p<FT, 0>(L2, g1);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      D2[p] = D2[p] * HGP(HG_RJ2, p);
-      ze[p] = (g1[p] - a[p]) * HGP(HG_RJ2, p);
-    }
-    deta4p(D2, mw, vl, a); deta4p(ze, mw, vl, b);
-    dxi4p<FT, 1>(D2, dD1); dxi4p<FT, 1>(ze, dz1);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      V rJ2 = HGP(HG_RJ2, p);
-      V Qa = (dD1[p] * P.ddf - (HGP(HG_GC11, p) * b[p] - HGP(HG_GC12, p) * dz1[p]) * rJ2) * L.sc;
-      V Qb = (a[p] * P.ddf - (HGP(HG_GC12, p) * b[p] - HGP(HG_GC22, p) * dz1[p]) * rJ2) * L.sc;
-      old1[p] = old1[p] - Qa * P.nu4v; old2[p] = old2[p] - Qb * P.nu4v;
-    }
-    if (cv) { st4q(old1, gT + 16 * nv, nv); st4q(old2, gT + 32 * nv, nv); }
-  } else if (part == 1) {  // Yₜ.ρe_tot −= ν₄ₛ wdivₕ(ρ gradₕ(∇²s_d))  (hyperdiffusion.jl:291,307)
-    V rho[2], Ls[2], old3[2], Q1[2], Q2[2];
-    ld4q(rho, Yc + offc, nv, cv, FT(1));
-    ld4q(Ls, gH + 48 * nv, nv, cv, FT(0));
-    ld4q(old3, gT + 48 * nv, nv, cv, FT(0));
-    __syncthreads();
-    deta4p(Ls, md, vl, a);
-    dxi4p<FT, 0>(Ls, g1);
-    METRIC_FLUX(Q1, Q2, g1, a, rho[p] * HGP(HG_J2, p))
-    div4p<FT, 1>(Q1, Q2, mw, vl, b);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) old3[p] = old3[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
-    if (cv) st4q(old3, gT + 48 * nv, nv);
-  } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u))  (hyperdiffusion.jl:277)
-    V rho[2], L3[2], oldf[2], P1[2], P2_[2], q[2], w[2];
-    ld4q(rho, Yc + offc, nv, cv, FT(1));
-    ld4q(L3, gH + 32 * nv, nv, cv, FT(0));
-    ld4q(oldf, gF, nf, fv, FT(0));
-    __syncthreads();
-    deta4p(L3, md, vl, a);
-    dxi4p<FT, 0>(L3, g1);
-    METRIC_FLUX(P1, P2_, g1, a, HGP(HG_J2, p))
-    div4p<FT, 1>(P1, P2_, mw, vl, b);
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      q[p] = (b[p] * L.sc) * HGP(HG_RJ2, p);
-      w[p] = rho[p] * L.mc;
-    }
-    sputq(s_w, w, j, v); sputq(s_a, q, j, v);
-    __syncthreads();
-    if (fv) {
-      V wl[2], ql[2];
-      const int vm = v > 0 ? v - 1 : 0;
-      sgetq(s_w, wl, j, vm); sgetq(s_a, ql, j, vm);
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        V val;
-        if (v == 0) val = q[p];
-        else if (v == nv) val = ql[p];
-        else {
-          V num = fma2(w[p], q[p], wl[p] * ql[p]), den = wl[p] + w[p];
-          val = V(num.lo() / den.lo(), num.hi() / den.hi());
-        }
-        oldf[p] = oldf[p] - val * P.nu4v;
-      }
-      st4q(oldf, gF, nf);
-    }
   }
 }
 

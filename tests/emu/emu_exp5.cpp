@@ -1,4 +1,4 @@
-// CPU emulation of the explicit-tendency kernels of the benchmarked step, k5_exp_a and k5_exp_c (kernels_pair.cuh; Float64
+// CPU emulation of the explicit-tendency kernels of the benchmarked step, k5_exp_a (kernels_pair.cuh) and k7_exp_c (kernels_lvl.cuh; Float64
 // instantiations), from their unchanged source.  On top of the CTA emulator of emu_vdiff.cpp this one emulates warp shuffles: the 32
 // host threads of a warp meet at a per-warp barrier, publish their value, and read the source lane's (all shuffles of these kernels are
 // executed by full, converged warps).  griddepcontrol.* assembles to nothing; the packed-Float32 PTX is not instantiated.
@@ -24,6 +24,7 @@ template <class T> inline T shfl_emu(T v, int src_lane) {
 }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return shfl_emu(v, (int)(threadIdx.x & 31) ^ m); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return shfl_emu(v, src); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return shfl_emu(v, l >= d ? l - d : l); }
 inline void __syncwarp(unsigned = 0xffffffffu) { g_warp[threadIdx.x >> 5].bar.arrive_and_wait(); }
 inline int __any_sync(unsigned, int pred) {
   WarpX& w = g_warp[threadIdx.x >> 5];
@@ -42,6 +43,7 @@ __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.w
 #include "kernels_row.cuh"
 #include "kernels_row.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_lvl.cuh"
 
 using namespace b200;
 typedef double FT;
@@ -66,7 +68,8 @@ static void run_grid(int nx, int ny, F&& body) {
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, ν₄ᵥ, ν₄ₛ, divergence damping factor, hyperdiff, rayleigh, viscous,
 //     energy upwinding, ncf, tracer upwinding ; vl: [14][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw, bruh, bvc, bvf ; D [16], w [4]
-// which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k5_exp_c (reads H, updates Ytc, Ytf), 2 / 3 = k5_tracer_a / k5_tracer_c
+// which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k7_exp_c (kernels_lvl.cuh: reads H, updates Ytc, Ytf; one thread per (element, level), 4 elements per CTA),
+//        2 / 3 = k5_tracer_a / k5_tracer_c
 extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh, int nv, const double* sc, const double* vl, const double* Dm,
                                                                const double* w, const double* hgeo, const double* Yc, const double* Yf,
                                                                double* Ytc, double* Ytf, double* H, double* Ylc) {
@@ -97,7 +100,7 @@ extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh
   P.tupw = (int)sc[17];
   const int ntr = P.ncf - 4;
   if (which == 0) run_grid(nh, 1, [&] { k5_exp_a<FT, 0>(P, hgeo, &V, Yc, Yf, Ytc, Ytf, H); });
-  else if (which == 1) run_grid(nh, 3, [&] { k5_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
+  else if (which == 1) run_grid((nh + LVL_EPB - 1) / LVL_EPB, 3, [&] { k7_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
   // passive tracers (grid = elements × tracers): 2 = k5_tracer_a (Yₜ, Yₜ_lim, ∇²χ → H), 3 = k5_tracer_c (tracer hyperdiffusion → Yₜ_lim)
   else if (which == 2) run_grid(nh, ntr, [&] { k5_tracer_a<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ylc, H); });
   else run_grid(nh, ntr, [&] { k5_tracer_c<FT>(P, hgeo, &V, Yc, H, Ylc); });

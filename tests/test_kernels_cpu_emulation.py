@@ -1,7 +1,7 @@
 """The CUDA kernel sources of climaatmos.jl_b200/csrc, executed on the CPU: tests/emu/ compiles the kernel headers UNCHANGED with g++
 against a stub cuda_runtime.h and runs each CTA with 256 host threads — a std::barrier for __syncthreads(), per-warp barriers and an
 exchange buffer for warp shuffles / votes / __syncwarp (emu_exp5.cpp) — and the results are compared with the oracle (Float64
-instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k5_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_ldiv2, k_t_post_imp2), and
+instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k7_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_ldiv2, k_t_post_imp2), and
 the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
 Test infrastructure only: it checks indexing, phase structure and arithmetic of the very code that runs on the B200, not timing and
@@ -399,7 +399,7 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
 
 @pytest.fixture(scope="module")
 def emux():
-    """tests/emu/emu_exp5.cpp: k5_exp_a / k5_exp_c (Float64 instantiations) on the CTA emulator with emulated warp shuffles."""
+    """tests/emu/emu_exp5.cpp: k5_exp_a / k7_exp_c (Float64 instantiations) on the CTA emulator with emulated warp shuffles."""
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     out = os.path.join(HERE, "emu", "_build")
@@ -431,7 +431,7 @@ def _full_hgeo(g, P, deep):
 
 @pytest.mark.parametrize("deep,sponge,ze,dzb", [(True, True, 12, 400.0), (False, False, 12, 400.0), (True, True, 63, 30.0), (True, False, 3, 8000.0)])
 def test_emulated_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze, dzb):
-    """k5_exp_a and k5_exp_c — the two explicit-tendency kernels of the benchmarked step (packed row layout, ξ² contractions by warp
+    """k5_exp_a and k7_exp_c — the two explicit-tendency kernels of the benchmarked step (packed row layout, ξ² contractions by warp
     shuffles) — run on the CPU from their unchanged source (Float64 instantiation): the pre-DSS tendencies and ∇² fields against the
     oracle's element-local `_rt_pre`, the hyperdiffusion apply against `_rt_post` on the same ∇² fields."""
     P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
@@ -639,7 +639,7 @@ def test_emulated_fused_increment_dss_matches_oracle(emud, he, ze, ntr, dmask):
 
 @pytest.mark.parametrize("deep,sponge,he,ze,dzb", [(True, True, 2, 12, 400.0), (False, False, 3, 5, 3000.0)])
 def test_emulated_t_exp_composite_matches_oracle(emux, emud, deep, sponge, he, ze, dzb):
-    """T_exp_T_lim! as the library launches it — k5_exp_a → k_dss2 of the ∇² fields → k5_exp_c — entirely on the CPU emulator, against the
+    """T_exp_T_lim! as the library launches it — k5_exp_a → k_dss2 of the ∇² fields → k7_exp_c — entirely on the CPU emulator, against the
     oracle's remaining_tendency! (which includes its own weighted DSS of the ∇² fields)."""
     HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
     P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
@@ -695,10 +695,10 @@ def test_emulated_t_exp_composite_matches_oracle(emux, emud, deep, sponge, he, z
 def test_emulated_fused_step_matches_oracle_step(emux, emud, emu5, emu, vdiff):
     """One ARS343 step assembled from the emulated PRODUCT kernels in the data flow of the fused stepper (capi.cu: impl_step, fused path):
     stage-solution form of the increments (U_i = u + Σ α_ij (N_j − u) + dt Σ β_ij T_exp[j], k_axpy_dss with dmask), k5_imp_stage → k_dss2,
-    T_exp = k5_exp_a → k_dss2(∇²) → k5_exp_c, and the stiffly-accurate final increment from N₄ — against the oracle's LITERAL step
+    T_exp = k5_exp_a → k_dss2(∇²) → k7_exp_c, and the stiffly-accurate final increment from N₄ — against the oracle's LITERAL step
     (u + dt Σ bⱼ (T_exp[j] + T_imp[j]) with T_imp formed explicitly).  The host orchestration below restates impl_step's coefficient
     recursion; the arithmetic on the fields is all done by the kernels' own source.  With vertical diffusion: explicit → k_vdiff_tend2
-    after k5_exp_c; implicit → k_imp_stage_diff in place of k5_imp_stage (the data flow of the fused stepper)."""
+    after k7_exp_c; implicit → k_imp_stage_diff in place of k5_imp_stage (the data flow of the fused stepper)."""
     HG_DSSW, HG_A00, HG_AI00 = 13, 14, 18
     P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0, D_0_diffusion=40.0, H_diffusion=6000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=8, z_max=30000.0, dz_bottom=500.0, radius=P.planet_radius)
