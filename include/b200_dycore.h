@@ -13,6 +13,15 @@
  *     i.e. C order [h][f][j][i][v].  Y.c: Nf = 4 (ρ, uₕ₁, uₕ₂, ρe_tot), Nv levels;
  *     Y.f: Nf = 1 (u₃), Nv+1 levels.  Nq = 4 only.
  *   - there is NO CPU fallback: every compute entry point requires a CUDA device.
+ *
+ * Limits (checked by b200_create, which fails with a message instead of computing something else):
+ *   Nq = 4 (nh_poly 3); 2 <= nv <= 63 (a column of faces is one 64-lane row of the kernels); flat grid (NoWarp topography: the
+ *   metric is used in factored form, 2-D per-node part x per-level scale); dry thermodynamics + up to 4 PASSIVE tracers (no
+ *   active rho*q_tot: moist 0M needs Thermodynamics.jl's saturation adjustment); <= 32 neighbour ranks.
+ *   b200_step_ars343 is ARS343 with ONE Newton iteration per implicit stage (max_newton_iters_ode: 1, the reference's setting
+ *   for these configurations); any other stepper / Newton loop drives the individual hook entry points.  ldiv! is the direct
+ *   BlockArrowheadSolve (or the ApproximateBlockArrowheadIterativeSolve with implicit vertical diffusion); the Krylov
+ *   method of implicit/jacobian.jl:87-96 is not served.
  */
 #ifndef B200_DYCORE_H
 #define B200_DYCORE_H
