@@ -201,16 +201,8 @@ def pin_to_gpu_numa_node(local_rank):
     try:
         import torch
 
-        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bdf is None:
-            import pynvml
-
-            pynvml.nvmlInit()
-            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
-            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
-        bdf = bdf.lower()
-        if len(bdf.split(":")[0]) == 8:
-            bdf = bdf[4:]
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
         if node < 0:
             return None

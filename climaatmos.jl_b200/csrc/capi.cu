@@ -105,6 +105,8 @@ struct b200_ctx {
   int32_t* d_lim_ghost_node = nullptr;  // per ghost element: a node whose column this rank receives
   void* Tlc[4] = {nullptr, nullptr, nullptr, nullptr};  // T_lim of the four stages (stepper, limiter on)  // records [d_node_off[e], d_node_off[e+1]) are owned by local element e
   void* d_jac = nullptr;
+  void *d_jsnap_c = nullptr, *d_jsnap_f = nullptr;  // snapshot of the state Wfact was called with (dry path: ldiv! recomputes the coefficients)
+  double jsnap_dtg = 0; bool jac_planes_valid = false;
   void* d_jacd = nullptr;  // vertical-diffusion Jacobian planes (k_vdiff_jac)
   void* d_kdec = nullptr;  // [LV] DecayWithHeightDiffusion K(z_c)
   // native stepper storage (allocated lazily)
@@ -426,12 +428,13 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k5_tracer_a<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row<FT>(3)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_lim_vborrow<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_imp_stage_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_PROFILES * 4 * LVP * sizeof(FT))));
-  CK(cudaFuncSetAttribute(k_ldiv2<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(11 * SLAB * sizeof(FT))));
   return 0;
 }
 
@@ -568,7 +571,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off); fr(c->d_lim_nbr_off); fr(c->d_lim_nbr); fr(c->d_lim_bnd); fr(c->d_lim_E); fr(c->d_lim_ghost_node);
   for (int i = 0; i < 4; ++i) fr(c->Tlc[i]);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
-  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->d_jacd); fr(c->d_kdec); fr(c->H);
+  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->d_jsnap_c); fr(c->d_jsnap_f); fr(c->d_jacd); fr(c->d_kdec); fr(c->H);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Nsc[i]); fr(c->Nsf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
@@ -610,6 +613,14 @@ template <class FT>
 static int impl_cache_imp(b200_ctx* c, void* Yc, void* Yf, const b200_cacheptrs* o, cudaStream_t s) {
   b200_cacheptrs z = {};
   if (!o) o = &z;
+  if (!o->u_c && !o->u3_f && !o->K_c && !o->T_c && !o->p_c && !o->h_tot_c) {
+    // no p.precomputed field requested: all that is left of cache_imp! is the u₃ boundary filter (the tendency kernels recompute the
+    // thermodynamics from Y themselves, DESIGN.md "Deviations")
+    const int ncols = c->dims.nh * 16;
+    launchx(c->pdl & 8, k_u3_filter<FT>, dim3((2 * ncols + 255) / 256), dim3(256), 0, s, (FT*)Yf, ncols, c->dims.nv + 1);
+    LAUNCH_CHECK(c);
+    return 0;
+  }
   k_cache_imp<FT><<<c->dims.nh, NT, smem_slabs<FT>(1), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                           (const FT*)Yc, (FT*)Yf, (FT*)o->u_c, (FT*)o->u3_f, (FT*)o->K_c,
                                                           (FT*)o->T_c, (FT*)o->p_c, (FT*)o->h_tot_c);
@@ -647,19 +658,37 @@ extern "C" int b200_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, con
   return c->ft == 4 ? impl_t_imp<float>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream) : impl_t_imp<double>(c, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
 
+// Coefficient planes of the last Wfact (k_wfact2): what k_ldiv_diff consumes with implicit vertical diffusion, and what
+// b200_debug_jacobian exports.
 template <class FT>
-static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, cudaStream_t s) {
+static int launch_wfact_planes(b200_ctx* c, const void* Yc, const void* Yf, double dtg, cudaStream_t s) {
   if (!c->d_jac) CK(cudaMalloc(&c->d_jac, (size_t)c->dims.nh * JC_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
   k_wfact2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                               (const FT*)Yc, (const FT*)Yf, (FT)dtg, (FT*)c->d_jac);
   LAUNCH_CHECK(c);
-  if (vdiff_implicit(c)) {  // update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261)
+  c->jac_planes_valid = true;
+  return 0;
+}
+// Wfact (update_jacobian!).  Dry path: the Jacobian is a function of (Y, dtγ) only, so Wfact keeps a SNAPSHOT of Y (S bytes) and
+// ldiv! recomputes the band coefficients from it in registers (k5_imp_stage<…, LDIV>), instead of streaming 15 coefficient planes
+// (3·S) out here and back in there (profiles/r2_hook_path.md).  The snapshot (not the pointer) is kept because a stepper may update Y
+// between Wfact and a later ldiv! (Jacobian reuse across Newton iterations).
+template <class FT>
+static int impl_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, cudaStream_t s) {
+  c->jac_planes_valid = false;
+  if (vdiff_implicit(c)) {  // update_diffusion_jacobian! (manual_sparse_jacobian.jl:1031-1261): planes for k_ldiv_diff
+    if (launch_wfact_planes<FT>(c, Yc, Yf, dtg, s)) return -1;
     if (!c->d_jacd) CK(cudaMalloc(&c->d_jacd, (size_t)c->dims.nh * JD_N * 16 * (c->dims.nv + 1) * sizeof(FT)));
     k_vdiff_jac<FT><<<c->dims.nh, NT, smem_slabs<FT>(14), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
                                                              (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT)dtg,
                                                              (FT*)c->d_jacd);
     LAUNCH_CHECK(c);
+    return 0;
   }
+  if (!c->d_jsnap_c) { CK(cudaMalloc(&c->d_jsnap_c, c->nc() * sizeof(FT))); CK(cudaMalloc(&c->d_jsnap_f, c->nf() * sizeof(FT))); }
+  CK(cudaMemcpyAsync(c->d_jsnap_c, Yc, c->nc() * sizeof(FT), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(c->d_jsnap_f, Yf, c->nf() * sizeof(FT), cudaMemcpyDeviceToDevice, s));
+  c->jsnap_dtg = dtg;
   return 0;
 }
 extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dtg, double, void* stream) {
@@ -670,9 +699,8 @@ extern "C" int b200_wfact(b200_ctx* c, const void* Yc, const void* Yf, double dt
 
 template <class FT>
 static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const void* Rf, cudaStream_t s) {
-  if (!c->d_jac) return fail("b200_ldiv: b200_wfact has not been called");
   if (vdiff_implicit(c)) {  // ApproximateBlockArrowheadIterativeSolve (manual_sparse_jacobian.jl:538-578)
-    if (!c->d_jacd) return fail("b200_ldiv: b200_wfact has not been called");
+    if (!c->d_jac || !c->d_jacd) return fail("b200_ldiv: b200_wfact has not been called");
     // 16-lane Thomas sweeps (a parallel-cyclic-reduction version measured slower on B200: 15.2 vs 10.5 ms/step, profiles/r2_opt_in_validation.md)
     k_ldiv_diff<FT><<<c->dims.nh, NT, (22 * SLAB + LV) * sizeof(FT), s>>>(make_par<FT>(c), make_vdiff<FT>(c), (const VLev<FT>*)c->d_vlev,
                                                                  (const FT*)c->d_jac, (const FT*)c->d_jacd, (const FT*)Rc,
@@ -680,8 +708,17 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
     LAUNCH_CHECK(c);
     return 0;
   }
-  k_ldiv2<FT><<<c->dims.nh, NT, 11 * SLAB * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_jac, (const FT*)Rc, (const FT*)Rf,
-                                                           (FT*)dYc, (FT*)dYf);
+  if (!c->d_jsnap_c) return fail("b200_ldiv: b200_wfact has not been called");
+  // exact BlockArrowheadSolve (manual_sparse_jacobian.jl:579-584): Schur complement onto u₃, PCR, back-substitution — the coefficient
+  // code of the fused implicit stage on the Wfact snapshot
+  if (c->dims.nv == 63 && !c->generic_nv)
+    launchx(c->pdl & 16, k5_imp_stage<FT, 63, true>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo,
+            (const VLev<FT>*)c->d_vlev, (const FT*)c->d_jsnap_c, (const FT*)c->d_jsnap_f, (FT*)dYc, (FT*)dYf, (FT)c->jsnap_dtg, (const FT*)Rc,
+            (const FT*)Rf);
+  else
+    launchx(c->pdl & 16, k5_imp_stage<FT, 0, true>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo,
+            (const VLev<FT>*)c->d_vlev, (const FT*)c->d_jsnap_c, (const FT*)c->d_jsnap_f, (FT*)dYc, (FT*)dYf, (FT)c->jsnap_dtg, (const FT*)Rc,
+            (const FT*)Rf);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -691,7 +728,12 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
 extern "C" int b200_debug_jacobian(b200_ctx* c, void* dst, int64_t capacity_bytes, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_debug_jacobian: null context");
-  if (!c->d_jac) return fail("b200_debug_jacobian: b200_wfact has not been called");
+  if (!c->jac_planes_valid) {  // dry path: Wfact kept a snapshot; materialise the planes from it now
+    if (!c->d_jsnap_c) return fail("b200_debug_jacobian: b200_wfact has not been called");
+    const int rc = c->ft == 4 ? launch_wfact_planes<float>(c, c->d_jsnap_c, c->d_jsnap_f, c->jsnap_dtg, (cudaStream_t)stream)
+                              : launch_wfact_planes<double>(c, c->d_jsnap_c, c->d_jsnap_f, c->jsnap_dtg, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   const size_t bytes = (size_t)c->dims.nh * JC_N * 16 * (c->dims.nv + 1) * (size_t)c->ft;
   if ((size_t)capacity_bytes < bytes) return fail("b200_debug_jacobian: destination too small");
   CK(cudaMemcpyAsync(dst, c->d_jac, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -1208,10 +1250,10 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
   }
   if (c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k5_imp_stage<FT, 63>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else
     launchx(c->pdl & 16, k5_imp_stage<FT, 0>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   LAUNCH_CHECK(c);
   return 0;
 }

@@ -51,10 +51,16 @@ __device__ __forceinline__ void st2g(const P2<FT> (&a)[2], FT* __restrict__ g, i
 }
 
 // NVC: compile-time number of levels (63 for every production configuration: all global offsets become immediates); 0 = run-time
-template <class FT, int NVC>
+// LDIV = false: the fused implicit stage  N = U − J(U)⁻¹·dtγ·T_imp(U) [+ T_post_imp! correction]  (b200_implicit_stage, the fused stepper).
+// LDIV = true:  ldiv!(ΔY, J, R) of the hook path (jacobian.jl:78-82) with the SAME coefficient code: (Yc, Yf) is the snapshot of the
+//               state that Wfact was called with (b200_wfact keeps S bytes instead of writing 15 coefficient planes), (Rc, Rf) the
+//               right-hand side, (Nc, Nf) receive ΔY.  Differences to the stage: the residuals come from R instead of T_imp, the
+//               (u₃, uₕ) bidiagonal blocks enter the Schur right-hand side (R_uₕ = 0 in the stage), Δuₕ = −R_uₕ, Δ(ρχ) = −R_ρχ.
+template <class FT, int NVC, bool LDIV = false>
 __global__ void __launch_bounds__(256, 2)
 k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-             const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg) {
+             const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg, const FT* __restrict__ Rc = nullptr,
+             const FT* __restrict__ Rf = nullptr) {
   using V2 = P2<FT>;
   pdl_launch();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -72,7 +78,7 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   const FT sc2i = vlev->sc2i[vc], phi = vlev->phic[vc], mc = vlev->mc[vc], mclo = vlev->mc[vmc], rmc = vlev->rmc[vc],
            rmclo = vlev->rmc[vmc], g33lo = vlev->g33f[vf], g33hi = vlev->g33f[vf1], g33m = vlev->g33f[vm],
            dphif = vlev->dphif[vf], beta = P.rayleigh ? vlev->brw[vf] : FT(0);
-  pdl_wait(Yc, Yf, Nc, Nf);
+  pdl_wait(Yc, Yf, Nc, Nf, Rc, Rf);
   const int cs = 16 * nv;  // component stride of Y.c
   const FT* gY = Yc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + v);   // (ρ, node n0, level v) of this thread
   const FT* gYf = Yf + ((size_t)e * 16 * nf + n0 * nf + v);
@@ -83,7 +89,26 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
   ld2g(re, gY + 3 * cs, nv, cv, FT(0)); ld2g(u3, gYf, nf, interior, FT(0));  // u₃ boundary filter on load
 #pragma unroll
   for (int p = 0; p < 2; ++p) { s_rho[o0 + p * PLV] = rho[p]; s_u3[o0 + p * PLV] = u3[p]; }
-  if (cv) {  // uₕ is copied through (R_uₕ = 0); passive tracers: ΔU = 0
+  // ldiv!: the right-hand side at this level and the level below (second load: an L1 hit), and the state of the level below
+  V2 Rr[2], R1[2], R2[2], Re[2], R3[2], Rr_lo[2], R1_lo[2], R2_lo[2], Re_lo[2], u1_lo[2], u2_lo[2];
+  if (LDIV) {
+    const FT* gR = Rc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + v);
+    ld2g(Rr, gR, nv, cv, FT(0)); ld2g(R1, gR + cs, nv, cv, FT(0)); ld2g(R2, gR + 2 * cs, nv, cv, FT(0)); ld2g(Re, gR + 3 * cs, nv, cv, FT(0));
+    ld2g(R3, Rf + ((size_t)e * 16 * nf + n0 * nf + v), nf, fv, FT(0));
+    ld2g(Rr_lo, gR - 1, nv, interior, FT(0)); ld2g(R1_lo, gR + cs - 1, nv, interior, FT(0));
+    ld2g(R2_lo, gR + 2 * cs - 1, nv, interior, FT(0)); ld2g(Re_lo, gR + 3 * cs - 1, nv, interior, FT(0));
+    ld2g(u1_lo, gY + cs - 1, nv, interior, FT(0)); ld2g(u2_lo, gY + 2 * cs - 1, nv, interior, FT(0));
+    if (cv) {  // Δuₕ = −R_uₕ ((uₕ,uₕ) = −I), Δ(ρχ) = −R_ρχ (passive tracers: the fallback −I block, manual_sparse_jacobian.jl:476-481)
+      V2 m1[2] = {-R1[0], -R1[1]}, m2[2] = {-R2[0], -R2[1]};
+      st2g(m1, gN + cs, nv); st2g(m2, gN + 2 * cs, nv);
+      for (int q = 4; q < P.ncf; ++q) {
+        V2 t[2];
+        ld2g(t, gR + q * cs, nv, true, FT(0));
+        V2 m[2] = {-t[0], -t[1]};
+        st2g(m, gN + q * cs, nv);
+      }
+    }
+  } else if (cv) {  // uₕ is copied through (R_uₕ = 0); passive tracers: ΔU = 0
     st2g(u1, gN + cs, nv); st2g(u2, gN + 2 * cs, nv);
     for (int q = 4; q < P.ncf; ++q) {
       V2 t[2];
@@ -92,12 +117,17 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     }
   }
   const FT* hgp = hgeo + (size_t)e * HG_N * 16 + n0;
-  V2 Kh[2];
+  V2 Kh[2], ck1[2], ck2[2], ck1_lo[2], ck2_lo[2];  // ck: ∂K/∂uₕ = CT12(uₕ) at this centre and the one below (ldiv! only)
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     const V2 g11 = ldpair(hgp + HG_GI11 * 16 + 2 * p), g12 = ldpair(hgp + HG_GI12 * 16 + 2 * p), g22 = ldpair(hgp + HG_GI22 * 16 + 2 * p);
     const V2 c1 = fma2(g12, u2[p], g11 * u1[p]), c2 = fma2(g22, u2[p], g12 * u1[p]);
     Kh[p] = (fma2(u2[p], c2, u1[p] * c1) * sc2i) * FT(0.5);
+    if (LDIV) {
+      const FT sc2i_lo = vlev->sc2i[vmc];
+      ck1[p] = c1 * sc2i; ck2[p] = c2 * sc2i;
+      ck1_lo[p] = fma2(g12, u2_lo[p], g11 * u1_lo[p]) * sc2i_lo; ck2_lo[p] = fma2(g22, u2_lo[p], g12 * u1_lo[p]) * sc2i_lo;
+    }
   }
   __syncthreads();  // (1) ρ, u₃ slabs
   // ---- centre thermodynamics (level v) and face mass-flux pieces (face v)
@@ -142,7 +172,8 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       b0[p] = a0[p] * hf0; b1[p] = a1[p] * hfp;
       R0[p] = rho[p] + rr; E0[p] = re[p] + rre;
     }
-    cl[p] = cu[p] = cr[p] = V2(FT(0)); cd[p] = V2(dtg * (-beta) - FT(1));
+    cl[p] = cu[p] = V2(FT(0)); cd[p] = V2(dtg * (-beta) - FT(1));
+    cr[p] = LDIV ? R3[p] : V2(FT(0));  // boundary rows of ldiv!: x = R₃/(−dtγβ − 1)
     if (interior) {
       const V2 hfm = v > 1 ? (hm2 + hl) * FT(0.5) : V2(FT(0));
       const V2 Am = s_A[om], Mm = s_M[om], u3m = s_u3[om];
@@ -171,7 +202,12 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       const V2 re_a = ((Mh0 - Mm * hfm) * (-dtg)) * rmclo, re_b = ((Mp * hfp - Mh0) * (-dtg)) * rmc;
       const V2 tf = -((V2(dphif) - dphr) + (((thpl + thp) * FT(0.5)) * P.cp_d) * dPi) - u3[p] * beta;
       cl[p] = l; cd[p] = d; cu[p] = u;
-      cr[p] = fma2(tf, V2(dtg), fma2(ur_lo, rr_a, ur_hi * rr_b) + fma2(ue_lo, re_a, ue_hi * re_b));
+      if (LDIV) {  // Schur right-hand side R₃ + A₃ρ R_ρ + A₃e R_ρe + A₃uₕ R_uₕ  (A₃uₕ = dtγ·(−κρ/ᶠρ)·CT12(uₕ), manual_sparse_jacobian.jl:855-868)
+        const V2 xl = x_lo * dtg, xh = x_hi * dtg;
+        cr[p] = R3[p] + (fma2(ur_lo, Rr_lo[p], ur_hi * Rr[p]) + fma2(ue_lo, Re_lo[p], ue_hi * Re[p])) +
+                (fma2(xl * ck1_lo[p], R1_lo[p], (xh * ck1[p]) * R1[p]) + fma2(xl * ck2_lo[p], R2_lo[p], (xh * ck2[p]) * R2[p]));
+      } else
+        cr[p] = fma2(tf, V2(dtg), fma2(ur_lo, rr_a, ur_hi * rr_b) + fma2(ue_lo, re_a, ue_hi * re_b));
     }
   }
   V2 x0[2], x1[2];  // ΔU.f.u₃ at faces v and v+1
@@ -210,6 +246,17 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
     __syncthreads();
 #pragma unroll
     for (int p = 0; p < 2; ++p) x1[p] = bx[o0 + p * PLV - v + vp];
+  }
+  if (LDIV) {  // ΔY: Δu₃ = x, Δρ = A_ρ3 x − R_ρ, Δρe_tot = A_e3 x − R_ρe (back-substitution of the scalar rows; A₁₁ = −I)
+    V2 dr[2], de[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      dr[p] = fma2(a1[p], x1[p], a0[p] * x0[p]) - Rr[p];
+      de[p] = fma2(b1[p], x1[p], b0[p] * x0[p]) - Re[p];
+    }
+    if (cv) { st2g(dr, gN, nv); st2g(de, gN + 3 * cs, nv); }
+    if (fv) st2g(x0, gNf, nf);
+    return;
   }
   // ---- U ← U − ΔU (back-substitution of the scalar rows)
   V2 nr[2], nre[2], nu[2], nu1[2];

@@ -17,7 +17,7 @@
 //   k_vdiff_jac, k_ldiv_diff                     diffusion Jacobian planes; approximate arrowhead solve (16-lane Thomas sweeps)
 //   k_imp_stage_diff                             fused implicit stage with implicit diffusion (b200_implicit_stage, the fused stepper)
 //   k_lim_vborrow                                lim!: vertical mass-borrowing limiter (off unless configured)
-//   k_t_imp2, k_wfact2, k_t_post_imp2, k_ldiv2   the dry hook kernels (quarter element per CTA; PCR column solve)
+//   k_t_imp2, k_wfact2, k_t_post_imp2            the dry hook kernels (quarter element per CTA); ldiv! is k5_imp_stage<…, LDIV> (kernels_imp5.cuh)
 // Removed in round 2 after the A/B record was committed: the element-slab first generation (k_vdiff_tend, k_t_imp, k_wfact, k_ldiv,
 // k_t_post_imp: slower) and the PCR variants of the diffusion solve (k_vdiff_jac2 + k_ldiv_diff2: 15.2 vs 10.5 ms/step).
 //
@@ -532,106 +532,16 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
   if (v < nf) gF[n * nf + v] = FT(0);
 }
 
-// Parallel cyclic reduction of the 16 tridiagonal systems of an element in the slab layout (row i of column n at n·LVP + i), by all NT
-// threads: log₂ n elimination steps with strides 1, 2, 4, …; each step every row eliminates its two neighbours at the current stride
-//   r₋ = aᵢ/bᵢ₋ₛ, r₊ = cᵢ/bᵢ₊ₛ:  a′ = −r₋aᵢ₋ₛ, c′ = −r₊cᵢ₊ₛ, b′ = bᵢ − r₋cᵢ₋ₛ − r₊aᵢ₊ₛ, d′ = dᵢ − r₋dᵢ₋ₛ − r₊dᵢ₊ₛ
-// (rows outside [0, n) act as identity rows), then x = d/b.  (l, d, u) are left untouched — the matrix is copied into the work slabs
-// (wa, wb, wc) — and x holds the right-hand side on entry, the solution on exit.  Contains block barriers; starts and ends with one.
-// The systems here are strictly diagonally dominant (−I plus dtγ × a diffusion or acoustic operator), so no pivoting is needed.
-template <class FT>
-__device__ __forceinline__ void pcr_slab(const FT* l, const FT* d, const FT* u, FT* x, int n, FT* wa, FT* wb, FT* wc) {
-  __syncthreads();
-  for (int k = 0; k < NIT; ++k) {
-    const int idx = threadIdx.x + k * NT, o = (idx >> 6) * LVP + (idx & 63);
-    if ((idx & 63) < n) { wa[o] = l[o]; wb[o] = d[o]; wc[o] = u[o]; }
-  }
-  __syncthreads();
-  for (int s = 1; s < n; s <<= 1) {
-    FT na[NIT], nb[NIT], nc[NIT], nd[NIT];
-    for (int k = 0; k < NIT; ++k) {
-      const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
-      na[k] = nc[k] = nd[k] = FT(0); nb[k] = FT(1);
-      if (i < n) {
-        FT A = FT(0), B = wb[o], C = FT(0), Dd = x[o];
-        if (i - s >= 0) { const FT r = wa[o] / wb[o - s]; A = -r * wa[o - s]; B -= r * wc[o - s]; Dd -= r * x[o - s]; }
-        if (i + s < n) { const FT r = wc[o] / wb[o + s]; C = -r * wc[o + s]; B -= r * wa[o + s]; Dd -= r * x[o + s]; }
-        na[k] = A; nb[k] = B; nc[k] = C; nd[k] = Dd;
-      }
-    }
-    __syncthreads();
-    for (int k = 0; k < NIT; ++k) {
-      const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
-      if (i < n) { wa[o] = na[k]; wb[o] = nb[k]; wc[o] = nc[k]; x[o] = nd[k]; }
-    }
-    __syncthreads();
-  }
-  for (int k = 0; k < NIT; ++k) {
-    const int idx = threadIdx.x + k * NT, i = idx & 63, o = (idx >> 6) * LVP + i;
-    if (i < n) x[o] = x[o] / wb[o];
-  }
-  __syncthreads();
-}
-
-// k_ldiv with the 16-lane Thomas sweep replaced by parallel cyclic reduction over all threads (pcr_slab); round-off differences only.
-template <class FT>
-__global__ void __launch_bounds__(NT) k_ldiv2(Par<FT> P, const FT* __restrict__ jac, const FT* __restrict__ Rc,
-                                              const FT* __restrict__ Rf, FT* dYc, FT* dYf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<FT> sm(smem_raw);
-  FT* sl = sm.take(SLAB); FT* sd = sm.take(SLAB); FT* su = sm.take(SLAB); FT* sr = sm.take(SLAB);
-  FT* rr = sm.take(SLAB); FT* r1 = sm.take(SLAB); FT* r2 = sm.take(SLAB); FT* re = sm.take(SLAB);
-  FT* wa = sm.take(SLAB); FT* wb = sm.take(SLAB); FT* wc = sm.take(SLAB);
-  const int h = blockIdx.x, nv = P.nv, nf = nv + 1;
-  const FT* gj = jac + (size_t)h * JC_N * 16 * nf;
-  const size_t pl = (size_t)16 * nf;
-  const FT* gRc = Rc + (size_t)h * P.ncf * 16 * nv;
-  load_slab(sl, gj + JC_L * pl, nf); load_slab(sd, gj + JC_D * pl, nf); load_slab(su, gj + JC_U * pl, nf);
-  load_slab(rr, gRc, nv); load_slab(r1, gRc + 16 * nv, nv); load_slab(r2, gRc + 32 * nv, nv); load_slab(re, gRc + 48 * nv, nv);
-  __syncthreads();
-  const FT* gRf = Rf + (size_t)h * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, f = idx & 63;
-    if (f >= nf) continue;
-    size_t o = (size_t)n * nf + f;
-    int s = n * LVP + f;
-    FT rhs = gRf[o];
-    if (f > 0 && f < nv) {
-      rhs += gj[JC_UR_LO * pl + o] * rr[s - 1] + gj[JC_UR_HI * pl + o] * rr[s];
-      rhs += gj[JC_UE_LO * pl + o] * re[s - 1] + gj[JC_UE_HI * pl + o] * re[s];
-      rhs += gj[JC_U1_LO * pl + o] * r1[s - 1] + gj[JC_U1_HI * pl + o] * r1[s];
-      rhs += gj[JC_U2_LO * pl + o] * r2[s - 1] + gj[JC_U2_HI * pl + o] * r2[s];
-    }
-    sr[s] = rhs;
-  }
-  pcr_slab(sl, sd, su, sr, nf, wa, wb, wc);
-  FT* gdc = dYc + (size_t)h * P.ncf * 16 * nv;
-  FT* gdf = dYf + (size_t)h * 16 * nf;
-  for (int idx = threadIdx.x; idx < NN * LV; idx += NT) {
-    int n = idx >> 6, v = idx & 63;
-    int s = n * LVP + v;
-    size_t o = (size_t)n * nf + v;
-    if (v < nf) gdf[o] = sr[s];
-    if (v < nv) {
-      FT x0 = sr[s], x1 = sr[s + 1];
-      gdc[(0 * 16 + n) * nv + v] = gj[JC_RU_LO * pl + o] * x0 + gj[JC_RU_HI * pl + o] * x1 - rr[s];
-      gdc[(1 * 16 + n) * nv + v] = -r1[s];
-      gdc[(2 * 16 + n) * nv + v] = -r2[s];
-      gdc[(3 * 16 + n) * nv + v] = gj[JC_EU_LO * pl + o] * x0 + gj[JC_EU_HI * pl + o] * x1 - re[s];
-      for (int q = 4; q < P.ncf; ++q) gdc[(q * 16 + n) * nv + v] = -gRc[(q * 16 + n) * nv + v];
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Fused implicit stage WITH implicit vertical diffusion (B200_VDIFF_FUSED=1; matches the oracle's stage in the CPU CTA emulator, not
-// yet run on a B200): what b200_implicit_stage / k5_imp_stage do for the dry Jacobian, extended by the diffusion tendency, the
-// diffusion blocks and the approximate arrowhead iteration — cache_imp! (u₃ filter) → Wfact → R = dtγ·T_imp(U) → ldiv! → N = U − ΔU →
-// cache_imp! → T_post_imp! — in ONE kernel, out of place.  Quarter element per CTA, one point per thread; every coefficient profile
-// lives in shared memory (48 profiles of 4·LVP words: 50 KB in Float32), tridiagonal solves by parallel cyclic reduction with one row
-// per thread.  Algebra as in k_ldiv_diff (T-based Schur operator and preconditioner).
+// Fused implicit stage WITH implicit vertical diffusion (the default for implicit_diffusion since round 2; parity-green on a B200):
+// what b200_implicit_stage / k5_imp_stage do for the dry Jacobian, extended by the diffusion tendency, the diffusion blocks and the
+// approximate arrowhead iteration — cache_imp! (u₃ filter) → Wfact → R = dtγ·T_imp(U) → ldiv! → N = U − ΔU → cache_imp! → T_post_imp! —
+// in ONE kernel, out of place.  Quarter element per CTA, one point per thread; every coefficient profile lives in shared memory
+// (48 profiles of 4·LVP words: 50 KB in Float32), tridiagonal solves by parallel cyclic reduction with one row per thread.  Algebra
+// as in k_ldiv_diff (T-based Schur operator and preconditioner).
 constexpr int QD_PROFILES = 48;
 
-// PCR over the 4 columns of the CTA, one row per thread: thread (column, v) owns row v at index o; see pcr_slab.
+// PCR over the 4 columns of the CTA, one row per thread: thread (column, v) owns row v at index o.
 template <class FT>
 __device__ __forceinline__ void pcr_q(const FT* l, const FT* d, const FT* u, FT* x, int n, int o, int v, FT* wa, FT* wb, FT* wc) {
   __syncthreads();

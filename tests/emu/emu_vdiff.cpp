@@ -87,7 +87,7 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
   return 0;
 }
 
-// The dry hook kernels (k_cache_imp of kernels_implicit.cuh; k_t_imp2, k_wfact2, k_ldiv2, k_t_post_imp2 of kernels_vdiff.cuh; validated
+// The dry hook kernels (k_cache_imp of kernels_implicit.cuh; k_t_imp2, k_wfact2, k_t_post_imp2 of kernels_vdiff.cuh; validated
 // on the B200, emulated here so that the CPU test tier exercises the product source too): cache_imp! → T_imp! → Wfact → ldiv! → T_post_imp!.
 // sc as in emu_vdiff plus sc[16] = energy upwinding (0 | 1 | 3).  Sc/Sf are unused (kept for the call signature).  Outputs: Yf is filtered in place; Tc/pc/hc/Kc [nh][16][nv];
 // Ytc/Ytf (T_imp), dYc/dYf (ldiv of Rc/Rf), Ypc (T_post_imp centres), Sc/Sf (state after the fused stage).
@@ -109,7 +109,7 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
   run_grid(nh, [&] { k_cache_imp<FT>(P, hgeo, &V, Yc, Yf, (FT*)nullptr, (FT*)nullptr, Kc, Tc, pc, hc); });
   run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
   run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
-  run_grid(nh, [&] { k_ldiv2<FT>(P, jac, Rc, Rf, dYc, dYf); });
+  (void)Rc; (void)Rf; (void)dYc; (void)dYf;  // ldiv! of the dry path is k5_imp_stage<…, LDIV>: emu_imp5.cpp (emu_ldiv5)
   run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
   (void)Sc; (void)Sf;
   return 0;

@@ -1,7 +1,7 @@
 """The CUDA kernel sources of climaatmos.jl_b200/csrc, executed on the CPU: tests/emu/ compiles the kernel headers UNCHANGED with g++
 against a stub cuda_runtime.h and runs each CTA with 256 host threads — a std::barrier for __syncthreads(), per-warp barriers and an
 exchange buffer for warp shuffles / votes / __syncwarp (emu_exp5.cpp) — and the results are compared with the oracle (Float64
-instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k7_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_ldiv2, k_t_post_imp2), and
+instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k7_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_t_post_imp2; ldiv! = k5_imp_stage in LDIV mode), and
 the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
 Test infrastructure only: it checks indexing, phase structure and arithmetic of the very code that runs on the B200, not timing and
@@ -152,7 +152,7 @@ def test_emulated_vertical_mass_borrowing_kernel_matches_oracle(emu):
 
 @pytest.mark.parametrize("upw,rayleigh,deep", [("vanleer_limiter", True, True), ("first_order", False, False), ("none", False, True), ("third_order", True, True)])
 def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
-    """k_cache_imp, k_t_imp2, k_wfact2 → k_ldiv2, k_t_post_imp2 (quarter element per CTA, parallel cyclic reduction) on the CPU emulator
+    """k_cache_imp, k_t_imp2, k_wfact2, k_t_post_imp2 (quarter element per CTA) on the CPU emulator
     against the oracle's cache_imp! / T_imp! / Wfact + ldiv! / T_post_imp! (Float64)."""
     P = prm.DycoreParams(zd_rayleigh=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=12, z_max=30000.0, dz_bottom=400.0, radius=P.planet_radius, deep_atmosphere=deep)
@@ -198,11 +198,13 @@ def test_emulated_dry_hook_kernels_match_oracle(emu, upw, rayleigh, deep):
     tc, tf = o.implicit_tendency(oc, of, pc)
     assert rel(Ytc[:, 0], tc[:, 0]) < 1e-12 and rel(Ytc[:, 3], tc[:, 3]) < 1e-12 and rel(Ytf, tf) < 1e-11
     assert np.all(Ytc[:, 1:3] == 0)
+    # Wfact planes (k_wfact2: what the implicit-diffusion solve and b200_debug_jacobian consume) against the oracle's blocks; ldiv! of
+    # the dry path is k5_imp_stage<…, LDIV> (test_emulated_default_fused_implicit_stage_matches_oracle)
     Jm = o.update_jacobian(oc, of, pc, dtg)
-    dc, df = o.ldiv(Jm, Rc, Rf)
-    for k in range(4):
-        assert rel(dYc[:, k], dc[:, k]) < 1e-11, k
-    assert rel(dYf, df) < 1e-11
+    for k, w in ((3, Jm["u3_rho"][0]), (4, Jm["u3_rho"][1]), (5, Jm["u3_rhoe"][0]), (6, Jm["u3_rhoe"][1]), (7, Jm["u3_uh"][0][0]), (10, Jm["u3_uh"][1][1])):
+        assert rel(jac[:, k].reshape(nh, 4, 4, nv + 1), w) < 1e-11, k
+    for k, w in ((11, Jm["rho_u3"][0]), (12, Jm["rho_u3"][1]), (13, Jm["rhoe_u3"][0]), (14, Jm["rhoe_u3"][1])):
+        assert rel(jac[:, k].reshape(nh, 4, 4, nv + 1)[..., :-1], w) < 1e-11, k
     pc_c, pc_f = o.correct_implicit_advection_tendency(oc, of, pc)
     if upw != "none":  # with :none the host returns zeros without launching the kernel (capi.cu: impl_t_post)
         assert rel(Ypc[:, 3], pc_c[:, 3]) < 1e-10
@@ -395,6 +397,21 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
         assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
     assert rel(Nc[:, 0] - Yc[:, 0], Uc[:, 0] - Yc[:, 0]) < 1e-8 and rel(Nc[:, 3] - Yc[:, 3], Uc[:, 3] - Yc[:, 3]) < 1e-8
     assert rel(Nf, Uf) < 1e-10
+    # ldiv! of the hook path = the same kernel in LDIV mode on the state Wfact saw (b200_wfact keeps a snapshot): ΔY = J(Y, dtγ)⁻¹ R for a
+    # random right-hand side with ALL components non-zero (R_uₕ ≠ 0 exercises the (u₃, uₕ) blocks, R_ρχ the tracer fallback block)
+    Yf0 = Yf.copy()
+    Yf0[..., 0] = 0
+    Yf0[..., -1] = 0  # Wfact is called on a filtered state (cache_imp! precedes it)
+    pc = o.set_implicit_precomputed_quantities(Yc[:, :4].copy(), Yf0.copy())
+    Jm = o.update_jacobian(Yc, Yf0, pc, dtg)
+    Rc = np.ascontiguousarray(rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3)
+    Rf = np.ascontiguousarray(rng.standard_normal(Yf.shape))
+    dc, df = o.ldiv(Jm, Rc, Rf)
+    dYc, dYf = np.zeros_like(Yc), np.zeros_like(Yf)
+    assert emu5.emu_ldiv5(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf0), p(Rc), p(Rf), p(dYc), p(dYf)) == 0
+    for k in range(ncf):
+        assert rel(dYc[:, k], dc[:, k]) < 1e-11, ("ldiv", k, rel(dYc[:, k], dc[:, k]))
+    assert rel(dYf, df) < 1e-11, ("ldiv u3", rel(dYf, df))
 
 
 @pytest.fixture(scope="module")
