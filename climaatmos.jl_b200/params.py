@@ -41,6 +41,19 @@ class DycoreParams:
     C_E: float = 0.0044
     H_diffusion: float = 7000.0
     D_0_diffusion: float = 1.0
+    # moist thermodynamics (EquilibriumMicrophysics0M; docs/src/thermodynamics.md:60-150; Thermodynamics.jl 1.3.0 parameter names,
+    # ClimaParams defaults [UPSTREAM-RECALL]).  Calorically perfect constituents, reference temperature T_0 = triple point.
+    R_v: float = 8.3144598 / 0.01801528
+    cp_v: float = 1859.0
+    cp_l: float = 4181.0
+    cp_i: float = 2100.0
+    LH_v0: float = 2.5008e6
+    LH_s0: float = 2.8344e6
+    T_triple: float = 273.16
+    press_triple: float = 611.657
+    T_freeze: float = 273.15
+    T_icenuc: float = 233.0
+    pow_icenuc: float = 1.0
 
     @property
     def cp_d(self):
@@ -49,6 +62,22 @@ class DycoreParams:
     @property
     def cv_d(self):
         return self.cp_d - self.R_d
+
+    @property
+    def cv_v(self):
+        return self.cp_v - self.R_v
+
+    @property
+    def LH_f0(self):
+        return self.LH_s0 - self.LH_v0
+
+    @property
+    def e_int_v0(self):  # internal energy of vapour at T_0 (liquid water is the zero)
+        return self.LH_v0 - self.R_v * self.T_0
+
+    @property
+    def e_int_i0(self):
+        return self.LH_f0
 
 
 @dataclasses.dataclass
@@ -76,6 +105,10 @@ class DycoreNumerics:
     implicit_diffusion: bool = False
     approximate_linear_solve_iters: int = 1
     disable_momentum_vertical_diffusion: bool = False
+    # microphysics_model: None (DryModel) | "0M" (EquilibriumMicrophysics0M: ρq_tot is component 4 of Y.c, thermodynamically active,
+    # condensate diagnosed by saturation adjustment; the 0M precipitation sink itself is a parameterised tendency outside the dycore,
+    # BASELINE.json configs[2] "dycore + tracer advection only")
+    microphysics_model: str | None = None
 
 
 # ARS343 tableau (Ascher–Ruuth–Spiteri 1997 §2.7), as used by ClimaTimeSteppers' IMEXAlgorithm

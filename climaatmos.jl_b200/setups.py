@@ -88,6 +88,32 @@ def dry_baroclinic_wave(grid, params, perturb=True):
     return _assemble(grid, params, T, p, u, v)
 
 
+def moist_baroclinic_wave(grid, params, perturb=True, q_0=0.018):
+    """MoistBaroclinicWave (src/setups/MoistBaroclinicWave.jl:50-92): the dry wave with the moisture profile
+    q_tot = q_0 exp(−(φ/40°)⁴) exp(−((p − MSLP)/340 hPa)²) below 100 hPa (1e-12 above) and T = T_v/(1 + 0.608 q_tot); assembly by
+    src/setups/common/prognostic_variables.jl:44-85 with q_liq = q_ice = 0: ρ = p/(R_m T), ρe_tot = ρ(I(T, q_tot) + K + Φ) with the
+    moist internal energy of docs/src/thermodynamics.md:103-111, ρq_tot = ρ q_tot (component 4 of Y.c)."""
+    z = np.broadcast_to(grid.z_c[None, None, None, :], (grid.nelems, grid.nq, grid.nq, grid.nv))
+    lat = grid.lat[..., None]
+    lon = grid.lon[..., None]
+    T, p, u, v = _barowave_values(z, lat, lon, params, perturb=perturb, deep=grid.deep)
+    q = np.where(p <= 1.0e4, 1e-12, q_0 * np.exp(-((lat / 40.0) ** 4)) * np.exp(-(((p - params.MSLP) / 3.4e4) ** 2)))
+    T = T / (1 + 0.608 * q)
+    P = params
+    R_m = P.R_d * (1 - q) + P.R_v * q
+    cv_m = P.cv_d + (P.cv_v - P.cv_d) * q
+    Yc4, Yf = _assemble(grid, params, T, p, u, v)
+    rho = p / (R_m * T)
+    e_int = cv_m * (T - P.T_0) + q * P.e_int_v0 - (1 - q) * P.R_d * P.T_0
+    e_tot = e_int + 0.5 * (u * u + v * v) + P.grav * grid.z_c[None, None, None, :]
+    Yc = np.zeros((grid.nelems, 5, grid.nq, grid.nq, grid.nv), dtype=grid.FT)
+    Yc[:, 0] = rho
+    Yc[:, 1:3] = Yc4[:, 1:3]
+    Yc[:, 3] = rho * e_tot
+    Yc[:, 4] = rho * q
+    return Yc, Yf
+
+
 def decaying_profile(grid, params, perturb=True, T_s=290.0, T_min=220.0, H_t=8000.0):
     """Thermodynamics.jl ``DecayingTemperatureProfile`` [UPSTREAM-RECALL] + the 0.1 K
     longitudinal perturbation below 5 km of src/setups/DecayingProfile.jl:39-66; zero wind."""

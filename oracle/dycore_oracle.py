@@ -111,6 +111,8 @@ class Oracle:
                 tot[e, j, i] = ssum
         self.dss_w = np.asarray(WJ2 / tot, dtype=FT)
         self.lat_rad = np.radians(g.lat)[..., None]
+        if self.moist and (getattr(numerics, "vert_diff", None) or numerics.held_suarez):
+            raise ValueError("oracle: microphysics_model 0M is restated without vertical diffusion / Held–Suarez forcing")
 
     def slice(self, sl):
         """Shallow copy whose element-local arrays are views of the element range ``sl``; every tendency /
@@ -284,6 +286,123 @@ class Oracle:
         P, FT = self.P, self.FT
         return FT(P.cp_d) * (self.T_ref(p) - FT(P.T_0)) + self.phi_r(p)
 
+    # ------------------------------------------------------------------ moist thermodynamics (EquilibriumMicrophysics0M)
+    # Thermodynamics.jl 1.3.0 is not vendored; these restate its PUBLISHED formulation as documented in
+    # docs/src/thermodynamics.md:60-150 (calorically perfect constituents, Romps 2008 energy references, Rankine–Kirchhoff
+    # saturation vapour pressure, Pressel 2015 liquid-fraction-weighted latent heat, Kaul 2015 supercooled-liquid ramp)
+    # and are anchored on the reference's call sites (precomputed_quantities.jl:735-815, manual_sparse_jacobian.jl:653-690).
+    @property
+    def moist(self):
+        return getattr(self.N, "microphysics_model", None) == "0M"
+
+    @property
+    def q0(self):
+        """Index of the first PASSIVE tracer in Y.c (prognostic_variables.jl:54-61: ρ, uₕ, ρe_tot, ρq_tot, chemistry…)."""
+        return 5 if self.moist else 4
+
+    def gas_constant_air(self, qt, ql, qi):  # R_m = R_d (1 − q_t) + R_v q_v   (thermodynamics.md:62-66)
+        P, FT = self.P, self.FT
+        return FT(P.R_d) * (FT(1) - qt) + FT(P.R_v) * (qt - ql - qi)
+
+    def cv_m(self, qt, ql, qi):  # thermodynamics.md:78-81
+        P, FT = self.P, self.FT
+        return FT(P.cv_d) + FT(P.cv_v - P.cv_d) * qt + FT(P.cp_l - P.cv_v) * ql + FT(P.cp_i - P.cv_v) * qi
+
+    def internal_energy(self, T, qt, ql, qi):  # thermodynamics.md:103-111
+        P, FT = self.P, self.FT
+        return (self.cv_m(qt, ql, qi) * (T - FT(P.T_0)) + (qt - ql - qi) * FT(P.e_int_v0) - qi * FT(P.e_int_i0)
+                - (FT(1) - qt) * FT(P.R_d * P.T_0))
+
+    def air_temperature(self, e_int, qt, ql, qi):  # the inversion of internal_energy
+        P, FT = self.P, self.FT
+        return FT(P.T_0) + (e_int - (qt - ql - qi) * FT(P.e_int_v0) + qi * FT(P.e_int_i0) + (FT(1) - qt) * FT(P.R_d * P.T_0)) / self.cv_m(qt, ql, qi)
+
+    def liquid_fraction(self, T):
+        """Supercooled-liquid ramp between T_icenuc and T_freeze (thermodynamics.md:158-164); returns (λ, dλ/dT)."""
+        P, FT = self.P, self.FT
+        w = FT(P.T_freeze - P.T_icenuc)
+        x = np.clip((T - FT(P.T_icenuc)) / w, FT(0), FT(1))
+        n = FT(P.pow_icenuc)
+        inside = (T > FT(P.T_icenuc)) & (T < FT(P.T_freeze))
+        lam = np.where(T >= FT(P.T_freeze), FT(1), np.where(T <= FT(P.T_icenuc), FT(0), x**n))
+        dlam = np.where(inside, n * np.where(inside, x, FT(1)) ** (n - FT(1)) / w, FT(0))
+        return lam.astype(FT), dlam.astype(FT)
+
+    def _ln_pvs(self, T, lam):
+        """ln of the Rankine–Kirchhoff saturation vapour pressure with the λ-weighted latent heat (thermodynamics.md:129-139):
+        p_vs = p_tr (T/T_tr)^(Δcp/R_v) exp((L_0 − Δcp T_0)/R_v (1/T_tr − 1/T)); λ = 1 over liquid, 0 over ice."""
+        P, FT = self.P, self.FT
+        dcp = lam * FT(P.cp_v - P.cp_l) + (FT(1) - lam) * FT(P.cp_v - P.cp_i)
+        L0 = lam * FT(P.LH_v0) + (FT(1) - lam) * FT(P.LH_s0)
+        return (np.log(FT(P.press_triple)) + dcp / FT(P.R_v) * np.log(T / FT(P.T_triple))
+                + (L0 - dcp * FT(P.T_0)) / FT(P.R_v) * (FT(1) / FT(P.T_triple) - FT(1) / T)), dcp, L0
+
+    def q_vap_saturation(self, T, rho, lam):
+        lnp, _, _ = self._ln_pvs(T, lam)
+        return np.exp(lnp) / (rho * self.FT(self.P.R_v) * T)
+
+    def saturation_adjustment(self, rho, e_int, qt, maxiter=40):
+        """TD.saturation_adjustment(thermo_params, TD.ρe(), ρ, e_int, q_tot) → (T, q_liq, q_ice)
+        (precomputed_quantities.jl:639-642): unsaturated air keeps T(e_int, q_tot); otherwise T solves
+        e_int = I(T, q_tot, λ q_c, (1 − λ) q_c) with q_c = max(0, q_tot − q_vs(T, ρ)) (equilibrium partition), by Newton's method
+        with the analytic derivative from the all-vapour temperature, iterated to round-off (the reference stops at a relative
+        temperature tolerance of 1e-4 after a Newton step [UPSTREAM-RECALL], i.e. at an error of the order of the tolerance
+        squared).  Safeguard for strongly supersaturated input only: an iterate beyond the dew point (q_c = 0, where the residual
+        is linear and Newton would return to the starting point) is pulled back half-way to the last iterate with a negative
+        residual; ordinary atmospheric states never take that branch."""
+        P, FT = self.P, self.FT
+        z = np.zeros_like(qt)
+        T1 = self.air_temperature(e_int, qt, z, z)
+        lam, dlam = self.liquid_fraction(T1)
+        sat = qt > self.q_vap_saturation(T1, rho, lam)
+        T = T1.copy()
+        if np.any(sat):
+            Ts, r, e, q = T1[sat], rho[sat], e_int[sat], qt[sat]
+            Tlo = Ts.copy()
+            tol = FT(8) * np.finfo(FT).eps
+            for _ in range(maxiter):
+                lam, dlam = self.liquid_fraction(Ts)
+                lnp, dcp, L0 = self._ln_pvs(Ts, lam)
+                qvs = np.exp(lnp) / (r * FT(P.R_v) * Ts)
+                dlnp = (L0 + dcp * (Ts - FT(P.T_0))) / (FT(P.R_v) * Ts * Ts) + dlam * (
+                    FT(P.cp_i - P.cp_l) / FT(P.R_v) * np.log(Ts / FT(P.T_triple))
+                    + (FT(-P.LH_f0) - FT(P.cp_i - P.cp_l) * FT(P.T_0)) / FT(P.R_v) * (FT(1) / FT(P.T_triple) - FT(1) / Ts))
+                on = q > qvs
+                qc = np.where(on, q - qvs, FT(0))
+                dqc = -qvs * (dlnp - FT(1) / Ts)
+                ql, qi = lam * qc, (FT(1) - lam) * qc
+                dql, dqi = dlam * qc + lam * dqc, -dlam * qc + (FT(1) - lam) * dqc
+                f = self.internal_energy(Ts, q, ql, qi) - e
+                df = (self.cv_m(q, ql, qi) + (Ts - FT(P.T_0)) * (FT(P.cp_l - P.cv_v) * dql + FT(P.cp_i - P.cv_v) * dqi)
+                      - dqc * FT(P.e_int_v0) - dqi * FT(P.e_int_i0))
+                Tlo = np.where(on & (f < 0), Ts, Tlo)
+                Tn = np.where(on, Ts - f / df, FT(0.5) * (Tlo + Ts))
+                done = on & (np.abs(Tn - Ts) <= tol * Ts)
+                Ts = Tn
+                if np.all(done):
+                    break
+            T[sat] = Ts
+        lam, _ = self.liquid_fraction(T)
+        qc = np.where(sat, np.maximum(FT(0), qt - self.q_vap_saturation(T, rho, lam)), FT(0))
+        return T, (lam * qc).astype(FT), ((FT(1) - lam) * qc).astype(FT)
+
+    def q_tot_r(self, p):
+        """refstate_thermodynamics.jl:140-150: RH_ref · q_sat(T_r(p), ρ_r(p)) over liquid, zero above 250 hPa."""
+        FT = self.FT
+        T_r = self.T_ref(p)
+        rho_r = p / (FT(self.P.R_d) * T_r)
+        return np.where(p < FT(25000), FT(0), FT(0.5) * self.q_vap_saturation(T_r, rho_r, np.ones_like(p)))
+
+    def h_eff_plus_Phi(self, T, qt, ql, qi):
+        """ᶜh_eff_plus_Φ! (eddy_diffusion_closures.jl:970-983) with ᶜsuspended_water (:997-1007, equilibrium branch):
+        (h_v q_v + h_l q_l + h_i q_i)/max(q_v + q_l + q_i, ε) + Φ; h_v = cp_v (T − T_0) + L_v0, h_l = cp_l (T − T_0),
+        h_i = cp_i (T − T_0) − L_f0 (thermodynamics.md:117-121)."""
+        P, FT = self.P, self.FT
+        qv, ql, qi = np.maximum(FT(0), qt - ql - qi), np.maximum(FT(0), ql), np.maximum(FT(0), qi)
+        dT = T - FT(P.T_0)
+        num = (FT(P.cp_v) * dT + FT(P.LH_v0)) * qv + (FT(P.cp_l) * dT) * ql + (FT(P.cp_i) * dT - FT(P.LH_f0)) * qi
+        return num / np.maximum(qv + ql + qi, np.finfo(FT).eps) + self.Phi
+
     # ------------------------------------------------------------------ sponges
     def beta_rayleigh(self, z, alpha):  # rayleigh_sponge.jl:7-28
         P = self.P
@@ -313,6 +432,13 @@ class Oracle:
         c1, c2 = self.ct12(u1, u2, c)
         K = FT(0.5) * ((u1 * c1 + u2 * c2) + self.interp_f2c(u3 * (f.g33 * u3)) + FT(2) * (FT(0) * u3c))
         e_int = rhoe / rho - K - self.Phi
+        if self.moist:  # :735-747 EquilibriumMicrophysics0M (no T floor in this branch), :794-815
+            qt = np.maximum(FT(0), Yc[:, 4] / rho)
+            T, ql, qi = self.saturation_adjustment(rho, e_int, qt)
+            Rm = self.gas_constant_air(qt, ql, qi)
+            h_tot = rhoe / rho + Rm * T  # TD.total_enthalpy = e_tot + R_m T
+            p = rho * Rm * T
+            return dict(u1=u1, u2=u2, u3c=u3c, fu3=fu3, K=K, T=T, p=p, h_tot=h_tot, qt=qt, ql=ql, qi=qi, Rm=Rm, cvm=self.cv_m(qt, ql, qi))
         # Thermodynamics.jl air_temperature with the dry-air reference internal energy −R_d·T_0
         # (docs/src/thermodynamics.md:103-111): e_int = cv_d (T − T_0) − R_d T_0
         T = np.maximum(FT(P.T_min_sgs), FT(P.T_0) + (e_int + FT(P.R_d) * FT(P.T_0)) / FT(P.cv_d))
@@ -334,7 +460,10 @@ class Oracle:
             return -self.advdiv_f2c(rJf * self.upwind3(fu3, chi))
         raise ValueError(upwinding)
 
-    def theta_v(self, T, p):
+    def theta_v(self, T, p, pc=None):
+        """refstate_thermodynamics.jl:56-61: θ_v = T R_m / (Π R_d)."""
+        if pc is not None and "Rm" in pc:
+            return T * pc["Rm"] / (self.exner(p) * self.FT(self.P.R_d))
         return T / self.exner(p)
 
     def implicit_tendency(self, Yc, Yf, pc):
@@ -344,8 +473,10 @@ class Oracle:
         rho = Yc[:, 0]
         Ytc[:, 0] -= self.advdiv_f2c(self.interp_c2f(rho * self.c.J) / self.f.J * pc["fu3"])
         Ytc[:, 3] += self.vertical_transport(rho, pc["fu3"], pc["h_tot"], self.N.dt, "none")
+        if self.moist:  # :210-214 central transport of the active tracer ρq_tot (q_tot = specific(ρq_tot, ρ), not clipped)
+            Ytc[:, 4] += self.vertical_transport(rho, pc["fu3"], Yc[:, 4] / rho, self.N.dt, "none")
         p, T = pc["p"], pc["T"]
-        dth = self.theta_v(T, p) - self.theta_vr(p)
+        dth = self.theta_v(T, p, pc) - self.theta_vr(p)
         Ytf[:, 0] -= self.gradv_Phi - self.gradv_c2f(self.phi_r(p)) + FT(P.cp_d) * self.interp_c2f(dth) * self.gradv_c2f(self.exner(p))
         if self.N.rayleigh_sponge:
             Ytf[:, 0] += -self.beta_rayleigh(self.f.z, P.alpha_rayleigh_w) * Yf[:, 0]
@@ -552,12 +683,12 @@ class Oracle:
                 put_tri(1, D["uh_uh"]); put_tri(2, D["uh_uh"])
             for q in range(4, nc):
                 put_tri(q, D["tracer"])
-        for q, key in ((0, "rho_u3"), (3, "rhoe_u3")):
+        for q, key in ((0, "rho_u3"), (3, "rhoe_u3")) + (((4, "rhoq_u3"),) if "rhoq_u3" in Jm else ()):
             lo, hi = [sel(a) for a in Jm[key]]
             for k in range(nv):
                 M[o(q) + k, o3 + k] += lo[k]
                 M[o(q) + k, o3 + k + 1] += hi[k]
-        for q, blk in ((0, Jm["u3_rho"]), (3, Jm["u3_rhoe"]), (1, Jm["u3_uh"][0]), (2, Jm["u3_uh"][1])):
+        for q, blk in ((0, Jm["u3_rho"]), (3, Jm["u3_rhoe"]), (1, Jm["u3_uh"][0]), (2, Jm["u3_uh"][1])) + (((4, Jm["u3_rhoq"]),) if "u3_rhoq" in Jm else ()):
             lo, hi = [sel(a) for a in blk]
             for fidx in range(nv + 1):
                 if fidx > 0:
@@ -575,6 +706,10 @@ class Oracle:
         up = self.vertical_transport(rho, pc["fu3"], pc["h_tot"], self.N.dt, self.N.energy_upwinding)
         ce = self.vertical_transport(rho, pc["fu3"], pc["h_tot"], self.N.dt, "none")
         Ytc[:, 3] = up - ce
+        if self.moist:  # :333-338
+            q = Yc[:, 4] / rho
+            Ytc[:, 4] = (self.vertical_transport(rho, pc["fu3"], q, self.N.dt, self.N.energy_upwinding)
+                         - self.vertical_transport(rho, pc["fu3"], q, self.N.dt, "none"))
         return Ytc, Ytf
 
     # ------------------------------------------------------------------ Wfact / ldiv!
@@ -589,7 +724,8 @@ class Oracle:
         rho, u1, u2 = Yc[:, 0], Yc[:, 1], Yc[:, 2]
         u3 = Yf[:, 0]
         K, p, T, h_tot = pc["K"], pc["p"], pc["T"], pc["h_tot"]
-        kappa = FT(P.R_d) / FT(P.cv_d)  # ᶜkappa_m_field! :653-662 (dry)
+        moist = self.moist
+        kappa = pc["Rm"] / pc["cvm"] if moist else FT(P.R_d) / FT(P.cv_d)  # ᶜkappa_m_field! :653-662
         z = lambda a: np.zeros_like(a)
         # :746-754
         dK_duh = self.ct12(u1, u2, c)  # Diag(CT12(uₕ)ᵀ)
@@ -612,7 +748,7 @@ class Oracle:
         A_rho_u3 = (dtg * adv_lo * f.g33[..., :-1], dtg * adv_hi * f.g33[..., 1:])
         A_rhoe_u3 = (dtg * adv_lo * (hf * f.g33)[..., :-1], dtg * adv_hi * (hf * f.g33)[..., 1:])
         # :816-825
-        thv = self.theta_v(T, p)
+        thv = self.theta_v(T, p, pc)
         Pi = self.exner(p)
         dp_drho = kappa * (FT(P.T_0) * FT(P.cp_d) - K - self.Phi) + (FT(P.R_d) - kappa * FT(P.cv_d)) * T
         buoy = FT(P.cp_d) * self.interp_c2f(thv) * self.gradv_c2f(Pi) / rf  # diag on faces
@@ -627,7 +763,7 @@ class Oracle:
             dtg * (pg_lo * cl(dp_drho) + buoy * im_lo),
             dtg * (pg_hi * ch(dp_drho) + buoy * im_hi),
         )
-        A_u3_rhoe = (dtg * pg_lo * kappa, dtg * pg_hi * kappa)
+        A_u3_rhoe = (dtg * pg_lo * cl(kappa), dtg * pg_hi * ch(kappa)) if moist else (dtg * pg_lo * kappa, dtg * pg_hi * kappa)
         # :855-868
         mk = lambda a: -kappa * a
         A_u3_uh = tuple(
@@ -641,6 +777,11 @@ class Oracle:
         beta = self.beta_rayleigh(f.z, P.alpha_rayleigh_w) if self.N.rayleigh_sponge else z(rf)
         A_u3_u3 = (dtg * l, dtg * (d - beta) - FT(1), dtg * u)
         Jm = dict(rho_u3=A_rho_u3, rhoe_u3=A_rhoe_u3, u3_rho=A_u3_rho, u3_rhoe=A_u3_rhoe, u3_uh=A_u3_uh, u3_u3=A_u3_u3)
+        if moist:  # (ρq_tot, u₃) :770-790 and (u₃, ρq_tot) :827-831 with ᶜ∂p∂ρq_tot_field! :670-690
+            qf = self.interp_c2f(Yc[:, 4] / rho)
+            Jm["rhoq_u3"] = (dtg * adv_lo * (qf * f.g33)[..., :-1], dtg * adv_hi * (qf * f.g33)[..., 1:])
+            dp_dq = kappa * (-FT(P.e_int_v0) - FT(P.R_d * P.T_0) - FT(P.cv_v - P.cv_d) * (T - FT(P.T_0))) + FT(P.R_v - P.R_d) * T
+            Jm["u3_rhoq"] = (dtg * pg_lo * cl(dp_dq), dtg * pg_hi * ch(dp_dq))
         if self.vert_diff and self.implicit_diffusion:  # diffusion_flag = DerivativeFlag(atmos.diff_mode) (:88)
             self.update_diffusion_jacobian(Jm, Yc, pc, dtg)
         return Jm
@@ -661,7 +802,10 @@ class Oracle:
         fh = lambda a: np.concatenate([a[..., 1:], a[..., -1:] * 0], -1)  # face f+1
         l, d, u = [a.copy() for a in Jm["u3_u3"]]
         # Schur: A22 + A21·A12 (A11 = -I)
-        for a21, a12 in ((Jm["u3_rho"], Jm["rho_u3"]), (Jm["u3_rhoe"], Jm["rhoe_u3"])):
+        # moist without diffusion/sedimentation: ApproximateBlockArrowheadIterativeSolve (:538-578) with A₁₁ = −I — its main-diagonal
+        # preconditioner IS A₁₁, so every iterate equals the exact arrowhead solve with one more scalar (ρq_tot)
+        scal = [(0, "rho"), (3, "rhoe")] + ([(4, "rhoq")] if "rhoq_u3" in Jm else [])
+        for a21, a12 in [(Jm["u3_" + k], Jm[k + "_u3"]) for _, k in scal]:
             lo21, hi21 = a21  # row f: centres f-1, f
             lo12, hi12 = a12  # row k: faces k, k+1
             l += lo21 * cl(lo12)
@@ -669,9 +813,9 @@ class Oracle:
             u += hi21 * ch(hi12)
         # velocities first: Δuₕ = -R_uₕ ; passive tracers only have the fallback -I block (:476-481)
         dYc[:, 1], dYc[:, 2] = -R1, -R2
-        dYc[:, 4:] = -Rc[:, 4:]
+        dYc[:, self.q0:] = -Rc[:, self.q0:]
         rhs = R3.copy()
-        for a21, r in ((Jm["u3_rho"], Rrho), (Jm["u3_rhoe"], Rre)):
+        for a21, r in [(Jm["u3_" + k], Rc[:, idx]) for idx, k in scal]:
             rhs += a21[0] * cl(r) + a21[1] * ch(r)
         for a in range(2):
             r = (R1, R2)[a]
@@ -692,8 +836,9 @@ class Oracle:
             x[..., i] = dp[..., i] - cp[..., i] * x[..., i + 1]
         dYf[:, 0] = x
         # back-substitute scalars: -Δρ + A12 Δu₃ = R  ⇒ Δρ = A12 Δu₃ - R
-        for idx, a12, r in ((0, Jm["rho_u3"], Rrho), (3, Jm["rhoe_u3"], Rre)):
-            dYc[:, idx] = a12[0] * x[..., :-1] + a12[1] * x[..., 1:] - r
+        for idx, k in scal:
+            a12 = Jm[k + "_u3"]
+            dYc[:, idx] = a12[0] * x[..., :-1] + a12[1] * x[..., 1:] - Rc[:, idx]
         return dYc, dYf
 
     # ------------------------------------------------------------------ DSS
@@ -877,9 +1022,9 @@ class Oracle:
         Ylc = np.zeros_like(Yc)
         self._tracer_pre(Ytc, Ylc, Yc, Yf, pc)
         if L is not None:
-            Lq = self._tracer_laplacians(Yc)
+            Lq = self._tracer_laplacians(Yc, pc)
             self.weighted_dss([("c12", [L[0], L[1]]), ("scalar", [L[2]]), ("scalar", [L[3]])] + [("scalar", [a]) for a in Lq])  # :18-21
-            self._rt_post(Ytc, Ytf, Yc, L)
+            self._rt_post(Ytc, Ytf, Yc, L, pc, Lq[0] if self.moist else None)
             self._tracer_post(Ylc, Yc, Lq)
         return (Ytc, Ytf, Ylc) if with_lim else (Ytc + Ylc, Ytf)
 
@@ -893,18 +1038,35 @@ class Oracle:
         c1, c2 = self.ct12(u1, u2, c)
         for q in range(4, Yc.shape[1]):
             chi = Yc[:, q] / rho
-            Ylc[:, q] -= self.split_div(rho * c1, rho * c2, chi, c)
+            Ylc[:, q] -= self.split_div(rho * c1, rho * c2, chi, c)  # every tracer variable, ρq_tot included (advection.jl:121-124)
+            if q < self.q0:
+                # ρq_tot: vertical transport is implicit (advection.jl:250); viscous sponge on the total water: the aggregate
+                # tendency goes to ρq_tot AND ρ, the water enthalpy flux to ρe_tot (viscous_sponge.jl:158-199)
+                if N.viscous_sponge:
+                    g = self.grad(chi)
+                    g = self.ct12(g[0], g[1], c)
+                    d = self.beta_viscous(c.z) * self.wdiv(rho * g[0], rho * g[1], c)
+                    Ytc[:, q] += d
+                    Ytc[:, 0] += d
+                    hw = rho * self.h_eff_plus_Phi(pc["T"], pc["qt"], pc["ql"], pc["qi"])
+                    Ytc[:, 3] += self.beta_viscous(c.z) * self.wdiv(hw * g[0], hw * g[1], c)
+                continue
             Ytc[:, q] += self.vertical_transport(rho, pc["fu3"], chi, N.dt, N.tracer_upwinding)
             if N.viscous_sponge:
                 g = self.grad(chi)
                 g = self.ct12(g[0], g[1], c)
                 Ytc[:, q] += self.beta_viscous(c.z) * self.wdiv(rho * g[0], rho * g[1], c)
 
-    def _tracer_laplacians(self, Yc):
-        """prep_tracer_hyperdiffusion_tendency! (hyperdiffusion.jl:420-432): ∇²χ = wdivₕ(gradₕ(ρχ/ρ))."""
+    def _tracer_laplacians(self, Yc, pc=None):
+        """prep_tracer_hyperdiffusion_tendency! (hyperdiffusion.jl:420-432): ∇²χ = wdivₕ(gradₕ(ρχ/ρ)).  For ρq_tot the field that
+        is used afterwards is ᶜ∇²q_tot_eff = wdivₕ(gradₕ(q_tot − q_tot_r(p))) (hyperdiffusion.jl:148-165); the plain ∇²q_tot the
+        reference also computes (and DSSes) is never read, so the q_tot slot carries ∇²q_tot_eff."""
         out = []
         for q in range(4, Yc.shape[1]):
-            g = self.grad(Yc[:, q] / Yc[:, 0])
+            chi = Yc[:, q] / Yc[:, 0]
+            if q < self.q0:
+                chi = chi - self.q_tot_r(pc["p"])
+            g = self.grad(chi)
             out.append(self.wdiv(*self.ct12(g[0], g[1], self.c), self.c))
         return out
 
@@ -914,10 +1076,13 @@ class Oracle:
         for k, q in enumerate(range(4, Yc.shape[1])):
             g = self.grad(Lq[k])
             g = self.ct12(g[0], g[1], self.c)
-            Ylc[:, q] -= self.nu4_scalar * self.wdiv(rho * g[0], rho * g[1], self.c)
+            d = self.nu4_scalar * self.wdiv(rho * g[0], rho * g[1], self.c)
+            Ylc[:, q] -= d
+            if q < self.q0:  # hyperdiffusion.jl:480-484: the water mass tendency also enters Yₜ.c.ρ
+                Ylc[:, 0] -= d
 
-    def _rt_post(self, Ytc, Ytf, Yc, L):
-        """apply_hyperdiffusion_tendency! (hyperdiffusion.jl:247-307) on the DSSed ∇² fields (element-local)."""
+    def _rt_post(self, Ytc, Ytf, Yc, L, pc=None, Lq_tot=None):
+        """apply_hyperdiffusion_tendency! (hyperdiffusion.jl:247-316) on the DSSed ∇² fields (element-local)."""
         FT, N, c = self.FT, self.N, self.c
         rho = Yc[:, 0]
         L1, L2, L3, Ls = L
@@ -930,6 +1095,11 @@ class Oracle:
         gL = self.grad(Ls)
         gL = self.ct12(gL[0], gL[1], c)
         Ytc[:, 3] -= self.nu4_scalar * self.wdiv(rho * gL[0], rho * gL[1], c)  # :291,307
+        if self.moist:  # water enthalpy flux ν ρ (h_eff + Φ) gradₕ(∇²q_tot_eff)  (:293-306)
+            gq = self.grad(Lq_tot)
+            gq = self.ct12(gq[0], gq[1], c)
+            hw = rho * self.h_eff_plus_Phi(pc["T"], pc["qt"], pc["ql"], pc["qi"])
+            Ytc[:, 3] -= self.nu4_scalar * self.wdiv(hw * gq[0], hw * gq[1], c)
 
     def _rt_pre(self, Yc, Yf, pc):
         """Everything of remaining_tendency! that is element-local before the DSS of the ∇² fields.
@@ -947,7 +1117,7 @@ class Oracle:
         Ytc[:, 0] -= self.split_div(rho * c1, rho * c2, one, c)
         Ytc[:, 3] -= self.split_div(rho * c1, rho * c2, h_tot, c)
         Pi = self.exner(p)
-        dth = self.theta_v(T, p) - self.theta_vr(p)
+        dth = self.theta_v(T, p, pc) - self.theta_vr(p)
         g1 = self.grad(K + self.Phi - self.phi_r(p))
         gPi, gth, gthPi = self.grad(Pi), self.grad(dth), self.grad(dth * Pi)
         for a in range(2):
@@ -1111,7 +1281,7 @@ class Oracle:
                 if L is not None:
                     for k in range(4):
                         Ls[k][sl] = L[k]
-                    for k, lq in enumerate(sub._tracer_laplacians(Uc[sl])):
+                    for k, lq in enumerate(sub._tracer_laplacians(Uc[sl], pc)):
                         Ls[4 + k][sl] = lq
 
             pmap(pre)
@@ -1119,7 +1289,8 @@ class Oracle:
                 self.weighted_dss([("c12", [Ls[0], Ls[1]]), ("scalar", [Ls[2]]), ("scalar", [Ls[3]])] + [("scalar", [a]) for a in Ls[4:]])
 
                 def post(sub, sl):
-                    sub._rt_post(Ytc[sl], Ytf[sl], Uc[sl], tuple(a[sl] for a in Ls[:4]))
+                    pc = sub.set_implicit_precomputed_quantities(Uc[sl], Uf[sl]) if self.moist else None  # (idempotent on a filtered state)
+                    sub._rt_post(Ytc[sl], Ytf[sl], Uc[sl], tuple(a[sl] for a in Ls[:4]), pc, Ls[4][sl] if self.moist else None)
                     sub._tracer_post(Ylc[sl] if limiter else Ytc[sl], Uc[sl], [a[sl] for a in Ls[4:]])
 
                 pmap(post)
