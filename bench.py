@@ -40,8 +40,9 @@ ZD = 40000.0  # zd_rayleigh = zd_viscous as in toml/longrun_held_suarez.toml (SU
 
 def workload(n_gpus, config="weak"):
     """BASELINE.json configs.  "weak" (default) is the north-star series; the others are extra measurements (--config):
-    "strong": dry BW he60/ze63 on every N (configs[4]); "he16": dry BW he16/ze63 (configs[1]); "tracer": he30/ze63 with one passive
-    tracer (configs[2], dycore + tracer advection only); "hs": Held–Suarez he6/ze10 (configs[0])."""
+    "strong": dry BW he60/ze63 on every N (configs[4]); "he16": dry BW he16/ze63 (configs[1]); "moist": he30/ze63 0M-moist baroclinic
+    wave with the thermodynamically active ρq_tot (configs[2], dycore + tracer advection only); "tracer": the same grid dry with one
+    passive tracer; "hs": Held–Suarez he6/ze10 (configs[0])."""
     if config == "strong":
         return dict(h_elem=60, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=45.0, scaling="strong", name="dry_baroclinic_wave")
     if config == "he16":
@@ -53,6 +54,8 @@ def workload(n_gpus, config="weak"):
     w = dict(h_elem=h, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=dt, scaling="weak", name="dry_baroclinic_wave", series="he30_per_gpu")
     if config == "tracer":
         w.update(tracers=1, name="dry_baroclinic_wave + 1 passive tracer")
+    if config == "moist":  # configs[2] as the reference runs it: EquilibriumMicrophysics0M, ρq_tot thermodynamically active
+        w.update(moist=True, ic="MoistBaroclinicWave", name="moist_baroclinic_wave 0M (active rho*q_tot: dycore + tracer advection only)")
     if config in ("vdiff", "vdiff_implicit"):
         w.update(vert_diff="DecayWithHeightDiffusion", implicit_diffusion=(config == "vdiff_implicit"),
                  name="dry_baroclinic_wave + vertical diffusion (" + ("implicit, 2 solver iterations" if config == "vdiff_implicit" else "explicit") + ")")
@@ -136,9 +139,11 @@ def oracle_steps(w, P, cores, steps, warm, budget_s, FT=np.float32):
     sponge = w.get("sponge", True)
     hs = w.get("rad") == "held_suarez"
     N = prm.DycoreNumerics(dt=w["dt"], rayleigh_sponge=sponge, viscous_sponge=sponge, held_suarez=hs, disable_momentum_vertical_diffusion=hs,
-                           vert_diff=w.get("vert_diff"), implicit_diffusion=bool(w.get("implicit_diffusion", False)), approximate_linear_solve_iters=2)
+                           vert_diff=w.get("vert_diff"), implicit_diffusion=bool(w.get("implicit_diffusion", False)), approximate_linear_solve_iters=2,
+                           microphysics_model="0M" if w.get("moist") else None)
     o = Oracle(g, P, N, FT)
-    Yc, Yf = setups.decaying_profile(g, P) if w.get("ic") == "DecayingProfile" else setups.dry_baroclinic_wave(g, P)
+    Yc, Yf = (setups.decaying_profile(g, P) if w.get("ic") == "DecayingProfile" else
+              setups.moist_baroclinic_wave(g, P) if w.get("moist") else setups.dry_baroclinic_wave(g, P))
     for _ in range(w.get("tracers", 0)):
         chi = 0.5 * (1 + np.sin(np.radians(g.lat[..., None])) * np.cos(np.radians(g.lon[..., None]))) * np.exp(-np.broadcast_to(g.z_c, Yc[:, 0].shape) / 8000.0)
         Yc = np.concatenate([Yc, (Yc[:, 0].astype(np.float64) * chi).astype(FT)[:, None]], axis=1)
@@ -263,7 +268,7 @@ def main():
     ap.add_argument("--min-timed-s", type=float, default=0.6, help="repeat the K-step block until this much device time has been measured")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multi-gpu-check", action="store_true", help="skip the N > 1 bitwise check against a single-GPU run")
-    ap.add_argument("--config", default="weak", choices=["weak", "strong", "he16", "tracer", "hs", "vdiff", "vdiff_implicit"], help="BASELINE.json config (default: the north-star weak series)")
+    ap.add_argument("--config", default="weak", choices=["weak", "strong", "he16", "tracer", "moist", "hs", "vdiff", "vdiff_implicit"], help="BASELINE.json config (default: the north-star weak series)")
     ap.add_argument("--unfused", action="store_true", help="hook-by-hook implicit stage instead of the fused kernel")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -284,9 +289,10 @@ def main():
     sponge = w.get("sponge", True)
     ntr = w.get("tracers", 0)
     tracers = [lambda lat, lon, z: 0.5 * (1 + np.sin(np.radians(lat)) * np.cos(np.radians(lon))) * np.exp(-z / 8000.0)] * ntr or None
+    ntr += 1 if w.get("moist") else 0  # tracer components of Y.c (ρq_tot counts)
     sim = dycore.AtmosSimulation(FT=np.float32, h_elem=w["h_elem"], z_elem=w["z_elem"], z_max=w["z_max"], dz_bottom=w["dz_bottom"],
                                  dt=w["dt"], rayleigh_sponge=sponge, viscous_sponge=sponge, params=P, rad=w.get("rad"), tracers=tracers,
-                                 initial_condition=w.get("ic", "DryBaroclinicWave"),
+                                 initial_condition=w.get("ic", "DryBaroclinicWave"), microphysics_model="0M" if w.get("moist") else None,
                                  vert_diff=w.get("vert_diff"), implicit_diffusion=w.get("implicit_diffusion", False), approximate_linear_solve_iters=2,
                                  comms=comms if nranks > 1 else None)
     fused = not args.unfused
@@ -433,7 +439,7 @@ def main():
     else:
         k_ms = time_kernel(lambda: sim.remaining_tendency_phase_a(Yt, sim.Y))
         nbytes = 2 * (4 * c_b + f_b) + 4 * c_b
-        kern.append({"kernel": "k5_exp_a<float, 63>", "what": "T_exp_T_lim! pre-DSS kernel (dry components)", "ms_per_launch": k_ms, "launches_per_step": 4,
+        kern.append({"kernel": "k5_exp_a<float, 0, MOIST>" if w.get("moist") else "k5_exp_a<float, 63>", "what": "T_exp_T_lim! pre-DSS kernel (dry components)", "ms_per_launch": k_ms, "launches_per_step": 4,
                      "share_of_step": 4 * k_ms / ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (k_ms * 1e-3) / 1e9,
                      "frac": nbytes / (k_ms * 1e-3) / 1e9 / peak})
     dom = max(kern, key=lambda r: r["share_of_step"])

@@ -51,7 +51,9 @@ class Params(C.Structure):
                                                                "hs_dtheta_z", "hs_T_min", "MSLP")] + [("sem_quasimonotone_limiter", C.c_int32)] + [
         (n, C.c_int32) for n in ("vert_diff", "implicit_diffusion", "approximate_linear_solve_iters",
                                  "disable_momentum_vertical_diffusion")] + [(n, C.c_double) for n in ("C_E", "H_diffusion", "D_0_diffusion")] + [
-        ("vertical_water_borrowing_limiter", C.c_int32)]
+        ("vertical_water_borrowing_limiter", C.c_int32), ("microphysics_0M", C.c_int32)] + [
+        (n, C.c_double) for n in ("R_v", "cp_v", "cp_l", "cp_i", "LH_v0", "LH_s0", "T_triple", "press_triple", "T_freeze", "T_icenuc",
+                                  "pow_icenuc")]
 
 
 class CachePtrs(C.Structure):
@@ -149,7 +151,10 @@ def make_params(P, N, grid) -> Params:
         approximate_linear_solve_iters=int(getattr(N, "approximate_linear_solve_iters", 1)),
         disable_momentum_vertical_diffusion=int(getattr(N, "disable_momentum_vertical_diffusion", False)),
         C_E=getattr(P, "C_E", 0.0), H_diffusion=getattr(P, "H_diffusion", 1.0), D_0_diffusion=getattr(P, "D_0_diffusion", 0.0),
-        vertical_water_borrowing_limiter=int(getattr(N, "tracer_nonnegativity_method", None) == "vertical_water_borrowing"))
+        vertical_water_borrowing_limiter=int(getattr(N, "tracer_nonnegativity_method", None) == "vertical_water_borrowing"),
+        microphysics_0M=int(getattr(N, "microphysics_model", None) == "0M"),
+        R_v=P.R_v, cp_v=P.cp_v, cp_l=P.cp_l, cp_i=P.cp_i, LH_v0=P.LH_v0, LH_s0=P.LH_s0, T_triple=P.T_triple,
+        press_triple=P.press_triple, T_freeze=P.T_freeze, T_icenuc=P.T_icenuc, pow_icenuc=P.pow_icenuc)
 
 
 def create_context(grid, P, N, part=None, nccl_id: bytes | None = None, rank: int = 0, nranks: int = 1, n_tracers: int = 0):

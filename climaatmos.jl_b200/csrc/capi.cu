@@ -113,6 +113,7 @@ struct b200_ctx {
   void *Uc[2] = {nullptr, nullptr}, *Uf[2] = {nullptr, nullptr};
   void *Tec[4] = {}, *Tef[4] = {}, *Tic[4] = {}, *Tif[4] = {};
   void* H = nullptr;
+  void* Hw = nullptr;  // moist (0M): ρ(h_eff + Φ) [nh][16][nv] for the water enthalpy flux of the hyperdiffusion apply
   void *Rc = nullptr, *Rf = nullptr, *dc = nullptr, *df = nullptr;
   // halo
   int rank = 0, nranks = 1;
@@ -249,6 +250,14 @@ static Par<FT> make_par(const b200_ctx* c) {
   P.nu4v = (FT)p.nu4_vorticity; P.nu4s = (FT)p.nu4_scalar; P.ddf = (FT)p.divergence_damping_factor;
   P.nh = c->dims.nh; P.nv = c->dims.nv; P.ncf = c->ncf(); P.tupw = p.tracer_upwinding;
   P.hyperdiff = p.hyperdiff; P.rayleigh = p.rayleigh_sponge; P.viscous = p.viscous_sponge; P.upwinding = p.energy_upwinding;
+  P.moist = p.microphysics_0M;
+  memset(&P.M, 0, sizeof(P.M));
+  if (p.microphysics_0M) {
+    P.M.R_v = (FT)p.R_v; P.M.cv_v = (FT)(p.cp_v - p.R_v); P.M.cp_v = (FT)p.cp_v; P.M.cp_l = (FT)p.cp_l; P.M.cp_i = (FT)p.cp_i;
+    P.M.LH_v0 = (FT)p.LH_v0; P.M.LH_s0 = (FT)p.LH_s0; P.M.e_v0 = (FT)(p.LH_v0 - p.R_v * p.T_0); P.M.e_i0 = (FT)(p.LH_s0 - p.LH_v0);
+    P.M.T_tr = (FT)p.T_triple; P.M.ln_ptr = (FT)log(p.press_triple); P.M.T_frz = (FT)p.T_freeze; P.M.T_icn = (FT)p.T_icenuc;
+    P.M.pow_icn = (FT)p.pow_icenuc;
+  }
   return P;
 }
 
@@ -430,6 +439,9 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>(true)));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>(true)));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_lim_vborrow<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SLAB * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
@@ -552,6 +564,14 @@ extern "C" int b200_create(b200_ctx** out, const b200_dims* d, const b200_geomet
   if (p->implicit_diffusion && !p->vert_diff)
     return fail("b200_create: implicit_diffusion needs a vert_diff model (the reference's update_diffusion_jacobian! has no diffusivity otherwise)");
   if (p->vert_diff && p->approximate_linear_solve_iters < 0) return fail("b200_create: approximate_linear_solve_iters < 0");
+  if (p->microphysics_0M) {
+    if (p->microphysics_0M != 1) return fail("b200_create: microphysics_0M must be 0 (DryModel) or 1 (EquilibriumMicrophysics0M)");
+    if (d->n_tracers < 1) return fail("b200_create: microphysics_0M needs n_tracers >= 1 (rho*q_tot is component 4 of Y.c)");
+    if (p->vert_diff || p->held_suarez)
+      return fail("b200_create: the moist (0M) state is built without vertical diffusion and without the Held-Suarez forcing");
+    if (!(p->R_v > 0 && p->cp_v > p->R_v && p->cp_l > 0 && p->cp_i > 0 && p->T_triple > 0 && p->press_triple > 0 && p->T_freeze > p->T_icenuc))
+      return fail("b200_create: microphysics_0M needs the Thermodynamics parameters (R_v, cp_v, cp_l, cp_i, LH_v0, LH_s0, T_triple, press_triple, T_freeze > T_icenuc)");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("b200_create: no CUDA device (this library has no CPU fallback)");
@@ -571,7 +591,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   fr(c->d_hgeo); fr(c->d_vlev); fr(c->d_dssrec); fr(c->d_node_off); fr(c->d_lim_nbr_off); fr(c->d_lim_nbr); fr(c->d_lim_bnd); fr(c->d_lim_E); fr(c->d_lim_ghost_node);
   for (int i = 0; i < 4; ++i) fr(c->Tlc[i]);
   for (void* p : c->p2p_peer) if (p) cudaIpcCloseMemHandle(p);
-  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->d_jsnap_c); fr(c->d_jsnap_f); fr(c->d_jacd); fr(c->d_kdec); fr(c->H);
+  fr(c->p2p_buf); fr(c->d_p2p_seq); fr(c->d_slot_nbr); fr(c->d_slot_dst); fr(c->d_nbr_nhg); fr(c->d_nbr_rank); fr(c->d_p2p_dst); fr(c->d_p2p_flags); fr(c->d_off); fr(c->d_mem); fr(c->d_jac); fr(c->d_jsnap_c); fr(c->d_jsnap_f); fr(c->d_jacd); fr(c->d_kdec); fr(c->H); fr(c->Hw);
   for (int i = 0; i < 2; ++i) { fr(c->Uc[i]); fr(c->Uf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Nsc[i]); fr(c->Nsf[i]); }
   for (int i = 0; i < 4; ++i) { fr(c->Tec[i]); fr(c->Tef[i]); fr(c->Tic[i]); fr(c->Tif[i]); }
@@ -711,7 +731,11 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
   if (!c->d_jsnap_c) return fail("b200_ldiv: b200_wfact has not been called");
   // exact BlockArrowheadSolve (manual_sparse_jacobian.jl:579-584): Schur complement onto u₃, PCR, back-substitution — the coefficient
   // code of the fused implicit stage on the Wfact snapshot
-  if (c->dims.nv == 63 && !c->generic_nv)
+  if (c->prm.microphysics_0M)
+    launchx(c->pdl & 16, k5_imp_stage<FT, 0, true, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
+            (const VLev<FT>*)c->d_vlev, (const FT*)c->d_jsnap_c, (const FT*)c->d_jsnap_f, (FT*)dYc, (FT*)dYf, (FT)c->jsnap_dtg, (const FT*)Rc,
+            (const FT*)Rf);
+  else if (c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k5_imp_stage<FT, 63, true>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo,
             (const VLev<FT>*)c->d_vlev, (const FT*)c->d_jsnap_c, (const FT*)c->d_jsnap_f, (FT*)dYc, (FT*)dYf, (FT)c->jsnap_dtg, (const FT*)Rc,
             (const FT*)Rf);
@@ -728,6 +752,7 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
 extern "C" int b200_debug_jacobian(b200_ctx* c, void* dst, int64_t capacity_bytes, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_debug_jacobian: null context");
+  if (c->prm.microphysics_0M) return fail("b200_debug_jacobian: the coefficient planes are a dry-path debug aid (moist contexts solve from the Wfact snapshot)");
   if (!c->jac_planes_valid) {  // dry path: Wfact kept a snapshot; materialise the planes from it now
     if (!c->d_jsnap_c) return fail("b200_debug_jacobian: b200_wfact has not been called");
     const int rc = c->ft == 4 ? launch_wfact_planes<float>(c, c->d_jsnap_c, c->d_jsnap_f, c->jsnap_dtg, (cudaStream_t)stream)
@@ -1044,13 +1069,18 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
   const bool hd = c->prm.hyperdiff != 0;
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
   const bool nv63 = c->dims.nv == 63 && !c->generic_nv;
+  const bool moist = c->prm.microphysics_0M != 0;
+  if (moist && hd && !c->Hw) CK(cudaMalloc(&c->Hw, (size_t)c->dims.nh * 16 * c->dims.nv * sizeof(FT)));
   if (phase == 0) {
-    if (nv63)
+    if (moist)  // moist thermodynamic state + ∇²q_tot_eff → H[4], ρ(h_eff + Φ) → Hw (run-time nv; 1 CTA/SM)
+      launchx(c->pdl & 1, k5_exp_a<FT, 0, true>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw);
+    else if (nv63)
       launchx(c->pdl & 1, k5_exp_a<FT, 63>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)nullptr);
     else
       launchx(c->pdl & 1, k5_exp_a<FT, 0>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                            (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr);
+                                                            (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)nullptr);
     LAUNCH_CHECK(c);
     if (c->dims.n_tracers > 0) {
       k5_tracer_a<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(3), s>>>(
@@ -1074,6 +1104,11 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     if (c->dims.n_tracers > 0) {
       k5_tracer_c<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(0), s>>>(
           make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)c->H, (FT*)(Ylc ? Ylc : Ytc));
+      LAUNCH_CHECK(c);
+    }
+    if (moist) {  // water mass → ρq_tot and ρ of Yₜ_lim, water enthalpy flux → ρe_tot of Yₜ
+      k_moist_c<FT><<<c->dims.nh, CT, smem_row<FT>(0), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
+                                                          (const FT*)c->H, (const FT*)c->Hw, (FT*)Ytc, (FT*)(Ylc ? Ylc : Ytc));
       LAUNCH_CHECK(c);
     }
   }
@@ -1248,7 +1283,10 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
     LAUNCH_CHECK(c);
     return 0;
   }
-  if (c->dims.nv == 63 && !c->generic_nv)
+  if (c->prm.microphysics_0M)
+    launchx(c->pdl & 16, k5_imp_stage<FT, 0, false, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
+            (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
+  else if (c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k5_imp_stage<FT, 63>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
             (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else

@@ -50,6 +50,12 @@ struct VLev {
   FT Dw[16];     // weak derivative matrix   Dw[i*4+k] = -D[k][i] w_k / w_i
 };
 
+// moist thermodynamics parameters (EquilibriumMicrophysics0M, moist.cuh); all zero for dry contexts
+template <class FT>
+struct MPar {
+  FT R_v, cv_v, cp_v, cp_l, cp_i, LH_v0, LH_s0, e_v0 /* L_v0 − R_v T_0 */, e_i0 /* L_f0 */, T_tr, ln_ptr /* ln p_triple */, T_frz, T_icn, pow_icn;
+};
+
 template <class FT>
 struct Par {
   FT R_d, cp_d, cv_d, T_0, p0, kappa, Ts_ref, Tmin_ref, T_min_sgs, dt;
@@ -61,6 +67,8 @@ struct Par {
   int hyperdiff, rayleigh, viscous, upwinding;
   int hs;  // Held–Suarez forcing
   FT hs_ka, hs_ks, hs_kf, hs_sigb, hs_isig, hs_dTy, hs_Teq, hs_dthz, hs_Tmin, hs_iMSLP, hs_ikap;
+  int moist;  // microphysics_model 0M: component 4 of Y.c is the thermodynamically active ρq_tot
+  MPar<FT> M;
 };
 
 // Programmatic dependent launch (capi.cu: launchx).  pdl_launch lets the next kernel of the stream start its CTAs as soon as every

@@ -12,6 +12,7 @@
 // keeps them in shared memory only.
 #pragma once
 #include "common.cuh"
+#include "moist.cuh"
 
 namespace b200 {
 
@@ -69,7 +70,9 @@ __global__ void __launch_bounds__(NT) k_cache_imp(Par<FT> P, const FT* __restric
       FT u2 = gYc[(2 * 16 + n) * nv + v], re = gYc[(3 * 16 + n) * nv + v];
       FT lo = s_u3[n * LVP + v], hi = s_u3[n * LVP + v + 1];
       FT K = kinetic(hg, V, u1, u2, lo, hi, n, v);
-      Pt<FT> t = thermo(P, rho, re, K, V.phic[v]);
+      Pt<FT> t;
+      if (P.moist) { Mst<FT> m; t = thermo_m(P, rho, re, gYc[(4 * 16 + n) * nv + v], K, V.phic[v], m); }  // :735-815 (0M branch)
+      else t = thermo(P, rho, re, K, V.phic[v]);
       size_t o = ((size_t)h * 16 + n) * nv + v;
       if (Kc) Kc[o] = K;
       if (Tc) Tc[o] = t.T;

@@ -11,12 +11,10 @@
 // grid = (elements, tracers).  The vertical Jacobian factor of WJ is constant over a slab and cancels, so the horizontal W·J2 is used.
 #pragma once
 #include "common.cuh"
+#include "moist.cuh"  // eps_
 
 namespace b200 {
 
-template <class FT> __device__ __forceinline__ FT eps_();
-template <> __device__ __forceinline__ float eps_<float>() { return 1.1920929e-07f; }
-template <> __device__ __forceinline__ double eps_<double>() { return 2.220446049250313e-16; }
 
 // E (multi-rank only): the bounds again, in the shape of a centre field [h][2·ntr][16][nv] (every node column of the element holds
 // the element's bound), so the ordinary peer-memory halo (k_pack_p2p: the node columns shared with each neighbour) carries them.

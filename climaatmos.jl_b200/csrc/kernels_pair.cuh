@@ -8,6 +8,7 @@
 #include "kernels_row.cuh"
 #include "pair.cuh"
 #include "thermo2.cuh"
+#include "moist.cuh"
 
 namespace b200 {
 
@@ -112,10 +113,14 @@ __device__ __forceinline__ void sgetq(const FT* s, P2<FT> (&a)[2], int j, int v)
 
 // ---------------------------------------------------------------------------------------------
 // NVC: compile-time number of levels (63 in every production configuration), 0 = run-time P.nv
-template <class FT, int NVC>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
+// MOIST (microphysics_model 0M; component 4 of Y.c is the active ρq_tot): moist thermodynamic state (moist.cuh); ∇²q_tot_eff =
+// wdivₕ(gradₕ(q_tot − q_tot_r(p))) → H[4] (hyperdiffusion.jl:148-165); ρ(h_eff + Φ) → Hw for the water enthalpy flux of the apply
+// kernel (:293-306); viscous sponge on the total water: the aggregate tendency also enters ρ, its enthalpy flux ρe_tot
+// (viscous_sponge.jl:158-199; the ρq_tot part itself is written by k5_tracer_a).  The dry instantiations are unchanged.
+template <class FT, int NVC, bool MOIST = false>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 && !MOIST ? 2 : 1))
 k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-         const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H) {
+         const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H, FT* __restrict__ Hw = nullptr) {
   using V = P2<FT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
@@ -132,6 +137,8 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   V rho[2], u1[2], u2[2], re[2], u3[2], U1[2], U2[2];
   ld4q(rho, gY, nv, cv, FT(1)); ld4q(u1, gY + 16 * nv, nv, cv, FT(0)); ld4q(u2, gY + 32 * nv, nv, cv, FT(0));
   ld4q(re, gY + 48 * nv, nv, cv, FT(0)); ld4q(u3, Yf + offf, nf, fv, FT(0));
+  V rq[2], qs[2], qe[2], hw[2];  // MOIST: ρq_tot, q_tot, q_tot − q_tot_r(p), h_eff + Φ
+  if (MOIST) ld4q(rq, gY + 64 * nv, nv, cv, FT(0));
   sputq(s_u3, u3, j, v); sputq(s_r, rho, j, v); sputq(s_u1, u1, j, v); sputq(s_u2, u2, j, v);
   __syncthreads();  // hg + first exchange slabs
   V c1[2], c2[2];
@@ -152,7 +159,19 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       V kv = fma2(u3h[p], u3h[p] * L.g33hi, u3[p] * (u3[p] * L.g33lo)) * FT(0.5);
       K[p] = (kh + kv) * FT(0.5);
       u3c[p] = (u3[p] + u3h[p]) * FT(0.5);
-      const Pt2<FT> t = thermo2(P, rho[p], re[p], K[p], L.phi);
+      Pt2<FT> t;
+      if constexpr (MOIST) {
+        Mst<FT> m0, m1;
+        const Pt<FT> ta = thermo_m(P, rho[p].lo(), re[p].lo(), rq[p].lo(), K[p].lo(), L.phi, m0);
+        const Pt<FT> tb = thermo_m(P, rho[p].hi(), re[p].hi(), rq[p].hi(), K[p].hi(), L.phi, m1);
+        t = pack_pt(ta, tb);
+        qs[p] = V(rq[p].lo() / rho[p].lo(), rq[p].hi() / rho[p].hi());
+        const FT Tra = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * pow7(ta.Pi), Trb = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * pow7(tb.Pi);
+        qe[p] = qs[p] - V(q_tot_r(P, ta.p, Tra), q_tot_r(P, tb.p, Trb));
+        hw[p] = V(h_eff_plus_phi(P, m0, L.phi), h_eff_plus_phi(P, m1, L.phi));
+      } else {
+        t = thermo2(P, rho[p], re[p], K[p], L.phi);
+      }
       hh[p] = t.h; Pi[p] = t.Pi; th[p] = t.thp;
       sE[p] = (K[p] + L.phi) - t.phir;
       sd[p] = fma2(t.T - P.T_0, P.cp_d, V(L.phi));
@@ -189,7 +208,8 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     div4p<FT, 1>(F1, F2, mw, vl, wd);
 #pragma unroll
     for (int p = 0; p < 2; ++p) { wd[p] = wd[p] * rjs[p]; G1[p] = F1[p] * hh[p]; G2[p] = F2[p] * hh[p]; }
-    if (cv) { V nwd[2] = {-wd[0], -wd[1]}; st4q(nwd, gT, nv); }
+    V rt[2] = {-wd[0], -wd[1]};
+    if (!MOIST && cv) st4q(rt, gT, nv);
     div4p<FT, 1>(G1, G2, mw, vl, t);
     deta4p(hh, md, vl, g2);
     dxi4p<FT, 0>(hh, g1);
@@ -206,7 +226,19 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       div4p<FT, 1>(S1, S2, mw, vl, t);
 #pragma unroll
       for (int p = 0; p < 2; ++p) et[p] = fma2(t[p] * rjs[p], L.bvc, et[p]);
+      if constexpr (MOIST) {  // β wdivₕ(ρ gradₕ q_tot) → ρ ; β wdivₕ(ρ (h_eff + Φ) gradₕ q_tot) → ρe_tot
+        deta4p(qs, md, vl, g2);
+        dxi4p<FT, 0>(qs, g1);
+        METRIC_FLUX(S1, S2, g1, g2, rho[p] * HGP(HG_J2, p))
+        div4p<FT, 1>(S1, S2, mw, vl, t);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) { rt[p] = fma2(t[p] * rjs[p], L.bvc, rt[p]); S1[p] = S1[p] * hw[p]; S2[p] = S2[p] * hw[p]; }
+        div4p<FT, 1>(S1, S2, mw, vl, t);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) et[p] = fma2(t[p] * rjs[p], L.bvc, et[p]);
+      }
     }
+    if (MOIST && cv) st4q(rt, gT, nv);
     if (cv) st4q(et, gT + 48 * nv, nv);
     if (gH) {  // ∇²(s_d − s_d,r)  (hyperdiffusion.jl:142-147)
       V Q1[2], Q2[2];
@@ -217,6 +249,15 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
 #pragma unroll
       for (int p = 0; p < 2; ++p) t[p] = t[p] * rjs[p];
       if (cv) st4q(t, gH + 48 * nv, nv);
+      if constexpr (MOIST) {  // ∇²q_tot_eff and ρ(h_eff + Φ)
+        deta4p(qe, md, vl, g2);
+        dxi4p<FT, 0>(qe, g1);
+        METRIC_FLUX(Q1, Q2, g1, g2, HGP(HG_J2, p))
+        div4p<FT, 1>(Q1, Q2, mw, vl, t);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) { t[p] = t[p] * rjs[p]; hw[p] = hw[p] * rho[p]; }
+        if (cv) { st4q(t, gH + 64 * nv, nv); st4q(hw, Hw + ((size_t)e * 16 * nv + (n0 * nv + v)), nv); }
+      }
     }
   }
   // ---- momentum: split-form PGF (advection.jl:82-88)
@@ -362,6 +403,9 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   B200_ROW_PROLOGUE
   ROW_COLUMNS
   const int q = 4 + blockIdx.y;
+  // ρq_tot of a moist (0M) context: horizontal advection and the sponge as for any tracer; its vertical transport is implicit
+  // (advection.jl:250) and its ∇² slot carries ∇²q_tot_eff, written by k5_exp_a<…, MOIST>
+  const bool active = P.moist && q == 4;
   const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   V rho[2], u1[2], u2[2], rq[2], u3[2], chi[2];
   ld4p(rho, gY, nv, j, v, cv, FT(1)); ld4p(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4p(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
@@ -392,7 +436,7 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
     lim[p] = -((t[p] * rjs[p]) * FT(0.5) + fma2(chi[p], wd[p], adv) * FT(0.5));
     out[p] = V(FT(0));
   }
-  if (H) {  // ∇²χ
+  if (H && !active) {  // ∇²χ
     V Q1[2], Q2[2];
     METRIC_FLUX(Q1, Q2, g1, g2, HGP(HG_J2, p))
     div4p<FT, 1>(Q1, Q2, mw, vl, t);
@@ -409,7 +453,7 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   }
   // vertical transport: flux through face v of (ᶠinterp(ρJ)/J2)·u³·χ_face, zero on the boundary faces
   {
-    const bool interior = v > 0 && v < nv;
+    const bool interior = v > 0 && v < nv && !active;
     FT fx[4];
     const int vm = v > 0 ? v - 1 : 0, vm2 = v > 1 ? v - 2 : 0, vp = v < nv - 1 ? v + 1 : v;
 #pragma unroll
@@ -465,6 +509,7 @@ k5_tracer_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   using V = P2<FT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
+  if (P.moist && blockIdx.y == 0) return;  // ρq_tot: k_moist_c
   B200_ROW_PROLOGUE
   ROW_COLUMNS
   const int q = 4 + blockIdx.y;
@@ -481,6 +526,48 @@ k5_tracer_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
 #pragma unroll
   for (int p = 0; p < 2; ++p) old[p] = old[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
   if (cv) st4p(old, gT, nv, j, v);
+}
+
+// Water part of the hyperdiffusion apply for a moist (0M) context, on the DSSed ∇²q_tot_eff = H[4] (same row layout):
+//   d = ν₄ₛ wdivₕ(ρ gradₕ(∇²q_tot_eff)):  ρq_totₜ −= d and ρₜ −= d, both in Yₜ_lim   (hyperdiffusion.jl:475-484)
+//   ρe_totₜ −= ν₄ₛ wdivₕ(ρ (h_eff + Φ) gradₕ(∇²q_tot_eff)) in Yₜ                       (:293-307); Hw = ρ(h_eff + Φ) from k5_exp_a
+// Tlim = Yₜ_lim.c, or Yₜ.c when the caller has no limited part (native stepper without a limiter).
+template <class FT>
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
+k_moist_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+          const FT* __restrict__ H, const FT* __restrict__ Hw, FT* __restrict__ Ytc, FT* __restrict__ Tlim) {
+  using V = P2<FT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FT* hg = reinterpret_cast<FT*>(smem_raw);
+  B200_ROW_PROLOGUE
+  ROW_COLUMNS
+  const size_t base = (size_t)e * P.ncf * 16 * nv;
+  V rho[2], Lq[2], rh[2], a[2], g1[2], Q1[2], Q2[2], b[2], old[2];
+  ld4p(rho, Yc + base, nv, j, v, cv, FT(1));
+  ld4p(Lq, H + base + (size_t)4 * 16 * nv, nv, j, v, cv, FT(0));
+  ld4p(rh, Hw + (size_t)e * 16 * nv, nv, j, v, cv, FT(0));
+  __syncthreads();
+  deta4p(Lq, md, vl, a);
+  dxi4p<FT, 0>(Lq, g1);
+  METRIC_FLUX(Q1, Q2, g1, a, rho[p] * HGP(HG_J2, p))
+  div4p<FT, 1>(Q1, Q2, mw, vl, b);
+  V d[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) d[p] = ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
+  FT* gl = Tlim + base;
+  ld4p(old, gl, nv, j, v, cv, FT(0));
+  old[0] = old[0] - d[0]; old[1] = old[1] - d[1];
+  if (cv) st4p(old, gl, nv, j, v);
+  ld4p(old, gl + (size_t)4 * 16 * nv, nv, j, v, cv, FT(0));
+  old[0] = old[0] - d[0]; old[1] = old[1] - d[1];
+  if (cv) st4p(old, gl + (size_t)4 * 16 * nv, nv, j, v);
+  METRIC_FLUX(Q1, Q2, g1, a, rh[p] * HGP(HG_J2, p))
+  div4p<FT, 1>(Q1, Q2, mw, vl, b);
+  FT* ge = Ytc + base + (size_t)3 * 16 * nv;
+  ld4p(old, ge, nv, j, v, cv, FT(0));
+#pragma unroll
+  for (int p = 0; p < 2; ++p) old[p] = old[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
+  if (cv) st4p(old, ge, nv, j, v);
 }
 
 }  // namespace b200

@@ -440,6 +440,7 @@ __device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, c
   for (int k = 0; k < 12; ++k) *f[k] = base + k * 4 * LVP - quarter * 4 * LVP;
   const FT* gY = Yc + (size_t)h * P.ncf * 16 * nv;
   const int o = n * LVP + v;
+  FT* qprof = base + 13 * 4 * LVP - quarter * 4 * LVP;  // moist (0M) contexts: q_tot = ρq_tot/ρ (profile 13; 12 and 14 are scratch)
   if (v < nv) {
     S.rho[o] = gY[(0 * 16 + n) * nv + v]; S.u1[o] = gY[(1 * 16 + n) * nv + v];
     S.u2[o] = gY[(2 * 16 + n) * nv + v]; S.re[o] = gY[(3 * 16 + n) * nv + v];
@@ -448,12 +449,20 @@ __device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, c
   __syncthreads();
   if (v < nv) {
     FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
-    Pt<FT> t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
+    Pt<FT> t;
+    if (P.moist) {
+      Mst<FT> m;
+      const FT rq = gY[(4 * 16 + n) * nv + v];
+      t = thermo_m(P, S.rho[o], S.re[o], rq, K, V.phic[v], m);
+      qprof[o] = rq / S.rho[o];
+    } else {
+      t = thermo(P, S.rho[o], S.re[o], K, V.phic[v]);
+    }
     S.K[o] = K; S.h[o] = t.h; S.Pi[o] = t.Pi; S.thv[o] = t.thv; S.thp[o] = t.thp; S.phr[o] = pgf_aux(t); S.T[o] = t.T;
   }
   __syncthreads();
 }
-constexpr int Q_WORDS = 13 * 4 * LVP;  // 12 profiles + one scratch profile
+constexpr int Q_WORDS = 15 * 4 * LVP;  // 12 profiles + scratch + (moist) q_tot + scratch
 
 template <class FT>
 __global__ void __launch_bounds__(NT) k_t_imp2(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
@@ -472,6 +481,12 @@ __global__ void __launch_bounds__(NT) k_t_imp2(Par<FT> P, const FT* __restrict__
     gT[(0 * 16 + n) * nv + v] = rt; gT[(1 * 16 + n) * nv + v] = FT(0);
     gT[(2 * 16 + n) * nv + v] = FT(0); gT[(3 * 16 + n) * nv + v] = et;
     for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
+    if (P.moist) {  // central transport of the active tracer ρq_tot (implicit_tendency.jl:210-214): timp_center with q_tot for h_tot
+      ImpSlabs<FT> Sq = S;
+      Sq.h = reinterpret_cast<FT*>(smem_raw) + 13 * 4 * LVP - quarter * 4 * LVP;
+      FT rt2, qt; timp_center(V, Sq, n, v, nv, rt2, qt);
+      gT[(4 * 16 + n) * nv + v] = qt;
+    }
   }
   if (v < nf) gF[n * nf + v] = timp_face(P, V, S, n, v, nv);
 }
@@ -512,14 +527,18 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
   FT* base = reinterpret_cast<FT*>(smem_raw);
   q_prepare(P, V, hg, Yc, Yf, h, quarter, base, S);
   FT* flx = base + 12 * 4 * LVP - quarter * 4 * LVP;
+  FT* qprof = base + 13 * 4 * LVP - quarter * 4 * LVP;
+  FT* flq = base + 14 * 4 * LVP - quarter * 4 * LVP;
   const int o = n * LVP + v;
   if (v < nf) {
-    FT r = FT(0);
+    FT r = FT(0), rq = FT(0);
     if (v > 0 && v < nv) {
       FT w = V.g33f[v] * S.u3[o];
       r = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, S.h, o, v, nv, w);
+      if (P.moist) rq = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, qprof, o, v, nv, w);
     }
     flx[o] = r;
+    if (P.moist) flq[o] = rq;
   }
   __syncthreads();
   FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
@@ -528,6 +547,7 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
     gT[(0 * 16 + n) * nv + v] = FT(0); gT[(1 * 16 + n) * nv + v] = FT(0); gT[(2 * 16 + n) * nv + v] = FT(0);
     gT[(3 * 16 + n) * nv + v] = -(flx[o + 1] - flx[o]) / V.mc[v];
     for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
+    if (P.moist) gT[(4 * 16 + n) * nv + v] = -(flq[o + 1] - flq[o]) / V.mc[v];  // implicit_tendency.jl:333-338
   }
   if (v < nf) gF[n * nf + v] = FT(0);
 }

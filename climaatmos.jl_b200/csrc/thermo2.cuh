@@ -42,6 +42,14 @@ __device__ __forceinline__ Pt2<FT> thermo2(const Par<FT>& P, P2<FT> rho, P2<FT> 
   return o;
 }
 
+// two scalar thermodynamic states → one packed state
+template <class FT>
+__device__ __forceinline__ Pt2<FT> pack_pt(const Pt<FT>& a, const Pt<FT>& b) {
+  Pt2<FT> o;
+  o.T = P2<FT>(a.T, b.T); o.p = P2<FT>(a.p, b.p); o.h = P2<FT>(a.h, b.h); o.Pi = P2<FT>(a.Pi, b.Pi); o.thp = P2<FT>(a.thp, b.thp);
+  o.thv = P2<FT>(a.thv, b.thv); o.phir = P2<FT>(a.phir, b.phir); o.sdr = P2<FT>(a.sdr, b.sdr); o.lnPi = P2<FT>(a.lnPi, b.lnPi);
+  return o;
+}
 // Packed form of pgf_aux / pgf_diff (common.cuh): Float32 evaluates ΔΠ and ΔΦ_r between adjacent levels in difference form from
 // κ·log(p_hi/p_lo); Float64 keeps the literal differences.  expm1 by its Taylor series (|Δ| ≲ 0.35 for any grid with Δz ≤ 8 km:
 // the x¹⁰/10! remainder is < 10⁻¹¹).

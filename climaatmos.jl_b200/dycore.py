@@ -66,6 +66,7 @@ class AtmosSimulation:
                  initial_condition="DryBaroclinicWave", energy_q_tot_upwinding="vanleer_limiter", rad=None,
                  tracers=None, tracer_upwinding="vanleer_limiter", apply_sem_quasimonotone_limiter=False,
                  vert_diff=None, implicit_diffusion=False, approximate_linear_solve_iters=1, tracer_nonnegativity_method=None,
+                 microphysics_model=None, q_0=0.018,
                  params: DycoreParams | None = None, device=None, comms=None, grid=None):
         torch = _torch()
         self.torch = torch
@@ -80,12 +81,18 @@ class AtmosSimulation:
                                        vert_diff=vert_diff, implicit_diffusion=bool(implicit_diffusion),
                                        approximate_linear_solve_iters=int(approximate_linear_solve_iters),
                                        disable_momentum_vertical_diffusion=(rad == "held_suarez"),
-                                       tracer_nonnegativity_method=tracer_nonnegativity_method)
+                                       tracer_nonnegativity_method=tracer_nonnegativity_method,
+                                       # microphysics_model: None (dry) | "0M" (EquilibriumMicrophysics0M: ρq_tot is component 4 of Y.c)
+                                       microphysics_model=microphysics_model)
         self.grid = grid or make_sphere_grid(FT=self.FT, h_elem=h_elem, z_elem=z_elem, z_max=z_max, dz_bottom=dz_bottom,
                                              radius=self.params.planet_radius, deep_atmosphere=deep_atmosphere)
         self.comms = comms  # parallel.DistributedComms or None
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        if initial_condition == "DryBaroclinicWave":
+        if (microphysics_model == "0M") != (initial_condition == "MoistBaroclinicWave"):
+            raise ValueError('microphysics_model "0M" goes with initial_condition "MoistBaroclinicWave" (and only with it)')
+        if initial_condition == "MoistBaroclinicWave":
+            Yc, Yf = setups.moist_baroclinic_wave(self.grid, self.params, q_0=q_0)
+        elif initial_condition == "DryBaroclinicWave":
             Yc, Yf = setups.dry_baroclinic_wave(self.grid, self.params)
         elif initial_condition == "DecayingProfile":
             Yc, Yf = setups.decaying_profile(self.grid, self.params)
@@ -93,8 +100,9 @@ class AtmosSimulation:
             raise ValueError(f"unknown initial_condition {initial_condition}")
         # passive grid-scale tracers ρχ appended after ρe_tot (e.g. the chemistry tracer ρq_gas_A,
         # setups/common/prognostic_variables.jl:138-145): ``tracers`` = list of χ(lat°, lon°, z) callables or arrays
-        self.n_tracers = len(tracers) if tracers else 0
-        if self.n_tracers:
+        n_passive = len(tracers) if tracers else 0
+        self.n_tracers = n_passive + (1 if microphysics_model == "0M" else 0)  # tracer components of Y.c (ρq_tot first)
+        if n_passive:
             zz = np.broadcast_to(self.grid.z_c, Yc[:, 0].shape)
             extra = []
             for tr in tracers:

@@ -16,8 +16,9 @@
  *
  * Limits (checked by b200_create, which fails with a message instead of computing something else):
  *   Nq = 4 (nh_poly 3); 2 <= nv <= 63 (a column of faces is one 64-lane row of the kernels); flat grid (NoWarp topography: the
- *   metric is used in factored form, 2-D per-node part x per-level scale); dry thermodynamics + up to 4 PASSIVE tracers (no
- *   active rho*q_tot: moist 0M needs Thermodynamics.jl's saturation adjustment); <= 32 neighbour ranks.
+ *   metric is used in factored form, 2-D per-node part x per-level scale); dry thermodynamics or the equilibrium-moist (0M) state
+ *   with an active rho*q_tot, up to 4 tracer components in all (rho*q_tot counts as the first); the moist state excludes vertical
+ *   diffusion and the Held-Suarez forcing; <= 32 neighbour ranks.
  *   b200_step_ars343 is ARS343 with ONE Newton iteration per implicit stage (max_newton_iters_ode: 1, the reference's setting
  *   for these configurations); any other stepper / Newton loop drives the individual hook entry points.  ldiv! is the direct
  *   BlockArrowheadSolve (or the ApproximateBlockArrowheadIterativeSolve with implicit vertical diffusion); the Krylov
@@ -40,7 +41,8 @@ typedef struct {
   int32_t nq;        /* GLL nodes per direction; must be 4 */
   int32_t ft_bytes;  /* 4 = Float32, 8 = Float64 */
   int32_t deep;      /* 1 = DeepSphericalGlobalGeometry, 0 = shallow (grids.jl:64-68) */
-  int32_t n_tracers; /* passive grid-scale tracers ρχ appended to Y.c after ρe_tot (0..4): Y.c has Nf = 4 + n_tracers */
+  int32_t n_tracers; /* grid-scale tracers ρχ appended to Y.c after ρe_tot (0..4): Y.c has Nf = 4 + n_tracers; with
+                        params.microphysics_0M the first of them is ρq_tot (prognostic_variables.jl:54-61), the others passive */
 } b200_dims;
 
 /* Geometry, copied from the live ClimaCore objects (HOST pointers, double precision; the
@@ -104,6 +106,15 @@ typedef struct {
   /* tracer_nonnegativity_method: vertical_water_borrowing (default_config.yml:190-198; src/cache/cache.jl:216-219): lim! also applies
    * ClimaCore's Limiters.VerticalMassBorrowingLimiter((0,)) to χ = ρχ/ρ of every tracer (limited_tendencies.jl:95-121); 0 = off */
   int32_t vertical_water_borrowing_limiter;
+  /* microphysics_model: 0 = DryModel, 1 = EquilibriumMicrophysics0M — component 4 of Y.c (the first of the n_tracers >= 1 tracer
+   * components) is the thermodynamically ACTIVE rho*q_tot: moist thermodynamic state with saturation adjustment
+   * (src/cache/precomputed_quantities.jl:735-815), central vertical transport + post-Newton correction of q_tot
+   * (implicit_tendency.jl:210-214, 333-338), the (rho q_tot, u3) / (u3, rho q_tot) Jacobian blocks with kappa_m
+   * (manual_sparse_jacobian.jl:653-690, 770-790, 827-831), grad^2 q_tot_eff and the water enthalpy / mass split of hyperdiffusion and
+   * viscous sponge (hyperdiffusion.jl:148-165, 293-306, 475-484; viscous_sponge.jl:158-199).  The 0M precipitation sink itself is a
+   * parameterised tendency outside the dycore.  Thermodynamics.jl parameters (docs/src/thermodynamics.md:60-150): */
+  int32_t microphysics_0M;
+  double R_v, cp_v, cp_l, cp_i, LH_v0, LH_s0, T_triple, press_triple, T_freeze, T_icenuc, pow_icenuc;
 } b200_params;
 
 /* Optional device pointers to p.precomputed fields written by b200_cache_imp (any may be NULL).

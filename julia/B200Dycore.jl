@@ -18,6 +18,7 @@ import ClimaCore: Fields, Spaces, Topologies, Quadratures, Geometry, Meshes
 import ClimaComms, CUDA, LinearAlgebra
 import ..ClimaAtmos as CA
 import ..ClimaAtmos.Parameters as CAP
+import Thermodynamics.Parameters as TDP   # TD.TP in the reference (refstate_thermodynamics.jl:57)
 
 const lib = get(ENV, "B200_DYCORE_LIB", joinpath(@__DIR__, "..", "deps", "libb200dycore.so"))
 
@@ -58,6 +59,9 @@ struct ParamsC
     disable_momentum_vertical_diffusion::Int32
     C_E::Float64; H_diffusion::Float64; D_0_diffusion::Float64
     vertical_water_borrowing_limiter::Int32
+    microphysics_0M::Int32       # 0 DryModel, 1 EquilibriumMicrophysics0M (ρq_tot = first tracer component, thermodynamically active)
+    R_v::Float64; cp_v::Float64; cp_l::Float64; cp_i::Float64; LH_v0::Float64; LH_s0::Float64
+    T_triple::Float64; press_triple::Float64; T_freeze::Float64; T_icenuc::Float64; pow_icenuc::Float64
 end
 struct CachePtrs
     u_c::Ptr{Cvoid}; u3_f::Ptr{Cvoid}; K_c::Ptr{Cvoid}; T_c::Ptr{Cvoid}; p_c::Ptr{Cvoid}; h_tot_c::Ptr{Cvoid}
@@ -120,6 +124,9 @@ function create(Y, p; approximate_solve_iters = 1)   # = B200Jacobian(...).appro
     topo_c = TopologyC(pointer(faces), length(faces) ÷ 5, pointer(lv), pointer(lvo), length(lvo) - 1, length(nbr),
                        pointer(nbr), pointer(soff), pointer(selems), pointer(roff), pointer(gid))
     rs, vs = p.atmos.rayleigh_sponge, p.atmos.viscous_sponge
+    thp = CAP.thermodynamics_params(params)                             # Thermodynamics.Parameters accessors (TD.TP, refstate_thermodynamics.jl:57)
+    p.atmos.microphysics_model isa Union{CA.DryModel, CA.EquilibriumMicrophysics0M} ||
+        error("B200Dycore: only DryModel and EquilibriumMicrophysics0M are served")
     vd = p.atmos.vertical_diffusion
     prm = ParamsC(CAP.R_d(params), CAP.cp_d(params), CAP.cv_d(params), CAP.T_0(params), CAP.grav(params), CAP.Omega(params),
                   CAP.p_ref_theta(params), CAP.T_surf_ref(params), CAP.T_min_ref(params), CAP.T_min_sgs(params),
@@ -138,7 +145,10 @@ function create(Y, p; approximate_solve_iters = 1)   # = B200Jacobian(...).appro
                   vd isa CA.VerticalDiffusion ? Float64(vd.C_E) : 0.0,
                   vd isa CA.DecayWithHeightDiffusion ? Float64(vd.H) : 1.0,
                   vd isa CA.DecayWithHeightDiffusion ? Float64(vd.D₀) : 0.0,
-                  p.numerics.vertical_water_borrowing_limiter === nothing ? 0 : 1)                # cache.jl:213-219
+                  p.numerics.vertical_water_borrowing_limiter === nothing ? 0 : 1,                # cache.jl:213-219
+                  p.atmos.microphysics_model isa CA.EquilibriumMicrophysics0M ? 1 : 0,            # precomputed_quantities.jl:735
+                  TDP.R_v(thp), TDP.cp_v(thp), TDP.cp_l(thp), TDP.cp_i(thp), TDP.LH_v0(thp), TDP.LH_s0(thp),
+                  TDP.T_triple(thp), TDP.press_triple(thp), TDP.T_freeze(thp), TDP.T_icenuc(thp), TDP.pow_icenuc(thp))
     id = zeros(UInt8, 128)
     if nranks > 1
         rank == 0 && check(ccall((:b200_nccl_unique_id, lib), Cint, (Ptr{UInt8},), id), "b200_nccl_unique_id")

@@ -22,6 +22,7 @@ __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.w
 
 using namespace b200;
 typedef double FT;
+#include "emu_moist.h"
 
 template <class F>
 static void run_grid(int nblocks, F&& body) {
@@ -52,7 +53,9 @@ extern "C" __attribute__((visibility("default"))) int emu_imp5(int nh, int nv, c
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
-  run_grid(nh, [&] { k5_imp_stage<FT, 0>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  emu_apply_moist(P, sc[3]);
+  if (g_moist_on) run_grid(nh, [&] { k5_imp_stage<FT, 0, false, true>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  else run_grid(nh, [&] { k5_imp_stage<FT, 0>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
   return 0;
 }
 
@@ -69,6 +72,8 @@ extern "C" __attribute__((visibility("default"))) int emu_ldiv5(int nh, int nv, 
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
-  run_grid(nh, [&] { k5_imp_stage<FT, 0, true>(P, hgeo, &V, Yc, Yf, dYc, dYf, (FT)sc[10], Rc, Rf); });
+  emu_apply_moist(P, sc[3]);
+  if (g_moist_on) run_grid(nh, [&] { k5_imp_stage<FT, 0, true, true>(P, hgeo, &V, Yc, Yf, dYc, dYf, (FT)sc[10], Rc, Rf); });
+  else run_grid(nh, [&] { k5_imp_stage<FT, 0, true>(P, hgeo, &V, Yc, Yf, dYc, dYf, (FT)sc[10], Rc, Rf); });
   return 0;
 }

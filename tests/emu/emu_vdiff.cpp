@@ -21,6 +21,7 @@ using namespace b200;
 #define EMU_FT double
 #endif
 typedef EMU_FT FT;  // -DEMU_FT=float builds the Float32 instantiations (arrays are FT, the scalar block sc stays double)
+#include "emu_moist.h"
 
 template <class F>
 static void run_grid(int nblocks, F&& body) {
@@ -106,9 +107,10 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  emu_apply_moist(P, sc[3]);
   run_grid(nh, [&] { k_cache_imp<FT>(P, hgeo, &V, Yc, Yf, (FT*)nullptr, (FT*)nullptr, Kc, Tc, pc, hc); });
   run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
-  run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });
+  if (!g_moist_on) run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });  // debug planes: dry only
   (void)Rc; (void)Rf; (void)dYc; (void)dYf;  // ldiv! of the dry path is k5_imp_stage<…, LDIV>: emu_imp5.cpp (emu_ldiv5)
   run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
   (void)Sc; (void)Sf;

@@ -1,0 +1,183 @@
+"""GPU parity tests of the MOIST (EquilibriumMicrophysics0M, BASELINE.json configs[2]) path through the C-ABI against the oracle's
+moist path on the same seeded inputs: every hook, the fused implicit stage, the fused and the hook-by-hook ARS343 step, with and
+without sponges / hyperdiffusion / a passive tracer / the limiter, Float64 (bar 1e-11; north star 1e-12) and Float32 (bar 1e-5 on
+ρ, uₕ, ρe_tot, ρq_tot; u₃ as in tests/test_gpu_parity.py).  The states carry cloudy points (q_0 raised where stated), so the
+saturation-adjustment iteration runs on the device."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from climaatmos_jl_b200 import dycore, params as prm
+from oracle.dycore_oracle import Oracle
+from tests.conftest import record_parity
+from tests.test_gpu_parity import rel, U3_COARSE
+
+torch = pytest.importorskip("torch")
+
+NAMES = ("rho", "u1", "u2", "rhoe", "rhoq")
+CASES = {
+    "he4ze10": (4, 10, 30000.0, 500.0, 400.0, False),
+    "he3ze63": (3, 63, 60000.0, 30.0, 120.0, True),
+    "he2ze31": (2, 31, 45000.0, 300.0, 200.0, True),
+}
+
+
+def make(FT, name, q_0=0.03, **kw):
+    he, ze, zmax, dzb, dt, sp = CASES[name]
+    P = prm.DycoreParams(zd_rayleigh=0.66 * zmax, zd_viscous=0.66 * zmax)
+    sim = dycore.AtmosSimulation(FT=FT, h_elem=he, z_elem=ze, z_max=zmax, dz_bottom=dzb, dt=dt, rayleigh_sponge=sp, viscous_sponge=sp,
+                                 params=P, microphysics_model="0M", initial_condition="MoistBaroclinicWave", q_0=q_0, **kw)
+    return sim, P
+
+
+def perturbed_state(sim, FT):
+    Yc0, Yf0 = sim.Y.cpu()
+    rng = np.random.default_rng(1234)
+    Yc = (Yc0.astype(np.float64) * (1 + 1e-3 * rng.standard_normal(Yc0.shape))).astype(FT)
+    Yf = (0.5 * sim.grid.dz_f * rng.standard_normal(Yf0.shape)).astype(FT)
+    return Yc, Yf, rng
+
+
+def check(gc, gf, oc, of, t, what, ncomp=5):
+    errs = {}
+    for k in range(ncomp):
+        n = NAMES[k] if k < 5 else f"chi{k - 5}"
+        errs[n] = rel(gc[:, k], oc[:, k])
+    errs["u3"] = rel(gf[:, 0], of[:, 0])
+    record_parity("moist " + what, dict(dtype=str(gc.dtype), shape=list(gc.shape), **errs))
+    for n, e in errs.items():
+        bar = t.get(n, t["rho"])
+        assert e <= bar, f"{what}: {n} rel-L2 {e:.3e} > {bar:.1e}"
+
+
+def tol(FT, kind="state", u3=1e-5):
+    if FT == np.float64:
+        return dict(rho=1e-11, u3=1e-11)
+    if kind == "state":
+        return dict(rho=1e-5, u3=u3)
+    return dict(rho=1e-5, u1=2e-4, u2=2e-4, rhoe=1e-4, rhoq=2e-4, u3=2e-4)
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["he4ze10", "he3ze63"])
+def test_moist_hooks_match_oracle(FT, name):
+    sim, P = make(FT, name)
+    o = Oracle(sim.grid, P, sim.numerics, FT)
+    Yc, Yf, rng = perturbed_state(sim, FT)
+    Y = sim.to_device(Yc, Yf)
+    oc, of = Yc.copy(), Yf.copy()
+    t_state, t_tend = tol(FT, "state"), tol(FT, "tend")
+    sim.dss(Y)
+    o.dss_state(oc, of)
+    check(*Y.cpu(), oc, of, t_state, "dss")
+    pre = {k: torch.zeros_like(Y.c[:, 0:1]) for k in ("K_c", "T_c", "p_c", "h_tot_c")}
+    sim.set_implicit_precomputed_quantities(Y, precomputed=pre)
+    pc = o.set_implicit_precomputed_quantities(oc, of)
+    assert ((pc["ql"] + pc["qi"]) > 0).mean() > 0.005  # cloudy points: the Newton branch of the saturation adjustment runs
+    lim = 1e-11 if FT == np.float64 else 2e-6
+    for k, kk in (("K_c", "K"), ("T_c", "T"), ("p_c", "p"), ("h_tot_c", "h_tot")):
+        assert rel(pre[k].cpu().numpy()[:, 0], pc[kk]) < lim, k
+    Yt = Y.zeros_like()
+    sim.implicit_tendency(Yt, Y)
+    check(*Yt.cpu(), *o.implicit_tendency(oc, of, pc), t_tend, "t_imp")
+    dtg = sim.dt * 0.4358665215
+    sim.update_jacobian(Y, dtg)
+    Jm = o.update_jacobian(oc, of, pc, dtg)
+    Rc = (rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3).astype(FT)
+    Rf = rng.standard_normal(Yf.shape).astype(FT)
+    R = sim.to_device(Rc, Rf)
+    dY = R.zeros_like()
+    sim.ldiv(dY, R)
+    check(*dY.cpu(), *o.ldiv(Jm, Rc, Rf), t_state if FT == np.float64 else dict(rho=2e-5, u1=1e-6, u2=1e-6, rhoe=2e-5, rhoq=2e-5, u3=2e-5), "ldiv")
+    sim.correct_implicit_advection_tendency(Yt, Y)
+    tc, tf = o.correct_implicit_advection_tendency(oc, of, pc)
+    gc, gf = Yt.cpu()
+    for k in (3, 4):
+        assert rel(gc[:, k], tc[:, k]) < (1e-10 if FT == np.float64 else 5e-4), k
+    assert np.all(gc[:, :3] == 0) and np.all(gf == 0)
+    Yl = Y.zeros_like()
+    Yl.c.fill_(7.0)
+    sim.remaining_tendency(Yt, Yl, Y)
+    tc, tf, lc = o.remaining_tendency(oc, of, pc, with_lim=True)
+    check(*Yt.cpu(), tc, tf, t_tend, "t_exp")
+    gl = Yl.c.cpu().numpy()
+    for k in (0, 4):  # Yₜ_lim: ρq_tot (advection + water hyperdiffusion) and ρ (the water mass that hyperdiffuses)
+        assert rel(gl[:, k], lc[:, k]) < (1e-10 if FT == np.float64 else 2e-4), ("T_lim", k, rel(gl[:, k], lc[:, k]))
+    assert np.all(gl[:, 1:4] == 0) and float(Yl.f.abs().max()) == 0.0
+    sim.close()
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+@pytest.mark.parametrize("name,upw", [("he4ze10", "vanleer_limiter"), ("he3ze63", "vanleer_limiter"), ("he2ze31", "third_order"),
+                                      ("he2ze31", "first_order"), ("he4ze10", "none")])
+def test_moist_fused_step_matches_oracle_step(FT, name, upw):
+    sim, P = make(FT, name, energy_q_tot_upwinding=upw)
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    Yc0, Yf0 = sim.Y.cpu()
+    sim.step(fused=True)
+    gc, gf = sim.Y.cpu()
+    oc, of = o.step(Yc0.astype(np.float64), Yf0.astype(np.float64))
+    check(gc, gf, oc, of, tol(FT, "state", u3=U3_COARSE if name == "he4ze10" else 1e-5), f"step {name} {upw}")
+    # total water and mass are conserved by the step
+    W = o.c.WJ
+    for k in (0, 4):
+        a, b = (W * Yc0[:, k].astype(np.float64)).sum(), (W * gc[:, k].astype(np.float64)).sum()
+        assert abs(a - b) / abs(a) < (1e-12 if FT == np.float64 else 2e-6), (k, a, b)
+    sim.close()
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_moist_hook_by_hook_step_equals_fused_step(FT):
+    sim, P = make(FT, "he2ze31")
+    sim2, _ = make(FT, "he2ze31")
+    for _ in range(2):
+        sim.step(fused=True)
+        sim2.step(fused=False)
+    a, af = sim.Y.cpu()
+    b, bf = sim2.Y.cpu()
+    bar = 1e-12 if FT == np.float64 else 2e-6
+    for k in range(5):
+        assert rel(a[:, k], b[:, k]) < bar, (k, rel(a[:, k], b[:, k]))
+    assert rel(af, bf) < (1e-11 if FT == np.float64 else 2e-5)
+    sim.close()
+    sim2.close()
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_moist_step_with_passive_tracer_limiter_and_no_hyperdiffusion(FT):
+    """ρq_tot + one passive tracer with the SEM quasi-monotone limiter (lim! also limits ρq_tot; Yₜ_lim carries ρ), and the same
+    configuration without hyperdiffusion."""
+    tr = [lambda lat, lon, z: 1e-3 * (1.5 + np.sin(np.radians(lon)) * np.cos(np.radians(lat))) * np.exp(-z / 8000.0)]
+    for kw in (dict(apply_sem_quasimonotone_limiter=True), dict(hyperdiff=False)):
+        sim, P = make(FT, "he2ze31", tracers=tr, **kw)
+        o = Oracle(sim.grid, P, sim.numerics, np.float64)
+        Yc0, Yf0 = sim.Y.cpu()
+        sim.step(fused=True)
+        gc, gf = sim.Y.cpu()
+        oc, of = o.step(Yc0.astype(np.float64), Yf0.astype(np.float64))
+        check(gc, gf, oc, of, tol(FT, "state"), f"step tracer {sorted(kw)}", ncomp=6)
+        sim.close()
+
+
+def test_moist_create_rejects_what_is_not_built():
+    with pytest.raises(RuntimeError, match="vertical diffusion"):
+        make(np.float32, "he4ze10", vert_diff="DecayWithHeightDiffusion")
+    with pytest.raises(RuntimeError, match="Held-Suarez"):
+        make(np.float32, "he4ze10", rad="held_suarez")
+
+
+def test_moist_full_size_step_is_finite_and_conserves_water():
+    """BASELINE.json configs[2] shape: he30/ze63 Float32, 0M-moist baroclinic wave, 10 fused steps (graph-replayed)."""
+    P = prm.DycoreParams(zd_rayleigh=40000.0, zd_viscous=40000.0)
+    sim = dycore.AtmosSimulation(FT=np.float32, h_elem=30, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=90.0, rayleigh_sponge=True,
+                                 viscous_sponge=True, params=P, microphysics_model="0M", initial_condition="MoistBaroclinicWave")
+    W = torch.from_numpy((sim.grid.W * sim.grid.J2)[..., None] * (((sim.grid.radius + sim.grid.z_c) / sim.grid.radius) ** 2 * sim.grid.dz_c)).to(sim.device)
+    m0 = [float((W * sim.Y.c[:, k].double()).sum()) for k in (0, 4)]
+    for _ in range(10):
+        sim.step(fused=True)
+    assert bool(torch.isfinite(sim.Y.c).all()) and bool(torch.isfinite(sim.Y.f).all())
+    m1 = [float((W * sim.Y.c[:, k].double()).sum()) for k in (0, 4)]
+    for a, b in zip(m0, m1):
+        assert abs(a - b) / abs(a) < 5e-6, (a, b)
+    sim.close()
