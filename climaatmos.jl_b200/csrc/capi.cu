@@ -257,6 +257,9 @@ static Par<FT> make_par(const b200_ctx* c) {
     P.M.LH_v0 = (FT)p.LH_v0; P.M.LH_s0 = (FT)p.LH_s0; P.M.e_v0 = (FT)(p.LH_v0 - p.R_v * p.T_0); P.M.e_i0 = (FT)(p.LH_s0 - p.LH_v0);
     P.M.T_tr = (FT)p.T_triple; P.M.ln_ptr = (FT)log(p.press_triple); P.M.T_frz = (FT)p.T_freeze; P.M.T_icn = (FT)p.T_icenuc;
     P.M.pow_icn = (FT)p.pow_icenuc;
+    P.M.A_liq = (FT)((p.cp_v - p.cp_l) / p.R_v); P.M.A_ice = (FT)((p.cp_v - p.cp_i) / p.R_v);
+    P.M.B_liq = (FT)((p.LH_v0 - (p.cp_v - p.cp_l) * p.T_0) / p.R_v); P.M.B_ice = (FT)((p.LH_s0 - (p.cp_v - p.cp_i) * p.T_0) / p.R_v);
+    P.M.iT_tr = (FT)(1.0 / p.T_triple); P.M.epsv = (FT)(p.R_v / p.R_d);
   }
   return P;
 }
@@ -440,7 +443,9 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>()));
   CK(cudaFuncSetAttribute(k5_exp_a<FT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
+  CK(cudaFuncSetAttribute(k5_exp_a<FT, 63, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rowq<FT>(9)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>(true)));
+  CK(cudaFuncSetAttribute(k5_imp_stage<FT, 63, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>(true)));
   CK(cudaFuncSetAttribute(k5_imp_stage<FT, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5<FT>(true)));
   CK(cudaFuncSetAttribute(k_cache_imp<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(1)));
   CK(cudaFuncSetAttribute(k_lim_vborrow<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SLAB * sizeof(FT))));
@@ -1072,7 +1077,10 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
   const bool moist = c->prm.microphysics_0M != 0;
   if (moist && hd && !c->Hw) CK(cudaMalloc(&c->Hw, (size_t)c->dims.nh * 16 * c->dims.nv * sizeof(FT)));
   if (phase == 0) {
-    if (moist)  // moist thermodynamic state + ∇²q_tot_eff → H[4], ρ(h_eff + Φ) → Hw (run-time nv; 1 CTA/SM)
+    if (moist && nv63)  // moist thermodynamic state + ∇²q_tot_eff → H[4], ρ(h_eff + Φ) → Hw
+      launchx(c->pdl & 1, k5_exp_a<FT, 63, true>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw);
+    else if (moist)
       launchx(c->pdl & 1, k5_exp_a<FT, 0, true>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
               (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw);
     else if (nv63)
@@ -1283,7 +1291,10 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
     LAUNCH_CHECK(c);
     return 0;
   }
-  if (c->prm.microphysics_0M)
+  if (c->prm.microphysics_0M && c->dims.nv == 63 && !c->generic_nv)
+    launchx(c->pdl & 16, k5_imp_stage<FT, 63, false, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
+            (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
+  else if (c->prm.microphysics_0M)
     launchx(c->pdl & 16, k5_imp_stage<FT, 0, false, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
             (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else if (c->dims.nv == 63 && !c->generic_nv)

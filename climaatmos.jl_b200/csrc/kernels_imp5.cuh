@@ -20,7 +20,7 @@
 #include "kernels_row.cuh"
 #include "pair.cuh"
 #include "thermo2.cuh"
-#include "moist.cuh"
+#include "moist2.cuh"
 
 namespace b200 {
 
@@ -81,7 +81,7 @@ __device__ __forceinline__ void st2g(const P2<FT> (&a)[2], FT* __restrict__ g, i
 //               ApproximateBlockArrowheadIterativeSolve of :538-578 is the exact arrowhead solve with one more rank-one term in the
 //               Schur tridiagonal), central transport of q_tot (implicit_tendency.jl:210-214) and its post-Newton correction.
 template <class FT, int NVC, bool LDIV = false, bool MOIST = false>
-__global__ void __launch_bounds__(256, MOIST ? 1 : 2)
+__global__ void __launch_bounds__(256, (MOIST && sizeof(FT) == 8) ? 1 : 2)
 k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
              const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg, const FT* __restrict__ Rc = nullptr,
              const FT* __restrict__ Rf = nullptr) {
@@ -171,13 +171,10 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       const V2 K = Kh[p] + (u3[p] * (u3[p] * g33lo) + u3h[p] * (u3h[p] * g33hi)) * FT(0.25);
       Pt2<FT> t;
       if constexpr (MOIST) {
-        Mst<FT> m0, m1;
-        const Pt<FT> ta = thermo_m(P, rho[p].lo(), re[p].lo(), rq[p].lo(), K.lo(), phi, m0);
-        const Pt<FT> tb = thermo_m(P, rho[p].hi(), re[p].hi(), rq[p].hi(), K.hi(), phi, m1);
-        t = pack_pt(ta, tb);
-        kapv[p] = V2(m0.Rm / m0.cvm, m1.Rm / m1.cvm);  // ᶜkappa_m_field! (:653-662)
-        dpq = V2(dp_drhoq(P, m0), dp_drhoq(P, m1));
-        qv[p] = V2(rq[p].lo() / rho[p].lo(), rq[p].hi() / rho[p].hi());
+        Mst2<FT> m;
+        t = thermo2m(P, rho[p], re[p], rq[p], K, phi, m);
+        dpq = dp_drhoq2(P, m, kapv[p]);  // ᶜ∂p∂ρq_tot_field! (:670-690), ᶜkappa_m_field! (:653-662)
+        qv[p] = div2(rq[p], rho[p]);
         dp = t.T * (V2(P.R_d) - kapv[p] * P.cv_d) + ((V2(P.T_0 * P.cp_d) - K) - phi) * kapv[p];
       } else {
         t = thermo2(P, rho[p], re[p], K, phi);
@@ -354,11 +351,9 @@ k5_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
       if (cv) {
         const V2 K = Kh[p] + (nu[p] * (nu[p] * g33lo) + nu1[p] * (nu1[p] * g33hi)) * FT(0.25);
         if constexpr (MOIST) {
-          Mst<FT> m0, m1;
-          const Pt<FT> ta = thermo_m(P, nr[p].lo(), nre[p].lo(), nq[p].lo(), K.lo(), phi, m0);
-          const Pt<FT> tb = thermo_m(P, nr[p].hi(), nre[p].hi(), nq[p].hi(), K.hi(), phi, m1);
-          hn[p] = V2(ta.h, tb.h);
-          qn[p] = V2(nq[p].lo() / nr[p].lo(), nq[p].hi() / nr[p].hi());
+          Mst2<FT> m;
+          hn[p] = thermo2m(P, nr[p], nre[p], nq[p], K, phi, m).h;
+          qn[p] = div2(nq[p], nr[p]);
         } else {
           const V2 etot = nre[p] * rcpn2(nr[p]);
           const V2 T = max2(P.T_min_sgs, fma2(((etot - K) - phi) + P.RT0, V2(P.icv), V2(P.T_0)));

@@ -8,7 +8,7 @@
 #include "kernels_row.cuh"
 #include "pair.cuh"
 #include "thermo2.cuh"
-#include "moist.cuh"
+#include "moist2.cuh"
 
 namespace b200 {
 
@@ -118,7 +118,7 @@ __device__ __forceinline__ void sgetq(const FT* s, P2<FT> (&a)[2], int j, int v)
 // kernel (:293-306); viscous sponge on the total water: the aggregate tendency also enters ρ, its enthalpy flux ρe_tot
 // (viscous_sponge.jl:158-199; the ρq_tot part itself is written by k5_tracer_a).  The dry instantiations are unchanged.
 template <class FT, int NVC, bool MOIST = false>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 && !MOIST ? 2 : 1))
+__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
 k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
          const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H, FT* __restrict__ Hw = nullptr) {
   using V = P2<FT>;
@@ -161,14 +161,11 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       u3c[p] = (u3[p] + u3h[p]) * FT(0.5);
       Pt2<FT> t;
       if constexpr (MOIST) {
-        Mst<FT> m0, m1;
-        const Pt<FT> ta = thermo_m(P, rho[p].lo(), re[p].lo(), rq[p].lo(), K[p].lo(), L.phi, m0);
-        const Pt<FT> tb = thermo_m(P, rho[p].hi(), re[p].hi(), rq[p].hi(), K[p].hi(), L.phi, m1);
-        t = pack_pt(ta, tb);
-        qs[p] = V(rq[p].lo() / rho[p].lo(), rq[p].hi() / rho[p].hi());
-        const FT Tra = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * pow7(ta.Pi), Trb = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * pow7(tb.Pi);
-        qe[p] = qs[p] - V(q_tot_r(P, ta.p, Tra), q_tot_r(P, tb.p, Trb));
-        hw[p] = V(h_eff_plus_phi(P, m0, L.phi), h_eff_plus_phi(P, m1, L.phi));
+        Mst2<FT> m;
+        t = thermo2m(P, rho[p], re[p], rq[p], K[p], L.phi, m);
+        qs[p] = div2(rq[p], rho[p]);
+        qe[p] = qs[p] - q_tot_r2(P, t);
+        hw[p] = h_eff_plus_phi2(P, m, L.phi);
       } else {
         t = thermo2(P, rho[p], re[p], K[p], L.phi);
       }

@@ -22,7 +22,8 @@ struct Mst {
 };
 
 template <class FT> __device__ __forceinline__ FT gas_constant_air(const Par<FT>& P, FT qt, FT ql, FT qi) {
-  return P.R_d * (FT(1) - qt) + P.M.R_v * (qt - ql - qi);
+  // = R_d (1 − q_t) + R_v q_v, summed around the exact constant R_d (small terms first: one final rounding in Float32)
+  return P.R_d + ((P.M.R_v - P.R_d) * qt - P.M.R_v * (ql + qi));
 }
 template <class FT> __device__ __forceinline__ FT cv_m(const Par<FT>& P, FT qt, FT ql, FT qi) {
   return P.cv_d + (P.M.cv_v - P.cv_d) * qt + (P.M.cp_l - P.M.cv_v) * ql + (P.M.cp_i - P.M.cv_v) * qi;
@@ -118,13 +119,15 @@ __device__ __forceinline__ Pt<FT> thermo_m(const Par<FT>& P, FT rho, FT rhoe, FT
   m = saturation_adjustment(P, rho, eint, fmax_(FT(0), rhoq / rho));
   o.T = m.T;
   o.h = etot + m.Rm * o.T;  // TD.total_enthalpy = e_tot + R_m T
-  o.p = rho * m.Rm * o.T;
+  // virtual temperature T_v = T R_m/R_d = T + T·((R_v/R_d − 1) q_t − (R_v/R_d) q_c): p = ρ R_d T_v and θ_v = T_v/Π share it
+  const FT epsv = P.M.R_v / P.R_d;
+  const FT Tv = fma_(o.T, (epsv - FT(1)) * m.qt - epsv * (m.ql + m.qi), o.T);
+  o.p = (rho * P.R_d) * Tv;
   const FT lnPi = P.kappa * log_(o.p * P.ip0);  // TD.exner_given_pressure: the dry exponent R_d/cp_d
   o.Pi = exp_(lnPi);
   o.lnPi = lnPi;
   const FT Pi7 = pow7(o.Pi);
   const FT Tr = P.Tmin_ref + (P.Ts_ref - P.Tmin_ref) * Pi7;
-  const FT Tv = o.T * m.Rm / P.R_d;  // θ_v = T R_m / (Π R_d)
   o.thv = Tv / o.Pi;
   o.thp = (Tv - Tr) / o.Pi;
   o.phir = -P.cp_d * (P.Tmin_ref * lnPi + P.dTs7 * (Pi7 - FT(1)));

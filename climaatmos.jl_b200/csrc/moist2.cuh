@@ -1,0 +1,103 @@
+// moist2.cuh — packed (two-lane) moist thermodynamic state for the k5_* kernels (microphysics_model 0M).
+// The common path — unsaturated air — is evaluated on f32x2 pairs like thermo2 (FFMA2 algebra, packed log/exp, MUFU reciprocals):
+// the all-vapour temperature, q_vs(T, ρ) for the saturation test, then p, Π, θ_v and the reference-state quantities.  A lane that is
+// saturated takes the scalar Newton iteration of moist.cuh (rare, data-dependent).  Same formulas as thermo_m / the oracle; the
+// Rankine–Kirchhoff exponents A = Δcp/R_v and B = (L_0 − Δcp T_0)/R_v are linear in the liquid fraction and come precomputed
+// (MPar: A_liq, A_ice, B_liq, B_ice).  Float64 instantiates the same code on the two-member struct (libm log/exp, IEEE division).
+#pragma once
+#include "moist.cuh"
+#include "thermo2.cuh"
+
+namespace b200 {
+
+template <class FT>
+struct Mst2 {
+  P2<FT> T, qt /* q_tot_nonneg */, ql, qi, Rm, cvm;
+};
+
+template <class FT> __device__ __forceinline__ P2<FT> div2(P2<FT> a, P2<FT> b) { return a * rcpn2(b); }
+
+// ln p_vs(T) on pairs for a given liquid fraction pair
+template <class FT>
+__device__ __forceinline__ P2<FT> ln_pvs2(const Par<FT>& P, P2<FT> T, P2<FT> lam) {
+  using V = P2<FT>;
+  const V A = fma2(lam, V(P.M.A_liq - P.M.A_ice), V(P.M.A_ice)), B = fma2(lam, V(P.M.B_liq - P.M.B_ice), V(P.M.B_ice));
+  return fma2(B, V(P.M.iT_tr) - rcpn2(T), fma2(A, logp(T * P.M.iT_tr), V(P.M.ln_ptr)));
+}
+template <class FT>
+__device__ __forceinline__ P2<FT> liquid_fraction2(const Par<FT>& P, P2<FT> T) {
+  FT d0, d1;
+  return P2<FT>(liquid_fraction(P, T.lo(), d0), liquid_fraction(P, T.hi(), d1));
+}
+
+// thermodynamic state of a pair of points from (ρ, ρe_tot, ρq_tot, K, Φ): Pt2 as thermo2, the moist extras in m
+template <class FT>
+__device__ __forceinline__ Pt2<FT> thermo2m(const Par<FT>& P, P2<FT> rho, P2<FT> rhoe, P2<FT> rhoq, P2<FT> K, FT Phi, Mst2<FT>& m) {
+  using V = P2<FT>;
+  Pt2<FT> o;
+  const V irho = rcpn2(rho);
+  const V etot = rhoe * irho;
+  const V eint = (etot - K) - Phi;
+  const V qt = max2(FT(0), rhoq * irho);
+  // all-vapour temperature T_1 = T_0 + (e_int − q_t e_v0 + (1 − q_t) R_d T_0)/cv_m(q_t)
+  const V cvu = fma2(qt, V(P.M.cv_v - P.cv_d), V(P.cv_d));
+  const V num = (eint - qt * P.M.e_v0) + (V(FT(1)) - qt) * P.RT0;
+  V T = fma2(num, rcpn2(cvu), V(P.T_0));
+  V ql(FT(0)), qi(FT(0));
+  {  // saturated?  q_t > q_vs(T_1, ρ) with the liquid fraction of T_1
+    const V qvs = expp(ln_pvs2(P, T, liquid_fraction2(P, T))) * rcpn2((rho * P.M.R_v) * T);
+    const bool s0 = qt.lo() > qvs.lo(), s1 = qt.hi() > qvs.hi();
+    if (s0 || s1) {  // Newton iteration per saturated lane (moist.cuh)
+      FT t0 = T.lo(), t1 = T.hi(), l0 = FT(0), l1 = FT(0), i0 = FT(0), i1 = FT(0);
+      if (s0) { const Mst<FT> a = saturation_adjustment(P, rho.lo(), eint.lo(), qt.lo()); t0 = a.T; l0 = a.ql; i0 = a.qi; }
+      if (s1) { const Mst<FT> a = saturation_adjustment(P, rho.hi(), eint.hi(), qt.hi()); t1 = a.T; l1 = a.ql; i1 = a.qi; }
+      T = V(t0, t1); ql = V(l0, l1); qi = V(i0, i1);
+    }
+  }
+  const V qc = ql + qi;
+  m.T = T; m.qt = qt; m.ql = ql; m.qi = qi;
+  m.Rm = V(P.R_d) + (qt * (P.M.R_v - P.R_d) - qc * P.M.R_v);
+  m.cvm = fma2(qi, V(P.M.cp_i - P.M.cv_v), fma2(ql, V(P.M.cp_l - P.M.cv_v), cvu));
+  o.T = T;
+  o.h = fma2(m.Rm, T, etot);  // TD.total_enthalpy = e_tot + R_m T
+  const V Tv = fma2(T, qt * (P.M.epsv - FT(1)) - qc * P.M.epsv, T);  // T R_m/R_d
+  o.p = (rho * P.R_d) * Tv;
+  o.lnPi = logp(o.p * P.ip0) * P.kappa;
+  o.Pi = expp(o.lnPi);
+  const V rPi = rcpn2(o.Pi);
+  const V x2 = o.Pi * o.Pi, x4 = x2 * x2;
+  const V Pi7 = (x4 * x2) * o.Pi;
+  const V Tr = fma2(Pi7, V(P.Ts_ref - P.Tmin_ref), V(P.Tmin_ref));
+  o.thv = Tv * rPi;
+  o.thp = (Tv - Tr) * rPi;
+  o.phir = fma2(o.lnPi, V(P.Tmin_ref), (Pi7 - FT(1)) * P.dTs7) * (-P.cp_d);
+  o.sdr = fma2(Tr - P.T_0, V(P.cp_d), o.phir);
+  return o;
+}
+// T_r(p) of a state returned by thermo2m
+template <class FT> __device__ __forceinline__ P2<FT> t_ref2(const Par<FT>& P, const Pt2<FT>& t) {
+  const P2<FT> x2 = t.Pi * t.Pi, x4 = x2 * x2;
+  return fma2((x4 * x2) * t.Pi, P2<FT>(P.Ts_ref - P.Tmin_ref), P2<FT>(P.Tmin_ref));
+}
+// q_tot_r(p) = ½ q_sat(T_r, ρ_r = p/(R_d T_r)) over liquid = ½ p_vs,liq(T_r) R_d/(R_v p), zero below 250 hPa
+template <class FT> __device__ __forceinline__ P2<FT> q_tot_r2(const Par<FT>& P, const Pt2<FT>& t) {
+  using V = P2<FT>;
+  const V q = (expp(ln_pvs2(P, t_ref2(P, t), V(FT(1)))) * (FT(0.5) / P.M.epsv)) * rcpn2(t.p);
+  return V(t.p.lo() < FT(25000) ? FT(0) : q.lo(), t.p.hi() < FT(25000) ? FT(0) : q.hi());
+}
+// ᶜh_eff_plus_Φ!
+template <class FT> __device__ __forceinline__ P2<FT> h_eff_plus_phi2(const Par<FT>& P, const Mst2<FT>& m, FT Phi) {
+  using V = P2<FT>;
+  const V qv = max2(FT(0), m.qt - m.ql - m.qi), ql = max2(FT(0), m.ql), qi = max2(FT(0), m.qi);
+  const V dT = m.T - P.T_0;
+  const V num = fma2(fma2(dT, V(P.M.cp_i), V(-P.M.e_i0)), qi, fma2(dT * P.M.cp_l, ql, fma2(dT, V(P.M.cp_v), V(P.M.LH_v0)) * qv));
+  return num * rcpn2(max2(eps_<FT>(), (qv + ql) + qi)) + Phi;
+}
+// ∂p/∂ρq_tot at constant ρ, ρe_tot with κ_m = R_m/cv_m (also returned)
+template <class FT> __device__ __forceinline__ P2<FT> dp_drhoq2(const Par<FT>& P, const Mst2<FT>& m, P2<FT>& kap) {
+  using V = P2<FT>;
+  kap = m.Rm * rcpn2(m.cvm);
+  return fma2(kap, V(-P.M.e_v0 - P.RT0) - (m.T - P.T_0) * (P.M.cv_v - P.cv_d), m.T * (P.M.R_v - P.R_d));
+}
+
+}  // namespace b200

@@ -20,4 +20,8 @@ static void emu_apply_moist(P_& P, double T_0) {
   P.M.R_v = m[0]; P.M.cv_v = m[1] - m[0]; P.M.cp_v = m[1]; P.M.cp_l = m[2]; P.M.cp_i = m[3]; P.M.LH_v0 = m[4]; P.M.LH_s0 = m[5];
   P.M.e_v0 = m[4] - m[0] * T_0; P.M.e_i0 = m[5] - m[4]; P.M.T_tr = m[6]; P.M.ln_ptr = std::log(m[7]); P.M.T_frz = m[8]; P.M.T_icn = m[9];
   P.M.pow_icn = m[10];
+  const double R_d = P.R_d;
+  P.M.A_liq = (m[1] - m[2]) / m[0]; P.M.A_ice = (m[1] - m[3]) / m[0];
+  P.M.B_liq = (m[4] - (m[1] - m[2]) * T_0) / m[0]; P.M.B_ice = (m[5] - (m[1] - m[3]) * T_0) / m[0];
+  P.M.iT_tr = 1.0 / m[6]; P.M.epsv = m[0] / R_d;
 }
