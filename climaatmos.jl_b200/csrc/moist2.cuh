@@ -1,7 +1,8 @@
 // moist2.cuh — packed (two-lane) moist thermodynamic state for the k5_* kernels (microphysics_model 0M).
 // The common path — unsaturated air — is evaluated on f32x2 pairs like thermo2 (FFMA2 algebra, packed log/exp, MUFU reciprocals):
-// the all-vapour temperature, q_vs(T, ρ) for the saturation test, then p, Π, θ_v and the reference-state quantities.  A lane that is
-// saturated takes the scalar Newton iteration of moist.cuh (rare, data-dependent).  Same formulas as thermo_m / the oracle; the
+// the all-vapour temperature, q_vs(T, ρ) for the saturation test, then p, Π, θ_v and the reference-state quantities.  Pairs with a
+// saturated lane run the Newton iteration of the saturation adjustment, also packed (saturation_adjustment2; in the baroclinic-wave
+// setups every column is ice-saturated near its very cold top, so about half of the warps take it).  Same formulas as thermo_m / the oracle; the
 // Rankine–Kirchhoff exponents A = Δcp/R_v and B = (L_0 − Δcp T_0)/R_v are linear in the liquid fraction and come precomputed
 // (MPar: A_liq, A_ice, B_liq, B_ice).  Float64 instantiates the same code on the two-member struct (libm log/exp, IEEE division).
 #pragma once
@@ -30,6 +31,59 @@ __device__ __forceinline__ P2<FT> liquid_fraction2(const Par<FT>& P, P2<FT> T) {
   return P2<FT>(liquid_fraction(P, T.lo(), d0), liquid_fraction(P, T.hi(), d1));
 }
 
+// Saturation adjustment on a pair: the Newton iteration of moist.cuh (same residual, derivative, safeguard and stopping rule) in packed
+// arithmetic, both lanes at once; lanes that are unsaturated (sat = false) or finished keep their value.  d/dT ln p_vs at fixed λ is
+// A/T + B/T² with the precomputed exponents.  Returns T; ql, qi are the equilibrium partition at the returned T.
+template <class FT>
+__device__ __forceinline__ P2<FT> saturation_adjustment2(const Par<FT>& P, P2<FT> rho, P2<FT> eint, P2<FT> qt, P2<FT> cvu, P2<FT> T1, bool s0, bool s1,
+                                                         P2<FT>& ql, P2<FT>& qi) {
+  using V = P2<FT>;
+  V T = T1, Tlo = T1;
+  const FT tol = FT(8) * eps_<FT>();
+  const V irvr = rcpn2(rho * P.M.R_v);
+  const V base = (qt * P.M.e_v0 - (V(FT(1)) - qt) * P.RT0) - eint;  // the T-independent part of the residual
+  bool a0 = s0, a1 = s1;
+  for (int it = 0; it < 40 && (a0 || a1); ++it) {
+    FT d0, d1;
+    const V lam(liquid_fraction(P, T.lo(), d0), liquid_fraction(P, T.hi(), d1)), dlam(d0, d1);
+    const V A = fma2(lam, V(P.M.A_liq - P.M.A_ice), V(P.M.A_ice)), B = fma2(lam, V(P.M.B_liq - P.M.B_ice), V(P.M.B_ice));
+    const V rT = rcpn2(T), lt = logp(T * P.M.iT_tr), dr = V(P.M.iT_tr) - rT;
+    const V qvs = expp(fma2(B, dr, fma2(A, lt, V(P.M.ln_ptr)))) * (irvr * rT);
+    const V dlnp = fma2(dlam, fma2(dr, V(P.M.B_liq - P.M.B_ice), lt * (P.M.A_liq - P.M.A_ice)), fma2(A, T, B) * (rT * rT));
+    const bool on0 = qt.lo() > qvs.lo(), on1 = qt.hi() > qvs.hi();
+    const V d = qt - qvs, qc(on0 ? d.lo() : FT(0), on1 ? d.hi() : FT(0));
+    const V dqc = -(qvs * (dlnp - rT));
+    const V l = lam * qc, i = qc - l;
+    const V dl = fma2(lam, dqc, dlam * qc), di = dqc - dl;
+    const V cvm = fma2(i, V(P.M.cp_i - P.M.cv_v), fma2(l, V(P.M.cp_l - P.M.cv_v), cvu));
+    const V dT = T - P.T_0;
+    const V f = fma2(cvm, dT, base) - fma2(i, V(P.M.e_i0), qc * P.M.e_v0);
+    const V df = fma2(dT, fma2(di, V(P.M.cp_i - P.M.cv_v), dl * (P.M.cp_l - P.M.cv_v)), cvm) - fma2(di, V(P.M.e_i0), dqc * P.M.e_v0);
+    const V nw = T - f * rcpn2(df), bs = (Tlo + T) * FT(0.5);
+    FT t0 = T.lo(), t1 = T.hi(), lo0 = Tlo.lo(), lo1 = Tlo.hi();
+    if (a0) {
+      if (on0 && f.lo() < FT(0)) lo0 = t0;
+      const FT tn = on0 ? nw.lo() : bs.lo();
+      a0 = !(on0 && abs_(tn - t0) <= tol * t0);
+      t0 = tn;
+    }
+    if (a1) {
+      if (on1 && f.hi() < FT(0)) lo1 = t1;
+      const FT tn = on1 ? nw.hi() : bs.hi();
+      a1 = !(on1 && abs_(tn - t1) <= tol * t1);
+      t1 = tn;
+    }
+    T = V(t0, t1); Tlo = V(lo0, lo1);
+  }
+  // equilibrium partition at the converged temperature (saturated lanes only)
+  FT d0, d1;
+  const V lam(liquid_fraction(P, T.lo(), d0), liquid_fraction(P, T.hi(), d1));
+  const V qvs = expp(ln_pvs2(P, T, lam)) * (irvr * rcpn2(T));
+  const V d = qt - qvs, qc(s0 ? fmax_(FT(0), d.lo()) : FT(0), s1 ? fmax_(FT(0), d.hi()) : FT(0));
+  ql = lam * qc; qi = qc - ql;
+  return T;
+}
+
 // thermodynamic state of a pair of points from (ρ, ρe_tot, ρq_tot, K, Φ): Pt2 as thermo2, the moist extras in m
 template <class FT>
 __device__ __forceinline__ Pt2<FT> thermo2m(const Par<FT>& P, P2<FT> rho, P2<FT> rhoe, P2<FT> rhoq, P2<FT> K, FT Phi, Mst2<FT>& m) {
@@ -47,12 +101,7 @@ __device__ __forceinline__ Pt2<FT> thermo2m(const Par<FT>& P, P2<FT> rho, P2<FT>
   {  // saturated?  q_t > q_vs(T_1, ρ) with the liquid fraction of T_1
     const V qvs = expp(ln_pvs2(P, T, liquid_fraction2(P, T))) * rcpn2((rho * P.M.R_v) * T);
     const bool s0 = qt.lo() > qvs.lo(), s1 = qt.hi() > qvs.hi();
-    if (s0 || s1) {  // Newton iteration per saturated lane (moist.cuh)
-      FT t0 = T.lo(), t1 = T.hi(), l0 = FT(0), l1 = FT(0), i0 = FT(0), i1 = FT(0);
-      if (s0) { const Mst<FT> a = saturation_adjustment(P, rho.lo(), eint.lo(), qt.lo()); t0 = a.T; l0 = a.ql; i0 = a.qi; }
-      if (s1) { const Mst<FT> a = saturation_adjustment(P, rho.hi(), eint.hi(), qt.hi()); t1 = a.T; l1 = a.ql; i1 = a.qi; }
-      T = V(t0, t1); ql = V(l0, l1); qi = V(i0, i1);
-    }
+    if (s0 || s1) T = saturation_adjustment2(P, rho, eint, qt, cvu, T, s0, s1, ql, qi);
   }
   const V qc = ql + qi;
   m.T = T; m.qt = qt; m.ql = ql; m.qi = qi;

@@ -9,7 +9,7 @@ P = prm.DycoreParams(zd_rayleigh=40000.0, zd_viscous=40000.0)
 MOIST = bool(os.environ.get("MOIST"))  # MOIST=1: the 0M-moist configuration (BASELINE.json configs[2])
 sim = dycore.AtmosSimulation(FT=np.float32, h_elem=he, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=90.0 * 30 / he,
                              rayleigh_sponge=True, viscous_sponge=True, params=P,
-                             **(dict(microphysics_model="0M", initial_condition="MoistBaroclinicWave") if MOIST else {}))
+                             **(dict(microphysics_model="0M", initial_condition="MoistBaroclinicWave", q_0=float(os.environ.get("Q0", "0.018"))) if MOIST else {}))
 for _ in range(3):
     sim.step(True)
 Y = sim.Y
