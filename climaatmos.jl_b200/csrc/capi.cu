@@ -260,6 +260,7 @@ static Par<FT> make_par(const b200_ctx* c) {
     P.M.A_liq = (FT)((p.cp_v - p.cp_l) / p.R_v); P.M.A_ice = (FT)((p.cp_v - p.cp_i) / p.R_v);
     P.M.B_liq = (FT)((p.LH_v0 - (p.cp_v - p.cp_l) * p.T_0) / p.R_v); P.M.B_ice = (FT)((p.LH_s0 - (p.cp_v - p.cp_i) * p.T_0) / p.R_v);
     P.M.iT_tr = (FT)(1.0 / p.T_triple); P.M.epsv = (FT)(p.R_v / p.R_d);
+    P.M.q_neg = (FT)(0.25 * (sizeof(FT) == 4 ? 1.1920929e-07 : 2.220446049250313e-16) * p.cv_d / p.LH_s0);
   }
   return P;
 }

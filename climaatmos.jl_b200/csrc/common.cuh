@@ -56,6 +56,7 @@ struct MPar {
   FT R_v, cv_v, cp_v, cp_l, cp_i, LH_v0, LH_s0, e_v0 /* L_v0 − R_v T_0 */, e_i0 /* L_f0 */, T_tr, ln_ptr /* ln p_triple */, T_frz, T_icn, pow_icn;
   // derived (host, double precision): Rankine–Kirchhoff exponents A = Δcp/R_v, B = (L_0 − Δcp T_0)/R_v over liquid / ice, 1/T_triple, R_v/R_d
   FT A_liq, A_ice, B_liq, B_ice, iT_tr, epsv;
+  FT q_neg;  // ¼ ulp · cv_d / L_s0: below q_t = q_neg·T condensation cannot change T in this precision (moist2.cuh)
 };
 
 template <class FT>

@@ -99,9 +99,19 @@ __device__ __forceinline__ Pt2<FT> thermo2m(const Par<FT>& P, P2<FT> rho, P2<FT>
   V T = fma2(num, rcpn2(cvu), V(P.T_0));
   V ql(FT(0)), qi(FT(0));
   {  // saturated?  q_t > q_vs(T_1, ρ) with the liquid fraction of T_1
-    const V qvs = expp(ln_pvs2(P, T, liquid_fraction2(P, T))) * rcpn2((rho * P.M.R_v) * T);
+    const V lam1 = liquid_fraction2(P, T);
+    const V qvs = expp(ln_pvs2(P, T, lam1)) * rcpn2((rho * P.M.R_v) * T);
     const bool s0 = qt.lo() > qvs.lo(), s1 = qt.hi() > qvs.hi();
-    if (s0 || s1) T = saturation_adjustment2(P, rho, eint, qt, cvu, T, s0, s1, ql, qi);
+    if (s0 || s1) {
+      // Newton only where the latent heating can move T in this precision: q_t L_s/cv_d ≥ ¼ ulp(T).  Below that (the ice-saturated,
+      // very cold and dry top of the baroclinic-wave columns: q_t = 1e-12) T_1 IS the adjusted temperature and the condensate is
+      // the excess at T_1.  In Float64 the threshold is q_t ≈ 1e-20: never taken.
+      const bool g0 = s0 && qt.lo() >= P.M.q_neg * T.lo(), g1 = s1 && qt.hi() >= P.M.q_neg * T.hi();
+      const V d = qt - qvs, qc1((s0 && !g0) ? d.lo() : FT(0), (s1 && !g1) ? d.hi() : FT(0));
+      V l(FT(0)), i(FT(0));
+      if (g0 || g1) T = saturation_adjustment2(P, rho, eint, qt, cvu, T, g0, g1, l, i);
+      ql = fma2(lam1, qc1, l); qi = i + (qc1 - lam1 * qc1);
+    }
   }
   const V qc = ql + qi;
   m.T = T; m.qt = qt; m.ql = ql; m.qi = qi;

@@ -24,4 +24,5 @@ static void emu_apply_moist(P_& P, double T_0) {
   P.M.A_liq = (m[1] - m[2]) / m[0]; P.M.A_ice = (m[1] - m[3]) / m[0];
   P.M.B_liq = (m[4] - (m[1] - m[2]) * T_0) / m[0]; P.M.B_ice = (m[5] - (m[1] - m[3]) * T_0) / m[0];
   P.M.iT_tr = 1.0 / m[6]; P.M.epsv = m[0] / R_d;
+  P.M.q_neg = 0.25 * 2.220446049250313e-16 * P.cv_d / m[5];
 }
