@@ -19,6 +19,7 @@ inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 // the inline PTX statements of common.cuh assemble to nothing
 __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
 #include "kernels_imp5.cuh"
+#include "kernels_imp5d.cuh"
 
 using namespace b200;
 typedef double FT;
@@ -75,5 +76,25 @@ extern "C" __attribute__((visibility("default"))) int emu_ldiv5(int nh, int nv, 
   emu_apply_moist(P, sc[3]);
   if (g_moist_on) run_grid(nh, [&] { k5_imp_stage<FT, 0, true, true>(P, hgeo, &V, Yc, Yf, dYc, dYf, (FT)sc[10], Rc, Rf); });
   else run_grid(nh, [&] { k5_imp_stage<FT, 0, true>(P, hgeo, &V, Yc, Yf, dYc, dYf, (FT)sc[10], Rc, Rf); });
+  return 0;
+}
+
+// k5_imp_stage_diff (kernels_imp5d.cuh): the fused implicit stage with implicit vertical diffusion in the packed row layout.
+// sc as emu_imp5 plus sc[13] = diffusion mode (1 | 2), sc[14] = momentum diffusion, sc[15] = n_iters, sc[16] = C_E·Δz₁/2; kdec [64]
+extern "C" __attribute__((visibility("default"))) int emu_imp5d(int nh, int nv, const double* sc, const double* vl, const double* hgeo, const double* kdec,
+                                                                const double* Uc, const double* Uf, double* Nc, double* Nf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = (int)sc[12]; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[11];
+  VDiff<FT> D;
+  D.mode = (int)sc[13]; D.momentum = (int)sc[14]; D.n_iters = (int)sc[15]; D.ce_za = sc[16]; D.eps = 2.220446049250313e-16; D.cpcv = sc[1] / sc[2];
+  D.kdec = kdec;
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  run_grid(nh, [&] { k5_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
   return 0;
 }

@@ -230,7 +230,7 @@ def test_emulated_vdiff_kernels_at_the_column_height_limits(emu, ze, dzb):
     ("DecayWithHeightDiffusion", True, False, 2, 1, "vanleer_limiter", True, 63, 30.0),
     ("DecayWithHeightDiffusion", True, False, 0, 1, "vanleer_limiter", False, 2, 15000.0),
 ])
-def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, dm, iters, ntr, upw, rayleigh, ze, dzb):
+def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, emu5, vd, deep, dm, iters, ntr, upw, rayleigh, ze, dzb):
     """k_imp_stage_diff: cache_imp! → Wfact → T_imp! → ldiv! (approximate arrowhead iteration) → U −= ΔU → cache_imp! →
     T_post_imp! with implicit vertical diffusion in ONE kernel, against the oracle's hook sequence (Float64).  The input state has
     non-zero u₃ on the boundary faces: the kernel must treat them as zero like cache_imp!."""
@@ -274,6 +274,15 @@ def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, vd, deep, d
         assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
         assert rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8 or np.abs(Uc[:, k] - Yc[:, k]).max() == 0, ("increment", k)
     assert rel(Nf, Uf) < 1e-10
+    # the packed-row-layout version of the same stage (k5_imp_stage_diff, kernels_imp5d.cuh: what b200_implicit_stage launches)
+    sc5 = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), dtg,
+                    {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[upw], ncf, mode, 0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2])
+    N5c, N5f = np.zeros_like(Yc), np.zeros_like(Yf)
+    assert emu5.emu_imp5d(nh, nv, p(sc5), p(vl), p(hgeo), p(kdec), p(Yc), p(Yf), p(N5c), p(N5f)) == 0
+    for k in range(ncf):
+        assert rel(N5c[:, k], Uc[:, k]) < 1e-12, ("k5_imp_stage_diff", k, rel(N5c[:, k], Uc[:, k]))
+        assert rel(N5c[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8 or np.abs(Uc[:, k] - Yc[:, k]).max() == 0, ("k5 increment", k, rel(N5c[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]))
+    assert rel(N5f, Uf) < 1e-10, ("k5 u3", rel(N5f, Uf))
 
 
 @pytest.mark.parametrize("vd,upw", [("DecayWithHeightDiffusion", "vanleer_limiter"), ("VerticalDiffusion", "first_order")])
