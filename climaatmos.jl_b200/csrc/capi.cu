@@ -22,6 +22,7 @@
 #include "kernels_limiter.cuh"
 #include "kernels_vdiff.cuh"
 #include "kernels_imp5d.cuh"
+#include "kernels_imp8.cuh"
 
 using namespace b200;
 
@@ -142,6 +143,7 @@ struct b200_ctx {
   int pdl = 63;       // B200_PDL=<bit mask>: programmatic dependent launch per kernel group (1 exp_a, 2 exp_c, 4 dss2, 8 axpy, 16 imp, 32 diff); 0 = off
   int zform = 1;       // B200_ZFORM=0: the fused stepper forms T_imp[j] = (N_j − U_j)/dtγ (side stream) instead of using the stage solutions
   void *Nsc[4] = {nullptr, nullptr, nullptr, nullptr}, *Nsf[4] = {nullptr, nullptr, nullptr, nullptr};  // stage solutions N_j (zform)
+  int imp_kernel = 8;  // B200_IMP_KERNEL=5: the shared-memory slab version k5_imp_stage (A/B runs; LDIV and moist contexts always use it)
   int stiff_final = 1; // B200_STIFF_FINAL=0: literal final increment u + dt Σ b_j (T_exp[j] + T_imp[j]) in the fused path too
   int fuse_axdss = 1; // B200_FUSE_AXDSS=0: stage increment and state DSS as two passes (k_axpy_n, k_dss2) instead of k_axpy_dss
   struct StepGraph { cudaGraphExec_t exec; void *Yc, *Yf; int64_t launches; };
@@ -466,6 +468,7 @@ static int create_body(b200_ctx* c, const b200_dims* d, const b200_geometry* G, 
   if (const char* e = getenv("B200_GRAPH")) c->use_graph = atoi(e);
   if (const char* e = getenv("B200_PDL")) c->pdl = atoi(e);
   if (const char* e = getenv("B200_STIFF_FINAL")) c->stiff_final = atoi(e);
+  if (const char* e = getenv("B200_IMP_KERNEL")) c->imp_kernel = atoi(e);
   if (const char* e = getenv("B200_ZFORM")) c->zform = atoi(e);
   if (const char* e = getenv("B200_FUSE_AXDSS")) c->fuse_axdss = atoi(e);
   if (const char* e = getenv("B200_GENERIC_NV")) c->generic_nv = atoi(e);
@@ -1310,6 +1313,12 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
   else if (c->prm.microphysics_0M)
     launchx(c->pdl & 16, k5_imp_stage<FT, 0, false, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
             (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
+  else if (c->imp_kernel == 8 && c->dims.nv == 63 && !c->generic_nv)  // warp per column pair: no shared memory, shuffle PCR (kernels_imp8.cuh)
+    launchx(c->pdl & 16, k8_imp_stage<FT, 63>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+  else if (c->imp_kernel == 8)
+    launchx(c->pdl & 16, k8_imp_stage<FT, 0>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
   else if (c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k5_imp_stage<FT, 63>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
             (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);

@@ -1,0 +1,235 @@
+// kernels_imp8.cuh — fused implicit stage, fourth generation: a WARP PER COLUMN PAIR, no shared memory, no block barriers.
+//
+// Same arithmetic as k5_imp_stage (kernels_imp5.cuh; cache_imp! → Wfact → T_imp! residual → ldiv! → U −= ΔU → cache_imp! → T_post_imp!;
+// implicit_tendency.jl:36-98,185-339, manual_sparse_jacobian.jl:713-870,504-585).  Layout: one element per CTA of 8 warps; warp w owns
+// the columns (nodes) 2w and 2w+1 as ONE f32x2 pair, lane k owns the two consecutive levels 2k and 2k+1 of that pair — so a column of
+// 64 faces is exactly one warp.  Consequences on B200:
+//   * vertical neighbours are registers of the same thread (level 2k ↔ 2k+1) or one shuffle from the adjacent lane: the 13 pair slabs
+//     (54 KB) and the 12 block barriers of k5_imp_stage are gone;
+//   * the Schur tridiagonal systems are solved inside the warp: one cyclic-reduction step eliminates the odd rows thread-locally (one
+//     shuffle set), the 32 even rows are reduced by parallel cyclic reduction with shuffles (5 steps), the odd rows follow by
+//     back-substitution — 68 shuffles per solve instead of 108 64-bit shared-memory accesses and 7 barriers;
+//   * pointwise algebra stays packed (FFMA2/FMUL2/FADD2 over the two columns); global accesses are 256-byte contiguous per warp and
+//     field (two 32-bit accesses per thread: node stride 63 words is not 8-byte aligned for odd nodes).
+#pragma once
+#include "kernels_imp5.cuh"
+
+namespace b200 {
+
+template <class FT> __device__ __forceinline__ P2<FT> shup(const P2<FT>& a, int d = 1) {
+  return P2<FT>(__shfl_up_sync(FULLM, a.lo(), d), __shfl_up_sync(FULLM, a.hi(), d));
+}
+template <class FT> __device__ __forceinline__ P2<FT> shdn(const P2<FT>& a, int d = 1) {
+  return P2<FT>(__shfl_down_sync(FULLM, a.lo(), d), __shfl_down_sync(FULLM, a.hi(), d));
+}
+// the thread's two rows of a column-pair field: g points at (node 2w, level 2k); the second column is `nlev` further
+template <class FT>
+__device__ __forceinline__ void ld8(P2<FT> (&a)[2], const FT* __restrict__ g, int nlev, bool ok0, bool ok1, FT dflt) {
+  const FT a00 = ok0 ? g[0] : dflt, a01 = ok0 ? g[nlev] : dflt, a10 = ok1 ? g[1] : dflt, a11 = ok1 ? g[nlev + 1] : dflt;
+  a[0] = P2<FT>(a00, a01); a[1] = P2<FT>(a10, a11);
+}
+template <class FT>
+__device__ __forceinline__ void st8(const P2<FT> (&a)[2], FT* __restrict__ g, int nlev, bool ok0, bool ok1) {
+  if (ok0) { g[0] = a[0].lo(); g[nlev] = a[0].hi(); }
+  if (ok1) { g[1] = a[1].lo(); g[nlev + 1] = a[1].hi(); }
+}
+
+// Tridiagonal solve inside the warp: rows 2k (p = 0) and 2k+1 (p = 1) of lane k, coefficients (l, d, u) and right-hand side y of the
+// thread's column pair.  Rows outside the system must be identity rows (l = u = 0, y = 0); row 0 has l = 0 and the last row u = 0.
+// Returns x[2].  (cyclic reduction of the odd rows + PCR of the 32 even rows + back-substitution)
+template <class FT>
+__device__ __forceinline__ void warp_tridiag(int lane, const P2<FT> (&l)[2], const P2<FT> (&d)[2], const P2<FT> (&u)[2], const P2<FT> (&r)[2],
+                                             P2<FT> (&x)[2]) {
+  using V2 = P2<FT>;
+  V2 a[2], c[2], y[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const V2 rd = rcpn2(d[p]);
+    a[p] = l[p] * rd; c[p] = u[p] * rd; y[p] = r[p] * rd;
+  }
+  // eliminate x[2k−1] (odd row of lane k−1) and x[2k+1] (own odd row) from the even row 2k
+  const V2 a1u = shup(a[1]), c1u = shup(c[1]), y1u = shup(y[1]);  // lane 0: a[0] = 0, so its own values are harmless
+  V2 A, C, Y;
+  {
+    const V2 rd = rcpn2(V2(FT(1)) - fma2(a[0], c1u, c[0] * a[1]));
+    A = -((a[0] * a1u) * rd);
+    C = -((c[0] * c[1]) * rd);
+    Y = (y[0] - fma2(a[0], y1u, c[0] * y[1])) * rd;
+  }
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const bool hm = lane >= s, hp = lane + s < 32;
+    V2 Am = shup(A, s), Cm = shup(C, s), Ym = shup(Y, s), Ap = shdn(A, s), Cp = shdn(C, s), Yp = shdn(Y, s);
+    if (!hm) { Am = V2(FT(0)); Cm = V2(FT(0)); Ym = V2(FT(0)); }
+    if (!hp) { Ap = V2(FT(0)); Cp = V2(FT(0)); Yp = V2(FT(0)); }
+    const V2 rd = rcpn2(V2(FT(1)) - fma2(C, Ap, A * Cm));
+    Y = (Y - fma2(C, Yp, A * Ym)) * rd;
+    A = -((A * Am) * rd);
+    C = -((C * Cp) * rd);
+  }
+  x[0] = Y;
+  const V2 x0d = shdn(Y);  // lane 31: c[1] = 0 (last row)
+  x[1] = y[1] - fma2(a[1], Y, c[1] * x0d);
+}
+
+template <class FT, int NVC>
+__global__ void __launch_bounds__(256, sizeof(FT) == 4 ? 2 : 1)
+k8_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
+             const FT* __restrict__ Yf, FT* __restrict__ Nc, FT* __restrict__ Nf, FT dtg) {
+  using V2 = P2<FT>;
+  pdl_launch();
+  const int e = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, n0 = 2 * w, nv = NVC ? NVC : P.nv, nf = nv + 1;
+  const FT kap = P.R_d / P.cv_d;
+  // per-level constants of the thread's two levels v = 2·lane + p
+  bool cv[2], fv[2], interior[2];
+  FT sc2i[2], phi[2], mc[2], mclo[2], rmc[2], rmclo[2], g33lo[2], g33hi[2], g33m[2], dphif[2], beta[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    cv[p] = v < nv; fv[p] = v < nf; interior[p] = v > 0 && v < nv;
+    const int vm = v > 0 ? v - 1 : 0;
+    const int vc = cv[p] ? v : nv - 1, vmc = vm < nv ? vm : nv - 1, vf = fv[p] ? v : nv, vf1 = v + 1 <= nv ? v + 1 : nv;
+    sc2i[p] = vlev->sc2i[vc]; phi[p] = vlev->phic[vc]; mc[p] = vlev->mc[vc]; mclo[p] = vlev->mc[vmc]; rmc[p] = vlev->rmc[vc];
+    rmclo[p] = vlev->rmc[vmc]; g33lo[p] = vlev->g33f[vf]; g33hi[p] = vlev->g33f[vf1]; g33m[p] = vlev->g33f[vm < nf ? vm : nv];
+    dphif[p] = vlev->dphif[vf]; beta[p] = P.rayleigh ? vlev->brw[vf] : FT(0);
+  }
+  const FT* hgp = hgeo + (size_t)e * HG_N * 16 + n0;
+  const V2 g11 = ldpair(hgp + HG_GI11 * 16), g12 = ldpair(hgp + HG_GI12 * 16), g22 = ldpair(hgp + HG_GI22 * 16);
+  pdl_wait(Yc, Yf, Nc, Nf);
+  const int cs = 16 * nv;
+  const FT* gY = Yc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + 2 * lane);
+  const FT* gYf = Yf + ((size_t)e * 16 * nf + n0 * nf + 2 * lane);
+  FT* gN = Nc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + 2 * lane);
+  FT* gNf = Nf + ((size_t)e * 16 * nf + n0 * nf + 2 * lane);
+  V2 rho[2], u1[2], u2[2], re[2], u3[2];
+  ld8(rho, gY, nv, cv[0], cv[1], FT(1)); ld8(u1, gY + cs, nv, cv[0], cv[1], FT(0)); ld8(u2, gY + 2 * cs, nv, cv[0], cv[1], FT(0));
+  ld8(re, gY + 3 * cs, nv, cv[0], cv[1], FT(0)); ld8(u3, gYf, nf, interior[0], interior[1], FT(0));  // u₃ boundary filter on load
+  // uₕ is copied through (R_uₕ = 0); passive tracers: ΔU = 0
+  st8(u1, gN + cs, nv, cv[0], cv[1]); st8(u2, gN + 2 * cs, nv, cv[0], cv[1]);
+  for (int q = 4; q < P.ncf; ++q) {
+    V2 t[2];
+    ld8(t, gY + q * cs, nv, cv[0], cv[1], FT(0));
+    st8(t, gN + q * cs, nv, cv[0], cv[1]);
+  }
+  // ---- centre thermodynamics and face mass-flux pieces
+  V2 Kh[2], h[2], Pi[2], thv[2], thp[2], phr[2], dp[2], A[2], M[2];
+  const V2 u3d0 = shdn(u3[0]), rhou1 = shup(rho[1]);
+  V2 u3h[2] = {u3[1], u3d0};     // u₃ at face v + 1
+  V2 rlo[2] = {rhou1, rho[0]};   // ρ at centre v − 1
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const V2 c1 = fma2(g12, u2[p], g11 * u1[p]), c2 = fma2(g22, u2[p], g12 * u1[p]);
+    Kh[p] = (fma2(u2[p], c2, u1[p] * c1) * sc2i[p]) * FT(0.5);
+    h[p] = V2(FT(0)); Pi[p] = V2(FT(1)); thv[p] = V2(FT(0)); thp[p] = V2(FT(0)); phr[p] = V2(FT(1)); dp[p] = V2(FT(0));
+    if (cv[p]) {
+      const V2 K = Kh[p] + (u3[p] * (u3[p] * g33lo[p]) + u3h[p] * (u3h[p] * g33hi[p])) * FT(0.25);
+      const Pt2<FT> t = thermo2(P, rho[p], re[p], K, phi[p]);
+      h[p] = t.h; Pi[p] = t.Pi; thv[p] = t.thv; thp[p] = t.thp; phr[p] = pgf_aux2(t);
+      dp[p] = fma2(t.T, V2(P.R_d - kap * P.cv_d), ((V2(P.T_0 * P.cp_d) - K) - phi[p]) * kap);  // ∂p/∂ρ (manual_sparse_jacobian.jl:816-818)
+    }
+    A[p] = M[p] = V2(FT(0));
+    if (interior[p]) {
+      const V2 mr = fma2(rho[p], V2(mc[p]), rlo[p] * mclo[p]) * FT(0.5);
+      A[p] = (mr * dtg) * g33lo[p];
+      M[p] = mr * (u3[p] * g33lo[p]);
+    }
+  }
+  // ---- vertical neighbours: level v − 1 (m1), v − 2 (m2), v + 1 (p1) of the thread's two levels
+  const V2 hu0 = shup(h[0]), hu1 = shup(h[1]), hd0 = shdn(h[0]);
+  const V2 Au1 = shup(A[1]), Ad0 = shdn(A[0]), Mu1 = shup(M[1]), Md0 = shdn(M[0]), u3u1 = shup(u3[1]);
+  const V2 Piu1 = shup(Pi[1]), thvu1 = shup(thv[1]), thpu1 = shup(thp[1]), phru1 = shup(phr[1]), dpu1 = shup(dp[1]);
+  const V2 h_m1[2] = {hu1, h[0]}, h_m2[2] = {hu0, hu1}, h_p1[2] = {h[1], hd0};
+  const V2 A_m1[2] = {Au1, A[0]}, A_p1[2] = {A[1], Ad0}, M_m1[2] = {Mu1, M[0]}, M_p1[2] = {M[1], Md0}, u3_m1[2] = {u3u1, u3[0]};
+  const V2 Pi_m1[2] = {Piu1, Pi[0]}, thv_m1[2] = {thvu1, thv[0]}, thp_m1[2] = {thpu1, thp[0]}, phr_m1[2] = {phru1, phr[0]}, dp_m1[2] = {dpu1, dp[0]};
+  // ---- Schur tridiagonal and right-hand side of face row v (manual_sparse_jacobian.jl:746-868)
+  V2 R0[2], E0[2], a0[2], a1[2], b0[2], b1[2], cl[2], cd[2], cu[2], cr[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    const V2 hl = h_m1[p], hm2 = h_m2[p], hp1 = h_p1[p];
+    const V2 hf0 = v > 0 ? (hl + h[p]) * FT(0.5) : V2(FT(0));
+    const V2 hfp = v < nv - 1 ? (h[p] + hp1) * FT(0.5) : V2(FT(0));
+    const V2 Ap = A_p1[p], Mp = M_p1[p];
+    {
+      const V2 rr = ((Mp - M[p]) * (-dtg)) * rmc[p], rre = ((Mp * hfp - M[p] * hf0) * (-dtg)) * rmc[p];
+      a0[p] = A[p] * rmc[p]; a1[p] = -(Ap * rmc[p]);
+      b0[p] = a0[p] * hf0; b1[p] = a1[p] * hfp;
+      R0[p] = rho[p] + rr; E0[p] = re[p] + rre;
+    }
+    cl[p] = cu[p] = V2(FT(0)); cd[p] = V2(dtg * (-beta[p]) - FT(1)); cr[p] = V2(FT(0));
+    if (interior[p]) {
+      const V2 hfm = v > 1 ? (hm2 + hl) * FT(0.5) : V2(FT(0));
+      const V2 Am = A_m1[p], Mm = M_m1[p], u3m = u3_m1[p];
+      const V2 irf = rcpn2((rlo[p] + rho[p]) * FT(0.5));
+      V2 dPi, dphr;
+      pgf_diff2(P, Pi_m1[p], Pi[p], phr_m1[p], phr[p], dPi, dphr);
+      const V2 buoy = ((((thv_m1[p] + thv[p]) * FT(0.5)) * P.cp_d) * dPi) * irf;
+      const V2 hb = buoy * FT(0.5);
+      const V2 ur_lo = fma2(irf, dp_m1[p], hb) * dtg, ur_hi = (hb - irf * dp[p]) * dtg;
+      const V2 ue_lo = (irf * dtg) * kap, ue_hi = -ue_lo;
+      const V2 x_lo = irf * (rlo[p] * (-kap)), x_hi = -(irf * (rho[p] * (-kap)));
+      const V2 k0 = u3[p] * (FT(0.5) * g33lo[p]);
+      V2 l = (x_lo * (u3m * (FT(0.5) * g33m[p]))) * dtg;
+      V2 d = (fma2(x_hi, k0, x_lo * k0) - beta[p]) * dtg - FT(1);
+      V2 u = (x_hi * (u3h[p] * (FT(0.5) * g33hi[p]))) * dtg;
+      const V2 ru_lo_a = Am * rmclo[p], ru_hi_a = -(A[p] * rmclo[p]), ru_lo_b = a0[p], ru_hi_b = a1[p];
+      l = l + fma2(ue_lo, ru_lo_a * hfm, ur_lo * ru_lo_a);
+      d = d + (fma2(ur_hi, ru_lo_b, ur_lo * ru_hi_a) + fma2(ue_hi, ru_lo_b * hf0, ue_lo * (ru_hi_a * hf0)));
+      u = u + fma2(ue_hi, ru_hi_b * hfp, ur_hi * ru_hi_b);
+      const V2 rr_a = ((M[p] - Mm) * (-dtg)) * rmclo[p], rr_b = ((Mp - M[p]) * (-dtg)) * rmc[p];
+      const V2 Mh0 = M[p] * hf0;
+      const V2 re_a = ((Mh0 - Mm * hfm) * (-dtg)) * rmclo[p], re_b = ((Mp * hfp - Mh0) * (-dtg)) * rmc[p];
+      const V2 tf = -((V2(dphif[p]) - dphr) + (((thp_m1[p] + thp[p]) * FT(0.5)) * P.cp_d) * dPi) - u3[p] * beta[p];
+      cl[p] = l; cd[p] = d; cu[p] = u;
+      cr[p] = fma2(tf, V2(dtg), fma2(ur_lo, rr_a, ur_hi * rr_b) + fma2(ue_lo, re_a, ue_hi * re_b));
+    }
+  }
+  V2 x0[2];
+  warp_tridiag(lane, cl, cd, cu, cr, x0);
+  const V2 x1[2] = {x0[1], shdn(x0[0])};  // ΔU.f.u₃ at face v + 1
+  // ---- U ← U − ΔU (back-substitution of the scalar rows)
+  V2 nr[2], nre[2], nu[2], nu1[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    nr[p] = R0[p] - fma2(a1[p], x1[p], a0[p] * x0[p]);
+    nre[p] = E0[p] - fma2(b1[p], x1[p], b0[p] * x0[p]);
+    nu[p] = interior[p] ? u3[p] - x0[p] : V2(FT(0));
+    nu1[p] = (v + 1 < nv) ? u3h[p] - x1[p] : V2(FT(0));
+  }
+  st8(nr, gN, nv, cv[0], cv[1]);
+  st8(nu, gNf, nf, fv[0], fv[1]);
+  if (P.upwinding != 0) {
+    // ---- h_tot of the updated state (cache_imp! after the Newton update), then the (upwinded − centred) enthalpy flux
+    V2 hn[2], rn[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      hn[p] = V2(FT(0)); rn[p] = cv[p] ? nr[p] : V2(FT(1));
+      if (cv[p]) {
+        const V2 K = Kh[p] + (nu[p] * (nu[p] * g33lo[p]) + nu1[p] * (nu1[p] * g33hi[p])) * FT(0.25);
+        const V2 etot = nre[p] * rcpn2(nr[p]);
+        const V2 T = max2(P.T_min_sgs, fma2(((etot - K) - phi[p]) + P.RT0, V2(P.icv), V2(P.T_0)));
+        hn[p] = fma2(T, V2(P.R_d), etot);
+      }
+    }
+    const V2 hnu0 = shup(hn[0]), hnu1 = shup(hn[1]), hnd0 = shdn(hn[0]), rnu1 = shup(rn[1]);
+    const V2 hn_m1[2] = {hnu1, hn[0]}, hn_m2[2] = {hnu0, hnu1}, hn_p1[2] = {hn[1], hnd0}, rn_m1[2] = {rnu1, rn[0]};
+    V2 flx[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int v = 2 * lane + p;
+      flx[p] = V2(FT(0));
+      if (interior[p]) {
+        const V2 wv = nu[p] * g33lo[p];
+        const V2 mr = fma2(nr[p], V2(mc[p]), rn_m1[p] * mclo[p]) * FT(0.5);
+        flx[p] = (mr * wv) * upw_minus_central2(P, wv, hn_m2[p], hn_m1[p], hn[p], hn_p1[p], v, nv);
+      }
+    }
+    const V2 fp[2] = {flx[1], shdn(flx[0])};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) nre[p] = nre[p] + ((-(fp[p] - flx[p])) * rmc[p]) * dtg;
+  }
+  st8(nre, gN + 3 * cs, nv, cv[0], cv[1]);
+}
+
+}  // namespace b200

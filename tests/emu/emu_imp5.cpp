@@ -11,8 +11,22 @@ std::barrier<>* g_cta_barrier = nullptr;
 namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
 #define __constant__
 #define FULL_MASK_EMU 0xffffffffu
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { __builtin_trap(); return v; }   // only the two-sided Thomas variant shuffles
-template <class T> inline T __shfl_sync(unsigned, T v, int) { __builtin_trap(); return v; }
+// warp shuffles (k8_imp_stage): the 32 host threads of a warp meet at a per-warp barrier, publish their value and read the source lane's
+struct WarpX { std::barrier<> bar{32}; alignas(16) unsigned char buf[32][16]; };
+static WarpX g_warp[8];
+template <class T> inline T shfl_emu(T v, int src_lane) {
+  WarpX& w = g_warp[threadIdx.x >> 5];
+  const int l = threadIdx.x & 31;
+  memcpy(w.buf[l], &v, sizeof(T));
+  w.bar.arrive_and_wait();
+  T r; memcpy(&r, w.buf[src_lane & 31], sizeof(T));
+  w.bar.arrive_and_wait();
+  return r;
+}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return shfl_emu(v, (int)(threadIdx.x & 31) ^ m); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return shfl_emu(v, src); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return shfl_emu(v, l >= d ? l - d : l); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return shfl_emu(v, l + d < 32 ? l + d : l); }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 // griddepcontrol.* (programmatic dependent launch) is a no-op for a single emulated grid: teach the assembler two empty macros so that
@@ -20,6 +34,7 @@ inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
 #include "kernels_imp5.cuh"
 #include "kernels_imp5d.cuh"
+#include "kernels_imp8.cuh"
 
 using namespace b200;
 typedef double FT;
@@ -96,5 +111,21 @@ extern "C" __attribute__((visibility("default"))) int emu_imp5d(int nh, int nv, 
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
   run_grid(nh, [&] { k5_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  return 0;
+}
+
+// k8_imp_stage (kernels_imp8.cuh): the dry fused implicit stage with a warp per column pair (no shared memory, shuffle PCR); sc as emu_imp5
+extern "C" __attribute__((visibility("default"))) int emu_imp8(int nh, int nv, const double* sc, const double* vl, const double* hgeo,
+                                                               const double* Uc, const double* Uf, double* Nc, double* Nf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = (int)sc[12]; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[11];
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  run_grid(nh, [&] { k8_imp_stage<FT, 0>(P, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
   return 0;
 }

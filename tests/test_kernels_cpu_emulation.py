@@ -406,6 +406,13 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
         assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
     assert rel(Nc[:, 0] - Yc[:, 0], Uc[:, 0] - Yc[:, 0]) < 1e-8 and rel(Nc[:, 3] - Yc[:, 3], Uc[:, 3] - Yc[:, 3]) < 1e-8
     assert rel(Nf, Uf) < 1e-10
+    # the warp-per-column-pair version (k8_imp_stage, kernels_imp8.cuh: shuffle neighbours and shuffle PCR, no shared memory)
+    N8c, N8f = np.zeros_like(Yc), np.zeros_like(Yf)
+    assert emu5.emu_imp8(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf), p(N8c), p(N8f)) == 0
+    for k in range(ncf):
+        assert rel(N8c[:, k], Uc[:, k]) < 1e-12, ("k8", k, rel(N8c[:, k], Uc[:, k]))
+    assert rel(N8c[:, 0] - Yc[:, 0], Uc[:, 0] - Yc[:, 0]) < 1e-8 and rel(N8c[:, 3] - Yc[:, 3], Uc[:, 3] - Yc[:, 3]) < 1e-8
+    assert rel(N8f, Uf) < 1e-10, ("k8 u3", rel(N8f, Uf))
     # ldiv! of the hook path = the same kernel in LDIV mode on the state Wfact saw (b200_wfact keeps a snapshot): ΔY = J(Y, dtγ)⁻¹ R for a
     # random right-hand side with ALL components non-zero (R_uₕ ≠ 0 exercises the (u₃, uₕ) blocks, R_ρχ the tracer fallback block)
     Yf0 = Yf.copy()
