@@ -34,42 +34,60 @@ __device__ __forceinline__ void st8(const P2<FT> (&a)[2], FT* __restrict__ g, in
   if (ok1) { g[1] = a[1].lo(); g[nlev + 1] = a[1].hi(); }
 }
 
-// Tridiagonal solve inside the warp: rows 2k (p = 0) and 2k+1 (p = 1) of lane k, coefficients (l, d, u) and right-hand side y of the
-// thread's column pair.  Rows outside the system must be identity rows (l = u = 0, y = 0); row 0 has l = 0 and the last row u = 0.
-// Returns x[2].  (cyclic reduction of the odd rows + PCR of the 32 even rows + back-substitution)
-template <class FT>
-__device__ __forceinline__ void warp_tridiag(int lane, const P2<FT> (&l)[2], const P2<FT> (&d)[2], const P2<FT> (&u)[2], const P2<FT> (&r)[2],
-                                             P2<FT> (&x)[2]) {
+// Tridiagonal solves inside the warp: rows 2k (p = 0) and 2k+1 (p = 1) of lane k, coefficients (l, d, u) and NR right-hand sides of
+// the thread's column pair.  Rows outside the system must be identity rows (l = u = 0, y = 0); row 0 has l = 0 and the last row u = 0.
+// The solutions replace the right-hand sides.  (cyclic reduction of the odd rows + PCR of the 32 even rows + back-substitution)
+template <class FT, int NR>
+__device__ __forceinline__ void warp_tridiag_n(int lane, const P2<FT> (&l)[2], const P2<FT> (&d)[2], const P2<FT> (&u)[2], P2<FT> (&y)[NR][2]) {
   using V2 = P2<FT>;
-  V2 a[2], c[2], y[2];
+  V2 a[2], c[2];
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     const V2 rd = rcpn2(d[p]);
-    a[p] = l[p] * rd; c[p] = u[p] * rd; y[p] = r[p] * rd;
+    a[p] = l[p] * rd; c[p] = u[p] * rd;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) y[r][p] = y[r][p] * rd;
   }
   // eliminate x[2k−1] (odd row of lane k−1) and x[2k+1] (own odd row) from the even row 2k
-  const V2 a1u = shup(a[1]), c1u = shup(c[1]), y1u = shup(y[1]);  // lane 0: a[0] = 0, so its own values are harmless
-  V2 A, C, Y;
+  const V2 a1u = shup(a[1]), c1u = shup(c[1]);  // lane 0: a[0] = 0, so its own values are harmless
+  V2 A, C, Y[NR];
   {
     const V2 rd = rcpn2(V2(FT(1)) - fma2(a[0], c1u, c[0] * a[1]));
     A = -((a[0] * a1u) * rd);
     C = -((c[0] * c[1]) * rd);
-    Y = (y[0] - fma2(a[0], y1u, c[0] * y[1])) * rd;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) Y[r] = (y[r][0] - fma2(a[0], shup(y[r][1]), c[0] * y[r][1])) * rd;
   }
 #pragma unroll
   for (int s = 1; s < 32; s <<= 1) {
     const bool hm = lane >= s, hp = lane + s < 32;
-    V2 Am = shup(A, s), Cm = shup(C, s), Ym = shup(Y, s), Ap = shdn(A, s), Cp = shdn(C, s), Yp = shdn(Y, s);
-    if (!hm) { Am = V2(FT(0)); Cm = V2(FT(0)); Ym = V2(FT(0)); }
-    if (!hp) { Ap = V2(FT(0)); Cp = V2(FT(0)); Yp = V2(FT(0)); }
+    V2 Am = shup(A, s), Cm = shup(C, s), Ap = shdn(A, s), Cp = shdn(C, s);
+    if (!hm) { Am = V2(FT(0)); Cm = V2(FT(0)); }
+    if (!hp) { Ap = V2(FT(0)); Cp = V2(FT(0)); }
     const V2 rd = rcpn2(V2(FT(1)) - fma2(C, Ap, A * Cm));
-    Y = (Y - fma2(C, Yp, A * Ym)) * rd;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      V2 Ym = shup(Y[r], s), Yp = shdn(Y[r], s);
+      if (!hm) Ym = V2(FT(0));
+      if (!hp) Yp = V2(FT(0));
+      Y[r] = (Y[r] - fma2(C, Yp, A * Ym)) * rd;
+    }
     A = -((A * Am) * rd);
     C = -((C * Cp) * rd);
   }
-  x[0] = Y;
-  const V2 x0d = shdn(Y);  // lane 31: c[1] = 0 (last row)
-  x[1] = y[1] - fma2(a[1], Y, c[1] * x0d);
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const V2 x0d = shdn(Y[r]);  // lane 31: c[1] = 0 (last row)
+    y[r][1] = y[r][1] - fma2(a[1], Y[r], c[1] * x0d);
+    y[r][0] = Y[r];
+  }
+}
+template <class FT>
+__device__ __forceinline__ void warp_tridiag(int lane, const P2<FT> (&l)[2], const P2<FT> (&d)[2], const P2<FT> (&u)[2], const P2<FT> (&r)[2],
+                                             P2<FT> (&x)[2]) {
+  P2<FT> y[1][2] = {{r[0], r[1]}};
+  warp_tridiag_n<FT, 1>(lane, l, d, u, y);
+  x[0] = y[0][0]; x[1] = y[0][1];
 }
 
 template <class FT, int NVC>

@@ -35,6 +35,7 @@ __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.w
 #include "kernels_imp5.cuh"
 #include "kernels_imp5d.cuh"
 #include "kernels_imp8.cuh"
+#include "kernels_imp8d.cuh"
 
 using namespace b200;
 typedef double FT;
@@ -110,7 +111,9 @@ extern "C" __attribute__((visibility("default"))) int emu_imp5d(int nh, int nv, 
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
-  run_grid(nh, [&] { k5_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  // sc[17] = 8: the warp-per-column-pair version (kernels_imp8d.cuh)
+  if ((int)sc[17] == 8) run_grid(nh, [&] { k8_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  else run_grid(nh, [&] { k5_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
   return 0;
 }
 
