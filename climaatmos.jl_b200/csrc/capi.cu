@@ -744,7 +744,14 @@ static int impl_ldiv(b200_ctx* c, void* dYc, void* dYf, const void* Rc, const vo
   if (!c->d_jsnap_c) return fail("b200_ldiv: b200_wfact has not been called");
   // exact BlockArrowheadSolve (manual_sparse_jacobian.jl:579-584): Schur complement onto u₃, PCR, back-substitution — the coefficient
   // code of the fused implicit stage on the Wfact snapshot
-  if (c->prm.microphysics_0M)
+  const bool nv63_ = c->dims.nv == 63 && !c->generic_nv;
+#define K8_LDIV(NV_, MOIST_)                                                                                                                     \
+  launchx(c->pdl & 16, k8_imp_stage<FT, NV_, true, MOIST_>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, \
+          (const FT*)c->d_jsnap_c, (const FT*)c->d_jsnap_f, (FT*)dYc, (FT*)dYf, (FT)c->jsnap_dtg, (const FT*)Rc, (const FT*)Rf)
+  if (c->imp_kernel == 8) {  // warp per column pair (kernels_imp8.cuh)
+    if (c->prm.microphysics_0M) { if (nv63_) K8_LDIV(63, true); else K8_LDIV(0, true); }
+    else { if (nv63_) K8_LDIV(63, false); else K8_LDIV(0, false); }
+  } else if (c->prm.microphysics_0M)
     launchx(c->pdl & 16, k5_imp_stage<FT, 0, true, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
             (const VLev<FT>*)c->d_vlev, (const FT*)c->d_jsnap_c, (const FT*)c->d_jsnap_f, (FT*)dYc, (FT*)dYf, (FT)c->jsnap_dtg, (const FT*)Rc,
             (const FT*)Rf);
@@ -1316,7 +1323,13 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
     LAUNCH_CHECK(c);
     return 0;
   }
-  if (c->prm.microphysics_0M && c->dims.nv == 63 && !c->generic_nv)
+  if (c->prm.microphysics_0M && c->imp_kernel == 8 && c->dims.nv == 63 && !c->generic_nv)
+    launchx(c->pdl & 16, k8_imp_stage<FT, 63, false, true>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
+  else if (c->prm.microphysics_0M && c->imp_kernel == 8)
+    launchx(c->pdl & 16, k8_imp_stage<FT, 0, false, true>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
+  else if (c->prm.microphysics_0M && c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k5_imp_stage<FT, 63, false, true>, c->dims.nh, 256, smem_imp5<FT>(true), s, make_par<FT>(c), (const FT*)c->d_hgeo,
             (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else if (c->prm.microphysics_0M)
@@ -1324,10 +1337,10 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
             (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else if (c->imp_kernel == 8 && c->dims.nv == 63 && !c->generic_nv)  // warp per column pair: no shared memory, shuffle PCR (kernels_imp8.cuh)
     launchx(c->pdl & 16, k8_imp_stage<FT, 63>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else if (c->imp_kernel == 8)
     launchx(c->pdl & 16, k8_imp_stage<FT, 0>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
+            (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else if (c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k5_imp_stage<FT, 63>, c->dims.nh, 256, smem_imp5<FT>(), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
             (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);

@@ -430,6 +430,11 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
     for k in range(ncf):
         assert rel(dYc[:, k], dc[:, k]) < 1e-11, ("ldiv", k, rel(dYc[:, k], dc[:, k]))
     assert rel(dYf, df) < 1e-11, ("ldiv u3", rel(dYf, df))
+    dYc, dYf = np.zeros_like(Yc), np.zeros_like(Yf)
+    assert emu5.emu_ldiv8(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf0), p(Rc), p(Rf), p(dYc), p(dYf)) == 0
+    for k in range(ncf):
+        assert rel(dYc[:, k], dc[:, k]) < 1e-11, ("ldiv8", k, rel(dYc[:, k], dc[:, k]))
+    assert rel(dYf, df) < 1e-11, ("ldiv8 u3", rel(dYf, df))
 
 
 @pytest.fixture(scope="module")

@@ -66,17 +66,18 @@ def test_emulated_moist_implicit_stage_and_ldiv_match_oracle(emu5, upw, rayleigh
     mp = moist_par(P)
     try:
         assert emu5.emu_set_moist(p(mp), None) == 0
-        Nc, Nf = np.zeros_like(Yc), np.zeros_like(Yf)
-        assert emu5.emu_imp5(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf), p(Nc), p(Nf)) == 0
         Uc, Uf = Yc.copy(), Yf.copy()
         pc0 = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
         assert ((pc0["ql"] + pc0["qi"]) > 0).mean() > 0.005  # cloudy points present: the Newton branch of the adjustment runs
         o._implicit_stage_local(Uc, Uf, dtg, lambda s: None)
-        for k in range(ncf):
-            assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
-        for k in (0, 3, 4):
-            assert rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8, (k, rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]))
-        assert rel(Nf, Uf) < 1e-10
+        for fn in (emu5.emu_imp5, emu5.emu_imp8):  # shared-memory slab layout / warp-per-column-pair layout
+            Nc, Nf = np.zeros_like(Yc), np.zeros_like(Yf)
+            assert fn(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf), p(Nc), p(Nf)) == 0
+            for k in range(ncf):
+                assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
+            for k in (0, 3, 4):
+                assert rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8, (k, rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]))
+            assert rel(Nf, Uf) < 1e-10
         # LDIV mode on the Wfact snapshot
         Yf0 = Yf.copy()
         Yf0[..., 0] = 0
@@ -86,11 +87,12 @@ def test_emulated_moist_implicit_stage_and_ldiv_match_oracle(emu5, upw, rayleigh
         Rc = np.ascontiguousarray(rng.standard_normal(Yc.shape) * np.abs(Yc).mean(axis=(0, 2, 3, 4), keepdims=True) * 1e-3)
         Rf = np.ascontiguousarray(rng.standard_normal(Yf.shape))
         dc, df = o.ldiv(Jm, Rc, Rf)
-        dYc, dYf = np.zeros_like(Yc), np.zeros_like(Yf)
-        assert emu5.emu_ldiv5(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf0), p(Rc), p(Rf), p(dYc), p(dYf)) == 0
-        for k in range(ncf):
-            assert rel(dYc[:, k], dc[:, k]) < 1e-11, ("ldiv", k, rel(dYc[:, k], dc[:, k]))
-        assert rel(dYf, df) < 1e-11
+        for fn in (emu5.emu_ldiv5, emu5.emu_ldiv8):
+            dYc, dYf = np.zeros_like(Yc), np.zeros_like(Yf)
+            assert fn(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf0), p(Rc), p(Rf), p(dYc), p(dYf)) == 0
+            for k in range(ncf):
+                assert rel(dYc[:, k], dc[:, k]) < 1e-11, ("ldiv", k, rel(dYc[:, k], dc[:, k]))
+            assert rel(dYf, df) < 1e-11
     finally:
         emu5.emu_set_moist(None, None)
 
