@@ -679,8 +679,12 @@ static int launch_vdiff_tend(b200_ctx* c, void* Ytc, const void* Yc, const void*
 
 template <class FT>
 static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
-  k_t_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  if (c->prm.microphysics_0M)
+    k_t_imp2<FT, true><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                      (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  else
+    k_t_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS_DRY * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
   if (vdiff_implicit(c)) return launch_vdiff_tend<FT>(c, Ytc, Yc, Yf, s);  // implicit_tendency.jl:69-78
   return 0;
@@ -797,8 +801,12 @@ static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const 
     CK(cudaMemsetAsync(Ytf, 0, c->nf() * sizeof(FT), s));
     return 0;
   }
-  k_t_post_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-                                                                   (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  if (c->prm.microphysics_0M)
+    k_t_post_imp2<FT, true><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                           (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
+  else
+    k_t_post_imp2<FT><<<c->dims.nh * 4, NT, Q_WORDS_DRY * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
+                                                                     (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   LAUNCH_CHECK(c);
   return 0;
 }
@@ -1323,10 +1331,12 @@ static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const
     LAUNCH_CHECK(c);
     return 0;
   }
-  if (c->prm.microphysics_0M && c->imp_kernel == 8 && c->dims.nv == 63 && !c->generic_nv)
+  // moist stage: two saturation adjustments per point dominate, the shared-memory layout measures 242 µs against 256 µs for the
+  // warp-per-column-pair one (profiles/r2_moist.md): k8 only on request (B200_IMP_KERNEL=88)
+  if (c->prm.microphysics_0M && c->imp_kernel == 88 && c->dims.nv == 63 && !c->generic_nv)
     launchx(c->pdl & 16, k8_imp_stage<FT, 63, false, true>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
             (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
-  else if (c->prm.microphysics_0M && c->imp_kernel == 8)
+  else if (c->prm.microphysics_0M && c->imp_kernel == 88)
     launchx(c->pdl & 16, k8_imp_stage<FT, 0, false, true>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
             (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg, (const FT*)nullptr, (const FT*)nullptr);
   else if (c->prm.microphysics_0M && c->dims.nv == 63 && !c->generic_nv)

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(NT) k_lim_vborrow(const VLev<FT>* __restrict__
 // the 2 that the 12 whole-element slabs of the first generation allow).  The per-point device functions of kernels_implicit.cuh
 // (timp_center, timp_face, face_coef, center_coef, upwind_minus_central) are reused unchanged: they address a profile as
 // p[n·LVP + v] with the element node n, so the ImpSlabs pointers are shifted by −4·quarter·LVP.
-template <class FT>
+template <class FT, bool MOIST = false>
 __device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, const FT* hg, const FT* __restrict__ Yc,
                                           const FT* __restrict__ Yf, int h, int quarter, FT* base, ImpSlabs<FT>& S) {
   const int nl = threadIdx.x >> 6, n = quarter * 4 + nl, v = threadIdx.x & 63, nv = P.nv, nf = nv + 1;
@@ -450,7 +450,7 @@ __device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, c
   if (v < nv) {
     FT K = kinetic(hg, V, S.u1[o], S.u2[o], S.u3[o], S.u3[o + 1], n, v);
     Pt<FT> t;
-    if (P.moist) {
+    if constexpr (MOIST) {
       Mst<FT> m;
       const FT rq = gY[(4 * 16 + n) * nv + v];
       t = thermo_m(P, S.rho[o], S.re[o], rq, K, V.phic[v], m);
@@ -463,8 +463,9 @@ __device__ __forceinline__ void q_prepare(const Par<FT>& P, const VLev<FT>& V, c
   __syncthreads();
 }
 constexpr int Q_WORDS = 15 * 4 * LVP;  // 12 profiles + scratch + (moist) q_tot + scratch
+constexpr int Q_WORDS_DRY = 13 * 4 * LVP;  // dry contexts: 12 profiles + scratch
 
-template <class FT>
+template <class FT, bool MOIST = false>
 __global__ void __launch_bounds__(NT) k_t_imp2(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
                                                const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(NT) k_t_imp2(Par<FT> P, const FT* __restrict__
   const VLev<FT>& V = *vlev;
   const FT* hg = hgeo + (size_t)h * HG_N * 16;
   ImpSlabs<FT> S;
-  q_prepare(P, V, hg, Yc, Yf, h, quarter, reinterpret_cast<FT*>(smem_raw), S);
+  q_prepare<FT, MOIST>(P, V, hg, Yc, Yf, h, quarter, reinterpret_cast<FT*>(smem_raw), S);
   FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
   FT* gF = Ytf + (size_t)h * 16 * nf;
   if (v < nv) {
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(NT) k_t_imp2(Par<FT> P, const FT* __restrict__
     gT[(0 * 16 + n) * nv + v] = rt; gT[(1 * 16 + n) * nv + v] = FT(0);
     gT[(2 * 16 + n) * nv + v] = FT(0); gT[(3 * 16 + n) * nv + v] = et;
     for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
-    if (P.moist) {  // central transport of the active tracer ρq_tot (implicit_tendency.jl:210-214): timp_center with q_tot for h_tot
+    if constexpr (MOIST) {  // central transport of the active tracer ρq_tot (implicit_tendency.jl:210-214): timp_center with q_tot for h_tot
       ImpSlabs<FT> Sq = S;
       Sq.h = reinterpret_cast<FT*>(smem_raw) + 13 * 4 * LVP - quarter * 4 * LVP;
       FT rt2, qt; timp_center(V, Sq, n, v, nv, rt2, qt);
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(NT) k_wfact2(Par<FT> P, const FT* __restrict__
   gj[JC_RU_LO * pl + o] = a; gj[JC_RU_HI * pl + o] = b; gj[JC_EU_LO * pl + o] = cc; gj[JC_EU_HI * pl + o] = dd;
 }
 
-template <class FT>
+template <class FT, bool MOIST = false>
 __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev,
                                                     const FT* __restrict__ Yc, const FT* __restrict__ Yf, FT* Ytc, FT* Ytf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
   const FT* hg = hgeo + (size_t)h * HG_N * 16;
   ImpSlabs<FT> S;
   FT* base = reinterpret_cast<FT*>(smem_raw);
-  q_prepare(P, V, hg, Yc, Yf, h, quarter, base, S);
+  q_prepare<FT, MOIST>(P, V, hg, Yc, Yf, h, quarter, base, S);
   FT* flx = base + 12 * 4 * LVP - quarter * 4 * LVP;
   FT* qprof = base + 13 * 4 * LVP - quarter * 4 * LVP;
   FT* flq = base + 14 * 4 * LVP - quarter * 4 * LVP;
@@ -535,10 +536,10 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
     if (v > 0 && v < nv) {
       FT w = V.g33f[v] * S.u3[o];
       r = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, S.h, o, v, nv, w);
-      if (P.moist) rq = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, qprof, o, v, nv, w);
+      if (MOIST) rq = rho_mface(V, S.rho, o, v) * w * upwind_minus_central(P, qprof, o, v, nv, w);
     }
     flx[o] = r;
-    if (P.moist) flq[o] = rq;
+    if (MOIST) flq[o] = rq;
   }
   __syncthreads();
   FT* gT = Ytc + (size_t)h * P.ncf * 16 * nv;
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(NT) k_t_post_imp2(Par<FT> P, const FT* __restr
     gT[(0 * 16 + n) * nv + v] = FT(0); gT[(1 * 16 + n) * nv + v] = FT(0); gT[(2 * 16 + n) * nv + v] = FT(0);
     gT[(3 * 16 + n) * nv + v] = -(flx[o + 1] - flx[o]) / V.mc[v];
     for (int q = 4; q < P.ncf; ++q) gT[(q * 16 + n) * nv + v] = FT(0);
-    if (P.moist) gT[(4 * 16 + n) * nv + v] = -(flq[o + 1] - flq[o]) / V.mc[v];  // implicit_tendency.jl:333-338
+    if (MOIST) gT[(4 * 16 + n) * nv + v] = -(flq[o + 1] - flq[o]) / V.mc[v];  // implicit_tendency.jl:333-338
   }
   if (v < nf) gF[n * nf + v] = FT(0);
 }

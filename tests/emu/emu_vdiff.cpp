@@ -109,10 +109,12 @@ extern "C" __attribute__((visibility("default"))) int emu_hooks(int nh, int nv, 
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
   emu_apply_moist(P, sc[3]);
   run_grid(nh, [&] { k_cache_imp<FT>(P, hgeo, &V, Yc, Yf, (FT*)nullptr, (FT*)nullptr, Kc, Tc, pc, hc); });
-  run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+  if (g_moist_on) run_grid(nh * 4, [&] { k_t_imp2<FT, true>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+  else run_grid(nh * 4, [&] { k_t_imp2<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
   if (!g_moist_on) run_grid(nh * 4, [&] { k_wfact2<FT>(P, hgeo, &V, Yc, Yf, dtg, jac); });  // debug planes: dry only
   (void)Rc; (void)Rf; (void)dYc; (void)dYf;  // ldiv! of the dry path is k5_imp_stage<…, LDIV>: emu_imp5.cpp (emu_ldiv5)
-  run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  if (g_moist_on) run_grid(nh * 4, [&] { k_t_post_imp2<FT, true>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  else run_grid(nh * 4, [&] { k_t_post_imp2<FT>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
   (void)Sc; (void)Sf;
   return 0;
 }
