@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 : > gpurun_out/configs_1gpu.jsonl
 python bench.py --steps 20 --warmup 3 2>/dev/null | tail -1 >> gpurun_out/configs_1gpu.jsonl
-for cfg in he16 tracer hs strong vdiff vdiff_implicit; do
+for cfg in he16 moist tracer hs strong vdiff vdiff_implicit; do
   python bench.py --config $cfg --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 >> gpurun_out/configs_1gpu.jsonl
 done
 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 >> gpurun_out/configs_1gpu.jsonl
