@@ -430,7 +430,7 @@ def main():
         sim.remaining_tendency_phase(1, Yt, sim.Y)  # DSS of the ∇² fields
         for name, fn, nbytes, per_step, what in (
                 ("k5_exp_a<float, 63>", lambda: sim.remaining_tendency_phase_a(Yt, sim.Y), 2 * S_b + H_b, 4, "T_exp_T_lim! pre-DSS kernel: read S, write S + H"),
-                ("k5_imp_stage<float, 63>", lambda: sim.implicit_stage(N2, sim.Y, dtg), 2 * S_b, 3, "fused implicit stage: read S, write S"),
+                ("k8_imp_stage<float, 63>", lambda: sim.implicit_stage(N2, sim.Y, dtg), 2 * S_b, 3, "fused implicit stage (warp per column pair): read S, write S"),
                 ("k7_exp_c<float, 63>", lambda: sim.remaining_tendency_phase_c(Yt, sim.Y), c_b + H_b + 2 * (3 * c_b + f_b), 4,
                  "hyperdiffusion apply: read ρ + H, read-modify-write uₕ, ρe_tot, u₃ of Yₜ")):
             k_ms = time_kernel(fn)
@@ -497,8 +497,8 @@ def main():
 
 
 # ncu --set full DRAM traffic per launch at he30/ze63 Float32 (bytes): see profiles/ (updated per round with the capture)
-TRAFFIC_SOURCE = "profiles/r1_ncu_full_session2_kernels.txt"
-TRAFFIC = {"k5_exp_a<float, 63>": 256.0e6, "k5_imp_stage<float, 63>": 176.7e6, "k7_exp_c<float, 63>": None}
+TRAFFIC_SOURCE = "profiles/r2_ncu_full_final_step_kernels.txt"
+TRAFFIC = {"k5_exp_a<float, 63>": 255.7e6, "k8_imp_stage<float, 63>": 174.4e6, "k7_exp_c<float, 63>": 264.1e6}
 
 
 if __name__ == "__main__":

@@ -1098,23 +1098,24 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
   if (hd && !c->H) CK(cudaMalloc(&c->H, c->nc() * sizeof(FT)));
   const bool nv63 = c->dims.nv == 63 && !c->generic_nv;
   const bool moist = c->prm.microphysics_0M != 0;
+  const int n_passive = c->dims.n_tracers - (moist ? 1 : 0);
   if (moist && hd && !c->Hw) CK(cudaMalloc(&c->Hw, (size_t)c->dims.nh * 16 * c->dims.nv * sizeof(FT)));
   if (phase == 0) {
     if (moist && nv63)  // moist thermodynamic state + ∇²q_tot_eff → H[4], ρ(h_eff + Φ) → Hw
       launchx(c->pdl & 1, k5_exp_a<FT, 63, true>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw);
+              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw, (FT*)Ylc);
     else if (moist)
       launchx(c->pdl & 1, k5_exp_a<FT, 0, true>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw);
+              (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)c->Hw, (FT*)Ylc);
     else if (nv63)
       launchx(c->pdl & 1, k5_exp_a<FT, 63>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)nullptr);
+                                                             (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)nullptr, (FT*)nullptr);
     else
       launchx(c->pdl & 1, k5_exp_a<FT, 0>, c->dims.nh, CT, smem_rowq<FT>(9), s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                            (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)nullptr);
+                                                            (const FT*)Yf, (FT*)Ytc, (FT*)Ytf, hd ? (FT*)c->H : nullptr, (FT*)nullptr, (FT*)nullptr);
     LAUNCH_CHECK(c);
-    if (c->dims.n_tracers > 0) {
-      k5_tracer_a<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(3), s>>>(
+    if (n_passive > 0) {
+      k5_tracer_a<FT><<<dim3(c->dims.nh, n_passive), CT, smem_row<FT>(3), s>>>(
           make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ylc,
           hd ? (FT*)c->H : nullptr);
       LAUNCH_CHECK(c);
@@ -1132,8 +1133,8 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
       launchx(c->pdl & 2, k7_exp_c<FT, 0>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
               (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
     LAUNCH_CHECK(c);
-    if (c->dims.n_tracers > 0) {
-      k5_tracer_c<FT><<<dim3(c->dims.nh, c->dims.n_tracers), CT, smem_row<FT>(0), s>>>(
+    if (n_passive > 0) {
+      k5_tracer_c<FT><<<dim3(c->dims.nh, n_passive), CT, smem_row<FT>(0), s>>>(
           make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)c->H, (FT*)(Ylc ? Ylc : Ytc));
       LAUNCH_CHECK(c);
     }

@@ -115,12 +115,15 @@ __device__ __forceinline__ void sgetq(const FT* s, P2<FT> (&a)[2], int j, int v)
 // NVC: compile-time number of levels (63 in every production configuration), 0 = run-time P.nv
 // MOIST (microphysics_model 0M; component 4 of Y.c is the active ρq_tot): moist thermodynamic state (moist.cuh); ∇²q_tot_eff =
 // wdivₕ(gradₕ(q_tot − q_tot_r(p))) → H[4] (hyperdiffusion.jl:148-165); ρ(h_eff + Φ) → Hw for the water enthalpy flux of the apply
-// kernel (:293-306); viscous sponge on the total water: the aggregate tendency also enters ρ, its enthalpy flux ρe_tot
-// (viscous_sponge.jl:158-199; the ρq_tot part itself is written by k5_tracer_a).  The dry instantiations are unchanged.
+// kernel (:293-306); the whole ρq_tot tendency of this phase — horizontal advection −split_divₕ(ρu, q_tot) into Yₜ_lim (advection.jl:121-124;
+// ρu and wdivₕ(ρu) are already in registers) and the viscous sponge on the total water, whose aggregate tendency also enters ρ and whose
+// enthalpy flux enters ρe_tot (viscous_sponge.jl:158-199).  k5_tracer_a then only serves the passive tracers.  The dry instantiations are
+// unchanged.
 template <class FT, int NVC, bool MOIST = false>
 __global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 2 : 1))
 k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-         const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H, FT* __restrict__ Hw = nullptr) {
+         const FT* __restrict__ Yf, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ H, FT* __restrict__ Hw = nullptr,
+         FT* __restrict__ Ylc = nullptr) {
   using V = P2<FT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
@@ -207,6 +210,20 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     for (int p = 0; p < 2; ++p) { wd[p] = wd[p] * rjs[p]; G1[p] = F1[p] * hh[p]; G2[p] = F2[p] * hh[p]; }
     V rt[2] = {-wd[0], -wd[1]};
     if (!MOIST && cv) st4q(rt, gT, nv);
+    V gq1[2], gq2[2], limq[2], outq[2];  // MOIST: gradₕ q_tot, −split_divₕ(ρu, q_tot), sponge part of the ρq_tot tendency
+    if constexpr (MOIST) {
+      V Q1[2], Q2[2], tq[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) { Q1[p] = F1[p] * qs[p]; Q2[p] = F2[p] * qs[p]; outq[p] = V(FT(0)); }
+      div4p<FT, 1>(Q1, Q2, mw, vl, tq);
+      deta4p(qs, md, vl, gq2);
+      dxi4p<FT, 0>(qs, gq1);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        V adv = fma2(F2[p], gq2[p], F1[p] * gq1[p]) * rjs[p];
+        limq[p] = -((tq[p] * rjs[p]) * FT(0.5) + fma2(qs[p], wd[p], adv) * FT(0.5));
+      }
+    }
     div4p<FT, 1>(G1, G2, mw, vl, t);
     deta4p(hh, md, vl, g2);
     dxi4p<FT, 0>(hh, g1);
@@ -223,19 +240,24 @@ k5_exp_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       div4p<FT, 1>(S1, S2, mw, vl, t);
 #pragma unroll
       for (int p = 0; p < 2; ++p) et[p] = fma2(t[p] * rjs[p], L.bvc, et[p]);
-      if constexpr (MOIST) {  // β wdivₕ(ρ gradₕ q_tot) → ρ ; β wdivₕ(ρ (h_eff + Φ) gradₕ q_tot) → ρe_tot
-        deta4p(qs, md, vl, g2);
-        dxi4p<FT, 0>(qs, g1);
-        METRIC_FLUX(S1, S2, g1, g2, rho[p] * HGP(HG_J2, p))
+      if constexpr (MOIST) {  // β wdivₕ(ρ gradₕ q_tot) → ρq_tot and ρ ; β wdivₕ(ρ (h_eff + Φ) gradₕ q_tot) → ρe_tot
+        METRIC_FLUX(S1, S2, gq1, gq2, rho[p] * HGP(HG_J2, p))
         div4p<FT, 1>(S1, S2, mw, vl, t);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) { rt[p] = fma2(t[p] * rjs[p], L.bvc, rt[p]); S1[p] = S1[p] * hw[p]; S2[p] = S2[p] * hw[p]; }
+        for (int p = 0; p < 2; ++p) {
+          outq[p] = (t[p] * rjs[p]) * L.bvc;
+          rt[p] = fma2(t[p] * rjs[p], L.bvc, rt[p]); S1[p] = S1[p] * hw[p]; S2[p] = S2[p] * hw[p];
+        }
         div4p<FT, 1>(S1, S2, mw, vl, t);
 #pragma unroll
         for (int p = 0; p < 2; ++p) et[p] = fma2(t[p] * rjs[p], L.bvc, et[p]);
       }
     }
-    if (MOIST && cv) st4q(rt, gT, nv);
+    if (MOIST && cv) {
+      st4q(rt, gT, nv);
+      if (Ylc) { st4q(outq, gT + 64 * nv, nv); st4q(limq, Ylc + offc + 64 * nv, nv); }
+      else { outq[0] = outq[0] + limq[0]; outq[1] = outq[1] + limq[1]; st4q(outq, gT + 64 * nv, nv); }
+    }
     if (cv) st4q(et, gT + 48 * nv, nv);
     if (gH) {  // ∇²(s_d − s_d,r)  (hyperdiffusion.jl:142-147)
       V Q1[2], Q2[2];
@@ -399,10 +421,8 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   FT *s_chi = sx, *s_r = sx + SLAB, *s_fx = sx + 2 * SLAB;
   B200_ROW_PROLOGUE
   ROW_COLUMNS
-  const int q = 4 + blockIdx.y;
-  // ρq_tot of a moist (0M) context: horizontal advection and the sponge as for any tracer; its vertical transport is implicit
-  // (advection.jl:250) and its ∇² slot carries ∇²q_tot_eff, written by k5_exp_a<…, MOIST>
-  const bool active = P.moist && q == 4;
+  // passive tracers only: in a moist (0M) context component 4 is the active ρq_tot, served by k5_exp_a<…, MOIST> / k_moist_c
+  const int q = 4 + (P.moist ? 1 : 0) + blockIdx.y;
   const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   V rho[2], u1[2], u2[2], rq[2], u3[2], chi[2];
   ld4p(rho, gY, nv, j, v, cv, FT(1)); ld4p(u1, gY + 16 * nv, nv, j, v, cv, FT(0)); ld4p(u2, gY + 32 * nv, nv, j, v, cv, FT(0));
@@ -433,7 +453,7 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
     lim[p] = -((t[p] * rjs[p]) * FT(0.5) + fma2(chi[p], wd[p], adv) * FT(0.5));
     out[p] = V(FT(0));
   }
-  if (H && !active) {  // ∇²χ
+  if (H) {  // ∇²χ
     V Q1[2], Q2[2];
     METRIC_FLUX(Q1, Q2, g1, g2, HGP(HG_J2, p))
     div4p<FT, 1>(Q1, Q2, mw, vl, t);
@@ -450,7 +470,7 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   }
   // vertical transport: flux through face v of (ᶠinterp(ρJ)/J2)·u³·χ_face, zero on the boundary faces
   {
-    const bool interior = v > 0 && v < nv && !active;
+    const bool interior = v > 0 && v < nv;
     FT fx[4];
     const int vm = v > 0 ? v - 1 : 0, vm2 = v > 1 ? v - 2 : 0, vp = v < nv - 1 ? v + 1 : v;
 #pragma unroll
@@ -506,10 +526,9 @@ k5_tracer_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   using V = P2<FT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FT* hg = reinterpret_cast<FT*>(smem_raw);
-  if (P.moist && blockIdx.y == 0) return;  // ρq_tot: k_moist_c
   B200_ROW_PROLOGUE
   ROW_COLUMNS
-  const int q = 4 + blockIdx.y;
+  const int q = 4 + (P.moist ? 1 : 0) + blockIdx.y;  // passive tracers (ρq_tot of a moist context: k_moist_c)
   V rho[2], Lq[2], old[2], a[2], g1[2], Q1[2], Q2[2], b[2];
   FT* gT = Tgt + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv;
   ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));

@@ -89,3 +89,33 @@ def test_hundred_steps_bounded_drift_ze63_with_u3():
         assert e["u3"] <= 5e-2, (k, e)
     assert e100["u3"] <= 1.5 * max(hist[25]["u3"], hist[50]["u3"]), hist  # bounded, not growing
     sim.close()
+
+
+def test_moist_config_one_step_float32_he30():
+    """BASELINE.json configs[2] as the reference runs it — the 0M-moist baroclinic wave at he30/ze63 with the thermodynamically active
+    ρq_tot (dt 90 s): Float32 CUDA after one fused step against the Float64 oracle.  ρ, uₕ, ρe_tot, ρq_tot within the 1e-5 north-star
+    bar; u₃ within the moist Float32 bar of tests/test_gpu_moist.py (the floor of the reference's own formulation in Float32 there is
+    2.4e-5 … 7.9e-5, tests/test_oracle_moist.py::test_float32_floor_of_the_moist_reference_formulation).  Water and mass conserved."""
+    from tests.test_gpu_moist import U3_MOIST
+
+    P = prm.DycoreParams(zd_rayleigh=ZD, zd_viscous=ZD)
+    sim = dycore.AtmosSimulation(FT=np.float32, h_elem=30, z_elem=63, z_max=60000.0, dz_bottom=30.0, dt=90.0, rayleigh_sponge=True,
+                                 viscous_sponge=True, params=P, microphysics_model="0M", initial_condition="MoistBaroclinicWave")
+    Yc0, Yf0 = sim.Y.cpu()
+    o = Oracle(sim.grid, P, sim.numerics, np.float64)
+    cores = max(1, min(32, len(os.sched_getaffinity(0))))
+    with ThreadPoolExecutor(cores) as pool:
+        oc, of = o.step(Yc0.astype(np.float64), Yf0.astype(np.float64), pool=pool, nchunks=cores)
+    sim.step(fused=True)
+    torch.cuda.synchronize()
+    gc, gf = sim.Y.cpu()
+    e = {n: rel(gc[:, k], oc[:, k]) for k, n in enumerate(NAMES + ("rhoq",))}
+    e["u3"] = rel(gf[:, 0], of[:, 0])
+    record_parity("one_step_moist_he30ze63_f32", e)
+    for n, v in e.items():
+        assert v <= (U3_MOIST if n == "u3" else 1e-5), f"moist he30/ze63 Float32 after one step: {n} rel-L2 {v:.3e} ({e})"
+    W = o.c.WJ
+    for k in (0, 4):
+        a, b = (W * Yc0[:, k].astype(np.float64)).sum(), (W * gc[:, k].astype(np.float64)).sum()
+        assert abs(a - b) / abs(a) < 2e-6, (k, a, b)
+    sim.close()

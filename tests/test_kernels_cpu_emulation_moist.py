@@ -115,7 +115,7 @@ def test_emulated_moist_explicit_tendency_kernels_match_oracle(emux, deep, spong
     try:
         assert emux.emu_set_moist(p(mp), p(Hw)) == 0
         Ytc, Ytf, H, Ylc = np.zeros_like(Yc), np.zeros_like(Yf), np.zeros_like(Yc), np.zeros_like(Yc)
-        assert emux.emu_exp5(0, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), None) == 0
+        assert emux.emu_exp5(0, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), p(Ylc)) == 0
         assert emux.emu_exp5(2, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(H), p(Ylc)) == 0
         pc = o.set_implicit_precomputed_quantities(Yc.copy(), Yf.copy())
         assert ((pc["ql"] + pc["qi"]) > 0).mean() > 0.005
