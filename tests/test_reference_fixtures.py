@@ -29,6 +29,7 @@ CASES = {
     "he4ze10_f64": (4, 10, 30000.0, 500.0, 400.0, False, np.float64, None),
     "he6ze10_f32": (6, 10, 30000.0, 500.0, 400.0, False, np.float32, None),
     "he3ze63_f64": (3, 63, 60000.0, 30.0, 120.0, True, np.float64, 40000.0),
+    "he4ze10_moist_f64": (4, 10, 30000.0, 500.0, 400.0, False, np.float64, None),  # EquilibriumMicrophysics0M, MoistBaroclinicWave
 }
 
 
@@ -54,7 +55,7 @@ def setup(case):
     kw = dict(zd_rayleigh=zd, zd_viscous=zd) if zd else {}
     P = prm.DycoreParams(**kw)
     g = G.make_sphere_grid(FT=FT, h_elem=he, z_elem=ze, z_max=zmax, dz_bottom=dzb, radius=P.planet_radius)
-    N = prm.DycoreNumerics(dt=dt, rayleigh_sponge=sp, viscous_sponge=sp)
+    N = prm.DycoreNumerics(dt=dt, rayleigh_sponge=sp, viscous_sponge=sp, microphysics_model="0M" if "moist" in case else None)
     return R, P, g, N, FT, (1e-12 if FT == np.float64 else 1e-5)
 
 

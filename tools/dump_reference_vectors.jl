@@ -44,6 +44,13 @@ cases = Dict(
     "he3ze63_f64" => merge(common, Dict("h_elem" => 3, "z_elem" => 63, "z_max" => 60000.0, "dz_bottom" => 30.0, "dt" => "120secs",
                                         "rayleigh_sponge" => true, "viscous_sponge" => true, "FLOAT_TYPE" => "Float64",
                                         "toml" => ["toml/longrun_held_suarez.toml"])),
+    # BASELINE configs[2] in small: the 0M-moist baroclinic wave (EquilibriumMicrophysics0M, thermodynamically active ρq_tot).  The
+    # precipitation sink of the 0M scheme is a parameterised tendency outside the dycore hooks dumped here (remaining_tendency! contains
+    # it through additional_tendency!: the oracle comparison of that hook therefore needs `precip_model`-free settings or a tolerance on
+    # ρq_tot/ρe_tot/ρ where q_liq + q_ice > 0; every other hook is unaffected).
+    "he4ze10_moist_f64" => merge(common, Dict("h_elem" => 4, "z_elem" => 10, "z_max" => 30000.0, "dz_bottom" => 500.0, "dt" => "400secs",
+                                              "rayleigh_sponge" => false, "viscous_sponge" => false, "FLOAT_TYPE" => "Float64",
+                                              "initial_condition" => "MoistBaroclinicWave", "microphysics_model" => "0M")),
 )
 
 # ---- raw binary writer -------------------------------------------------------------------------------------------------------------
