@@ -679,7 +679,14 @@ static int launch_vdiff_tend(b200_ctx* c, void* Ytc, const void* Yc, const void*
 
 template <class FT>
 static int impl_t_imp(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const void* Yf, cudaStream_t s) {
-  if (c->prm.microphysics_0M)
+#define K8_HOOK(KERNEL, NV_, MOIST_)                                                                                                      \
+  launchx(0, KERNEL<FT, NV_, MOIST_>, c->dims.nh, 256, 0, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, \
+          (const FT*)Yf, (FT*)Ytc, (FT*)Ytf)
+  const bool nv63h = c->dims.nv == 63 && !c->generic_nv;
+  if (c->imp_kernel == 8) {  // warp per column pair (kernels_imp8.cuh)
+    if (c->prm.microphysics_0M) { if (nv63h) K8_HOOK(k8_t_imp, 63, true); else K8_HOOK(k8_t_imp, 0, true); }
+    else { if (nv63h) K8_HOOK(k8_t_imp, 63, false); else K8_HOOK(k8_t_imp, 0, false); }
+  } else if (c->prm.microphysics_0M)
     k_t_imp2<FT, true><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                       (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   else
@@ -801,7 +808,11 @@ static int impl_t_post(b200_ctx* c, void* Ytc, void* Ytf, const void* Yc, const 
     CK(cudaMemsetAsync(Ytf, 0, c->nf() * sizeof(FT), s));
     return 0;
   }
-  if (c->prm.microphysics_0M)
+  const bool nv63h = c->dims.nv == 63 && !c->generic_nv;
+  if (c->imp_kernel == 8) {
+    if (c->prm.microphysics_0M) { if (nv63h) K8_HOOK(k8_t_post_imp, 63, true); else K8_HOOK(k8_t_post_imp, 0, true); }
+    else { if (nv63h) K8_HOOK(k8_t_post_imp, 63, false); else K8_HOOK(k8_t_post_imp, 0, false); }
+  } else if (c->prm.microphysics_0M)
     k_t_post_imp2<FT, true><<<c->dims.nh * 4, NT, Q_WORDS * sizeof(FT), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
                                                                            (const FT*)Yc, (const FT*)Yf, (FT*)Ytc, (FT*)Ytf);
   else
@@ -1465,18 +1476,18 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
         if (impl_imp_stage<FT>(c, Nc, Nf, Uc, Uf, dtg, s)) return -1;
       } else {
         if (impl_cache_imp<FT>(c, Uc, Uf, nullptr, s)) return -1;
-        CK(cudaMemcpyAsync(Nc, Uc, bc, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(Nf, Uf, bf, cudaMemcpyDeviceToDevice, s));
-        if (impl_wfact<FT>(c, Nc, Nf, dtg, s)) return -1;
-        if (impl_t_imp<FT>(c, c->Rc, c->Rf, Nc, Nf, s)) return -1;
+        // temp = U stays in (Uc, Uf); the Newton iterate starts as U, so Wfact / T_imp! read U itself and the update is written out of
+        // place (N = U − ΔU): the same values as copying U into N first, without the two state copies
+        if (impl_wfact<FT>(c, Uc, Uf, dtg, s)) return -1;
+        if (impl_t_imp<FT>(c, c->Rc, c->Rf, Uc, Uf, s)) return -1;
         {  // R = temp + dtγ·T_imp(U) − U
-          const void* Tc[2] = {c->Rc, Nc}; const void* Tf[2] = {c->Rf, Nf}; double cf[2] = {dtg, -1.0};
+          const void* Tc[2] = {c->Rc, Uc}; const void* Tf[2] = {c->Rf, Uf}; double cf[2] = {dtg, -1.0};
           if (impl_axpy<FT>(c, c->Rc, c->Rf, Uc, Uf, 2, Tc, Tf, cf, s)) return -1;
         }
         if (impl_ldiv<FT>(c, c->dc, c->df, c->Rc, c->Rf, s)) return -1;
         {
           const void* Tc[1] = {c->dc}; const void* Tf[1] = {c->df}; double cf[1] = {-1.0};
-          if (impl_axpy<FT>(c, Nc, Nf, Nc, Nf, 1, Tc, Tf, cf, s)) return -1;
+          if (impl_axpy<FT>(c, Nc, Nf, Uc, Uf, 1, Tc, Tf, cf, s)) return -1;
         }
         if (impl_cache_imp<FT>(c, Nc, Nf, nullptr, s)) return -1;
         if (c->prm.energy_upwinding != 0) {

@@ -358,3 +358,162 @@ k8_imp_stage(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict_
 }
 
 }  // namespace b200
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// Hook kernels in the warp-per-column-pair layout (the hook-by-hook path a ClimaTimeSteppers integration drives):
+//   k8_t_imp       implicit_tendency! (implicit_tendency.jl:36-98,185-298; the diffusion part is added by k_vdiff_tend2)
+//   k8_t_post_imp  correct_implicit_advection_tendency! (:322-339)
+// Same arithmetic as k_t_imp2 / k_t_post_imp2 (kernels_vdiff.cuh: one point per thread, quarter element per CTA, 12 shared profiles),
+// without shared memory and barriers; the state is used as it comes (cache_imp! has filtered u₃ on the boundary faces before).
+template <class FT, int NVC, bool MOIST = false>
+__global__ void __launch_bounds__(256, sizeof(FT) == 4 ? 2 : 1)
+k8_t_imp(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc, const FT* __restrict__ Yf,
+         FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
+  using V2 = P2<FT>;
+  const int e = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, n0 = 2 * w, nv = NVC ? NVC : P.nv, nf = nv + 1;
+  bool cv[2], fv[2], interior[2];
+  FT sc2i[2], phi[2], mc[2], mclo[2], rmc[2], g33lo[2], g33hi[2], dphif[2], beta[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    cv[p] = v < nv; fv[p] = v < nf; interior[p] = v > 0 && v < nv;
+    const int vm = v > 0 ? v - 1 : 0;
+    const int vc = cv[p] ? v : nv - 1, vmc = vm < nv ? vm : nv - 1, vf = fv[p] ? v : nv, vf1 = v + 1 <= nv ? v + 1 : nv;
+    sc2i[p] = vlev->sc2i[vc]; phi[p] = vlev->phic[vc]; mc[p] = vlev->mc[vc]; mclo[p] = vlev->mc[vmc]; rmc[p] = vlev->rmc[vc];
+    g33lo[p] = vlev->g33f[vf]; g33hi[p] = vlev->g33f[vf1]; dphif[p] = vlev->dphif[vf]; beta[p] = P.rayleigh ? vlev->brw[vf] : FT(0);
+  }
+  const FT* hgp = hgeo + (size_t)e * HG_N * 16 + n0;
+  const V2 g11 = ldpair(hgp + HG_GI11 * 16), g12 = ldpair(hgp + HG_GI12 * 16), g22 = ldpair(hgp + HG_GI22 * 16);
+  const int cs = 16 * nv;
+  const FT* gY = Yc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + 2 * lane);
+  FT* gT = Ytc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + 2 * lane);
+  V2 rho[2], u1[2], u2[2], re[2], u3[2], rq[2];
+  ld8(rho, gY, nv, cv[0], cv[1], FT(1)); ld8(u1, gY + cs, nv, cv[0], cv[1], FT(0)); ld8(u2, gY + 2 * cs, nv, cv[0], cv[1], FT(0));
+  ld8(re, gY + 3 * cs, nv, cv[0], cv[1], FT(0)); ld8(u3, Yf + ((size_t)e * 16 * nf + n0 * nf + 2 * lane), nf, fv[0], fv[1], FT(0));
+  if (MOIST) ld8(rq, gY + 4 * cs, nv, cv[0], cv[1], FT(0));
+  const V2 zero[2] = {V2(FT(0)), V2(FT(0))};
+  st8(zero, gT + cs, nv, cv[0], cv[1]); st8(zero, gT + 2 * cs, nv, cv[0], cv[1]);
+  for (int q = MOIST ? 5 : 4; q < P.ncf; ++q) st8(zero, gT + q * cs, nv, cv[0], cv[1]);
+  const V2 u3h[2] = {u3[1], shdn(u3[0])}, rlo[2] = {shup(rho[1]), rho[0]};
+  V2 h[2], Pi[2], thp[2], phr[2], M[2], qv[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    h[p] = V2(FT(0)); Pi[p] = V2(FT(1)); thp[p] = V2(FT(0)); phr[p] = V2(FT(1)); qv[p] = V2(FT(0));
+    if (cv[p]) {
+      const V2 c1 = fma2(g12, u2[p], g11 * u1[p]), c2 = fma2(g22, u2[p], g12 * u1[p]);
+      const V2 K = (fma2(u2[p], c2, u1[p] * c1) * sc2i[p]) * FT(0.5) + (u3[p] * (u3[p] * g33lo[p]) + u3h[p] * (u3h[p] * g33hi[p])) * FT(0.25);
+      Pt2<FT> t;
+      if constexpr (MOIST) { Mst2<FT> m; t = thermo2m(P, rho[p], re[p], rq[p], K, phi[p], m); qv[p] = div2(rq[p], rho[p]); }
+      else t = thermo2(P, rho[p], re[p], K, phi[p]);
+      h[p] = t.h; Pi[p] = t.Pi; thp[p] = t.thp; phr[p] = pgf_aux2(t);
+    }
+    M[p] = V2(FT(0));
+    if (interior[p]) M[p] = (fma2(rho[p], V2(mc[p]), rlo[p] * mclo[p]) * FT(0.5)) * (u3[p] * g33lo[p]);  // ᶠinterp(ρJ) u³ / J2
+  }
+  const V2 h_m1[2] = {shup(h[1]), h[0]}, h_p1[2] = {h[1], shdn(h[0])}, M_p1[2] = {M[1], shdn(M[0])};
+  const V2 Pi_m1[2] = {shup(Pi[1]), Pi[0]}, thp_m1[2] = {shup(thp[1]), thp[0]}, phr_m1[2] = {shup(phr[1]), phr[0]};
+  V2 q_m1[2], q_p1[2];
+  if (MOIST) { q_m1[0] = shup(qv[1]); q_m1[1] = qv[0]; q_p1[0] = qv[1]; q_p1[1] = shdn(qv[0]); }
+  V2 rt[2], et[2], qt[2], tf[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    const V2 hf0 = v > 0 ? (h_m1[p] + h[p]) * FT(0.5) : V2(FT(0)), hfp = v < nv - 1 ? (h[p] + h_p1[p]) * FT(0.5) : V2(FT(0));
+    const V2 Mp = M_p1[p];
+    rt[p] = -((Mp - M[p]) * rmc[p]);
+    et[p] = -((Mp * hfp - M[p] * hf0) * rmc[p]);
+    if constexpr (MOIST) {
+      const V2 qf0 = v > 0 ? (q_m1[p] + qv[p]) * FT(0.5) : V2(FT(0)), qfp = v < nv - 1 ? (qv[p] + q_p1[p]) * FT(0.5) : V2(FT(0));
+      qt[p] = -((Mp * qfp - M[p] * qf0) * rmc[p]);
+    }
+    tf[p] = V2(FT(0));
+    if (interior[p]) {
+      V2 dPi, dphr;
+      pgf_diff2(P, Pi_m1[p], Pi[p], phr_m1[p], phr[p], dPi, dphr);
+      tf[p] = -((V2(dphif[p]) - dphr) + (((thp_m1[p] + thp[p]) * FT(0.5)) * P.cp_d) * dPi);
+    }
+    if (P.rayleigh) tf[p] = tf[p] - u3[p] * beta[p];
+  }
+  st8(rt, gT, nv, cv[0], cv[1]); st8(et, gT + 3 * cs, nv, cv[0], cv[1]);
+  if (MOIST) st8(qt, gT + 4 * cs, nv, cv[0], cv[1]);
+  st8(tf, Ytf + ((size_t)e * 16 * nf + n0 * nf + 2 * lane), nf, fv[0], fv[1]);
+}
+
+template <class FT, int NVC, bool MOIST = false>
+__global__ void __launch_bounds__(256, sizeof(FT) == 4 ? 2 : 1)
+k8_t_post_imp(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc, const FT* __restrict__ Yf,
+              FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
+  using V2 = P2<FT>;
+  const int e = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, n0 = 2 * w, nv = NVC ? NVC : P.nv, nf = nv + 1;
+  bool cv[2], fv[2], interior[2];
+  FT sc2i[2], phi[2], mc[2], mclo[2], rmc[2], g33lo[2], g33hi[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    cv[p] = v < nv; fv[p] = v < nf; interior[p] = v > 0 && v < nv;
+    const int vm = v > 0 ? v - 1 : 0;
+    const int vc = cv[p] ? v : nv - 1, vmc = vm < nv ? vm : nv - 1, vf = fv[p] ? v : nv, vf1 = v + 1 <= nv ? v + 1 : nv;
+    sc2i[p] = vlev->sc2i[vc]; phi[p] = vlev->phic[vc]; mc[p] = vlev->mc[vc]; mclo[p] = vlev->mc[vmc]; rmc[p] = vlev->rmc[vc];
+    g33lo[p] = vlev->g33f[vf]; g33hi[p] = vlev->g33f[vf1];
+  }
+  const FT* hgp = hgeo + (size_t)e * HG_N * 16 + n0;
+  const V2 g11 = ldpair(hgp + HG_GI11 * 16), g12 = ldpair(hgp + HG_GI12 * 16), g22 = ldpair(hgp + HG_GI22 * 16);
+  const int cs = 16 * nv;
+  const FT* gY = Yc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + 2 * lane);
+  FT* gT = Ytc + ((size_t)e * P.ncf * 16 * nv + n0 * nv + 2 * lane);
+  V2 rho[2], u1[2], u2[2], re[2], u3[2], rq[2];
+  ld8(rho, gY, nv, cv[0], cv[1], FT(1)); ld8(u1, gY + cs, nv, cv[0], cv[1], FT(0)); ld8(u2, gY + 2 * cs, nv, cv[0], cv[1], FT(0));
+  ld8(re, gY + 3 * cs, nv, cv[0], cv[1], FT(0)); ld8(u3, Yf + ((size_t)e * 16 * nf + n0 * nf + 2 * lane), nf, fv[0], fv[1], FT(0));
+  if (MOIST) ld8(rq, gY + 4 * cs, nv, cv[0], cv[1], FT(0));
+  const V2 zero[2] = {V2(FT(0)), V2(FT(0))};
+  st8(zero, gT, nv, cv[0], cv[1]); st8(zero, gT + cs, nv, cv[0], cv[1]); st8(zero, gT + 2 * cs, nv, cv[0], cv[1]);
+  for (int q = MOIST ? 5 : 4; q < P.ncf; ++q) st8(zero, gT + q * cs, nv, cv[0], cv[1]);
+  st8(zero, Ytf + ((size_t)e * 16 * nf + n0 * nf + 2 * lane), nf, fv[0], fv[1]);
+  const V2 u3h[2] = {u3[1], shdn(u3[0])};
+  V2 h[2], qv[2], rn[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    h[p] = V2(FT(0)); qv[p] = V2(FT(0)); rn[p] = cv[p] ? rho[p] : V2(FT(1));
+    if (cv[p]) {
+      const V2 c1 = fma2(g12, u2[p], g11 * u1[p]), c2 = fma2(g22, u2[p], g12 * u1[p]);
+      const V2 K = (fma2(u2[p], c2, u1[p] * c1) * sc2i[p]) * FT(0.5) + (u3[p] * (u3[p] * g33lo[p]) + u3h[p] * (u3h[p] * g33hi[p])) * FT(0.25);
+      if constexpr (MOIST) { Mst2<FT> m; h[p] = thermo2m(P, rho[p], re[p], rq[p], K, phi[p], m).h; qv[p] = div2(rq[p], rho[p]); }
+      else h[p] = thermo2(P, rho[p], re[p], K, phi[p]).h;
+    }
+  }
+  const V2 hu0 = shup(h[0]), hu1 = shup(h[1]), hd0 = shdn(h[0]), rnu1 = shup(rn[1]);
+  const V2 h_m1[2] = {hu1, h[0]}, h_m2[2] = {hu0, hu1}, h_p1[2] = {h[1], hd0}, rn_m1[2] = {rnu1, rn[0]};
+  V2 q_m1[2], q_m2[2], q_p1[2];
+  if (MOIST) {
+    const V2 qu0 = shup(qv[0]), qu1 = shup(qv[1]), qd0 = shdn(qv[0]);
+    q_m1[0] = qu1; q_m1[1] = qv[0]; q_m2[0] = qu0; q_m2[1] = qu1; q_p1[0] = qv[1]; q_p1[1] = qd0;
+  }
+  V2 flx[2], flq[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int v = 2 * lane + p;
+    flx[p] = V2(FT(0)); flq[p] = V2(FT(0));
+    if (interior[p]) {
+      const V2 wv = u3[p] * g33lo[p];
+      const V2 mr = fma2(rho[p], V2(mc[p]), rn_m1[p] * mclo[p]) * FT(0.5);
+      flx[p] = (mr * wv) * upw_minus_central2(P, wv, h_m2[p], h_m1[p], h[p], h_p1[p], v, nv);
+      if (MOIST) flq[p] = (mr * wv) * upw_minus_central2(P, wv, q_m2[p], q_m1[p], qv[p], q_p1[p], v, nv);
+    }
+  }
+  const V2 fp[2] = {flx[1], shdn(flx[0])};
+  V2 et[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) et[p] = (-(fp[p] - flx[p])) * rmc[p];
+  st8(et, gT + 3 * cs, nv, cv[0], cv[1]);
+  if (MOIST) {
+    const V2 fq[2] = {flq[1], shdn(flq[0])};
+    V2 qt[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) qt[p] = (-(fq[p] - flq[p])) * rmc[p];
+    st8(qt, gT + 4 * cs, nv, cv[0], cv[1]);
+  }
+}
+
+}  // namespace b200

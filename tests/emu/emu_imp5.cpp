@@ -152,3 +152,26 @@ extern "C" __attribute__((visibility("default"))) int emu_ldiv8(int nh, int nv, 
   else run_grid(nh, [&] { k8_imp_stage<FT, 0, true>(P, hgeo, &V, Yc, Yf, dYc, dYf, (FT)sc[10], Rc, Rf); });
   return 0;
 }
+
+// k8_t_imp / k8_t_post_imp (kernels_imp8.cuh): T_imp! and T_post_imp! of the hook path in the warp-per-column-pair layout; sc as emu_imp5
+extern "C" __attribute__((visibility("default"))) int emu_hooks8(int nh, int nv, const double* sc, const double* vl, const double* hgeo,
+                                                                 const double* Yc, const double* Yf, double* Ytc, double* Ytf, double* Ypc, double* Ypf) {
+  Par<FT> P;
+  memset(&P, 0, sizeof(P));
+  P.R_d = sc[0]; P.cp_d = sc[1]; P.cv_d = sc[2]; P.T_0 = sc[3]; P.p0 = sc[4]; P.kappa = sc[0] / sc[1]; P.Ts_ref = sc[5];
+  P.Tmin_ref = sc[6]; P.T_min_sgs = sc[7]; P.dt = sc[8]; P.icv = 1.0 / sc[2]; P.ip0 = 1.0 / sc[4]; P.dTs7 = (sc[5] - sc[6]) / 7.0;
+  P.RT0 = sc[0] * sc[3]; P.nh = nh; P.nv = nv; P.ncf = (int)sc[12]; P.rayleigh = (int)sc[9]; P.upwinding = (int)sc[11];
+  static VLev<FT> V;
+  memset(&V, 0, sizeof(V));
+  FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
+  for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
+  emu_apply_moist(P, sc[3]);
+  if (g_moist_on) {
+    run_grid(nh, [&] { k8_t_imp<FT, 0, true>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+    run_grid(nh, [&] { k8_t_post_imp<FT, 0, true>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  } else {
+    run_grid(nh, [&] { k8_t_imp<FT, 0>(P, hgeo, &V, Yc, Yf, Ytc, Ytf); });
+    run_grid(nh, [&] { k8_t_post_imp<FT, 0>(P, hgeo, &V, Yc, Yf, Ypc, Ypf); });
+  }
+  return 0;
+}

@@ -435,6 +435,18 @@ def test_emulated_default_fused_implicit_stage_matches_oracle(emu5, upw, rayleig
     for k in range(ncf):
         assert rel(dYc[:, k], dc[:, k]) < 1e-11, ("ldiv8", k, rel(dYc[:, k], dc[:, k]))
     assert rel(dYf, df) < 1e-11, ("ldiv8 u3", rel(dYf, df))
+    # T_imp! and T_post_imp! of the hook path in the same layout (k8_t_imp, k8_t_post_imp)
+    Ytc, Ytf, Ypc, Ypf = np.full_like(Yc, 7.0), np.full_like(Yf, 7.0), np.full_like(Yc, 7.0), np.full_like(Yf, 7.0)
+    assert emu5.emu_hooks8(nh, nv, p(sc), p(vl), p(hgeo), p(Yc), p(Yf0), p(Ytc), p(Ytf), p(Ypc), p(Ypf)) == 0
+    tc, tf = o.implicit_tendency(Yc, Yf0, pc)
+    for k in (0, 3):
+        assert rel(Ytc[:, k], tc[:, k]) < 1e-11, ("k8_t_imp", k, rel(Ytc[:, k], tc[:, k]))
+    assert np.abs(Ytc[:, 1:3]).max() == 0 and not np.any(Ytc[:, 4:])
+    assert rel(Ytf, tf) < 1e-9, ("k8_t_imp u3", rel(Ytf, tf))
+    if upw != "none":
+        qc, qf = o.correct_implicit_advection_tendency(Yc, Yf0, pc)
+        assert rel(Ypc[:, 3], qc[:, 3]) < 1e-10, ("k8_t_post_imp", rel(Ypc[:, 3], qc[:, 3]))
+        assert np.abs(Ypc[:, :3]).max() == 0 and not np.any(Ypc[:, 4:]) and np.abs(Ypf).max() == 0
 
 
 @pytest.fixture(scope="module")
