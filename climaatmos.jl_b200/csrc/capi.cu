@@ -35,6 +35,9 @@ static int fail(const std::string& m) {
   if (g_cur) ctx_set_err(g_cur, m);
   return -1;
 }
+// A halo wait of an earlier call timed out (a peer rank died or fell out of step): the state is invalid; say so instead of computing on.
+struct b200_ctx;
+static int halo_failed(const b200_ctx* c, const char* who);
 struct CtxScope {
   b200_ctx* prev;
   explicit CtxScope(b200_ctx* c) : prev(g_cur) { g_cur = c; }
@@ -131,6 +134,7 @@ struct b200_ctx {
   void* p2p_buf = nullptr;      // [2 parities][p2p_cap bytes] ghost slabs written by the neighbours, then int flags[nranks]
   size_t p2p_cap = 0;
   bool p2p_ready = false;
+  int* h_p2p_err = nullptr;     // host-mapped error word written by a halo wait that timed out (kernels_dss.cuh: g_p2p_err)
   int* d_p2p_seq = nullptr;     // device-side exchange number, followed by the pack-kernel completion counter (kernels_dss.cuh: P2PSig)
   int n_int_nodes = 0;          // records [0, n_int_nodes) have no ghost member (sorted first)
   std::vector<void*> p2p_peer;  // mapped neighbour buffers
@@ -462,6 +466,13 @@ static int set_attrs() {
   return 0;
 }
 
+static int halo_failed(const b200_ctx* c, const char* who) {
+  if (!c->h_p2p_err) return 0;
+  const int e = *reinterpret_cast<volatile int*>(c->h_p2p_err);
+  if (!e) return 0;
+  return fail(std::string(who) + ": the DSS halo timed out earlier (neighbour rank " + std::to_string((e & 0xff) - 1) + " never signalled exchange " +
+              std::to_string(e >> 8) + "): a peer rank died or fell out of step; the state of this context is invalid");
+}
 extern "C" int b200_destroy(b200_ctx* c);
 static int create_body(b200_ctx* c, const b200_dims* d, const b200_geometry* G, const b200_topology* T, const b200_params* p,
                        const void* nccl_id, int rank, int nranks) {
@@ -613,6 +624,7 @@ extern "C" int b200_destroy(b200_ctx* c) {
   if (c->gstream) { cudaStreamDestroy(c->gstream); cudaEventDestroy(c->ev_gin); cudaEventDestroy(c->ev_gout); }
   if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->comm) g_nccl.CommDestroy(c->comm);
+  if (c->h_p2p_err) cudaFreeHost(c->h_p2p_err);
   delete c;
   return 0;
 }
@@ -888,6 +900,14 @@ extern "C" int b200_halo_import(b200_ctx* c, const void* handles, const int32_t*
   CK(cudaMemcpy(c->d_p2p_dst, dst.data(), 2 * nn * sizeof(void*), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(int)));
   CK(cudaMemset(c->d_p2p_seq, 0, 2 * sizeof(int)));
+  {  // error word of the halo waits: host-mapped, so a timeout is visible to the host without a device synchronisation
+    if (!c->h_p2p_err) CK(cudaHostAlloc((void**)&c->h_p2p_err, sizeof(int), cudaHostAllocMapped));
+    *c->h_p2p_err = 0;
+    int* dptr = nullptr;
+    CK(cudaHostGetDevicePointer((void**)&dptr, c->h_p2p_err, 0));
+    CK(cudaMemcpyToSymbol(g_p2p_err, &dptr, sizeof(dptr)));
+    if (const char* e = getenv("B200_P2P_SPIN_LIMIT")) { long long lim = atoll(e); CK(cudaMemcpyToSymbol(g_p2p_spin, &lim, sizeof(lim))); }
+  }
   c->p2p_ready = true;
   return 0;
 }
@@ -1061,6 +1081,7 @@ extern "C" int b200_dss(b200_ctx* c, void* const* fields, const int32_t* nf, con
                         int32_t nfields, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_dss: null context");
+  if (halo_failed(c, "b200_dss")) return -1;
   if (nfields > 8) return fail("b200_dss: at most 8 fields per call");
   DssField F[8];
   for (int k = 0; k < nfields; ++k) F[k] = {fields[k], nf[k], is_face[k], kind[k]};
@@ -1160,6 +1181,7 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
 extern "C" int b200_t_exp_phase(b200_ctx* c, int32_t phase, void* Ytc, void* Ytf, const void* Yc, const void* Yf, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_t_exp_phase: null context");
+  if (halo_failed(c, "b200_t_exp_phase")) return -1;
   return c->ft == 4 ? impl_t_exp_phase<float>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream)
                     : impl_t_exp_phase<double>(c, phase, Ytc, Ytf, Yc, Yf, (cudaStream_t)stream);
 }
@@ -1177,6 +1199,7 @@ extern "C" int b200_t_exp_lim(b200_ctx* c, void* Ytc, void* Ytf, void* Ylc, void
                               void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_t_exp_lim: null context");
+  if (halo_failed(c, "b200_t_exp_lim")) return -1;
   return c->ft == 4 ? impl_t_exp<float>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream)
                     : impl_t_exp<double>(c, Ytc, Ytf, Ylc, Ylf, Yc, Yf, (cudaStream_t)stream);
 }
@@ -1255,6 +1278,7 @@ static int impl_lim(b200_ctx* c, void* Yc, const void* refc, cudaStream_t s) {
 extern "C" int b200_lim(b200_ctx* c, void* Yc, void* Yf, const void* ref_Yc, const void* ref_Yf, double, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_lim: null context");
+  if (halo_failed(c, "b200_lim")) return -1;
   (void)Yf; (void)ref_Yf;
   return c->ft == 4 ? impl_lim<float>(c, Yc, ref_Yc, (cudaStream_t)stream) : impl_lim<double>(c, Yc, ref_Yc, (cudaStream_t)stream);
 }
@@ -1557,6 +1581,7 @@ static int impl_step(b200_ctx* c, void* Yc, void* Yf, int fused, cudaStream_t s)
 extern "C" int b200_step_ars343(b200_ctx* c, void* Yc, void* Yf, double, int32_t fused, void* stream) {
   CtxScope scope_(c);
   if (!c) return fail("b200_step_ars343: null context");
+  if (halo_failed(c, "b200_step_ars343")) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   auto run = [&](cudaStream_t q) { return c->ft == 4 ? impl_step<float>(c, Yc, Yf, fused, q) : impl_step<double>(c, Yc, Yf, fused, q); };
   // One CUDA graph per state buffer: ≈35 kernel launches, the side-stream fork/join and the memsets replay as one launch.

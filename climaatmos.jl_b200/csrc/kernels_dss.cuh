@@ -35,9 +35,17 @@ struct DssArgs {
 
 // wait (inside a consumer kernel) until every neighbour has raised its flag to the current exchange number: thread 0 of the
 // block polls the flags in my own memory, the block then proceeds
-// a rank that waits longer than this many SM clocks (≈ 30 s) for a neighbour traps instead of hanging the GPU: the error then
-// surfaces on the host at the next CUDA call
-constexpr long long P2P_SPIN_LIMIT = 60000000000ll;
+// A rank that waits longer than g_p2p_spin SM clocks (≈ 30 s by default) for a neighbour neither hangs the GPU nor traps (a trap
+// would destroy the CUDA context): it records (neighbour rank + 1) | exchange number << 8 in the context's host-mapped error word and
+// goes on with whatever the ghost block holds; every C-ABI entry point that uses the halo checks that word first and returns an
+// error code with a message (capi.cu: halo_failed) — the state is invalid from then on, the process is not.
+__device__ int* g_p2p_err = nullptr;               // host-mapped error word (set by b200_halo_import), 0 = ok
+__device__ long long g_p2p_spin = 60000000000ll;   // B200_P2P_SPIN_LIMIT overrides (tests)
+__device__ __forceinline__ bool p2p_timed_out(long long t0, int nbr, int value) {
+  if (clock64() - t0 <= g_p2p_spin) return false;
+  if (g_p2p_err) { *reinterpret_cast<volatile int*>(g_p2p_err) = (nbr + 1) | (value << 8); __threadfence_system(); }
+  return true;
+}
 struct P2PWait { const int* flags; const int* nbr_rank; const int* seq; int nn; };
 __device__ __forceinline__ void p2p_block_wait(const P2PWait& W) {
   if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -47,7 +55,7 @@ __device__ __forceinline__ void p2p_block_wait(const P2PWait& W) {
       const volatile int* f = W.flags + W.nbr_rank[q];
       while (*f < value) {
         __nanosleep(40);
-        if (clock64() - t0 > P2P_SPIN_LIMIT) { printf("b200 halo: neighbour %d never signalled exchange %d\n", W.nbr_rank[q], value); __trap(); }
+        if (p2p_timed_out(t0, W.nbr_rank[q], value)) break;
       }
     }
     __threadfence_system();
@@ -227,7 +235,7 @@ __global__ void k_p2p_wait(const int* __restrict__ flags, const int* __restrict_
     const long long t0 = clock64();
     while (*f < value) {
       __nanosleep(50);
-      if (clock64() - t0 > P2P_SPIN_LIMIT) { printf("b200 halo: neighbour %d never signalled exchange %d\n", nbr_rank[q], value); __trap(); }
+      if (p2p_timed_out(t0, nbr_rank[q], value)) break;
     }
     __threadfence_system();
   }

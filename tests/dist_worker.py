@@ -112,8 +112,43 @@ def nccl_step(tracers=False):
         sys.exit(3)
 
 
+def halo_timeout():
+    """Two ranks; after two common steps rank 1 stops stepping while rank 0 steps on.  Rank 0's halo wait must time out (the spin limit is
+    shortened through B200_P2P_SPIN_LIMIT), the process and its CUDA context must survive, and the NEXT call on rank 0 must return an error
+    code with a message naming the neighbour — not a trap, not a hang."""
+    import torch
+    from climaatmos_jl_b200 import dycore, params as prm
+    from climaatmos_jl_b200.parallel import DistributedComms
+
+    os.environ["B200_P2P_SPIN_LIMIT"] = "400000000"  # ≈ 0.2 s of SM clocks
+    comms = DistributedComms()
+    P = prm.DycoreParams(zd_rayleigh=20000.0, zd_viscous=20000.0)
+    sim = dycore.AtmosSimulation(comms=comms, FT=np.float32, h_elem=4, z_elem=15, z_max=30000.0, dz_bottom=300.0, dt=300.0, params=P)
+    assert getattr(sim, "peer_halo", False), "needs the peer-memory halo"
+    for _ in range(2):
+        sim.step(True)
+    torch.cuda.synchronize()
+    comms.barrier()
+    msg = ""
+    if comms.rank == 0:
+        sim.step(True)  # the neighbour never arrives: every halo wait of this step times out, the kernels run on
+        torch.cuda.synchronize()  # the context is alive (a trap would raise here)
+        try:
+            sim.step(True)
+        except RuntimeError as e:
+            msg = str(e)
+        ok = "halo timed out" in msg and "neighbour rank 1" in msg
+        x = torch.ones(4, device="cuda").sum().item()  # CUDA still works in this process
+        print(f"rank 0: timeout_reported={ok and x == 4.0} message={msg[:160]!r}", flush=True)
+    comms.barrier()
+    comms.finalize()
+    os._exit(0)  # the contexts hold peer mappings of a rank that is out of step: skip the orderly teardown
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "nccl-step":
+    if sys.argv[1] == "halo-timeout":
+        halo_timeout()
+    elif sys.argv[1] == "nccl-step":
         nccl_step()
     elif sys.argv[1] == "nccl-step-tracer-limiter":
         nccl_step(tracers=True)
