@@ -13,6 +13,10 @@
  *     i.e. C order [h][f][j][i][v].  Y.c: Nf = 4 (ρ, uₕ₁, uₕ₂, ρe_tot), Nv levels;
  *     Y.f: Nf = 1 (u₃), Nv+1 levels.  Nq = 4 only.
  *   - there is NO CPU fallback: every compute entry point requires a CUDA device.
+ *   - multi-rank contexts: a DSS halo wait that times out (a peer rank died or fell out of step; ~30 s of SM clocks,
+ *     B200_P2P_SPIN_LIMIT overrides) does not trap and does not hang: the kernels run on, the context records the event in a
+ *     host-mapped word, and the NEXT entry point that uses the halo (b200_dss, b200_t_exp_lim, b200_lim, b200_step_ars343) returns
+ *     <0 with a message naming the neighbour rank; the state of that context is invalid from then on, the process is not.
  *
  * Limits (checked by b200_create, which fails with a message instead of computing something else):
  *   Nq = 4 (nh_poly 3); 2 <= nv <= 63 (a column of faces is one 64-lane row of the kernels); flat grid (NoWarp topography: the
