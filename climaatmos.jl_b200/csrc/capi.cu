@@ -21,7 +21,6 @@
 #include "kernels_imp5.cuh"
 #include "kernels_limiter.cuh"
 #include "kernels_vdiff.cuh"
-#include "kernels_imp5d.cuh"
 #include "kernels_imp8.cuh"
 #include "kernels_imp8d.cuh"
 
@@ -461,8 +460,6 @@ static int set_attrs() {
   CK(cudaFuncSetAttribute(k_vdiff_jac<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slabs<FT>(14)));
   CK(cudaFuncSetAttribute(k_ldiv_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((22 * SLAB + LV) * sizeof(FT))));
   CK(cudaFuncSetAttribute(k_imp_stage_diff<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QD_PROFILES * 4 * LVP * sizeof(FT))));
-  CK(cudaFuncSetAttribute(k5_imp_stage_diff<FT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5d<FT>()));
-  CK(cudaFuncSetAttribute(k5_imp_stage_diff<FT, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_imp5d<FT>()));
   return 0;
 }
 
@@ -1345,24 +1342,18 @@ template <class FT>
 static int impl_imp_stage(b200_ctx* c, void* Nc, void* Nf, const void* Uc, const void* Uf, double dtg, cudaStream_t s) {
   const size_t bc = c->nc() * sizeof(FT), bf = c->nf() * sizeof(FT);
   if (vdiff_implicit(c)) {  // implicit vertical diffusion: the fused stage with the diffusion blocks and the approximate arrowhead iteration
-    // default: warp per column pair, in-warp tridiagonal solves (kernels_imp8d.cuh).  A/B switches: B200_VDIFF_STAGE=5 the packed
-    // shared-memory layout with block-wide PCR (kernels_imp5d.cuh), =1 the one-point-per-thread k_imp_stage_diff
+    // warp per column pair, in-warp tridiagonal solves (kernels_imp8d.cuh); B200_VDIFF_STAGE=1 selects the one-point-per-thread
+    // k_imp_stage_diff (the first generation, kept as the Float32-emulatable reference of the CPU tests).  The intermediate packed
+    // shared-memory version (block-wide PCR, 3.24 ms/step) was removed once its A/B record was in profiles/.
     static const int stage_sel = getenv("B200_VDIFF_STAGE") ? atoi(getenv("B200_VDIFF_STAGE")) : 8;
-    const bool scalar_stage = stage_sel == 1;
-    if (stage_sel == 8 && c->dims.nv == 63 && !c->generic_nv)
-      launchx(c->pdl & 16, k8_imp_stage_diff<FT, 63>, c->dims.nh, 256, 0, s, make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-              (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
-    else if (stage_sel == 8)
-      launchx(c->pdl & 16, k8_imp_stage_diff<FT, 0>, c->dims.nh, 256, 0, s, make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
-              (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
-    else if (scalar_stage)
+    if (stage_sel == 1)
       k_imp_stage_diff<FT><<<c->dims.nh * 4, NT, (size_t)QD_PROFILES * 4 * LVP * sizeof(FT), s>>>(
           make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
     else if (c->dims.nv == 63 && !c->generic_nv)
-      launchx(c->pdl & 16, k5_imp_stage_diff<FT, 63>, c->dims.nh, 256, smem_imp5d<FT>(), s, make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+      launchx(c->pdl & 16, k8_imp_stage_diff<FT, 63>, c->dims.nh, 256, 0, s, make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
               (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
     else
-      launchx(c->pdl & 16, k5_imp_stage_diff<FT, 0>, c->dims.nh, 256, smem_imp5d<FT>(), s, make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
+      launchx(c->pdl & 16, k8_imp_stage_diff<FT, 0>, c->dims.nh, 256, 0, s, make_par<FT>(c), make_vdiff<FT>(c), (const FT*)c->d_hgeo,
               (const VLev<FT>*)c->d_vlev, (const FT*)Uc, (const FT*)Uf, (FT*)Nc, (FT*)Nf, (FT)dtg);
     LAUNCH_CHECK(c);
     return 0;

@@ -1,12 +1,12 @@
 // kernels_imp8d.cuh — fused implicit stage WITH implicit vertical diffusion in the warp-per-column-pair layout of kernels_imp8.cuh.
 //
-// Same algebra as k5_imp_stage_diff / k_imp_stage_diff (cache_imp! → Wfact incl. update_diffusion_jacobian! → R = dtγ·T_imp(U) incl. the
+// Same algebra as k_imp_stage_diff (kernels_vdiff.cuh; cache_imp! → Wfact incl. update_diffusion_jacobian! → R = dtγ·T_imp(U) incl. the
 // diffusion tendency → ldiv! = ApproximateBlockArrowheadIterativeSolve → N = U − ΔU → cache_imp! → T_post_imp!; reference:
 // implicit_tendency.jl:36-98,185-339, vertical_diffusion_boundary_layer.jl:64-154, manual_sparse_jacobian.jl:713-870,1031-1261,538-578).
 // Every tridiagonal system — (uₕ,uₕ) with two right-hand sides, A_ee = (ρe_tot,ρe_tot) (1 + n_iters + 1 solves), the preconditioner
 // P of the Schur complement (1 + n_iters solves), the passive-tracer blocks — is solved inside the warp by warp_tridiag_n: no shared
-// memory and no block barrier.  (The shared-memory version k5_imp_stage_diff needs 68 block barriers and is bound by the LDS/STS
-// traffic of its PCR steps: ≈ 600 µs per launch at he30/ze63.)
+// memory and no block barrier.  (An intermediate version in the packed shared-memory layout of k5_imp_stage — block-wide PCR, 68 block
+// barriers, bound by the LDS/STS traffic of its PCR steps — measured ≈ 600 µs per launch at he30/ze63 and was removed; this one ≈ 310 µs.)
 #pragma once
 #include "kernels_imp8.cuh"
 #include "kernels_vdiff.cuh"

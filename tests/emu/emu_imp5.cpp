@@ -33,7 +33,6 @@ inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 // the inline PTX statements of common.cuh assemble to nothing
 __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
 #include "kernels_imp5.cuh"
-#include "kernels_imp5d.cuh"
 #include "kernels_imp8.cuh"
 #include "kernels_imp8d.cuh"
 
@@ -95,7 +94,7 @@ extern "C" __attribute__((visibility("default"))) int emu_ldiv5(int nh, int nv, 
   return 0;
 }
 
-// k5_imp_stage_diff (kernels_imp5d.cuh): the fused implicit stage with implicit vertical diffusion in the packed row layout.
+// k8_imp_stage_diff (kernels_imp8d.cuh): the fused implicit stage with implicit vertical diffusion, warp per column pair.
 // sc as emu_imp5 plus sc[13] = diffusion mode (1 | 2), sc[14] = momentum diffusion, sc[15] = n_iters, sc[16] = C_E·Δz₁/2; kdec [64]
 extern "C" __attribute__((visibility("default"))) int emu_imp5d(int nh, int nv, const double* sc, const double* vl, const double* hgeo, const double* kdec,
                                                                 const double* Uc, const double* Uf, double* Nc, double* Nf) {
@@ -111,9 +110,7 @@ extern "C" __attribute__((visibility("default"))) int emu_imp5d(int nh, int nv, 
   memset(&V, 0, sizeof(V));
   FT* dst[11] = {V.sc2i, V.sf2i, V.sf, V.dzc, V.dzf, V.mc, V.rmc, V.g33f, V.phic, V.dphif, V.brw};
   for (int a = 0; a < 11; ++a) memcpy(dst[a], vl + a * 64, 64 * sizeof(FT));
-  // sc[17] = 8: the warp-per-column-pair version (kernels_imp8d.cuh)
-  if ((int)sc[17] == 8) run_grid(nh, [&] { k8_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
-  else run_grid(nh, [&] { k5_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
+  run_grid(nh, [&] { k8_imp_stage_diff<FT, 0>(P, D, hgeo, &V, Uc, Uf, Nc, Nf, (FT)sc[10]); });
   return 0;
 }
 

@@ -274,10 +274,10 @@ def test_emulated_fused_implicit_diffusion_stage_matches_oracle(emu, emu5, vd, d
         assert rel(Nc[:, k], Uc[:, k]) < 1e-12, (k, rel(Nc[:, k], Uc[:, k]))
         assert rel(Nc[:, k] - Yc[:, k], Uc[:, k] - Yc[:, k]) < 1e-8 or np.abs(Uc[:, k] - Yc[:, k]).max() == 0, ("increment", k)
     assert rel(Nf, Uf) < 1e-10
-    # the packed-row-layout version of the same stage (k5_imp_stage_diff, kernels_imp5d.cuh: what b200_implicit_stage launches)
+    # the warp-per-column-pair version of the same stage (k8_imp_stage_diff, kernels_imp8d.cuh: what b200_implicit_stage launches)
     sc5 = np.array([P.R_d, P.cp_d, P.cv_d, P.T_0, P.p_ref_theta, P.T_surf_ref, P.T_min_ref, P.T_min_sgs, N.dt, float(rayleigh), dtg,
                     {"none": 0, "first_order": 1, "third_order": 2, "vanleer_limiter": 3}[upw], ncf, mode, 0 if dm else 1, iters, P.C_E * g.dz_c[0] / 2, 5])
-    for layout in (5, 8):  # 8: the warp-per-column-pair version k8_imp_stage_diff (kernels_imp8d.cuh), the default of b200_implicit_stage
+    for layout in (8,):
         sc5[17] = layout
         N5c, N5f = np.zeros_like(Yc), np.zeros_like(Yf)
         assert emu5.emu_imp5d(nh, nv, p(sc5), p(vl), p(hgeo), p(kdec), p(Yc), p(Yf), p(N5c), p(N5f)) == 0
