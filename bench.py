@@ -202,15 +202,22 @@ def workload_name(w):
 
 def pin_to_gpu_numa_node(local_rank):
     """Run this rank (and first-touch its pinned staging buffers) on the NUMA node its GPU hangs off, so that the e2e copies of the
-    ranks of one box do not all stage through one socket's memory.  Best effort: any failure leaves the affinity untouched."""
+    ranks of one box do not all stage through one socket's memory.  Best effort: any failure leaves the affinity untouched.
+    Returns (node or None, one-line diagnosis) — the diagnosis goes into the e2e object so that a box that hides its topology
+    (a VM reporting numa_node = -1 or a single node) is visible in the bench line."""
     try:
+        import glob
         import torch
 
+        nodes = len(glob.glob("/sys/devices/system/node/node[0-9]*"))
         pr = torch.cuda.get_device_properties(local_rank)
         bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
-        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+        if not os.path.exists(path):
+            return None, f"{nodes} NUMA node(s) visible; {path} missing"
+        node = int(open(path).read())
         if node < 0:
-            return None
+            return None, f"{nodes} NUMA node(s) visible; GPU {bdf} reports numa_node = {node} (topology hidden)"
         cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
         ids = set()
         for part in cpus.split(","):
@@ -219,10 +226,10 @@ def pin_to_gpu_numa_node(local_rank):
         ids &= os.sched_getaffinity(0)
         if ids:
             os.sched_setaffinity(0, ids)
-            return node
-    except Exception:
-        return None
-    return None
+            return node, f"{nodes} NUMA node(s) visible; rank pinned to node {node} ({len(ids)} cpus)"
+        return None, f"{nodes} NUMA node(s) visible; node {node} has no cpu in this process's affinity mask"
+    except Exception as ex:  # noqa: BLE001
+        return None, f"probe failed: {type(ex).__name__}: {ex}"
 
 
 def multi_gpu_check(comms):
@@ -342,7 +349,7 @@ def main():
     # k+1 and the copy-out of step k-1 overlap the compute of step k (PCIe is full duplex).  With two buffers each buffer's
     # cycle copy-out → copy-in → compute is serial and bounds the step at (D2H + H2D + compute)/2 = 3.03 ms; the third
     # buffer lets the three legs run concurrently (round 2).
-    numa_node = pin_to_gpu_numa_node(comms.local_rank) if nranks > 1 else None
+    numa_node, numa_diag = pin_to_gpu_numa_node(comms.local_rank) if nranks > 1 else (None, "single rank: not pinned")
     FieldVector = dycore.FieldVector
     NB = 3
     dev = [sim.Y] + [sim.Y.clone() for _ in range(NB - 1)]
@@ -473,7 +480,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": sy(ms_e2e) * eq, "unit": "SYPD", "sypd_raw": sy(ms_e2e), "ms_per_step": ms_e2e, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "pipeline": "3 streams (copy-in / step / copy-out) over 3 state buffers; pinned staging buffers first-touched on the GPU's NUMA node",
-                    "numa_node": numa_node, "finite": e2e_ok, "timed_blocks": len(e2e_blocks)},
+                    "numa_node": numa_node, "numa_diag": numa_diag, "finite": e2e_ok, "timed_blocks": len(e2e_blocks)},
             "roofline": {"bound": "hbm", "kernel": f"{dom['kernel']} ({dom['what']}; the largest share of the step)",
                          "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                          "traffic": traffic * nh_local / 5400.0 if traffic else None, "traffic_source": TRAFFIC_SOURCE if traffic else None,
