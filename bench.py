@@ -364,7 +364,7 @@ def main():
     ev_in = [torch.cuda.Event() for _ in range(NB)]
     ev_cmp = [torch.cuda.Event() for _ in range(NB)]
     ev_out = [torch.cuda.Event() for _ in range(NB)]
-    state = {"k": 0}
+    state = {"k": 0, "compute": True}
 
     def upload(k):
         b = k % NB
@@ -382,7 +382,8 @@ def main():
         upload(k + 1)  # prefetch the next step's input while this step computes
         s_cmp.wait_event(ev_in[b])
         sim.Y = dev[b]
-        sim.step(fused)
+        if state["compute"]:
+            sim.step(fused)
         ev_cmp[b].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[b])
@@ -404,6 +405,11 @@ def main():
     ms_e2e = float(np.median(e2e_blocks))
     torch.cuda.synchronize()
     e2e_ok = bool(torch.isfinite(h_out[0][0]).all().item())
+    # the same pipeline with the step left out (all ranks at once): what the box's host <-> device path alone allows
+    state["compute"] = False
+    copy_blocks = [timed(Ke, e2e_step, tail=lambda: [s_cmp.wait_event(e) for e in ev_out])[0] for _ in range(3)]
+    state["compute"] = True
+    ms_copies = float(np.median(copy_blocks))
     state_bytes = int(h_in[0][0].numel() * 4 + h_in[0][1].numel() * 4)
     sim.Y = dev[0]
 
@@ -480,7 +486,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": sy(ms_e2e) * eq, "unit": "SYPD", "sypd_raw": sy(ms_e2e), "ms_per_step": ms_e2e, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
                     "pipeline": "3 streams (copy-in / step / copy-out) over 3 state buffers; pinned staging buffers first-touched on the GPU's NUMA node",
-                    "numa_node": numa_node, "numa_diag": numa_diag, "finite": e2e_ok, "timed_blocks": len(e2e_blocks)},
+                    "copies_only_ms_per_step": ms_copies, "numa_node": numa_node, "numa_diag": numa_diag, "finite": e2e_ok, "timed_blocks": len(e2e_blocks)},
             "roofline": {"bound": "hbm", "kernel": f"{dom['kernel']} ({dom['what']}; the largest share of the step)",
                          "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                          "traffic": traffic * nh_local / 5400.0 if traffic else None, "traffic_source": TRAFFIC_SOURCE if traffic else None,
