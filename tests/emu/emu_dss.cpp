@@ -1,12 +1,10 @@
 // CPU emulation of the weighted-DSS kernel of the benchmarked step, k_dss2 (kernels_dss.cuh; Float64 instantiation, single-rank path),
 // from its unchanged source, with the node records built like capi.cu:create_geo builds them.  Test infrastructure only.
-#include <thread>
 #include <vector>
 #define b200 b200_emud
 #include "cuda_runtime.h"
 thread_local uint3_emu threadIdx, blockIdx;
-std::barrier<>* g_cta_barrier = nullptr;
-// static __shared__ arrays of these kernels: one instance per kernel instantiation, shared by the 256 host threads of the emulated CTA
+// static __shared__ arrays of these kernels: one instance per kernel instantiation, shared by the 256 fibers of the emulated CTA
 #undef __shared__
 #define __shared__ static
 struct dim3_emu { unsigned x, y, z; };
@@ -24,6 +22,7 @@ __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.w
 
 using namespace b200;
 typedef double FT;
+static uint3_emu tid64x4(int t) { return uint3_emu{(unsigned)(t & 63), (unsigned)(t >> 6), 0}; }  // blockDim = (64, 4)
 
 // state DSS (ρ, (uₕ₁,uₕ₂) as a Covariant12 pair, ρe_tot, u₃): off/mem = CSR of the unique perimeter nodes (mem = elem·16 + node),
 // hgeo [nh][HG_N][16] with HG_DSSW, HG_A**, HG_AI** filled
@@ -53,19 +52,11 @@ extern "C" __attribute__((visibility("default"))) int emu_dss_state(int nh, int 
   A.it[3] = DssItem{Yf, nullptr, nullptr, nullptr, nv + 1, 16 * (nv + 1), 0};
   P2PWait W{nullptr, nullptr, nullptr, 0};
   const int nblocks = (nnodes + 3) / 4;
-  std::barrier<> bar(256);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < 256; ++t)
-    th.emplace_back([&, t] {
-      for (int b = 0; b < nblocks; ++b) {
-        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
-        blockIdx = {(unsigned)b, 0, 0};
-        k_dss2<FT, 4, 0x2, false, false>(A, rec.data(), 0, nnodes, nh, W);
-        bar.arrive_and_wait();
-      }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = [&] { k_dss2<FT, 4, 0x2, false, false>(A, rec.data(), 0, nnodes, nh, W); };
+  for (int b = 0; b < nblocks; ++b) {
+    blockIdx = {(unsigned)b, 0, 0};
+    emu::run_cta(256, tid64x4, fn);
+  }
   return 0;
 }
 
@@ -103,19 +94,11 @@ extern "C" __attribute__((visibility("default"))) int emu_axpy_dss3(int nh, int 
   A.dmask = dmask; A.ncf = ncf; A.nv = nv; A.nh = nh;
   P2PWait W{nullptr, nullptr, nullptr, 0};
   const int nbn = (nnodes + 3) / 4, nint = nh, nblocks = nbn + nint;
-  std::barrier<> bar(256);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < 256; ++t)
-    th.emplace_back([&, t] {
-      for (int b = 0; b < nblocks; ++b) {
-        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
-        blockIdx = {(unsigned)b, 0, 0};
-        k_axpy_dss<FT, 3, false, false>(A, rec.data(), 0, nnodes, nbn, nint, W);
-        bar.arrive_and_wait();
-      }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = [&] { k_axpy_dss<FT, 3, false, false>(A, rec.data(), 0, nnodes, nbn, nint, W); };
+  for (int b = 0; b < nblocks; ++b) {
+    blockIdx = {(unsigned)b, 0, 0};
+    emu::run_cta(256, tid64x4, fn);
+  }
   return 0;
 }
 
@@ -133,19 +116,11 @@ extern "C" __attribute__((visibility("default"))) int emu_dss_h(int nh, int nv, 
   A.it[2] = DssItem{H + 3 * cs, nullptr, nullptr, nullptr, nv, ncf * cs, 0};
   P2PWait W{nullptr, nullptr, nullptr, 0};
   const int nblocks = (nnodes + 3) / 4;
-  std::barrier<> bar(256);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < 256; ++t)
-    th.emplace_back([&, t] {
-      for (int b = 0; b < nblocks; ++b) {
-        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
-        blockIdx = {(unsigned)b, 0, 0};
-        k_dss2<FT, 3, 0x1, false, false>(A, rec.data(), 0, nnodes, nh, W);
-        bar.arrive_and_wait();
-      }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = [&] { k_dss2<FT, 3, 0x1, false, false>(A, rec.data(), 0, nnodes, nh, W); };
+  for (int b = 0; b < nblocks; ++b) {
+    blockIdx = {(unsigned)b, 0, 0};
+    emu::run_cta(256, tid64x4, fn);
+  }
   return 0;
 }
 
@@ -154,19 +129,11 @@ template <int N>
 static void run_axdss(const AxDssArgs<FT>& A, const std::vector<DssNode<FT>>& rec, int nnodes, int nh) {
   P2PWait W{nullptr, nullptr, nullptr, 0};
   const int nbn = (nnodes + 3) / 4, nint = nh, nblocks = nbn + nint;
-  std::barrier<> bar(256);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < 256; ++t)
-    th.emplace_back([&, t] {
-      for (int b = 0; b < nblocks; ++b) {
-        threadIdx = {(unsigned)(t & 63), (unsigned)(t >> 6), 0};
-        blockIdx = {(unsigned)b, 0, 0};
-        k_axpy_dss<FT, N, false, false>(A, rec.data(), 0, nnodes, nbn, nint, W);
-        bar.arrive_and_wait();
-      }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = [&] { k_axpy_dss<FT, N, false, false>(A, rec.data(), 0, nnodes, nbn, nint, W); };
+  for (int b = 0; b < nblocks; ++b) {
+    blockIdx = {(unsigned)b, 0, 0};
+    emu::run_cta(256, tid64x4, fn);
+  }
 }
 extern "C" __attribute__((visibility("default"))) int emu_axpy_dss_n(int n, int nh, int nv, int ncf, int nnodes, const int* off, const int* mem,
                                                                      const double* hgeo, const double* base_c, const double* base_f,

@@ -1,43 +1,14 @@
 // CPU emulation of the explicit-tendency kernels of the benchmarked step, k5_exp_a (kernels_pair.cuh) and k7_exp_c (kernels_lvl.cuh; Float64
-// instantiations), from their unchanged source.  On top of the CTA emulator of emu_vdiff.cpp this one emulates warp shuffles: the 32
-// host threads of a warp meet at a per-warp barrier, publish their value, and read the source lane's (all shuffles of these kernels are
-// executed by full, converged warps).  griddepcontrol.* assembles to nothing; the packed-Float32 PTX is not instantiated.
+// instantiations), from their unchanged source, on the fiber CTA emulator of cuda_runtime.h with its emulated warp shuffles (the 32
+// lanes of a warp meet at a per-warp barrier, publish their value, and read the source lane's).  griddepcontrol.* assembles to nothing; the packed-Float32 PTX is not instantiated.
 // Test infrastructure only (tests/test_kernels_cpu_emulation.py).
-#include <thread>
 #include <vector>
 #define b200 b200_emux
+#define EMU_WARP_INTRINSICS
 #include "cuda_runtime.h"
 thread_local uint3_emu threadIdx, blockIdx;
-std::barrier<>* g_cta_barrier = nullptr;
 namespace b200 { alignas(128) unsigned char smem_raw[256 * 1024]; }
 #define __constant__
-struct WarpX { std::barrier<> bar{32}; alignas(16) unsigned char buf[32][16]; };
-static WarpX g_warp[8];
-template <class T> inline T shfl_emu(T v, int src_lane) {
-  WarpX& w = g_warp[threadIdx.x >> 5];
-  const int l = threadIdx.x & 31;
-  memcpy(w.buf[l], &v, sizeof(T));
-  w.bar.arrive_and_wait();
-  T r; memcpy(&r, w.buf[src_lane & 31], sizeof(T));
-  w.bar.arrive_and_wait();
-  return r;
-}
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return shfl_emu(v, (int)(threadIdx.x & 31) ^ m); }
-template <class T> inline T __shfl_sync(unsigned, T v, int src) { return shfl_emu(v, src); }
-template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return shfl_emu(v, l >= d ? l - d : l); }
-inline void __syncwarp(unsigned = 0xffffffffu) { g_warp[threadIdx.x >> 5].bar.arrive_and_wait(); }
-inline int __any_sync(unsigned, int pred) {
-  WarpX& w = g_warp[threadIdx.x >> 5];
-  const int l = threadIdx.x & 31;
-  memcpy(w.buf[l], &pred, sizeof(int));
-  w.bar.arrive_and_wait();
-  int any = 0;
-  for (int k = 0; k < 32; ++k) { int p; memcpy(&p, w.buf[k], sizeof(int)); any |= (p != 0); }
-  w.bar.arrive_and_wait();
-  return any;
-}
-inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
-inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
 #include "kernels_implicit.cuh"
 #include "kernels_row.cuh"
@@ -51,20 +22,12 @@ typedef double FT;
 
 template <class F>
 static void run_grid(int nx, int ny, F&& body) {
-  std::barrier<> bar(256);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < 256; ++t)
-    th.emplace_back([&, t] {
-      for (int y = 0; y < ny; ++y)
-        for (int b = 0; b < nx; ++b) {
-          threadIdx = {(unsigned)t, 0, 0};
-          blockIdx = {(unsigned)b, (unsigned)y, 0};
-          body();
-          bar.arrive_and_wait();
-        }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = body;
+  for (int y = 0; y < ny; ++y)
+    for (int b = 0; b < nx; ++b) {
+      blockIdx = {(unsigned)b, (unsigned)y, 0};
+      emu::run_cta(256, fn);
+    }
 }
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, ν₄ᵥ, ν₄ₛ, divergence damping factor, hyperdiff, rayleigh, viscous,

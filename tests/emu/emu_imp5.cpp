@@ -2,33 +2,14 @@
 // the second-largest kernel of the benchmarked step — with the same CTA emulator as emu_vdiff.cpp.  The kernel source is compiled
 // unchanged; griddepcontrol.* assembles to nothing (empty assembler macros), and the packed-Float32 PTX belongs to specialisations
 // that are not instantiated here.  Test infrastructure only.
-#include <thread>
 #include <vector>
 #define b200 b200_emu5
+#define EMU_WARP_INTRINSICS
 #include "cuda_runtime.h"
 thread_local uint3_emu threadIdx, blockIdx;
-std::barrier<>* g_cta_barrier = nullptr;
 namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
 #define __constant__
 #define FULL_MASK_EMU 0xffffffffu
-// warp shuffles (k8_imp_stage): the 32 host threads of a warp meet at a per-warp barrier, publish their value and read the source lane's
-struct WarpX { std::barrier<> bar{32}; alignas(16) unsigned char buf[32][16]; };
-static WarpX g_warp[8];
-template <class T> inline T shfl_emu(T v, int src_lane) {
-  WarpX& w = g_warp[threadIdx.x >> 5];
-  const int l = threadIdx.x & 31;
-  memcpy(w.buf[l], &v, sizeof(T));
-  w.bar.arrive_and_wait();
-  T r; memcpy(&r, w.buf[src_lane & 31], sizeof(T));
-  w.bar.arrive_and_wait();
-  return r;
-}
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return shfl_emu(v, (int)(threadIdx.x & 31) ^ m); }
-template <class T> inline T __shfl_sync(unsigned, T v, int src) { return shfl_emu(v, src); }
-template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return shfl_emu(v, l >= d ? l - d : l); }
-template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { const int l = threadIdx.x & 31; return shfl_emu(v, l + d < 32 ? l + d : l); }
-inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
-inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 // griddepcontrol.* (programmatic dependent launch) is a no-op for a single emulated grid: teach the assembler two empty macros so that
 // the inline PTX statements of common.cuh assemble to nothing
 __asm__(".macro griddepcontrol.launch_dependents\n.endm\n.macro griddepcontrol.wait\n.endm");
@@ -42,19 +23,11 @@ typedef double FT;
 
 template <class F>
 static void run_grid(int nblocks, F&& body) {
-  std::barrier<> bar(256);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < 256; ++t)
-    th.emplace_back([&, t] {
-      for (int b = 0; b < nblocks; ++b) {
-        threadIdx = {(unsigned)t, 0, 0};
-        blockIdx = {(unsigned)b, 0, 0};
-        body();
-        bar.arrive_and_wait();
-      }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = body;
+  for (int b = 0; b < nblocks; ++b) {
+    blockIdx = {(unsigned)b, 0, 0};
+    emu::run_cta(256, fn);
+  }
 }
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh, dtγ, energy upwinding, ncf

@@ -1,8 +1,7 @@
 // CPU emulation of single CTAs running the vertical-diffusion kernels of climaatmos.jl_b200/csrc/kernels_vdiff.cuh (and k_wfact2, whose
 // planes k_ldiv_diff consumes) — the kernel source is compiled unchanged by g++ against the stub cuda_runtime.h in this directory;
-// 256 host threads play the threads of a block.  Test infrastructure only (tests/test_kernels_cpu_emulation.py): it checks
+// the threads of a block are the fibers of the CTA emulator in cuda_runtime.h.  Test infrastructure only (tests/test_kernels_cpu_emulation.py): it checks
 // indexing, barriers-as-phases and arithmetic of the kernels against the oracle when no GPU is at hand.  It is NOT a product path.
-#include <thread>
 #include <vector>
 
 // The product library exports host stubs with the kernels' mangled names; when both are loaded in one process the dynamic linker
@@ -10,7 +9,6 @@
 #define b200 b200_emu
 #include "cuda_runtime.h"
 thread_local uint3_emu threadIdx, blockIdx;
-std::barrier<>* g_cta_barrier = nullptr;
 namespace b200 { alignas(16) unsigned char smem_raw[256 * 1024]; }
 
 #include "kernels_vdiff.cuh"
@@ -25,19 +23,11 @@ typedef EMU_FT FT;  // -DEMU_FT=float builds the Float32 instantiations (arrays 
 
 template <class F>
 static void run_grid(int nblocks, F&& body) {
-  std::barrier<> bar(NT);
-  g_cta_barrier = &bar;
-  std::vector<std::thread> th;
-  for (int t = 0; t < NT; ++t)
-    th.emplace_back([&, t] {
-      for (int b = 0; b < nblocks; ++b) {
-        threadIdx = {(unsigned)t, 0, 0};
-        blockIdx = {(unsigned)b, 0, 0};
-        body();
-        bar.arrive_and_wait();  // next block reuses the shared memory
-      }
-    });
-  for (auto& x : th) x.join();
+  const std::function<void()> fn = body;
+  for (int b = 0; b < nblocks; ++b) {  // one CTA after the other: the next block reuses the shared memory
+    blockIdx = {(unsigned)b, 0, 0};
+    emu::run_cta(NT, fn);
+  }
 }
 
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, rayleigh(0/1), mode, momentum, n_iters, C_E·Δz₁/2, dtγ, [15]-[17] unused here
@@ -70,21 +60,12 @@ extern "C" __attribute__((visibility("default"))) int emu_vborrow(int nh, int nv
   static VLev<FT> V;
   memset(&V, 0, sizeof(V));
   memcpy(V.dzc, dzc, 64 * sizeof(FT));
-  for (int t = 0; t < ncf - 4; ++t) {
-    std::barrier<> bar(NT);
-    g_cta_barrier = &bar;
-    std::vector<std::thread> th;
-    for (int k = 0; k < NT; ++k)
-      th.emplace_back([&, k] {
-        for (int b = 0; b < nh; ++b) {
-          threadIdx = {(unsigned)k, 0, 0};
-          blockIdx = {(unsigned)b, (unsigned)t, 0};
-          k_lim_vborrow<FT>(&V, Yc, ncf, nv, (FT)0);
-          bar.arrive_and_wait();
-        }
-      });
-    for (auto& x : th) x.join();
-  }
+  const std::function<void()> fn = [&] { k_lim_vborrow<FT>(&V, Yc, ncf, nv, (FT)0); };
+  for (int t = 0; t < ncf - 4; ++t)
+    for (int b = 0; b < nh; ++b) {
+      blockIdx = {(unsigned)b, (unsigned)t, 0};
+      emu::run_cta(NT, fn);
+    }
   return 0;
 }
 

@@ -1,6 +1,7 @@
 """The CUDA kernel sources of climaatmos.jl_b200/csrc, executed on the CPU: tests/emu/ compiles the kernel headers UNCHANGED with g++
-against a stub cuda_runtime.h and runs each CTA with 256 host threads — a std::barrier for __syncthreads(), per-warp barriers and an
-exchange buffer for warp shuffles / votes / __syncwarp (emu_exp5.cpp) — and the results are compared with the oracle (Float64
+against a stub cuda_runtime.h and runs each CTA as 256 cooperative fibers on one host thread — a fiber runs to its next barrier and
+yields; __syncthreads(), per-warp barriers and an exchange slot per lane for warp shuffles / votes / __syncwarp (tests/emu/cuda_runtime.h) —
+and the results are compared with the oracle (Float64
 instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k7_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_t_post_imp2; ldiv! = k5_imp_stage in LDIV mode), and
 the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
