@@ -1153,20 +1153,15 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     DssField F = {c->H, c->ncf(), 0, 1};  // (∇²u₁, ∇²u₂) pair, ∇²u₃, ∇²s_d, ∇²χ…
     if (impl_dss<FT>(c, &F, 1, s)) return -1;
   } else if (phase == 2 && hd) {
-    const dim3 g7((c->dims.nh + LVL_EPB - 1) / LVL_EPB, 3);
+    const dim3 g7((c->dims.nh + LVL_EPB - 1) / LVL_EPB, 3 + n_passive);  // parts 3..: hyperdiffusion of the passive tracers
     const size_t sm7 = LVL_EPB * 16 * sizeof(FT);
     if (nv63)
       launchx(c->pdl & 2, k7_exp_c<FT, 63>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf, (FT*)(Ylc ? Ylc : Ytc));
     else
       launchx(c->pdl & 2, k7_exp_c<FT, 0>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf);
+              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf, (FT*)(Ylc ? Ylc : Ytc));
     LAUNCH_CHECK(c);
-    if (n_passive > 0) {
-      k5_tracer_c<FT><<<dim3(c->dims.nh, n_passive), CT, smem_row<FT>(0), s>>>(
-          make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc, (const FT*)c->H, (FT*)(Ylc ? Ylc : Ytc));
-      LAUNCH_CHECK(c);
-    }
     if (moist) {  // water mass → ρq_tot and ρ of Yₜ_lim, water enthalpy flux → ρe_tot of Yₜ
       k_moist_c<FT><<<c->dims.nh, CT, smem_row<FT>(0), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
                                                           (const FT*)c->H, (const FT*)c->Hw, (FT*)Ytc, (FT*)(Ylc ? Ylc : Ytc));

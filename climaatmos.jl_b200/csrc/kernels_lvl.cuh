@@ -61,12 +61,14 @@ __device__ __forceinline__ void st16(const P2<FT> (&a)[4][2], FT* __restrict__ g
 // metric pair of component c for nodes (4j + 2p, 4j + 2p + 1), straight from global memory (warp-uniform address: one L1 transaction)
 #define HG16(c, j, p) ldpair(&hg[(c) * 16 + 4 * (j) + 2 * (p)])
 
-// blockIdx.y = part (0: ∇⁴uₕ → Yₜ.uₕ, 1: ρe_tot, 2: u₃).  One launch for the three parts: per-part launches with their own register
-// budgets (part 1 fits 64 registers, part 0 80) measured slower (74 vs 65 µs, profiles/r2_k7_exp_c.md).
+// blockIdx.y = part (0: ∇⁴uₕ → Yₜ.uₕ, 1: ρe_tot, 2: u₃, 3 + k: passive tracer k — apply_tracer_hyperdiffusion_tendency!,
+// ρχₜ_lim −= ν₄ₛ wdivₕ(ρ gradₕ ∇²χ), hyperdiffusion.jl:524-532, into Tlim = Yₜ_lim.c or Yₜ.c; the same arithmetic as part 1 on H[4 + k],
+// which replaced the row-layout kernel k5_tracer_c, 21.8 µs per tracer).  One launch for all parts: per-part launches with their own
+// register budgets (part 1 fits 64 registers, part 0 80) measured slower (74 vs 65 µs, profiles/r2_k7_exp_c.md).
 template <class FT, int NVC>
 __global__ void __launch_bounds__(LVL_EPB * 64, (sizeof(FT) == 4 ? 2 : 1))
 k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf) {
+         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ Tlim = nullptr) {
   using V = P2<FT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];  // LVL_EPB·16 values: part 2, node values of level 31 for the thread of level 32
   FT (*s_q)[16] = reinterpret_cast<FT (*)[16]>(smem_raw);     // (the two warps of an element)
@@ -78,7 +80,7 @@ k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   const int vc = v < nv ? v : nv - 1, vm = v > 0 ? v - 1 : 0;
   const FT sc = vlev->sc2i[vc], mc = vlev->mc[vc], mclo = vlev->mc[vm < nv ? vm : nv - 1];
   const FT* hg = hgeo + (size_t)(live ? e : 0) * HG_N * 16;
-  pdl_wait(Yc, H, Ytc, Ytf);
+  pdl_wait(Yc, H, Ytc, Ytf, Tlim);
   const size_t offc = (size_t)(live ? e : 0) * P.ncf * 16 * nv + v;  // (node 0, level v) of component 0
   const int cs = 16 * nv;
   if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
@@ -121,26 +123,30 @@ k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     //                                                              part 2: L = ∇²u₃,  w = J2    (hyperdiffusion.jl:277)
     V rho[4][2], Ls[4][2], g1[4][2], g2[4][2], Q1[4][2], Q2[4][2], b[4][2];
     ld16(rho, Yc + offc, nv, cv, FT(1));
-    ld16(Ls, H + offc + (part == 1 ? 3 : 2) * cs, nv, cv, FT(0));
+    // component of the scalar: 3 = ρe_tot (part 1), 2 = ∇²u₃ (part 2), first passive tracer + k (part 3 + k; a moist context keeps
+    // component 4 for the active ρq_tot, served by k_moist_c)
+    const int comp = part == 1 ? 3 : part == 2 ? 2 : 4 + (P.moist ? 1 : 0) + (part - 3);
+    ld16(Ls, H + offc + comp * cs, nv, cv, FT(0));
     deta16<FT, 0>(Ls, g2);
     dxi16<FT, 0>(Ls, g1);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        const V w_ = part == 1 ? rho[j][p] * HG16(HG_J2, j, p) : HG16(HG_J2, j, p);
+        const V w_ = part != 2 ? rho[j][p] * HG16(HG_J2, j, p) : HG16(HG_J2, j, p);
         Q1[j][p] = w_ * fma2(HG16(HG_GI12, j, p), g2[j][p], HG16(HG_GI11, j, p) * g1[j][p]);
         Q2[j][p] = w_ * fma2(HG16(HG_GI22, j, p), g2[j][p], HG16(HG_GI12, j, p) * g1[j][p]);
       }
     div16<FT, 1>(Q1, Q2, b);
-    if (part == 1) {
+    if (part != 2) {
       V old3[4][2];
-      ld16(old3, Ytc + offc + 3 * cs, nv, cv, FT(0));
+      FT* tgt = (part == 1 ? Ytc : Tlim) + offc + comp * cs;
+      ld16(old3, tgt, nv, cv, FT(0));
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int p = 0; p < 2; ++p) old3[j][p] = old3[j][p] - ((b[j][p] * sc) * HG16(HG_RJ2, j, p)) * P.nu4s;
-      if (cv) st16(old3, Ytc + offc + 3 * cs, nv);
+      if (cv) st16(old3, tgt, nv);
     } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u)): face v from the centres v − 1 and v
       V q[4][2], ql[4][2], rlo[4][2], oldf[4][2];
 #pragma unroll

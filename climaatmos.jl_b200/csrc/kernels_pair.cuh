@@ -408,7 +408,7 @@ namespace b200 {
 //                explicit vertical transport            ρχₜ += −ᶜadvdivᵥ(ᶠinterp(ρJ)/ᶠJ · U(ᶠu³, χ)) with tracer_upwinding
 //                                                       (advection.jl:249-255; implicit_tendency.jl:120-143)
 //                viscous sponge                          ρχₜ += β wdivₕ(ρ gradₕ χ)              (viscous_sponge.jl:226-231)
-//   k5_tracer_c  apply_tracer_hyperdiffusion_tendency!  ρχₜ_lim −= ν₄ₛ wdivₕ(ρ gradₕ ∇²χ)       (hyperdiffusion.jl:524-532)
+//   (apply_tracer_hyperdiffusion_tendency!, ρχₜ_lim −= ν₄ₛ wdivₕ(ρ gradₕ ∇²χ), hyperdiffusion.jl:524-532: parts 3.. of k7_exp_c, kernels_lvl.cuh)
 // With Ylc == nullptr (native stepper: lim! is a no-op) the limited part is accumulated into Yₜ as well.
 template <class FT>
 __global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 3 : 1))
@@ -517,31 +517,6 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
       st4p(out, gT, nv, j, v);
     }
   }
-}
-
-template <class FT>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
-k5_tracer_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-            const FT* __restrict__ H, FT* __restrict__ Tgt) {
-  using V = P2<FT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FT* hg = reinterpret_cast<FT*>(smem_raw);
-  B200_ROW_PROLOGUE
-  ROW_COLUMNS
-  const int q = 4 + (P.moist ? 1 : 0) + blockIdx.y;  // passive tracers (ρq_tot of a moist context: k_moist_c)
-  V rho[2], Lq[2], old[2], a[2], g1[2], Q1[2], Q2[2], b[2];
-  FT* gT = Tgt + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv;
-  ld4p(rho, Yc + (size_t)e * P.ncf * 16 * nv, nv, j, v, cv, FT(1));
-  ld4p(Lq, H + (size_t)e * P.ncf * 16 * nv + (size_t)q * 16 * nv, nv, j, v, cv, FT(0));
-  ld4p(old, gT, nv, j, v, cv, FT(0));
-  __syncthreads();
-  deta4p(Lq, md, vl, a);
-  dxi4p<FT, 0>(Lq, g1);
-  METRIC_FLUX(Q1, Q2, g1, a, rho[p] * HGP(HG_J2, p))
-  div4p<FT, 1>(Q1, Q2, mw, vl, b);
-#pragma unroll
-  for (int p = 0; p < 2; ++p) old[p] = old[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
-  if (cv) st4p(old, gT, nv, j, v);
 }
 
 // Water part of the hyperdiffusion apply for a moist (0M) context, on the DSSed ∇²q_tot_eff = H[4] (same row layout):

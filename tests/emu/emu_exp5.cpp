@@ -33,7 +33,7 @@ static void run_grid(int nx, int ny, F&& body) {
 // sc: R_d, cp_d, cv_d, T_0, p_ref_theta, T_surf_ref, T_min_ref, T_min_sgs, dt, ν₄ᵥ, ν₄ₛ, divergence damping factor, hyperdiff, rayleigh, viscous,
 //     energy upwinding, ncf, tracer upwinding ; vl: [14][64] = sc2i, sf2i, sf, dzc, dzf, mc, rmc, g33f, phic, dphif, brw, bruh, bvc, bvf ; D [16], w [4]
 // which: 0 = k5_exp_a (writes Ytc, Ytf, H), 1 = k7_exp_c (kernels_lvl.cuh: reads H, updates Ytc, Ytf; one thread per (element, level), 4 elements per CTA),
-//        2 / 3 = k5_tracer_a / k5_tracer_c
+//        2 / 3 = k5_tracer_a / the tracer parts of k7_exp_c
 extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh, int nv, const double* sc, const double* vl, const double* Dm,
                                                                const double* w, const double* hgeo, const double* Yc, const double* Yf,
                                                                double* Ytc, double* Ytf, double* H, double* Ylc) {
@@ -69,8 +69,13 @@ extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh
   else if (which == 4) run_grid(nh, 1, [&] { k_moist_c<FT>(P, hgeo, &V, Yc, H, (const FT*)g_moist_Hw, Ytc, Ylc ? Ylc : Ytc); });
   else if (which == 0) run_grid(nh, 1, [&] { k5_exp_a<FT, 0>(P, hgeo, &V, Yc, Yf, Ytc, Ytf, H); });
   else if (which == 1) run_grid((nh + LVL_EPB - 1) / LVL_EPB, 3, [&] { k7_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
-  // passive tracers (grid = elements × tracers): 2 = k5_tracer_a (Yₜ, Yₜ_lim, ∇²χ → H), 3 = k5_tracer_c (tracer hyperdiffusion → Yₜ_lim)
+  // passive tracers (grid = elements × tracers): 2 = k5_tracer_a (Yₜ, Yₜ_lim, ∇²χ → H), 3 = parts 3.. of k7_exp_c (tracer hyperdiffusion → Yₜ_lim)
   else if (which == 2) { if (ntr - g_moist_on > 0) run_grid(nh, ntr - g_moist_on, [&] { k5_tracer_a<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ylc, H); }); }
-  else if (ntr - g_moist_on > 0) run_grid(nh, ntr - g_moist_on, [&] { k5_tracer_c<FT>(P, hgeo, &V, Yc, H, Ylc); });
+  else if (ntr - g_moist_on > 0) {  // parts 3.. of k7_exp_c only (run_grid's y index is offset by the three dry parts)
+    const int nb = (nh + LVL_EPB - 1) / LVL_EPB;
+    const std::function<void()> fn = [&] { k7_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf, Ylc); };
+    for (int y = 3; y < 3 + ntr - g_moist_on; ++y)
+      for (int b = 0; b < nb; ++b) { blockIdx = {(unsigned)b, (unsigned)y, 0}; emu::run_cta(256, fn); }
+  }
   return 0;
 }

@@ -2,7 +2,7 @@
 against a stub cuda_runtime.h and runs each CTA as 256 cooperative fibers on one host thread — a fiber runs to its next barrier and
 yields; __syncthreads(), per-warp barriers and an exchange slot per lane for warp shuffles / votes / __syncwarp (tests/emu/cuda_runtime.h) —
 and the results are compared with the oracle (Float64
-instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k7_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a, k5_tracer_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_t_post_imp2; ldiv! = k5_imp_stage in LDIV mode), and
+instantiations; a Float32 build for the slab / quarter-element kernels).  Covered: k5_exp_a, k_dss2, k7_exp_c, k5_imp_stage, k_axpy_dss (every kernel of the benchmarked step), k5_tracer_a and the tracer parts of k7_exp_c, the dry hook kernels (k_cache_imp, k_t_imp2, k_wfact2, k_t_post_imp2; ldiv! = k5_imp_stage in LDIV mode), and
 the vertical-diffusion / limiter kernels of kernels_vdiff.cuh.
 
 Test infrastructure only: it checks indexing, phase structure and arithmetic of the very code that runs on the B200, not timing and
@@ -537,7 +537,7 @@ def test_emulated_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze,
                                                 ("vanleer_limiter", False, 3, 8000.0), ("third_order", True, 12, 400.0), ("third_order", False, 3, 8000.0),
                                                 ("third_order", False, 4, 6000.0)])
 def test_emulated_tracer_kernels_match_oracle(emux, tupw, sponge, ze, dzb):
-    """k5_tracer_a / k5_tracer_c (passive tracers: horizontal advection into Yₜ_lim, ∇²χ, explicit vertical transport with tracer_upwinding,
+    """k5_tracer_a / parts 3.. of k7_exp_c (passive tracers: horizontal advection into Yₜ_lim, ∇²χ, explicit vertical transport with tracer_upwinding,
     viscous sponge; tracer hyperdiffusion) on the CPU emulator against the oracle's `_tracer_pre`, `_tracer_laplacians`, `_tracer_post`."""
     P = prm.DycoreParams(zd_rayleigh=12000.0, zd_viscous=12000.0)
     g = G.make_sphere_grid(FT=np.float64, h_elem=2, z_elem=ze, z_max=30000.0, dz_bottom=dzb, radius=P.planet_radius)
