@@ -1157,16 +1157,11 @@ static int impl_t_exp_phase(b200_ctx* c, int phase, void* Ytc, void* Ytf, const 
     const size_t sm7 = LVL_EPB * 16 * sizeof(FT);
     if (nv63)
       launchx(c->pdl & 2, k7_exp_c<FT, 63>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf, (FT*)(Ylc ? Ylc : Ytc));
+              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf, (FT*)(Ylc ? Ylc : Ytc), (const FT*)c->Hw);
     else
       launchx(c->pdl & 2, k7_exp_c<FT, 0>, g7, LVL_EPB * 64, sm7, s, make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev,
-              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf, (FT*)(Ylc ? Ylc : Ytc));
+              (const FT*)Yc, (const FT*)c->H, (FT*)Ytc, (FT*)Ytf, (FT*)(Ylc ? Ylc : Ytc), (const FT*)c->Hw);
     LAUNCH_CHECK(c);
-    if (moist) {  // water mass → ρq_tot and ρ of Yₜ_lim, water enthalpy flux → ρe_tot of Yₜ
-      k_moist_c<FT><<<c->dims.nh, CT, smem_row<FT>(0), s>>>(make_par<FT>(c), (const FT*)c->d_hgeo, (const VLev<FT>*)c->d_vlev, (const FT*)Yc,
-                                                          (const FT*)c->H, (const FT*)c->Hw, (FT*)Ytc, (FT*)(Ylc ? Ylc : Ytc));
-      LAUNCH_CHECK(c);
-    }
   }
   return 0;
 }

@@ -61,14 +61,15 @@ __device__ __forceinline__ void st16(const P2<FT> (&a)[4][2], FT* __restrict__ g
 // metric pair of component c for nodes (4j + 2p, 4j + 2p + 1), straight from global memory (warp-uniform address: one L1 transaction)
 #define HG16(c, j, p) ldpair(&hg[(c) * 16 + 4 * (j) + 2 * (p)])
 
-// blockIdx.y = part (0: ∇⁴uₕ → Yₜ.uₕ, 1: ρe_tot, 2: u₃, 3 + k: passive tracer k — apply_tracer_hyperdiffusion_tendency!,
+// blockIdx.y = part (0: ∇⁴uₕ → Yₜ.uₕ, 1: ρe_tot (+ the water terms of a moist context), 2: u₃, 3 + k: passive tracer k — apply_tracer_hyperdiffusion_tendency!,
 // ρχₜ_lim −= ν₄ₛ wdivₕ(ρ gradₕ ∇²χ), hyperdiffusion.jl:524-532, into Tlim = Yₜ_lim.c or Yₜ.c; the same arithmetic as part 1 on H[4 + k],
 // which replaced the row-layout kernel k5_tracer_c, 21.8 µs per tracer).  One launch for all parts: per-part launches with their own
 // register budgets (part 1 fits 64 registers, part 0 80) measured slower (74 vs 65 µs, profiles/r2_k7_exp_c.md).
 template <class FT, int NVC>
 __global__ void __launch_bounds__(LVL_EPB * 64, (sizeof(FT) == 4 ? 2 : 1))
 k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ Tlim = nullptr) {
+         const FT* __restrict__ H, FT* __restrict__ Ytc, FT* __restrict__ Ytf, FT* __restrict__ Tlim = nullptr,
+         const FT* __restrict__ Hw = nullptr) {
   using V = P2<FT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];  // LVL_EPB·16 values: part 2, node values of level 31 for the thread of level 32
   FT (*s_q)[16] = reinterpret_cast<FT (*)[16]>(smem_raw);     // (the two warps of an element)
@@ -80,7 +81,7 @@ k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
   const int vc = v < nv ? v : nv - 1, vm = v > 0 ? v - 1 : 0;
   const FT sc = vlev->sc2i[vc], mc = vlev->mc[vc], mclo = vlev->mc[vm < nv ? vm : nv - 1];
   const FT* hg = hgeo + (size_t)(live ? e : 0) * HG_N * 16;
-  pdl_wait(Yc, H, Ytc, Ytf, Tlim);
+  pdl_wait(Yc, H, Ytc, Ytf, Tlim, Hw);
   const size_t offc = (size_t)(live ? e : 0) * P.ncf * 16 * nv + v;  // (node 0, level v) of component 0
   const int cs = 16 * nv;
   if (part == 0) {  // ∇⁴uₕ = δ_div·wgradₕ(divₕ(∇²u)) − wcurlₕ(curlₕ(∇²u))  (hyperdiffusion.jl:273-276)
@@ -124,7 +125,7 @@ k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
     V rho[4][2], Ls[4][2], g1[4][2], g2[4][2], Q1[4][2], Q2[4][2], b[4][2];
     ld16(rho, Yc + offc, nv, cv, FT(1));
     // component of the scalar: 3 = ρe_tot (part 1), 2 = ∇²u₃ (part 2), first passive tracer + k (part 3 + k; a moist context keeps
-    // component 4 for the active ρq_tot, served by k_moist_c)
+    // component 4 for the active ρq_tot, whose water terms are in part 1)
     const int comp = part == 1 ? 3 : part == 2 ? 2 : 4 + (P.moist ? 1 : 0) + (part - 3);
     ld16(Ls, H + offc + comp * cs, nv, cv, FT(0));
     deta16<FT, 0>(Ls, g2);
@@ -146,6 +147,51 @@ k7_exp_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vl
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int p = 0; p < 2; ++p) old3[j][p] = old3[j][p] - ((b[j][p] * sc) * HG16(HG_RJ2, j, p)) * P.nu4s;
+      if (part == 1 && P.moist) {
+        // water part of the apply for a moist (0M) context, on the DSSed ∇²q_tot_eff = H[4] (this replaced the row-layout kernel k_moist_c):
+        //   d = ν₄ₛ wdivₕ(ρ gradₕ(∇²q_tot_eff)):  ρq_totₜ −= d and ρₜ −= d, both in Tlim = Yₜ_lim or Yₜ   (hyperdiffusion.jl:475-484)
+        //   ρe_totₜ −= ν₄ₛ wdivₕ(ρ (h_eff + Φ) gradₕ(∇²q_tot_eff))                                       (:293-307); Hw = ρ(h_eff + Φ) from k5_exp_a
+        V Lq[4][2], rh[4][2], d[4][2];
+        ld16(Lq, H + offc + 4 * cs, nv, cv, FT(0));
+        ld16(rh, Hw + ((size_t)(live ? e : 0) * 16 * nv + v), nv, cv, FT(0));
+        deta16<FT, 0>(Lq, g2);
+        dxi16<FT, 0>(Lq, g1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const V w_ = rho[j][p] * HG16(HG_J2, j, p);
+            Q1[j][p] = w_ * fma2(HG16(HG_GI12, j, p), g2[j][p], HG16(HG_GI11, j, p) * g1[j][p]);
+            Q2[j][p] = w_ * fma2(HG16(HG_GI22, j, p), g2[j][p], HG16(HG_GI12, j, p) * g1[j][p]);
+          }
+        div16<FT, 1>(Q1, Q2, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) d[j][p] = ((b[j][p] * sc) * HG16(HG_RJ2, j, p)) * P.nu4s;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // ρ (component 0) and ρq_tot (component 4)
+          V o_[4][2];
+          FT* tl = Tlim + offc + (k ? 4 : 0) * cs;
+          ld16(o_, tl, nv, cv, FT(0));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { o_[j][0] = o_[j][0] - d[j][0]; o_[j][1] = o_[j][1] - d[j][1]; }
+          if (cv) st16(o_, tl, nv);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const V w_ = rh[j][p] * HG16(HG_J2, j, p);
+            Q1[j][p] = w_ * fma2(HG16(HG_GI12, j, p), g2[j][p], HG16(HG_GI11, j, p) * g1[j][p]);
+            Q2[j][p] = w_ * fma2(HG16(HG_GI22, j, p), g2[j][p], HG16(HG_GI12, j, p) * g1[j][p]);
+          }
+        div16<FT, 1>(Q1, Q2, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int p = 0; p < 2; ++p) old3[j][p] = old3[j][p] - ((b[j][p] * sc) * HG16(HG_RJ2, j, p)) * P.nu4s;
+      }
       if (cv) st16(old3, tgt, nv);
     } else {  // Yₜ.f.u₃ −= ν₄ᵥ ᶠwinterp(ᶜJ ρ, C3(∇⁴u)): face v from the centres v − 1 and v
       V q[4][2], ql[4][2], rlo[4][2], oldf[4][2];

@@ -421,7 +421,7 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
   FT *s_chi = sx, *s_r = sx + SLAB, *s_fx = sx + 2 * SLAB;
   B200_ROW_PROLOGUE
   ROW_COLUMNS
-  // passive tracers only: in a moist (0M) context component 4 is the active ρq_tot, served by k5_exp_a<…, MOIST> / k_moist_c
+  // passive tracers only: in a moist (0M) context component 4 is the active ρq_tot, served by k5_exp_a<…, MOIST> / part 1 of k7_exp_c
   const int q = 4 + (P.moist ? 1 : 0) + blockIdx.y;
   const FT* gY = Yc + (size_t)e * P.ncf * 16 * nv;
   V rho[2], u1[2], u2[2], rq[2], u3[2], chi[2];
@@ -517,48 +517,6 @@ k5_tracer_a(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__
       st4p(out, gT, nv, j, v);
     }
   }
-}
-
-// Water part of the hyperdiffusion apply for a moist (0M) context, on the DSSed ∇²q_tot_eff = H[4] (same row layout):
-//   d = ν₄ₛ wdivₕ(ρ gradₕ(∇²q_tot_eff)):  ρq_totₜ −= d and ρₜ −= d, both in Yₜ_lim   (hyperdiffusion.jl:475-484)
-//   ρe_totₜ −= ν₄ₛ wdivₕ(ρ (h_eff + Φ) gradₕ(∇²q_tot_eff)) in Yₜ                       (:293-307); Hw = ρ(h_eff + Φ) from k5_exp_a
-// Tlim = Yₜ_lim.c, or Yₜ.c when the caller has no limited part (native stepper without a limiter).
-template <class FT>
-__global__ void __launch_bounds__(CT, (sizeof(FT) == 4 ? 4 : 2))
-k_moist_c(Par<FT> P, const FT* __restrict__ hgeo, const VLev<FT>* __restrict__ vlev, const FT* __restrict__ Yc,
-          const FT* __restrict__ H, const FT* __restrict__ Hw, FT* __restrict__ Ytc, FT* __restrict__ Tlim) {
-  using V = P2<FT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  FT* hg = reinterpret_cast<FT*>(smem_raw);
-  B200_ROW_PROLOGUE
-  ROW_COLUMNS
-  const size_t base = (size_t)e * P.ncf * 16 * nv;
-  V rho[2], Lq[2], rh[2], a[2], g1[2], Q1[2], Q2[2], b[2], old[2];
-  ld4p(rho, Yc + base, nv, j, v, cv, FT(1));
-  ld4p(Lq, H + base + (size_t)4 * 16 * nv, nv, j, v, cv, FT(0));
-  ld4p(rh, Hw + (size_t)e * 16 * nv, nv, j, v, cv, FT(0));
-  __syncthreads();
-  deta4p(Lq, md, vl, a);
-  dxi4p<FT, 0>(Lq, g1);
-  METRIC_FLUX(Q1, Q2, g1, a, rho[p] * HGP(HG_J2, p))
-  div4p<FT, 1>(Q1, Q2, mw, vl, b);
-  V d[2];
-#pragma unroll
-  for (int p = 0; p < 2; ++p) d[p] = ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
-  FT* gl = Tlim + base;
-  ld4p(old, gl, nv, j, v, cv, FT(0));
-  old[0] = old[0] - d[0]; old[1] = old[1] - d[1];
-  if (cv) st4p(old, gl, nv, j, v);
-  ld4p(old, gl + (size_t)4 * 16 * nv, nv, j, v, cv, FT(0));
-  old[0] = old[0] - d[0]; old[1] = old[1] - d[1];
-  if (cv) st4p(old, gl + (size_t)4 * 16 * nv, nv, j, v);
-  METRIC_FLUX(Q1, Q2, g1, a, rh[p] * HGP(HG_J2, p))
-  div4p<FT, 1>(Q1, Q2, mw, vl, b);
-  FT* ge = Ytc + base + (size_t)3 * 16 * nv;
-  ld4p(old, ge, nv, j, v, cv, FT(0));
-#pragma unroll
-  for (int p = 0; p < 2; ++p) old[p] = old[p] - ((b[p] * L.sc) * HGP(HG_RJ2, p)) * P.nu4s;
-  if (cv) st4p(old, ge, nv, j, v);
 }
 
 }  // namespace b200

@@ -65,10 +65,9 @@ extern "C" __attribute__((visibility("default"))) int emu_exp5(int which, int nh
   emu_apply_moist(P, sc[3]);
   const int ntr = P.ncf - 4;
   if (which == 0 && g_moist_on) run_grid(nh, 1, [&] { k5_exp_a<FT, 0, true>(P, hgeo, &V, Yc, Yf, Ytc, Ytf, H, (FT*)g_moist_Hw, Ylc); });
-  // 4 = k_moist_c: water part of the hyperdiffusion apply (reads H[4] and Hw; updates ρe_tot of Ytc and ρ, ρq_tot of Ylc, or of Ytc when Ylc is NULL)
-  else if (which == 4) run_grid(nh, 1, [&] { k_moist_c<FT>(P, hgeo, &V, Yc, H, (const FT*)g_moist_Hw, Ytc, Ylc ? Ylc : Ytc); });
+  // (moist: part 1 of k7_exp_c also applies the water terms — reads H[4] and Hw; updates ρe_tot of Ytc and ρ, ρq_tot of Ylc, or of Ytc when Ylc is NULL)
   else if (which == 0) run_grid(nh, 1, [&] { k5_exp_a<FT, 0>(P, hgeo, &V, Yc, Yf, Ytc, Ytf, H); });
-  else if (which == 1) run_grid((nh + LVL_EPB - 1) / LVL_EPB, 3, [&] { k7_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf); });
+  else if (which == 1) run_grid((nh + LVL_EPB - 1) / LVL_EPB, 3, [&] { k7_exp_c<FT, 0>(P, hgeo, &V, Yc, H, Ytc, Ytf, Ylc ? Ylc : Ytc, (const FT*)g_moist_Hw); });
   // passive tracers (grid = elements × tracers): 2 = k5_tracer_a (Yₜ, Yₜ_lim, ∇²χ → H), 3 = parts 3.. of k7_exp_c (tracer hyperdiffusion → Yₜ_lim)
   else if (which == 2) { if (ntr - g_moist_on > 0) run_grid(nh, ntr - g_moist_on, [&] { k5_tracer_a<FT>(P, hgeo, &V, Yc, Yf, Ytc, Ylc, H); }); }
   else if (ntr - g_moist_on > 0) {  // parts 3.. of k7_exp_c only (run_grid's y index is offset by the three dry parts)

@@ -1,7 +1,7 @@
 // Moist (EquilibriumMicrophysics0M) switch of the CTA emulators: emu_set_moist(mp, Hw) with
 // mp = [R_v, cp_v, cp_l, cp_i, LH_v0, LH_s0, T_triple, press_triple, T_freeze, T_icenuc, pow_icenuc] turns the following calls of this
 // library into moist ones (Par::moist = 1, Par::M filled as capi.cu:make_par does); mp = NULL switches back to dry.  Hw: the
-// ρ(h_eff + Φ) buffer [nh][16][nv] that k5_exp_a<…, MOIST> writes and k_moist_c reads.  Test infrastructure only.
+// ρ(h_eff + Φ) buffer [nh][16][nv] that k5_exp_a<…, MOIST> writes and part 1 of k7_exp_c reads.  Test infrastructure only.
 #pragma once
 static double g_moist_par[11];
 static int g_moist_on = 0;

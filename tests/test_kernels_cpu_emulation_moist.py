@@ -1,6 +1,6 @@
 """The MOIST (EquilibriumMicrophysics0M) instantiations of the product kernels, executed on the CPU by the CTA emulator of tests/emu/
 (see tests/test_kernels_cpu_emulation.py) and compared with the oracle's moist path: k5_imp_stage<…, MOIST> (fused stage and LDIV
-mode), k5_exp_a<…, MOIST>, k5_tracer_a / the tracer parts of k7_exp_c with the active ρq_tot, k_moist_c, and the hook kernels k_cache_imp, k_t_imp2,
+mode), k5_exp_a<…, MOIST>, k5_tracer_a / the tracer parts of k7_exp_c with the active ρq_tot (water terms: part 1 of k7_exp_c), and the hook kernels k_cache_imp, k_t_imp2,
 k_t_post_imp2 in a moist context.  The states carry cloudy points (q_0 raised), so the saturation-adjustment branch runs.
 Test infrastructure only."""
 import ctypes as C
@@ -113,7 +113,7 @@ def test_emulated_moist_implicit_stage_and_ldiv_match_oracle(emu5, upw, rayleigh
 @pytest.mark.parametrize("deep,sponge,ze,dzb,ntr", [(True, True, 12, 400.0, 0), (False, False, 12, 400.0, 1), (True, True, 63, 30.0, 0)])
 def test_emulated_moist_explicit_tendency_kernels_match_oracle(emux, deep, sponge, ze, dzb, ntr):
     """T_exp_T_lim! of a moist context, kernel by kernel: k5_exp_a<MOIST> (+ k5_tracer_a) against the oracle's element-local
-    `_rt_pre` / `_tracer_pre` / `_tracer_laplacians`, then k7_exp_c (incl. its tracer parts) + k_moist_c against `_rt_post` / `_tracer_post`."""
+    `_rt_pre` / `_tracer_pre` / `_tracer_laplacians`, then k7_exp_c (incl. its water terms and tracer parts) against `_rt_post` / `_tracer_post`."""
     P, g, N, o, Yc, Yf, rng = make(deep, sponge, "vanleer_limiter", ze, dzb, ntr, seed=17)
     Yf[..., 0] = 0
     Yf[..., -1] = 0
@@ -156,9 +156,9 @@ def test_emulated_moist_explicit_tendency_kernels_match_oracle(emux, deep, spong
         Hin = np.ascontiguousarray(np.stack(list(L) + list(Lq), axis=1))
         o._rt_post(tc, tf, Yc, L, pc, Lq[0])
         o._tracer_post(lc, Yc, Lq)
-        assert emux.emu_exp5(1, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), None) == 0
+        # k7_exp_c parts 0-2 (part 1 carries the water terms of the moist context: ρ, ρq_tot of Yₜ_lim and the enthalpy flux), then its tracer parts
+        assert emux.emu_exp5(1, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), p(Ylc)) == 0
         assert emux.emu_exp5(3, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), p(Ylc)) == 0
-        assert emux.emu_exp5(4, nh, nv, p(sc), p(vl), p(Dm), p(wq), p(hgeo), p(Yc), p(Yf), p(Ytc), p(Ytf), p(Hin), p(Ylc)) == 0
         for k in range(ncf):
             if np.abs(tc[:, k]).max() > 0:
                 assert rel(Ytc[:, k], tc[:, k]) < 1e-10, ("apply", k, rel(Ytc[:, k], tc[:, k]))
