@@ -267,3 +267,32 @@ def test_julia_glue_is_structurally_complete():
     for cname, jname in (("b200_dims", "Dims"), ("b200_geometry", "GeometryC"), ("b200_topology", "TopologyC"), ("b200_params", "ParamsC"),
                          ("b200_cacheptrs", "CachePtrs")):
         assert c_fields(cname) == jl_fields(jname), (cname, c_fields(cname), jl_fields(jname))
+
+
+def test_bench_measurement_model_matches_the_survey_numbers():
+    """bench.py's host-side pieces (no GPU): the weak series of SURVEY.md §8d.4 (h_elem 30/42/60/85 at N = 1/2/4/8, dt ∝ 1/h_elem), the
+    he30-equivalent SYPD factor (1 at N = 1; value_N/(N·value_1) is then the efficiency normalised by elements per GPU), the byte model
+    54.5 S + 14 H (7.17 GB per dry he30/ze63 step, 8.66 GB with one tracer, 2.04 GB at he16 — the figures of §8d), and the NUMA probe's
+    (node, diagnosis) contract when no GPU is visible."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    hs = {n: bench.workload(n)["h_elem"] for n in (1, 2, 4, 8)}
+    assert hs == {1: 30, 2: 42, 4: 60, 8: 85}
+    for n, h in hs.items():
+        w = bench.workload(n)
+        assert w["z_elem"] == 63 and w["scaling"] == "weak" and w["dt"] == float(round(90.0 * 30 / h))
+        eq = bench.equiv_factor(w, 6 * h * h)
+        assert abs(eq - (90.0 / w["dt"]) * (6 * h * h / 5400.0)) < 1e-12
+    assert bench.equiv_factor(bench.workload(1), 5400) == 1.0
+    assert bench.equiv_factor(bench.workload(8, "strong"), 21600) == 1.0 and bench.workload(8, "strong")["h_elem"] == 60
+    assert abs(bench.model_bytes_per_step(86400, 63) / 1e9 - 7.17) < 0.01
+    assert abs(bench.model_bytes_per_step(86400, 63, k=1) / 1e9 - 8.66) < 0.01
+    assert abs(bench.model_bytes_per_step(24576, 63) / 1e9 - 2.04) < 0.01
+    m = bench.workload(1, "moist")
+    assert m["moist"] and m["ic"] == "MoistBaroclinicWave" and m["h_elem"] == 30
+    node, diag = bench.pin_to_gpu_numa_node(0)
+    assert (node is None or isinstance(node, int)) and isinstance(diag, str) and diag
